@@ -1,0 +1,697 @@
+/**
+ * @file advance.cuh
+ * @brief Blackwell-native neighbour-expansion (advance) kernels with in-kernel output compaction.
+ *
+ * These replace the reference load balancers
+ *   block_mapped_kernel   include/gunrock/framework/operators/advance/block_mapped.hxx:67-191
+ *   merge_path_kernel     include/gunrock/framework/operators/advance/merge_path.hxx:112-280
+ *   thread_mapped lambda  include/gunrock/framework/operators/advance/thread_mapped.hxx:58-81
+ * with the same operator contract (advance.hxx:35-49): `op(src, dst, edge, weight) -> bool` is
+ * called exactly once per (input-frontier occurrence, out-edge); a `true` puts `dst` in the output
+ * frontier.  Differences by design:
+ *   - the output frontier is COMPACT: rejected edges occupy no slot (the reference writes -1 and
+ *     leaves the culling to a second full pass, filter/predicated.hxx:30).  Compaction is done
+ *     in-kernel with warp ballots into a per-warp shared-memory staging buffer that is flushed with
+ *     one global atomicAdd per ~100 vertices;
+ *   - frontier sizes live in device memory, no host round trip between operators;
+ *   - power-law rows are degree-binned: rows >= hub_threshold are deferred to a grid-wide bin whose
+ *     column-index slabs are staged into shared memory with cp.async.bulk (TMA engine) and walked
+ *     by the CTA; rows >= 32 are walked by a warp; short rows are packed by a warp scan;
+ *   - grids are persistent (multiples of the SM count) and fetch work through an atomic cursor.
+ */
+#pragma once
+
+#include <gunrock/b200/ptx.cuh>
+#include <gunrock/b200/runtime.cuh>
+#include <gunrock/b200/scan.cuh>
+
+namespace gunrock {
+namespace b200 {
+
+enum class advance_input_t { vertices, graph };
+enum class advance_output_t { vertices, edges, none };
+
+/// Per-warp staging buffer: ballot-compacted appends, flushed with one global atomic.
+template <int kCap, bool kDegSum>
+struct warp_emitter_t {
+  int* s_buf;  // this warp's kCap ints of shared memory
+  int cnt;     // warp-uniform fill level
+  int* out;
+  int* out_count;
+  int out_capacity;
+  const int* row_offsets;
+  ctrl_t* ctrl;
+
+  __device__ __forceinline__ void init(int* smem, int* out_, int* out_count_, int cap,
+                                       const int* ro, ctrl_t* c) {
+    s_buf = smem;
+    cnt = 0;
+    out = out_;
+    out_count = out_count_;
+    out_capacity = cap;
+    row_offsets = ro;
+    ctrl = c;
+  }
+  /// Must be called by all 32 lanes (converged).
+  __device__ __forceinline__ void push(bool keep, int item) {
+    unsigned m = __ballot_sync(kFull, keep);
+    if (m) {
+      if (keep)
+        s_buf[cnt + __popc(m & lanemask_lt())] = item;
+      cnt += __popc(m);
+      if (cnt > kCap - 32)
+        flush();
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    __syncwarp();
+    if (cnt) {
+      int base = 0;
+      if (lane_id() == 0)
+        base = atomicAdd(out_count, cnt);
+      base = __shfl_sync(kFull, base, 0);
+      if (base + cnt > out_capacity) {  // never write past the frontier buffer; host raises
+        if (lane_id() == 0)
+          ctrl->overflow = 1;
+        cnt = max(0, out_capacity - base);
+      }
+      unsigned long long ds = 0;
+      for (int i = lane_id(); i < cnt; i += 32) {
+        int v = s_buf[i];
+        out[base + i] = v;
+        if (kDegSum)
+          ds += static_cast<unsigned>(row_offsets[v + 1] - row_offsets[v]);
+      }
+      if (kDegSum) {
+        ds = warp_sum(ds);
+        if (lane_id() == 0 && ds)
+          atomicAdd(&ctrl->deg_sum, ds);
+      }
+    }
+    __syncwarp();
+    cnt = 0;
+  }
+};
+
+struct advance_params_t {
+  csr_view_t g;
+  const int* in = nullptr;        // input frontier (null when input is the whole graph)
+  const int* in_count = nullptr;  // device count (null when input is the whole graph)
+  int* out = nullptr;
+  int* out_count = nullptr;
+  int out_capacity = 0;
+  int* hubs = nullptr;  // deferred rows
+  int hub_capacity = 0;
+  ctrl_t* ctrl = nullptr;
+  int hub_threshold = 1 << 30;
+  int tma_ok = 0;                  // column_indices / values are 16-byte aligned
+  const int* tile_rows = nullptr;  // merge_path: first row of every tile
+};
+
+constexpr int kEmitCap = 128;       // ints per warp in the staging buffer
+constexpr int kSmallCap = 32 * 31;  // max packed short-row edges per warp pass
+
+/**
+ * @brief Degree-binned persistent advance ("block_mapped" in the reference's enum).
+ * One warp fetches 32 frontier entries at a time; hubs are deferred, rows >= 32 edges are walked
+ * by the whole warp (coalesced), the rest are packed with a warp scan + shared owner table.
+ */
+template <int kThreads, advance_input_t kIn, advance_output_t kOut, bool kDegSum, bool kWeights,
+          typename Op>
+__global__ void __launch_bounds__(kThreads)
+advance_binned_kernel(advance_params_t p, Op op) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ int s_emit[kWarps][kEmitCap];
+  __shared__ unsigned char s_owner[kWarps][kSmallCap + 32];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int* __restrict__ ro = p.g.row_offsets;
+  const int* __restrict__ ci = p.g.column_indices;
+  const float* __restrict__ vals = p.g.values;
+  const int n = (kIn == advance_input_t::graph) ? p.g.n_vertices : *p.in_count;
+
+  warp_emitter_t<kEmitCap, kDegSum> em;
+  em.init(s_emit[warp], p.out, p.out_count, p.out_capacity, ro, p.ctrl);
+  unsigned long long edges_seen = 0;
+
+  for (;;) {
+    int base = 0;
+    if (lane == 0)
+      base = atomicAdd(&p.ctrl->work, 32);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= n)
+      break;
+    int idx = base + lane;
+    int v = -1;
+    if (idx < n)
+      v = (kIn == advance_input_t::graph) ? idx : p.in[idx];
+    int start = 0, deg = 0;
+    if (v >= 0) {
+      start = ro[v];
+      deg = ro[v + 1] - start;
+    }
+    edges_seen += static_cast<unsigned>(deg);
+    // -- grid bin: defer hubs ------------------------------------------------------------
+    if (deg >= p.hub_threshold) {
+      int slot = atomicAdd(&p.ctrl->hub_count, 1);
+      if (slot < p.hub_capacity) {  // list full (duplicate-heavy frontier): keep it in the warp bin
+        p.hubs[slot] = v;
+        deg = 0;
+      }
+    }
+    // -- warp bin: rows of >= 32 edges, one at a time, coalesced ---------------------------
+    unsigned big = __ballot_sync(kFull, deg >= 32);
+    while (big) {
+      int leader = __ffs(big) - 1;
+      big &= big - 1;
+      int s = __shfl_sync(kFull, start, leader);
+      int d = __shfl_sync(kFull, deg, leader);
+      int u = __shfl_sync(kFull, v, leader);
+      if (lane == leader)
+        deg = 0;
+      for (int off = 0; off < d; off += 32) {
+        int e = s + off + lane;
+        bool keep = false;
+        int nb = -1;
+        if (off + lane < d) {
+          nb = ld_stream(ci + e);
+          float w = (kWeights && vals) ? ld_stream(vals + e) : 1.0f;
+          keep = op(u, nb, e, w);
+        }
+        if (kOut != advance_output_t::none)
+          em.push(keep, kOut == advance_output_t::edges ? e : nb);
+      }
+    }
+    // -- thread bin: short rows packed by a warp scan ---------------------------------------
+    int incl = warp_inclusive_sum(deg);
+    int excl = incl - deg;
+    int total = __shfl_sync(kFull, incl, 31);
+    if (total) {
+      for (int k = 0; k < deg; ++k)
+        s_owner[warp][excl + k] = static_cast<unsigned char>(lane);
+      __syncwarp();
+      for (int r0 = 0; r0 < total; r0 += 32) {
+        int r = r0 + lane;
+        bool valid = r < total;
+        int owner = valid ? s_owner[warp][r] : 0;
+        int s = __shfl_sync(kFull, start, owner);
+        int ex = __shfl_sync(kFull, excl, owner);
+        int u = __shfl_sync(kFull, v, owner);
+        bool keep = false;
+        int nb = -1;
+        int e = s + (r - ex);
+        if (valid) {
+          nb = ld_stream(ci + e);
+          float w = (kWeights && vals) ? ld_stream(vals + e) : 1.0f;
+          keep = op(u, nb, e, w);
+        }
+        if (kOut != advance_output_t::none)
+          em.push(keep, kOut == advance_output_t::edges ? e : nb);
+      }
+      __syncwarp();
+    }
+  }
+  if (kOut != advance_output_t::none)
+    em.flush();
+  edges_seen = warp_sum(edges_seen);
+  if (lane == 0 && edges_seen)
+    atomicAdd(&p.ctrl->edges, edges_seen);
+}
+
+/**
+ * @brief Grid bin: every deferred hub row is cut into kChunk-edge slabs; slabs are dealt
+ * round-robin to a persistent grid; each slab is staged into shared memory by ONE thread issuing
+ * a cp.async.bulk (TMA engine, double buffered on two mbarriers) and then walked by the CTA.
+ * When the CSR arrays are not 16-byte aligned (p.tma_ok == 0) the slab is read with plain
+ * coalesced loads instead.
+ */
+template <int kThreads, int kChunk, advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
+__global__ void __launch_bounds__(kThreads)
+advance_hub_kernel(advance_params_t p, Op op) {
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kBatch = 512;        // hub descriptors resident in shared memory at once
+  constexpr int kSlab = kChunk + 4;  // +4: slabs start at a 16-byte aligned column index
+  static_assert(kChunk % 4 == 0, "slab size must keep 16-byte granularity");
+  __shared__ int s_emit[kWarps][kEmitCap];
+  __shared__ int s_start[kBatch];
+  __shared__ int s_end[kBatch];
+  __shared__ int s_vertex[kBatch];
+  __shared__ int s_prefix[kBatch + 1];
+  __shared__ int s_scan[kWarps];
+  __shared__ __align__(16) int s_idx[2][kSlab];
+  __shared__ __align__(16) float s_val[kWeights ? 2 : 1][kWeights ? kSlab : 4];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int* __restrict__ ro = p.g.row_offsets;
+  const int* __restrict__ ci = p.g.column_indices;
+  const float* __restrict__ vals = p.g.values;
+  const bool use_vals = kWeights && vals != nullptr;
+  const bool tma = p.tma_ok != 0;
+  const int n_hubs = min(p.ctrl->hub_count, p.hub_capacity);
+  if (n_hubs == 0)
+    return;
+
+  warp_emitter_t<kEmitCap, kDegSum> em;
+  em.init(s_emit[warp], p.out, p.out_count, p.out_capacity, ro, p.ctrl);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned phase_bits = 0;
+
+  // owner hub of slab g inside the resident batch: largest h with s_prefix[h] <= g
+  auto find_hub = [&](int g, int nb) {
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (s_prefix[mid] <= g)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    return lo;
+  };
+  auto issue = [&](int g, int nb, int buf) {
+    int h = find_hub(g, nb);
+    int e0 = s_start[h] + (g - s_prefix[h]) * kChunk;
+    int cnt = min(kChunk, s_end[h] - e0);
+    int a0 = e0 & ~3;
+    int a1 = (e0 + cnt + 3) & ~3;
+    uint32_t bytes = static_cast<uint32_t>(a1 - a0) * 4u;
+    mbar_expect_tx(&s_bar[buf], use_vals ? 2 * bytes : bytes);
+    bulk_g2s(&s_idx[buf][0], ci + a0, bytes, &s_bar[buf]);
+    if (use_vals)
+      bulk_g2s(&s_val[kWeights ? buf : 0][0], vals + a0, bytes, &s_bar[buf]);
+  };
+
+  int rot = 0;  // slabs dealt by earlier batches: keeps the round-robin deal balanced
+  for (int b0 = 0; b0 < n_hubs; b0 += kBatch) {
+    const int nb = min(kBatch, n_hubs - b0);
+    // descriptors + exclusive slab-count prefix of this batch
+    int carry = 0;
+    for (int i0 = 0; i0 < nb; i0 += kThreads) {
+      int i = i0 + threadIdx.x;
+      int chunks = 0;
+      if (i < nb) {
+        int v = p.hubs[b0 + i];
+        int s = ro[v], e = ro[v + 1];
+        s_start[i] = s;
+        s_end[i] = e;
+        s_vertex[i] = v;
+        chunks = (e - s + kChunk - 1) / kChunk;
+      }
+      int incl = warp_inclusive_sum(chunks);
+      if (lane == 31)
+        s_scan[warp] = incl;
+      __syncthreads();
+      int woff = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        int x = s_scan[w];
+        if (w < warp)
+          woff += x;
+        tot += x;
+      }
+      if (i < nb)
+        s_prefix[i] = carry + woff + incl - chunks;
+      carry += tot;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0)
+      s_prefix[nb] = carry;
+    __syncthreads();
+    const int total = carry;
+
+    int g = (blockIdx.x + gridDim.x - (rot % gridDim.x)) % gridDim.x;
+    if (tma && g < total && threadIdx.x == 0)
+      issue(g, nb, 0);
+    int buf = 0;
+    for (; g < total; g += gridDim.x) {
+      int gn = g + gridDim.x;
+      if (tma && gn < total && threadIdx.x == 0)
+        issue(gn, nb, buf ^ 1);
+      const int h = find_hub(g, nb);
+      const int u = s_vertex[h];
+      const int e0 = s_start[h] + (g - s_prefix[h]) * kChunk;
+      const int cnt = min(kChunk, s_end[h] - e0);
+      const int a0 = e0 & ~3;
+      if (tma) {
+        mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
+        phase_bits ^= 1u << buf;
+      }
+      for (int i0 = 0; i0 < cnt; i0 += kThreads) {
+        int i = i0 + threadIdx.x;
+        bool keep = false;
+        int nbv = -1;
+        int e = e0 + i;
+        if (i < cnt) {
+          float w = 1.0f;
+          if (tma) {
+            nbv = s_idx[buf][e - a0];
+            if (use_vals)
+              w = s_val[kWeights ? buf : 0][e - a0];
+          } else {
+            nbv = ld_stream(ci + e);
+            if (use_vals)
+              w = ld_stream(vals + e);
+          }
+          keep = op(u, nbv, e, w);
+        }
+        if (kOut != advance_output_t::none)
+          em.push(keep, kOut == advance_output_t::edges ? e : nbv);
+      }
+      __syncthreads();  // all reads of s_idx[buf] retire before it is refilled
+      buf ^= 1;
+    }
+    rot += total;
+    __syncthreads();
+  }
+  if (kOut != advance_output_t::none)
+    em.flush();
+}
+
+/// One thread per frontier entry, serial walk ("thread_mapped", thread_mapped.hxx:58-81).
+template <int kThreads, advance_input_t kIn, advance_output_t kOut, bool kDegSum, bool kWeights,
+          typename Op>
+__global__ void __launch_bounds__(kThreads)
+advance_thread_mapped_kernel(advance_params_t p, Op op) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ int s_emit[kWarps][kEmitCap];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int* __restrict__ ro = p.g.row_offsets;
+  const int* __restrict__ ci = p.g.column_indices;
+  const float* __restrict__ vals = p.g.values;
+  const int n = (kIn == advance_input_t::graph) ? p.g.n_vertices : *p.in_count;
+  warp_emitter_t<kEmitCap, kDegSum> em;
+  em.init(s_emit[warp], p.out, p.out_count, p.out_capacity, ro, p.ctrl);
+  unsigned long long edges_seen = 0;
+  for (;;) {
+    int base = 0;
+    if (lane == 0)
+      base = atomicAdd(&p.ctrl->work, 32);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= n)
+      break;
+    int idx = base + lane;
+    int v = -1;
+    if (idx < n)
+      v = (kIn == advance_input_t::graph) ? idx : p.in[idx];
+    int start = 0, deg = 0;
+    if (v >= 0) {
+      start = ro[v];
+      deg = ro[v + 1] - start;
+    }
+    edges_seen += static_cast<unsigned>(deg);
+    int maxdeg = deg;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+      maxdeg = max(maxdeg, __shfl_xor_sync(kFull, maxdeg, d));
+    for (int k = 0; k < maxdeg; ++k) {
+      bool keep = false;
+      int nb = -1;
+      int e = start + k;
+      if (k < deg) {
+        nb = ci[e];
+        float w = (kWeights && vals) ? vals[e] : 1.0f;
+        keep = op(v, nb, e, w);
+      }
+      if (kOut != advance_output_t::none)
+        em.push(keep, kOut == advance_output_t::edges ? e : nb);
+    }
+  }
+  if (kOut != advance_output_t::none)
+    em.flush();
+  edges_seen = warp_sum(edges_seen);
+  if (lane == 0 && edges_seen)
+    atomicAdd(&p.ctrl->edges, edges_seen);
+}
+
+/// merge_path partition: tile t starts in row tile_rows[t] = max{ i : scanned[i] <= t*kTile }.
+/// One thread per tile, so the log2(n) dependent loads of each search overlap across tiles.
+template <int kTile>
+__global__ void merge_path_partition_kernel(const int* __restrict__ scanned,
+                                            const int* __restrict__ n_ptr,
+                                            int n_fixed,
+                                            int* __restrict__ tile_rows) {
+  const int n = n_ptr ? *n_ptr : n_fixed;
+  if (n == 0)
+    return;
+  const int total = scanned[n];
+  const int ntiles = (total + kTile - 1) / kTile;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += gridDim.x * blockDim.x) {
+    long long r = static_cast<long long>(t) * kTile;
+    int row;
+    if (r >= total) {
+      row = n;
+    } else {
+      int lo = 0, hi = n;  // scanned[lo] <= r < scanned[hi]
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (scanned[mid] <= r)
+          lo = mid;
+        else
+          hi = mid;
+      }
+      row = lo;
+    }
+    tile_rows[t] = row;
+  }
+}
+
+/**
+ * @brief Edge-balanced tiles over the degree scan of the frontier ("merge_path").
+ * scanned[i] = exclusive prefix of deg(frontier[i]), scanned[n] = total (device resident).
+ * A tile is kTile consecutive edge ranks.  The CTA stages the non-empty rows that overlap the
+ * tile (first rank, CSR base, vertex) in shared memory; each warp then walks 32 ranks at a time:
+ * one warp-uniform search gives the row window, lanes finish with a <= 5-step local search.
+ * Column loads are coalesced within rows; every tile costs the same number of edges whatever
+ * the degree skew.
+ */
+template <int kThreads, int kTile, advance_input_t kIn, advance_output_t kOut, bool kDegSum,
+          bool kWeights, typename Op>
+__global__ void __launch_bounds__(kThreads)
+advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, Op op) {
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kRows = kTile + 2;  // kTile edges overlap at most kTile non-empty rows (+ sentinel)
+  __shared__ int s_emit[kWarps][kEmitCap];
+  __shared__ int s_rank[kRows];  // first global rank of each staged row
+  __shared__ int s_base[kRows];  // CSR offset of the row's first edge
+  __shared__ int s_vert[kRows];
+  __shared__ int s_wcount[kWarps];
+  __shared__ int s_nrows;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int* __restrict__ ro = p.g.row_offsets;
+  const int* __restrict__ ci = p.g.column_indices;
+  const float* __restrict__ vals = p.g.values;
+  const int n = (kIn == advance_input_t::graph) ? p.g.n_vertices : *p.in_count;
+  if (n == 0)
+    return;
+  const int total = scanned[n];
+  const int ntiles = (total + kTile - 1) / kTile;
+  warp_emitter_t<kEmitCap, kDegSum> em;
+  em.init(s_emit[warp], p.out, p.out_count, p.out_capacity, ro, p.ctrl);
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r_begin = tile * kTile;
+    const int r_end = min(total, r_begin + kTile);
+    const int row0 = p.tile_rows[tile];
+    const int row1 = min(n - 1, p.tile_rows[tile + 1]);  // last row that can overlap the tile
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s_nrows = 0;
+    __syncthreads();
+    for (int i0 = row0; i0 <= row1; i0 += kThreads) {
+      int i = i0 + threadIdx.x;
+      int sc = 0;
+      bool live = false;
+      if (i <= row1) {
+        sc = scanned[i];
+        int sc_next = scanned[i + 1];
+        live = sc_next > sc && sc < r_end && sc_next > r_begin;
+      }
+      unsigned m = __ballot_sync(kFull, live);
+      if (lane == 0)
+        s_wcount[warp] = __popc(m);
+      __syncthreads();
+      int off = s_nrows;
+      for (int w = 0; w < warp; ++w)
+        off += s_wcount[w];
+      if (live) {
+        int slot = off + __popc(m & lanemask_lt());
+        int v = (kIn == advance_input_t::graph) ? i : p.in[i];
+        s_rank[slot] = sc;
+        s_base[slot] = ro[v];
+        s_vert[slot] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int add = 0;
+        for (int w = 0; w < kWarps; ++w)
+          add += s_wcount[w];
+        s_nrows += add;
+      }
+      __syncthreads();
+    }
+    const int nrows = s_nrows;
+    if (threadIdx.x == 0)
+      s_rank[nrows] = r_end;  // sentinel
+    __syncthreads();
+    for (int r0 = r_begin + warp * 32; r0 < r_end; r0 += kThreads) {
+      int a = 0, b = nrows;  // warp-uniform: last staged row with s_rank <= r0
+      while (b - a > 1) {
+        int mid = (a + b) >> 1;
+        if (s_rank[mid] <= r0)
+          a = mid;
+        else
+          b = mid;
+      }
+      int r = r0 + lane;
+      bool valid = r < r_end;
+      bool keep = false;
+      int nb = -1, e = 0;
+      if (valid) {
+        int c = a, d = min(nrows, a + 33);  // at most 32 row starts fall inside 32 ranks
+        while (d - c > 1) {
+          int mid = (c + d) >> 1;
+          if (s_rank[mid] <= r)
+            c = mid;
+          else
+            d = mid;
+        }
+        int u = s_vert[c];
+        e = s_base[c] + (r - s_rank[c]);
+        nb = ld_stream(ci + e);
+        float w = (kWeights && vals) ? ld_stream(vals + e) : 1.0f;
+        keep = op(u, nb, e, w);
+      }
+      if (kOut != advance_output_t::none)
+        em.push(keep, kOut == advance_output_t::edges ? e : nb);
+    }
+  }
+  if (kOut != advance_output_t::none)
+    em.flush();
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&p.ctrl->edges, static_cast<unsigned long long>(total));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host launchers
+// ---------------------------------------------------------------------------------------------
+enum class lb_t { thread_mapped, block_mapped, merge_path };
+
+struct advance_launch_t {
+  lb_t lb = lb_t::block_mapped;
+  int hub_threshold = 4096;  // rows >= this go to the grid (TMA slab) bin; block_mapped only
+  int ctas_per_sm = 4;
+};
+
+__global__ void place_scan_total_kernel(int* scanned, const int* n_ptr, int n_fixed,
+                                        const int* total) {
+  int n = n_ptr ? *n_ptr : n_fixed;
+  scanned[n] = *total;
+}
+
+/// Degree scan of the frontier for merge_path (replaces helpers.hxx:41-111): scanned[0..n].
+inline const int* frontier_degree_scan(workspace_t& ws,
+                                       const csr_view_t& g,
+                                       const int* in,
+                                       const int* in_count,
+                                       int n_upper_bound) {
+  int* scanned = ws.scanned.ensure(static_cast<size_t>(n_upper_bound) + 2);
+  const int* ro = g.row_offsets;
+  auto value = [=] __device__(int i) -> int {
+    int v = in[i];
+    return v >= 0 ? ro[v + 1] - ro[v] : 0;
+  };
+  auto emit = [=] __device__(int i, int excl, int) { scanned[i] = excl; };
+  int* total_slot = scanned + n_upper_bound + 1;
+  lookback_scan(ws, in_count, 0, n_upper_bound, value, emit, total_slot);
+  place_scan_total_kernel<<<1, 1, 0, ws.stream>>>(scanned, in_count, 0, total_slot);
+  ws.launches += 1;
+  return scanned;
+}
+
+inline bool aligned16(const void* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+/**
+ * @brief Launch one advance.  `in == nullptr` means the whole graph is the input frontier.
+ * `in_upper_bound` bounds *in_count (buffer sizing only).  `ctrl_out` (optional) returns the
+ * control block holding deg_sum / edges / overflow for this launch.
+ */
+template <advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
+inline void launch_advance(workspace_t& ws,
+                           const csr_view_t& g,
+                           const int* in,
+                           const int* in_count,
+                           int in_upper_bound,
+                           int* out,
+                           int* out_count,
+                           int out_capacity,
+                           Op op,
+                           const advance_launch_t& cfg,
+                           ctrl_t** ctrl_out = nullptr) {
+  constexpr int kThreads = 256;
+  constexpr int kTile = 2048;
+  const int sms = device_info_t::get().sm_count;
+  advance_params_t p;
+  p.g = g;
+  p.in = in;
+  p.in_count = in_count;
+  p.out = out;
+  p.out_count = out_count;
+  p.out_capacity = out_capacity;
+  const int grid = sms * cfg.ctas_per_sm;
+  const bool graph_in = (in == nullptr);
+  if (cfg.lb == lb_t::thread_mapped) {
+    p.ctrl = ws.next_ctrl();
+    if (graph_in)
+      advance_thread_mapped_kernel<kThreads, advance_input_t::graph, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, 0, ws.stream>>>(p, op);
+    else
+      advance_thread_mapped_kernel<kThreads, advance_input_t::vertices, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, 0, ws.stream>>>(p, op);
+  } else if (cfg.lb == lb_t::merge_path) {
+    // the CSR offsets ARE the degree scan when the whole graph is the frontier
+    const int* scanned =
+        graph_in ? g.row_offsets : frontier_degree_scan(ws, g, in, in_count, in_upper_bound);
+    // ranks are int32 (as in the reference, merge_path.hxx:325-327), so 2^31/kTile tiles bound
+    // every possible frontier, duplicates included.
+    int* tile_rows = ws.tile_rows.ensure((static_cast<size_t>(1) << 31) / kTile + 4);
+    merge_path_partition_kernel<kTile><<<sms, 256, 0, ws.stream>>>(scanned, in_count, g.n_vertices,
+                                                                   tile_rows);
+    p.tile_rows = tile_rows;
+    p.ctrl = ws.next_ctrl();
+    if (graph_in)
+      advance_merge_path_kernel<kThreads, kTile, advance_input_t::graph, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
+    else
+      advance_merge_path_kernel<kThreads, kTile, advance_input_t::vertices, kOut, kDegSum,
+                                kWeights><<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
+  } else {
+    p.ctrl = ws.next_ctrl();
+    p.hub_threshold = cfg.hub_threshold < 32 ? 32 : cfg.hub_threshold;
+    p.hub_capacity = g.n_edges / p.hub_threshold + 1024;
+    p.hubs = ws.hubs.ensure(static_cast<size_t>(p.hub_capacity));
+    p.tma_ok = aligned16(g.column_indices) && (!kWeights || !g.values || aligned16(g.values));
+    if (graph_in)
+      advance_binned_kernel<kThreads, advance_input_t::graph, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, 0, ws.stream>>>(p, op);
+    else
+      advance_binned_kernel<kThreads, advance_input_t::vertices, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, 0, ws.stream>>>(p, op);
+    advance_hub_kernel<kThreads, 2048, kOut, kDegSum, kWeights>
+        <<<sms * 2, kThreads, 0, ws.stream>>>(p, op);
+  }
+  ws.launches += (cfg.lb == lb_t::thread_mapped) ? 1 : 2;
+  if (ctrl_out)
+    *ctrl_out = p.ctrl;
+  B2G_CHECK(cudaGetLastError());
+}
+
+}  // namespace b200
+}  // namespace gunrock

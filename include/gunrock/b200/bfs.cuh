@@ -1,0 +1,363 @@
+/**
+ * @file bfs.cuh
+ * @brief Fused level-synchronous BFS enactor for B200: bitmap visited set, compacting top-down
+ * (push) advance, bottom-up (pull) sweep and the Beamer direction switch.
+ *
+ * Path replaced: gunrock::bfs::enactor_t::loop + enactor_t::enact
+ *   include/gunrock/algorithms/bfs.hxx:93-147, include/gunrock/framework/enactor.hxx:243-288.
+ * Result contract kept (bfs.hxx:59-69, examples/algorithms/bfs/bfs_cpu.hxx:32-63):
+ *   distances[v] = BFS depth, INT_MAX when unreachable; predecessors untouched.
+ * The reference's per-edge `atomicMin(&distances[n], iter+1)` (bfs.hxx:125-127) is replaced by a
+ * test-and-set on a V-bit visited map that stays L2 resident (8 MiB at scale 26): edges into
+ * already-visited vertices cost one cached 4-byte read and no atomic.  Depths are identical
+ * because both are level-synchronous: a vertex is claimed in the first level that reaches it.
+ * The direction-optimised variant (advance_direction_t::optimized is a dead parameter in the
+ * reference) is new design: Beamer et al.'s alpha/beta switch.
+ */
+#pragma once
+
+#include <climits>
+#include <vector>
+
+#include <gunrock/b200/advance.cuh>
+
+namespace gunrock {
+namespace b200 {
+
+/// Top-down edge functor: claim `dst` on the visited bitmap, label it, keep it.
+struct bfs_claim_op {
+  unsigned* visited;
+  int* dist;
+  int next_level;
+  __device__ __forceinline__ bool operator()(int, int dst, int, float) const {
+    if (!bitmap_test_and_set(visited, dst))
+      return false;
+    dist[dst] = next_level;
+    return true;
+  }
+};
+
+/// The reference's own functor (bfs.hxx:105-128), kept selectable for like-for-like runs.
+struct bfs_atomic_min_op {
+  int* dist;
+  int next_level;
+  __device__ __forceinline__ bool operator()(int, int dst, int, float) const {
+    int old = atomicMin(dist + dst, next_level);
+    return next_level < old;
+  }
+};
+
+__global__ void bfs_reset_kernel(int* dist, unsigned* visited, unsigned* fbm, int n_vertices,
+                                 int source, int* q0, int* counts) {
+  const int words = (n_vertices + 31) / 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vertices;
+       i += gridDim.x * blockDim.x) {
+    dist[i] = (i == source) ? 0 : INT_MAX;
+    if (i < words) {
+      unsigned bit = (i == (source >> 5)) ? (1u << (source & 31)) : 0u;
+      visited[i] = bit;
+      fbm[i] = 0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    q0[0] = source;
+    counts[0] = 1;
+    counts[1] = 0;
+  }
+}
+
+__global__ void queue_to_bitmap_kernel(const int* __restrict__ q, const int* __restrict__ count,
+                                       unsigned* __restrict__ bm) {
+  const int n = *count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int v = q[i];
+    atomicOr(bm + (v >> 5), 1u << (v & 31));
+  }
+}
+
+/// Enumerate set bits into a queue (order is irrelevant to BFS; one atomic per warp pass).
+__global__ void bitmap_to_queue_kernel(const unsigned* __restrict__ bm, int words, int* q,
+                                       int* count) {
+  const int lane = lane_id();
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int w0 = gw * 32; w0 < words; w0 += warps * 32) {
+    int wi = w0 + lane;
+    unsigned w = wi < words ? bm[wi] : 0u;
+    int c = __popc(w);
+    int incl = warp_inclusive_sum(c);
+    int total = __shfl_sync(kFull, incl, 31);
+    if (!total)
+      continue;
+    int base = 0;
+    if (lane == 0)
+      base = atomicAdd(count, total);
+    base = __shfl_sync(kFull, base, 0) + incl - c;
+    int vb = wi << 5;
+    while (w) {
+      int b = __ffs(w) - 1;
+      w &= w - 1;
+      q[base++] = vb + b;
+    }
+  }
+}
+
+/**
+ * @brief Bottom-up sweep.  One warp owns one 32-vertex word of the visited map, so the map and
+ * the next-frontier map are updated with plain stores (no atomics).  Each lane walks its
+ * vertex's in-neighbours until one is in the current frontier; lanes still searching after
+ * kSerial steps are finished by the whole warp, 32 neighbours per step.
+ * `in` is the CSC (or the CSR itself for a symmetric graph).
+ */
+template <int kThreads, int kSerial>
+__global__ void __launch_bounds__(kThreads)
+bfs_bottom_up_kernel(csr_view_t in, unsigned* __restrict__ visited,
+                     const unsigned* __restrict__ frontier, unsigned* __restrict__ next, int* dist,
+                     int next_level, ctrl_t* ctrl, int* next_count) {
+  const int lane = lane_id();
+  const int words = (in.n_vertices + 31) / 32;
+  const int warps = (gridDim.x * kThreads) >> 5;
+  const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const int* __restrict__ ro = in.row_offsets;
+  const int* __restrict__ ci = in.column_indices;
+  unsigned long long scanned = 0, found_deg = 0;
+  int found_cnt = 0;
+  for (int wi = gw; wi < words; wi += warps) {
+    const unsigned vis = visited[wi];
+    if (vis == 0xffffffffu) {
+      if (lane == 0)
+        next[wi] = 0;
+      continue;
+    }
+    const int v = (wi << 5) + lane;
+    bool searching = v < in.n_vertices && !((vis >> lane) & 1u);
+    int start = 0, end = 0;
+    if (searching) {
+      start = ro[v];
+      end = ro[v + 1];
+    }
+    const int deg = end - start;
+    bool found = false;
+    int e = start;
+    for (int k = 0; k < kSerial; ++k) {
+      if (searching && e < end) {
+        int u = ci[e++];
+        ++scanned;
+        if (bitmap_test(frontier, u)) {
+          found = true;
+          searching = false;
+        }
+      }
+    }
+    if (e >= end)
+      searching = false;
+    unsigned rest = __ballot_sync(kFull, searching);
+    while (rest) {
+      int leader = __ffs(rest) - 1;
+      rest &= rest - 1;
+      int s = __shfl_sync(kFull, e, leader);
+      int t = __shfl_sync(kFull, end, leader);
+      bool hit = false;
+      for (int off = s; off < t && !hit; off += 32) {
+        int idx = off + lane;
+        bool mine = false;
+        if (idx < t) {
+          ++scanned;
+          mine = bitmap_test(frontier, ci[idx]);
+        }
+        hit = __any_sync(kFull, mine);
+      }
+      if (lane == leader)
+        found = hit;
+    }
+    const unsigned fm = __ballot_sync(kFull, found);
+    if (found) {
+      dist[v] = next_level;
+      found_deg += static_cast<unsigned>(deg);
+    }
+    if (lane == 0) {
+      next[wi] = fm;
+      if (fm)
+        visited[wi] = vis | fm;
+    }
+    found_cnt += found ? 1 : 0;
+  }
+  scanned = warp_sum(scanned);
+  found_deg = warp_sum(found_deg);
+  found_cnt = warp_sum(found_cnt);
+  if (lane == 0) {
+    if (scanned)
+      atomicAdd(&ctrl->edges, scanned);
+    if (found_cnt) {
+      atomicAdd(&ctrl->deg_sum, found_deg);
+      atomicAdd(next_count, found_cnt);
+    }
+  }
+}
+
+struct bfs_level_stat_t {
+  int direction;  // 0 = top-down (push), 1 = bottom-up (pull)
+  int frontier;   // vertices in the input frontier
+  unsigned long long frontier_edges;  // sum of their degrees
+  unsigned long long edges_inspected; // column indices actually read
+};
+
+struct bfs_config_t {
+  advance_launch_t advance;
+  int direction = 0;    // 0 push only, 1 pull only (after the first level), 2 optimised
+  int use_atomic_min_op = 0;  // 1: the reference's per-edge atomicMin functor
+  double alpha = 14.0;  // top-down -> bottom-up when m_f > m_u / alpha
+  double beta = 24.0;   // bottom-up -> top-down when n_f < V / beta
+};
+
+/// Persistent per-graph BFS scratch (allocated once; nothing is allocated inside run()).
+struct bfs_scratch_t {
+  dbuf_t<unsigned> visited, fbm, nbm;
+  dbuf_t<int> q[2];
+  dbuf_t<int> counts;  // [0],[1] queue sizes
+  struct host_fb_t {
+    int count;
+    int overflow;
+    unsigned long long deg_sum;
+    unsigned long long edges;
+  };
+  host_fb_t* h_fb = nullptr;  // pinned
+  ~bfs_scratch_t() {
+    if (h_fb)
+      cudaFreeHost(h_fb);
+  }
+  void ensure(int V) {
+    size_t words = (static_cast<size_t>(V) + 31) / 32 + 4;
+    visited.ensure(words);
+    fbm.ensure(words);
+    nbm.ensure(words);
+    q[0].ensure(static_cast<size_t>(V) + 64);
+    q[1].ensure(static_cast<size_t>(V) + 64);
+    counts.ensure(4);
+    if (!h_fb)
+      B2G_CHECK(cudaMallocHost(&h_fb, sizeof(host_fb_t)));
+  }
+};
+
+__global__ void bfs_feedback_kernel(const int* count, const ctrl_t* a, const ctrl_t* b,
+                                    bfs_scratch_t::host_fb_t* fb) {
+  fb->count = *count;
+  unsigned long long ds = a ? a->deg_sum : 0, ed = a ? a->edges : 0;
+  int ov = a ? a->overflow : 0;
+  if (b) {
+    ds += b->deg_sum;
+    ed += b->edges;
+    ov |= b->overflow;
+  }
+  fb->deg_sum = ds;
+  fb->edges = ed;
+  fb->overflow = ov;
+}
+
+/**
+ * @brief Run BFS from `source` into `dist` (device, V ints).  `out_g` is the CSR, `in_g` the
+ * transpose used by the bottom-up sweep (pass the CSR again for symmetric graphs; pass a view with
+ * row_offsets == nullptr to disable pull).  Returns the number of levels executed.
+ */
+inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
+                   const csr_view_t& in_g, int source, int* dist, const bfs_config_t& cfg,
+                   std::vector<bfs_level_stat_t>* levels = nullptr) {
+  const int V = out_g.n_vertices;
+  const int sms = device_info_t::get().sm_count;
+  sc.ensure(V);
+  cudaStream_t st = ws.stream;
+  const int words = (V + 31) / 32;
+  bfs_reset_kernel<<<sms * 8, 256, 0, st>>>(dist, sc.visited.ptr, sc.fbm.ptr, V, source,
+                                             sc.q[0].ptr, sc.counts.ptr);
+  ws.launches += 1;
+  const bool can_pull =
+      in_g.row_offsets != nullptr && cfg.direction != 0 && !cfg.use_atomic_min_op;
+  int cur = 0;
+  int level = 0;
+  bool bottom_up = false;      // representation of the current frontier: queue (false) / bitmap
+  long long n_f = 1;           // frontier vertices
+  unsigned long long m_f = 0;  // frontier out-degree sum (unknown for the source until probed)
+  unsigned long long explored = 0;
+  {
+    // degree of the source, for the first direction decision
+    int ro2[2];
+    B2G_CHECK(cudaMemcpyAsync(ro2, out_g.row_offsets + source, 2 * sizeof(int),
+                              cudaMemcpyDeviceToHost, st));
+    B2G_CHECK(cudaStreamSynchronize(st));
+    m_f = static_cast<unsigned long long>(ro2[1] - ro2[0]);
+  }
+  unsigned* fbm = sc.fbm.ptr;
+  unsigned* nbm = sc.nbm.ptr;
+  while (n_f > 0) {
+    // ---- choose direction for this level (Beamer et al.) --------------------------------
+    bool want_bottom_up = bottom_up;
+    if (can_pull) {
+      unsigned long long m_u = static_cast<unsigned long long>(out_g.n_edges) - explored;
+      if (cfg.direction == 1)
+        want_bottom_up = level > 0;
+      else if (!bottom_up)
+        want_bottom_up = static_cast<double>(m_f) > static_cast<double>(m_u) / cfg.alpha;
+      else
+        want_bottom_up = !(static_cast<double>(n_f) < static_cast<double>(V) / cfg.beta);
+    }
+    explored += m_f;
+    ctrl_t* ca = nullptr;
+    ctrl_t* cb = nullptr;
+    const int* count_ptr;
+    if (want_bottom_up) {
+      if (!bottom_up) {  // queue -> bitmap
+        B2G_CHECK(cudaMemsetAsync(fbm, 0, sizeof(unsigned) * words, st));
+        queue_to_bitmap_kernel<<<sms * 4, 256, 0, st>>>(sc.q[cur].ptr, sc.counts.ptr + cur, fbm);
+        ws.launches += 1;
+      }
+      ca = ws.next_ctrl();
+      B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 2, 0, sizeof(int), st));
+      bfs_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(in_g, sc.visited.ptr, fbm, nbm, dist,
+                                                           level + 1, ca, sc.counts.ptr + 2);
+      ws.launches += 1;
+      unsigned* t = fbm;
+      fbm = nbm;
+      nbm = t;
+      bottom_up = true;
+      count_ptr = sc.counts.ptr + 2;
+    } else {
+      if (bottom_up) {  // bitmap -> queue
+        B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + cur, 0, sizeof(int), st));
+        bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(fbm, words, sc.q[cur].ptr,
+                                                        sc.counts.ptr + cur);
+        ws.launches += 1;
+        bottom_up = false;
+      }
+      int nxt = cur ^ 1;
+      B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
+      int ub = static_cast<int>(n_f < V ? n_f : V);
+      if (cfg.use_atomic_min_op) {
+        bfs_atomic_min_op op{dist, level + 1};
+        launch_advance<advance_output_t::vertices, true, false>(
+            ws, out_g, sc.q[cur].ptr, sc.counts.ptr + cur, ub, sc.q[nxt].ptr,
+            sc.counts.ptr + nxt, V, op, cfg.advance, &ca);
+      } else {
+        bfs_claim_op op{sc.visited.ptr, dist, level + 1};
+        launch_advance<advance_output_t::vertices, true, false>(
+            ws, out_g, sc.q[cur].ptr, sc.counts.ptr + cur, ub, sc.q[nxt].ptr,
+            sc.counts.ptr + nxt, V, op, cfg.advance, &ca);
+      }
+      cur = nxt;
+      count_ptr = sc.counts.ptr + cur;
+    }
+    bfs_feedback_kernel<<<1, 1, 0, st>>>(count_ptr, ca, cb, sc.h_fb);
+    ws.launches += 1;
+    B2G_CHECK(cudaStreamSynchronize(st));
+    if (sc.h_fb->overflow)
+      throw std::runtime_error("bfs: output frontier overflow");
+    if (levels)
+      levels->push_back({want_bottom_up ? 1 : 0, static_cast<int>(n_f), m_f, sc.h_fb->edges});
+    n_f = sc.h_fb->count;
+    m_f = sc.h_fb->deg_sum;
+    ++level;
+  }
+  return level;
+}
+
+}  // namespace b200
+}  // namespace gunrock

@@ -1,0 +1,139 @@
+/**
+ * @file sssp.cuh
+ * @brief Frontier Bellman-Ford SSSP enactor on the compacting advance kernels.
+ *
+ * Path replaced: gunrock::sssp::enactor_t::loop, include/gunrock/algorithms/sssp.hxx:104-159
+ * (advance with the `shortest_path` lambda :116-130, bypass filter with `remove_completed_paths`
+ * :132-151).  Result contract (sssp.hxx:66-79, examples/algorithms/sssp/sssp_cpu.hxx:36-67):
+ * fp32 distances, FLT_MAX when unreachable, source = 0.
+ *
+ * Bit-exactness: every stored value is fl32(dist[u] + w) for some in-edge, dist only decreases,
+ * and a vertex whose distance dropped is always re-expanded, so the run ends at the least fixed
+ * point of d[v] = min_u fl32(d[u] + w_uv) -- the same array the reference's lazy Dijkstra reaches
+ * (SURVEY.md 8a R16).  The add is a plain fp32 add (no FMA contraction is possible: one operand
+ * pair), the min is an integer atomicMin/atomicMax on the IEEE bit pattern, which is order
+ * preserving for same-sign floats -- cheaper than the reference's CAS loop
+ * (include/gunrock/cuda/atomic_functions.hxx:35-45) and returns the same old value.
+ *
+ * The reference's racy `visited[v] == iteration` dedup (sssp.hxx:134-139) becomes an atomicExch
+ * on the stamp inside the edge functor, so a vertex enters the next frontier exactly once per
+ * iteration and the separate filter pass disappears.
+ */
+#pragma once
+
+#include <cfloat>
+#include <vector>
+
+#include <gunrock/b200/advance.cuh>
+
+namespace gunrock {
+namespace b200 {
+
+/// fp32 atomic min valid for any mix of signs (no NaNs): returns the previous value.
+__device__ __forceinline__ float atomic_min_float(float* addr, float value) {
+  return (value >= 0.0f)
+             ? __int_as_float(atomicMin(reinterpret_cast<int*>(addr), __float_as_int(value)))
+             : __uint_as_float(
+                   atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(value)));
+}
+
+struct sssp_relax_op {
+  float* dist;
+  int* stamp;
+  int iteration;
+  __device__ __forceinline__ bool operator()(int src, int dst, int, float w) const {
+    float nd = __fadd_rn(ld_relaxed(dist + src), w);
+    float old = atomic_min_float(dist + dst, nd);
+    if (!(nd < old))
+      return false;
+    return atomicExch(stamp + dst, iteration) != iteration;
+  }
+};
+
+__global__ void sssp_reset_kernel(float* dist, int* stamp, int n_vertices, int source, int* q0,
+                                  int* counts) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vertices;
+       i += gridDim.x * blockDim.x) {
+    dist[i] = (i == source) ? 0.0f : FLT_MAX;
+    stamp[i] = -1;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    q0[0] = source;
+    counts[0] = 1;
+    counts[1] = 0;
+  }
+}
+
+struct sssp_scratch_t {
+  dbuf_t<int> stamp;
+  dbuf_t<int> q[2];
+  dbuf_t<int> counts;
+  struct host_fb_t {
+    int count;
+    int overflow;
+    unsigned long long edges;
+  };
+  host_fb_t* h_fb = nullptr;
+  ~sssp_scratch_t() {
+    if (h_fb)
+      cudaFreeHost(h_fb);
+  }
+  void ensure(int V) {
+    stamp.ensure(static_cast<size_t>(V) + 64);
+    q[0].ensure(static_cast<size_t>(V) + 64);
+    q[1].ensure(static_cast<size_t>(V) + 64);
+    counts.ensure(4);
+    if (!h_fb)
+      B2G_CHECK(cudaMallocHost(&h_fb, sizeof(host_fb_t)));
+  }
+};
+
+__global__ void sssp_feedback_kernel(const int* count, const ctrl_t* c,
+                                     sssp_scratch_t::host_fb_t* fb) {
+  fb->count = *count;
+  fb->overflow = c->overflow;
+  fb->edges = c->edges;
+}
+
+struct sssp_level_stat_t {
+  int frontier;
+  unsigned long long edges_relaxed;
+};
+
+/// Returns the number of iterations; `dist` is a device array of V floats.
+inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, int source,
+                    float* dist, const advance_launch_t& cfg,
+                    std::vector<sssp_level_stat_t>* levels = nullptr) {
+  const int V = g.n_vertices;
+  const int sms = device_info_t::get().sm_count;
+  sc.ensure(V);
+  cudaStream_t st = ws.stream;
+  sssp_reset_kernel<<<sms * 8, 256, 0, st>>>(dist, sc.stamp.ptr, V, source, sc.q[0].ptr,
+                                              sc.counts.ptr);
+  ws.launches += 1;
+  int cur = 0, iteration = 0;
+  long long n_f = 1;
+  while (n_f > 0) {
+    int nxt = cur ^ 1;
+    B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
+    sssp_relax_op op{dist, sc.stamp.ptr, iteration};
+    ctrl_t* c = nullptr;
+    launch_advance<advance_output_t::vertices, false, true>(
+        ws, g, sc.q[cur].ptr, sc.counts.ptr + cur, static_cast<int>(n_f < V ? n_f : V),
+        sc.q[nxt].ptr, sc.counts.ptr + nxt, V, op, cfg, &c);
+    sssp_feedback_kernel<<<1, 1, 0, st>>>(sc.counts.ptr + nxt, c, sc.h_fb);
+    ws.launches += 1;
+    B2G_CHECK(cudaStreamSynchronize(st));
+    if (sc.h_fb->overflow)
+      throw std::runtime_error("sssp: output frontier overflow");
+    if (levels)
+      levels->push_back({static_cast<int>(n_f), sc.h_fb->edges});
+    n_f = sc.h_fb->count;
+    cur = nxt;
+    ++iteration;
+  }
+  return iteration;
+}
+
+}  // namespace b200
+}  // namespace gunrock

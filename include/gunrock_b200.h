@@ -1,0 +1,169 @@
+/*
+ * gunrock_b200.h -- C ABI of the B200-native frontier engine (libgunrock_b200.so).
+ *
+ * Gunrock itself has no C ABI / plugin boundary: its public surface is the header-only C++17
+ * template API.  That surface is re-implemented source-compatibly under
+ * include/gunrock/ (so examples/algorithms/{bfs,sssp,pr} compile unchanged).  THIS header is the
+ * seam *below* the user lambda: the three named algorithms with their fixed edge functors, the
+ * operators they are built from, and the ingest steps either side -- plain pointers and sizes,
+ * no C++ / torch types -- which is what a language binding (ctypes, cgo, JNI, the reference's own
+ * nanobind module python/src/gunrock/bindings.cu:186-266) would bind.  INTEGRATION.md shows the
+ * reference-side stubs.
+ *
+ * Conventions
+ *   - vertex_t = edge_t = int32, weight_t = float32 (examples/algorithms/bfs/bfs.cu:15-17).
+ *   - every function returns 0 on success, a negative b2g error or a positive cudaError_t;
+ *     b2g_last_error() returns a thread-local message for the last failure.
+ *   - `*_loc` arguments say where a caller buffer lives: B2G_HOST or B2G_DEVICE.
+ *   - a graph handle owns (or views) device-resident CSR arrays; calls on one handle must not
+ *     overlap in time (one stream per handle), matching the reference where run() is synchronous
+ *     (include/gunrock/framework/enactor.hxx:266-288).
+ *   - The library never falls back to a CPU path: without a CUDA device every compute entry
+ *     point fails with B2G_ERR_NO_DEVICE.
+ */
+#ifndef GUNROCK_B200_H_
+#define GUNROCK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)
+
+#define B2G_HOST 0
+#define B2G_DEVICE 1
+
+#define B2G_ERR_INVALID (-1)
+#define B2G_ERR_NO_DEVICE (-2)
+#define B2G_ERR_OVERFLOW (-3)
+#define B2G_ERR_INTERNAL (-4)
+
+/* operators::load_balance_t (include/gunrock/framework/operators/configs.hxx:52-60) */
+#define B2G_LB_THREAD_MAPPED 0
+#define B2G_LB_BLOCK_MAPPED 2
+#define B2G_LB_MERGE_PATH 4
+/* operators::advance_direction_t (configs.hxx:78-82) */
+#define B2G_DIR_FORWARD 0   /* push  */
+#define B2G_DIR_BACKWARD 1  /* pull  */
+#define B2G_DIR_OPTIMIZED 2 /* push/pull switch */
+/* operators::filter_algorithm_t (configs.hxx:92-97) */
+#define B2G_FILTER_REMOVE 0
+#define B2G_FILTER_PREDICATED 1
+#define B2G_FILTER_COMPACT 2
+#define B2G_FILTER_BYPASS 3
+
+typedef struct b2g_graph b2g_graph_t; /* opaque */
+
+/* Mirrors gunrock::options_t (include/gunrock/algorithms/algorithms.hxx:27-72) plus the knobs the
+ * reference hard-codes or lacks.  Zero-initialise then call b2g_options_default(). */
+typedef struct b2g_options {
+  int advance_load_balance; /* B2G_LB_*          default block_mapped (algorithms.hxx:29-30) */
+  int filter_algorithm;     /* B2G_FILTER_*      default predicated   (algorithms.hxx:33-34) */
+  int enable_filter;        /* ignored by the fused enactors: their advance output is compact */
+  int enable_uniquify;
+  int best_effort_uniquify;
+  float uniquify_percent;
+  int advance_direction;    /* B2G_DIR_*         default forward (the reference has push only) */
+  int hub_threshold;        /* rows >= this many edges go to the TMA slab bin (block_mapped) */
+  int ctas_per_sm;          /* persistent grid = #SM x this */
+  int reference_functor;    /* 1: BFS uses the reference's per-edge atomicMin lambda */
+  float do_alpha, do_beta;  /* Beamer switch parameters for B2G_DIR_OPTIMIZED */
+  void* stream;             /* cudaStream_t to run on (NULL = the handle's own stream) */
+} b2g_options_t;
+
+/* Per-run report.  levels[] arrays are filled up to n_levels (capped at B2G_MAX_LEVELS). */
+#define B2G_MAX_LEVELS 4096
+typedef struct b2g_stats {
+  float elapsed_ms;            /* CUDA events around the enactor loop, reference timed region */
+  int iterations;              /* BSP iterations executed (enactor_t::iteration) */
+  int kernel_launches;         /* kernels this library launched inside the timed region */
+  unsigned long long edges_touched; /* column indices read (MTEPS numerator) */
+  unsigned long long vertices_touched;
+  int n_levels;
+  int level_direction[64];     /* first 64 levels: 0 push, 1 pull */
+  int level_frontier[64];
+  unsigned long long level_edges[64];
+} b2g_stats_t;
+
+int b2g_version(void);
+const char* b2g_last_error(void);
+/* Number of visible CUDA devices (0 when there is none); never fails. */
+int b2g_device_count(void);
+void b2g_options_default(b2g_options_t* o);
+
+/* ---- graph ingest -------------------------------------------------------------------------
+ * Replaces format::csr_t<device>::from_coo + graph::build<device>
+ * (include/gunrock/formats/csr.hxx:81-140, include/gunrock/graph/build.hxx:29-36). */
+
+/* CSR arrays (row_offsets[V+1], column_indices[E], values[E] or NULL => 1.0f) are COPIED to the
+ * device from host or device memory. `symmetric`!=0 lets pull-mode reuse the CSR as its own CSC. */
+int b2g_graph_create_csr(int n_vertices, int n_edges, const int* row_offsets,
+                         const int* column_indices, const float* values, int loc, int symmetric,
+                         b2g_graph_t** out);
+/* Non-owning view over caller-owned DEVICE arrays (graph::graph_t semantics, graph/graph.hxx:189-196). */
+int b2g_graph_view_csr(int n_vertices, int n_edges, const int* row_offsets,
+                       const int* column_indices, const float* values, int symmetric,
+                       b2g_graph_t** out);
+/* COO (host, n entries, row-major stable order as csr.hxx:81-140) -> device CSR. */
+int b2g_graph_create_coo(int n_rows, int n_cols, int nnz, const int* I, const int* J,
+                         const float* V, int symmetric, b2g_graph_t** out);
+/* Synthetic workload: counter-based RMAT pairs generated on the device, self loops
+ * dropped, optional mirroring, sorted + deduplicated into CSR.  weights: 0 none, 1 integer 1..63,
+ * 2 non-integer 1+63*u01 (symmetric hash of the endpoints, weight_seed). */
+int b2g_graph_create_rmat(int scale, long long n_pairs, unsigned long long seed, int mirror,
+                          int fold_vertices /* 0 = 2^scale */, int weights,
+                          unsigned long long weight_seed, b2g_graph_t** out);
+/* Build the transpose (CSC) on the device for pull traversal of non-symmetric graphs
+ * (replaces format::csc_t::from_csr, include/gunrock/formats/csc.hxx:62-102). Idempotent. */
+int b2g_graph_build_transpose(b2g_graph_t* g);
+int b2g_graph_destroy(b2g_graph_t* g);
+int b2g_graph_info(const b2g_graph_t* g, int* n_vertices, int* n_edges, int* has_values,
+                   int* symmetric);
+/* Device pointers of the resident CSR (read-only; lifetime = the handle). */
+int b2g_graph_device_ptrs(const b2g_graph_t* g, const int** row_offsets,
+                          const int** column_indices, const float** values);
+/* Copy the resident CSR back (any pointer may be NULL). */
+int b2g_graph_download(const b2g_graph_t* g, int* row_offsets, int* column_indices, float* values);
+/* Vertex of maximum out-degree (lowest id on ties) -- the bench source rule. */
+int b2g_graph_max_degree_vertex(const b2g_graph_t* g, int* vertex, int* degree);
+
+/* ---- algorithms (fused enactors) ----------------------------------------------------------- */
+
+/* gunrock::bfs::run (include/gunrock/algorithms/bfs.hxx:162-182): distances[V] int32, INT_MAX if
+ * unreachable.  distances lives at dist_loc (host => D2H copy inside the call). */
+int b2g_bfs(b2g_graph_t* g, int source, const b2g_options_t* opt, int* distances, int dist_loc,
+            b2g_stats_t* stats);
+/* gunrock::sssp::run (include/gunrock/algorithms/sssp.hxx:176-198): fp32 distances, FLT_MAX if
+ * unreachable.  Requires edge values. */
+int b2g_sssp(b2g_graph_t* g, int source, const b2g_options_t* opt, float* distances, int dist_loc,
+             b2g_stats_t* stats);
+/* gunrock::pr::run (include/gunrock/algorithms/pr.hxx:211-236): alpha damping, tol on
+ * max|p - plast|; max_iter <= 0 = no cap (as the reference). Pull over the transpose. */
+int b2g_pr(b2g_graph_t* g, float alpha, float tol, int max_iter, const b2g_options_t* opt,
+           float* p, int p_loc, b2g_stats_t* stats);
+
+/* ---- operators with the fixed functors (for operator-level parity tests and bindings) ------
+ * Frontiers are DEVICE int32 arrays plus a DEVICE int32 element count.                         */
+
+/* operators::advance::execute (advance/advance.hxx:94-133) with the BFS claim functor: out
+ * receives the newly claimed neighbours, compacted.  `labels` (V ints) gets `label` written for
+ * each claimed vertex, `visited_bitmap` (ceil(V/32) words) is updated. */
+int b2g_advance_bfs(b2g_graph_t* g, const int* in, const int* in_count, int in_capacity, int* out,
+                    int* out_count, int out_capacity, unsigned* visited_bitmap, int* labels,
+                    int label, const b2g_options_t* opt, unsigned long long* edges_touched);
+/* operators::filter::execute (filter/filter.hxx:72-100), predicate "vertex is valid and
+ * keep_mask[vertex] != 0" (keep_mask may be NULL = keep all valid).  alg = B2G_FILTER_*;
+ * bypass keeps the size and writes -1 for rejected entries. */
+int b2g_filter(b2g_graph_t* g, int alg, const int* in, const int* in_count, int in_capacity,
+               int* out, int* out_count, const unsigned char* keep_mask);
+/* operators::uniquify::execute (uniquify/uniquify.hxx:26-94).  best_effort != 0: adjacent
+ * duplicates only (no sort); else exact: the sorted unique set (bitmap enumeration). */
+int b2g_uniquify(b2g_graph_t* g, const int* in, const int* in_count, int in_capacity, int* out,
+                 int* out_count, int best_effort);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUNROCK_B200_H_ */
