@@ -1,0 +1,28 @@
+#!/bin/bash
+# Gates for the drop-in boundary (need /root/reference; binaries land in examples/bin/, git-ignored,
+# and travel to the GPU box with the snapshot):
+#  1. the reference's UNCHANGED example translation units examples/algorithms/{bfs,sssp,pr}/*.cu
+#     compiled against THIS repository's headers            -> bin/{bfs,sssp,pr}
+#  2. the same with -DGUNROCK_B200_OPERATOR_PATH (our algorithm headers on the generic operators
+#     instead of the fused enactors)                        -> bin/{bfs,sssp,pr}_ops
+#  3. the reference's own algorithm headers (algorithms/{bfs,sssp,pr}.hxx) on our framework /
+#     operator headers                                      -> bin/ref_algorithms
+set -e
+ROOT="$(cd "$(dirname "$0")/.." && pwd)"
+REF=${REF:-/root/reference}
+OUT="$ROOT/examples/bin"
+mkdir -p "$OUT"
+FLAGS="-std=c++17 -O3 -lineinfo --extended-lambda --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -I$ROOT/include -diag-suppress 20050"
+pids=()
+for alg in bfs sssp pr; do
+  nvcc $FLAGS -I"$REF/examples/algorithms/$alg" -o "$OUT/$alg" "$REF/examples/algorithms/$alg/$alg.cu" & pids+=($!)
+  nvcc $FLAGS -DGUNROCK_B200_OPERATOR_PATH -I"$REF/examples/algorithms/$alg" -o "$OUT/${alg}_ops" "$REF/examples/algorithms/$alg/$alg.cu" & pids+=($!)
+done
+A="$REF/include/gunrock/algorithms"
+nvcc $FLAGS -I"$REF/examples/algorithms/bfs" -I"$REF/examples/algorithms/sssp" \
+  -DREF_BFS_HXX="\"$A/bfs.hxx\"" -DREF_SSSP_HXX="\"$A/sssp.hxx\"" -DREF_PR_HXX="\"$A/pr.hxx\"" \
+  -o "$OUT/ref_algorithms" "$ROOT/examples/ref_algorithms_driver.cu" & pids+=($!)
+rc=0
+for p in "${pids[@]}"; do wait $p || rc=1; done
+ls -la "$OUT"
+exit $rc

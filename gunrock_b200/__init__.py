@@ -51,7 +51,8 @@ class _Stats(C.Structure):
     _fields_ = [("elapsed_ms", C.c_float), ("iterations", C.c_int), ("kernel_launches", C.c_int),
                 ("edges_touched", C.c_ulonglong), ("vertices_touched", C.c_ulonglong),
                 ("n_levels", C.c_int), ("level_direction", C.c_int * 64),
-                ("level_frontier", C.c_int * 64), ("level_edges", C.c_ulonglong * 64)]
+                ("level_frontier", C.c_int * 64), ("level_edges", C.c_ulonglong * 64),
+                ("level_kernel_ms", C.c_float * 64)]
 
 
 @dataclass
@@ -89,6 +90,7 @@ class stats_t:
     level_direction: list = field(default_factory=list)
     level_frontier: list = field(default_factory=list)
     level_edges: list = field(default_factory=list)
+    level_kernel_ms: list = field(default_factory=list)
 
 
 class GunrockB200Error(RuntimeError):
@@ -174,7 +176,7 @@ def _stats_out(s: _Stats) -> stats_t:
     return stats_t(float(s.elapsed_ms), int(s.iterations), int(s.kernel_launches),
                    int(s.edges_touched), int(s.vertices_touched),
                    list(s.level_direction[:n]), list(s.level_frontier[:n]),
-                   list(s.level_edges[:n]))
+                   list(s.level_edges[:n]), list(s.level_kernel_ms[:n]))
 
 
 class graph_t:

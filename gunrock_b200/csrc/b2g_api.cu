@@ -14,13 +14,12 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include <gunrock/b200/advance.cuh>
 #include <gunrock/b200/bfs.cuh>
 #include <gunrock/b200/filter.cuh>
 #include <gunrock/b200/pr.cuh>
 #include <gunrock/b200/sssp.cuh>
+#include <gunrock/b200/transpose.cuh>
 
 using namespace gunrock::b200;
 
@@ -66,8 +65,7 @@ struct b2g_graph {
   // owned storage (padded so 16-byte TMA slabs may over-read the tail)
   dbuf_t<int> ro, ci;
   dbuf_t<float> vals;
-  dbuf_t<int> t_ro, t_ci;
-  dbuf_t<float> t_vals;
+  transpose_t transpose;
   bool has_vals = false;
   bool has_transpose = false;
   csr_view_t view;    // CSR
@@ -170,8 +168,12 @@ __host__ __device__ inline float edge_weight(unsigned long long seed, int u, int
   unsigned long long h = hash3(seed, lo, hi);
   if (mode == 1)
     return static_cast<float>(1 + static_cast<int>(h % 63ull));
-  float u01 = static_cast<float>(h >> 40) * (1.0f / 16777216.0f);
+  float u01 = static_cast<float>(h >> 40) * (1.0f / 16777216.0f);  // exact: 24-bit integer x 2^-24
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(1.0f, __fmul_rn(63.0f, u01));  // no FMA contraction: must match the host value
+#else
   return 1.0f + 63.0f * u01;
+#endif
 }
 
 constexpr unsigned long long kDropKey = ~0ull;
@@ -209,25 +211,6 @@ __global__ void rmat_keys_kernel(int scale, long long n_pairs, unsigned long lon
   }
 }
 
-__global__ void coo_keys_kernel(int nnz, const int* I, const int* J, unsigned long long* keys) {
-  // stable by (row, original position): key = row << 32 | position
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += gridDim.x * blockDim.x)
-    keys[k] = (static_cast<unsigned long long>(static_cast<unsigned>(I[k])) << 32) |
-              static_cast<unsigned>(k);
-}
-
-/// row_offsets from sorted row ids: rows (prev, cur] start at position i.
-__global__ void offsets_from_sorted_rows_kernel(const int* __restrict__ rows, const int* n_ptr,
-                                                int n_fixed, int n_vertices, int* ro) {
-  const int n = n_ptr ? *n_ptr : n_fixed;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
-    int prev = (i == 0) ? -1 : rows[i - 1];
-    int cur = (i == n) ? n_vertices : rows[i];
-    for (int r = prev + 1; r <= cur; ++r)
-      ro[r] = i;
-  }
-}
-
 __global__ void degree_argmax_kernel(const int* __restrict__ ro, int n, unsigned long long* best) {
   // pack (degree, ~vertex) so the max picks the largest degree, lowest id
   unsigned long long local = 0;
@@ -244,78 +227,12 @@ __global__ void degree_argmax_kernel(const int* __restrict__ ro, int n, unsigned
     atomicMax(best, local);
 }
 
-/// Sort 64-bit keys on the device (ingest only).
-void sort_keys(unsigned long long* keys, unsigned long long* alt, size_t n, int end_bit,
-               cudaStream_t st, unsigned long long** sorted) {
-  cub::DoubleBuffer<unsigned long long> db(keys, alt);
-  size_t temp_bytes = 0;
-  B2G_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, db, static_cast<long long>(n), 0,
-                                           end_bit, st));
-  void* temp = nullptr;
-  B2G_CHECK(cudaMalloc(&temp, temp_bytes ? temp_bytes : 16));
-  cudaError_t e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, db, static_cast<long long>(n), 0,
-                                                 end_bit, st);
-  cudaError_t e2 = cudaStreamSynchronize(st);
-  cudaFree(temp);
-  B2G_CHECK(e);
-  B2G_CHECK(e2);
-  *sorted = db.Current();
-}
-
-/// Transpose a device CSR: key = (col << 32 | edge position) sorted -> stable by source order.
+/// Transpose a device CSR (gunrock/b200/transpose.cuh); cached on the handle.
 void build_transpose(b2g_graph* g) {
   if (g->has_transpose)
     return;
-  const int V = g->n_vertices, E = g->n_edges;
-  cudaStream_t st = g->ws.stream;
-  const int sms = device_info_t::get().sm_count;
-  g->t_ro.ensure(static_cast<size_t>(V) + 1 + 16);
-  g->t_ci.ensure(static_cast<size_t>(E) + 16);
-  if (g->view.values)
-    g->t_vals.ensure(static_cast<size_t>(E) + 16);
-  dbuf_t<unsigned long long> k0, k1;
-  dbuf_t<int> rows;
-  k0.ensure(static_cast<size_t>(E) + 1);
-  k1.ensure(static_cast<size_t>(E) + 1);
-  rows.ensure(static_cast<size_t>(E) + 1);
-  if (E > 0) {
-    coo_keys_kernel<<<sms * 8, 256, 0, st>>>(E, g->view.column_indices, nullptr, k0.ptr);
-    int bits = 32;
-    while (bits < 64 && (1ll << (bits - 32)) < V)
-      ++bits;
-    unsigned long long* sorted = nullptr;
-    sort_keys(k0.ptr, k1.ptr, static_cast<size_t>(E), bits, st, &sorted);
-    const int* ro = g->view.row_offsets;
-    const float* vals = g->view.values;
-    int* t_ci = g->t_ci.ptr;
-    float* t_vals = vals ? g->t_vals.ptr : nullptr;
-    int* rows_p = rows.ptr;
-    // source row of CSR position e: binary search in row_offsets
-    auto fill = [=] __device__(int i) {
-      unsigned long long key = sorted[i];
-      int e = static_cast<int>(static_cast<unsigned>(key));
-      int lo = 0, hi = V;  // ro[lo] <= e < ro[hi]
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (ro[mid] <= e)
-          lo = mid;
-        else
-          hi = mid;
-      }
-      t_ci[i] = lo;
-      if (t_vals)
-        t_vals[i] = vals[e];
-      rows_p[i] = static_cast<int>(key >> 32);
-    };
-    for_each_index<<<sms * 8, 256, 0, st>>>(E, fill);
-  }
-  offsets_from_sorted_rows_kernel<<<sms * 4, 256, 0, st>>>(rows.ptr, nullptr, E, V, g->t_ro.ptr);
-  B2G_CHECK(cudaStreamSynchronize(st));
-  g->t_view.n_vertices = V;
-  g->t_view.n_edges = E;
-  g->t_view.row_offsets = g->t_ro.ptr;
-  g->t_view.column_indices = g->t_ci.ptr;
-  g->t_view.values = g->view.values ? g->t_vals.ptr : nullptr;
+  g->transpose.build(g->ws, g->view);
+  g->t_view = g->transpose.view;
   g->has_transpose = true;
 }
 
@@ -347,12 +264,9 @@ b2g_graph* create_coo_impl(int n_rows, int nnz, const int* I, const int* J, cons
     B2G_CHECK(cudaMemcpyAsync(dJ.ptr, J, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
     if (V)
       B2G_CHECK(cudaMemcpyAsync(dV.ptr, V, sizeof(float) * nnz, cudaMemcpyHostToDevice, st));
-    coo_keys_kernel<<<sms * 8, 256, 0, st>>>(nnz, dI.ptr, dJ.ptr, k0.ptr);
-    int bits = 32;
-    while (bits < 64 && (1ll << (bits - 32)) < n_rows)
-      ++bits;
-    unsigned long long* sorted = nullptr;
-    sort_keys(k0.ptr, k1.ptr, static_cast<size_t>(nnz), bits, st, &sorted);
+    position_keys_kernel<<<sms * 8, 256, 0, st>>>(nnz, dI.ptr, k0.ptr);
+    unsigned long long* sorted =
+        sort_keys_u64(k0.ptr, k1.ptr, static_cast<size_t>(nnz), key_bits_for(n_rows), st);
     int* ci = g->ci.ptr;
     float* vals = g->vals.ptr;
     int* rows_p = rows.ptr;
@@ -367,8 +281,7 @@ b2g_graph* create_coo_impl(int n_rows, int nnz, const int* I, const int* J, cons
     };
     for_each_index<<<sms * 8, 256, 0, st>>>(nnz, fill);
   }
-  offsets_from_sorted_rows_kernel<<<sms * 4, 256, 0, st>>>(rows.ptr, nullptr, nnz, n_rows,
-                                                           g->ro.ptr);
+  offsets_from_sorted_rows_kernel<<<sms * 4, 256, 0, st>>>(rows.ptr, nnz, n_rows, g->ro.ptr);
   B2G_CHECK(cudaStreamSynchronize(st));
   g->set_views();
   return g.release();
@@ -388,8 +301,7 @@ b2g_graph* create_rmat_impl(int scale, long long n_pairs, unsigned long long see
   k0.ensure(n_keys + 1);
   k1.ensure(n_keys + 1);
   rmat_keys_kernel<<<sms * 16, 256, 0, st>>>(scale, n_pairs, seed, mirror, fold_vertices, k0.ptr);
-  unsigned long long* sorted = nullptr;
-  sort_keys(k0.ptr, k1.ptr, n_keys, 64, st, &sorted);
+  unsigned long long* sorted = sort_keys_u64(k0.ptr, k1.ptr, n_keys, 64, st);
   // unique + drop sentinel -> compact (row, col) lists via the look-back select
   dbuf_t<int> rows, count;
   rows.ensure(n_keys + 1);
@@ -420,7 +332,7 @@ b2g_graph* create_rmat_impl(int scale, long long n_pairs, unsigned long long see
   B2G_CHECK(cudaMemcpyAsync(&nnz, count.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
   B2G_CHECK(cudaStreamSynchronize(st));
   g->ro.ensure(static_cast<size_t>(V) + 1 + 16);
-  offsets_from_sorted_rows_kernel<<<sms * 4, 256, 0, st>>>(rows.ptr, nullptr, nnz, V, g->ro.ptr);
+  offsets_from_sorted_rows_kernel<<<sms * 4, 256, 0, st>>>(rows.ptr, nnz, V, g->ro.ptr);
   B2G_CHECK(cudaStreamSynchronize(st));
   g->n_vertices = V;
   g->n_edges = nnz;
@@ -696,6 +608,7 @@ int b2g_bfs(b2g_graph_t* g, int source, const b2g_options_t* opt, int* distances
           stats->level_direction[i] = levels[i].direction;
           stats->level_frontier[i] = levels[i].frontier;
           stats->level_edges[i] = levels[i].edges_inspected;
+          stats->level_kernel_ms[i] = levels[i].kernel_ms;
         }
       }
     }
@@ -736,6 +649,7 @@ int b2g_sssp(b2g_graph_t* g, int source, const b2g_options_t* opt, float* distan
         if (i < 64) {
           stats->level_frontier[i] = levels[i].frontier;
           stats->level_edges[i] = levels[i].edges_relaxed;
+          stats->level_kernel_ms[i] = levels[i].kernel_ms;
         }
       }
     }

@@ -588,7 +588,7 @@ struct advance_launch_t {
   int ctas_per_sm = 4;
 };
 
-__global__ void place_scan_total_kernel(int* scanned, const int* n_ptr, int n_fixed,
+static __global__ void place_scan_total_kernel(int* scanned, const int* n_ptr, int n_fixed,
                                         const int* total) {
   int n = n_ptr ? *n_ptr : n_fixed;
   scanned[n] = *total;

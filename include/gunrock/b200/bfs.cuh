@@ -47,7 +47,7 @@ struct bfs_atomic_min_op {
   }
 };
 
-__global__ void bfs_reset_kernel(int* dist, unsigned* visited, unsigned* fbm, int n_vertices,
+static __global__ void bfs_reset_kernel(int* dist, unsigned* visited, unsigned* fbm, int n_vertices,
                                  int source, int* q0, int* counts) {
   const int words = (n_vertices + 31) / 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vertices;
@@ -66,7 +66,7 @@ __global__ void bfs_reset_kernel(int* dist, unsigned* visited, unsigned* fbm, in
   }
 }
 
-__global__ void queue_to_bitmap_kernel(const int* __restrict__ q, const int* __restrict__ count,
+static __global__ void queue_to_bitmap_kernel(const int* __restrict__ q, const int* __restrict__ count,
                                        unsigned* __restrict__ bm) {
   const int n = *count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -76,7 +76,7 @@ __global__ void queue_to_bitmap_kernel(const int* __restrict__ q, const int* __r
 }
 
 /// Enumerate set bits into a queue (order is irrelevant to BFS; one atomic per warp pass).
-__global__ void bitmap_to_queue_kernel(const unsigned* __restrict__ bm, int words, int* q,
+static __global__ void bitmap_to_queue_kernel(const unsigned* __restrict__ bm, int words, int* q,
                                        int* count) {
   const int lane = lane_id();
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -200,6 +200,7 @@ struct bfs_level_stat_t {
   int frontier;   // vertices in the input frontier
   unsigned long long frontier_edges;  // sum of their degrees
   unsigned long long edges_inspected; // column indices actually read
+  float kernel_ms = 0.0f;             // device time of this level's advance / sweep kernels
 };
 
 struct bfs_config_t {
@@ -222,9 +223,13 @@ struct bfs_scratch_t {
     unsigned long long edges;
   };
   host_fb_t* h_fb = nullptr;  // pinned
+  cudaEvent_t ev[128] = {};   // per-level event pairs (first 64 levels are timed)
   ~bfs_scratch_t() {
     if (h_fb)
       cudaFreeHost(h_fb);
+    for (auto e : ev)
+      if (e)
+        cudaEventDestroy(e);
   }
   void ensure(int V) {
     size_t words = (static_cast<size_t>(V) + 31) / 32 + 4;
@@ -236,10 +241,13 @@ struct bfs_scratch_t {
     counts.ensure(4);
     if (!h_fb)
       B2G_CHECK(cudaMallocHost(&h_fb, sizeof(host_fb_t)));
+    if (!ev[0])
+      for (auto& e : ev)
+        B2G_CHECK(cudaEventCreate(&e));
   }
 };
 
-__global__ void bfs_feedback_kernel(const int* count, const ctrl_t* a, const ctrl_t* b,
+static __global__ void bfs_feedback_kernel(const int* count, const ctrl_t* a, const ctrl_t* b,
                                     bfs_scratch_t::host_fb_t* fb) {
   fb->count = *count;
   unsigned long long ds = a ? a->deg_sum : 0, ed = a ? a->edges : 0;
@@ -301,6 +309,8 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
         want_bottom_up = !(static_cast<double>(n_f) < static_cast<double>(V) / cfg.beta);
     }
     explored += m_f;
+    if (level < 64)
+      B2G_CHECK(cudaEventRecord(sc.ev[2 * level], st));
     ctrl_t* ca = nullptr;
     ctrl_t* cb = nullptr;
     const int* count_ptr;
@@ -345,6 +355,8 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       cur = nxt;
       count_ptr = sc.counts.ptr + cur;
     }
+    if (level < 64)
+      B2G_CHECK(cudaEventRecord(sc.ev[2 * level + 1], st));
     bfs_feedback_kernel<<<1, 1, 0, st>>>(count_ptr, ca, cb, sc.h_fb);
     ws.launches += 1;
     B2G_CHECK(cudaStreamSynchronize(st));
@@ -356,6 +368,9 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
     m_f = sc.h_fb->deg_sum;
     ++level;
   }
+  if (levels)
+    for (int l = 0; l < level && l < 64; ++l)
+      cudaEventElapsedTime(&(*levels)[l].kernel_ms, sc.ev[2 * l], sc.ev[2 * l + 1]);
   return level;
 }
 

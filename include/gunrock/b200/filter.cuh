@@ -85,7 +85,7 @@ inline void launch_unique_adjacent(workspace_t& ws,
   lookback_scan(ws, in_count, 0, in_upper_bound, value, emit, out_count);
 }
 
-__global__ void bitmap_mark_kernel(const int* __restrict__ in,
+static __global__ void bitmap_mark_kernel(const int* __restrict__ in,
                                    const int* __restrict__ in_count,
                                    unsigned* __restrict__ bitmap,
                                    int* __restrict__ has_invalid) {

@@ -48,7 +48,7 @@ struct pr_scratch_t {
 
 /// reset (pr.hxx:65-93): p = (float)(1.0/V), plast = 0, iweights = alpha / rowsum (sequential
 /// fp32 sum of the row's weights, as get_weight does) or 0.
-__global__ void pr_reset_kernel(csr_view_t g, float alpha, float* p, float* plast, float* iw) {
+static __global__ void pr_reset_kernel(csr_view_t g, float alpha, float* p, float* plast, float* iw) {
   const int V = g.n_vertices;
   const float p0 = static_cast<float>(1.0 / static_cast<double>(V));
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
@@ -175,7 +175,7 @@ pr_pull_kernel(csr_view_t t, float alpha, const float* __restrict__ c,
     atomicMax(err_bits, __float_as_uint(err));
 }
 
-__global__ void pr_err_feedback_kernel(unsigned* err_bits, float* h_err) {
+static __global__ void pr_err_feedback_kernel(unsigned* err_bits, float* h_err) {
   *h_err = __uint_as_float(*err_bits);
   *err_bits = 0;
 }

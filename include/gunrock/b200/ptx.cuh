@@ -152,14 +152,22 @@ __device__ __forceinline__ void fence_proxy_async() {
 // ---------------------------------------------------------------------------------------------
 // Bitmap helpers (32 vertices per word).
 // ---------------------------------------------------------------------------------------------
+/// L1-cacheable weak load.  Used for the visited / frontier bitmaps: bits only ever go 0 -> 1, so
+/// a stale line can only answer "not set", and every such answer is re-checked by an atomic.
+__device__ __forceinline__ unsigned ld_cached(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+/// Read-only (for the whole kernel) bitmap probe through the non-coherent path.
 __device__ __forceinline__ bool bitmap_test(const unsigned* bm, int v) {
-  return (ld_relaxed(bm + (v >> 5)) >> (v & 31)) & 1u;
+  return (__ldg(bm + (v >> 5)) >> (v & 31)) & 1u;
 }
 /// Returns true iff this call set the bit (i.e. the caller "won" the vertex).
 __device__ __forceinline__ bool bitmap_test_and_set(unsigned* bm, int v) {
   unsigned bit = 1u << (v & 31);
   unsigned* w = bm + (v >> 5);
-  if (ld_relaxed(w) & bit)
+  if (ld_cached(w) & bit)
     return false;
   return !(atomicOr(w, bit) & bit);
 }

@@ -111,9 +111,11 @@ struct workspace_t {
   dbuf_t<int> scanned;                    // degree scan for merge_path
   dbuf_t<int> tile_rows;                  // merge_path tile -> first row
   dbuf_t<unsigned long long> tile_state;  // look-back status words
+  dbuf_t<unsigned> uniq_bitmap;           // exact-uniquify V-bit map (kept zeroed between uses)
   int ctrl_ring = 0;
   unsigned scan_epoch = 0;  // launch epoch of the look-back status words
   int launches = 0;         // kernels launched through this workspace (reported as gpu_launches)
+  unsigned long long edges_accounted = 0;  // host-side sum of ctrl_t::edges folded in so far
   static constexpr int kCtrlRing = 256;
 
   void init(cudaStream_t s) {

@@ -50,7 +50,7 @@ struct sssp_relax_op {
   }
 };
 
-__global__ void sssp_reset_kernel(float* dist, int* stamp, int n_vertices, int source, int* q0,
+static __global__ void sssp_reset_kernel(float* dist, int* stamp, int n_vertices, int source, int* q0,
                                   int* counts) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vertices;
        i += gridDim.x * blockDim.x) {
@@ -74,9 +74,13 @@ struct sssp_scratch_t {
     unsigned long long edges;
   };
   host_fb_t* h_fb = nullptr;
+  cudaEvent_t ev[128] = {};
   ~sssp_scratch_t() {
     if (h_fb)
       cudaFreeHost(h_fb);
+    for (auto e : ev)
+      if (e)
+        cudaEventDestroy(e);
   }
   void ensure(int V) {
     stamp.ensure(static_cast<size_t>(V) + 64);
@@ -85,10 +89,13 @@ struct sssp_scratch_t {
     counts.ensure(4);
     if (!h_fb)
       B2G_CHECK(cudaMallocHost(&h_fb, sizeof(host_fb_t)));
+    if (!ev[0])
+      for (auto& e : ev)
+        B2G_CHECK(cudaEventCreate(&e));
   }
 };
 
-__global__ void sssp_feedback_kernel(const int* count, const ctrl_t* c,
+static __global__ void sssp_feedback_kernel(const int* count, const ctrl_t* c,
                                      sssp_scratch_t::host_fb_t* fb) {
   fb->count = *count;
   fb->overflow = c->overflow;
@@ -98,6 +105,7 @@ __global__ void sssp_feedback_kernel(const int* count, const ctrl_t* c,
 struct sssp_level_stat_t {
   int frontier;
   unsigned long long edges_relaxed;
+  float kernel_ms = 0.0f;
 };
 
 /// Returns the number of iterations; `dist` is a device array of V floats.
@@ -118,9 +126,13 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
     B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
     sssp_relax_op op{dist, sc.stamp.ptr, iteration};
     ctrl_t* c = nullptr;
+    if (iteration < 64)
+      B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration], st));
     launch_advance<advance_output_t::vertices, false, true>(
         ws, g, sc.q[cur].ptr, sc.counts.ptr + cur, static_cast<int>(n_f < V ? n_f : V),
         sc.q[nxt].ptr, sc.counts.ptr + nxt, V, op, cfg, &c);
+    if (iteration < 64)
+      B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration + 1], st));
     sssp_feedback_kernel<<<1, 1, 0, st>>>(sc.counts.ptr + nxt, c, sc.h_fb);
     ws.launches += 1;
     B2G_CHECK(cudaStreamSynchronize(st));
@@ -132,6 +144,9 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
     cur = nxt;
     ++iteration;
   }
+  if (levels)
+    for (int l = 0; l < iteration && l < 64; ++l)
+      cudaEventElapsedTime(&(*levels)[l].kernel_ms, sc.ev[2 * l], sc.ev[2 * l + 1]);
   return iteration;
 }
 

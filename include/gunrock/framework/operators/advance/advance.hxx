@@ -1,0 +1,168 @@
+/**
+ * @file advance.hxx
+ * @brief `operators::advance::execute` -- same three entry points as the reference
+ * (include/gunrock/framework/operators/advance/advance.hxx:94-133 eight-argument form, :196-225
+ * enactor form, :247-275 `execute_runtime`), dispatching to the sm_100a kernels in
+ * include/gunrock/b200/advance.cuh instead of block_mapped.hxx / merge_path.hxx / thread_mapped.hxx.
+ *
+ * Operator contract unchanged (advance.hxx:35-49): `op(source, neighbor, edge, weight) -> bool`,
+ * called once per (input entry, out-edge); `true` adds the neighbour (or the edge id for an edge
+ * output) to the output frontier.  Behavioural differences, all documented in DESIGN.md:
+ *   - the output frontier is compact (no invalid slots); a following filter sees only valid ids;
+ *   - nothing synchronises with the host; the output size stays on the device until asked for;
+ *   - `direction` is accepted and ignored exactly as in the reference -- pull and
+ *     direction-optimised traversal are provided by the fused enactors (gunrock/b200/bfs.cuh);
+ *   - multi-context execution (`context.size() != 1`) is rejected here as in the reference
+ *     (advance.hxx:129-132); the partitioned multi-GPU path lives above the C ABI.
+ */
+#pragma once
+
+#include <gunrock/b200/advance.cuh>
+#include <gunrock/cuda/context.hxx>
+#include <gunrock/error.hxx>
+#include <gunrock/framework/operators/configs.hxx>
+
+namespace gunrock {
+namespace operators {
+namespace advance {
+
+namespace detail {
+
+/// Adapts the user's `op(vertex_t const&, vertex_t const&, edge_t const&, weight_t const&)`.
+template <typename graph_t, typename operator_t>
+struct op_adapter_t {
+  operator_t op;
+  __device__ __forceinline__ bool operator()(int src, int dst, int edge, float w) const {
+    typename graph_t::vertex_type s = src, d = dst;
+    typename graph_t::edge_type e = edge;
+    typename graph_t::weight_type wt = w;
+    return op(s, d, e, wt);
+  }
+};
+
+inline b200::lb_t to_lb(load_balance_t lb) {
+  switch (lb) {
+    case load_balance_t::thread_mapped:
+      return b200::lb_t::thread_mapped;
+    case load_balance_t::merge_path:
+    case load_balance_t::merge_path_v2:
+      return b200::lb_t::merge_path;
+    default:
+      return b200::lb_t::block_mapped;
+  }
+}
+
+}  // namespace detail
+
+/**
+ * @brief Eight-argument form: explicit input / output frontiers.
+ * `segments` (the reference's scanned work domain) is accepted for source compatibility; the
+ * degree scan lives in the context's workspace.
+ */
+template <load_balance_t lb,
+          advance_direction_t direction,
+          advance_io_type_t input_type,
+          advance_io_type_t output_type,
+          typename graph_t,
+          typename operator_t,
+          typename frontier_t,
+          typename work_tiles_t>
+void execute(graph_t& G,
+             operator_t op,
+             frontier_t* input,
+             frontier_t* output,
+             work_tiles_t& segments,
+             gcuda::multi_context_t& context) {
+  error::throw_if_exception(context.size() != 1, "`context.size() != 1` not supported");
+  static_assert(input_type != advance_io_type_t::edges,
+                "edge input frontiers are not supported by the B200 advance");
+  auto context0 = context.get_context(0);
+  b200::workspace_t& ws = context0->workspace();
+  auto view = G.csr_view();
+  detail::op_adapter_t<graph_t, operator_t> f{op};
+  b200::advance_launch_t cfg;
+  cfg.lb = detail::to_lb(lb);
+
+  const int* in = nullptr;
+  const int* in_count = nullptr;
+  int in_bound = view.n_vertices;
+  if (input_type != advance_io_type_t::graph) {
+    in = reinterpret_cast<const int*>(input->get());
+    in_count = input->count_ptr();
+    in_bound = static_cast<int>(input->size_upper_bound());
+  }
+  b200::ctrl_t* ctrl = nullptr;
+  if constexpr (output_type == advance_io_type_t::none) {
+    b200::launch_advance<b200::advance_output_t::none, false, true>(
+        ws, view, in, in_count, in_bound, nullptr, nullptr, 0, f, cfg, &ctrl);
+  } else {
+    // Size the output for the duplicate-free worst case, as the reference's enactor does
+    // (enactor.hxx:161-193); a kernel that would overflow raises on the next size query.
+    std::size_t want = static_cast<std::size_t>(
+        view.n_edges > view.n_vertices ? view.n_edges : view.n_vertices);
+    if (output->get_capacity() < want)
+      output->reserve(want);
+    output->bind_stream(ws.stream);
+    output->set_number_of_elements(0);
+    constexpr b200::advance_output_t kOut = output_type == advance_io_type_t::edges
+                                                ? b200::advance_output_t::edges
+                                                : b200::advance_output_t::vertices;
+    b200::launch_advance<kOut, false, true>(
+        ws, view, in, in_count, in_bound, reinterpret_cast<int*>(output->get()), output->count_ptr(),
+        static_cast<int>(output->get_capacity()), f, cfg, &ctrl);
+    output->mark_produced(ws.stream, ctrl);
+  }
+}
+
+/// Enactor form: uses (and by default swaps) the enactor's ping-pong buffers (advance.hxx:196-225).
+template <load_balance_t lb = load_balance_t::merge_path,
+          advance_direction_t direction = advance_direction_t::forward,
+          advance_io_type_t input_type = advance_io_type_t::vertices,
+          advance_io_type_t output_type = advance_io_type_t::vertices,
+          typename graph_t,
+          typename enactor_type,
+          typename operator_type>
+void execute(graph_t& G,
+             enactor_type* E,
+             operator_type op,
+             gcuda::multi_context_t& context,
+             bool swap_buffers = true) {
+  execute<lb, direction, input_type, output_type>(G, op, E->get_input_frontier(),
+                                                  E->get_output_frontier(),
+                                                  E->scanned_work_domain, context);
+  if (swap_buffers && (output_type != advance_io_type_t::none))
+    E->swap_frontier_buffers();
+}
+
+/// Runtime load-balance selection (advance.hxx:247-275).
+template <typename graph_t, typename enactor_type, typename operator_type>
+void execute_runtime(graph_t& G,
+                     enactor_type* E,
+                     operator_type op,
+                     load_balance_t lb,
+                     gcuda::multi_context_t& context,
+                     bool swap_buffers = true) {
+  constexpr auto fwd = advance_direction_t::forward;
+  constexpr auto v = advance_io_type_t::vertices;
+  switch (lb) {
+    case load_balance_t::thread_mapped:
+      execute<load_balance_t::thread_mapped, fwd, v, v>(G, E, op, context, swap_buffers);
+      break;
+    case load_balance_t::merge_path:
+    case load_balance_t::merge_path_v2:
+      execute<load_balance_t::merge_path, fwd, v, v>(G, E, op, context, swap_buffers);
+      break;
+    case load_balance_t::block_mapped:
+    case load_balance_t::warp_mapped:
+    case load_balance_t::bucketing:
+    case load_balance_t::work_stealing:
+      execute<load_balance_t::block_mapped, fwd, v, v>(G, E, op, context, swap_buffers);
+      break;
+    default:
+      error::throw_if_exception(cudaErrorUnknown, "Load balance type not supported.");
+  }
+}
+
+}  // namespace advance
+}  // namespace operators
+}  // namespace gunrock

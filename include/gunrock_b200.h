@@ -84,6 +84,7 @@ typedef struct b2g_stats {
   int level_direction[64];     /* first 64 levels: 0 push, 1 pull */
   int level_frontier[64];
   unsigned long long level_edges[64];
+  float level_kernel_ms[64];   /* device time of the level's advance / sweep kernel(s) (CUDA events) */
 } b2g_stats_t;
 
 int b2g_version(void);

@@ -1,0 +1,124 @@
+"""GPU tests of the drop-in boundary: the reference's UNCHANGED example programs
+(examples/algorithms/{bfs,sssp,pr}/*.cu) and the reference's own algorithm headers, compiled against
+this repository's headers (examples/build_reference_examples.sh, built where /root/reference exists;
+the binaries travel to the GPU box).  `--validate` compares against the reference CPU validators
+that are compiled into those binaries."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT, bits_to_f32
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "examples", "bin")
+
+
+def need(name):
+    p = os.path.join(BIN, name)
+    if not os.path.exists(p):
+        pytest.skip(f"{p} not built (needs /root/reference at build time)")
+    return p
+
+
+def write_general_mtx(path, ro, ci, w=None):
+    n = len(ro) - 1
+    src = np.repeat(np.arange(n), np.diff(ro))
+    with open(path, "w") as f:
+        kind = "pattern" if w is None else "real"
+        f.write(f"%%MatrixMarket matrix coordinate {kind} general\n{n} {n} {len(ci)}\n")
+        if w is None:
+            f.write("\n".join(f"{u + 1} {v + 1}" for u, v in zip(src, ci)) + "\n")
+        else:
+            f.write("\n".join(f"{u + 1} {v + 1} {float(x)!r}" for u, v, x in zip(src, ci, w)) + "\n")
+
+
+@pytest.fixture(scope="module")
+def chesapeake_mtx(golden, tmp_path_factory):
+    g = golden["chesapeake"]
+    I, J = np.array(g["coo_I"]), np.array(g["coo_J"])
+    p = tmp_path_factory.mktemp("mtx") / "chesapeake.mtx"
+    with open(p, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate pattern symmetric\n")
+        f.write(f"{g['n_rows']} {g['n_rows']} {len(I) // 2}\n")
+        for k in range(0, len(I), 2):
+            f.write(f"{I[k] + 1} {J[k] + 1}\n")
+    return str(p)
+
+
+@pytest.fixture(scope="module")
+def rmat_mtx(tmp_path_factory):
+    ro, ci = oracle.rmat_csr(13, 8, 123)
+    w = oracle.edge_weights(5, ro, ci, False)     # integers 1..63: exact through the text file
+    d = tmp_path_factory.mktemp("mtx")
+    write_general_mtx(d / "rmat13.mtx", ro, ci, w)
+    return str(d / "rmat13.mtx"), ro, ci, w
+
+
+def run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+@pytest.mark.parametrize("variant", ["", "_ops"])
+@pytest.mark.parametrize("extra", [[], ["--advance_load_balance", "merge_path", "--enable_filter",
+                                        "--filter_algorithm", "compact"],
+                                   ["--advance_load_balance", "thread_mapped"]])
+def test_reference_bfs_example_validates(chesapeake_mtx, golden, variant, extra):
+    """BASELINE.json configs[0]: BFS on chesapeake.mtx src=0, --validate vs the reference CPU."""
+    out = run([need("bfs" + variant), "-m", chesapeake_mtx, "--src", "0", "--validate"] + extra)
+    assert "Number of errors : 0" in out, out
+    m = re.search(r"GPU distances\[:40\] = ([\d ]+)", out)
+    got = [int(x) for x in m.group(1).split()]
+    assert got == golden["chesapeake"]["bfs"]["0"][:len(got)]
+
+
+@pytest.mark.parametrize("variant", ["", "_ops"])
+def test_reference_examples_on_rmat(rmat_mtx, variant):
+    path, ro, ci, w = rmat_mtx
+    src = int(np.diff(ro).argmax())
+    for lb in ("block_mapped", "merge_path"):
+        out = run([need("bfs" + variant), "-m", path, "--src", str(src), "--validate",
+                   "--advance_load_balance", lb])
+        assert "Number of errors : 0" in out, out
+        out = run([need("sssp" + variant), "-m", path, "--src", str(src), "--validate",
+                   "--advance_load_balance", lb])
+        assert "Number of errors : 0" in out, out
+    if variant == "":
+        out = run([need("bfs"), "-m", path, "--src", str(src), "--validate", "--advance_direction", "optimized"])
+        assert "Number of errors : 0" in out, out
+
+
+@pytest.mark.parametrize("variant,tol", [("", 1e-6), ("_ops", 2e-4)])
+def test_reference_pr_example(rmat_mtx, variant, tol):
+    """pr.cu has no --validate: compare the printed head with the oracle.
+    The fused pull path meets the 1e-6 bar; the operator path keeps the reference's fp32 atomicAdd
+    spread, whose summation order is unspecified (looser tolerance, stated here)."""
+    path, ro, ci, w = rmat_mtx
+    out = run([need("pr" + variant), "-m", path])
+    m = re.search(r"GPU rank\[:40\] = (.+)", out)
+    got = np.array([float(x) for x in m.group(1).split()])
+    exp, _ = oracle.pr(ro, ci, w, 0.85, 1e-6)
+    assert np.allclose(got, exp[:len(got)], rtol=max(tol, 2e-6), atol=0)  # 6 printed digits
+
+
+def test_reference_algorithm_headers_on_our_operators(rmat_mtx, chesapeake_mtx):
+    path, ro, ci, w = rmat_mtx
+    src = int(np.diff(ro).argmax())
+    for mtx, s in ((chesapeake_mtx, 0), (path, src)):
+        for lb in ("block_mapped", "merge_path", "thread_mapped"):
+            out = run([need("ref_algorithms"), mtx, str(s), lb])
+            assert "ref-bfs.hxx on B200 operators" in out and out.count("errors : 0") == 2, out
+            assert re.search(r"sum : (0\.99\d+|1(\.0\d*)?)", out), out
+
+
+def test_export_metrics_json(chesapeake_mtx, tmp_path):
+    import json
+    run([need("bfs"), "-m", chesapeake_mtx, "--src", "0", "--export_metrics", "-d", str(tmp_path), "-f", "o.json"])
+    j = json.load(open(tmp_path / "o.json"))
+    assert j["primitive"] == "bfs" and j["num_vertices"] == 39 and j["num_edges"] == 340
+    assert j["edges_visited"][0] == 340 and j["search_depths"][0] == 3 and j["mteps"][0] > 0
