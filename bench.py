@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--lb", default=None, choices=["thread_mapped", "block_mapped", "merge_path"])
     ap.add_argument("--direction", default=None, choices=["forward", "backward", "optimized"])
     ap.add_argument("--hub-threshold", type=int, default=4096)
-    ap.add_argument("--ctas-per-sm", type=int, default=4)
+    ap.add_argument("--ctas-per-sm", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
@@ -373,6 +373,7 @@ def main():
                    "l2_policy": "inputs larger than L2 (column indices %.0f MB > 126 MB)" % (G.n_edges * 4 / 1e6),
                    "levels": last.iterations, "level_direction": last.level_direction,
                    "level_frontier": last.level_frontier, "level_edges": last.level_edges[:last.iterations],
+                   "level_kernel_ms": [round(x, 4) for x in last.level_kernel_ms[:last.iterations]],
                    "edges_touched_per_step": agg["edges"] // args.steps,
                    "graph500_mteps": (G.n_edges * (len(sources) * world if world > 1 else 1)) / (ms / args.steps) / 1e3},
         "e2e": {"value": e2e, "unit": "MTEPS", "h2d_bytes_per_step": 4 * (len(sources) if world > 1 else 1),

@@ -66,7 +66,7 @@ class options_t:
     uniquify_percent: float = 100.0
     advance_direction: int = advance_direction_t.forward
     hub_threshold: int = 4096
-    ctas_per_sm: int = 4
+    ctas_per_sm: int = 8
     reference_functor: bool = False
     do_alpha: float = 14.0
     do_beta: float = 24.0

@@ -132,7 +132,7 @@ advance_launch_t to_launch(const b2g_options_t& o) {
       a.lb = lb_t::block_mapped;
   }
   a.hub_threshold = o.hub_threshold > 0 ? o.hub_threshold : 4096;
-  a.ctas_per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 4;
+  a.ctas_per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 8;
   return a;
 }
 
@@ -384,7 +384,7 @@ void b2g_options_default(b2g_options_t* o) {
   o->uniquify_percent = 100.0f;
   o->advance_direction = B2G_DIR_FORWARD;
   o->hub_threshold = 4096;
-  o->ctas_per_sm = 4;
+  o->ctas_per_sm = 8;
   o->reference_functor = 0;
   o->do_alpha = 14.0f;
   o->do_beta = 24.0f;
@@ -671,7 +671,8 @@ int b2g_pr(b2g_graph_t* g, float alpha, float tol, int max_iter, const b2g_optio
       d_p = reinterpret_cast<float*>(g->misc.ensure(static_cast<size_t>(V) + 16));
     int launches0 = g->ws.launches;
     B2G_CHECK(cudaEventRecord(g->ev0, st));
-    int iters = pr_run(g->ws, g->pr, g->view, g->t_view, alpha, tol, max_iter, d_p);
+    std::vector<pr_iter_stat_t> it_stats;
+    int iters = pr_run(g->ws, g->pr, g->view, g->t_view, alpha, tol, max_iter, d_p, &it_stats);
     B2G_CHECK(cudaEventRecord(g->ev1, st));
     if (p_loc == B2G_HOST)
       B2G_CHECK(cudaMemcpyAsync(p, d_p, sizeof(float) * static_cast<size_t>(V),
@@ -684,6 +685,11 @@ int b2g_pr(b2g_graph_t* g, float alpha, float tol, int max_iter, const b2g_optio
       stats->n_levels = iters;
       stats->edges_touched = static_cast<unsigned long long>(g->n_edges) * iters;
       stats->vertices_touched = static_cast<unsigned long long>(V) * iters;
+      for (size_t i = 0; i < it_stats.size() && i < 64; ++i) {
+        stats->level_frontier[i] = V;
+        stats->level_edges[i] = static_cast<unsigned long long>(g->n_edges);
+        stats->level_kernel_ms[i] = it_stats[i].kernel_ms;
+      }
     }
     return 0;
   });

@@ -475,13 +475,14 @@ template <int kThreads, int kTile, advance_input_t kIn, advance_output_t kOut, b
 __global__ void __launch_bounds__(kThreads)
 advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, Op op) {
   constexpr int kWarps = kThreads / 32;
-  constexpr int kRows = kTile + 2;  // kTile edges overlap at most kTile non-empty rows (+ sentinel)
+  constexpr int kRows = kTile + 36;  // kTile edges overlap at most kTile non-empty rows (+ 33 sentinels)
   __shared__ int s_emit[kWarps][kEmitCap];
   __shared__ int s_rank[kRows];  // first global rank of each staged row
   __shared__ int s_base[kRows];  // CSR offset of the row's first edge
   __shared__ int s_vert[kRows];
   __shared__ int s_wcount[kWarps];
   __shared__ int s_nrows;
+  __shared__ int s_tile;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int* __restrict__ ro = p.g.row_offsets;
   const int* __restrict__ ci = p.g.column_indices;
@@ -494,7 +495,15 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
   warp_emitter_t<kEmitCap, kDegSum> em;
   em.init(s_emit[warp], p.out, p.out_count, p.out_capacity, ro, p.ctrl);
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (;;) {
+    // dynamic tile ticket: CTAs that become resident late simply take fewer tiles
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s_tile = atomicAdd(&p.ctrl->work, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= ntiles)
+      break;
     const int r_begin = tile * kTile;
     const int r_end = min(total, r_begin + kTile);
     const int row0 = p.tile_rows[tile];
@@ -523,7 +532,7 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
         int slot = off + __popc(m & lanemask_lt());
         int v = (kIn == advance_input_t::graph) ? i : p.in[i];
         s_rank[slot] = sc;
-        s_base[slot] = ro[v];
+        s_base[slot] = ro[v] - sc;
         s_vert[slot] = v;
       }
       __syncthreads();
@@ -536,39 +545,47 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
       __syncthreads();
     }
     const int nrows = s_nrows;
-    if (threadIdx.x == 0)
-      s_rank[nrows] = r_end;  // sentinel
+    if (threadIdx.x < 33)
+      s_rank[nrows + threadIdx.x] = r_end;  // sentinels: no row starts inside [r_end, ...)
     __syncthreads();
-    for (int r0 = r_begin + warp * 32; r0 < r_end; r0 += kThreads) {
-      int a = 0, b = nrows;  // warp-uniform: last staged row with s_rank <= r0
+    // Each warp owns a contiguous span of the tile and walks it 32 ranks at a time, so its row
+    // cursor only moves forward: one binary search per span, then per chunk the row starts that
+    // fall inside the 32 ranks are turned into a bit mask (one REDUX) and every lane derives its
+    // row as cursor + popc(mask & lanes_le) -- no per-edge search.
+    constexpr int kSpan = kTile / kWarps;
+    const int w_begin = r_begin + warp * kSpan;
+    const int w_end = min(r_end, w_begin + kSpan);
+    if (w_begin < w_end) {
+      int a = 0, b = nrows;  // last staged row with s_rank <= w_begin
       while (b - a > 1) {
         int mid = (a + b) >> 1;
-        if (s_rank[mid] <= r0)
+        if (s_rank[mid] <= w_begin)
           a = mid;
         else
           b = mid;
       }
-      int r = r0 + lane;
-      bool valid = r < r_end;
-      bool keep = false;
-      int nb = -1, e = 0;
-      if (valid) {
-        int c = a, d = min(nrows, a + 33);  // at most 32 row starts fall inside 32 ranks
-        while (d - c > 1) {
-          int mid = (c + d) >> 1;
-          if (s_rank[mid] <= r)
-            c = mid;
-          else
-            d = mid;
+      for (int r0 = w_begin; r0 < w_end; r0 += 32) {
+        // invariant: s_rank[a] <= r0 <= s_rank[a+1].  Row starts of rows a+1.. that fall inside
+        // [r0, r0+32) become bits (strictly increasing starts => at most 32 of them).
+        int nxt = s_rank[min(a + 1 + lane, nrows + 32)] - r0;
+        unsigned bit = (nxt >= 0 && nxt < 32) ? (1u << nxt) : 0u;
+        unsigned starts = __reduce_or_sync(kFull, bit);
+        int r = r0 + lane;
+        bool valid = r < w_end;
+        int row = a + __popc(starts & (0xffffffffu >> (31 - lane)));
+        bool keep = false;
+        int nb = -1, e = 0;
+        if (valid) {
+          int u = s_vert[row];
+          e = s_base[row] + r;  // s_base holds (CSR offset - first rank) of the row
+          nb = ld_stream(ci + e);
+          float w = (kWeights && vals) ? ld_stream(vals + e) : 1.0f;
+          keep = op(u, nb, e, w);
         }
-        int u = s_vert[c];
-        e = s_base[c] + (r - s_rank[c]);
-        nb = ld_stream(ci + e);
-        float w = (kWeights && vals) ? ld_stream(vals + e) : 1.0f;
-        keep = op(u, nb, e, w);
+        if (kOut != advance_output_t::none)
+          em.push(keep, kOut == advance_output_t::edges ? e : nb);
+        a += __popc(starts);
       }
-      if (kOut != advance_output_t::none)
-        em.push(keep, kOut == advance_output_t::edges ? e : nb);
     }
   }
   if (kOut != advance_output_t::none)
@@ -585,7 +602,7 @@ enum class lb_t { thread_mapped, block_mapped, merge_path };
 struct advance_launch_t {
   lb_t lb = lb_t::block_mapped;
   int hub_threshold = 4096;  // rows >= this go to the grid (TMA slab) bin; block_mapped only
-  int ctas_per_sm = 4;
+  int ctas_per_sm = 8;
 };
 
 static __global__ void place_scan_total_kernel(int* scanned, const int* n_ptr, int n_fixed,

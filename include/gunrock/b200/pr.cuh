@@ -18,6 +18,9 @@
  */
 #pragma once
 
+#include <stdexcept>
+#include <vector>
+
 #include <gunrock/b200/ptx.cuh>
 #include <gunrock/b200/runtime.cuh>
 
@@ -25,24 +28,43 @@ namespace gunrock {
 namespace b200 {
 
 constexpr int kPrPartials = 1024;  // fixed number of dangling-sum partials (deterministic tree)
+constexpr int kPrTile = 2048;      // in-edges per pull tile (8 KiB of source ids per TMA slab)
 
 struct pr_scratch_t {
   dbuf_t<float> plast, iw, c;
-  dbuf_t<double> partials;
-  dbuf_t<unsigned> err;  // fp32 bit pattern of max |p - plast|
+  dbuf_t<double> partials;           // kPrPartials dangling partial sums
+  dbuf_t<double> head, tail;         // per-tile partial sums of rows crossing a tile boundary
+  dbuf_t<int> first_owned;           // per tile: first row whose first in-edge rank >= tile start
+  dbuf_t<int> tail_row;              // per tile: row left incomplete at the tile end, or -1
+  dbuf_t<unsigned> err;              // [0] fp32 bits of max|p - plast|, [1] prepare ticket
+  dbuf_t<float> base;                // (1 - alpha + dangling) / V of the current iteration
+  const int* tiled_offsets = nullptr;  // CSC offsets the tile table was built for
   float* h_err = nullptr;
+  cudaEvent_t ev[128] = {};
   ~pr_scratch_t() {
     if (h_err)
       cudaFreeHost(h_err);
+    for (auto e : ev)
+      if (e)
+        cudaEventDestroy(e);
   }
-  void ensure(int V) {
+  void ensure(int V, int E) {
     plast.ensure(static_cast<size_t>(V) + 16);
     iw.ensure(static_cast<size_t>(V) + 16);
     c.ensure(static_cast<size_t>(V) + 16);
     partials.ensure(kPrPartials);
+    size_t tiles = static_cast<size_t>(E) / kPrTile + 4;
+    head.ensure(tiles);
+    tail.ensure(tiles);
+    first_owned.ensure(tiles);
+    tail_row.ensure(tiles);
     err.ensure(4);
+    base.ensure(4);
     if (!h_err)
       B2G_CHECK(cudaMallocHost(&h_err, sizeof(float)));
+    if (!ev[0])
+      for (auto& e : ev)
+        B2G_CHECK(cudaEventCreate(&e));
   }
 };
 
@@ -69,12 +91,37 @@ static __global__ void pr_reset_kernel(csr_view_t g, float alpha, float* p, floa
   }
 }
 
-/// prepare: plast = p, c = plast*iw, and kPrPartials deterministic fp64 partial dangling sums.
+/// Tile table of the CSC (built once per graph): first_owned[t] = smallest row r with
+/// offsets[r] >= t * kPrTile, first_owned[ntiles] = V.
+static __global__ void pr_tile_table_kernel(const int* __restrict__ offsets, int V, int ntiles,
+                                            int* __restrict__ first_owned) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += gridDim.x * blockDim.x) {
+    if (t == ntiles) {
+      first_owned[t] = V;
+      continue;
+    }
+    long long t0 = static_cast<long long>(t) * kPrTile;
+    int lo = -1, hi = V;  // offsets[lo] < t0 <= offsets[hi]   (offsets[V] = E >= t0)
+    while (hi - lo > 1) {
+      int mid = lo + ((hi - lo) >> 1);
+      if (offsets[mid] < t0)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    first_owned[t] = hi;
+  }
+}
+
+/// prepare: plast = p, c = plast*iw, kPrPartials deterministic fp64 partial dangling sums; the
+/// last CTA to finish folds them (fixed order) into base = (1 - alpha + dsum) / V.
 template <int kThreads>
 __global__ void __launch_bounds__(kThreads)
 pr_prepare_kernel(int V, float alpha, const float* __restrict__ p, const float* __restrict__ iw,
-                  float* __restrict__ plast, float* __restrict__ c, double* __restrict__ partials) {
+                  float* __restrict__ plast, float* __restrict__ c, double* __restrict__ partials,
+                  unsigned* ticket, float* base_out) {
   __shared__ double s_red[kThreads / 32];
+  __shared__ bool s_last;
   // contiguous slice per CTA so the partial is independent of the grid's scheduling
   const int per = (V + gridDim.x - 1) / gridDim.x;
   const int lo = blockIdx.x * per, hi = min(V, lo + per);
@@ -95,82 +142,201 @@ pr_prepare_kernel(int V, float alpha, const float* __restrict__ p, const float* 
     for (int w = 0; w < kThreads / 32; ++w)
       t += s_red[w];
     partials[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {
+    __threadfence();
+    double t = 0.0;
+    const int chunk = (gridDim.x + 31) / 32;
+    for (int i = 0; i < chunk; ++i) {
+      int k = threadIdx.x * chunk + i;
+      if (k < static_cast<int>(gridDim.x))
+        t += __ldcg(partials + k);
+    }
+    t = warp_sum(t);  // xor tree: fixed order
+    if (threadIdx.x == 0) {
+      const float dsum = static_cast<float>(t);
+      *base_out = __fdiv_rn(__fadd_rn(__fsub_rn(1.0f, alpha), dsum), static_cast<float>(V));
+      *ticket = 0;
+    }
   }
 }
 
 /**
- * @brief pull: one warp fetches 32 destination rows; rows >= 32 in-edges are reduced by the whole
- * warp (coalesced index stream, fp64 shuffle reduction), shorter rows by their lane.
+ * @brief pull, tile version.  The CSC edge array is cut into kPrTile-edge tiles handed out by an
+ * atomic ticket; a tile's source ids are staged HBM -> shared memory by ONE thread with
+ * cp.async.bulk (TMA engine, SASS UBLKCP; the next tile's slab is in flight while this one is
+ * reduced).  Threads gather c[src] (x weight) for the slab into shared memory (8 independent
+ * gathers in flight per thread), then the rows that START inside the tile are reduced: short
+ * segments by one thread, segments >= 64 by a warp, all in fp64.  Rows that cross a tile end leave
+ * a partial (tail of this tile / head of the following ones) that pr_fixup_kernel folds in a
+ * fixed order, so the result does not depend on scheduling.
  */
-template <int kThreads>
+template <int kThreads, bool kWeights>
 __global__ void __launch_bounds__(kThreads)
-pr_pull_kernel(csr_view_t t, float alpha, const float* __restrict__ c,
-               const float* __restrict__ plast, const double* __restrict__ partials,
-               float* __restrict__ p, unsigned* err_bits, ctrl_t* ctrl) {
-  const int lane = lane_id();
-  const int V = t.n_vertices;
+pr_pull_tile_kernel(csr_view_t t, int ntiles, const int* __restrict__ first_owned,
+                    const float* __restrict__ c, const float* __restrict__ plast,
+                    const float* __restrict__ base_ptr, float* __restrict__ p,
+                    double* __restrict__ head, double* __restrict__ tail,
+                    int* __restrict__ tail_row, unsigned* err_bits, ctrl_t* ctrl) {
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kLong = 64;
+  constexpr int kMaxLong = kPrTile / kLong + 2;
+  __shared__ __align__(16) int s_src[2][kPrTile];
+  __shared__ __align__(16) float s_w[kWeights ? 2 : 1][kWeights ? kPrTile : 4];
+  __shared__ float s_x[kPrTile];
+  __shared__ int s_long_row[kMaxLong];  // row id, or -1 for the head segment
+  __shared__ int s_long_lo[kMaxLong], s_long_hi[kMaxLong];
+  __shared__ int s_nlong;
+  __shared__ int s_ticket[2];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int V = t.n_vertices, E = t.n_edges;
   const int* __restrict__ ro = t.row_offsets;
-  const int* __restrict__ ci = t.column_indices;
-  const float* __restrict__ vals = t.values;
-  // base term, identical in every thread: fixed-order fp64 sum of the partials
-  double ds = 0.0;
-  for (int i = 0; i < kPrPartials; ++i)
-    ds += partials[i];
-  const float dsum = static_cast<float>(ds);
-  const float base_f = __fdiv_rn(__fadd_rn(__fsub_rn(1.0f, alpha), dsum), static_cast<float>(V));
-  const double base = static_cast<double>(base_f);
+  const double base = static_cast<double>(*base_ptr);
   float err = 0.0f;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int tile, int buf) {  // thread 0 only
+    int t0 = tile * kPrTile;
+    int cnt = min(kPrTile, E - t0);
+    uint32_t bytes = static_cast<uint32_t>((cnt + 3) & ~3) * 4u;
+    if (bytes == 0)
+      bytes = 16;  // E == 0: one empty tile, arrays are padded
+    mbar_expect_tx(&s_bar[buf], kWeights ? 2 * bytes : bytes);
+    bulk_g2s(&s_src[buf][0], t.column_indices + t0, bytes, &s_bar[buf]);
+    if (kWeights)
+      bulk_g2s(&s_w[kWeights ? buf : 0][0], t.values + t0, bytes, &s_bar[buf]);
+  };
+  if (threadIdx.x == 0) {
+    s_ticket[0] = atomicAdd(&ctrl->work, 1);
+    if (s_ticket[0] < ntiles)
+      issue(s_ticket[0], 0);
+  }
+  __syncthreads();
+  int buf = 0;
+  unsigned phase_bits = 0;
   for (;;) {
-    int b = 0;
-    if (lane == 0)
-      b = atomicAdd(&ctrl->work, 32);
-    b = __shfl_sync(kFull, b, 0);
-    if (b >= V)
+    const int tile = s_ticket[buf];
+    if (tile >= ntiles)
       break;
-    const int v = b + lane;
-    int start = 0, deg = 0;
-    if (v < V) {
-      start = ro[v];
-      deg = ro[v + 1] - start;
+    if (threadIdx.x == 0) {  // prefetch the next tile's slab
+      int nt = atomicAdd(&ctrl->work, 1);
+      s_ticket[buf ^ 1] = nt;
+      if (nt < ntiles)
+        issue(nt, buf ^ 1);
+      s_nlong = 0;
     }
-    double acc = 0.0;
-    bool mine_done = false;
-    unsigned big = __ballot_sync(kFull, deg >= 32);
-    while (big) {
-      int leader = __ffs(big) - 1;
-      big &= big - 1;
-      int s = __shfl_sync(kFull, start, leader);
-      int d = __shfl_sync(kFull, deg, leader);
-      double part = 0.0;
-      for (int off = lane; off < d; off += 32) {
-        int u = ld_stream(ci + s + off);
-        float x = c[u];
-        if (vals)
-          x = __fmul_rn(x, ld_stream(vals + s + off));
-        part += static_cast<double>(x);
-      }
-      part = warp_sum(part);
-      if (lane == leader) {
-        acc = part;
-        mine_done = true;
+    const int t0 = tile * kPrTile;
+    const int t1 = min(E, t0 + kPrTile);
+    const int cnt = t1 - t0;
+    mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
+    phase_bits ^= 1u << buf;
+    // ---- gather contributions of the slab ------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < kPrTile / kThreads; ++j) {
+      int k = threadIdx.x + j * kThreads;
+      if (k < cnt) {
+        float x = c[s_src[buf][k]];
+        if (kWeights)
+          x = __fmul_rn(x, s_w[kWeights ? buf : 0][k]);
+        s_x[k] = x;
       }
     }
-    if (!mine_done) {
-      for (int k = 0; k < deg; ++k) {
-        int u = ci[start + k];
-        float x = c[u];
-        if (vals)
-          x = __fmul_rn(x, vals[start + k]);
-        acc += static_cast<double>(x);
+    __syncthreads();
+    // ---- rows owned by this tile ------------------------------------------------------------
+    const int lo = first_owned[tile];
+    const int hi = (tile == ntiles - 1) ? V : first_owned[tile + 1];
+    const int first_start = lo < V ? ro[lo] : E;
+    if (threadIdx.x == 0) {
+      tail_row[tile] = -1;
+      if (first_start > t0) {  // row lo-1 started earlier and reaches into this tile: head segment
+        int slot = atomicAdd(&s_nlong, 1);
+        s_long_row[slot] = -1;
+        s_long_lo[slot] = 0;
+        s_long_hi[slot] = min(first_start, t1) - t0;
       }
     }
-    if (v < V) {
-      float pv = static_cast<float>(base + acc);
-      p[v] = pv;
-      err = fmaxf(err, fabsf(pv - plast[v]));
+    for (int r = lo + threadIdx.x; r < hi; r += kThreads) {
+      const int s = ro[r], e = ro[r + 1];
+      const int seg_hi = min(e, t1) - t0, seg_lo = s - t0;
+      if (seg_hi - seg_lo >= kLong || e > t1) {  // long, or crosses the tile end (tail)
+        int slot = atomicAdd(&s_nlong, 1);
+        s_long_row[slot] = r;
+        s_long_lo[slot] = seg_lo;
+        s_long_hi[slot] = seg_hi;
+      } else {
+        double acc = 0.0;
+        for (int k = seg_lo; k < seg_hi; ++k)
+          acc += static_cast<double>(s_x[k]);
+        float pv = static_cast<float>(base + acc);
+        p[r] = pv;
+        err = fmaxf(err, fabsf(pv - plast[r]));
+      }
     }
+    __syncthreads();
+    const int nlong = s_nlong;
+    for (int i = warp; i < nlong; i += kWarps) {
+      const int r = s_long_row[i], a = s_long_lo[i], b = s_long_hi[i];
+      double acc = 0.0;
+      for (int k = a + lane; k < b; k += 32)
+        acc += static_cast<double>(s_x[k]);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if (r < 0) {
+          head[tile] = acc;
+        } else if (ro[r + 1] > t1) {
+          tail[tile] = acc;
+          tail_row[tile] = r;
+        } else {
+          float pv = static_cast<float>(base + acc);
+          p[r] = pv;
+          err = fmaxf(err, fabsf(pv - plast[r]));
+        }
+      }
+    }
+    __syncthreads();  // s_x, s_long_*, s_src[buf] are free again
+    buf ^= 1;
   }
   err = warp_max(err);
+  if (lane == 0 && err > 0.0f)
+    atomicMax(err_bits, __float_as_uint(err));
+}
+
+/// Fold the partials of rows that span several tiles: total = tail(t) + sum of head(t+1 .. tB),
+/// lanes strided over the following tiles, fixed xor-tree order.  One warp per tile.
+static __global__ void pr_fixup_kernel(csr_view_t t, int ntiles, const int* __restrict__ tail_row,
+                                       const double* __restrict__ head,
+                                       const double* __restrict__ tail,
+                                       const float* __restrict__ base_ptr,
+                                       const float* __restrict__ plast, float* __restrict__ p,
+                                       unsigned* err_bits) {
+  const int lane = lane_id();
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const double base = static_cast<double>(*base_ptr);
+  float err = 0.0f;
+  for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles; tile += warps) {
+    const int r = tail_row[tile];
+    if (r < 0)
+      continue;
+    const int last_tile = (t.row_offsets[r + 1] - 1) / kPrTile;
+    double acc = 0.0;
+    for (int k = tile + 1 + lane; k <= last_tile; k += 32)
+      acc += head[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float pv = static_cast<float>(base + (tail[tile] + acc));
+      p[r] = pv;
+      err = fmaxf(err, fabsf(pv - plast[r]));
+    }
+  }
   if (lane == 0 && err > 0.0f)
     atomicMax(err_bits, __float_as_uint(err));
 }
@@ -180,16 +346,31 @@ static __global__ void pr_err_feedback_kernel(unsigned* err_bits, float* h_err) 
   *err_bits = 0;
 }
 
+struct pr_iter_stat_t {
+  float kernel_ms = 0.0f;  // prepare + pull + fixup of one iteration
+};
+
 /// Returns the iteration count.  g = CSR (out-edges, for iweights), t = CSC (in-edges, pulled).
 inline int pr_run(workspace_t& ws, pr_scratch_t& sc, const csr_view_t& g, const csr_view_t& t,
-                  float alpha, float tol, int max_iter, float* p) {
-  const int V = g.n_vertices;
+                  float alpha, float tol, int max_iter, float* p,
+                  std::vector<pr_iter_stat_t>* iters_out = nullptr) {
+  const int V = g.n_vertices, E = t.n_edges;
   const int sms = device_info_t::get().sm_count;
-  sc.ensure(V);
+  sc.ensure(V, E);
   cudaStream_t st = ws.stream;
+  const int ntiles = E > 0 ? (E + kPrTile - 1) / kPrTile : 1;
+  if (sc.tiled_offsets != t.row_offsets) {  // per-graph table (ingest-like, not per iteration)
+    pr_tile_table_kernel<<<sms * 2, 256, 0, st>>>(t.row_offsets, V, ntiles, sc.first_owned.ptr);
+    sc.tiled_offsets = t.row_offsets;
+    ws.launches += 1;
+  }
   pr_reset_kernel<<<sms * 8, 256, 0, st>>>(g, alpha, p, sc.plast.ptr, sc.iw.ptr);
-  B2G_CHECK(cudaMemsetAsync(sc.err.ptr, 0, sizeof(unsigned), st));
+  B2G_CHECK(cudaMemsetAsync(sc.err.ptr, 0, 2 * sizeof(unsigned), st));
   ws.launches += 1;
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(t.column_indices) & 15u) == 0 &&
+                      (!t.values || (reinterpret_cast<uintptr_t>(t.values) & 15u) == 0);
+  if (!tma_ok)
+    throw std::runtime_error("pagerank pull needs 16-byte aligned CSC arrays (TMA slabs)");
   int iteration = 0;
   for (;;) {
     if (iteration > 0) {
@@ -201,14 +382,33 @@ inline int pr_run(workspace_t& ws, pr_scratch_t& sc, const csr_view_t& g, const 
     }
     if (max_iter > 0 && iteration >= max_iter)
       break;
+    if (iteration < 64)
+      B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration], st));
     pr_prepare_kernel<256><<<kPrPartials, 256, 0, st>>>(V, alpha, p, sc.iw.ptr, sc.plast.ptr,
-                                                        sc.c.ptr, sc.partials.ptr);
+                                                        sc.c.ptr, sc.partials.ptr, sc.err.ptr + 1,
+                                                        sc.base.ptr);
     ctrl_t* ctrl = ws.next_ctrl();
-    pr_pull_kernel<256><<<sms * 8, 256, 0, st>>>(t, alpha, sc.c.ptr, sc.plast.ptr, sc.partials.ptr,
-                                                 p, sc.err.ptr, ctrl);
-    ws.launches += 2;
+    const int grid = sms * 4;
+    if (t.values)
+      pr_pull_tile_kernel<256, true><<<grid, 256, 0, st>>>(
+          t, ntiles, sc.first_owned.ptr, sc.c.ptr, sc.plast.ptr, sc.base.ptr, p, sc.head.ptr,
+          sc.tail.ptr, sc.tail_row.ptr, sc.err.ptr, ctrl);
+    else
+      pr_pull_tile_kernel<256, false><<<grid, 256, 0, st>>>(
+          t, ntiles, sc.first_owned.ptr, sc.c.ptr, sc.plast.ptr, sc.base.ptr, p, sc.head.ptr,
+          sc.tail.ptr, sc.tail_row.ptr, sc.err.ptr, ctrl);
+    pr_fixup_kernel<<<sms, 256, 0, st>>>(t, ntiles, sc.tail_row.ptr, sc.head.ptr, sc.tail.ptr,
+                                         sc.base.ptr, sc.plast.ptr, p, sc.err.ptr);
+    if (iteration < 64)
+      B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration + 1], st));
+    ws.launches += 3;
     B2G_CHECK(cudaGetLastError());
     ++iteration;
+  }
+  if (iters_out) {
+    iters_out->resize(iteration);
+    for (int l = 0; l < iteration && l < 64; ++l)
+      cudaEventElapsedTime(&(*iters_out)[l].kernel_ms, sc.ev[2 * l], sc.ev[2 * l + 1]);
   }
   return iteration;
 }

@@ -103,7 +103,7 @@ def test_reference_pr_example(rmat_mtx, variant, tol):
     m = re.search(r"GPU rank\[:40\] = (.+)", out)
     got = np.array([float(x) for x in m.group(1).split()])
     exp, _ = oracle.pr(ro, ci, w, 0.85, 1e-6)
-    assert np.allclose(got, exp[:len(got)], rtol=max(tol, 2e-6), atol=0)  # 6 printed digits
+    assert np.allclose(got, exp[:len(got)], rtol=max(tol, 1e-5), atol=0)  # print::head shows 6 significant digits
 
 
 def test_reference_algorithm_headers_on_our_operators(rmat_mtx, chesapeake_mtx):
