@@ -16,6 +16,7 @@
 
 #include <gunrock/b200/advance.cuh>
 #include <gunrock/b200/bfs.cuh>
+#include <gunrock/b200/bfs_partitioned.cuh>
 #include <gunrock/b200/filter.cuh>
 #include <gunrock/b200/pr.cuh>
 #include <gunrock/b200/sssp.cuh>
@@ -75,6 +76,12 @@ struct b2g_graph {
   bfs_scratch_t bfs;
   sssp_scratch_t sssp;
   pr_scratch_t pr;
+  bool partitioned = false;
+  partition_t pt;
+  part_bfs_state_t part;
+  dbuf_t<unsigned long long> part_deg;
+  ctrl_t* part_ctrl = nullptr;
+  int part_level_dir = 0;
   dbuf_t<unsigned> uniq_bitmap;
   dbuf_t<int> misc;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -179,7 +186,7 @@ __host__ __device__ inline float edge_weight(unsigned long long seed, int u, int
 constexpr unsigned long long kDropKey = ~0ull;
 
 __global__ void rmat_keys_kernel(int scale, long long n_pairs, unsigned long long seed, int mirror,
-                                 int fold, unsigned long long* keys) {
+                                 int fold, unsigned long long* keys, int nparts = 1, int part = 0) {
   const unsigned TA = 37356u, TAB = 49807u, TABC = 62259u;
   for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n_pairs;
        k += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -202,6 +209,16 @@ __global__ void rmat_keys_kernel(int scale, long long n_pairs, unsigned long lon
     unsigned long long b = (static_cast<unsigned long long>(v) << 32) | u;
     if (u == v)
       a = b = kDropKey;
+    if (nparts > 1) {  // keep only edges whose source this rank owns; row = local row id
+      if (u != v) {
+        a = (u % nparts == static_cast<unsigned>(part))
+                ? ((static_cast<unsigned long long>(u / nparts) << 32) | v)
+                : kDropKey;
+        b = (v % nparts == static_cast<unsigned>(part))
+                ? ((static_cast<unsigned long long>(v / nparts) << 32) | u)
+                : kDropKey;
+      }
+    }
     if (mirror) {
       keys[2 * k] = a;
       keys[2 * k + 1] = b;
@@ -288,19 +305,23 @@ b2g_graph* create_coo_impl(int n_rows, int nnz, const int* I, const int* J, cons
 }
 
 b2g_graph* create_rmat_impl(int scale, long long n_pairs, unsigned long long seed, int mirror,
-                            int fold_vertices, int weights, unsigned long long weight_seed) {
+                            int fold_vertices, int weights, unsigned long long weight_seed,
+                            int nparts = 1, int part = 0) {
   std::unique_ptr<b2g_graph> g(new b2g_graph());
   g->init_runtime();
   cudaStream_t st = g->ws.stream;
   const int sms = device_info_t::get().sm_count;
-  const int V = fold_vertices > 0 ? fold_vertices : (1 << scale);
+  const int V_global = fold_vertices > 0 ? fold_vertices : (1 << scale);
+  const partition_t pt = partition_t::make(V_global, nparts, part);
+  const int V = nparts > 1 ? pt.n_local : V_global;
   const size_t n_keys = static_cast<size_t>(n_pairs) * (mirror ? 2 : 1);
   if (n_keys > static_cast<size_t>(INT_MAX))
     throw std::runtime_error("rmat: more than INT_MAX candidate keys (int32 edge ids)");
   dbuf_t<unsigned long long> k0, k1;
   k0.ensure(n_keys + 1);
   k1.ensure(n_keys + 1);
-  rmat_keys_kernel<<<sms * 16, 256, 0, st>>>(scale, n_pairs, seed, mirror, fold_vertices, k0.ptr);
+  rmat_keys_kernel<<<sms * 16, 256, 0, st>>>(scale, n_pairs, seed, mirror, fold_vertices, k0.ptr,
+                                             nparts, part);
   unsigned long long* sorted = sort_keys_u64(k0.ptr, k1.ptr, n_keys, 64, st);
   // unique + drop sentinel -> compact (row, col) lists via the look-back select
   dbuf_t<int> rows, count;
@@ -339,6 +360,10 @@ b2g_graph* create_rmat_impl(int scale, long long n_pairs, unsigned long long see
   g->symmetric = mirror ? 1 : 0;
   g->has_vals = weights != 0;
   g->set_views();
+  if (nparts > 1) {
+    g->partitioned = true;
+    g->pt = pt;
+  }
   return g.release();
 }
 
@@ -763,6 +788,248 @@ int b2g_uniquify(b2g_graph_t* g, const int* in, const int* in_count, int in_capa
                           out_count);
     }
     B2G_CHECK(cudaStreamSynchronize(st));
+    return 0;
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU BFS: per-rank steps (exchange is done by the host between the calls)
+// ---------------------------------------------------------------------------------------------
+int b2g_graph_create_rmat_part(int scale, long long n_pairs, unsigned long long seed, int mirror,
+                               int nparts, int part, b2g_graph_t** out) {
+  if (!out || scale < 1 || scale > 30 || n_pairs < 0 || nparts < 1 || part < 0 || part >= nparts ||
+      nparts > 64)
+    return fail(B2G_ERR_INVALID, "b2g_graph_create_rmat_part: bad arguments");
+  if (!have_device())
+    return fail(B2G_ERR_NO_DEVICE, "no CUDA device: libgunrock_b200 has no CPU fallback");
+  return guarded([&] {
+    b2g_graph* g = create_rmat_impl(scale, n_pairs, seed, mirror, 0, 0, 0, nparts, part);
+    if (nparts == 1) {
+      g->partitioned = true;
+      g->pt = partition_t::make(g->n_vertices, 1, 0);
+    }
+    *out = g;
+    return 0;
+  });
+}
+
+int b2g_graph_create_csr_part(int n_global_vertices, int nparts, int part, int n_local_edges,
+                              const int* row_offsets, const int* column_indices, int loc,
+                              int symmetric, b2g_graph_t** out) {
+  if (!out || n_global_vertices < 0 || nparts < 1 || nparts > 64 || part < 0 || part >= nparts)
+    return fail(B2G_ERR_INVALID, "b2g_graph_create_csr_part: bad arguments");
+  partition_t pt = partition_t::make(n_global_vertices, nparts, part);
+  int rc = b2g_graph_create_csr(pt.n_local, n_local_edges, row_offsets, column_indices, nullptr, loc,
+                                symmetric, out);
+  if (rc)
+    return rc;
+  (*out)->partitioned = true;
+  (*out)->pt = pt;
+  return 0;
+}
+
+int b2g_part_info(const b2g_graph_t* g, int* n_global, int* nparts, int* part, int* n_local,
+                  int* words_per_rank) {
+  if (!g || !g->partitioned)
+    return fail(B2G_ERR_INVALID, "not a partitioned graph");
+  if (n_global)
+    *n_global = g->pt.n_global;
+  if (nparts)
+    *nparts = g->pt.nparts;
+  if (part)
+    *part = g->pt.part;
+  if (n_local)
+    *n_local = g->pt.n_local;
+  if (words_per_rank)
+    *words_per_rank = (g->pt.rows_of(0) + 31) / 32;
+  return 0;
+}
+
+int b2g_part_bfs_begin(b2g_graph_t* g, int source, int send_capacity) {
+  if (!g || !g->partitioned || source < 0 || source >= g->pt.n_global || send_capacity < 1)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_begin: bad arguments");
+  return guarded([&] {
+    cudaStream_t st = g->ws.stream;
+    auto& S = g->part;
+    S.ensure(g->pt, send_capacity);
+    g->part_deg.ensure(2);
+    const int sms = device_info_t::get().sm_count;
+    const int sent_words = (g->pt.n_global + 31) / 32;
+    part_reset_kernel<<<sms * 8, 256, 0, st>>>(g->pt, source, S.dist.ptr, S.visited.ptr, S.sent.ptr,
+                                                sent_words, S.q[0].ptr, S.counts.ptr);
+    part_seed_kernel<<<1, 1, 0, st>>>(g->pt, source, S.dist.ptr, S.visited.ptr);
+    B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(S.overflow.ptr, 0, sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(g->part_deg.ptr, 0, 16, st));
+    g->ws.launches += 2;
+    S.cur = 0;
+    S.frontier_is_bitmap = false;
+    g->part_ctrl = nullptr;
+    B2G_CHECK(cudaStreamSynchronize(st));
+    return 0;
+  });
+}
+
+int b2g_part_bfs_topdown(b2g_graph_t* g, int level, const b2g_options_t* opt, int* send_counts,
+                         unsigned long long* edges_touched) {
+  if (!g || !g->partitioned || !send_counts)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_topdown: bad arguments");
+  return guarded([&] {
+    b2g_options_t o = resolved(opt);
+    cudaStream_t st = g->ws.stream;
+    auto& S = g->part;
+    const int sms = device_info_t::get().sm_count;
+    if (S.frontier_is_bitmap) {  // bitmap -> queue
+      B2G_CHECK(cudaMemsetAsync(S.counts.ptr + S.cur, 0, sizeof(int), st));
+      bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(S.fbm.ptr, S.local_words(), S.q[S.cur].ptr,
+                                                      S.counts.ptr + S.cur);
+      g->ws.launches += 1;
+      S.frontier_is_bitmap = false;
+    }
+    const int nxt = S.cur ^ 1;
+    B2G_CHECK(cudaMemsetAsync(S.counts.ptr + nxt, 0, sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
+    part_claim_op op{g->pt,       S.visited.ptr,  S.sent.ptr,        S.dist.ptr, level + 1,
+                     S.send_buf.ptr, S.send_count.ptr, S.send_cap, S.overflow.ptr};
+    ctrl_t* c = nullptr;
+    launch_advance<advance_output_t::vertices, true, false>(
+        g->ws, g->view, S.q[S.cur].ptr, S.counts.ptr + S.cur, g->pt.n_local, S.q[nxt].ptr,
+        S.counts.ptr + nxt, g->pt.n_local, op, to_launch(o), &c);
+    g->part_ctrl = c;
+    part_feedback_kernel<<<1, 1, 0, st>>>(S.counts.ptr + nxt, c, S.send_count.ptr, S.overflow.ptr,
+                                          g->pt.nparts, S.h_fb);
+    g->ws.launches += 1;
+    B2G_CHECK(cudaStreamSynchronize(st));
+    if (S.h_fb->overflow)
+      return fail(B2G_ERR_OVERFLOW, "partitioned bfs: send buffer or frontier overflow");
+    for (int i = 0; i < g->pt.nparts; ++i)
+      send_counts[i] = S.h_fb->send_count[i];
+    if (edges_touched)
+      *edges_touched = S.h_fb->edges;
+    g->part_level_dir = 0;
+    return 0;
+  });
+}
+
+int b2g_part_bfs_send_buffer(b2g_graph_t* g, int** send_buf, int* send_capacity) {
+  if (!g || !g->partitioned || !g->part.send_buf.ptr)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_send_buffer: call b2g_part_bfs_begin first");
+  if (send_buf)
+    *send_buf = g->part.send_buf.ptr;
+  if (send_capacity)
+    *send_capacity = g->part.send_cap;
+  return 0;
+}
+
+int b2g_part_bfs_claim(b2g_graph_t* g, int level, const int* recv, int n_recv) {
+  if (!g || !g->partitioned || n_recv < 0 || (n_recv && !recv))
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_claim: bad arguments");
+  return guarded([&] {
+    if (n_recv == 0)
+      return 0;
+    auto& S = g->part;
+    const int nxt = S.cur ^ 1;
+    int grid = (n_recv + 255) / 256;
+    const int cap = device_info_t::get().sm_count * 8;
+    part_claim_received_kernel<<<grid < cap ? grid : cap, 256, 0, g->ws.stream>>>(
+        g->pt, recv, n_recv, S.visited.ptr, S.dist.ptr, level + 1, g->view.row_offsets, S.q[nxt].ptr,
+        S.counts.ptr + nxt, g->part_deg.ptr);
+    g->ws.launches += 1;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_bfs_frontier_bitmap(b2g_graph_t* g, unsigned* out) {
+  if (!g || !g->partitioned || !out)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_frontier_bitmap: bad arguments");
+  return guarded([&] {
+    auto& S = g->part;
+    cudaStream_t st = g->ws.stream;
+    const size_t bytes = sizeof(unsigned) * static_cast<size_t>(S.words_per_rank());
+    if (S.frontier_is_bitmap) {
+      B2G_CHECK(cudaMemcpyAsync(out, S.fbm.ptr, bytes, cudaMemcpyDeviceToDevice, st));
+    } else {
+      B2G_CHECK(cudaMemsetAsync(out, 0, bytes, st));
+      part_queue_to_bitmap_kernel<<<device_info_t::get().sm_count * 4, 256, 0, st>>>(
+          S.q[S.cur].ptr, S.counts.ptr + S.cur, out);
+      g->ws.launches += 1;
+    }
+    B2G_CHECK(cudaStreamSynchronize(st));
+    return 0;
+  });
+}
+
+int b2g_part_bfs_bottomup(b2g_graph_t* g, int level, const unsigned* frontier_all,
+                          unsigned long long* edges_touched) {
+  if (!g || !g->partitioned || !frontier_all)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_bottomup: bad arguments");
+  return guarded([&] {
+    auto& S = g->part;
+    cudaStream_t st = g->ws.stream;
+    build_transpose(g);  // symmetric graphs alias the CSR
+    ctrl_t* c = g->ws.next_ctrl();
+    B2G_CHECK(cudaMemsetAsync(S.counts.ptr + 2, 0, sizeof(int), st));
+    // padding words of the next map (beyond local_words) must stay clear for the all-gather
+    B2G_CHECK(cudaMemsetAsync(S.nbm.ptr, 0, sizeof(unsigned) * S.words_per_rank(), st));
+    part_bottom_up_kernel<256, 8><<<device_info_t::get().sm_count * 8, 256, 0, st>>>(
+        g->pt, g->t_view, S.words_per_rank(), S.visited.ptr, frontier_all, S.nbm.ptr, S.dist.ptr,
+        level + 1, c, S.counts.ptr + 2);
+    g->part_ctrl = c;
+    part_feedback_kernel<<<1, 1, 0, st>>>(S.counts.ptr + 2, c, S.send_count.ptr, S.overflow.ptr, 0,
+                                          S.h_fb);
+    g->ws.launches += 2;
+    B2G_CHECK(cudaStreamSynchronize(st));
+    if (edges_touched)
+      *edges_touched = S.h_fb->edges;
+    g->part_level_dir = 1;
+    return 0;
+  });
+}
+
+int b2g_part_bfs_end_level(b2g_graph_t* g, long long* n_frontier, long long* frontier_degree) {
+  if (!g || !g->partitioned)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_end_level: bad arguments");
+  return guarded([&] {
+    auto& S = g->part;
+    cudaStream_t st = g->ws.stream;
+    unsigned long long extra = 0;
+    int count = 0;
+    if (g->part_level_dir == 1) {  // bottom-up produced a bitmap
+      unsigned* t = S.fbm.ptr;
+      std::swap(S.fbm.ptr, S.nbm.ptr);
+      std::swap(S.fbm.cap, S.nbm.cap);
+      (void)t;
+      S.frontier_is_bitmap = true;
+      B2G_CHECK(cudaMemcpyAsync(&count, S.counts.ptr + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    } else {
+      S.cur ^= 1;
+      S.frontier_is_bitmap = false;
+      B2G_CHECK(cudaMemcpyAsync(&count, S.counts.ptr + S.cur, sizeof(int), cudaMemcpyDeviceToHost, st));
+      B2G_CHECK(cudaMemcpyAsync(&extra, g->part_deg.ptr, 8, cudaMemcpyDeviceToHost, st));
+    }
+    unsigned long long ds = 0;
+    if (g->part_ctrl)
+      B2G_CHECK(cudaMemcpyAsync(&ds, &g->part_ctrl->deg_sum, 8, cudaMemcpyDeviceToHost, st));
+    B2G_CHECK(cudaStreamSynchronize(st));
+    B2G_CHECK(cudaMemsetAsync(g->part_deg.ptr, 0, 8, st));
+    g->part_ctrl = nullptr;
+    if (n_frontier)
+      *n_frontier = count;
+    if (frontier_degree)
+      *frontier_degree = static_cast<long long>(ds + extra);
+    return 0;
+  });
+}
+
+int b2g_part_bfs_distances(b2g_graph_t* g, int* distances, int loc) {
+  if (!g || !g->partitioned || !distances)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_distances: bad arguments");
+  return guarded([&] {
+    B2G_CHECK(cudaMemcpyAsync(distances, g->part.dist.ptr, sizeof(int) * static_cast<size_t>(g->pt.n_local),
+                              loc == B2G_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                              g->ws.stream));
+    B2G_CHECK(cudaStreamSynchronize(g->ws.stream));
     return 0;
   });
 }

@@ -1,0 +1,374 @@
+"""Multi-GPU BFS: 1-D (cyclic) vertex partition, one process per GPU, per-level frontier exchange over
+NCCL (``torch.distributed`` is the plumbing; the per-rank work is the sm_100a kernels behind
+``b2g_part_*`` in ``include/gunrock_b200.h``).
+
+The reference has no multi-GPU execution (``advance``/``filter`` throw for ``context.size() != 1``,
+``include/gunrock/framework/operators/advance/advance.hxx:129-132``); its only multi-device artefact is
+``gcuda::multi_context_t`` (``include/gunrock/cuda/context.hxx:146-216``).  This module is the design of
+SURVEY.md section 8e:
+
+* top-down level: local advance; neighbours owned by a peer are forwarded once (a per-rank "sent"
+  bitmap), grouped by owner; ``all_to_all_single`` of the counts, then of the ids; owners claim.
+* bottom-up level: ``all_gather`` of the frontier bitmap (V/8 bytes in total), purely local sweep.
+* direction / termination: ``all_reduce`` of (frontier vertices, frontier out-degree, edges inspected).
+
+The algorithm is written once (``_run_levels``) against two small interfaces so the same code runs
+(a) one rank per process over torch.distributed, (b) several simulated ranks in one process (single
+GPU tests), and (c) on CPU under gloo with a numpy stand-in engine (tests only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import (DEVICE, HOST, GunrockB200Error, _check, _Options, advance_direction_t, lib,
+               options_t)
+
+
+def _bind():
+    L = lib()
+    if getattr(L, "_mg_bound", False):
+        return L
+    vp, ip = C.c_void_p, C.c_int
+    L.b2g_graph_create_rmat_part.argtypes = [ip, C.c_longlong, C.c_ulonglong, ip, ip, ip, C.POINTER(vp)]
+    L.b2g_graph_create_csr_part.argtypes = [ip, ip, ip, ip, vp, vp, ip, ip, C.POINTER(vp)]
+    L.b2g_part_info.argtypes = [vp] + [C.POINTER(ip)] * 5
+    L.b2g_part_bfs_begin.argtypes = [vp, ip, ip]
+    L.b2g_part_bfs_topdown.argtypes = [vp, ip, C.POINTER(_Options), C.POINTER(ip), C.POINTER(C.c_ulonglong)]
+    L.b2g_part_bfs_send_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(ip)]
+    L.b2g_part_bfs_claim.argtypes = [vp, ip, vp, ip]
+    L.b2g_part_bfs_frontier_bitmap.argtypes = [vp, vp]
+    L.b2g_part_bfs_bottomup.argtypes = [vp, ip, vp, C.POINTER(C.c_ulonglong)]
+    L.b2g_part_bfs_end_level.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.b2g_part_bfs_distances.argtypes = [vp, vp, ip]
+    L.b2g_graph_destroy.argtypes = [vp]
+    L._mg_bound = True
+    return L
+
+
+def owner_of(v, nparts: int):
+    return v % nparts
+
+
+def local_of(v, nparts: int):
+    return v // nparts
+
+
+def rows_of(n_global: int, nparts: int, part: int) -> int:
+    return (n_global - part + nparts - 1) // nparts
+
+
+def partition_csr(ro: np.ndarray, ci: np.ndarray, nparts: int, part: int):
+    """Rank ``part``'s share of a global CSR: its rows (cyclic), global column ids."""
+    n = len(ro) - 1
+    rows = np.arange(part, n, nparts)
+    deg = (ro[rows + 1] - ro[rows]).astype(np.int64)
+    lro = np.zeros(len(rows) + 1, np.int64)
+    np.cumsum(deg, out=lro[1:])
+    take = np.repeat(ro[rows].astype(np.int64) - lro[:-1], deg) + np.arange(lro[-1])
+    return lro.astype(np.int32), np.ascontiguousarray(ci[take], np.int32)
+
+
+class PartitionedGraph:
+    """One rank's share of a 1-D partitioned graph, resident on the current CUDA device."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+        L = _bind()
+        v = [C.c_int() for _ in range(5)]
+        _check(L.b2g_part_info(self._h, *[C.byref(x) for x in v]), "b2g_part_info")
+        self.n_global, self.nparts, self.part, self.n_local, self.words_per_rank = (x.value for x in v)
+
+    @staticmethod
+    def rmat(scale: int, n_pairs: int, seed: int, nparts: int, part: int, mirror: bool = True):
+        h = C.c_void_p()
+        _check(_bind().b2g_graph_create_rmat_part(scale, n_pairs, seed, int(mirror), nparts, part, C.byref(h)),
+               "b2g_graph_create_rmat_part")
+        return PartitionedGraph(h.value)
+
+    @staticmethod
+    def from_global_csr(ro, ci, nparts: int, part: int, symmetric: bool = True):
+        lro, lci = partition_csr(np.asarray(ro), np.asarray(ci), nparts, part)
+        h = C.c_void_p()
+        _check(_bind().b2g_graph_create_csr_part(len(ro) - 1, nparts, part, len(lci), lro.ctypes.data,
+                                                 lci.ctypes.data if len(lci) else None, HOST, int(symmetric),
+                                                 C.byref(h)), "b2g_graph_create_csr_part")
+        return PartitionedGraph(h.value)
+
+    def close(self):
+        if self._h:
+            _bind().b2g_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaRankEngine:
+    """The per-rank steps, on the GPU, through the C ABI."""
+
+    def __init__(self, G: PartitionedGraph, options: Optional[options_t] = None, send_capacity: int = 0):
+        import torch
+        self.torch = torch
+        self.G = G
+        self.L = _bind()
+        self.opt = (options or options_t())._c()
+        self.nparts, self.part = G.nparts, G.part
+        self.n_global, self.n_local, self.words_per_rank = G.n_global, G.n_local, G.words_per_rank
+        # a peer can be sent at most the vertices it owns, once each
+        self.send_capacity = send_capacity or (rows_of(G.n_global, G.nparts, 0) + 64)
+        self._send_view = None
+
+    def begin(self, source: int):
+        _check(self.L.b2g_part_bfs_begin(self.G._h, int(source), int(self.send_capacity)), "b2g_part_bfs_begin")
+        buf, cap = C.c_void_p(), C.c_int()
+        _check(self.L.b2g_part_bfs_send_buffer(self.G._h, C.byref(buf), C.byref(cap)), "b2g_part_bfs_send_buffer")
+        if getattr(self, "_send_ptr", None) != buf.value:
+            self._send_view = None
+        self._send_ptr, self._cap = buf.value, cap.value
+        self._bitmap = self.torch.empty(self.words_per_rank, dtype=self.torch.int32, device="cuda")
+
+    def topdown(self, level: int):
+        counts = (C.c_int * self.nparts)()
+        e = C.c_ulonglong()
+        _check(self.L.b2g_part_bfs_topdown(self.G._h, level, C.byref(self.opt), counts, C.byref(e)),
+               "b2g_part_bfs_topdown")
+        return list(counts), int(e.value)
+
+    def send_rows(self, counts: Sequence[int]):
+        """The packed send tensor: for every owner, its first counts[o] ids, concatenated."""
+        torch = self.torch
+        if self._send_view is None:   # zero-copy torch view of the library's [nparts, cap] buffer
+            self._send_view = torch.as_tensor(_DevArray(self._send_ptr, (self.nparts, self._cap)), device="cuda")
+        rows = [self._send_view[o, :n] for o, n in enumerate(counts) if n]
+        return torch.cat(rows) if rows else self.empty_ids(0)
+
+    def claim(self, level: int, recv):
+        n = int(recv.numel())
+        if n:
+            self.torch.cuda.current_stream().synchronize()   # recv was produced on torch's stream
+            _check(self.L.b2g_part_bfs_claim(self.G._h, level, recv.data_ptr(), n), "b2g_part_bfs_claim")
+
+    def frontier_bitmap(self):
+        _check(self.L.b2g_part_bfs_frontier_bitmap(self.G._h, self._bitmap.data_ptr()), "b2g_part_bfs_frontier_bitmap")
+        return self._bitmap
+
+    def bottomup(self, level: int, frontier_all) -> int:
+        self.torch.cuda.current_stream().synchronize()       # the all-gather ran on torch's stream
+        e = C.c_ulonglong()
+        _check(self.L.b2g_part_bfs_bottomup(self.G._h, level, frontier_all.data_ptr(), C.byref(e)),
+               "b2g_part_bfs_bottomup")
+        return int(e.value)
+
+    def end_level(self):
+        n, m = C.c_longlong(), C.c_longlong()
+        _check(self.L.b2g_part_bfs_end_level(self.G._h, C.byref(n), C.byref(m)), "b2g_part_bfs_end_level")
+        return int(n.value), int(m.value)
+
+    def distances(self):
+        d = self.torch.empty(self.n_local, dtype=self.torch.int32, device="cuda")
+        _check(self.L.b2g_part_bfs_distances(self.G._h, d.data_ptr(), DEVICE), "b2g_part_bfs_distances")
+        return d
+
+    def empty_ids(self, n: int):
+        return self.torch.empty(max(n, 1), dtype=self.torch.int32, device="cuda")[:n]
+
+
+class _DevArray:
+    """__cuda_array_interface__ wrapper so torch can view device memory owned by the C library."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+# ---------------------------------------------------------------------------------------------
+# communicators
+# ---------------------------------------------------------------------------------------------
+class TorchDistComm:
+    """One rank per process; NCCL on GPUs (gloo on CPU for the host-logic tests)."""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.backend = dist.get_backend(group)
+
+    def all_reduce_sum(self, values: Sequence[int], device):
+        t = self.torch.tensor(list(values), dtype=self.torch.int64, device=device)
+        self.dist.all_reduce(t, group=self.group)
+        return [int(x) for x in t.tolist()]
+
+    def exchange_ids(self, send, send_counts: Sequence[int], make_empty):
+        """all-to-all of variable-length int32 id lists (counts first, then the ids)."""
+        torch, dist = self.torch, self.dist
+        dev = send.device
+        sc = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
+        rc = torch.empty_like(sc)
+        if self.backend == "gloo":   # gloo has no all_to_all_single: counts via all_gather
+            allc = [torch.empty_like(sc) for _ in range(self.world)]
+            dist.all_gather(allc, sc, group=self.group)
+            rc = torch.stack(allc)[:, self.rank].contiguous()
+        else:
+            dist.all_to_all_single(rc, sc, group=self.group)
+        recv_counts = [int(x) for x in rc.tolist()]
+        recv = make_empty(int(sum(recv_counts)))
+        if self.backend == "gloo":
+            reqs, off_s, off_r = [], 0, 0
+            chunks_r = []
+            for p in range(self.world):
+                s = send[off_s:off_s + send_counts[p]]
+                off_s += send_counts[p]
+                r = recv[off_r:off_r + recv_counts[p]]
+                off_r += recv_counts[p]
+                if p == self.rank:
+                    r.copy_(s)
+                    continue
+                if send_counts[p]:
+                    reqs.append(dist.isend(s.contiguous(), p, group=self.group))
+                if recv_counts[p]:
+                    chunks_r.append((r, p))
+            for r, p in chunks_r:
+                tmp = torch.empty_like(r)
+                dist.recv(tmp, p, group=self.group)
+                r.copy_(tmp)
+            for q in reqs:
+                q.wait()
+        else:
+            dist.all_to_all_single(recv, send, output_split_sizes=recv_counts,
+                                   input_split_sizes=list(send_counts), group=self.group)
+        return recv
+
+    def all_gather_bitmap(self, local):
+        out = self.torch.empty(self.world * local.numel(), dtype=local.dtype, device=local.device)
+        self.dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out
+
+
+@dataclass
+class part_bfs_stats_t:
+    levels: int = 0
+    level_direction: List[int] = field(default_factory=list)
+    level_frontier: List[int] = field(default_factory=list)       # global
+    level_edges: List[int] = field(default_factory=list)          # global, inspected
+    edges_touched: int = 0
+    exchanged_ids: int = 0                                        # ids this rank sent
+
+
+def _decide(direction: int, level: int, bottom_up: bool, n_f: int, m_f: int, explored: int, n_global: int,
+            total_edges: int, alpha: float, beta: float) -> bool:
+    """Beamer's switch on GLOBAL counts (same rule as the single-GPU enactor, bfs.cuh)."""
+    if direction == advance_direction_t.forward or level == 0:
+        return False
+    if direction == advance_direction_t.backward:
+        return True
+    if not bottom_up:
+        return m_f > (total_edges - explored) / alpha
+    return not (n_f < n_global / beta)
+
+
+def bfs_rank(engine, comm, source: int, total_edges: int, direction: int = advance_direction_t.optimized,
+             alpha: float = 14.0, beta: float = 24.0):
+    """Run this rank's part of a partitioned BFS.  Returns (local distances, stats).
+    ``total_edges`` = global directed edge count (for the direction heuristic)."""
+    st = part_bfs_stats_t()
+    engine.begin(source)
+    dev = "cuda" if comm.backend != "gloo" else "cpu"
+    n_f, m_f, explored = 1, 0, 0
+    level, bottom_up = 0, False
+    while n_f > 0:
+        go_up = _decide(direction, level, bottom_up, n_f, m_f, explored, engine.n_global, total_edges, alpha, beta)
+        if level > 0:
+            explored += m_f
+        if go_up:
+            allbm = comm.all_gather_bitmap(engine.frontier_bitmap())
+            edges = engine.bottomup(level, allbm)
+        else:
+            counts, edges = engine.topdown(level)
+            send = engine.send_rows(counts)
+            recv = comm.exchange_ids(send, counts, engine.empty_ids)
+            engine.claim(level, recv)
+            st.exchanged_ids += int(sum(counts))
+        ln, lm = engine.end_level()
+        g = comm.all_reduce_sum([ln, lm, edges], dev)
+        st.level_direction.append(1 if go_up else 0)
+        st.level_frontier.append(n_f)
+        st.level_edges.append(g[2])
+        st.edges_touched += g[2]
+        if level == 0:
+            explored += g[2]
+        n_f, m_f = g[0], g[1]
+        bottom_up = go_up
+        level += 1
+    st.levels = level
+    return engine.distances(), st
+
+
+# ---------------------------------------------------------------------------------------------
+# several simulated ranks in ONE process (single-GPU tests of the multi-rank logic)
+# ---------------------------------------------------------------------------------------------
+def bfs_lockstep(engines: Sequence, source: int, total_edges: int,
+                 direction: int = advance_direction_t.optimized, alpha: float = 14.0, beta: float = 24.0):
+    """Same level loop, all ranks driven from one process; the 'collectives' are tensor copies."""
+    import torch
+    P = len(engines)
+    for e in engines:
+        e.begin(source)
+    st = part_bfs_stats_t()
+    n_f, m_f, explored, level, bottom_up = 1, 0, 0, 0, False
+    while n_f > 0:
+        go_up = _decide(direction, level, bottom_up, n_f, m_f, explored, engines[0].n_global, total_edges, alpha, beta)
+        if level > 0:
+            explored += m_f
+        edges = 0
+        if go_up:
+            allbm = torch.cat([e.frontier_bitmap().clone() for e in engines])
+            for e in engines:
+                edges += e.bottomup(level, allbm)
+        else:
+            sends, counts = [], []
+            for e in engines:
+                c, ed = e.topdown(level)
+                edges += ed
+                counts.append(c)
+                sends.append(e.send_rows(c))
+            for r, e in enumerate(engines):
+                parts = []
+                for p in range(P):
+                    off = sum(counts[p][:r])
+                    parts.append(sends[p][off:off + counts[p][r]])
+                recv = torch.cat(parts) if parts else e.empty_ids(0)
+                e.claim(level, recv.contiguous())
+            st.exchanged_ids += sum(sum(c) for c in counts)
+        tot_n = tot_m = 0
+        for e in engines:
+            ln, lm = e.end_level()
+            tot_n += ln
+            tot_m += lm
+        st.level_direction.append(1 if go_up else 0)
+        st.level_frontier.append(n_f)
+        st.level_edges.append(edges)
+        st.edges_touched += edges
+        if level == 0:
+            explored += edges
+        n_f, m_f, bottom_up = tot_n, tot_m, go_up
+        level += 1
+    st.levels = level
+    return [e.distances() for e in engines], st
+
+
+def gather_distances(local_dists: Sequence[np.ndarray], n_global: int) -> np.ndarray:
+    """Interleave the ranks' slices back into global vertex order (v -> rank v % P, row v // P)."""
+    P = len(local_dists)
+    out = np.empty(n_global, np.int32)
+    for r, d in enumerate(local_dists):
+        out[r::P] = np.asarray(d)[:rows_of(n_global, P, r)]
+    return out

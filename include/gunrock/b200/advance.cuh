@@ -21,6 +21,9 @@
  */
 #pragma once
 
+#include <type_traits>
+#include <utility>
+
 #include <gunrock/b200/ptx.cuh>
 #include <gunrock/b200/runtime.cuh>
 #include <gunrock/b200/scan.cuh>
@@ -30,6 +33,54 @@ namespace b200 {
 
 enum class advance_input_t { vertices, graph };
 enum class advance_output_t { vertices, edges, none };
+
+/**
+ * Optional two-phase protocol for edge functors.  A functor that also provides
+ *     token_t prefetch(int dst) const;                          // loads only, no side effects
+ *     bool    commit(int src, int dst, int edge, float w, token_t) const;
+ * lets the kernels issue the prefetches of several edges back to back (memory-level parallelism)
+ * before any of the dependent atomics.  Plain `bool operator()(src, dst, edge, w)` functors (user
+ * lambdas) are called as they are.
+ */
+template <typename Op, typename = void>
+struct op_traits {
+  static constexpr bool two_phase = false;
+  using token_t = int;
+};
+template <typename Op>
+struct op_traits<Op, std::void_t<decltype(&Op::commit)>> {
+  static constexpr bool two_phase = true;
+  using token_t = decltype(std::declval<const Op&>().prefetch(0));
+};
+template <typename Op>
+__device__ __forceinline__ typename op_traits<Op>::token_t op_prefetch(const Op& op, int dst) {
+  if constexpr (op_traits<Op>::two_phase)
+    return op.prefetch(dst);
+  else
+    return 0;
+}
+template <typename Op>
+__device__ __forceinline__ bool op_commit(const Op& op, int src, int dst, int e, float w,
+                                          typename op_traits<Op>::token_t tok) {
+  if constexpr (op_traits<Op>::two_phase)
+    return op.commit(src, dst, e, w, tok);
+  else
+    return op(src, dst, e, w);
+}
+/// Optional `int emit_as(int dst) const`: the value stored in the output frontier for a kept
+/// vertex (the partitioned BFS stores local row ids while column indices are global ids).
+template <typename Op, typename = void>
+struct op_has_emit_as : std::false_type {};
+template <typename Op>
+struct op_has_emit_as<Op, std::void_t<decltype(&Op::emit_as)>> : std::true_type {};
+template <typename Op>
+__device__ __forceinline__ int op_emit(const Op& op, int dst) {
+  if constexpr (op_has_emit_as<Op>::value)
+    return op.emit_as(dst);
+  else
+    return dst;
+}
+constexpr int kBatch = 4;  // 32-edge chunks whose loads are issued back to back per warp
 
 /// Per-warp staging buffer: ballot-compacted appends, flushed with one global atomic.
 template <int kCap, bool kDegSum>
@@ -168,17 +219,30 @@ advance_binned_kernel(advance_params_t p, Op op) {
       int u = __shfl_sync(kFull, v, leader);
       if (lane == leader)
         deg = 0;
-      for (int off = 0; off < d; off += 32) {
-        int e = s + off + lane;
-        bool keep = false;
-        int nb = -1;
-        if (off + lane < d) {
-          nb = ld_stream(ci + e);
-          float w = (kWeights && vals) ? ld_stream(vals + e) : 1.0f;
-          keep = op(u, nb, e, w);
+      for (int off = 0; off < d; off += 32 * kBatch) {
+        int e[kBatch], nb[kBatch];
+        float w[kBatch];
+        bool valid[kBatch], keep[kBatch];
+        typename op_traits<Op>::token_t tok[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+          e[k] = s + off + k * 32 + lane;
+          valid[k] = off + k * 32 + lane < d;
+          nb[k] = valid[k] ? ld_stream(ci + e[k]) : -1;
+          w[k] = (kWeights && vals && valid[k]) ? ld_stream(vals + e[k]) : 1.0f;
         }
-        if (kOut != advance_output_t::none)
-          em.push(keep, kOut == advance_output_t::edges ? e : nb);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+          if (valid[k])
+            tok[k] = op_prefetch(op, nb[k]);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+          keep[k] = valid[k] && op_commit(op, u, nb[k], e[k], w[k], tok[k]);
+        if (kOut != advance_output_t::none) {
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k)
+            em.push(keep[k], kOut == advance_output_t::edges ? e[k] : op_emit(op, nb[k]));
+        }
       }
     }
     // -- thread bin: short rows packed by a warp scan ---------------------------------------
@@ -205,7 +269,7 @@ advance_binned_kernel(advance_params_t p, Op op) {
           keep = op(u, nb, e, w);
         }
         if (kOut != advance_output_t::none)
-          em.push(keep, kOut == advance_output_t::edges ? e : nb);
+          em.push(keep, kOut == advance_output_t::edges ? e : op_emit(op, nb));
       }
       __syncwarp();
     }
@@ -228,14 +292,14 @@ template <int kThreads, int kChunk, advance_output_t kOut, bool kDegSum, bool kW
 __global__ void __launch_bounds__(kThreads)
 advance_hub_kernel(advance_params_t p, Op op) {
   constexpr int kWarps = kThreads / 32;
-  constexpr int kBatch = 512;        // hub descriptors resident in shared memory at once
+  constexpr int kHubs = 512;         // hub descriptors resident in shared memory at once
   constexpr int kSlab = kChunk + 4;  // +4: slabs start at a 16-byte aligned column index
   static_assert(kChunk % 4 == 0, "slab size must keep 16-byte granularity");
   __shared__ int s_emit[kWarps][kEmitCap];
-  __shared__ int s_start[kBatch];
-  __shared__ int s_end[kBatch];
-  __shared__ int s_vertex[kBatch];
-  __shared__ int s_prefix[kBatch + 1];
+  __shared__ int s_start[kHubs];
+  __shared__ int s_end[kHubs];
+  __shared__ int s_vertex[kHubs];
+  __shared__ int s_prefix[kHubs + 1];
   __shared__ int s_scan[kWarps];
   __shared__ __align__(16) int s_idx[2][kSlab];
   __shared__ __align__(16) float s_val[kWeights ? 2 : 1][kWeights ? kSlab : 4];
@@ -288,8 +352,8 @@ advance_hub_kernel(advance_params_t p, Op op) {
   };
 
   int rot = 0;  // slabs dealt by earlier batches: keeps the round-robin deal balanced
-  for (int b0 = 0; b0 < n_hubs; b0 += kBatch) {
-    const int nb = min(kBatch, n_hubs - b0);
+  for (int b0 = 0; b0 < n_hubs; b0 += kHubs) {
+    const int nb = min(kHubs, n_hubs - b0);
     // descriptors + exclusive slab-count prefix of this batch
     int carry = 0;
     for (int i0 = 0; i0 < nb; i0 += kThreads) {
@@ -342,26 +406,42 @@ advance_hub_kernel(advance_params_t p, Op op) {
         mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
         phase_bits ^= 1u << buf;
       }
-      for (int i0 = 0; i0 < cnt; i0 += kThreads) {
-        int i = i0 + threadIdx.x;
-        bool keep = false;
-        int nbv = -1;
-        int e = e0 + i;
-        if (i < cnt) {
-          float w = 1.0f;
-          if (tma) {
-            nbv = s_idx[buf][e - a0];
-            if (use_vals)
-              w = s_val[kWeights ? buf : 0][e - a0];
-          } else {
-            nbv = ld_stream(ci + e);
-            if (use_vals)
-              w = ld_stream(vals + e);
+      for (int i0 = 0; i0 < cnt; i0 += kThreads * kBatch) {
+        int e[kBatch], nbv[kBatch];
+        float w[kBatch];
+        bool valid[kBatch], keep[kBatch];
+        typename op_traits<Op>::token_t tok[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+          int i = i0 + k * kThreads + threadIdx.x;
+          e[k] = e0 + i;
+          valid[k] = i < cnt;
+          nbv[k] = -1;
+          w[k] = 1.0f;
+          if (valid[k]) {
+            if (tma) {
+              nbv[k] = s_idx[buf][e[k] - a0];
+              if (use_vals)
+                w[k] = s_val[kWeights ? buf : 0][e[k] - a0];
+            } else {
+              nbv[k] = ld_stream(ci + e[k]);
+              if (use_vals)
+                w[k] = ld_stream(vals + e[k]);
+            }
           }
-          keep = op(u, nbv, e, w);
         }
-        if (kOut != advance_output_t::none)
-          em.push(keep, kOut == advance_output_t::edges ? e : nbv);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+          if (valid[k])
+            tok[k] = op_prefetch(op, nbv[k]);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+          keep[k] = valid[k] && op_commit(op, u, nbv[k], e[k], w[k], tok[k]);
+        if (kOut != advance_output_t::none) {
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k)
+            em.push(keep[k], kOut == advance_output_t::edges ? e[k] : op_emit(op, nbv[k]));
+        }
       }
       __syncthreads();  // all reads of s_idx[buf] retire before it is refilled
       buf ^= 1;
@@ -419,7 +499,7 @@ advance_thread_mapped_kernel(advance_params_t p, Op op) {
         keep = op(v, nb, e, w);
       }
       if (kOut != advance_output_t::none)
-        em.push(keep, kOut == advance_output_t::edges ? e : nb);
+        em.push(keep, kOut == advance_output_t::edges ? e : op_emit(op, nb));
     }
   }
   if (kOut != advance_output_t::none)
@@ -564,27 +644,42 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
         else
           b = mid;
       }
-      for (int r0 = w_begin; r0 < w_end; r0 += 32) {
-        // invariant: s_rank[a] <= r0 <= s_rank[a+1].  Row starts of rows a+1.. that fall inside
-        // [r0, r0+32) become bits (strictly increasing starts => at most 32 of them).
-        int nxt = s_rank[min(a + 1 + lane, nrows + 32)] - r0;
-        unsigned bit = (nxt >= 0 && nxt < 32) ? (1u << nxt) : 0u;
-        unsigned starts = __reduce_or_sync(kFull, bit);
-        int r = r0 + lane;
-        bool valid = r < w_end;
-        int row = a + __popc(starts & (0xffffffffu >> (31 - lane)));
-        bool keep = false;
-        int nb = -1, e = 0;
-        if (valid) {
-          int u = s_vert[row];
-          e = s_base[row] + r;  // s_base holds (CSR offset - first rank) of the row
-          nb = ld_stream(ci + e);
-          float w = (kWeights && vals) ? ld_stream(vals + e) : 1.0f;
-          keep = op(u, nb, e, w);
+      for (int r0 = w_begin; r0 < w_end; r0 += 32 * kBatch) {
+        int row[kBatch], e[kBatch], nb[kBatch], u[kBatch];
+        float w[kBatch];
+        bool valid[kBatch], keep[kBatch];
+        typename op_traits<Op>::token_t tok[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+          // invariant: s_rank[a] <= rk <= s_rank[a+1].  Row starts of rows a+1.. that fall inside
+          // [rk, rk+32) become bits (strictly increasing starts => at most 32 of them).
+          const int rk = r0 + 32 * k;
+          int nxt = s_rank[min(a + 1 + lane, nrows + 32)] - rk;
+          unsigned bit = (nxt >= 0 && nxt < 32) ? (1u << nxt) : 0u;
+          unsigned starts = __reduce_or_sync(kFull, bit);
+          row[k] = min(a + __popc(starts & (0xffffffffu >> (31 - lane))), nrows - 1);
+          valid[k] = rk + lane < w_end;
+          a += __popc(starts);
         }
-        if (kOut != advance_output_t::none)
-          em.push(keep, kOut == advance_output_t::edges ? e : nb);
-        a += __popc(starts);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+          u[k] = s_vert[row[k]];
+          e[k] = s_base[row[k]] + r0 + 32 * k + lane;  // s_base = CSR offset - first rank of the row
+          nb[k] = valid[k] ? ld_stream(ci + e[k]) : -1;
+          w[k] = (kWeights && vals && valid[k]) ? ld_stream(vals + e[k]) : 1.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+          if (valid[k])
+            tok[k] = op_prefetch(op, nb[k]);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+          keep[k] = valid[k] && op_commit(op, u[k], nb[k], e[k], w[k], tok[k]);
+        if (kOut != advance_output_t::none) {
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k)
+            em.push(keep[k], kOut == advance_output_t::edges ? e[k] : op_emit(op, nb[k]));
+        }
       }
     }
   }
@@ -603,15 +698,13 @@ struct advance_launch_t {
   lb_t lb = lb_t::block_mapped;
   int hub_threshold = 4096;  // rows >= this go to the grid (TMA slab) bin; block_mapped only
   int ctas_per_sm = 8;
+  /// frontiers whose out-degree sum is below this take the single-kernel path (no scan, no hub
+  /// pass): fixed per-level cost matters more than balance there.
+  long long small_frontier_edges = 1 << 12;
 };
 
-static __global__ void place_scan_total_kernel(int* scanned, const int* n_ptr, int n_fixed,
-                                        const int* total) {
-  int n = n_ptr ? *n_ptr : n_fixed;
-  scanned[n] = *total;
-}
-
-/// Degree scan of the frontier for merge_path (replaces helpers.hxx:41-111): scanned[0..n].
+/// Degree scan of the frontier for merge_path (replaces helpers.hxx:41-111): scanned[0..n],
+/// scanned[n] = total, all written by the one look-back scan kernel.
 inline const int* frontier_degree_scan(workspace_t& ws,
                                        const csr_view_t& g,
                                        const int* in,
@@ -624,10 +717,7 @@ inline const int* frontier_degree_scan(workspace_t& ws,
     return v >= 0 ? ro[v + 1] - ro[v] : 0;
   };
   auto emit = [=] __device__(int i, int excl, int) { scanned[i] = excl; };
-  int* total_slot = scanned + n_upper_bound + 1;
-  lookback_scan(ws, in_count, 0, n_upper_bound, value, emit, total_slot);
-  place_scan_total_kernel<<<1, 1, 0, ws.stream>>>(scanned, in_count, 0, total_slot);
-  ws.launches += 1;
+  lookback_scan(ws, in_count, 0, n_upper_bound, value, emit, nullptr, scanned);
   return scanned;
 }
 
@@ -692,7 +782,7 @@ inline void launch_advance(workspace_t& ws,
   } else {
     p.ctrl = ws.next_ctrl();
     p.hub_threshold = cfg.hub_threshold < 32 ? 32 : cfg.hub_threshold;
-    p.hub_capacity = g.n_edges / p.hub_threshold + 1024;
+    p.hub_capacity = cfg.hub_threshold < (1 << 30) ? g.n_edges / p.hub_threshold + 1024 : 16;
     p.hubs = ws.hubs.ensure(static_cast<size_t>(p.hub_capacity));
     p.tma_ok = aligned16(g.column_indices) && (!kWeights || !g.values || aligned16(g.values));
     if (graph_in)
@@ -701,8 +791,11 @@ inline void launch_advance(workspace_t& ws,
     else
       advance_binned_kernel<kThreads, advance_input_t::vertices, kOut, kDegSum, kWeights>
           <<<grid, kThreads, 0, ws.stream>>>(p, op);
-    advance_hub_kernel<kThreads, 2048, kOut, kDegSum, kWeights>
-        <<<sms * 2, kThreads, 0, ws.stream>>>(p, op);
+    if (cfg.hub_threshold < (1 << 30))
+      advance_hub_kernel<kThreads, 2048, kOut, kDegSum, kWeights>
+          <<<sms * 2, kThreads, 0, ws.stream>>>(p, op);
+    else
+      ws.launches -= 1;
   }
   ws.launches += (cfg.lb == lb_t::thread_mapped) ? 1 : 2;
   if (ctrl_out)

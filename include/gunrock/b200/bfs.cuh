@@ -35,6 +35,20 @@ struct bfs_claim_op {
     dist[dst] = next_level;
     return true;
   }
+  /// two-phase protocol (advance.cuh op_traits): the probe is a pure cached load ...
+  __device__ __forceinline__ unsigned prefetch(int dst) const {
+    return ld_cached(visited + (dst >> 5));
+  }
+  /// ... and only edges whose probe saw a clear bit pay for the atomic.
+  __device__ __forceinline__ bool commit(int, int dst, int, float, unsigned word) const {
+    const unsigned bit = 1u << (dst & 31);
+    if (word & bit)
+      return false;
+    if (atomicOr(visited + (dst >> 5), bit) & bit)
+      return false;
+    dist[dst] = next_level;
+    return true;
+  }
 };
 
 /// The reference's own functor (bfs.hxx:105-128), kept selectable for like-for-like runs.
@@ -284,22 +298,16 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   int level = 0;
   bool bottom_up = false;      // representation of the current frontier: queue (false) / bitmap
   long long n_f = 1;           // frontier vertices
-  unsigned long long m_f = 0;  // frontier out-degree sum (unknown for the source until probed)
+  // frontier out-degree sum.  Not known for the source (probing it would cost a host round trip);
+  // level 0 always runs top-down on the small path and reports it.
+  unsigned long long m_f = 0;
   unsigned long long explored = 0;
-  {
-    // degree of the source, for the first direction decision
-    int ro2[2];
-    B2G_CHECK(cudaMemcpyAsync(ro2, out_g.row_offsets + source, 2 * sizeof(int),
-                              cudaMemcpyDeviceToHost, st));
-    B2G_CHECK(cudaStreamSynchronize(st));
-    m_f = static_cast<unsigned long long>(ro2[1] - ro2[0]);
-  }
   unsigned* fbm = sc.fbm.ptr;
   unsigned* nbm = sc.nbm.ptr;
   while (n_f > 0) {
     // ---- choose direction for this level (Beamer et al.) --------------------------------
     bool want_bottom_up = bottom_up;
-    if (can_pull) {
+    if (can_pull && level > 0) {
       unsigned long long m_u = static_cast<unsigned long long>(out_g.n_edges) - explored;
       if (cfg.direction == 1)
         want_bottom_up = level > 0;
@@ -308,7 +316,8 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       else
         want_bottom_up = !(static_cast<double>(n_f) < static_cast<double>(V) / cfg.beta);
     }
-    explored += m_f;
+    if (level > 0)
+      explored += m_f;
     if (level < 64)
       B2G_CHECK(cudaEventRecord(sc.ev[2 * level], st));
     ctrl_t* ca = nullptr;
@@ -341,16 +350,23 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       int nxt = cur ^ 1;
       B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
       int ub = static_cast<int>(n_f < V ? n_f : V);
+      advance_launch_t lcfg = cfg.advance;
+      if (level == 0) {
+        lcfg.lb = lb_t::block_mapped;  // one row of unknown length: binned kernel + hub slabs
+      } else if (static_cast<long long>(m_f) < cfg.advance.small_frontier_edges) {
+        lcfg.lb = lb_t::block_mapped;  // one kernel: warp/thread bins only
+        lcfg.hub_threshold = 1 << 30;
+      }
       if (cfg.use_atomic_min_op) {
         bfs_atomic_min_op op{dist, level + 1};
         launch_advance<advance_output_t::vertices, true, false>(
             ws, out_g, sc.q[cur].ptr, sc.counts.ptr + cur, ub, sc.q[nxt].ptr,
-            sc.counts.ptr + nxt, V, op, cfg.advance, &ca);
+            sc.counts.ptr + nxt, V, op, lcfg, &ca);
       } else {
         bfs_claim_op op{sc.visited.ptr, dist, level + 1};
         launch_advance<advance_output_t::vertices, true, false>(
             ws, out_g, sc.q[cur].ptr, sc.counts.ptr + cur, ub, sc.q[nxt].ptr,
-            sc.counts.ptr + nxt, V, op, cfg.advance, &ca);
+            sc.counts.ptr + nxt, V, op, lcfg, &ca);
       }
       cur = nxt;
       count_ptr = sc.counts.ptr + cur;
@@ -364,6 +380,8 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       throw std::runtime_error("bfs: output frontier overflow");
     if (levels)
       levels->push_back({want_bottom_up ? 1 : 0, static_cast<int>(n_f), m_f, sc.h_fb->edges});
+    if (level == 0)
+      explored += sc.h_fb->edges;  // the source's degree, learnt from the level it just ran
     n_f = sc.h_fb->count;
     m_f = sc.h_fb->deg_sum;
     ++level;

@@ -1,0 +1,343 @@
+/**
+ * @file bfs_partitioned.cuh
+ * @brief Per-rank kernels of the multi-GPU BFS: 1-D vertex partition, one process per GPU, the
+ * per-level remote-frontier exchange done by the host side with NCCL (torch.distributed
+ * all_to_all_single / all_gather / all_reduce over NVLink) -- gunrock_b200/multi_gpu.py.
+ *
+ * The reference has no multi-GPU execution at all (advance/filter throw for context.size() != 1,
+ * SURVEY.md F6); this is new design following SURVEY.md section 8e.
+ *
+ * Partition: CYCLIC.  Global vertex v lives on rank v % P at local row v / P.  That is the
+ * contiguous-block partition of the fixed relabelling pi(v) = (v % P) * ceil(V/P) + v / P, and it
+ * spreads RMAT's low-id hubs evenly without a permutation array.  A rank stores the CSR rows of its
+ * vertices with GLOBAL column ids (and, for pull, the CSC rows -- the same arrays for a symmetric
+ * graph), its slice of `distances` and of the visited bitmap.
+ *
+ * Top-down level = the ordinary advance (any load balancer) with `part_claim_op`:
+ *   local neighbour  -> test-and-set in the local visited map, label, emit its LOCAL row id;
+ *   remote neighbour -> first time this rank sees it (a V-bit "sent" map, 8 MiB at scale 26):
+ *                       append it to the owner's send buffer (warp-aggregated per owner).
+ * After the exchange, `part_claim_received_kernel` claims the received ids on their owner.
+ * Bottom-up level = all-gather of the frontier bitmap (V/8 bytes total), then a purely local
+ * sweep (`part_bottom_up_kernel`) -- no all-to-all.
+ */
+#pragma once
+
+#include <gunrock/b200/advance.cuh>
+#include <gunrock/b200/bfs.cuh>
+
+namespace gunrock {
+namespace b200 {
+
+struct partition_t {
+  int nparts = 1;
+  int part = 0;
+  int shift = 0;        // log2(nparts) when nparts is a power of two, else -1
+  int n_global = 0;     // global vertex count
+  int n_local = 0;      // rows owned by this rank
+  __host__ __device__ __forceinline__ int owner(int v) const {
+    return shift >= 0 ? (v & (nparts - 1)) : (v % nparts);
+  }
+  __host__ __device__ __forceinline__ int local(int v) const {
+    return shift >= 0 ? (v >> shift) : (v / nparts);
+  }
+  __host__ __device__ __forceinline__ int global(int l) const { return l * nparts + part; }
+  /// rows owned by rank r
+  __host__ __device__ __forceinline__ int rows_of(int r) const {
+    return (n_global - r + nparts - 1) / nparts;
+  }
+  static partition_t make(int n_global, int nparts, int part) {
+    partition_t p;
+    p.nparts = nparts;
+    p.part = part;
+    p.n_global = n_global;
+    p.shift = -1;
+    for (int s = 0; s < 31; ++s)
+      if ((1 << s) == nparts)
+        p.shift = s;
+    p.n_local = p.rows_of(part);
+    return p;
+  }
+};
+
+/// Top-down edge functor of the partitioned BFS (two-phase protocol, see advance.cuh).
+struct part_claim_op {
+  partition_t pt;
+  unsigned* visited;   // local rows
+  unsigned* sent;      // global ids already forwarded by this rank
+  int* dist;           // local rows
+  int next_level;
+  int* send_buf;       // nparts x send_cap
+  int* send_count;     // nparts
+  int send_cap;
+  int* overflow;
+
+  __device__ __forceinline__ unsigned prefetch(int dst) const {
+    return pt.owner(dst) == pt.part ? ld_cached(visited + (pt.local(dst) >> 5))
+                                    : ld_cached(sent + (dst >> 5));
+  }
+  __device__ __forceinline__ bool commit(int, int dst, int, float, unsigned word) const {
+    const int own = pt.owner(dst);
+    if (own == pt.part) {
+      const int l = pt.local(dst);
+      const unsigned bit = 1u << (l & 31);
+      if (word & bit)
+        return false;
+      if (atomicOr(visited + (l >> 5), bit) & bit)
+        return false;
+      dist[l] = next_level;
+      return true;
+    }
+    const unsigned bit = 1u << (dst & 31);
+    if (word & bit)
+      return false;
+    if (atomicOr(sent + (dst >> 5), bit) & bit)
+      return false;
+    // warp-aggregated append to the owner's send buffer
+    const unsigned act = __activemask();
+    const unsigned grp = __match_any_sync(act, own);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (lane_id() == leader)
+      base = atomicAdd(send_count + own, __popc(grp));
+    base = __shfl_sync(grp, base, leader);
+    const int slot = base + __popc(grp & lanemask_lt());
+    if (slot < send_cap)
+      send_buf[static_cast<size_t>(own) * send_cap + slot] = dst;
+    else
+      *overflow = 1;
+    return false;
+  }
+  __device__ __forceinline__ bool operator()(int s, int d, int e, float w) const {
+    return commit(s, d, e, w, prefetch(d));
+  }
+  /// the local frontier holds LOCAL row ids
+  __device__ __forceinline__ int emit_as(int dst) const { return pt.local(dst); }
+};
+
+/// Claim ids received from peers (global ids owned by this rank) into the next local frontier.
+static __global__ void part_claim_received_kernel(partition_t pt, const int* __restrict__ recv,
+                                                  int n_recv, unsigned* visited, int* dist,
+                                                  int next_level, const int* __restrict__ ro,
+                                                  int* out, int* out_count,
+                                                  unsigned long long* deg_sum) {
+  const int lane = lane_id();
+  unsigned long long ds = 0;
+  for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < n_recv;
+       i0 += gridDim.x * blockDim.x) {
+    int i = i0 + lane;
+    bool won = false;
+    int l = 0;
+    if (i < n_recv) {
+      l = pt.local(recv[i]);
+      won = bitmap_test_and_set(visited, l);
+      if (won) {
+        dist[l] = next_level;
+        ds += static_cast<unsigned>(ro[l + 1] - ro[l]);
+      }
+    }
+    unsigned m = __ballot_sync(kFull, won);
+    if (m) {
+      int base = 0;
+      if (lane == 0)
+        base = atomicAdd(out_count, __popc(m));
+      base = __shfl_sync(kFull, base, 0);
+      if (won)
+        out[base + __popc(m & lanemask_lt())] = l;
+    }
+  }
+  ds = warp_sum(ds);
+  if (lane == 0 && ds)
+    atomicAdd(deg_sum, ds);
+}
+
+/// local queue (local row ids) -> local frontier bitmap
+static __global__ void part_queue_to_bitmap_kernel(const int* __restrict__ q,
+                                                   const int* __restrict__ count, unsigned* bm) {
+  const int n = *count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int l = q[i];
+    atomicOr(bm + (l >> 5), 1u << (l & 31));
+  }
+}
+
+/**
+ * @brief Bottom-up sweep over the rows this rank owns.  `frontier_all` is the all-gathered frontier
+ * bitmap, laid out rank-major: words [r * words_per_rank, (r+1) * words_per_rank) hold rank r's
+ * local rows.  Same structure as bfs_bottom_up_kernel (one warp per visited word).
+ */
+template <int kThreads, int kSerial>
+__global__ void __launch_bounds__(kThreads)
+part_bottom_up_kernel(partition_t pt, csr_view_t in, int words_per_rank,
+                      unsigned* __restrict__ visited, const unsigned* __restrict__ frontier_all,
+                      unsigned* __restrict__ next, int* dist, int next_level, ctrl_t* ctrl,
+                      int* next_count) {
+  const int lane = lane_id();
+  const int words = (pt.n_local + 31) / 32;
+  const int warps = (gridDim.x * kThreads) >> 5;
+  const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const int* __restrict__ ro = in.row_offsets;
+  const int* __restrict__ ci = in.column_indices;
+  auto in_frontier = [&](int u) -> bool {
+    int l = pt.local(u);
+    return (__ldg(frontier_all + pt.owner(u) * words_per_rank + (l >> 5)) >> (l & 31)) & 1u;
+  };
+  unsigned long long scanned = 0, found_deg = 0;
+  int found_cnt = 0;
+  for (int wi = gw; wi < words; wi += warps) {
+    const unsigned vis = visited[wi];
+    if (vis == 0xffffffffu) {
+      if (lane == 0)
+        next[wi] = 0;
+      continue;
+    }
+    const int v = (wi << 5) + lane;
+    bool searching = v < pt.n_local && !((vis >> lane) & 1u);
+    int start = 0, end = 0;
+    if (searching) {
+      start = ro[v];
+      end = ro[v + 1];
+    }
+    const int deg = end - start;
+    bool found = false;
+    int e = start;
+    for (int k = 0; k < kSerial; ++k) {
+      if (searching && e < end) {
+        int u = ci[e++];
+        ++scanned;
+        if (in_frontier(u)) {
+          found = true;
+          searching = false;
+        }
+      }
+    }
+    if (e >= end)
+      searching = false;
+    unsigned rest = __ballot_sync(kFull, searching);
+    while (rest) {
+      int leader = __ffs(rest) - 1;
+      rest &= rest - 1;
+      int s = __shfl_sync(kFull, e, leader);
+      int t = __shfl_sync(kFull, end, leader);
+      bool hit = false;
+      for (int off = s; off < t && !hit; off += 32) {
+        int idx = off + lane;
+        bool mine = false;
+        if (idx < t) {
+          ++scanned;
+          mine = in_frontier(ci[idx]);
+        }
+        hit = __any_sync(kFull, mine);
+      }
+      if (lane == leader)
+        found = hit;
+    }
+    const unsigned fm = __ballot_sync(kFull, found);
+    if (found) {
+      dist[v] = next_level;
+      found_deg += static_cast<unsigned>(deg);
+    }
+    if (lane == 0) {
+      next[wi] = fm;
+      if (fm)
+        visited[wi] = vis | fm;
+    }
+    found_cnt += found ? 1 : 0;
+  }
+  scanned = warp_sum(scanned);
+  found_deg = warp_sum(found_deg);
+  found_cnt = warp_sum(found_cnt);
+  if (lane == 0) {
+    if (scanned)
+      atomicAdd(&ctrl->edges, scanned);
+    if (found_cnt) {
+      atomicAdd(&ctrl->deg_sum, found_deg);
+      atomicAdd(next_count, found_cnt);
+    }
+  }
+}
+
+static __global__ void part_reset_kernel(partition_t pt, int source, int* dist, unsigned* visited,
+                                         unsigned* sent, int sent_words, int* q0, int* counts) {
+  const int lwords = (pt.n_local + 31) / 32;
+  const int n = max(pt.n_local, sent_words);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < pt.n_local)
+      dist[i] = 0x7fffffff;
+    if (i < lwords)
+      visited[i] = 0;
+    if (i < sent_words)
+      sent[i] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counts[0] = counts[1] = counts[2] = 0;
+    if (pt.owner(source) == pt.part)
+      counts[0] = 1, q0[0] = pt.local(source);
+  }
+}
+static __global__ void part_seed_kernel(partition_t pt, int source, int* dist, unsigned* visited) {
+  if (pt.owner(source) == pt.part) {
+    int l = pt.local(source);
+    dist[l] = 0;
+    visited[l >> 5] |= 1u << (l & 31);
+  }
+}
+
+/// Device state of one rank's share of a partitioned BFS (allocated once per graph).
+struct part_bfs_state_t {
+  partition_t pt;
+  dbuf_t<unsigned> visited, sent, fbm, nbm;
+  dbuf_t<int> q[2], counts, send_count, overflow, dist;
+  dbuf_t<int> send_buf;
+  int send_cap = 0;
+  int cur = 0;
+  bool frontier_is_bitmap = false;
+  struct host_fb_t {
+    int count;
+    int overflow;
+    unsigned long long deg_sum;
+    unsigned long long edges;
+    int send_count[64];
+  };
+  host_fb_t* h_fb = nullptr;
+  ctrl_t* last_ctrl = nullptr;
+  ~part_bfs_state_t() {
+    if (h_fb)
+      cudaFreeHost(h_fb);
+  }
+  int local_words() const { return (pt.n_local + 31) / 32; }
+  /// words per rank in the all-gathered frontier bitmap (identical on every rank)
+  int words_per_rank() const { return (pt.rows_of(0) + 31) / 32; }
+  void ensure(const partition_t& p, int send_capacity) {
+    pt = p;
+    size_t lw = static_cast<size_t>(words_per_rank()) + 4;
+    visited.ensure(lw);
+    fbm.ensure(lw);
+    nbm.ensure(lw);
+    sent.ensure((static_cast<size_t>(p.n_global) + 31) / 32 + 4);
+    q[0].ensure(static_cast<size_t>(p.n_local) + 64);
+    q[1].ensure(static_cast<size_t>(p.n_local) + 64);
+    dist.ensure(static_cast<size_t>(p.n_local) + 64);
+    counts.ensure(8);
+    send_count.ensure(64);
+    overflow.ensure(4);
+    send_cap = send_capacity;
+    send_buf.ensure(static_cast<size_t>(p.nparts) * send_capacity + 64);
+    if (!h_fb)
+      B2G_CHECK(cudaMallocHost(&h_fb, sizeof(host_fb_t)));
+  }
+};
+
+static __global__ void part_feedback_kernel(const int* count, const ctrl_t* c, const int* send_count,
+                                            const int* overflow, int nparts,
+                                            part_bfs_state_t::host_fb_t* fb) {
+  fb->count = *count;
+  fb->overflow = (c ? c->overflow : 0) | *overflow;
+  fb->deg_sum = c ? c->deg_sum : 0;
+  fb->edges = c ? c->edges : 0;
+  for (int i = 0; i < nparts && i < 64; ++i)
+    fb->send_count[i] = send_count[i];
+}
+
+}  // namespace b200
+}  // namespace gunrock

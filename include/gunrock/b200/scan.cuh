@@ -40,6 +40,7 @@ lookback_scan_kernel(const int* __restrict__ n_ptr,
                      ValueF value,
                      EmitF emit,
                      int* total_out,
+                     int* total_at_n,  // optional array: total_at_n[n] = grand total
                      unsigned long long* state,
                      ctrl_t* ctrl,
                      unsigned epoch) {
@@ -54,8 +55,12 @@ lookback_scan_kernel(const int* __restrict__ n_ptr,
   const int lane = lane_id(), warp = threadIdx.x >> 5;
 
   if (n == 0) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && total_out)
-      *total_out = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      if (total_out)
+        *total_out = 0;
+      if (total_at_n)
+        total_at_n[0] = 0;
+    }
     return;
   }
   for (;;) {
@@ -124,8 +129,12 @@ lookback_scan_kernel(const int* __restrict__ n_ptr,
         emit(idx, run, vals[k]);
       run += vals[k];
     }
-    if (tile == ntiles - 1 && threadIdx.x == 0 && total_out)
-      *total_out = s_prefix + block_total;
+    if (tile == ntiles - 1 && threadIdx.x == 0) {
+      if (total_out)
+        *total_out = s_prefix + block_total;
+      if (total_at_n)
+        total_at_n[n] = s_prefix + block_total;
+    }
     __syncthreads();  // s_tile / s_warp reuse
   }
 }
@@ -138,7 +147,8 @@ inline void lookback_scan(workspace_t& ws,
                           int n_upper_bound,
                           ValueF value,
                           EmitF emit,
-                          int* total_out) {
+                          int* total_out,
+                          int* total_at_n = nullptr) {
   constexpr int kThreads = 256, kItems = 8;
   unsigned& epoch = ws.scan_epoch;
   int max_tiles = (n_upper_bound + kThreads * kItems - 1) / (kThreads * kItems) + 1;
@@ -156,7 +166,7 @@ inline void lookback_scan(workspace_t& ws,
   if (grid > max_tiles)
     grid = max_tiles;
   lookback_scan_kernel<kThreads, kItems><<<grid, kThreads, 0, ws.stream>>>(
-      n_ptr, n_fixed, value, emit, total_out, ws.tile_state.ptr, ctrl, epoch);
+      n_ptr, n_fixed, value, emit, total_out, total_at_n, ws.tile_state.ptr, ctrl, epoch);
   ws.launches += 1;
   B2G_CHECK(cudaGetLastError());
 }

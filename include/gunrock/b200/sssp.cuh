@@ -48,6 +48,19 @@ struct sssp_relax_op {
       return false;
     return atomicExch(stamp + dst, iteration) != iteration;
   }
+  /// two-phase protocol: read the target's current distance first; a candidate that cannot
+  /// lower it needs no atomic at all (distances only decrease, so a stale read is conservative:
+  /// it can only let through a candidate the atomicMin then rejects).
+  __device__ __forceinline__ float prefetch(int dst) const { return ld_relaxed(dist + dst); }
+  __device__ __forceinline__ bool commit(int src, int dst, int, float w, float current) const {
+    float nd = __fadd_rn(ld_relaxed(dist + src), w);
+    if (!(nd < current))
+      return false;
+    float old = atomic_min_float(dist + dst, nd);
+    if (!(nd < old))
+      return false;
+    return atomicExch(stamp + dst, iteration) != iteration;
+  }
 };
 
 static __global__ void sssp_reset_kernel(float* dist, int* stamp, int n_vertices, int source, int* q0,
@@ -72,6 +85,7 @@ struct sssp_scratch_t {
     int count;
     int overflow;
     unsigned long long edges;
+    unsigned long long deg_sum;
   };
   host_fb_t* h_fb = nullptr;
   cudaEvent_t ev[128] = {};
@@ -100,6 +114,7 @@ static __global__ void sssp_feedback_kernel(const int* count, const ctrl_t* c,
   fb->count = *count;
   fb->overflow = c->overflow;
   fb->edges = c->edges;
+  fb->deg_sum = c->deg_sum;
 }
 
 struct sssp_level_stat_t {
@@ -121,6 +136,7 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
   ws.launches += 1;
   int cur = 0, iteration = 0;
   long long n_f = 1;
+  unsigned long long m_f = 0;  // out-degree sum of the frontier (0 = unknown, first iteration)
   while (n_f > 0) {
     int nxt = cur ^ 1;
     B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
@@ -128,9 +144,16 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
     ctrl_t* c = nullptr;
     if (iteration < 64)
       B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration], st));
-    launch_advance<advance_output_t::vertices, false, true>(
+    advance_launch_t lcfg = cfg;
+    if (iteration == 0) {
+      lcfg.lb = lb_t::block_mapped;  // one row of unknown length: binned kernel + hub slabs
+    } else if (static_cast<long long>(m_f) < cfg.small_frontier_edges) {
+      lcfg.lb = lb_t::block_mapped;  // single-kernel path for tiny frontiers
+      lcfg.hub_threshold = 1 << 30;
+    }
+    launch_advance<advance_output_t::vertices, true, true>(
         ws, g, sc.q[cur].ptr, sc.counts.ptr + cur, static_cast<int>(n_f < V ? n_f : V),
-        sc.q[nxt].ptr, sc.counts.ptr + nxt, V, op, cfg, &c);
+        sc.q[nxt].ptr, sc.counts.ptr + nxt, V, op, lcfg, &c);
     if (iteration < 64)
       B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration + 1], st));
     sssp_feedback_kernel<<<1, 1, 0, st>>>(sc.counts.ptr + nxt, c, sc.h_fb);
@@ -141,6 +164,7 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
     if (levels)
       levels->push_back({static_cast<int>(n_f), sc.h_fb->edges});
     n_f = sc.h_fb->count;
+    m_f = sc.h_fb->deg_sum;
     cur = nxt;
     ++iteration;
   }

@@ -163,6 +163,41 @@ int b2g_filter(b2g_graph_t* g, int alg, const int* in, const int* in_count, int 
 int b2g_uniquify(b2g_graph_t* g, const int* in, const int* in_count, int in_capacity, int* out,
                  int* out_count, int best_effort);
 
+/* ---- multi-GPU BFS: per-rank steps of the 1-D (cyclic) vertex partition -----------------------
+ * One process per GPU.  Global vertex v lives on rank v % nparts at local row v / nparts; a rank's
+ * CSR has its own rows with GLOBAL column ids.  The per-level remote-frontier exchange (NCCL
+ * all-to-all of the send buffers, all-gather of the frontier bitmap, all-reduce of the counts) is
+ * done by the host side between these calls (gunrock_b200/multi_gpu.py).  The reference has no
+ * multi-GPU execution (advance.hxx:129-132 throws); it only offers gcuda::multi_context_t
+ * (include/gunrock/cuda/context.hxx:146-216), whose role the process group plays here. */
+int b2g_graph_create_rmat_part(int scale, long long n_pairs, unsigned long long seed, int mirror,
+                               int nparts, int part, b2g_graph_t** out);
+/* Rank-local CSR (row_offsets[n_local+1], column_indices = global ids), host or device arrays. */
+int b2g_graph_create_csr_part(int n_global_vertices, int nparts, int part, int n_local_edges,
+                              const int* row_offsets, const int* column_indices, int loc,
+                              int symmetric, b2g_graph_t** out);
+int b2g_part_info(const b2g_graph_t* g, int* n_global, int* nparts, int* part, int* n_local,
+                  int* words_per_rank);
+/* Reset the rank's BFS state and seed `source` on its owner. send_capacity = ints per peer. */
+int b2g_part_bfs_begin(b2g_graph_t* g, int source, int send_capacity);
+/* Expand the local frontier top-down.  Local neighbours are claimed in place; new remote ones land
+ * in the per-owner send buffers.  send_counts (host, nparts ints) receives how many per owner. */
+int b2g_part_bfs_topdown(b2g_graph_t* g, int level, const b2g_options_t* opt, int* send_counts,
+                         unsigned long long* edges_touched);
+/* Device pointer to the send buffers: nparts rows of *send_capacity ints. */
+int b2g_part_bfs_send_buffer(b2g_graph_t* g, int** send_buf, int* send_capacity);
+/* Claim n_recv global ids (device array, all owned by this rank) received from peers. */
+int b2g_part_bfs_claim(b2g_graph_t* g, int level, const int* recv, int n_recv);
+/* Write the current local frontier as a bitmap of words_per_rank words (device). */
+int b2g_part_bfs_frontier_bitmap(b2g_graph_t* g, unsigned* out);
+/* Bottom-up sweep against the all-gathered frontier bitmap (nparts x words_per_rank words). */
+int b2g_part_bfs_bottomup(b2g_graph_t* g, int level, const unsigned* frontier_all,
+                          unsigned long long* edges_touched);
+/* Close the level: returns this rank's next-frontier size and its out-degree sum. */
+int b2g_part_bfs_end_level(b2g_graph_t* g, long long* n_frontier, long long* frontier_degree);
+/* Copy the rank's slice of the distances (n_local ints, local row order). */
+int b2g_part_bfs_distances(b2g_graph_t* g, int* distances, int loc);
+
 #pragma GCC visibility pop
 #ifdef __cplusplus
 }

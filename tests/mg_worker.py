@@ -1,0 +1,44 @@
+"""torchrun worker for the real multi-GPU test: partitioned BFS over NCCL, checked against the oracle."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+import gunrock_b200 as gb  # noqa: E402
+from gunrock_b200 import multi_gpu as mg  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scale, ef, seed = 16, 16, 0x5EED22
+    ro, ci = oracle.rmat_csr(scale, ef, seed)
+    src = int(np.diff(ro).argmax())
+    exp = oracle.bfs(ro, ci, src)
+    results = {}
+    # (a) partition of a host CSR, (b) the device RMAT generator producing the rank's share directly
+    for name, G in (("csr", mg.PartitionedGraph.from_global_csr(ro, ci, world, rank)),
+                    ("rmat", mg.PartitionedGraph.rmat(scale, ef << scale, seed, world, rank))):
+        for direction in (gb.advance_direction_t.forward, gb.advance_direction_t.optimized):
+            for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
+                eng = mg.CudaRankEngine(G, gb.options_t(advance_load_balance=lb))
+                d, st = mg.bfs_rank(eng, mg.TorchDistComm(), src, total_edges=len(ci), direction=direction)
+                ok = bool(np.array_equal(d.cpu().numpy(), exp[rank::world]))
+                t = torch.tensor([int(ok)], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                results[f"{name}/{direction}/{lb}"] = [int(t.item()), st.level_direction, st.exchanged_ids]
+        G.close()
+    if rank == 0:
+        print("MG_RESULT " + json.dumps(results), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,75 @@
+"""GPU tests of the partitioned (multi-GPU) BFS.
+* several simulated ranks on ONE GPU (the per-rank CUDA steps are the real ones; the exchange is a
+  tensor copy) -- runs wherever a single B200 is available;
+* a real NCCL run under torchrun when >= 2 GPUs are visible."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gb(built):
+    import gunrock_b200 as gb
+    if gb.device_count() < 1:
+        pytest.fail("GPU tests need a CUDA device")
+    return gb
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 8])
+def test_simulated_ranks_on_one_gpu(gb, P):
+    from gunrock_b200 import multi_gpu as mg
+    for scale, ef, seed, mirror in ((12, 16, 5, True), (15, 8, 0x5EED22, True)):
+        ro, ci = oracle.rmat_csr(scale, ef, seed, mirror=mirror)
+        deg = np.diff(ro)
+        graphs = [mg.PartitionedGraph.from_global_csr(ro, ci, P, r) for r in range(P)]
+        for src in (int(deg.argmax()), int(np.flatnonzero(deg > 0)[-1])):
+            exp = oracle.bfs(ro, ci, src)
+            for direction in (gb.advance_direction_t.forward, gb.advance_direction_t.optimized,
+                              gb.advance_direction_t.backward):
+                for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
+                    engines = [mg.CudaRankEngine(g, gb.options_t(advance_load_balance=lb, hub_threshold=256))
+                               for g in graphs]
+                    dists, st = mg.bfs_lockstep(engines, src, total_edges=len(ci), direction=direction)
+                    got = mg.gather_distances([d.cpu().numpy() for d in dists], len(ro) - 1)
+                    assert np.array_equal(got, exp), (P, scale, src, direction, lb)
+                    if direction == gb.advance_direction_t.forward:
+                        # push inspects every out-edge of every reached vertex exactly once
+                        assert st.edges_touched == int(deg[exp < 2**31 - 1].sum())
+        for g in graphs:
+            g.close()
+
+
+def test_partitioned_rmat_generator_matches_global(gb):
+    from gunrock_b200 import multi_gpu as mg
+    scale, ef, seed, P = 13, 8, 99, 4
+    ro, ci = oracle.rmat_csr(scale, ef, seed)
+    graphs = [mg.PartitionedGraph.rmat(scale, ef << scale, seed, P, r) for r in range(P)]
+    src = int(np.diff(ro).argmax())
+    engines = [mg.CudaRankEngine(g) for g in graphs]
+    dists, st = mg.bfs_lockstep(engines, src, total_edges=len(ci))
+    got = mg.gather_distances([d.cpu().numpy() for d in dists], len(ro) - 1)
+    assert np.array_equal(got, oracle.bfs(ro, ci, src))
+    assert sum(g.n_local for g in graphs) == len(ro) - 1
+
+
+def test_nccl_two_or_more_gpus(gb):
+    n = gb.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "mg_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("MG_RESULT ")][-1]
+    res = json.loads(line[len("MG_RESULT "):])
+    assert len(res) == 8 and all(v[0] == 1 for v in res.values()), res

@@ -1,0 +1,144 @@
+"""CPU tests (gloo, world_size 2 and 3) of the multi-GPU host logic in gunrock_b200/multi_gpu.py:
+partitioning, the id all-to-all, the bitmap all-gather, the global direction switch and termination.
+The per-rank compute is replaced by a numpy stand-in engine (test infrastructure -- the product
+engine is CudaRankEngine and needs a GPU); the level loop, communicator and partition helpers under
+test are the product's own code."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from conftest import ROOT
+
+from gunrock_b200 import advance_direction_t
+from gunrock_b200 import multi_gpu as mg
+
+INT_MAX = 2**31 - 1
+
+
+class NumpyRankEngine:
+    """Reference behaviour of one rank's steps (mirrors b2g_part_* in include/gunrock_b200.h)."""
+
+    def __init__(self, ro, ci, nparts, part):
+        self.nparts, self.part = nparts, part
+        self.n_global = len(ro) - 1
+        self.lro, self.lci = mg.partition_csr(ro, ci, nparts, part)
+        self.n_local = len(self.lro) - 1
+        self.words_per_rank = (mg.rows_of(self.n_global, nparts, 0) + 31) // 32
+
+    def begin(self, source):
+        self.dist = np.full(self.n_local, INT_MAX, np.int32)
+        self.sent = np.zeros(self.n_global, bool)
+        self.frontier = np.zeros(0, np.int64)          # local rows
+        if source % self.nparts == self.part:
+            self.dist[source // self.nparts] = 0
+            self.frontier = np.array([source // self.nparts])
+        self.next = []
+
+    def _neighbours(self, rows):
+        if len(rows) == 0:
+            return np.zeros(0, np.int64)
+        return np.concatenate([self.lci[self.lro[r]:self.lro[r + 1]] for r in rows]).astype(np.int64)
+
+    def topdown(self, level):
+        nb = self._neighbours(self.frontier)
+        own = nb % self.nparts
+        mine = np.unique(nb[own == self.part] // self.nparts)
+        mine = mine[self.dist[mine] == INT_MAX]
+        self.dist[mine] = level + 1
+        self.next = list(mine)
+        remote = np.unique(nb[own != self.part])
+        remote = remote[~self.sent[remote]]
+        self.sent[remote] = True
+        self._send = [remote[remote % self.nparts == o] for o in range(self.nparts)]
+        return [len(x) for x in self._send], len(nb)
+
+    def send_rows(self, counts):
+        return torch.from_numpy(np.concatenate(self._send).astype(np.int32)) if sum(counts) else self.empty_ids(0)
+
+    def claim(self, level, recv):
+        ids = np.unique(recv.numpy().astype(np.int64) // self.nparts)
+        ids = ids[self.dist[ids] == INT_MAX]
+        self.dist[ids] = level + 1
+        self.next += list(ids)
+
+    def frontier_bitmap(self):
+        bits = np.zeros(self.words_per_rank * 32, bool)
+        bits[self.frontier] = True
+        return torch.from_numpy(np.packbits(bits, bitorder="little").view(np.int32).copy())
+
+    def bottomup(self, level, frontier_all):
+        bits = np.unpackbits(frontier_all.numpy().view(np.uint8), bitorder="little")
+        scanned = 0
+        self.next = []
+        for r in np.flatnonzero(self.dist == INT_MAX):
+            for u in self.lci[self.lro[r]:self.lro[r + 1]]:
+                scanned += 1
+                if bits[(u % self.nparts) * self.words_per_rank * 32 + u // self.nparts]:
+                    self.dist[r] = level + 1
+                    self.next.append(r)
+                    break
+        return scanned
+
+    def end_level(self):
+        self.frontier = np.array(sorted(set(self.next)), np.int64)
+        self.next = []
+        deg = int((self.lro[self.frontier + 1] - self.lro[self.frontier]).sum()) if len(self.frontier) else 0
+        return len(self.frontier), deg
+
+    def distances(self):
+        return torch.from_numpy(self.dist)
+
+    def empty_ids(self, n):
+        return torch.empty(n, dtype=torch.int32)
+
+
+def _worker(rank, world, port, ro, ci, source, direction, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = NumpyRankEngine(ro, ci, world, rank)
+    comm = mg.TorchDistComm()
+    d, st = mg.bfs_rank(eng, comm, source, total_edges=len(ci), direction=direction)
+    np.save(os.path.join(out_dir, f"d{rank}.npy"), d.numpy())
+    np.save(os.path.join(out_dir, f"s{rank}.npy"), np.array(st.level_direction))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,direction", [(2, advance_direction_t.forward), (2, advance_direction_t.optimized),
+                                             (3, advance_direction_t.optimized)])
+def test_partitioned_bfs_over_gloo(tmp_path, world, direction):
+    ro, ci = oracle.rmat_csr(10, 8, 4242)
+    source = int(np.diff(ro).argmax())
+    port = 29500 + (os.getpid() % 2000) + world * 7 + direction
+    mp.spawn(_worker, args=(world, port, ro, ci, source, direction, str(tmp_path)), nprocs=world, join=True)
+    locs = [np.load(tmp_path / f"d{r}.npy") for r in range(world)]
+    got = mg.gather_distances(locs, len(ro) - 1)
+    assert np.array_equal(got, oracle.bfs(ro, ci, source))
+    dirs = np.load(tmp_path / "s0.npy")
+    if direction == advance_direction_t.optimized:
+        assert 1 in dirs and dirs[0] == 0          # the switch fired, level 0 stayed top-down
+    else:
+        assert not dirs.any()
+
+
+def test_partition_helpers():
+    ro, ci = oracle.rmat_csr(9, 8, 7)
+    n = len(ro) - 1
+    for P in (1, 2, 3, 8):
+        tot = 0
+        for r in range(P):
+            lro, lci = mg.partition_csr(ro, ci, P, r)
+            assert len(lro) - 1 == mg.rows_of(n, P, r)
+            for l in (0, len(lro) // 2, len(lro) - 2):
+                v = l * P + r
+                assert np.array_equal(lci[lro[l]:lro[l + 1]], ci[ro[v]:ro[v + 1]])
+            tot += len(lci)
+        assert tot == len(ci)
+    d = [np.arange(r, 10, 3, dtype=np.int32) for r in range(3)]
+    assert mg.gather_distances(d, 10).tolist() == list(range(10))
