@@ -105,6 +105,11 @@ _SYMBOLS = [
     "b2g_graph_build_transpose", "b2g_graph_destroy", "b2g_graph_info", "b2g_graph_device_ptrs",
     "b2g_graph_download", "b2g_graph_max_degree_vertex", "b2g_bfs", "b2g_sssp", "b2g_pr",
     "b2g_advance_bfs", "b2g_filter", "b2g_uniquify",
+    # multi-GPU per-rank steps (bound in gunrock_b200/multi_gpu.py)
+    "b2g_graph_create_rmat_part", "b2g_graph_create_csr_part", "b2g_part_info", "b2g_part_bfs_begin",
+    "b2g_part_bfs_topdown", "b2g_part_bfs_send_buffer", "b2g_part_bfs_claim",
+    "b2g_part_bfs_frontier_bitmap", "b2g_part_bfs_bottomup", "b2g_part_bfs_end_level",
+    "b2g_part_bfs_distances",
 ]
 
 
