@@ -49,6 +49,14 @@ WORKLOADS = {
     "bfs_do_rmat26": dict(alg="bfs", scale=26, ef=8, seed=0x5EED26, mirror=True, fold=0, weights=0,
                           lb="block_mapped", direction="optimized",
                           desc="BFS direction-optimised, RMAT-26 with 16 directed edges/vertex (int32-safe)"),
+    # config 5: 1-D vertex partition over the ranks + NCCL frontier exchange (strong scaling)
+    "bfs_part_rmat26": dict(alg="bfs", scale=26, ef=8, seed=0x5EED26, mirror=True, fold=0, weights=0,
+                            lb="block_mapped", direction="optimized", partitioned=True,
+                            desc="BFS direction-optimised, RMAT-26 (16 directed edges/vertex), 1-D cyclic vertex "
+                                 "partition across the ranks, NCCL all-to-all / all-gather frontier exchange"),
+    "bfs_part_rmat22": dict(alg="bfs", scale=22, ef=16, seed=0x5EED22, mirror=True, fold=0, weights=0,
+                            lb="block_mapped", direction="optimized", partitioned=True,
+                            desc="BFS direction-optimised, RMAT-22 ef16, 1-D partition + NCCL exchange"),
 }
 
 
@@ -197,6 +205,91 @@ def run_reference(args, wl, name):
     print(json.dumps(line), flush=True)
 
 
+def run_partitioned(args, wl, name, rank, world, local):
+    """BASELINE.json configs[4]: one BFS over a graph 1-D partitioned across the ranks (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    import gunrock_b200 as gb
+    from gunrock_b200 import multi_gpu as mg
+
+    n_pairs = wl["ef"] * (1 << wl["scale"])
+    G = mg.PartitionedGraph.rmat(wl["scale"], n_pairs, wl["seed"], world, rank, mirror=wl["mirror"])
+    comm = mg.TorchDistComm()
+    v, d = G.max_degree_vertex()
+    key = torch.tensor([(d << 32) | (0x7fffffff - v)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(key, op=dist.ReduceOp.MAX)
+    src = 0x7fffffff - int(key.item() & 0xffffffff)
+    total_edges = comm.all_reduce_sum([G.n_local_edges], "cuda")[0]
+    opt = gb.options_t(advance_load_balance=getattr(gb.load_balance_t, wl["lb"]),
+                       hub_threshold=args.hub_threshold, ctas_per_sm=args.ctas_per_sm)
+    eng = mg.CudaRankEngine(G, opt)
+    direction = getattr(gb.advance_direction_t, wl["direction"])
+
+    def step():
+        return mg.bfs_rank(eng, comm, src, total_edges, direction=direction)
+
+    for _ in range(max(args.warmup, 3)):
+        dloc, st = step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    edges = 0
+    for _ in range(args.steps):
+        dloc, st = step()
+        edges += st.edges_touched
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    # e2e: the rank's slice of the result is copied to pinned host memory inside the timed region
+    h = torch.empty(G.n_local, dtype=torch.int32).pin_memory()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        dloc, st2 = step()
+        h.copy_(dloc, non_blocking=False)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = float(ms2.item())
+    reached = torch.tensor([int((dloc < 2**31 - 1).sum())], device="cuda")
+    dist.all_reduce(reached)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peak, peak_kind = peaks()
+        value = edges / ms / 1e3
+        line = {"metric": f"MTEPS ({name})", "value": value, "unit": "MTEPS", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": wl["desc"], "vertices": G.n_global, "edges": total_edges, "source": src,
+                           "levels": st.levels, "level_direction": st.level_direction,
+                           "level_frontier": st.level_frontier, "level_edges": st.level_edges,
+                           "ids_exchanged_per_step_rank0": st.exchanged_ids, "reached_vertices": int(reached.item()),
+                           "l2_policy": "inputs larger than L2 per rank" if total_edges * 4 / world > 126e6 else
+                                        "per-rank column indices %.0f MB" % (total_edges * 4 / world / 1e6),
+                           "graph500_mteps": total_edges / (ms / args.steps) / 1e3},
+                "e2e": {"value": edges / ms2 / 1e3, "unit": "MTEPS", "h2d_bytes_per_step": 4,
+                        "d2h_bytes_per_step": G.n_local * 4, "ms_per_step": ms2 / args.steps},
+                "gpu_launches": None,
+                "roofline": {"bound": "hbm", "achieved": 4.0 * edges / world / (ms * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": 4.0 * edges / world / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "peak_kind": peak_kind, "kernel": "whole step per rank (advance + sweep + exchange)",
+                             "bytes_per_edge": 4},
+                "cpu_baseline": None, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    G.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -239,8 +332,12 @@ def main():
     if gb.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; libgunrock_b200 has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1 or wl.get("partitioned"):
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), rank=rank, world_size=world)
+    if wl.get("partitioned"):
+        return run_partitioned(args, wl, name, rank, world, local)
 
     # ---- graph, generated on the device (ingest is untimed, as in the reference) ----------------
     n_pairs = wl.get("pairs") or wl["ef"] * (1 << wl["scale"])

@@ -81,6 +81,18 @@ class PartitionedGraph:
         v = [C.c_int() for _ in range(5)]
         _check(L.b2g_part_info(self._h, *[C.byref(x) for x in v]), "b2g_part_info")
         self.n_global, self.nparts, self.part, self.n_local, self.words_per_rank = (x.value for x in v)
+        ne = C.c_int()
+        L.b2g_graph_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        _check(L.b2g_graph_info(self._h, None, C.byref(ne), None, None), "b2g_graph_info")
+        self.n_local_edges = ne.value
+
+    def max_degree_vertex(self):
+        """(global id, degree) of this rank's highest-degree vertex."""
+        L = _bind()
+        L.b2g_graph_max_degree_vertex.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        v, d = C.c_int(), C.c_int()
+        _check(L.b2g_graph_max_degree_vertex(self._h, C.byref(v), C.byref(d)), "b2g_graph_max_degree_vertex")
+        return v.value * self.nparts + self.part, d.value
 
     @staticmethod
     def rmat(scale: int, n_pairs: int, seed: int, nparts: int, part: int, mirror: bool = True):

@@ -80,6 +80,14 @@ __device__ __forceinline__ int op_emit(const Op& op, int dst) {
   else
     return dst;
 }
+/// Optional `static constexpr bool kNeedsSource = false`: the functor ignores its `src` argument,
+/// so kernels need not stage source ids (saves 8 KiB of shared memory per merge_path CTA, which
+/// goes to L1 and raises the hit rate of the bitmap probes).
+template <typename Op, typename = void>
+struct op_needs_source : std::true_type {};
+template <typename Op>
+struct op_needs_source<Op, std::void_t<decltype(Op::kNeedsSource)>>
+    : std::integral_constant<bool, Op::kNeedsSource> {};
 constexpr int kBatch = 4;  // 32-edge chunks whose loads are issued back to back per warp
 
 /// Per-warp staging buffer: ballot-compacted appends, flushed with one global atomic.
@@ -557,9 +565,11 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
   constexpr int kWarps = kThreads / 32;
   constexpr int kRows = kTile + 36;  // kTile edges overlap at most kTile non-empty rows (+ 33 sentinels)
   __shared__ int s_emit[kWarps][kEmitCap];
-  __shared__ int s_rank[kRows];  // first global rank of each staged row
-  __shared__ int s_base[kRows];  // CSR offset of the row's first edge
-  __shared__ int s_vert[kRows];
+  constexpr bool kSrc = op_needs_source<Op>::value;
+  static_assert(kTile < 65536 - 64, "row starts are kept as 16-bit offsets from the tile start");
+  __shared__ unsigned short s_rank[kRows];  // first rank of each staged row, relative to the tile
+  __shared__ int s_base[kRows];             // (CSR offset of the row's first edge) - (its first rank)
+  __shared__ int s_vert[kSrc ? kRows : 1];
   __shared__ int s_wcount[kWarps];
   __shared__ int s_nrows;
   __shared__ int s_tile;
@@ -611,9 +621,10 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
       if (live) {
         int slot = off + __popc(m & lanemask_lt());
         int v = (kIn == advance_input_t::graph) ? i : p.in[i];
-        s_rank[slot] = sc;
+        s_rank[slot] = static_cast<unsigned short>(max(sc, r_begin) - r_begin);
         s_base[slot] = ro[v] - sc;
-        s_vert[slot] = v;
+        if (kSrc)
+          s_vert[slot] = v;
       }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -626,7 +637,8 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
     }
     const int nrows = s_nrows;
     if (threadIdx.x < 33)
-      s_rank[nrows + threadIdx.x] = r_end;  // sentinels: no row starts inside [r_end, ...)
+      s_rank[nrows + threadIdx.x] =
+          static_cast<unsigned short>(r_end - r_begin);  // sentinels: no row starts past the tile
     __syncthreads();
     // Each warp owns a contiguous span of the tile and walks it 32 ranks at a time, so its row
     // cursor only moves forward: one binary search per span, then per chunk the row starts that
@@ -639,7 +651,7 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
       int a = 0, b = nrows;  // last staged row with s_rank <= w_begin
       while (b - a > 1) {
         int mid = (a + b) >> 1;
-        if (s_rank[mid] <= w_begin)
+        if (static_cast<int>(s_rank[mid]) + r_begin <= w_begin)
           a = mid;
         else
           b = mid;
@@ -654,7 +666,7 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
           // invariant: s_rank[a] <= rk <= s_rank[a+1].  Row starts of rows a+1.. that fall inside
           // [rk, rk+32) become bits (strictly increasing starts => at most 32 of them).
           const int rk = r0 + 32 * k;
-          int nxt = s_rank[min(a + 1 + lane, nrows + 32)] - rk;
+          int nxt = static_cast<int>(s_rank[min(a + 1 + lane, nrows + 32)]) + r_begin - rk;
           unsigned bit = (nxt >= 0 && nxt < 32) ? (1u << nxt) : 0u;
           unsigned starts = __reduce_or_sync(kFull, bit);
           row[k] = min(a + __popc(starts & (0xffffffffu >> (31 - lane))), nrows - 1);
@@ -663,7 +675,7 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
         }
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) {
-          u[k] = s_vert[row[k]];
+          u[k] = kSrc ? s_vert[row[k]] : -1;
           e[k] = s_base[row[k]] + r0 + 32 * k + lane;  // s_base = CSR offset - first rank of the row
           nb[k] = valid[k] ? ld_stream(ci + e[k]) : -1;
           w[k] = (kWeights && vals && valid[k]) ? ld_stream(vals + e[k]) : 1.0f;

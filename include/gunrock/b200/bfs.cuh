@@ -26,6 +26,7 @@ namespace b200 {
 
 /// Top-down edge functor: claim `dst` on the visited bitmap, label it, keep it.
 struct bfs_claim_op {
+  static constexpr bool kNeedsSource = false;
   unsigned* visited;
   int* dist;
   int next_level;
@@ -53,6 +54,7 @@ struct bfs_claim_op {
 
 /// The reference's own functor (bfs.hxx:105-128), kept selectable for like-for-like runs.
 struct bfs_atomic_min_op {
+  static constexpr bool kNeedsSource = false;
   int* dist;
   int next_level;
   __device__ __forceinline__ bool operator()(int, int dst, int, float) const {

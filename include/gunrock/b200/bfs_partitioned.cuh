@@ -62,6 +62,7 @@ struct partition_t {
 
 /// Top-down edge functor of the partitioned BFS (two-phase protocol, see advance.cuh).
 struct part_claim_op {
+  static constexpr bool kNeedsSource = false;
   partition_t pt;
   unsigned* visited;   // local rows
   unsigned* sent;      // global ids already forwarded by this rank

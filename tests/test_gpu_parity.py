@@ -188,6 +188,32 @@ def test_pagerank_vs_oracle(gb, mirror, weights):
     G.close()
 
 
+def test_pagerank_tile_edge_cases(gb):
+    """Rows that span many pull tiles (hubs), empty rows at tile borders, graphs with no edges."""
+    rng = np.random.default_rng(11)
+    cases = []
+    # no edges at all: every rank is (1 - alpha + alpha)/V = 1/V after one iteration
+    cases.append((np.zeros(6, np.int32), np.zeros(0, np.int32)))
+    # in-star: vertex 0 has in-degree 9000 (spans 5 tiles of 2048), everyone else dangling or leaf
+    n = 9001
+    I = np.arange(1, n, dtype=np.int32)
+    J = np.zeros(n - 1, np.int32)
+    cases.append(oracle.csr_from_coo(n, I, J)[:2])
+    # two hubs whose in-edge ranges straddle tile boundaries + a block of isolated vertices between
+    n = 12000
+    I = np.concatenate([rng.integers(0, n, 3000), rng.integers(0, n, 5000), rng.integers(0, n, 6000)]).astype(np.int32)
+    J = np.concatenate([np.full(3000, 5), np.full(5000, 7000), rng.integers(7001, n, 6000)]).astype(np.int32)
+    cases.append(oracle.csr_from_coo(n, I, J)[:2])
+    for ro, ci in cases:
+        G = gb.graph_t.from_csr(ro, ci, None, symmetric=False)
+        p = np.empty(G.n_vertices, np.float32)
+        st = gb.pr(G, p)
+        pe, iters = oracle.pr(ro, ci, None)
+        assert st.iterations == iters
+        assert np.allclose(p, pe, rtol=1e-6, atol=0), np.abs(p - pe).max()
+        G.close()
+
+
 def test_ingest_rmat_coo_transpose(gb):
     # device RMAT generator == oracle generator (same counter-based integer arithmetic)
     for scale, ef, seed, mirror in ((10, 16, 0x5EED10, True), (13, 8, 77, True), (12, 8, 5, False)):
