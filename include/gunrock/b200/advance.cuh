@@ -210,7 +210,15 @@ advance_binned_kernel(advance_params_t p, Op op) {
     }
     edges_seen += static_cast<unsigned>(deg);
     // -- grid bin: defer hubs ------------------------------------------------------------
-    if (deg >= p.hub_threshold) {
+    // A warp that drew many long rows would become the tail of the kernel (32 rows of up to
+    // hub_threshold edges, walked one after the other).  Bound its share: when the rows >= 32
+    // edges add up to more than kWarpBudget, everything >= kSpill edges goes to the slab bin too.
+    constexpr int kWarpBudget = 8192, kSpill = 256;
+    const int long_sum = warp_sum(deg >= 32 ? deg : 0);
+    const int defer_at = (long_sum > kWarpBudget && p.hub_threshold < (1 << 30))
+                             ? min(p.hub_threshold, kSpill)
+                             : p.hub_threshold;
+    if (deg >= defer_at) {
       int slot = atomicAdd(&p.ctrl->hub_count, 1);
       if (slot < p.hub_capacity) {  // list full (duplicate-heavy frontier): keep it in the warp bin
         p.hubs[slot] = v;
@@ -571,7 +579,6 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
   __shared__ int s_base[kRows];             // (CSR offset of the row's first edge) - (its first rank)
   __shared__ int s_vert[kSrc ? kRows : 1];
   __shared__ int s_wcount[kWarps];
-  __shared__ int s_nrows;
   __shared__ int s_tile;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int* __restrict__ ro = p.g.row_offsets;
@@ -585,12 +592,14 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
   warp_emitter_t<kEmitCap, kDegSum> em;
   em.init(s_emit[warp], p.out, p.out_count, p.out_capacity, ro, p.ctrl);
 
+  // Dynamic tile tickets (CTAs that become resident late simply take fewer tiles).  The ticket of
+  // the NEXT tile is drawn by thread 0 while the current tile is being walked, so a tile costs
+  // three block barriers in total: [A] previous tile retired + ticket visible, [B] per-warp live
+  // row counts visible, [C] staged rows + sentinels visible.
+  if (threadIdx.x == 0)
+    s_tile = atomicAdd(&p.ctrl->work, 1);
   for (;;) {
-    // dynamic tile ticket: CTAs that become resident late simply take fewer tiles
-    __syncthreads();
-    if (threadIdx.x == 0)
-      s_tile = atomicAdd(&p.ctrl->work, 1);
-    __syncthreads();
+    __syncthreads();  // [A]
     const int tile = s_tile;
     if (tile >= ntiles)
       break;
@@ -598,10 +607,7 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
     const int r_end = min(total, r_begin + kTile);
     const int row0 = p.tile_rows[tile];
     const int row1 = min(n - 1, p.tile_rows[tile + 1]);  // last row that can overlap the tile
-    __syncthreads();
-    if (threadIdx.x == 0)
-      s_nrows = 0;
-    __syncthreads();
+    int nrows = 0;  // identical in every thread
     for (int i0 = row0; i0 <= row1; i0 += kThreads) {
       int i = i0 + threadIdx.x;
       int sc = 0;
@@ -612,12 +618,19 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
         live = sc_next > sc && sc < r_end && sc_next > r_begin;
       }
       unsigned m = __ballot_sync(kFull, live);
+      if (i0 != row0)
+        __syncthreads();  // s_wcount of the previous batch has been consumed
       if (lane == 0)
         s_wcount[warp] = __popc(m);
-      __syncthreads();
-      int off = s_nrows;
-      for (int w = 0; w < warp; ++w)
-        off += s_wcount[w];
+      __syncthreads();  // [B]
+      int off = nrows, batch = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        int c = s_wcount[w];
+        if (w < warp)
+          off += c;
+        batch += c;
+      }
       if (live) {
         int slot = off + __popc(m & lanemask_lt());
         int v = (kIn == advance_input_t::graph) ? i : p.in[i];
@@ -626,20 +639,14 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
         if (kSrc)
           s_vert[slot] = v;
       }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int add = 0;
-        for (int w = 0; w < kWarps; ++w)
-          add += s_wcount[w];
-        s_nrows += add;
-      }
-      __syncthreads();
+      nrows += batch;
     }
-    const int nrows = s_nrows;
     if (threadIdx.x < 33)
       s_rank[nrows + threadIdx.x] =
           static_cast<unsigned short>(r_end - r_begin);  // sentinels: no row starts past the tile
-    __syncthreads();
+    __syncthreads();  // [C]
+    if (threadIdx.x == 0)
+      s_tile = atomicAdd(&p.ctrl->work, 1);  // next ticket, consumed after barrier [A]
     // Each warp owns a contiguous span of the tile and walks it 32 ranks at a time, so its row
     // cursor only moves forward: one binary search per span, then per chunk the row starts that
     // fall inside the 32 ranks are turned into a bit mask (one REDUX) and every lane derives its
@@ -794,7 +801,7 @@ inline void launch_advance(workspace_t& ws,
   } else {
     p.ctrl = ws.next_ctrl();
     p.hub_threshold = cfg.hub_threshold < 32 ? 32 : cfg.hub_threshold;
-    p.hub_capacity = cfg.hub_threshold < (1 << 30) ? g.n_edges / p.hub_threshold + 1024 : 16;
+    p.hub_capacity = cfg.hub_threshold < (1 << 30) ? g.n_edges / 256 + 1024 : 16;
     p.hubs = ws.hubs.ensure(static_cast<size_t>(p.hub_capacity));
     p.tma_ok = aligned16(g.column_indices) && (!kWeights || !g.values || aligned16(g.values));
     if (graph_in)
@@ -805,7 +812,7 @@ inline void launch_advance(workspace_t& ws,
           <<<grid, kThreads, 0, ws.stream>>>(p, op);
     if (cfg.hub_threshold < (1 << 30))
       advance_hub_kernel<kThreads, 2048, kOut, kDegSum, kWeights>
-          <<<sms * 2, kThreads, 0, ws.stream>>>(p, op);
+          <<<sms * 4, kThreads, 0, ws.stream>>>(p, op);
     else
       ws.launches -= 1;
   }

@@ -388,7 +388,7 @@ inline int pr_run(workspace_t& ws, pr_scratch_t& sc, const csr_view_t& g, const 
                                                         sc.c.ptr, sc.partials.ptr, sc.err.ptr + 1,
                                                         sc.base.ptr);
     ctrl_t* ctrl = ws.next_ctrl();
-    const int grid = sms * 4;
+    const int grid = sms * 8;  // tickets are dynamic; residency is capped by the hardware
     if (t.values)
       pr_pull_tile_kernel<256, true><<<grid, 256, 0, st>>>(
           t, ntiles, sc.first_owned.ptr, sc.c.ptr, sc.plast.ptr, sc.base.ptr, p, sc.head.ptr,

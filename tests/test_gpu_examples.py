@@ -122,3 +122,10 @@ def test_export_metrics_json(chesapeake_mtx, tmp_path):
     j = json.load(open(tmp_path / "o.json"))
     assert j["primitive"] == "bfs" and j["num_vertices"] == 39 and j["num_edges"] == 340
     assert j["edges_visited"][0] == 340 and j["search_depths"][0] == 3 and j["mteps"][0] > 0
+
+
+def test_header_api_selftest():
+    """frontier_t, advance (all load balancers, graph / vertex input, vertex / edge / no output), the
+    four filters, uniquify, parallel_for, launch_box_t and a hand-written BFS on the raw operators."""
+    out = run([need("api_selftest")])
+    assert "ALL OK" in out, out
