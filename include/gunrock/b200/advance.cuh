@@ -165,6 +165,7 @@ struct advance_params_t {
   int hub_threshold = 1 << 30;
   int tma_ok = 0;                  // column_indices / values are 16-byte aligned
   const int* tile_rows = nullptr;  // merge_path: first row of every tile
+  const int* row_base = nullptr;   // merge_path: CSR offset of every frontier row (next to the scan)
 };
 
 constexpr int kEmitCap = 128;       // ints per warp in the staging buffer
@@ -579,7 +580,7 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
   __shared__ int s_base[kRows];             // (CSR offset of the row's first edge) - (its first rank)
   __shared__ int s_vert[kSrc ? kRows : 1];
   __shared__ int s_wcount[kWarps];
-  __shared__ int s_tile;
+  __shared__ int s_tile, s_row0, s_row1;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int* __restrict__ ro = p.g.row_offsets;
   const int* __restrict__ ci = p.g.column_indices;
@@ -596,8 +597,19 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
   // the NEXT tile is drawn by thread 0 while the current tile is being walked, so a tile costs
   // three block barriers in total: [A] previous tile retired + ticket visible, [B] per-warp live
   // row counts visible, [C] staged rows + sentinels visible.
+  // Thread 0 also fetches the row window of the ticketed tile, so by the time the CTA reaches
+  // barrier [A] the only memory latency left in staging is one parallel round of loads
+  // (scan values + row bases).
+  auto draw_ticket = [&]() {
+    int t = atomicAdd(&p.ctrl->work, 1);
+    s_tile = t;
+    if (t < ntiles) {
+      s_row0 = p.tile_rows[t];
+      s_row1 = p.tile_rows[t + 1];
+    }
+  };
   if (threadIdx.x == 0)
-    s_tile = atomicAdd(&p.ctrl->work, 1);
+    draw_ticket();
   for (;;) {
     __syncthreads();  // [A]
     const int tile = s_tile;
@@ -605,16 +617,19 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
       break;
     const int r_begin = tile * kTile;
     const int r_end = min(total, r_begin + kTile);
-    const int row0 = p.tile_rows[tile];
-    const int row1 = min(n - 1, p.tile_rows[tile + 1]);  // last row that can overlap the tile
+    const int row0 = s_row0;
+    const int row1 = min(n - 1, s_row1);  // last row that can overlap the tile
     int nrows = 0;  // identical in every thread
     for (int i0 = row0; i0 <= row1; i0 += kThreads) {
       int i = i0 + threadIdx.x;
-      int sc = 0;
+      int sc = 0, rb = 0, vv = 0;
       bool live = false;
       if (i <= row1) {
         sc = scanned[i];
         int sc_next = scanned[i + 1];
+        rb = p.row_base[i];  // independent of the scan loads: one round of memory latency
+        if (kSrc)
+          vv = (kIn == advance_input_t::graph) ? i : p.in[i];
         live = sc_next > sc && sc < r_end && sc_next > r_begin;
       }
       unsigned m = __ballot_sync(kFull, live);
@@ -633,11 +648,10 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
       }
       if (live) {
         int slot = off + __popc(m & lanemask_lt());
-        int v = (kIn == advance_input_t::graph) ? i : p.in[i];
         s_rank[slot] = static_cast<unsigned short>(max(sc, r_begin) - r_begin);
-        s_base[slot] = ro[v] - sc;
+        s_base[slot] = rb - sc;
         if (kSrc)
-          s_vert[slot] = v;
+          s_vert[slot] = vv;
       }
       nrows += batch;
     }
@@ -646,7 +660,7 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
           static_cast<unsigned short>(r_end - r_begin);  // sentinels: no row starts past the tile
     __syncthreads();  // [C]
     if (threadIdx.x == 0)
-      s_tile = atomicAdd(&p.ctrl->work, 1);  // next ticket, consumed after barrier [A]
+      draw_ticket();  // next ticket + its row window, consumed after barrier [A]
     // Each warp owns a contiguous span of the tile and walks it 32 ranks at a time, so its row
     // cursor only moves forward: one binary search per span, then per chunk the row starts that
     // fall inside the 32 ranks are turned into a bit mask (one REDUX) and every lane derives its
@@ -708,6 +722,112 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
     atomicAdd(&p.ctrl->edges, static_cast<unsigned long long>(total));
 }
 
+/// Report of advance_tail_kernel (written to pinned host memory by the kernel).
+struct tail_report_t {
+  int levels;    // levels executed by this launch
+  int count;     // size of the frontier it stopped at
+  int cur;       // which of the two queues holds that frontier
+  int pad;
+  unsigned long long deg_sum;  // out-degree sum of that frontier
+  unsigned long long edges[16];
+  int frontier[16];
+};
+
+/**
+ * @brief Tail of a traversal in ONE launch: while the frontier stays tiny (its out-degree sum below
+ * `edge_budget`), a single CTA runs level after level -- warp per frontier vertex, ballot-compacted
+ * appends through a shared counter into the other global queue, one block barrier per level --
+ * instead of paying a launch + host round trip per level (RMAT traversals end with 2-4 levels of a
+ * few hundred edges each).  `make_op(level)` builds the level's edge functor.
+ */
+template <int kThreads, bool kWeights, typename OpMaker>
+__global__ void __launch_bounds__(kThreads)
+advance_tail_kernel(csr_view_t g, int* q0, int* q1, int* counts, int cur, int first_level,
+                    int max_levels, unsigned long long edge_budget, OpMaker make_op,
+                    tail_report_t* rep) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_deg, s_edges;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int* __restrict__ ro = g.row_offsets;
+  const int* __restrict__ ci = g.column_indices;
+  const float* __restrict__ vals = g.values;
+  int* q[2] = {q0, q1};
+  int n = counts[cur];
+  int level = first_level, done = 0;
+  unsigned long long deg_sum = 0;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      s_cnt = 0;
+      s_deg = 0;
+      s_edges = 0;
+    }
+    __syncthreads();
+    auto op = make_op(level);
+    const int* in = q[cur];
+    int* out = q[cur ^ 1];
+    unsigned long long my_deg = 0, my_edges = 0;
+    for (int i = warp; i < n; i += kWarps) {
+      const int v = in[i];
+      if (v < 0)
+        continue;
+      const int s = ro[v], d = ro[v + 1] - s;
+      if (lane == 0)
+        my_edges += static_cast<unsigned>(d);
+      for (int off = 0; off < d; off += 32) {
+        const int e = s + off + lane;
+        bool keep = false;
+        int nb = -1;
+        if (off + lane < d) {
+          nb = ci[e];
+          float w = (kWeights && vals) ? vals[e] : 1.0f;
+          keep = op(v, nb, e, w);
+        }
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (m) {
+          int base = 0;
+          if (lane == 0)
+            base = atomicAdd(&s_cnt, __popc(m));
+          base = __shfl_sync(kFull, base, 0);
+          if (keep) {
+            int x = op_emit(op, nb);
+            out[base + __popc(m & lanemask_lt())] = x;
+            my_deg += static_cast<unsigned>(ro[x + 1] - ro[x]);
+          }
+        }
+      }
+    }
+    my_deg = warp_sum(my_deg);
+    my_edges = warp_sum(my_edges);
+    if (lane == 0) {
+      if (my_deg)
+        atomicAdd(&s_deg, my_deg);
+      if (my_edges)
+        atomicAdd(&s_edges, my_edges);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && done < 16) {
+      rep->edges[done] = s_edges;
+      rep->frontier[done] = n;
+    }
+    n = s_cnt;
+    deg_sum = s_deg;
+    cur ^= 1;
+    ++level;
+    ++done;
+    if (n == 0 || deg_sum >= edge_budget || done >= max_levels)
+      break;
+    __syncthreads();  // everyone has read s_cnt / s_deg before they are cleared
+  }
+  if (threadIdx.x == 0) {
+    counts[cur] = n;
+    rep->levels = done;
+    rep->count = n;
+    rep->cur = cur;
+    rep->deg_sum = deg_sum;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------------------------
@@ -728,15 +848,22 @@ inline const int* frontier_degree_scan(workspace_t& ws,
                                        const csr_view_t& g,
                                        const int* in,
                                        const int* in_count,
-                                       int n_upper_bound) {
-  int* scanned = ws.scanned.ensure(static_cast<size_t>(n_upper_bound) + 2);
+                                       int n_upper_bound,
+                                       const int** row_base_out) {
+  int* scanned = ws.scanned.ensure(2 * static_cast<size_t>(n_upper_bound) + 4);
+  int* row_base = scanned + n_upper_bound + 2;  // CSR offset of every frontier row
   const int* ro = g.row_offsets;
   auto value = [=] __device__(int i) -> int {
     int v = in[i];
     return v >= 0 ? ro[v + 1] - ro[v] : 0;
   };
-  auto emit = [=] __device__(int i, int excl, int) { scanned[i] = excl; };
+  auto emit = [=] __device__(int i, int excl, int) {
+    scanned[i] = excl;
+    int v = in[i];
+    row_base[i] = v >= 0 ? ro[v] : 0;
+  };
   lookback_scan(ws, in_count, 0, n_upper_bound, value, emit, nullptr, scanned);
+  *row_base_out = row_base;
   return scanned;
 }
 
@@ -783,8 +910,10 @@ inline void launch_advance(workspace_t& ws,
           <<<grid, kThreads, 0, ws.stream>>>(p, op);
   } else if (cfg.lb == lb_t::merge_path) {
     // the CSR offsets ARE the degree scan when the whole graph is the frontier
-    const int* scanned =
-        graph_in ? g.row_offsets : frontier_degree_scan(ws, g, in, in_count, in_upper_bound);
+    const int* row_base = g.row_offsets;  // whole graph: row i starts at row_offsets[i]
+    const int* scanned = graph_in ? g.row_offsets
+                                  : frontier_degree_scan(ws, g, in, in_count, in_upper_bound, &row_base);
+    p.row_base = row_base;
     // ranks are int32 (as in the reference, merge_path.hxx:325-327), so 2^31/kTile tiles bound
     // every possible frontier, duplicates included.
     int* tile_rows = ws.tile_rows.ensure((static_cast<size_t>(1) << 31) / kTile + 4);

@@ -52,6 +52,15 @@ struct bfs_claim_op {
   }
 };
 
+/// Builds the claim functor of a given level (advance_tail_kernel runs several levels per launch).
+struct bfs_claim_maker {
+  unsigned* visited;
+  int* dist;
+  __device__ __forceinline__ bfs_claim_op operator()(int level) const {
+    return bfs_claim_op{visited, dist, level + 1};
+  }
+};
+
 /// The reference's own functor (bfs.hxx:105-128), kept selectable for like-for-like runs.
 struct bfs_atomic_min_op {
   static constexpr bool kNeedsSource = false;
@@ -239,10 +248,13 @@ struct bfs_scratch_t {
     unsigned long long edges;
   };
   host_fb_t* h_fb = nullptr;  // pinned
+  tail_report_t* h_tail = nullptr;  // pinned
   cudaEvent_t ev[128] = {};   // per-level event pairs (first 64 levels are timed)
   ~bfs_scratch_t() {
     if (h_fb)
       cudaFreeHost(h_fb);
+    if (h_tail)
+      cudaFreeHost(h_tail);
     for (auto e : ev)
       if (e)
         cudaEventDestroy(e);
@@ -257,6 +269,8 @@ struct bfs_scratch_t {
     counts.ensure(4);
     if (!h_fb)
       B2G_CHECK(cudaMallocHost(&h_fb, sizeof(host_fb_t)));
+    if (!h_tail)
+      B2G_CHECK(cudaMallocHost(&h_tail, sizeof(tail_report_t)));
     if (!ev[0])
       for (auto& e : ev)
         B2G_CHECK(cudaEventCreate(&e));
@@ -307,6 +321,36 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   unsigned* fbm = sc.fbm.ptr;
   unsigned* nbm = sc.nbm.ptr;
   while (n_f > 0) {
+    // ---- tiny queue frontier: run the tail of the traversal in one single-CTA launch ------------
+    if (level > 0 && !bottom_up && !cfg.use_atomic_min_op &&
+        static_cast<long long>(m_f) < cfg.advance.small_frontier_edges) {
+      if (level < 64)
+        B2G_CHECK(cudaEventRecord(sc.ev[2 * level], st));
+      advance_tail_kernel<1024, false><<<1, 1024, 0, st>>>(
+          out_g, sc.q[0].ptr, sc.q[1].ptr, sc.counts.ptr, cur, level, 16,
+          static_cast<unsigned long long>(cfg.advance.small_frontier_edges),
+          bfs_claim_maker{sc.visited.ptr, dist}, sc.h_tail);
+      if (level < 64)
+        B2G_CHECK(cudaEventRecord(sc.ev[2 * level + 1], st));
+      ws.launches += 1;
+      B2G_CHECK(cudaStreamSynchronize(st));
+      const tail_report_t& t = *sc.h_tail;
+      for (int k = 0; k < t.levels; ++k) {
+        explored += t.edges[k];
+        if (levels)
+          levels->push_back({0, t.frontier[k], t.edges[k], t.edges[k]});
+      }
+      // events were recorded once for the whole launch: later levels of it report 0 ms
+      for (int k = 1; k < t.levels && level + k < 64; ++k) {
+        B2G_CHECK(cudaEventRecord(sc.ev[2 * (level + k)], st));
+        B2G_CHECK(cudaEventRecord(sc.ev[2 * (level + k) + 1], st));
+      }
+      level += t.levels;
+      cur = t.cur;
+      n_f = t.count;
+      m_f = t.deg_sum;
+      continue;
+    }
     // ---- choose direction for this level (Beamer et al.) --------------------------------
     bool want_bottom_up = bottom_up;
     if (can_pull && level > 0) {

@@ -63,6 +63,14 @@ struct sssp_relax_op {
   }
 };
 
+struct sssp_relax_maker {
+  float* dist;
+  int* stamp;
+  __device__ __forceinline__ sssp_relax_op operator()(int iteration) const {
+    return sssp_relax_op{dist, stamp, iteration};
+  }
+};
+
 static __global__ void sssp_reset_kernel(float* dist, int* stamp, int n_vertices, int source, int* q0,
                                   int* counts) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vertices;
@@ -88,10 +96,13 @@ struct sssp_scratch_t {
     unsigned long long deg_sum;
   };
   host_fb_t* h_fb = nullptr;
+  tail_report_t* h_tail = nullptr;
   cudaEvent_t ev[128] = {};
   ~sssp_scratch_t() {
     if (h_fb)
       cudaFreeHost(h_fb);
+    if (h_tail)
+      cudaFreeHost(h_tail);
     for (auto e : ev)
       if (e)
         cudaEventDestroy(e);
@@ -103,6 +114,8 @@ struct sssp_scratch_t {
     counts.ensure(4);
     if (!h_fb)
       B2G_CHECK(cudaMallocHost(&h_fb, sizeof(host_fb_t)));
+    if (!h_tail)
+      B2G_CHECK(cudaMallocHost(&h_tail, sizeof(tail_report_t)));
     if (!ev[0])
       for (auto& e : ev)
         B2G_CHECK(cudaEventCreate(&e));
@@ -138,6 +151,32 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
   long long n_f = 1;
   unsigned long long m_f = 0;  // out-degree sum of the frontier (0 = unknown, first iteration)
   while (n_f > 0) {
+    // tiny frontier: finish (or continue) the run inside one single-CTA launch
+    if (iteration > 0 && static_cast<long long>(m_f) < cfg.small_frontier_edges) {
+      if (iteration < 64)
+        B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration], st));
+      advance_tail_kernel<1024, true><<<1, 1024, 0, st>>>(
+          g, sc.q[0].ptr, sc.q[1].ptr, sc.counts.ptr, cur, iteration, 16,
+          static_cast<unsigned long long>(cfg.small_frontier_edges),
+          sssp_relax_maker{dist, sc.stamp.ptr}, sc.h_tail);
+      if (iteration < 64)
+        B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration + 1], st));
+      ws.launches += 1;
+      B2G_CHECK(cudaStreamSynchronize(st));
+      const tail_report_t& t = *sc.h_tail;
+      for (int k = 0; k < t.levels; ++k)
+        if (levels)
+          levels->push_back({t.frontier[k], t.edges[k]});
+      for (int k = 1; k < t.levels && iteration + k < 64; ++k) {
+        B2G_CHECK(cudaEventRecord(sc.ev[2 * (iteration + k)], st));
+        B2G_CHECK(cudaEventRecord(sc.ev[2 * (iteration + k) + 1], st));
+      }
+      iteration += t.levels;
+      cur = t.cur;
+      n_f = t.count;
+      m_f = t.deg_sum;
+      continue;
+    }
     int nxt = cur ^ 1;
     B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
     sssp_relax_op op{dist, sc.stamp.ptr, iteration};
