@@ -226,7 +226,7 @@ def run_partitioned(args, wl, name, rank, world, local):
     direction = getattr(gb.advance_direction_t, wl["direction"])
 
     def step():
-        return mg.bfs_rank(eng, comm, src, total_edges, direction=direction)
+        return mg.bfs_rank_async(eng, comm, src, total_edges, direction=direction)
 
     for _ in range(max(args.warmup, 3)):
         dloc, st = step()

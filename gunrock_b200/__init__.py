@@ -109,7 +109,9 @@ _SYMBOLS = [
     "b2g_graph_create_rmat_part", "b2g_graph_create_csr_part", "b2g_part_info", "b2g_part_bfs_begin",
     "b2g_part_bfs_topdown", "b2g_part_bfs_send_buffer", "b2g_part_bfs_claim",
     "b2g_part_bfs_frontier_bitmap", "b2g_part_bfs_bottomup", "b2g_part_bfs_end_level",
-    "b2g_part_bfs_distances",
+    "b2g_part_bfs_distances", "b2g_part_set_stream", "b2g_part_bfs_topdown_async",
+    "b2g_part_bfs_claim_packed_async", "b2g_part_bfs_frontier_bitmap_async",
+    "b2g_part_bfs_bottomup_async", "b2g_part_bfs_end_level_async",
 ]
 
 

@@ -996,10 +996,8 @@ int b2g_part_bfs_end_level(b2g_graph_t* g, long long* n_frontier, long long* fro
     unsigned long long extra = 0;
     int count = 0;
     if (g->part_level_dir == 1) {  // bottom-up produced a bitmap
-      unsigned* t = S.fbm.ptr;
       std::swap(S.fbm.ptr, S.nbm.ptr);
       std::swap(S.fbm.cap, S.nbm.cap);
-      (void)t;
       S.frontier_is_bitmap = true;
       B2G_CHECK(cudaMemcpyAsync(&count, S.counts.ptr + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
     } else {
@@ -1018,6 +1016,137 @@ int b2g_part_bfs_end_level(b2g_graph_t* g, long long* n_frontier, long long* fro
       *n_frontier = count;
     if (frontier_degree)
       *frontier_degree = static_cast<long long>(ds + extra);
+    return 0;
+  });
+}
+
+// ---- sync-free variants ------------------------------------------------------------------------
+int b2g_part_set_stream(b2g_graph_t* g, void* stream) {
+  if (!g)
+    return fail(B2G_ERR_INVALID, "null graph");
+  return guarded([&] {
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g->own_stream;
+    if (s != g->ws.stream) {
+      B2G_CHECK(cudaStreamSynchronize(g->ws.stream));
+      g->ws.stream = s;
+    }
+    return 0;
+  });
+}
+
+int b2g_part_bfs_topdown_async(b2g_graph_t* g, int level, const b2g_options_t* opt, int* msg,
+                               int cap_s) {
+  if (!g || !g->partitioned || !msg || cap_s < 1)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_topdown_async: bad arguments");
+  return guarded([&] {
+    b2g_options_t o = resolved(opt);
+    cudaStream_t st = g->ws.stream;
+    auto& S = g->part;
+    const int sms = device_info_t::get().sm_count;
+    if (S.frontier_is_bitmap) {
+      B2G_CHECK(cudaMemsetAsync(S.counts.ptr + S.cur, 0, sizeof(int), st));
+      bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(S.fbm.ptr, S.local_words(), S.q[S.cur].ptr,
+                                                      S.counts.ptr + S.cur);
+      g->ws.launches += 1;
+      S.frontier_is_bitmap = false;
+    }
+    const int nxt = S.cur ^ 1;
+    B2G_CHECK(cudaMemsetAsync(S.counts.ptr + nxt, 0, sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
+    part_claim_op op{g->pt,       S.visited.ptr,  S.sent.ptr,        S.dist.ptr, level + 1,
+                     S.send_buf.ptr, S.send_count.ptr, S.send_cap, S.overflow.ptr};
+    ctrl_t* c = nullptr;
+    launch_advance<advance_output_t::vertices, true, false>(
+        g->ws, g->view, S.q[S.cur].ptr, S.counts.ptr + S.cur, g->pt.n_local, S.q[nxt].ptr,
+        S.counts.ptr + nxt, g->pt.n_local, op, to_launch(o), &c);
+    g->part_ctrl = c;
+    dim3 grid(32, g->pt.nparts);
+    part_pack_kernel<<<grid, 256, 0, st>>>(S.send_buf.ptr, S.send_count.ptr, S.send_cap,
+                                           g->pt.nparts, cap_s, msg);
+    g->ws.launches += 1;
+    g->part_level_dir = 0;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_bfs_claim_packed_async(b2g_graph_t* g, int level, const int* msgs, int cap_s) {
+  if (!g || !g->partitioned || !msgs)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_claim_packed_async: bad arguments");
+  return guarded([&] {
+    auto& S = g->part;
+    const int nxt = S.cur ^ 1;
+    dim3 grid(64, g->pt.nparts);
+    part_claim_packed_kernel<<<grid, 256, 0, g->ws.stream>>>(
+        g->pt, msgs, cap_s, S.visited.ptr, S.dist.ptr, level + 1, g->view.row_offsets, S.q[nxt].ptr,
+        S.counts.ptr + nxt, g->part_deg.ptr, S.overflow.ptr);
+    g->ws.launches += 1;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_bfs_frontier_bitmap_async(b2g_graph_t* g, unsigned* out) {
+  if (!g || !g->partitioned || !out)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_frontier_bitmap_async: bad arguments");
+  return guarded([&] {
+    auto& S = g->part;
+    cudaStream_t st = g->ws.stream;
+    const size_t bytes = sizeof(unsigned) * static_cast<size_t>(S.words_per_rank());
+    if (S.frontier_is_bitmap) {
+      B2G_CHECK(cudaMemcpyAsync(out, S.fbm.ptr, bytes, cudaMemcpyDeviceToDevice, st));
+    } else {
+      B2G_CHECK(cudaMemsetAsync(out, 0, bytes, st));
+      part_queue_to_bitmap_kernel<<<device_info_t::get().sm_count * 4, 256, 0, st>>>(
+          S.q[S.cur].ptr, S.counts.ptr + S.cur, out);
+      g->ws.launches += 1;
+    }
+    return 0;
+  });
+}
+
+int b2g_part_bfs_bottomup_async(b2g_graph_t* g, int level, const unsigned* frontier_all) {
+  if (!g || !g->partitioned || !frontier_all)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_bottomup_async: bad arguments");
+  return guarded([&] {
+    auto& S = g->part;
+    cudaStream_t st = g->ws.stream;
+    build_transpose(g);
+    ctrl_t* c = g->ws.next_ctrl();
+    B2G_CHECK(cudaMemsetAsync(S.counts.ptr + 2, 0, sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(S.nbm.ptr, 0, sizeof(unsigned) * S.words_per_rank(), st));
+    part_bottom_up_kernel<256, 8><<<device_info_t::get().sm_count * 8, 256, 0, st>>>(
+        g->pt, g->t_view, S.words_per_rank(), S.visited.ptr, frontier_all, S.nbm.ptr, S.dist.ptr,
+        level + 1, c, S.counts.ptr + 2);
+    g->part_ctrl = c;
+    g->ws.launches += 1;
+    g->part_level_dir = 1;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_bfs_end_level_async(b2g_graph_t* g, long long* stats) {
+  if (!g || !g->partitioned || !stats)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_end_level_async: bad arguments");
+  return guarded([&] {
+    auto& S = g->part;
+    cudaStream_t st = g->ws.stream;
+    const int* count_ptr;
+    if (g->part_level_dir == 1) {
+      std::swap(S.fbm.ptr, S.nbm.ptr);
+      std::swap(S.fbm.cap, S.nbm.cap);
+      S.frontier_is_bitmap = true;
+      count_ptr = S.counts.ptr + 2;
+    } else {
+      S.cur ^= 1;
+      S.frontier_is_bitmap = false;
+      count_ptr = S.counts.ptr + S.cur;
+    }
+    part_stats_kernel<<<1, 1, 0, st>>>(count_ptr, g->part_ctrl, g->part_deg.ptr, S.overflow.ptr, stats);
+    g->ws.launches += 1;
+    g->part_ctrl = nullptr;
+    B2G_CHECK(cudaGetLastError());
     return 0;
   });
 }

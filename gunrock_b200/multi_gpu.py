@@ -45,6 +45,12 @@ def _bind():
     L.b2g_part_bfs_end_level.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.b2g_part_bfs_distances.argtypes = [vp, vp, ip]
     L.b2g_graph_destroy.argtypes = [vp]
+    L.b2g_part_set_stream.argtypes = [vp, vp]
+    L.b2g_part_bfs_topdown_async.argtypes = [vp, ip, C.POINTER(_Options), vp, ip]
+    L.b2g_part_bfs_claim_packed_async.argtypes = [vp, ip, vp, ip]
+    L.b2g_part_bfs_frontier_bitmap_async.argtypes = [vp, vp]
+    L.b2g_part_bfs_bottomup_async.argtypes = [vp, ip, vp]
+    L.b2g_part_bfs_end_level_async.argtypes = [vp, vp]
     L._mg_bound = True
     return L
 
@@ -182,6 +188,31 @@ class CudaRankEngine:
         n, m = C.c_longlong(), C.c_longlong()
         _check(self.L.b2g_part_bfs_end_level(self.G._h, C.byref(n), C.byref(m)), "b2g_part_bfs_end_level")
         return int(n.value), int(m.value)
+
+    # ---- sync-free steps (enqueued on torch's current stream) ---------------------------------
+    def use_stream(self, stream=None):
+        s = stream if stream is not None else self.torch.cuda.current_stream()
+        _check(self.L.b2g_part_set_stream(self.G._h, s.cuda_stream), "b2g_part_set_stream")
+
+    def topdown_async(self, level: int, msg, cap_s: int):
+        _check(self.L.b2g_part_bfs_topdown_async(self.G._h, level, C.byref(self.opt), msg.data_ptr(), cap_s),
+               "b2g_part_bfs_topdown_async")
+
+    def claim_packed_async(self, level: int, msgs, cap_s: int):
+        _check(self.L.b2g_part_bfs_claim_packed_async(self.G._h, level, msgs.data_ptr(), cap_s),
+               "b2g_part_bfs_claim_packed_async")
+
+    def frontier_bitmap_async(self):
+        _check(self.L.b2g_part_bfs_frontier_bitmap_async(self.G._h, self._bitmap.data_ptr()),
+               "b2g_part_bfs_frontier_bitmap_async")
+        return self._bitmap
+
+    def bottomup_async(self, level: int, frontier_all):
+        _check(self.L.b2g_part_bfs_bottomup_async(self.G._h, level, frontier_all.data_ptr()),
+               "b2g_part_bfs_bottomup_async")
+
+    def end_level_async(self, stats):
+        _check(self.L.b2g_part_bfs_end_level_async(self.G._h, stats.data_ptr()), "b2g_part_bfs_end_level_async")
 
     def distances(self):
         d = self.torch.empty(self.n_local, dtype=self.torch.int32, device="cuda")
@@ -322,6 +353,58 @@ def bfs_rank(engine, comm, source: int, total_edges: int, direction: int = advan
         level += 1
     st.levels = level
     return engine.distances(), st
+
+
+def bfs_rank_async(engine, comm, source: int, total_edges: int,
+                   direction: int = advance_direction_t.optimized, alpha: float = 14.0, beta: float = 24.0,
+                   cap_s: int = 0):
+    """Same algorithm as ``bfs_rank`` with ONE host synchronisation per level.
+
+    Every per-rank step and every collective is enqueued on torch's current stream: the top-down
+    exchange is a fixed-split ``all_to_all_single`` of packed rows ``[count, ids...]`` (so no count
+    round trip is needed), the level statistics are all-reduced as a device tensor and only then read.
+    If a packed row overflows ``cap_s`` ids the run is repeated on the two-phase path (``bfs_rank``)."""
+    torch, dist = comm.torch, comm.dist
+    P = comm.world
+    cap_s = cap_s or min(rows_of(engine.n_global, P, 0) + 64, 1 << 20)
+    engine.begin(source)
+    engine.use_stream()
+    msg = torch.zeros((P, cap_s + 1), dtype=torch.int32, device="cuda")
+    msgs_in = torch.zeros_like(msg)
+    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    st = part_bfs_stats_t()
+    n_f, m_f, explored, level, bottom_up = 1, 0, 0, 0, False
+    while n_f > 0:
+        go_up = _decide(direction, level, bottom_up, n_f, m_f, explored, engine.n_global, total_edges, alpha, beta)
+        if level > 0:
+            explored += m_f
+        if go_up:
+            allbm = comm.all_gather_bitmap(engine.frontier_bitmap_async())
+            engine.bottomup_async(level, allbm)
+        else:
+            engine.topdown_async(level, msg, cap_s)
+            if P > 1:
+                dist.all_to_all_single(msgs_in, msg, group=comm.group)
+                engine.claim_packed_async(level, msgs_in, cap_s)
+        engine.end_level_async(stats)
+        if P > 1:
+            dist.all_reduce(stats, group=comm.group)
+        g = [int(x) for x in stats.tolist()]          # the level's only host synchronisation
+        if g[3]:
+            engine.L.b2g_part_set_stream(engine.G._h, None)
+            return bfs_rank(engine, comm, source, total_edges, direction, alpha, beta)
+        st.level_direction.append(1 if go_up else 0)
+        st.level_frontier.append(n_f)
+        st.level_edges.append(g[2])
+        st.edges_touched += g[2]
+        if level == 0:
+            explored += g[2]
+        n_f, m_f, bottom_up = g[0], g[1], go_up
+        level += 1
+    st.levels = level
+    d = engine.distances()
+    engine.L.b2g_part_set_stream(engine.G._h, None)
+    return d, st
 
 
 # ---------------------------------------------------------------------------------------------

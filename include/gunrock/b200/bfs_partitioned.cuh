@@ -329,6 +329,77 @@ struct part_bfs_state_t {
   }
 };
 
+/// Fixed-layout message for the sync-free exchange: row o = [count_o, ids ... (<= cap_s)].
+static __global__ void part_pack_kernel(const int* __restrict__ send_buf, const int* __restrict__ send_count,
+                                        int send_cap, int nparts, int cap_s, int* __restrict__ msg) {
+  for (int o = blockIdx.y; o < nparts; o += gridDim.y) {
+    const int n = send_count[o];
+    int* row = msg + static_cast<size_t>(o) * (cap_s + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      row[0] = n;
+    const int m = min(n, cap_s);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+      row[1 + i] = send_buf[static_cast<size_t>(o) * send_cap + i];
+  }
+}
+
+/// Claim the ids of every peer's packed message (rows of cap_s+1 ints); a message whose count
+/// exceeds cap_s raises *overflow (the host then falls back to the two-phase exchange).
+static __global__ void part_claim_packed_kernel(partition_t pt, const int* __restrict__ msgs, int cap_s,
+                                                unsigned* visited, int* dist, int next_level,
+                                                const int* __restrict__ ro, int* out, int* out_count,
+                                                unsigned long long* deg_sum, int* overflow) {
+  const int lane = lane_id();
+  unsigned long long ds = 0;
+  for (int src = blockIdx.y; src < pt.nparts; src += gridDim.y) {
+    if (src == pt.part)
+      continue;
+    const int* row = msgs + static_cast<size_t>(src) * (cap_s + 1);
+    int n = row[0];
+    if (n > cap_s) {
+      if (blockIdx.x == 0 && threadIdx.x == 0)
+        *overflow = 1;
+      n = cap_s;
+    }
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < n; i0 += gridDim.x * blockDim.x) {
+      int i = i0 + lane;
+      bool won = false;
+      int l = 0;
+      if (i < n) {
+        l = pt.local(row[1 + i]);
+        won = bitmap_test_and_set(visited, l);
+        if (won) {
+          dist[l] = next_level;
+          ds += static_cast<unsigned>(ro[l + 1] - ro[l]);
+        }
+      }
+      unsigned m = __ballot_sync(kFull, won);
+      if (m) {
+        int base = 0;
+        if (lane == 0)
+          base = atomicAdd(out_count, __popc(m));
+        base = __shfl_sync(kFull, base, 0);
+        if (won)
+          out[base + __popc(m & lanemask_lt())] = l;
+      }
+    }
+  }
+  ds = warp_sum(ds);
+  if (lane == 0 && ds)
+    atomicAdd(deg_sum, ds);
+}
+
+/// Level statistics into a device tensor (int64[4]: frontier size, its out-degree sum, edges
+/// inspected, overflow) -- all-reduced by the host side without reading them first.
+static __global__ void part_stats_kernel(const int* count, const ctrl_t* c, unsigned long long* extra_deg,
+                                         const int* overflow, long long* stats) {
+  stats[0] = *count;
+  stats[1] = static_cast<long long>((c ? c->deg_sum : 0) + *extra_deg);
+  stats[2] = static_cast<long long>(c ? c->edges : 0);
+  stats[3] = (c ? c->overflow : 0) | *overflow;
+  *extra_deg = 0;
+}
+
 static __global__ void part_feedback_kernel(const int* count, const ctrl_t* c, const int* send_count,
                                             const int* overflow, int nparts,
                                             part_bfs_state_t::host_fb_t* fb) {

@@ -195,6 +195,20 @@ int b2g_part_bfs_bottomup(b2g_graph_t* g, int level, const unsigned* frontier_al
                           unsigned long long* edges_touched);
 /* Close the level: returns this rank's next-frontier size and its out-degree sum. */
 int b2g_part_bfs_end_level(b2g_graph_t* g, long long* n_frontier, long long* frontier_degree);
+/* --- sync-free variants: everything is enqueued on `stream` (e.g. torch's current stream, so the
+ * NCCL collectives between the calls are stream ordered) and nothing is read back by the host;
+ * the only host synchronisation of a level is the caller's read of the all-reduced statistics. */
+int b2g_part_set_stream(b2g_graph_t* g, void* stream);
+/* top-down + pack: msg (device) = nparts rows of [count, ids ...] with cap_s id slots each. */
+int b2g_part_bfs_topdown_async(b2g_graph_t* g, int level, const b2g_options_t* opt, int* msg,
+                               int cap_s);
+/* claim every peer's packed row (msgs = nparts rows of cap_s+1 ints, as delivered by a fixed-split
+ * all-to-all).  A row whose count exceeds cap_s sets the level's overflow statistic. */
+int b2g_part_bfs_claim_packed_async(b2g_graph_t* g, int level, const int* msgs, int cap_s);
+int b2g_part_bfs_frontier_bitmap_async(b2g_graph_t* g, unsigned* out);
+int b2g_part_bfs_bottomup_async(b2g_graph_t* g, int level, const unsigned* frontier_all);
+/* stats (device, int64[4]) = {next frontier size, its out-degree sum, edges inspected, overflow}. */
+int b2g_part_bfs_end_level_async(b2g_graph_t* g, long long* stats);
 /* Copy the rank's slice of the distances (n_local ints, local row order). */
 int b2g_part_bfs_distances(b2g_graph_t* g, int* distances, int loc);
 

@@ -29,11 +29,13 @@ def main():
         for direction in (gb.advance_direction_t.forward, gb.advance_direction_t.optimized):
             for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
                 eng = mg.CudaRankEngine(G, gb.options_t(advance_load_balance=lb))
-                d, st = mg.bfs_rank(eng, mg.TorchDistComm(), src, total_edges=len(ci), direction=direction)
-                ok = bool(np.array_equal(d.cpu().numpy(), exp[rank::world]))
-                t = torch.tensor([int(ok)], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MIN)
-                results[f"{name}/{direction}/{lb}"] = [int(t.item()), st.level_direction, st.exchanged_ids]
+                for variant, fn, kw in (("2phase", mg.bfs_rank, {}), ("async", mg.bfs_rank_async, {}),
+                                        ("async-overflow", mg.bfs_rank_async, {"cap_s": 16})):
+                    d, st = fn(eng, mg.TorchDistComm(), src, total_edges=len(ci), direction=direction, **kw)
+                    ok = bool(np.array_equal(d.cpu().numpy(), exp[rank::world]))
+                    t = torch.tensor([int(ok)], device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    results[f"{name}/{direction}/{lb}/{variant}"] = [int(t.item()), st.level_direction]
         G.close()
     if rank == 0:
         print("MG_RESULT " + json.dumps(results), flush=True)

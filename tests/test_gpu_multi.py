@@ -72,4 +72,29 @@ def test_nccl_two_or_more_gpus(gb):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("MG_RESULT ")][-1]
     res = json.loads(line[len("MG_RESULT "):])
-    assert len(res) == 8 and all(v[0] == 1 for v in res.values()), res
+    assert len(res) == 24 and all(v[0] == 1 for v in res.values()), res
+
+
+def test_async_driver_single_rank(gb):
+    """world_size 1 under NCCL: the sync-free level loop (one host sync per level) on one GPU."""
+    import torch
+    import torch.distributed as dist
+    from gunrock_b200 import multi_gpu as mg
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29622")
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        ro, ci = oracle.rmat_csr(15, 16, 77)
+        G = mg.PartitionedGraph.from_global_csr(ro, ci, 1, 0)
+        src = int(np.diff(ro).argmax())
+        exp = oracle.bfs(ro, ci, src)
+        for direction in (gb.advance_direction_t.forward, gb.advance_direction_t.optimized):
+            eng = mg.CudaRankEngine(G)
+            d, st = mg.bfs_rank_async(eng, mg.TorchDistComm(), src, len(ci), direction=direction)
+            assert np.array_equal(d.cpu().numpy(), exp)
+            d, st = mg.bfs_rank(eng, mg.TorchDistComm(), src, len(ci), direction=direction)
+            assert np.array_equal(d.cpu().numpy(), exp)
+        G.close()
+    finally:
+        dist.destroy_process_group()
