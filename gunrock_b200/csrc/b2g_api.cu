@@ -855,8 +855,20 @@ int b2g_part_bfs_begin(b2g_graph_t* g, int source, int send_capacity) {
     g->part_deg.ensure(2);
     const int sms = device_info_t::get().sm_count;
     const int sent_words = (g->pt.n_global + 31) / 32;
+    const unsigned* premark = nullptr;
+    if (g->symmetric) {  // the local CSR doubles as the local CSC only for symmetric graphs
+      build_transpose(g);
+      if (S.unreachable_for != g->t_view.row_offsets) {
+        S.unreachable.ensure(static_cast<size_t>(S.words_per_rank()) + 4);
+        bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(g->t_view.row_offsets, g->pt.n_local,
+                                                            S.unreachable.ptr);
+        S.unreachable_for = g->t_view.row_offsets;
+        g->ws.launches += 1;
+      }
+      premark = S.unreachable.ptr;
+    }
     part_reset_kernel<<<sms * 8, 256, 0, st>>>(g->pt, source, S.dist.ptr, S.visited.ptr, S.sent.ptr,
-                                                sent_words, S.q[0].ptr, S.counts.ptr);
+                                                sent_words, S.q[0].ptr, S.counts.ptr, premark);
     part_seed_kernel<<<1, 1, 0, st>>>(g->pt, source, S.dist.ptr, S.visited.ptr);
     B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
     B2G_CHECK(cudaMemsetAsync(S.overflow.ptr, 0, sizeof(int), st));
@@ -964,6 +976,8 @@ int b2g_part_bfs_bottomup(b2g_graph_t* g, int level, const unsigned* frontier_al
                           unsigned long long* edges_touched) {
   if (!g || !g->partitioned || !frontier_all)
     return fail(B2G_ERR_INVALID, "b2g_part_bfs_bottomup: bad arguments");
+  if (!g->symmetric)
+    return fail(B2G_ERR_INVALID, "bottom-up on a partitioned graph needs a symmetric graph (the local CSR is its own CSC)");
   return guarded([&] {
     auto& S = g->part;
     cudaStream_t st = g->ws.stream;
@@ -1108,6 +1122,8 @@ int b2g_part_bfs_frontier_bitmap_async(b2g_graph_t* g, unsigned* out) {
 int b2g_part_bfs_bottomup_async(b2g_graph_t* g, int level, const unsigned* frontier_all) {
   if (!g || !g->partitioned || !frontier_all)
     return fail(B2G_ERR_INVALID, "b2g_part_bfs_bottomup_async: bad arguments");
+  if (!g->symmetric)
+    return fail(B2G_ERR_INVALID, "bottom-up on a partitioned graph needs a symmetric graph (the local CSR is its own CSC)");
   return guarded([&] {
     auto& S = g->part;
     cudaStream_t st = g->ws.stream;

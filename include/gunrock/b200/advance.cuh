@@ -168,21 +168,35 @@ struct advance_params_t {
   const int* row_base = nullptr;   // merge_path: CSR offset of every frontier row (next to the scan)
 };
 
-constexpr int kEmitCap = 128;       // ints per warp in the staging buffer
-constexpr int kSmallCap = 32 * 31;  // max packed short-row edges per warp pass
+constexpr int kEmitCap = 128;  // ints per warp in the staging buffer
 
 /**
- * @brief Degree-binned persistent advance ("block_mapped" in the reference's enum).
- * One warp fetches 32 frontier entries at a time; hubs are deferred, rows >= 32 edges are walked
- * by the whole warp (coalesced), the rest are packed with a warp scan + shared owner table.
+ * @brief "block_mapped": equal number of frontier entries per CTA, as in the reference
+ * (block_mapped.hxx:67-191: CTA loads 256 entries, block-scans their degrees, threads stride over
+ * the CTA's edge range and binary-search the owner per edge), rebuilt around the merge_path walk:
+ *   - a persistent CTA draws 256 entries per ticket; rows >= hub_threshold (or >= 256 edges when the
+ *     CTA's share would exceed kCtaBudget) are deferred to the grid bin (TMA slab kernel);
+ *   - the remaining degrees are block-scanned and the non-empty rows compacted into shared memory;
+ *   - every warp then walks 256-rank spans of the CTA's rank space: one binary search per span, row
+ *     starts inside each 32 ranks turned into a bit mask with one REDUX, kBatch chunks of loads in
+ *     flight -- no per-edge search, no separate warp / thread bins.
+ * Four block barriers per 256 entries; shared memory 7 KiB, so L1 keeps ~200 KiB for the probes.
  */
 template <int kThreads, advance_input_t kIn, advance_output_t kOut, bool kDegSum, bool kWeights,
           typename Op>
 __global__ void __launch_bounds__(kThreads)
 advance_binned_kernel(advance_params_t p, Op op) {
   constexpr int kWarps = kThreads / 32;
+  constexpr int kSpan = 256;            // ranks per warp span
+  constexpr int kCtaBudget = 1 << 16;   // edges a CTA keeps for itself per ticket
+  constexpr int kSpill = 256;           // rows at least this long are deferred when over budget
+  constexpr bool kSrc = op_needs_source<Op>::value;
   __shared__ int s_emit[kWarps][kEmitCap];
-  __shared__ unsigned char s_owner[kWarps][kSmallCap + 32];
+  __shared__ int s_rank[kThreads + 36];  // first rank of each live row of this ticket
+  __shared__ int s_base[kThreads + 36];  // (CSR offset of the row's first edge) - (its first rank)
+  __shared__ int s_vert[kSrc ? kThreads + 36 : 1];
+  __shared__ int s_wsum[kWarps], s_wlive[kWarps], s_wlong[kWarps];
+  __shared__ int s_ticket;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int* __restrict__ ro = p.g.row_offsets;
   const int* __restrict__ ci = p.g.column_indices;
@@ -193,14 +207,14 @@ advance_binned_kernel(advance_params_t p, Op op) {
   em.init(s_emit[warp], p.out, p.out_count, p.out_capacity, ro, p.ctrl);
   unsigned long long edges_seen = 0;
 
+  if (threadIdx.x == 0)
+    s_ticket = atomicAdd(&p.ctrl->work, kThreads);
   for (;;) {
-    int base = 0;
-    if (lane == 0)
-      base = atomicAdd(&p.ctrl->work, 32);
-    base = __shfl_sync(kFull, base, 0);
+    __syncthreads();  // [A] previous ticket retired, new ticket visible
+    const int base = s_ticket;
     if (base >= n)
       break;
-    int idx = base + lane;
+    const int idx = base + threadIdx.x;
     int v = -1;
     if (idx < n)
       v = (kIn == advance_input_t::graph) ? idx : p.in[idx];
@@ -210,41 +224,85 @@ advance_binned_kernel(advance_params_t p, Op op) {
       deg = ro[v + 1] - start;
     }
     edges_seen += static_cast<unsigned>(deg);
-    // -- grid bin: defer hubs ------------------------------------------------------------
-    // A warp that drew many long rows would become the tail of the kernel (32 rows of up to
-    // hub_threshold edges, walked one after the other).  Bound its share: when the rows >= 32
-    // edges add up to more than kWarpBudget, everything >= kSpill edges goes to the slab bin too.
-    constexpr int kWarpBudget = 8192, kSpill = 256;
-    const int long_sum = warp_sum(deg >= 32 ? deg : 0);
-    const int defer_at = (long_sum > kWarpBudget && p.hub_threshold < (1 << 30))
+    // ---- grid bin --------------------------------------------------------------------------
+    const int wl = warp_sum(deg >= kSpill ? deg : 0);
+    if (lane == 0)
+      s_wlong[warp] = wl;
+    __syncthreads();  // [B1]
+    int cta_long = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w)
+      cta_long += s_wlong[w];
+    const int defer_at = (cta_long > kCtaBudget && p.hub_threshold < (1 << 30))
                              ? min(p.hub_threshold, kSpill)
                              : p.hub_threshold;
     if (deg >= defer_at) {
       int slot = atomicAdd(&p.ctrl->hub_count, 1);
-      if (slot < p.hub_capacity) {  // list full (duplicate-heavy frontier): keep it in the warp bin
+      if (slot < p.hub_capacity) {  // list full (duplicate-heavy frontier): keep the row here
         p.hubs[slot] = v;
         deg = 0;
       }
     }
-    // -- warp bin: rows of >= 32 edges, one at a time, coalesced ---------------------------
-    unsigned big = __ballot_sync(kFull, deg >= 32);
-    while (big) {
-      int leader = __ffs(big) - 1;
-      big &= big - 1;
-      int s = __shfl_sync(kFull, start, leader);
-      int d = __shfl_sync(kFull, deg, leader);
-      int u = __shfl_sync(kFull, v, leader);
-      if (lane == leader)
-        deg = 0;
-      for (int off = 0; off < d; off += 32 * kBatch) {
-        int e[kBatch], nb[kBatch];
+    // ---- block scan of the degrees + compaction of the live rows ---------------------------
+    const int incl = warp_inclusive_sum(deg);
+    const unsigned live_m = __ballot_sync(kFull, deg > 0);
+    if (lane == 31)
+      s_wsum[warp] = incl;
+    if (lane == 0)
+      s_wlive[warp] = __popc(live_m);
+    __syncthreads();  // [B2]
+    int rank0 = incl - deg, slot = __popc(live_m & lanemask_lt()), total = 0, nrows = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      int ws = s_wsum[w], wc = s_wlive[w];
+      if (w < warp) {
+        rank0 += ws;
+        slot += wc;
+      }
+      total += ws;
+      nrows += wc;
+    }
+    if (deg > 0) {
+      s_rank[slot] = rank0;
+      s_base[slot] = start - rank0;
+      if (kSrc)
+        s_vert[slot] = v;
+    }
+    if (threadIdx.x < 33)
+      s_rank[nrows + threadIdx.x] = total;  // sentinels
+    __syncthreads();  // [C]
+    if (threadIdx.x == 0)
+      s_ticket = atomicAdd(&p.ctrl->work, kThreads);  // next ticket, read after barrier [A]
+    // ---- walk: warp w takes spans w, w + kWarps, ... of the CTA's rank space ---------------
+    for (int w_begin = warp * kSpan; w_begin < total; w_begin += kWarps * kSpan) {
+      const int w_end = min(total, w_begin + kSpan);
+      int a = 0, b = nrows;  // last live row with s_rank <= w_begin
+      while (b - a > 1) {
+        int mid = (a + b) >> 1;
+        if (s_rank[mid] <= w_begin)
+          a = mid;
+        else
+          b = mid;
+      }
+      for (int r0 = w_begin; r0 < w_end; r0 += 32 * kBatch) {
+        int row[kBatch], e[kBatch], nb[kBatch], u[kBatch];
         float w[kBatch];
         bool valid[kBatch], keep[kBatch];
         typename op_traits<Op>::token_t tok[kBatch];
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) {
-          e[k] = s + off + k * 32 + lane;
-          valid[k] = off + k * 32 + lane < d;
+          const int rk = r0 + 32 * k;
+          int nxt = s_rank[min(a + 1 + lane, nrows + 32)] - rk;
+          unsigned bit = (nxt >= 0 && nxt < 32) ? (1u << nxt) : 0u;
+          unsigned starts = __reduce_or_sync(kFull, bit);
+          row[k] = min(a + __popc(starts & (0xffffffffu >> (31 - lane))), nrows - 1);
+          valid[k] = rk + lane < w_end;
+          a += __popc(starts);
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+          u[k] = kSrc ? s_vert[row[k]] : -1;
+          e[k] = s_base[row[k]] + r0 + 32 * k + lane;
           nb[k] = valid[k] ? ld_stream(ci + e[k]) : -1;
           w[k] = (kWeights && vals && valid[k]) ? ld_stream(vals + e[k]) : 1.0f;
         }
@@ -254,41 +312,13 @@ advance_binned_kernel(advance_params_t p, Op op) {
             tok[k] = op_prefetch(op, nb[k]);
 #pragma unroll
         for (int k = 0; k < kBatch; ++k)
-          keep[k] = valid[k] && op_commit(op, u, nb[k], e[k], w[k], tok[k]);
+          keep[k] = valid[k] && op_commit(op, u[k], nb[k], e[k], w[k], tok[k]);
         if (kOut != advance_output_t::none) {
 #pragma unroll
           for (int k = 0; k < kBatch; ++k)
             em.push(keep[k], kOut == advance_output_t::edges ? e[k] : op_emit(op, nb[k]));
         }
       }
-    }
-    // -- thread bin: short rows packed by a warp scan ---------------------------------------
-    int incl = warp_inclusive_sum(deg);
-    int excl = incl - deg;
-    int total = __shfl_sync(kFull, incl, 31);
-    if (total) {
-      for (int k = 0; k < deg; ++k)
-        s_owner[warp][excl + k] = static_cast<unsigned char>(lane);
-      __syncwarp();
-      for (int r0 = 0; r0 < total; r0 += 32) {
-        int r = r0 + lane;
-        bool valid = r < total;
-        int owner = valid ? s_owner[warp][r] : 0;
-        int s = __shfl_sync(kFull, start, owner);
-        int ex = __shfl_sync(kFull, excl, owner);
-        int u = __shfl_sync(kFull, v, owner);
-        bool keep = false;
-        int nb = -1;
-        int e = s + (r - ex);
-        if (valid) {
-          nb = ld_stream(ci + e);
-          float w = (kWeights && vals) ? ld_stream(vals + e) : 1.0f;
-          keep = op(u, nb, e, w);
-        }
-        if (kOut != advance_output_t::none)
-          em.push(keep, kOut == advance_output_t::edges ? e : op_emit(op, nb));
-      }
-      __syncwarp();
     }
   }
   if (kOut != advance_output_t::none)

@@ -259,14 +259,15 @@ part_bottom_up_kernel(partition_t pt, csr_view_t in, int words_per_rank,
 }
 
 static __global__ void part_reset_kernel(partition_t pt, int source, int* dist, unsigned* visited,
-                                         unsigned* sent, int sent_words, int* q0, int* counts) {
+                                         unsigned* sent, int sent_words, int* q0, int* counts,
+                                         const unsigned* __restrict__ premark = nullptr) {
   const int lwords = (pt.n_local + 31) / 32;
   const int n = max(pt.n_local, sent_words);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (i < pt.n_local)
       dist[i] = 0x7fffffff;
     if (i < lwords)
-      visited[i] = 0;
+      visited[i] = premark ? premark[i] : 0u;
     if (i < sent_words)
       sent[i] = 0;
   }
@@ -287,7 +288,8 @@ static __global__ void part_seed_kernel(partition_t pt, int source, int* dist, u
 /// Device state of one rank's share of a partitioned BFS (allocated once per graph).
 struct part_bfs_state_t {
   partition_t pt;
-  dbuf_t<unsigned> visited, sent, fbm, nbm;
+  dbuf_t<unsigned> visited, sent, fbm, nbm, unreachable;
+  const int* unreachable_for = nullptr;
   dbuf_t<int> q[2], counts, send_count, overflow, dist;
   dbuf_t<int> send_buf;
   int send_cap = 0;
