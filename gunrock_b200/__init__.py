@@ -112,6 +112,10 @@ _SYMBOLS = [
     "b2g_part_bfs_distances", "b2g_part_set_stream", "b2g_part_bfs_topdown_async",
     "b2g_part_bfs_claim_packed_async", "b2g_part_bfs_frontier_bitmap_async",
     "b2g_part_bfs_bottomup_async", "b2g_part_bfs_end_level_async",
+    "b2g_graph_create_rmat_part_ex", "b2g_part_pr_outdegrees", "b2g_part_pr_begin", "b2g_part_pr_prepare",
+    "b2g_part_pr_pull", "b2g_part_pr_ranks",
+    "b2g_graph_create_csr_part_weighted", "b2g_part_sssp_begin", "b2g_part_sssp_relax_async",
+    "b2g_part_sssp_apply_packed_async", "b2g_part_sssp_end_iteration_async", "b2g_part_sssp_distances",
 ]
 
 

@@ -79,6 +79,8 @@ struct b2g_graph {
   bool partitioned = false;
   partition_t pt;
   part_bfs_state_t part;
+  part_pr_state_t ppr;
+  part_sssp_state_t psssp;
   dbuf_t<unsigned long long> part_deg;
   ctrl_t* part_ctrl = nullptr;
   int part_level_dir = 0;
@@ -186,7 +188,8 @@ __host__ __device__ inline float edge_weight(unsigned long long seed, int u, int
 constexpr unsigned long long kDropKey = ~0ull;
 
 __global__ void rmat_keys_kernel(int scale, long long n_pairs, unsigned long long seed, int mirror,
-                                 int fold, unsigned long long* keys, int nparts = 1, int part = 0) {
+                                 int fold, unsigned long long* keys, int nparts = 1, int part = 0,
+                                 int by_destination = 0) {
   const unsigned TA = 37356u, TAB = 49807u, TABC = 62259u;
   for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n_pairs;
        k += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -209,7 +212,15 @@ __global__ void rmat_keys_kernel(int scale, long long n_pairs, unsigned long lon
     unsigned long long b = (static_cast<unsigned long long>(v) << 32) | u;
     if (u == v)
       a = b = kDropKey;
-    if (nparts > 1) {  // keep only edges whose source this rank owns; row = local row id
+    if (by_destination) {  // rows are in-edge lists: store (destination, source)
+      unsigned t = u;
+      u = v;
+      v = t;
+      unsigned long long tk = a;
+      a = b;
+      b = tk;
+    }
+    if (nparts > 1) {  // keep only edges whose row vertex this rank owns; row = local row id
       if (u != v) {
         a = (u % nparts == static_cast<unsigned>(part))
                 ? ((static_cast<unsigned long long>(u / nparts) << 32) | v)
@@ -306,7 +317,7 @@ b2g_graph* create_coo_impl(int n_rows, int nnz, const int* I, const int* J, cons
 
 b2g_graph* create_rmat_impl(int scale, long long n_pairs, unsigned long long seed, int mirror,
                             int fold_vertices, int weights, unsigned long long weight_seed,
-                            int nparts = 1, int part = 0) {
+                            int nparts = 1, int part = 0, int by_destination = 0) {
   std::unique_ptr<b2g_graph> g(new b2g_graph());
   g->init_runtime();
   cudaStream_t st = g->ws.stream;
@@ -321,7 +332,7 @@ b2g_graph* create_rmat_impl(int scale, long long n_pairs, unsigned long long see
   k0.ensure(n_keys + 1);
   k1.ensure(n_keys + 1);
   rmat_keys_kernel<<<sms * 16, 256, 0, st>>>(scale, n_pairs, seed, mirror, fold_vertices, k0.ptr,
-                                             nparts, part);
+                                             nparts, part, by_destination);
   unsigned long long* sorted = sort_keys_u64(k0.ptr, k1.ptr, n_keys, 64, st);
   // unique + drop sentinel -> compact (row, col) lists via the look-back select
   dbuf_t<int> rows, count;
@@ -1163,6 +1174,248 @@ int b2g_part_bfs_end_level_async(b2g_graph_t* g, long long* stats) {
     g->ws.launches += 1;
     g->part_ctrl = nullptr;
     B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+// ---- partitioned PageRank ------------------------------------------------------------------------
+int b2g_graph_create_rmat_part_ex(int scale, long long n_pairs, unsigned long long seed, int mirror,
+                                  int fold_vertices, int by_destination, int nparts, int part,
+                                  b2g_graph_t** out) {
+  if (!out || scale < 1 || scale > 30 || n_pairs < 0 || nparts < 1 || part < 0 || part >= nparts ||
+      nparts > 64)
+    return fail(B2G_ERR_INVALID, "b2g_graph_create_rmat_part_ex: bad arguments");
+  if (!have_device())
+    return fail(B2G_ERR_NO_DEVICE, "no CUDA device: libgunrock_b200 has no CPU fallback");
+  return guarded([&] {
+    b2g_graph* g = create_rmat_impl(scale, n_pairs, seed, mirror, fold_vertices, 0, 0, nparts, part,
+                                    by_destination);
+    if (nparts == 1) {
+      g->partitioned = true;
+      g->pt = partition_t::make(g->n_vertices, 1, 0);
+    }
+    *out = g;
+    return 0;
+  });
+}
+
+int b2g_part_pr_outdegrees(b2g_graph_t* g, int* outdeg) {
+  if (!g || !g->partitioned || !outdeg)
+    return fail(B2G_ERR_INVALID, "b2g_part_pr_outdegrees: bad arguments");
+  return guarded([&] {
+    cudaStream_t st = g->ws.stream;
+    B2G_CHECK(cudaMemsetAsync(outdeg, 0, sizeof(int) * static_cast<size_t>(g->pt.n_global), st));
+    if (g->n_edges)
+      part_pr_outdeg_kernel<<<device_info_t::get().sm_count * 8, 256, 0, st>>>(
+          g->view.column_indices, g->n_edges, outdeg);
+    g->ws.launches += 1;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_pr_begin(b2g_graph_t* g, float alpha, const int* outdeg_global) {
+  if (!g || !g->partitioned || !outdeg_global)
+    return fail(B2G_ERR_INVALID, "b2g_part_pr_begin: bad arguments");
+  if (g->view.values)
+    return fail(B2G_ERR_INVALID, "partitioned PageRank supports unweighted graphs only");
+  return guarded([&] {
+    cudaStream_t st = g->ws.stream;
+    auto& S = g->ppr;
+    const int sms = device_info_t::get().sm_count;
+    S.nparts = g->pt.nparts;
+    S.part = g->pt.part;
+    S.n_global = g->pt.n_global;
+    S.n_local = g->pt.n_local;
+    S.rows_per_rank = g->pt.rows_of(0);
+    S.sc.ensure(S.n_local, g->n_edges);
+    S.p.ensure(static_cast<size_t>(S.n_local) + 16);
+    S.dsum.ensure(2);
+    S.err.ensure(2);
+    if (S.remapped.cap < static_cast<size_t>(g->n_edges) + 16 || S.t.row_offsets != g->view.row_offsets) {
+      S.remapped.ensure(static_cast<size_t>(g->n_edges) + 16);
+      if (g->n_edges)
+        part_pr_remap_kernel<<<sms * 8, 256, 0, st>>>(g->view.column_indices, g->n_edges, S.nparts,
+                                                      S.rows_per_rank, S.remapped.ptr);
+      S.t.n_vertices = S.n_local;
+      S.t.n_edges = g->n_edges;
+      S.t.row_offsets = g->view.row_offsets;
+      S.t.column_indices = S.remapped.ptr;
+      S.t.values = nullptr;
+      const int ntiles = g->n_edges > 0 ? (g->n_edges + kPrTile - 1) / kPrTile : 1;
+      pr_tile_table_kernel<<<sms * 2, 256, 0, st>>>(S.t.row_offsets, S.n_local, ntiles,
+                                                    S.sc.first_owned.ptr);
+      S.sc.tiled_offsets = S.t.row_offsets;
+      g->ws.launches += 2;
+    }
+    part_pr_reset_kernel<<<sms * 8, 256, 0, st>>>(S.n_local, S.nparts, S.part, S.n_global, alpha,
+                                                  outdeg_global, S.p.ptr, S.sc.plast.ptr, S.sc.iw.ptr);
+    B2G_CHECK(cudaMemsetAsync(S.sc.err.ptr, 0, 2 * sizeof(unsigned), st));
+    g->ws.launches += 1;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_pr_prepare(b2g_graph_t* g, float alpha, float* c_local, double* dsum_local) {
+  if (!g || !g->partitioned || !c_local || !dsum_local)
+    return fail(B2G_ERR_INVALID, "b2g_part_pr_prepare: bad arguments");
+  return guarded([&] {
+    auto& S = g->ppr;
+    cudaStream_t st = g->ws.stream;
+    if (S.rows_per_rank > S.n_local)  // zero the padding slot(s) of the gathered layout
+      B2G_CHECK(cudaMemsetAsync(c_local + S.n_local, 0, sizeof(float) * (S.rows_per_rank - S.n_local), st));
+    part_pr_prepare_kernel<256><<<kPrPartials, 256, 0, st>>>(S.n_local, alpha, S.p.ptr, S.sc.iw.ptr,
+                                                             S.sc.plast.ptr, c_local,
+                                                             S.sc.partials.ptr, S.sc.err.ptr + 1,
+                                                             dsum_local);
+    g->ws.launches += 1;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_pr_pull(b2g_graph_t* g, float alpha, const float* c_all, const double* dsum_global,
+                     float* err_local) {
+  if (!g || !g->partitioned || !c_all || !dsum_global || !err_local)
+    return fail(B2G_ERR_INVALID, "b2g_part_pr_pull: bad arguments");
+  return guarded([&] {
+    auto& S = g->ppr;
+    cudaStream_t st = g->ws.stream;
+    const int sms = device_info_t::get().sm_count;
+    const int ntiles = S.t.n_edges > 0 ? (S.t.n_edges + kPrTile - 1) / kPrTile : 1;
+    part_pr_base_kernel<<<1, 1, 0, st>>>(dsum_global, alpha, S.n_global, S.sc.base.ptr);
+    ctrl_t* ctrl = g->ws.next_ctrl();
+    pr_pull_tile_kernel<256, false><<<sms * 8, 256, 0, st>>>(
+        S.t, ntiles, S.sc.first_owned.ptr, c_all, S.sc.plast.ptr, S.sc.base.ptr, S.p.ptr,
+        S.sc.head.ptr, S.sc.tail.ptr, S.sc.tail_row.ptr, S.sc.err.ptr, ctrl);
+    pr_fixup_kernel<<<sms, 256, 0, st>>>(S.t, ntiles, S.sc.tail_row.ptr, S.sc.head.ptr, S.sc.tail.ptr,
+                                         S.sc.base.ptr, S.sc.plast.ptr, S.p.ptr, S.sc.err.ptr);
+    part_pr_err_kernel<<<1, 1, 0, st>>>(S.sc.err.ptr, err_local);
+    g->ws.launches += 4;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_pr_ranks(b2g_graph_t* g, float* p, int loc) {
+  if (!g || !g->partitioned || !p || !g->ppr.p.ptr)
+    return fail(B2G_ERR_INVALID, "b2g_part_pr_ranks: bad arguments");
+  return guarded([&] {
+    B2G_CHECK(cudaMemcpyAsync(p, g->ppr.p.ptr, sizeof(float) * static_cast<size_t>(g->ppr.n_local),
+                              loc == B2G_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                              g->ws.stream));
+    B2G_CHECK(cudaStreamSynchronize(g->ws.stream));
+    return 0;
+  });
+}
+
+// ---- partitioned SSSP ----------------------------------------------------------------------------
+int b2g_graph_create_csr_part_weighted(int n_global_vertices, int nparts, int part, int n_local_edges,
+                                       const int* row_offsets, const int* column_indices,
+                                       const float* values, int loc, int symmetric, b2g_graph_t** out) {
+  if (!out || n_global_vertices < 0 || nparts < 1 || nparts > 64 || part < 0 || part >= nparts)
+    return fail(B2G_ERR_INVALID, "b2g_graph_create_csr_part_weighted: bad arguments");
+  partition_t pt = partition_t::make(n_global_vertices, nparts, part);
+  int rc = b2g_graph_create_csr(pt.n_local, n_local_edges, row_offsets, column_indices, values, loc,
+                                symmetric, out);
+  if (rc)
+    return rc;
+  (*out)->partitioned = true;
+  (*out)->pt = pt;
+  return 0;
+}
+
+int b2g_part_sssp_begin(b2g_graph_t* g, int source, int send_capacity) {
+  if (!g || !g->partitioned || source < 0 || source >= g->pt.n_global || send_capacity < 1)
+    return fail(B2G_ERR_INVALID, "b2g_part_sssp_begin: bad arguments");
+  if (!g->view.values)
+    return fail(B2G_ERR_INVALID, "b2g_part_sssp_begin: the graph has no edge values");
+  return guarded([&] {
+    cudaStream_t st = g->ws.stream;
+    auto& S = g->psssp;
+    S.ensure(g->pt, send_capacity);
+    g->part_deg.ensure(2);
+    part_sssp_reset_kernel<<<device_info_t::get().sm_count * 8, 256, 0, st>>>(
+        g->pt, source, S.dist.ptr, S.stamp.ptr, S.best_sent.ptr, S.q[0].ptr, S.counts.ptr);
+    B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(S.overflow.ptr, 0, sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(g->part_deg.ptr, 0, 16, st));
+    g->ws.launches += 1;
+    S.cur = 0;
+    g->part_ctrl = nullptr;
+    B2G_CHECK(cudaStreamSynchronize(st));
+    return 0;
+  });
+}
+
+int b2g_part_sssp_relax_async(b2g_graph_t* g, int iteration, const b2g_options_t* opt, int* msg,
+                              int cap_s) {
+  if (!g || !g->partitioned || !msg || cap_s < 1)
+    return fail(B2G_ERR_INVALID, "b2g_part_sssp_relax_async: bad arguments");
+  return guarded([&] {
+    b2g_options_t o = resolved(opt);
+    cudaStream_t st = g->ws.stream;
+    auto& S = g->psssp;
+    const int nxt = S.cur ^ 1;
+    B2G_CHECK(cudaMemsetAsync(S.counts.ptr + nxt, 0, sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
+    part_relax_op op{g->pt,          S.dist.ptr,     S.stamp.ptr,      S.best_sent.ptr, iteration,
+                     S.send_ids.ptr, S.send_vals.ptr, S.send_count.ptr, S.send_cap,      S.overflow.ptr};
+    ctrl_t* c = nullptr;
+    launch_advance<advance_output_t::vertices, true, true>(
+        g->ws, g->view, S.q[S.cur].ptr, S.counts.ptr + S.cur, g->pt.n_local, S.q[nxt].ptr,
+        S.counts.ptr + nxt, g->pt.n_local, op, to_launch(o), &c);
+    g->part_ctrl = c;
+    dim3 grid(32, g->pt.nparts);
+    part_pack_pairs_kernel<<<grid, 256, 0, st>>>(S.send_ids.ptr, S.send_vals.ptr, S.send_count.ptr,
+                                                 S.send_cap, g->pt.nparts, cap_s, msg);
+    g->ws.launches += 1;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_sssp_apply_packed_async(b2g_graph_t* g, int iteration, const int* msgs, int cap_s) {
+  if (!g || !g->partitioned || !msgs)
+    return fail(B2G_ERR_INVALID, "b2g_part_sssp_apply_packed_async: bad arguments");
+  return guarded([&] {
+    auto& S = g->psssp;
+    const int nxt = S.cur ^ 1;
+    dim3 grid(64, g->pt.nparts);
+    part_relax_packed_kernel<<<grid, 256, 0, g->ws.stream>>>(
+        g->pt, msgs, cap_s, S.dist.ptr, S.stamp.ptr, iteration, g->view.row_offsets, S.q[nxt].ptr,
+        S.counts.ptr + nxt, g->part_deg.ptr, S.overflow.ptr);
+    g->ws.launches += 1;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_sssp_end_iteration_async(b2g_graph_t* g, long long* stats) {
+  if (!g || !g->partitioned || !stats)
+    return fail(B2G_ERR_INVALID, "b2g_part_sssp_end_iteration_async: bad arguments");
+  return guarded([&] {
+    auto& S = g->psssp;
+    S.cur ^= 1;
+    part_stats_kernel<<<1, 1, 0, g->ws.stream>>>(S.counts.ptr + S.cur, g->part_ctrl, g->part_deg.ptr,
+                                                 S.overflow.ptr, stats);
+    g->ws.launches += 1;
+    g->part_ctrl = nullptr;
+    B2G_CHECK(cudaGetLastError());
+    return 0;
+  });
+}
+
+int b2g_part_sssp_distances(b2g_graph_t* g, float* distances, int loc) {
+  if (!g || !g->partitioned || !distances || !g->psssp.dist.ptr)
+    return fail(B2G_ERR_INVALID, "b2g_part_sssp_distances: bad arguments");
+  return guarded([&] {
+    B2G_CHECK(cudaMemcpyAsync(distances, g->psssp.dist.ptr,
+                              sizeof(float) * static_cast<size_t>(g->pt.n_local),
+                              loc == B2G_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                              g->ws.stream));
+    B2G_CHECK(cudaStreamSynchronize(g->ws.stream));
     return 0;
   });
 }

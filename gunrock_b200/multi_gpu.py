@@ -51,6 +51,12 @@ def _bind():
     L.b2g_part_bfs_frontier_bitmap_async.argtypes = [vp, vp]
     L.b2g_part_bfs_bottomup_async.argtypes = [vp, ip, vp]
     L.b2g_part_bfs_end_level_async.argtypes = [vp, vp]
+    L.b2g_graph_create_rmat_part_ex.argtypes = [ip, C.c_longlong, C.c_ulonglong, ip, ip, ip, ip, ip, C.POINTER(vp)]
+    L.b2g_part_pr_outdegrees.argtypes = [vp, vp]
+    L.b2g_part_pr_begin.argtypes = [vp, C.c_float, vp]
+    L.b2g_part_pr_prepare.argtypes = [vp, C.c_float, vp, vp]
+    L.b2g_part_pr_pull.argtypes = [vp, C.c_float, vp, vp, vp]
+    L.b2g_part_pr_ranks.argtypes = [vp, vp, ip]
     L._mg_bound = True
     return L
 
@@ -101,15 +107,26 @@ class PartitionedGraph:
         return v.value * self.nparts + self.part, d.value
 
     @staticmethod
-    def rmat(scale: int, n_pairs: int, seed: int, nparts: int, part: int, mirror: bool = True):
+    def rmat(scale: int, n_pairs: int, seed: int, nparts: int, part: int, mirror: bool = True,
+             fold_vertices: int = 0, by_destination: bool = False):
+        """The rank's share generated on its GPU.  by_destination: rows are in-edge lists (for pull)."""
         h = C.c_void_p()
-        _check(_bind().b2g_graph_create_rmat_part(scale, n_pairs, seed, int(mirror), nparts, part, C.byref(h)),
-               "b2g_graph_create_rmat_part")
+        _check(_bind().b2g_graph_create_rmat_part_ex(scale, n_pairs, seed, int(mirror), fold_vertices,
+                                                     int(by_destination), nparts, part, C.byref(h)),
+               "b2g_graph_create_rmat_part_ex")
         return PartitionedGraph(h.value)
 
     @staticmethod
-    def from_global_csr(ro, ci, nparts: int, part: int, symmetric: bool = True):
-        lro, lci = partition_csr(np.asarray(ro), np.asarray(ci), nparts, part)
+    def from_global_csr(ro, ci, nparts: int, part: int, symmetric: bool = True, by_destination: bool = False):
+        ro, ci = np.asarray(ro), np.asarray(ci)
+        if by_destination and not symmetric:      # rows = in-edge lists: partition the transpose
+            n = len(ro) - 1
+            src = np.repeat(np.arange(n, dtype=np.int64), np.diff(ro))
+            order = np.lexsort((src, ci))
+            t_ro = np.zeros(n + 1, np.int64)
+            np.cumsum(np.bincount(ci, minlength=n), out=t_ro[1:])
+            ro, ci = t_ro.astype(np.int32), src[order].astype(np.int32)
+        lro, lci = partition_csr(ro, ci, nparts, part)
         h = C.c_void_p()
         _check(_bind().b2g_graph_create_csr_part(len(ro) - 1, nparts, part, len(lci), lro.ctypes.data,
                                                  lci.ctypes.data if len(lci) else None, HOST, int(symmetric),
@@ -191,8 +208,18 @@ class CudaRankEngine:
 
     # ---- sync-free steps (enqueued on torch's current stream) ---------------------------------
     def use_stream(self, stream=None):
-        s = stream if stream is not None else self.torch.cuda.current_stream()
-        _check(self.L.b2g_part_set_stream(self.G._h, s.cuda_stream), "b2g_part_set_stream")
+        """Run the sync-free steps on ``stream`` (default: a private torch stream of this engine, so
+        that collectives issued under ``torch.cuda.stream(engine.stream)`` are ordered with them).
+        The legacy default stream (handle 0) cannot be named through the C ABI, hence never used."""
+        if stream is None:
+            if getattr(self, "stream", None) is None:
+                self.stream = self.torch.cuda.Stream()
+            stream = self.stream
+        if stream.cuda_stream == 0:
+            raise GunrockB200Error("pass an explicit (non-default) CUDA stream")
+        self.stream = stream
+        _check(self.L.b2g_part_set_stream(self.G._h, stream.cuda_stream), "b2g_part_set_stream")
+        return stream
 
     def topdown_async(self, level: int, msg, cap_s: int):
         _check(self.L.b2g_part_bfs_topdown_async(self.G._h, level, C.byref(self.opt), msg.data_ptr(), cap_s),
@@ -213,6 +240,28 @@ class CudaRankEngine:
 
     def end_level_async(self, stats):
         _check(self.L.b2g_part_bfs_end_level_async(self.G._h, stats.data_ptr()), "b2g_part_bfs_end_level_async")
+
+    # ---- partitioned PageRank steps ------------------------------------------------------------
+    def pr_outdegrees(self):
+        t = self.torch.empty(self.n_global, dtype=self.torch.int32, device="cuda")
+        _check(self.L.b2g_part_pr_outdegrees(self.G._h, t.data_ptr()), "b2g_part_pr_outdegrees")
+        return t
+
+    def pr_begin(self, alpha: float, outdeg_global):
+        _check(self.L.b2g_part_pr_begin(self.G._h, alpha, outdeg_global.data_ptr()), "b2g_part_pr_begin")
+
+    def pr_prepare(self, alpha: float, c_local, dsum_local):
+        _check(self.L.b2g_part_pr_prepare(self.G._h, alpha, c_local.data_ptr(), dsum_local.data_ptr()),
+               "b2g_part_pr_prepare")
+
+    def pr_pull(self, alpha: float, c_all, dsum_global, err_local):
+        _check(self.L.b2g_part_pr_pull(self.G._h, alpha, c_all.data_ptr(), dsum_global.data_ptr(),
+                                       err_local.data_ptr()), "b2g_part_pr_pull")
+
+    def pr_ranks(self):
+        p = self.torch.empty(self.n_local, dtype=self.torch.float32, device="cuda")
+        _check(self.L.b2g_part_pr_ranks(self.G._h, p.data_ptr(), DEVICE), "b2g_part_pr_ranks")
+        return p
 
     def distances(self):
         d = self.torch.empty(self.n_local, dtype=self.torch.int32, device="cuda")
@@ -368,43 +417,120 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
     P = comm.world
     cap_s = cap_s or min(rows_of(engine.n_global, P, 0) + 64, 1 << 20)
     engine.begin(source)
-    engine.use_stream()
-    msg = torch.zeros((P, cap_s + 1), dtype=torch.int32, device="cuda")
-    msgs_in = torch.zeros_like(msg)
-    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    stream = engine.use_stream()
     st = part_bfs_stats_t()
-    n_f, m_f, explored, level, bottom_up = 1, 0, 0, 0, False
-    while n_f > 0:
-        go_up = _decide(direction, level, bottom_up, n_f, m_f, explored, engine.n_global, total_edges, alpha, beta)
-        if level > 0:
-            explored += m_f
-        if go_up:
-            allbm = comm.all_gather_bitmap(engine.frontier_bitmap_async())
-            engine.bottomup_async(level, allbm)
-        else:
-            engine.topdown_async(level, msg, cap_s)
+    overflowed = False
+    with torch.cuda.stream(stream):
+        msg = torch.zeros((P, cap_s + 1), dtype=torch.int32, device="cuda")
+        msgs_in = torch.zeros_like(msg)
+        stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+        n_f, m_f, explored, level, bottom_up = 1, 0, 0, 0, False
+        while n_f > 0:
+            go_up = _decide(direction, level, bottom_up, n_f, m_f, explored, engine.n_global, total_edges,
+                            alpha, beta)
+            if level > 0:
+                explored += m_f
+            if go_up:
+                allbm = comm.all_gather_bitmap(engine.frontier_bitmap_async())
+                engine.bottomup_async(level, allbm)
+            else:
+                engine.topdown_async(level, msg, cap_s)
+                if P > 1:
+                    dist.all_to_all_single(msgs_in, msg, group=comm.group)
+                    engine.claim_packed_async(level, msgs_in, cap_s)
+            engine.end_level_async(stats)
             if P > 1:
-                dist.all_to_all_single(msgs_in, msg, group=comm.group)
-                engine.claim_packed_async(level, msgs_in, cap_s)
-        engine.end_level_async(stats)
-        if P > 1:
-            dist.all_reduce(stats, group=comm.group)
-        g = [int(x) for x in stats.tolist()]          # the level's only host synchronisation
-        if g[3]:
-            engine.L.b2g_part_set_stream(engine.G._h, None)
-            return bfs_rank(engine, comm, source, total_edges, direction, alpha, beta)
-        st.level_direction.append(1 if go_up else 0)
-        st.level_frontier.append(n_f)
-        st.level_edges.append(g[2])
-        st.edges_touched += g[2]
-        if level == 0:
-            explored += g[2]
-        n_f, m_f, bottom_up = g[0], g[1], go_up
-        level += 1
-    st.levels = level
-    d = engine.distances()
+                dist.all_reduce(stats, group=comm.group)
+            g = [int(x) for x in stats.tolist()]          # the level's only host synchronisation
+            if g[3]:
+                overflowed = True
+                break
+            st.level_direction.append(1 if go_up else 0)
+            st.level_frontier.append(n_f)
+            st.level_edges.append(g[2])
+            st.edges_touched += g[2]
+            if level == 0:
+                explored += g[2]
+            n_f, m_f, bottom_up = g[0], g[1], go_up
+            level += 1
+        stream.synchronize()
     engine.L.b2g_part_set_stream(engine.G._h, None)
-    return d, st
+    if overflowed:
+        return bfs_rank(engine, comm, source, total_edges, direction, alpha, beta)
+    st.levels = level
+    return engine.distances(), st
+
+
+def pr_rank(engine, comm, alpha: float = 0.85, tol: float = 1e-6, max_iter: int = 0):
+    """This rank's part of a partitioned PageRank (pull over in-edge rows).  Per iteration:
+    prepare (c = plast*iw, dangling partial) -> all_gather(c) + all_reduce(dangling, SUM) -> pull ->
+    all_reduce(err, MAX) -> one host read.  Same recurrence and stopping rule as
+    include/gunrock/algorithms/pr.hxx:107-195.  Returns (owned ranks, iterations)."""
+    torch, dist = comm.torch, comm.dist
+    P = comm.world
+    stream = engine.use_stream()
+    R = rows_of(engine.n_global, P, 0)
+    with torch.cuda.stream(stream):
+        outdeg = engine.pr_outdegrees()
+        if P > 1:
+            dist.all_reduce(outdeg, group=comm.group)
+        engine.pr_begin(alpha, outdeg)
+        c_local = torch.zeros(R, dtype=torch.float32, device="cuda")
+        c_all = torch.zeros(P * R, dtype=torch.float32, device="cuda") if P > 1 else c_local
+        dsum = torch.zeros(1, dtype=torch.float64, device="cuda")
+        err = torch.zeros(1, dtype=torch.float32, device="cuda")
+        it = 0
+        while True:
+            if it > 0 and float(err.item()) < tol:          # the iteration's only host synchronisation
+                break
+            if max_iter > 0 and it >= max_iter:
+                break
+            engine.pr_prepare(alpha, c_local, dsum)
+            if P > 1:
+                dist.all_gather_into_tensor(c_all, c_local, group=comm.group)
+                dist.all_reduce(dsum, group=comm.group)
+            engine.pr_pull(alpha, c_all, dsum, err)
+            if P > 1:
+                dist.all_reduce(err, op=dist.ReduceOp.MAX, group=comm.group)
+            it += 1
+        stream.synchronize()
+    engine.L.b2g_part_set_stream(engine.G._h, None)
+    return engine.pr_ranks(), it
+
+
+def pr_lockstep(engines: Sequence, alpha: float = 0.85, tol: float = 1e-6, max_iter: int = 0):
+    """Several simulated ranks in one process (single-GPU test of the partitioned PageRank)."""
+    import torch
+    P = len(engines)
+    R = rows_of(engines[0].n_global, P, 0)
+    stream = engines[0].use_stream()
+    for e in engines[1:]:
+        e.use_stream(stream)
+    with torch.cuda.stream(stream):
+        outdeg = sum(e.pr_outdegrees() for e in engines)
+        for e in engines:
+            e.pr_begin(alpha, outdeg)
+        c_loc = [torch.zeros(R, dtype=torch.float32, device="cuda") for _ in engines]
+        ds = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in engines]
+        er = [torch.zeros(1, dtype=torch.float32, device="cuda") for _ in engines]
+        it, err = 0, 1.0
+        while True:
+            if it > 0 and err < tol:
+                break
+            if max_iter > 0 and it >= max_iter:
+                break
+            for e, c, d in zip(engines, c_loc, ds):
+                e.pr_prepare(alpha, c, d)
+            c_all = torch.cat(c_loc)
+            dsum = torch.stack(ds).sum(0)
+            for e, x in zip(engines, er):
+                e.pr_pull(alpha, c_all, dsum, x)
+            err = max(float(x.item()) for x in er)
+            it += 1
+        stream.synchronize()
+    for e in engines:
+        e.L.b2g_part_set_stream(e.G._h, None)
+    return [e.pr_ranks() for e in engines], it
 
 
 # ---------------------------------------------------------------------------------------------
@@ -463,7 +589,7 @@ def bfs_lockstep(engines: Sequence, source: int, total_edges: int,
 def gather_distances(local_dists: Sequence[np.ndarray], n_global: int) -> np.ndarray:
     """Interleave the ranks' slices back into global vertex order (v -> rank v % P, row v // P)."""
     P = len(local_dists)
-    out = np.empty(n_global, np.int32)
+    out = np.empty(n_global, np.asarray(local_dists[0]).dtype)
     for r, d in enumerate(local_dists):
         out[r::P] = np.asarray(d)[:rows_of(n_global, P, r)]
     return out

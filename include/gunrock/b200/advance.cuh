@@ -164,6 +164,7 @@ struct advance_params_t {
   ctrl_t* ctrl = nullptr;
   int hub_threshold = 1 << 30;
   int tma_ok = 0;                  // column_indices / values are 16-byte aligned
+  int entries_per_ticket = 256;    // block_mapped: frontier entries a CTA draws at a time (<= 256)
   const int* tile_rows = nullptr;  // merge_path: first row of every tile
   const int* row_base = nullptr;   // merge_path: CSR offset of every frontier row (next to the scan)
 };
@@ -207,8 +208,12 @@ advance_binned_kernel(advance_params_t p, Op op) {
   em.init(s_emit[warp], p.out, p.out_count, p.out_capacity, ro, p.ctrl);
   unsigned long long edges_seen = 0;
 
+  // Entries per ticket are chosen by the host from the frontier's average degree so that a ticket
+  // is worth ~16K edges: small enough to balance hub-heavy frontiers over ~10^3 resident CTAs,
+  // large enough to amortise the four barriers.
+  const int ept = min(kThreads, max(1, p.entries_per_ticket));
   if (threadIdx.x == 0)
-    s_ticket = atomicAdd(&p.ctrl->work, kThreads);
+    s_ticket = atomicAdd(&p.ctrl->work, ept);
   for (;;) {
     __syncthreads();  // [A] previous ticket retired, new ticket visible
     const int base = s_ticket;
@@ -216,7 +221,7 @@ advance_binned_kernel(advance_params_t p, Op op) {
       break;
     const int idx = base + threadIdx.x;
     int v = -1;
-    if (idx < n)
+    if (idx < n && threadIdx.x < ept)
       v = (kIn == advance_input_t::graph) ? idx : p.in[idx];
     int start = 0, deg = 0;
     if (v >= 0) {
@@ -272,7 +277,7 @@ advance_binned_kernel(advance_params_t p, Op op) {
       s_rank[nrows + threadIdx.x] = total;  // sentinels
     __syncthreads();  // [C]
     if (threadIdx.x == 0)
-      s_ticket = atomicAdd(&p.ctrl->work, kThreads);  // next ticket, read after barrier [A]
+      s_ticket = atomicAdd(&p.ctrl->work, ept);  // next ticket, read after barrier [A]
     // ---- walk: warp w takes spans w, w + kWarps, ... of the CTA's rank space ---------------
     for (int w_begin = warp * kSpan; w_begin < total; w_begin += kWarps * kSpan) {
       const int w_end = min(total, w_begin + kSpan);
@@ -398,8 +403,16 @@ advance_hub_kernel(advance_params_t p, Op op) {
       bulk_g2s(&s_val[kWeights ? buf : 0][0], vals + a0, bytes, &s_bar[buf]);
   };
 
-  int rot = 0;  // slabs dealt by earlier batches: keeps the round-robin deal balanced
-  for (int b0 = 0; b0 < n_hubs; b0 += kHubs) {
+  // Batches of kHubs rows are OWNED by groups of CTAs (a CTA stages only the descriptors of its own
+  // batches): with many deferred rows every CTA re-reading every descriptor would dominate.
+  const int nbatches = (n_hubs + kHubs - 1) / kHubs;
+  const bool many = nbatches >= static_cast<int>(gridDim.x);
+  const int first_batch = many ? blockIdx.x : static_cast<int>(blockIdx.x) % nbatches;
+  const int batch_step = many ? gridDim.x : (1 << 30);
+  const int member = many ? 0 : static_cast<int>(blockIdx.x) / nbatches;            // my index in the group
+  const int members = many ? 1 : (static_cast<int>(gridDim.x) - first_batch + nbatches - 1) / nbatches;
+  for (int bi = first_batch; bi < nbatches; bi += batch_step) {
+    const int b0 = bi * kHubs;
     const int nb = min(kHubs, n_hubs - b0);
     // descriptors + exclusive slab-count prefix of this batch
     int carry = 0;
@@ -436,12 +449,12 @@ advance_hub_kernel(advance_params_t p, Op op) {
     __syncthreads();
     const int total = carry;
 
-    int g = (blockIdx.x + gridDim.x - (rot % gridDim.x)) % gridDim.x;
+    int g = member;
     if (tma && g < total && threadIdx.x == 0)
       issue(g, nb, 0);
     int buf = 0;
-    for (; g < total; g += gridDim.x) {
-      int gn = g + gridDim.x;
+    for (; g < total; g += members) {
+      int gn = g + members;
       if (tma && gn < total && threadIdx.x == 0)
         issue(gn, nb, buf ^ 1);
       const int h = find_hub(g, nb);
@@ -493,8 +506,7 @@ advance_hub_kernel(advance_params_t p, Op op) {
       __syncthreads();  // all reads of s_idx[buf] retire before it is refilled
       buf ^= 1;
     }
-    rot += total;
-    __syncthreads();
+    __syncthreads();  // descriptors of this batch are dead; phase bits carry over per buffer
   }
   if (kOut != advance_output_t::none)
     em.flush();
@@ -870,6 +882,8 @@ struct advance_launch_t {
   /// frontiers whose out-degree sum is below this take the single-kernel path (no scan, no hub
   /// pass): fixed per-level cost matters more than balance there.
   long long small_frontier_edges = 1 << 12;
+  /// block_mapped: average out-degree of the frontier if the caller knows it (0 = unknown).
+  double avg_degree = 0.0;
 };
 
 /// Degree scan of the frontier for merge_path (replaces helpers.hxx:41-111): scanned[0..n],
@@ -963,6 +977,13 @@ inline void launch_advance(workspace_t& ws,
     p.hub_capacity = cfg.hub_threshold < (1 << 30) ? g.n_edges / 256 + 1024 : 16;
     p.hubs = ws.hubs.ensure(static_cast<size_t>(p.hub_capacity));
     p.tma_ok = aligned16(g.column_indices) && (!kWeights || !g.values || aligned16(g.values));
+    if (cfg.avg_degree > 0.0) {
+      int want = static_cast<int>(16384.0 / cfg.avg_degree);
+      int ept = 8;
+      while (ept * 2 <= want && ept < 256)
+        ept *= 2;
+      p.entries_per_ticket = ept;
+    }
     if (graph_in)
       advance_binned_kernel<kThreads, advance_input_t::graph, kOut, kDegSum, kWeights>
           <<<grid, kThreads, 0, ws.stream>>>(p, op);

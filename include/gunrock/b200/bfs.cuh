@@ -427,6 +427,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
       int ub = static_cast<int>(n_f < V ? n_f : V);
       advance_launch_t lcfg = cfg.advance;
+      lcfg.avg_degree = (level > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
       if (level == 0) {
         lcfg.lb = lb_t::block_mapped;  // one row of unknown length: binned kernel + hub slabs
       } else if (static_cast<long long>(m_f) < cfg.advance.small_frontier_edges) {

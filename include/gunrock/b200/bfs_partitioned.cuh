@@ -25,6 +25,7 @@
 
 #include <gunrock/b200/advance.cuh>
 #include <gunrock/b200/bfs.cuh>
+#include <gunrock/b200/sssp.cuh>
 
 namespace gunrock {
 namespace b200 {
@@ -412,6 +413,167 @@ static __global__ void part_feedback_kernel(const int* count, const ctrl_t* c, c
   for (int i = 0; i < nparts && i < 64; ++i)
     fb->send_count[i] = send_count[i];
 }
+
+// ---------------------------------------------------------------------------------------------
+// Partitioned SSSP: the same push exchange carrying (vertex, fp32 distance)
+// pairs; the receiver applies atomicMin.  Distances only ever decrease and every improvement is
+// re-expanded by its owner, so the distributed run reaches the same least fixed point as the
+// single-GPU run and the reference's CPU validator (bit-exact; see sssp.cuh).
+// ---------------------------------------------------------------------------------------------
+struct part_relax_op {
+  partition_t pt;
+  float* dist;        // local rows
+  int* stamp;         // local rows
+  float* best_sent;   // global ids: smallest candidate this rank already forwarded
+  int iteration;
+  int* send_ids;      // nparts x send_cap
+  float* send_vals;   // nparts x send_cap
+  int* send_count;
+  int send_cap;
+  int* overflow;
+
+  /// `src` is a LOCAL row id (the frontier holds local ids), `dst` a global id.
+  __device__ __forceinline__ float prefetch(int dst) const {
+    return pt.owner(dst) == pt.part ? ld_relaxed(dist + pt.local(dst)) : ld_relaxed(best_sent + dst);
+  }
+  __device__ __forceinline__ bool commit(int src, int dst, int, float w, float current) const {
+    const float nd = __fadd_rn(ld_relaxed(dist + src), w);
+    if (!(nd < current))
+      return false;
+    const int own = pt.owner(dst);
+    if (own == pt.part) {
+      const int l = pt.local(dst);
+      float old = atomic_min_float(dist + l, nd);
+      if (!(nd < old))
+        return false;
+      return atomicExch(stamp + l, iteration) != iteration;
+    }
+    float old = atomic_min_float(best_sent + dst, nd);
+    if (!(nd < old))
+      return false;
+    const unsigned act = __activemask();
+    const unsigned grp = __match_any_sync(act, own);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (lane_id() == leader)
+      base = atomicAdd(send_count + own, __popc(grp));
+    base = __shfl_sync(grp, base, leader);
+    const int slot = base + __popc(grp & lanemask_lt());
+    if (slot < send_cap) {
+      send_ids[static_cast<size_t>(own) * send_cap + slot] = dst;
+      send_vals[static_cast<size_t>(own) * send_cap + slot] = nd;
+    } else {
+      *overflow = 1;
+    }
+    return false;
+  }
+  __device__ __forceinline__ bool operator()(int s, int d, int e, float w) const {
+    return commit(s, d, e, w, prefetch(d));
+  }
+  __device__ __forceinline__ int emit_as(int dst) const { return pt.local(dst); }
+};
+
+/// msg row o = [count, ids[cap_s], value bits[cap_s]]
+static __global__ void part_pack_pairs_kernel(const int* __restrict__ send_ids,
+                                              const float* __restrict__ send_vals,
+                                              const int* __restrict__ send_count, int send_cap,
+                                              int nparts, int cap_s, int* __restrict__ msg) {
+  for (int o = blockIdx.y; o < nparts; o += gridDim.y) {
+    const int n = send_count[o];
+    int* row = msg + static_cast<size_t>(o) * (2 * cap_s + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      row[0] = n;
+    const int m = min(n, cap_s);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+      row[1 + i] = send_ids[static_cast<size_t>(o) * send_cap + i];
+      row[1 + cap_s + i] = __float_as_int(send_vals[static_cast<size_t>(o) * send_cap + i]);
+    }
+  }
+}
+
+static __global__ void part_relax_packed_kernel(partition_t pt, const int* __restrict__ msgs, int cap_s,
+                                                float* dist, int* stamp, int iteration,
+                                                const int* __restrict__ ro, int* out, int* out_count,
+                                                unsigned long long* deg_sum, int* overflow) {
+  const int lane = lane_id();
+  unsigned long long ds = 0;
+  for (int src = blockIdx.y; src < pt.nparts; src += gridDim.y) {
+    if (src == pt.part)
+      continue;
+    const int* row = msgs + static_cast<size_t>(src) * (2 * cap_s + 1);
+    int n = row[0];
+    if (n > cap_s) {
+      if (blockIdx.x == 0 && threadIdx.x == 0)
+        *overflow = 1;
+      n = cap_s;
+    }
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < n; i0 += gridDim.x * blockDim.x) {
+      int i = i0 + lane;
+      bool won = false;
+      int l = 0;
+      if (i < n) {
+        l = pt.local(row[1 + i]);
+        float nd = __int_as_float(row[1 + cap_s + i]);
+        float old = atomic_min_float(dist + l, nd);
+        if (nd < old)
+          won = atomicExch(stamp + l, iteration) != iteration;
+        if (won)
+          ds += static_cast<unsigned>(ro[l + 1] - ro[l]);
+      }
+      unsigned m = __ballot_sync(kFull, won);
+      if (m) {
+        int base = 0;
+        if (lane == 0)
+          base = atomicAdd(out_count, __popc(m));
+        base = __shfl_sync(kFull, base, 0);
+        if (won)
+          out[base + __popc(m & lanemask_lt())] = l;
+      }
+    }
+  }
+  ds = warp_sum(ds);
+  if (lane == 0 && ds)
+    atomicAdd(deg_sum, ds);
+}
+
+static __global__ void part_sssp_reset_kernel(partition_t pt, int source, float* dist, int* stamp,
+                                              float* best_sent, int* q0, int* counts) {
+  const int n = max(pt.n_local, pt.n_global);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < pt.n_local) {
+      dist[i] = (pt.owner(source) == pt.part && pt.local(source) == i) ? 0.0f : FLT_MAX;
+      stamp[i] = -1;
+    }
+    if (i < pt.n_global)
+      best_sent[i] = FLT_MAX;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counts[0] = counts[1] = 0;
+    if (pt.owner(source) == pt.part)
+      counts[0] = 1, q0[0] = pt.local(source);
+  }
+}
+
+struct part_sssp_state_t {
+  partition_t pt;
+  dbuf_t<float> dist, best_sent, send_vals;
+  dbuf_t<int> stamp, q[2], counts, send_ids, send_count, overflow;
+  int send_cap = 0, cur = 0;
+  void ensure(const partition_t& p, int send_capacity) {
+    pt = p;
+    dist.ensure(static_cast<size_t>(p.n_local) + 64);
+    stamp.ensure(static_cast<size_t>(p.n_local) + 64);
+    best_sent.ensure(static_cast<size_t>(p.n_global) + 64);
+    q[0].ensure(static_cast<size_t>(p.n_local) + 64);
+    q[1].ensure(static_cast<size_t>(p.n_local) + 64);
+    counts.ensure(8);
+    send_count.ensure(64);
+    overflow.ensure(4);
+    send_cap = send_capacity;
+    send_ids.ensure(static_cast<size_t>(p.nparts) * send_capacity + 64);
+    send_vals.ensure(static_cast<size_t>(p.nparts) * send_capacity + 64);
+  }
+};
 
 }  // namespace b200
 }  // namespace gunrock

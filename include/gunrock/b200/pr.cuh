@@ -341,6 +341,110 @@ static __global__ void pr_fixup_kernel(csr_view_t t, int ntiles, const int* __re
     atomicMax(err_bits, __float_as_uint(err));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Partitioned (multi-GPU) PageRank: the rank owns the destination vertices v % P == part with their
+// in-edges; per iteration the host side all-gathers c = plast * iweights (4 V bytes in total),
+// all-reduces the dangling sum (fp64) and the error (max), SURVEY.md section 8e.  The pull itself is
+// the same tile kernel: the column ids are remapped once to positions in the gathered array.
+// ---------------------------------------------------------------------------------------------
+/// outdeg[src] += 1 for every local in-edge (global array, all-reduced by the host afterwards).
+static __global__ void part_pr_outdeg_kernel(const int* __restrict__ src_ids, int n_edges, int* outdeg) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x)
+    atomicAdd(outdeg + src_ids[e], 1);
+}
+/// position of global vertex u in the rank-major gathered array: (u % P) * R + u / P
+static __global__ void part_pr_remap_kernel(const int* __restrict__ src_ids, int n_edges, int nparts,
+                                            int rows_per_rank, int* __restrict__ out) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x) {
+    int u = src_ids[e];
+    out[e] = (u % nparts) * rows_per_rank + u / nparts;
+  }
+}
+/// p = 1/V, plast = 0, iweights of the owned vertices from the global out-degrees.
+static __global__ void part_pr_reset_kernel(int n_local, int nparts, int part, int n_global, float alpha,
+                                            const int* __restrict__ outdeg, float* p, float* plast,
+                                            float* iw) {
+  const float p0 = static_cast<float>(1.0 / static_cast<double>(n_global));
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n_local; l += gridDim.x * blockDim.x) {
+    p[l] = p0;
+    plast[l] = 0.0f;
+    int d = outdeg[l * nparts + part];
+    float val = d <= (1 << 24) ? static_cast<float>(d) : 16777216.0f;
+    iw[l] = val != 0.0f ? __fdiv_rn(alpha, val) : 0.0f;
+  }
+}
+/// plast = p, c = plast*iw, this rank's fp64 dangling partial (last CTA folds the per-CTA partials).
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads)
+part_pr_prepare_kernel(int n_local, float alpha, const float* __restrict__ p,
+                       const float* __restrict__ iw, float* __restrict__ plast,
+                       float* __restrict__ c, double* __restrict__ partials, unsigned* ticket,
+                       double* dsum_out) {
+  __shared__ double s_red[kThreads / 32];
+  __shared__ bool s_last;
+  const int per = (n_local + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per, hi = min(n_local, lo + per);
+  double acc = 0.0;
+  for (int v = lo + threadIdx.x; v < hi; v += kThreads) {
+    float pv = p[v], w = iw[v];
+    plast[v] = pv;
+    c[v] = __fmul_rn(pv, w);
+    if (w == 0.0f)
+      acc += static_cast<double>(__fmul_rn(alpha, pv));
+  }
+  acc = warp_sum(acc);
+  if (lane_id() == 0)
+    s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w)
+      t += s_red[w];
+    partials[blockIdx.x] = t;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {
+    __threadfence();
+    double t = 0.0;
+    const int chunk = (gridDim.x + 31) / 32;
+    for (int i = 0; i < chunk; ++i) {
+      int k = threadIdx.x * chunk + i;
+      if (k < static_cast<int>(gridDim.x))
+        t += __ldcg(partials + k);
+    }
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      *dsum_out = t;
+      *ticket = 0;
+    }
+  }
+}
+/// base = (1 - alpha + (float)dsum_global) / V ; also publishes the previous error bits and clears them.
+static __global__ void part_pr_base_kernel(const double* dsum_global, float alpha, int n_global,
+                                           float* base_out) {
+  const float dsum = static_cast<float>(*dsum_global);
+  *base_out = __fdiv_rn(__fadd_rn(__fsub_rn(1.0f, alpha), dsum), static_cast<float>(n_global));
+}
+static __global__ void part_pr_err_kernel(unsigned* err_bits, float* err_out) {
+  *err_out = __uint_as_float(*err_bits);
+  *err_bits = 0;
+}
+
+/// Per-rank state of a partitioned PageRank.
+struct part_pr_state_t {
+  int nparts = 1, part = 0, n_global = 0, n_local = 0, rows_per_rank = 0;
+  dbuf_t<int> outdeg;       // global out-degrees (after the host's all-reduce)
+  dbuf_t<int> remapped;     // column ids -> positions in the gathered c array
+  dbuf_t<float> p;          // owned ranks
+  dbuf_t<double> dsum;      // [0] local dangling partial (in/out of the all-reduce)
+  dbuf_t<float> err;        // [0] local max |p - plast| (in/out of the all-reduce)
+  pr_scratch_t sc;
+  csr_view_t t;             // local in-edge rows with remapped columns
+  ctrl_t* ctrl = nullptr;
+};
+
 static __global__ void pr_err_feedback_kernel(unsigned* err_bits, float* h_err) {
   *h_err = __uint_as_float(*err_bits);
   *err_bits = 0;

@@ -184,6 +184,7 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
     if (iteration < 64)
       B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration], st));
     advance_launch_t lcfg = cfg;
+    lcfg.avg_degree = (iteration > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
     if (iteration == 0) {
       lcfg.lb = lb_t::block_mapped;  // one row of unknown length: binned kernel + hub slabs
     } else if (static_cast<long long>(m_f) < cfg.small_frontier_edges) {

@@ -209,6 +209,39 @@ int b2g_part_bfs_frontier_bitmap_async(b2g_graph_t* g, unsigned* out);
 int b2g_part_bfs_bottomup_async(b2g_graph_t* g, int level, const unsigned* frontier_all);
 /* stats (device, int64[4]) = {next frontier size, its out-degree sum, edges inspected, overflow}. */
 int b2g_part_bfs_end_level_async(b2g_graph_t* g, long long* stats);
+/* ---- multi-GPU PageRank (pull): the rank owns the DESTINATION vertices v % nparts == part and their
+ * in-edges (a partitioned graph whose rows are in-edge lists: any symmetric partitioned graph, or
+ * one created with by_destination != 0).  Per iteration the host side all-gathers c = plast*iweights,
+ * all-reduces the dangling sum (fp64, sum) and the error (fp32, max) between these calls; unweighted
+ * graphs only.  Everything is enqueued on the stream set with b2g_part_set_stream. */
+int b2g_graph_create_rmat_part_ex(int scale, long long n_pairs, unsigned long long seed, int mirror,
+                                  int fold_vertices, int by_destination, int nparts, int part,
+                                  b2g_graph_t** out);
+/* Count out-degrees of the local in-edges into outdeg (device, n_global ints, zeroed by the call). */
+int b2g_part_pr_outdegrees(b2g_graph_t* g, int* outdeg);
+/* Reset ranks and derive iweights from the ALL-REDUCED out-degrees (device, n_global ints). */
+int b2g_part_pr_begin(b2g_graph_t* g, float alpha, const int* outdeg_global);
+/* plast = p, c_local = plast*iweights (device, rows_per_rank floats, zero padded), dsum_local (device
+ * double) = this rank's dangling partial. */
+int b2g_part_pr_prepare(b2g_graph_t* g, float alpha, float* c_local, double* dsum_local);
+/* One pull over the owned rows: c_all = all-gathered c (nparts*rows_per_rank floats), dsum_global =
+ * all-reduced dangling sum (device double), err_local (device float) = max |p - plast| of this rank. */
+int b2g_part_pr_pull(b2g_graph_t* g, float alpha, const float* c_all, const double* dsum_global,
+                     float* err_local);
+/* Copy the owned ranks (n_local floats, local row order). */
+int b2g_part_pr_ranks(b2g_graph_t* g, float* p, int loc);
+/* ---- multi-GPU SSSP: the same push exchange carrying (vertex, fp32 distance) pairs; rows of the packed
+ * message are [count, ids[cap_s], distance bits[cap_s]] (2*cap_s+1 ints).  Needs edge values. */
+int b2g_graph_create_csr_part_weighted(int n_global_vertices, int nparts, int part, int n_local_edges,
+                                       const int* row_offsets, const int* column_indices,
+                                       const float* values, int loc, int symmetric, b2g_graph_t** out);
+int b2g_part_sssp_begin(b2g_graph_t* g, int source, int send_capacity);
+int b2g_part_sssp_relax_async(b2g_graph_t* g, int iteration, const b2g_options_t* opt, int* msg,
+                              int cap_s);
+int b2g_part_sssp_apply_packed_async(b2g_graph_t* g, int iteration, const int* msgs, int cap_s);
+/* stats (device int64[4]) = {next frontier size, its out-degree sum, edges relaxed, overflow}. */
+int b2g_part_sssp_end_iteration_async(b2g_graph_t* g, long long* stats);
+int b2g_part_sssp_distances(b2g_graph_t* g, float* distances, int loc);
 /* Copy the rank's slice of the distances (n_local ints, local row order). */
 int b2g_part_bfs_distances(b2g_graph_t* g, int* distances, int loc);
 

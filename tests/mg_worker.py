@@ -37,6 +37,17 @@ def main():
                     dist.all_reduce(t, op=dist.ReduceOp.MIN)
                     results[f"{name}/{direction}/{lb}/{variant}"] = [int(t.item()), st.level_direction]
         G.close()
+    # partitioned PageRank over NCCL (directed graph, in-edge partition)
+    dro, dci = oracle.rmat_csr(13, 8, 99, mirror=False)
+    G = mg.PartitionedGraph.from_global_csr(dro, dci, world, rank, symmetric=False, by_destination=True)
+    p, iters = mg.pr_rank(mg.CudaRankEngine(G), mg.TorchDistComm())
+    pe, eit = oracle.pr(dro, dci, None, 0.85, 1e-6)
+    mine = pe[rank::world]
+    ok = iters == eit and bool(np.all(np.abs(p.cpu().numpy() - mine) <= 1e-6 * np.abs(mine)))
+    t = torch.tensor([int(ok)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    results["pagerank"] = [int(t.item()), iters]
+    G.close()
     if rank == 0:
         print("MG_RESULT " + json.dumps(results), flush=True)
     dist.destroy_process_group()
