@@ -57,6 +57,12 @@ def _bind():
     L.b2g_part_pr_prepare.argtypes = [vp, C.c_float, vp, vp]
     L.b2g_part_pr_pull.argtypes = [vp, C.c_float, vp, vp, vp]
     L.b2g_part_pr_ranks.argtypes = [vp, vp, ip]
+    L.b2g_graph_create_csr_part_weighted.argtypes = [ip, ip, ip, ip, vp, vp, vp, ip, ip, C.POINTER(vp)]
+    L.b2g_part_sssp_begin.argtypes = [vp, ip, ip]
+    L.b2g_part_sssp_relax_async.argtypes = [vp, ip, C.POINTER(_Options), vp, ip]
+    L.b2g_part_sssp_apply_packed_async.argtypes = [vp, ip, vp, ip]
+    L.b2g_part_sssp_end_iteration_async.argtypes = [vp, vp]
+    L.b2g_part_sssp_distances.argtypes = [vp, vp, ip]
     L._mg_bound = True
     return L
 
@@ -73,15 +79,18 @@ def rows_of(n_global: int, nparts: int, part: int) -> int:
     return (n_global - part + nparts - 1) // nparts
 
 
-def partition_csr(ro: np.ndarray, ci: np.ndarray, nparts: int, part: int):
-    """Rank ``part``'s share of a global CSR: its rows (cyclic), global column ids."""
+def partition_csr(ro: np.ndarray, ci: np.ndarray, nparts: int, part: int, vals: Optional[np.ndarray] = None):
+    """Rank ``part``'s share of a global CSR: its rows (cyclic), global column ids (and values)."""
     n = len(ro) - 1
     rows = np.arange(part, n, nparts)
     deg = (ro[rows + 1] - ro[rows]).astype(np.int64)
     lro = np.zeros(len(rows) + 1, np.int64)
     np.cumsum(deg, out=lro[1:])
     take = np.repeat(ro[rows].astype(np.int64) - lro[:-1], deg) + np.arange(lro[-1])
-    return lro.astype(np.int32), np.ascontiguousarray(ci[take], np.int32)
+    out = lro.astype(np.int32), np.ascontiguousarray(ci[take], np.int32)
+    if vals is not None:
+        return out + (np.ascontiguousarray(np.asarray(vals)[take], np.float32),)
+    return out
 
 
 class PartitionedGraph:
@@ -114,6 +123,16 @@ class PartitionedGraph:
         _check(_bind().b2g_graph_create_rmat_part_ex(scale, n_pairs, seed, int(mirror), fold_vertices,
                                                      int(by_destination), nparts, part, C.byref(h)),
                "b2g_graph_create_rmat_part_ex")
+        return PartitionedGraph(h.value)
+
+    @staticmethod
+    def from_global_csr_weighted(ro, ci, vals, nparts: int, part: int, symmetric: bool = True):
+        lro, lci, lv = partition_csr(np.asarray(ro), np.asarray(ci), nparts, part, vals)
+        h = C.c_void_p()
+        _check(_bind().b2g_graph_create_csr_part_weighted(
+            len(ro) - 1, nparts, part, len(lci), lro.ctypes.data, lci.ctypes.data if len(lci) else None,
+            lv.ctypes.data if len(lv) else None, HOST, int(symmetric), C.byref(h)),
+            "b2g_graph_create_csr_part_weighted")
         return PartitionedGraph(h.value)
 
     @staticmethod
@@ -240,6 +259,27 @@ class CudaRankEngine:
 
     def end_level_async(self, stats):
         _check(self.L.b2g_part_bfs_end_level_async(self.G._h, stats.data_ptr()), "b2g_part_bfs_end_level_async")
+
+    # ---- partitioned SSSP steps ---------------------------------------------------------------------
+    def sssp_begin(self, source: int, send_capacity: int):
+        _check(self.L.b2g_part_sssp_begin(self.G._h, int(source), int(send_capacity)), "b2g_part_sssp_begin")
+
+    def sssp_relax_async(self, iteration: int, msg, cap_s: int):
+        _check(self.L.b2g_part_sssp_relax_async(self.G._h, iteration, C.byref(self.opt), msg.data_ptr(), cap_s),
+               "b2g_part_sssp_relax_async")
+
+    def sssp_apply_packed_async(self, iteration: int, msgs, cap_s: int):
+        _check(self.L.b2g_part_sssp_apply_packed_async(self.G._h, iteration, msgs.data_ptr(), cap_s),
+               "b2g_part_sssp_apply_packed_async")
+
+    def sssp_end_iteration_async(self, stats):
+        _check(self.L.b2g_part_sssp_end_iteration_async(self.G._h, stats.data_ptr()),
+               "b2g_part_sssp_end_iteration_async")
+
+    def sssp_distances(self):
+        d = self.torch.empty(self.n_local, dtype=self.torch.float32, device="cuda")
+        _check(self.L.b2g_part_sssp_distances(self.G._h, d.data_ptr(), DEVICE), "b2g_part_sssp_distances")
+        return d
 
     # ---- partitioned PageRank steps ------------------------------------------------------------
     def pr_outdegrees(self):
@@ -459,6 +499,85 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
         return bfs_rank(engine, comm, source, total_edges, direction, alpha, beta)
     st.levels = level
     return engine.distances(), st
+
+
+def sssp_rank(engine, comm, source: int, cap_s: int = 0):
+    """This rank's part of a partitioned SSSP (frontier Bellman-Ford, push exchange of
+    (vertex, fp32 distance) pairs, receiver applies atomicMin); one host sync per iteration.
+    Returns (owned fp32 distances, iterations, relaxed edges).  A packed row that overflows restarts
+    the run with a four times larger row."""
+    torch, dist = comm.torch, comm.dist
+    P = comm.world
+    rows = rows_of(engine.n_global, P, 0) + 64
+    cap_s = cap_s or min(rows, 1 << 20)
+    while True:
+        engine.sssp_begin(source, max(cap_s, rows))
+        stream = engine.use_stream()
+        overflowed, it, relaxed = False, 0, 0
+        with torch.cuda.stream(stream):
+            msg = torch.zeros((P, 2 * cap_s + 1), dtype=torch.int32, device="cuda")
+            msgs_in = torch.zeros_like(msg)
+            stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+            n_f = 1
+            while n_f > 0:
+                engine.sssp_relax_async(it, msg, cap_s)
+                if P > 1:
+                    dist.all_to_all_single(msgs_in, msg, group=comm.group)
+                    engine.sssp_apply_packed_async(it, msgs_in, cap_s)
+                engine.sssp_end_iteration_async(stats)
+                if P > 1:
+                    dist.all_reduce(stats, group=comm.group)
+                g = [int(x) for x in stats.tolist()]      # the iteration's only host synchronisation
+                if g[3]:
+                    overflowed = True
+                    break
+                n_f = g[0]
+                relaxed += g[2]
+                it += 1
+            stream.synchronize()
+        engine.L.b2g_part_set_stream(engine.G._h, None)
+        if not overflowed:
+            return engine.sssp_distances(), it, relaxed
+        cap_s *= 4
+
+
+def sssp_lockstep(engines: Sequence, source: int, cap_s: int = 0):
+    """Several simulated ranks in one process (single-GPU test of the partitioned SSSP)."""
+    import torch
+    P = len(engines)
+    rows = rows_of(engines[0].n_global, P, 0) + 64
+    cap_s = cap_s or min(rows, 1 << 20)
+    while True:
+        for e in engines:
+            e.sssp_begin(source, max(cap_s, rows))
+        stream = engines[0].use_stream()
+        for e in engines[1:]:
+            e.use_stream(stream)
+        overflowed, it = False, 0
+        with torch.cuda.stream(stream):
+            msgs = [torch.zeros((P, 2 * cap_s + 1), dtype=torch.int32, device="cuda") for _ in engines]
+            stats = [torch.zeros(4, dtype=torch.int64, device="cuda") for _ in engines]
+            n_f = 1
+            while n_f > 0:
+                for e, m in zip(engines, msgs):
+                    e.sssp_relax_async(it, m, cap_s)
+                for r, e in enumerate(engines):        # "all-to-all": rank r receives row r of every peer
+                    inbox = torch.stack([msgs[p][r] for p in range(P)]).contiguous()
+                    e.sssp_apply_packed_async(it, inbox, cap_s)
+                for e, s_ in zip(engines, stats):
+                    e.sssp_end_iteration_async(s_)
+                tot = torch.stack(stats).sum(0).tolist()
+                if tot[3]:
+                    overflowed = True
+                    break
+                n_f = int(tot[0])
+                it += 1
+            stream.synchronize()
+        for e in engines:
+            e.L.b2g_part_set_stream(e.G._h, None)
+        if not overflowed:
+            return [e.sssp_distances() for e in engines], it
+        cap_s *= 4
 
 
 def pr_rank(engine, comm, alpha: float = 0.85, tol: float = 1e-6, max_iter: int = 0):

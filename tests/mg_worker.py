@@ -48,6 +48,16 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     results["pagerank"] = [int(t.item()), iters]
     G.close()
+    # partitioned SSSP over NCCL
+    w = oracle.edge_weights(23, ro, ci, True)
+    G = mg.PartitionedGraph.from_global_csr_weighted(ro, ci, w, world, rank)
+    d, iters, relaxed = mg.sssp_rank(mg.CudaRankEngine(G), mg.TorchDistComm(), src)
+    es = oracle.sssp(ro, ci, w, src)[rank::world]
+    ok = bool(np.array_equal(d.cpu().numpy().view(np.uint32), es.view(np.uint32)))
+    t = torch.tensor([int(ok)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    results["sssp"] = [int(t.item()), iters]
+    G.close()
     if rank == 0:
         print("MG_RESULT " + json.dumps(results), flush=True)
     dist.destroy_process_group()

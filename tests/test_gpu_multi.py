@@ -72,7 +72,7 @@ def test_nccl_two_or_more_gpus(gb):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("MG_RESULT ")][-1]
     res = json.loads(line[len("MG_RESULT "):])
-    assert len(res) == 25 and all(v[0] == 1 for v in res.values()), res
+    assert len(res) == 26 and all(v[0] == 1 for v in res.values()), res
 
 
 def test_async_driver_single_rank(gb):
@@ -126,3 +126,22 @@ def test_partitioned_pagerank_simulated_ranks(gb, P, mirror):
         assert iters == exp_iters and np.array_equal(got2, got)
         for g in graphs:
             g.close()
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_partitioned_sssp_simulated_ranks(gb, P):
+    """Partitioned SSSP: (vertex, distance) pairs pushed to the owner; fp32 distances bit-exact."""
+    from gunrock_b200 import multi_gpu as mg
+    ro, ci = oracle.rmat_csr(13, 8, 606)
+    w = oracle.edge_weights(17, ro, ci, True)
+    graphs = [mg.PartitionedGraph.from_global_csr_weighted(ro, ci, w, P, r) for r in range(P)]
+    deg = np.diff(ro)
+    for src in (int(deg.argmax()), int(np.flatnonzero(deg > 0)[-1])):
+        exp = oracle.sssp(ro, ci, w, src)
+        for cap in (0, 8):        # 8: forces the overflow -> restart path
+            engines = [mg.CudaRankEngine(g, gb.options_t(hub_threshold=256)) for g in graphs]
+            ds, iters = mg.sssp_lockstep(engines, src, cap_s=cap)
+            got = mg.gather_distances([d.cpu().numpy() for d in ds], len(ro) - 1)
+            assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (P, src, cap)
+    for g in graphs:
+        g.close()
