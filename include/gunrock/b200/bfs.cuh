@@ -166,13 +166,19 @@ bfs_bottom_up_kernel(csr_view_t in, unsigned* __restrict__ visited,
   const int* __restrict__ ci = in.column_indices;
   unsigned long long scanned = 0, found_deg = 0;
   int found_cnt = 0;
-  for (int wi = gw; wi < words; wi += warps) {
-    const unsigned vis = visited[wi];
-    if (vis == 0xffffffffu) {
-      if (lane == 0)
-        next[wi] = 0;
-      continue;
-    }
+  // 32 words per warp pass: one coalesced load decides which of them still hold unvisited
+  // vertices (late levels: almost none), so the sweep is bandwidth- not latency-bound.
+  for (int w0 = gw * 32; w0 < words; w0 += warps * 32) {
+    const int my_wi = w0 + lane;
+    const unsigned my_vis = my_wi < words ? visited[my_wi] : 0xffffffffu;
+    if (my_wi < words && my_vis == 0xffffffffu)
+      next[my_wi] = 0;
+    unsigned todo = __ballot_sync(kFull, my_vis != 0xffffffffu);
+    while (todo) {
+    const int src_lane = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int wi = w0 + src_lane;
+    const unsigned vis = __shfl_sync(kFull, my_vis, src_lane);
     const int v = (wi << 5) + lane;
     bool searching = v < in.n_vertices && !((vis >> lane) & 1u);
     int start = 0, end = 0;
@@ -225,6 +231,7 @@ bfs_bottom_up_kernel(csr_view_t in, unsigned* __restrict__ visited,
         visited[wi] = vis | fm;
     }
     found_cnt += found ? 1 : 0;
+    }
   }
   scanned = warp_sum(scanned);
   found_deg = warp_sum(found_deg);
