@@ -27,6 +27,14 @@ A="$REF/include/gunrock/algorithms"
 nvcc $FLAGS -I"$REF/examples/algorithms/bfs" -I"$REF/examples/algorithms/sssp" \
   -DREF_BFS_HXX="\"$A/bfs.hxx\"" -DREF_SSSP_HXX="\"$A/sssp.hxx\"" -DREF_PR_HXX="\"$A/pr.hxx\"" \
   -o "$OUT/ref_algorithms" "$ROOT/examples/ref_algorithms_driver.cu" & pids+=($!)
+#  4. widening: the reference's OTHER algorithms -- their own algorithm headers and
+#     unchanged example TUs -- on our framework/operator headers -> bin/ext_<alg>
+SHIM="$OUT/shim/gunrock/algorithms"
+mkdir -p "$SHIM"
+for alg in bc color geo hits kcore ppr spmv; do
+  echo "#include \"$REF/include/gunrock/algorithms/$alg.hxx\"" > "$SHIM/$alg.hxx"
+  nvcc $FLAGS -I"$OUT/shim" -I"$REF/examples/algorithms/$alg" -o "$OUT/ext_$alg" "$REF/examples/algorithms/$alg/$alg.cu" & pids+=($!)
+done
 rc=0
 for p in "${pids[@]}"; do wait $p || rc=1; done
 ls -la "$OUT"

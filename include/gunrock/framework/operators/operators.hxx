@@ -5,3 +5,4 @@
 #include <gunrock/framework/operators/filter/filter.hxx>
 #include <gunrock/framework/operators/for/for.hxx>
 #include <gunrock/framework/operators/uniquify/uniquify.hxx>
+#include <gunrock/framework/operators/batch/batch.hxx>

@@ -51,6 +51,17 @@ __device__ __forceinline__ double atomicMax(double* addr, double value) {
 }  // namespace gcuda
 
 namespace math {
+
+/// Generic host/device min / max (used by geo.hxx and friends).
+template <typename type_t>
+__host__ __device__ __forceinline__ constexpr type_t min(const type_t& a, const type_t& b) {
+  return b < a ? b : a;
+}
+template <typename type_t>
+__host__ __device__ __forceinline__ constexpr type_t max(const type_t& a, const type_t& b) {
+  return a < b ? b : a;
+}
+
 namespace atomic {
 
 template <typename type_t>

@@ -129,3 +129,26 @@ def test_header_api_selftest():
     four filters, uniquify, parallel_for, launch_box_t and a hand-written BFS on the raw operators."""
     out = run([need("api_selftest")])
     assert "ALL OK" in out, out
+
+
+@pytest.mark.parametrize("alg", ["color", "kcore", "ppr", "spmv"])
+def test_other_reference_algorithms_validate_on_our_operators(alg, chesapeake_mtx, rmat_mtx):
+    """Widening: the reference's own color / kcore / ppr / spmv algorithm headers and
+    example programs, unchanged, on this repository's framework + operator headers; each program
+    checks itself against the reference CPU implementation compiled into it."""
+    path = rmat_mtx[0]
+    for mtx in (chesapeake_mtx, path):
+        out = run([need("ext_" + alg), "-m", mtx])
+        m = re.search(r"Number of errors : (\d+)", out)
+        assert m, out[-2000:]
+        assert int(m.group(1)) == 0, out[-2000:]
+
+
+@pytest.mark.parametrize("alg", ["bc", "geo", "hits"])
+def test_other_reference_algorithms_run(alg, chesapeake_mtx):
+    """bc / geo / hits have no validator in the reference; they must at least run to completion."""
+    extra = []
+    if alg == "geo":
+        pytest.skip("geo needs a coordinates file")
+    out = run([need("ext_" + alg), "-m", chesapeake_mtx] + extra)
+    assert "Elapsed" in out or "elapsed" in out.lower(), out[-1000:]
