@@ -216,6 +216,32 @@ int main() {
     CHECK(h[0] == n && h[1] == (int)I.size() && h[2] == (int)I.size() && h[3] == 76 * 77 / 2);
   }
 
+  // ---- neighborreduce (dead in the reference since ModernGPU was removed) -----------------------------
+  {
+    thrust::device_vector<float> x(n), y(n, -1.0f);
+    thrust::host_vector<float> hx(n);
+    for (int i = 0; i < n; ++i)
+      hx[i] = 0.25f * (i % 9);
+    x = hx;
+    const float* xp = x.data().get();
+    auto term = [G, xp] __host__ __device__(edge_t e) -> float {
+      return G.get_edge_weight(e) * xp[G.get_destination_vertex(e)];
+    };
+    auto plus = [] __host__ __device__(float a, float b) { return a + b; };
+    int* none = nullptr;
+    operators::neighborreduce::execute(G, none, y.data().get(), term, plus, 0.0f, ctx);
+    ctx.get_context(0)->synchronize();
+    thrust::host_vector<float> hy(y), hw(csr.nonzero_values);
+    bool ok = true;
+    for (int v = 0; v < n; ++v) {
+      double ref = 0;
+      for (int e = ro[v]; e < ro[v + 1]; ++e)
+        ref += (double)hw[e] * hx[ci[e]];
+      ok = ok && std::abs(hy[v] - ref) <= 1e-4 * (1.0 + std::abs(ref));
+    }
+    CHECK(ok);
+  }
+
   // ---- a hand-written BFS on the raw operators, checked against a host BFS ---------------------
   {
     thrust::device_vector<int> dist(n, std::numeric_limits<int>::max());

@@ -6,3 +6,4 @@
 #include <gunrock/framework/operators/for/for.hxx>
 #include <gunrock/framework/operators/uniquify/uniquify.hxx>
 #include <gunrock/framework/operators/batch/batch.hxx>
+#include <gunrock/framework/operators/neighborreduce/neighborreduce.hxx>
