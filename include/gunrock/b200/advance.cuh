@@ -341,9 +341,10 @@ advance_binned_kernel(advance_params_t p, Op op) {
  * coalesced loads instead.
  */
 template <int kThreads, int kChunk, advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kWeights ? 4 : 5)
 advance_hub_kernel(advance_params_t p, Op op) {
   constexpr int kWarps = kThreads / 32;
+  constexpr int kHB = kChunk / kThreads;  // slab edges per thread: all of them in flight at once
   constexpr int kHubs = 512;         // hub descriptors resident in shared memory at once
   constexpr int kSlab = kChunk + 4;  // +4: slabs start at a 16-byte aligned column index
   static_assert(kChunk % 4 == 0, "slab size must keep 16-byte granularity");
@@ -466,13 +467,13 @@ advance_hub_kernel(advance_params_t p, Op op) {
         mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
         phase_bits ^= 1u << buf;
       }
-      for (int i0 = 0; i0 < cnt; i0 += kThreads * kBatch) {
-        int e[kBatch], nbv[kBatch];
-        float w[kBatch];
-        bool valid[kBatch], keep[kBatch];
-        typename op_traits<Op>::token_t tok[kBatch];
+      for (int i0 = 0; i0 < cnt; i0 += kThreads * kHB) {
+        int e[kHB], nbv[kHB];
+        float w[kHB];
+        bool valid[kHB], keep[kHB];
+        typename op_traits<Op>::token_t tok[kHB];
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
+        for (int k = 0; k < kHB; ++k) {
           int i = i0 + k * kThreads + threadIdx.x;
           e[k] = e0 + i;
           valid[k] = i < cnt;
@@ -491,15 +492,15 @@ advance_hub_kernel(advance_params_t p, Op op) {
           }
         }
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k)
+        for (int k = 0; k < kHB; ++k)
           if (valid[k])
             tok[k] = op_prefetch(op, nbv[k]);
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k)
+        for (int k = 0; k < kHB; ++k)
           keep[k] = valid[k] && op_commit(op, u, nbv[k], e[k], w[k], tok[k]);
         if (kOut != advance_output_t::none) {
 #pragma unroll
-          for (int k = 0; k < kBatch; ++k)
+          for (int k = 0; k < kHB; ++k)
             em.push(keep[k], kOut == advance_output_t::edges ? e[k] : op_emit(op, nbv[k]));
         }
       }
@@ -992,7 +993,7 @@ inline void launch_advance(workspace_t& ws,
           <<<grid, kThreads, 0, ws.stream>>>(p, op);
     if (cfg.hub_threshold < (1 << 30))
       advance_hub_kernel<kThreads, 2048, kOut, kDegSum, kWeights>
-          <<<sms * 4, kThreads, 0, ws.stream>>>(p, op);
+          <<<sms * (kWeights ? 4 : 5), kThreads, 0, ws.stream>>>(p, op);
     else
       ws.launches -= 1;
   }

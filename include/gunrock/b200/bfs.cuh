@@ -76,14 +76,24 @@ struct bfs_atomic_min_op {
 /// sweep need not look at it again every level (60 % of an RMAT-26 graph is isolated vertices).
 /// The bits are OR-ed into the visited map at reset; top-down never targets them, and the source
 /// gets its own bit and label regardless.
-static __global__ void bfs_unreachable_map_kernel(const int* __restrict__ in_offsets, int n_vertices,
-                                                  unsigned* __restrict__ map) {
+/// Also emits first_in[v] = the first (lowest-id) in-neighbour of v: a dense V-int array the
+/// bottom-up sweep reads coalesced for its first probe -- in the heavy pull level most vertices find
+/// their parent there (sorted adjacency: the first neighbour is the likeliest hub) and never touch
+/// the scattered column-index sectors.
+static __global__ void bfs_unreachable_map_kernel(const int* __restrict__ in_offsets,
+                                                  const int* __restrict__ in_indices, int n_vertices,
+                                                  unsigned* __restrict__ map, int* __restrict__ first_in) {
   const int words = (n_vertices + 31) / 32;
   const int lane = lane_id();
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < words; wi += warps) {
     int v = (wi << 5) + lane;
-    bool dead = v >= n_vertices || in_offsets[v + 1] == in_offsets[v];
+    bool dead = true;
+    if (v < n_vertices) {
+      int s = in_offsets[v], e = in_offsets[v + 1];
+      dead = e == s;
+      first_in[v] = dead ? -1 : in_indices[s];
+    }
     unsigned m = __ballot_sync(kFull, dead);
     if (lane == 0)
       map[wi] = m;
@@ -155,7 +165,7 @@ static __global__ void bitmap_to_queue_kernel(const unsigned* __restrict__ bm, i
  */
 template <int kThreads, int kSerial>
 __global__ void __launch_bounds__(kThreads)
-bfs_bottom_up_kernel(csr_view_t in, unsigned* __restrict__ visited,
+bfs_bottom_up_kernel(csr_view_t in, const int* __restrict__ first_in, unsigned* __restrict__ visited,
                      const unsigned* __restrict__ frontier, unsigned* __restrict__ next, int* dist,
                      int next_level, ctrl_t* ctrl, int* next_count) {
   const int lane = lane_id();
@@ -181,14 +191,23 @@ bfs_bottom_up_kernel(csr_view_t in, unsigned* __restrict__ visited,
     const unsigned vis = __shfl_sync(kFull, my_vis, src_lane);
     const int v = (wi << 5) + lane;
     bool searching = v < in.n_vertices && !((vis >> lane) & 1u);
-    int start = 0, end = 0;
+    bool found = false;
+    // probe 0: the cached first in-neighbour (coalesced read, no column-index sector touched)
     if (searching) {
+      const int u0 = first_in[v];
+      ++scanned;
+      if (u0 >= 0 && bitmap_test(frontier, u0)) {
+        found = true;
+        searching = false;
+      }
+    }
+    int start = 0, end = 0;
+    if (searching || found) {
       start = ro[v];
       end = ro[v + 1];
     }
     const int deg = end - start;
-    bool found = false;
-    int e = start;
+    int e = start + 1;  // edge 0 was probe 0
     for (int k = 0; k < kSerial; ++k) {
       if (searching && e < end) {
         int u = ci[e++];
@@ -265,6 +284,7 @@ struct bfs_config_t {
 /// Persistent per-graph BFS scratch (allocated once; nothing is allocated inside run()).
 struct bfs_scratch_t {
   dbuf_t<unsigned> visited, fbm, nbm, unreachable;
+  dbuf_t<int> first_in;                  // first in-neighbour of every vertex (bottom-up probe 0)
   const int* unreachable_for = nullptr;  // in-offsets array the unreachable map was built from
   dbuf_t<int> q[2];
   dbuf_t<int> counts;  // [0],[1] queue sizes
@@ -338,7 +358,9 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   if (can_pull) {  // per-graph map of vertices without in-edges (built once, like the transpose)
     if (sc.unreachable_for != in_g.row_offsets) {
       sc.unreachable.ensure(static_cast<size_t>(words) + 4);
-      bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(in_g.row_offsets, V, sc.unreachable.ptr);
+      sc.first_in.ensure(static_cast<size_t>(V) + 64);
+      bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(in_g.row_offsets, in_g.column_indices, V,
+                                                          sc.unreachable.ptr, sc.first_in.ptr);
       sc.unreachable_for = in_g.row_offsets;
       ws.launches += 1;
     }
@@ -414,7 +436,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       }
       ca = ws.next_ctrl();
       B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 2, 0, sizeof(int), st));
-      bfs_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(in_g, sc.visited.ptr, fbm, nbm, dist,
+      bfs_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(in_g, sc.first_in.ptr, sc.visited.ptr, fbm, nbm, dist,
                                                            level + 1, ca, sc.counts.ptr + 2);
       ws.launches += 1;
       unsigned* t = fbm;
