@@ -774,6 +774,7 @@ struct tail_report_t {
   unsigned long long deg_sum;  // out-degree sum of that frontier
   unsigned long long edges[16];
   int frontier[16];
+  volatile int seq;  // written last, after a system fence (the host polls it)
 };
 
 /**
@@ -787,7 +788,7 @@ template <int kThreads, bool kWeights, typename OpMaker>
 __global__ void __launch_bounds__(kThreads)
 advance_tail_kernel(csr_view_t g, int* q0, int* q1, int* counts, int cur, int first_level,
                     int max_levels, unsigned long long edge_budget, OpMaker make_op,
-                    tail_report_t* rep) {
+                    tail_report_t* rep, int seq) {
   constexpr int kWarps = kThreads / 32;
   __shared__ int s_cnt;
   __shared__ unsigned long long s_deg, s_edges;
@@ -868,6 +869,8 @@ advance_tail_kernel(csr_view_t g, int* q0, int* q1, int* counts, int cur, int fi
     rep->count = n;
     rep->cur = cur;
     rep->deg_sum = deg_sum;
+    __threadfence_system();
+    rep->seq = seq;
   }
 }
 
@@ -883,6 +886,9 @@ struct advance_launch_t {
   /// frontiers whose out-degree sum is below this take the single-kernel path (no scan, no hub
   /// pass): fixed per-level cost matters more than balance there.
   long long small_frontier_edges = 1 << 12;
+  /// fused enactors only: merge_path requests below this many frontier edges use the scan-free
+  /// CTA walk (block_mapped kernels) -- the scan + partition launches cost more than they save.
+  long long mid_frontier_edges = 1 << 20;
   /// block_mapped: average out-degree of the frontier if the caller knows it (0 = unknown).
   double avg_degree = 0.0;
 };

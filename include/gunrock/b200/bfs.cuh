@@ -167,7 +167,12 @@ template <int kThreads, int kSerial>
 __global__ void __launch_bounds__(kThreads)
 bfs_bottom_up_kernel(csr_view_t in, const int* __restrict__ first_in, unsigned* __restrict__ visited,
                      const unsigned* __restrict__ frontier, unsigned* __restrict__ next, int* dist,
-                     int next_level, ctrl_t* ctrl, int* next_count) {
+                     int next_level, ctrl_t* ctrl, int* next_count, int* unv_out, int* unv_count) {
+  // vertices still unvisited after this sweep are collected (staged per warp, one atomic per ~100)
+  // so that the following bottom-up levels walk a dense list instead of sweeping every word
+  __shared__ int s_emit[kThreads / 32][kEmitCap];
+  warp_emitter_t<kEmitCap, false> em;
+  em.init(s_emit[threadIdx.x >> 5], unv_out, unv_count, in.n_vertices, nullptr, ctrl);
   const int lane = lane_id();
   const int words = (in.n_vertices + 31) / 32;
   const int warps = (gridDim.x * kThreads) >> 5;
@@ -192,19 +197,18 @@ bfs_bottom_up_kernel(csr_view_t in, const int* __restrict__ first_in, unsigned* 
     const int v = (wi << 5) + lane;
     bool searching = v < in.n_vertices && !((vis >> lane) & 1u);
     bool found = false;
-    // probe 0: the cached first in-neighbour (coalesced read, no column-index sector touched)
+    // probe 0: the cached first in-neighbour (coalesced read, no column-index sector touched);
+    // the row bounds are fetched alongside it so a miss costs no extra round trip
+    int start = 0, end = 0;
     if (searching) {
       const int u0 = first_in[v];
+      start = ro[v];
+      end = ro[v + 1];
       ++scanned;
       if (u0 >= 0 && bitmap_test(frontier, u0)) {
         found = true;
         searching = false;
       }
-    }
-    int start = 0, end = 0;
-    if (searching || found) {
-      start = ro[v];
-      end = ro[v + 1];
     }
     const int deg = end - start;
     int e = start + 1;  // edge 0 was probe 0
@@ -250,8 +254,113 @@ bfs_bottom_up_kernel(csr_view_t in, const int* __restrict__ first_in, unsigned* 
         visited[wi] = vis | fm;
     }
     found_cnt += found ? 1 : 0;
+    if (unv_out)
+      em.push(v < in.n_vertices && !((vis >> lane) & 1u) && !found, v);
     }
   }
+  if (unv_out)
+    em.flush();
+  scanned = warp_sum(scanned);
+  found_deg = warp_sum(found_deg);
+  found_cnt = warp_sum(found_cnt);
+  if (lane == 0) {
+    if (scanned)
+      atomicAdd(&ctrl->edges, scanned);
+    if (found_cnt) {
+      atomicAdd(&ctrl->deg_sum, found_deg);
+      atomicAdd(next_count, found_cnt);
+    }
+  }
+}
+
+/**
+ * @brief Bottom-up over a LIST of still-unvisited vertices (second and later consecutive pull
+ * levels).  After the first sweep only a few percent of the vertices are still unvisited but they
+ * are spread over almost every 32-vertex word, so sweeping words again would run with 2-3 active
+ * lanes per warp; here every lane has a vertex.  Found vertices set their bit in `next` / `visited`
+ * with atomicOr; the rest go to the next list.
+ */
+template <int kThreads, int kSerial>
+__global__ void __launch_bounds__(kThreads)
+bfs_bottom_up_list_kernel(csr_view_t in, const int* __restrict__ first_in, const int* __restrict__ unv_in,
+                          const int* __restrict__ unv_in_count, unsigned* visited,
+                          const unsigned* __restrict__ frontier, unsigned* next, int* dist,
+                          int next_level, ctrl_t* ctrl, int* next_count, int* unv_out, int* unv_count) {
+  __shared__ int s_emit[kThreads / 32][kEmitCap];
+  warp_emitter_t<kEmitCap, false> em;
+  em.init(s_emit[threadIdx.x >> 5], unv_out, unv_count, in.n_vertices, nullptr, ctrl);
+  const int lane = lane_id();
+  const int n = *unv_in_count;
+  const int* __restrict__ ro = in.row_offsets;
+  const int* __restrict__ ci = in.column_indices;
+  unsigned long long scanned = 0, found_deg = 0;
+  int found_cnt = 0;
+  for (;;) {
+    int base = 0;
+    if (lane == 0)
+      base = atomicAdd(&ctrl->work, 32);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= n)
+      break;
+    const int i = base + lane;
+    bool searching = i < n;
+    const int v = searching ? unv_in[i] : 0;
+    bool found = false;
+    int start = 0, end = 0;
+    if (searching) {
+      const int u0 = first_in[v];
+      start = ro[v];
+      end = ro[v + 1];
+      ++scanned;
+      if (u0 >= 0 && bitmap_test(frontier, u0)) {
+        found = true;
+        searching = false;
+      }
+    }
+    const int deg = end - start;
+    int e = start + 1;
+    for (int k = 0; k < kSerial; ++k) {
+      if (searching && e < end) {
+        int u = ci[e++];
+        ++scanned;
+        if (bitmap_test(frontier, u)) {
+          found = true;
+          searching = false;
+        }
+      }
+    }
+    if (e >= end)
+      searching = false;
+    unsigned rest = __ballot_sync(kFull, searching);
+    while (rest) {
+      int leader = __ffs(rest) - 1;
+      rest &= rest - 1;
+      int s = __shfl_sync(kFull, e, leader);
+      int t = __shfl_sync(kFull, end, leader);
+      bool hit = false;
+      for (int off = s; off < t && !hit; off += 32) {
+        int idx = off + lane;
+        bool mine = false;
+        if (idx < t) {
+          ++scanned;
+          mine = bitmap_test(frontier, ci[idx]);
+        }
+        hit = __any_sync(kFull, mine);
+      }
+      if (lane == leader)
+        found = hit;
+    }
+    if (found) {
+      dist[v] = next_level;
+      found_deg += static_cast<unsigned>(deg);
+      const unsigned bit = 1u << (v & 31);
+      atomicOr(next + (v >> 5), bit);
+      atomicOr(visited + (v >> 5), bit);
+      ++found_cnt;
+    }
+    em.push(i < n && !found, v);
+  }
+  em.flush();
   scanned = warp_sum(scanned);
   found_deg = warp_sum(found_deg);
   found_cnt = warp_sum(found_cnt);
@@ -285,6 +394,7 @@ struct bfs_config_t {
 struct bfs_scratch_t {
   dbuf_t<unsigned> visited, fbm, nbm, unreachable;
   dbuf_t<int> first_in;                  // first in-neighbour of every vertex (bottom-up probe 0)
+  dbuf_t<int> unv[2];                    // still-unvisited vertices (consecutive bottom-up levels)
   const int* unreachable_for = nullptr;  // in-offsets array the unreachable map was built from
   dbuf_t<int> q[2];
   dbuf_t<int> counts;  // [0],[1] queue sizes
@@ -293,8 +403,10 @@ struct bfs_scratch_t {
     int overflow;
     unsigned long long deg_sum;
     unsigned long long edges;
+    volatile int seq;  // written last (after a system fence): the host polls it
   };
   host_fb_t* h_fb = nullptr;  // pinned
+  int seq = 0;
   tail_report_t* h_tail = nullptr;  // pinned
   cudaEvent_t ev[128] = {};   // per-level event pairs (first 64 levels are timed)
   ~bfs_scratch_t() {
@@ -313,11 +425,15 @@ struct bfs_scratch_t {
     nbm.ensure(words);
     q[0].ensure(static_cast<size_t>(V) + 64);
     q[1].ensure(static_cast<size_t>(V) + 64);
-    counts.ensure(4);
-    if (!h_fb)
+    counts.ensure(8);
+    if (!h_fb) {
       B2G_CHECK(cudaMallocHost(&h_fb, sizeof(host_fb_t)));
-    if (!h_tail)
+      h_fb->seq = 0;
+    }
+    if (!h_tail) {
       B2G_CHECK(cudaMallocHost(&h_tail, sizeof(tail_report_t)));
+      h_tail->seq = 0;
+    }
     if (!ev[0])
       for (auto& e : ev)
         B2G_CHECK(cudaEventCreate(&e));
@@ -325,7 +441,7 @@ struct bfs_scratch_t {
 };
 
 static __global__ void bfs_feedback_kernel(const int* count, const ctrl_t* a, const ctrl_t* b,
-                                    bfs_scratch_t::host_fb_t* fb) {
+                                    bfs_scratch_t::host_fb_t* fb, int seq) {
   fb->count = *count;
   unsigned long long ds = a ? a->deg_sum : 0, ed = a ? a->edges : 0;
   int ov = a ? a->overflow : 0;
@@ -337,6 +453,8 @@ static __global__ void bfs_feedback_kernel(const int* count, const ctrl_t* a, co
   fb->deg_sum = ds;
   fb->edges = ed;
   fb->overflow = ov;
+  __threadfence_system();
+  fb->seq = seq;
 }
 
 /**
@@ -379,6 +497,8 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   unsigned long long explored = 0;
   unsigned* fbm = sc.fbm.ptr;
   unsigned* nbm = sc.nbm.ptr;
+  bool unv_valid = false;  // sc.unv[unv_cur] lists exactly the vertices still unvisited
+  int unv_cur = 0;
   while (n_f > 0) {
     // ---- tiny queue frontier: run the tail of the traversal in one single-CTA launch ------------
     if (level > 0 && !bottom_up && !cfg.use_atomic_min_op &&
@@ -388,11 +508,11 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       advance_tail_kernel<1024, false><<<1, 1024, 0, st>>>(
           out_g, sc.q[0].ptr, sc.q[1].ptr, sc.counts.ptr, cur, level, 16,
           static_cast<unsigned long long>(cfg.advance.small_frontier_edges),
-          bfs_claim_maker{sc.visited.ptr, dist}, sc.h_tail);
+          bfs_claim_maker{sc.visited.ptr, dist}, sc.h_tail, ++sc.seq);
       if (level < 64)
         B2G_CHECK(cudaEventRecord(sc.ev[2 * level + 1], st));
       ws.launches += 1;
-      B2G_CHECK(cudaStreamSynchronize(st));
+      wait_for_sequence(&sc.h_tail->seq, sc.seq, st);
       const tail_report_t& t = *sc.h_tail;
       for (int k = 0; k < t.levels; ++k) {
         explored += t.edges[k];
@@ -408,6 +528,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       cur = t.cur;
       n_f = t.count;
       m_f = t.deg_sum;
+      unv_valid = false;
       continue;
     }
     // ---- choose direction for this level (Beamer et al.) --------------------------------
@@ -435,9 +556,25 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
         ws.launches += 1;
       }
       ca = ws.next_ctrl();
+      sc.unv[0].ensure(static_cast<size_t>(V) + 64);
+      sc.unv[1].ensure(static_cast<size_t>(V) + 64);
       B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 2, 0, sizeof(int), st));
-      bfs_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(in_g, sc.first_in.ptr, sc.visited.ptr, fbm, nbm, dist,
-                                                           level + 1, ca, sc.counts.ptr + 2);
+      if (!unv_valid) {  // first pull level of a run of pull levels: sweep every visited word
+        B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));
+        bfs_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
+            in_g, sc.first_in.ptr, sc.visited.ptr, fbm, nbm, dist, level + 1, ca, sc.counts.ptr + 2,
+            sc.unv[0].ptr, sc.counts.ptr + 4);
+        unv_cur = 0;
+        unv_valid = true;
+      } else {  // later pull levels: dense list of the vertices still unvisited
+        const int o = unv_cur ^ 1;
+        B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4 + o, 0, sizeof(int), st));
+        B2G_CHECK(cudaMemsetAsync(nbm, 0, sizeof(unsigned) * words, st));
+        bfs_bottom_up_list_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
+            in_g, sc.first_in.ptr, sc.unv[unv_cur].ptr, sc.counts.ptr + 4 + unv_cur, sc.visited.ptr, fbm,
+            nbm, dist, level + 1, ca, sc.counts.ptr + 2, sc.unv[o].ptr, sc.counts.ptr + 4 + o);
+        unv_cur = o;
+      }
       ws.launches += 1;
       unsigned* t = fbm;
       fbm = nbm;
@@ -445,6 +582,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       bottom_up = true;
       count_ptr = sc.counts.ptr + 2;
     } else {
+      unv_valid = false;  // a push level claims vertices the list does not know about
       if (bottom_up) {  // bitmap -> queue
         B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + cur, 0, sizeof(int), st));
         bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(fbm, words, sc.q[cur].ptr,
@@ -459,6 +597,9 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       lcfg.avg_degree = (level > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
       if (level == 0) {
         lcfg.lb = lb_t::block_mapped;  // one row of unknown length: binned kernel + hub slabs
+      } else if (lcfg.lb == lb_t::merge_path &&
+                 static_cast<long long>(m_f) < cfg.advance.mid_frontier_edges) {
+        lcfg.lb = lb_t::block_mapped;  // mid-size frontier: skip the scan + partition launches
       } else if (static_cast<long long>(m_f) < cfg.advance.small_frontier_edges) {
         lcfg.lb = lb_t::block_mapped;  // one kernel: warp/thread bins only
         lcfg.hub_threshold = 1 << 30;
@@ -479,9 +620,9 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
     }
     if (level < 64)
       B2G_CHECK(cudaEventRecord(sc.ev[2 * level + 1], st));
-    bfs_feedback_kernel<<<1, 1, 0, st>>>(count_ptr, ca, cb, sc.h_fb);
+    bfs_feedback_kernel<<<1, 1, 0, st>>>(count_ptr, ca, cb, sc.h_fb, ++sc.seq);
     ws.launches += 1;
-    B2G_CHECK(cudaStreamSynchronize(st));
+    wait_for_sequence(&sc.h_fb->seq, sc.seq, st);
     if (sc.h_fb->overflow)
       throw std::runtime_error("bfs: output frontier overflow");
     if (levels)

@@ -103,6 +103,33 @@ struct dbuf_t {
   }
 };
 
+/**
+ * @brief Wait until a kernel has published `expected` in a pinned host word.  A feedback kernel
+ * writes its report to pinned memory, fences (`__threadfence_system`) and then stores the sequence
+ * number; polling that word returns a few microseconds after the kernel retires, where
+ * cudaStreamSynchronize costs 10-20 us of wake-up latency per BSP level.  The stream is queried
+ * every few thousand polls so an execution error still surfaces as an exception.
+ */
+inline void wait_for_sequence(const volatile int* word, int expected, cudaStream_t stream) {
+  for (unsigned spins = 1;; ++spins) {
+    if (*word == expected)
+      return;
+    if ((spins & 0xfff) == 0) {
+      cudaError_t q = cudaStreamQuery(stream);
+      if (q == cudaSuccess) {  // everything retired: the word must be there (or never will be)
+        if (*word == expected)
+          return;
+        B2G_CHECK(cudaStreamSynchronize(stream));
+        if (*word == expected)
+          return;
+        throw std::runtime_error("feedback sequence never arrived");
+      }
+      if (q != cudaErrorNotReady)
+        B2G_CHECK(q);
+    }
+  }
+}
+
 /// Scratch shared by all operator launches on one stream.
 struct workspace_t {
   cudaStream_t stream = nullptr;

@@ -94,7 +94,9 @@ struct sssp_scratch_t {
     int overflow;
     unsigned long long edges;
     unsigned long long deg_sum;
+    volatile int seq;
   };
+  int seq = 0;
   host_fb_t* h_fb = nullptr;
   tail_report_t* h_tail = nullptr;
   cudaEvent_t ev[128] = {};
@@ -112,10 +114,14 @@ struct sssp_scratch_t {
     q[0].ensure(static_cast<size_t>(V) + 64);
     q[1].ensure(static_cast<size_t>(V) + 64);
     counts.ensure(4);
-    if (!h_fb)
+    if (!h_fb) {
       B2G_CHECK(cudaMallocHost(&h_fb, sizeof(host_fb_t)));
-    if (!h_tail)
+      h_fb->seq = 0;
+    }
+    if (!h_tail) {
       B2G_CHECK(cudaMallocHost(&h_tail, sizeof(tail_report_t)));
+      h_tail->seq = 0;
+    }
     if (!ev[0])
       for (auto& e : ev)
         B2G_CHECK(cudaEventCreate(&e));
@@ -123,11 +129,13 @@ struct sssp_scratch_t {
 };
 
 static __global__ void sssp_feedback_kernel(const int* count, const ctrl_t* c,
-                                     sssp_scratch_t::host_fb_t* fb) {
+                                     sssp_scratch_t::host_fb_t* fb, int seq) {
   fb->count = *count;
   fb->overflow = c->overflow;
   fb->edges = c->edges;
   fb->deg_sum = c->deg_sum;
+  __threadfence_system();
+  fb->seq = seq;
 }
 
 struct sssp_level_stat_t {
@@ -158,11 +166,11 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
       advance_tail_kernel<1024, true><<<1, 1024, 0, st>>>(
           g, sc.q[0].ptr, sc.q[1].ptr, sc.counts.ptr, cur, iteration, 16,
           static_cast<unsigned long long>(cfg.small_frontier_edges),
-          sssp_relax_maker{dist, sc.stamp.ptr}, sc.h_tail);
+          sssp_relax_maker{dist, sc.stamp.ptr}, sc.h_tail, ++sc.seq);
       if (iteration < 64)
         B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration + 1], st));
       ws.launches += 1;
-      B2G_CHECK(cudaStreamSynchronize(st));
+      wait_for_sequence(&sc.h_tail->seq, sc.seq, st);
       const tail_report_t& t = *sc.h_tail;
       for (int k = 0; k < t.levels; ++k)
         if (levels)
@@ -187,6 +195,8 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
     lcfg.avg_degree = (iteration > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
     if (iteration == 0) {
       lcfg.lb = lb_t::block_mapped;  // one row of unknown length: binned kernel + hub slabs
+    } else if (lcfg.lb == lb_t::merge_path && static_cast<long long>(m_f) < cfg.mid_frontier_edges) {
+      lcfg.lb = lb_t::block_mapped;  // mid-size frontier: skip the scan + partition launches
     } else if (static_cast<long long>(m_f) < cfg.small_frontier_edges) {
       lcfg.lb = lb_t::block_mapped;  // single-kernel path for tiny frontiers
       lcfg.hub_threshold = 1 << 30;
@@ -196,9 +206,9 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
         sc.q[nxt].ptr, sc.counts.ptr + nxt, V, op, lcfg, &c);
     if (iteration < 64)
       B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration + 1], st));
-    sssp_feedback_kernel<<<1, 1, 0, st>>>(sc.counts.ptr + nxt, c, sc.h_fb);
+    sssp_feedback_kernel<<<1, 1, 0, st>>>(sc.counts.ptr + nxt, c, sc.h_fb, ++sc.seq);
     ws.launches += 1;
-    B2G_CHECK(cudaStreamSynchronize(st));
+    wait_for_sequence(&sc.h_fb->seq, sc.seq, st);
     if (sc.h_fb->overflow)
       throw std::runtime_error("sssp: output frontier overflow");
     if (levels)

@@ -138,7 +138,7 @@ def test_other_reference_algorithms_validate_on_our_operators(alg, chesapeake_mt
     checks itself against the reference CPU implementation compiled into it."""
     path = rmat_mtx[0]
     for mtx in (chesapeake_mtx, path):
-        out = run([need("ext_" + alg), "-m", mtx])
+        out = run([need("ext_" + alg), mtx])      # these examples take the file as argv[1]
         m = re.search(r"Number of errors : (\d+)", out)
         assert m, out[-2000:]
         assert int(m.group(1)) == 0, out[-2000:]
@@ -150,5 +150,5 @@ def test_other_reference_algorithms_run(alg, chesapeake_mtx):
     extra = []
     if alg == "geo":
         pytest.skip("geo needs a coordinates file")
-    out = run([need("ext_" + alg), "-m", chesapeake_mtx] + extra)
+    out = run([need("ext_" + alg), "-m", chesapeake_mtx] + extra)        # bc / hits use parameters_t
     assert "Elapsed" in out or "elapsed" in out.lower(), out[-1000:]
