@@ -871,10 +871,8 @@ int b2g_part_bfs_begin(b2g_graph_t* g, int source, int send_capacity) {
       build_transpose(g);
       if (S.unreachable_for != g->t_view.row_offsets) {
         S.unreachable.ensure(static_cast<size_t>(S.words_per_rank()) + 4);
-        S.first_in.ensure(static_cast<size_t>(g->pt.n_local) + 64);
-        bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(g->t_view.row_offsets,
-                                                            g->t_view.column_indices, g->pt.n_local,
-                                                            S.unreachable.ptr, S.first_in.ptr);
+        bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(g->t_view.row_offsets, g->pt.n_local,
+                                                            S.unreachable.ptr);
         S.unreachable_for = g->t_view.row_offsets;
         g->ws.launches += 1;
       }
@@ -1000,7 +998,7 @@ int b2g_part_bfs_bottomup(b2g_graph_t* g, int level, const unsigned* frontier_al
     // padding words of the next map (beyond local_words) must stay clear for the all-gather
     B2G_CHECK(cudaMemsetAsync(S.nbm.ptr, 0, sizeof(unsigned) * S.words_per_rank(), st));
     part_bottom_up_kernel<256, 8><<<device_info_t::get().sm_count * 8, 256, 0, st>>>(
-        g->pt, g->t_view, S.first_in.ptr, S.words_per_rank(), S.visited.ptr, frontier_all, S.nbm.ptr, S.dist.ptr,
+        g->pt, g->t_view, S.words_per_rank(), S.visited.ptr, frontier_all, S.nbm.ptr, S.dist.ptr,
         level + 1, c, S.counts.ptr + 2);
     g->part_ctrl = c;
     part_feedback_kernel<<<1, 1, 0, st>>>(S.counts.ptr + 2, c, S.send_count.ptr, S.overflow.ptr, 0,
@@ -1145,7 +1143,7 @@ int b2g_part_bfs_bottomup_async(b2g_graph_t* g, int level, const unsigned* front
     B2G_CHECK(cudaMemsetAsync(S.counts.ptr + 2, 0, sizeof(int), st));
     B2G_CHECK(cudaMemsetAsync(S.nbm.ptr, 0, sizeof(unsigned) * S.words_per_rank(), st));
     part_bottom_up_kernel<256, 8><<<device_info_t::get().sm_count * 8, 256, 0, st>>>(
-        g->pt, g->t_view, S.first_in.ptr, S.words_per_rank(), S.visited.ptr, frontier_all, S.nbm.ptr, S.dist.ptr,
+        g->pt, g->t_view, S.words_per_rank(), S.visited.ptr, frontier_all, S.nbm.ptr, S.dist.ptr,
         level + 1, c, S.counts.ptr + 2);
     g->part_ctrl = c;
     g->ws.launches += 1;

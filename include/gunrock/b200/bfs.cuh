@@ -16,7 +16,10 @@
  */
 #pragma once
 
+#include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include <gunrock/b200/advance.cuh>
@@ -76,24 +79,14 @@ struct bfs_atomic_min_op {
 /// sweep need not look at it again every level (60 % of an RMAT-26 graph is isolated vertices).
 /// The bits are OR-ed into the visited map at reset; top-down never targets them, and the source
 /// gets its own bit and label regardless.
-/// Also emits first_in[v] = the first (lowest-id) in-neighbour of v: a dense V-int array the
-/// bottom-up sweep reads coalesced for its first probe -- in the heavy pull level most vertices find
-/// their parent there (sorted adjacency: the first neighbour is the likeliest hub) and never touch
-/// the scattered column-index sectors.
-static __global__ void bfs_unreachable_map_kernel(const int* __restrict__ in_offsets,
-                                                  const int* __restrict__ in_indices, int n_vertices,
-                                                  unsigned* __restrict__ map, int* __restrict__ first_in) {
+static __global__ void bfs_unreachable_map_kernel(const int* __restrict__ in_offsets, int n_vertices,
+                                                  unsigned* __restrict__ map) {
   const int words = (n_vertices + 31) / 32;
   const int lane = lane_id();
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < words; wi += warps) {
     int v = (wi << 5) + lane;
-    bool dead = true;
-    if (v < n_vertices) {
-      int s = in_offsets[v], e = in_offsets[v + 1];
-      dead = e == s;
-      first_in[v] = dead ? -1 : in_indices[s];
-    }
+    bool dead = v >= n_vertices || in_offsets[v + 1] == in_offsets[v];
     unsigned m = __ballot_sync(kFull, dead);
     if (lane == 0)
       map[wi] = m;
@@ -165,7 +158,7 @@ static __global__ void bitmap_to_queue_kernel(const unsigned* __restrict__ bm, i
  */
 template <int kThreads, int kSerial>
 __global__ void __launch_bounds__(kThreads)
-bfs_bottom_up_kernel(csr_view_t in, const int* __restrict__ first_in, unsigned* __restrict__ visited,
+bfs_bottom_up_kernel(csr_view_t in, unsigned* __restrict__ visited,
                      const unsigned* __restrict__ frontier, unsigned* __restrict__ next, int* dist,
                      int next_level, ctrl_t* ctrl, int* next_count, int* unv_out, int* unv_count) {
   // vertices still unvisited after this sweep are collected (staged per warp, one atomic per ~100)
@@ -197,21 +190,13 @@ bfs_bottom_up_kernel(csr_view_t in, const int* __restrict__ first_in, unsigned* 
     const int v = (wi << 5) + lane;
     bool searching = v < in.n_vertices && !((vis >> lane) & 1u);
     bool found = false;
-    // probe 0: the cached first in-neighbour (coalesced read, no column-index sector touched);
-    // the row bounds are fetched alongside it so a miss costs no extra round trip
     int start = 0, end = 0;
     if (searching) {
-      const int u0 = first_in[v];
       start = ro[v];
       end = ro[v + 1];
-      ++scanned;
-      if (u0 >= 0 && bitmap_test(frontier, u0)) {
-        found = true;
-        searching = false;
-      }
     }
     const int deg = end - start;
-    int e = start + 1;  // edge 0 was probe 0
+    int e = start;
     for (int k = 0; k < kSerial; ++k) {
       if (searching && e < end) {
         int u = ci[e++];
@@ -282,7 +267,7 @@ bfs_bottom_up_kernel(csr_view_t in, const int* __restrict__ first_in, unsigned* 
  */
 template <int kThreads, int kSerial>
 __global__ void __launch_bounds__(kThreads)
-bfs_bottom_up_list_kernel(csr_view_t in, const int* __restrict__ first_in, const int* __restrict__ unv_in,
+bfs_bottom_up_list_kernel(csr_view_t in, const int* __restrict__ unv_in,
                           const int* __restrict__ unv_in_count, unsigned* visited,
                           const unsigned* __restrict__ frontier, unsigned* next, int* dist,
                           int next_level, ctrl_t* ctrl, int* next_count, int* unv_out, int* unv_count) {
@@ -308,17 +293,11 @@ bfs_bottom_up_list_kernel(csr_view_t in, const int* __restrict__ first_in, const
     bool found = false;
     int start = 0, end = 0;
     if (searching) {
-      const int u0 = first_in[v];
       start = ro[v];
       end = ro[v + 1];
-      ++scanned;
-      if (u0 >= 0 && bitmap_test(frontier, u0)) {
-        found = true;
-        searching = false;
-      }
     }
     const int deg = end - start;
-    int e = start + 1;
+    int e = start;
     for (int k = 0; k < kSerial; ++k) {
       if (searching && e < end) {
         int u = ci[e++];
@@ -393,7 +372,6 @@ struct bfs_config_t {
 /// Persistent per-graph BFS scratch (allocated once; nothing is allocated inside run()).
 struct bfs_scratch_t {
   dbuf_t<unsigned> visited, fbm, nbm, unreachable;
-  dbuf_t<int> first_in;                  // first in-neighbour of every vertex (bottom-up probe 0)
   dbuf_t<int> unv[2];                    // still-unvisited vertices (consecutive bottom-up levels)
   const int* unreachable_for = nullptr;  // in-offsets array the unreachable map was built from
   dbuf_t<int> q[2];
@@ -476,9 +454,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   if (can_pull) {  // per-graph map of vertices without in-edges (built once, like the transpose)
     if (sc.unreachable_for != in_g.row_offsets) {
       sc.unreachable.ensure(static_cast<size_t>(words) + 4);
-      sc.first_in.ensure(static_cast<size_t>(V) + 64);
-      bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(in_g.row_offsets, in_g.column_indices, V,
-                                                          sc.unreachable.ptr, sc.first_in.ptr);
+      bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(in_g.row_offsets, V, sc.unreachable.ptr);
       sc.unreachable_for = in_g.row_offsets;
       ws.launches += 1;
     }
@@ -499,7 +475,14 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   unsigned* nbm = sc.nbm.ptr;
   bool unv_valid = false;  // sc.unv[unv_cur] lists exactly the vertices still unvisited
   int unv_cur = 0;
+  // B2G_TRACE=1: host-side timeline of every level (microseconds since the run started)
+  static const bool trace = std::getenv("B2G_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto now_us = [&]() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  };
   while (n_f > 0) {
+    const double t_begin = trace ? now_us() : 0.0;
     // ---- tiny queue frontier: run the tail of the traversal in one single-CTA launch ------------
     if (level > 0 && !bottom_up && !cfg.use_atomic_min_op &&
         static_cast<long long>(m_f) < cfg.advance.small_frontier_edges) {
@@ -562,7 +545,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       if (!unv_valid) {  // first pull level of a run of pull levels: sweep every visited word
         B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));
         bfs_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
-            in_g, sc.first_in.ptr, sc.visited.ptr, fbm, nbm, dist, level + 1, ca, sc.counts.ptr + 2,
+            in_g, sc.visited.ptr, fbm, nbm, dist, level + 1, ca, sc.counts.ptr + 2,
             sc.unv[0].ptr, sc.counts.ptr + 4);
         unv_cur = 0;
         unv_valid = true;
@@ -571,7 +554,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
         B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4 + o, 0, sizeof(int), st));
         B2G_CHECK(cudaMemsetAsync(nbm, 0, sizeof(unsigned) * words, st));
         bfs_bottom_up_list_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
-            in_g, sc.first_in.ptr, sc.unv[unv_cur].ptr, sc.counts.ptr + 4 + unv_cur, sc.visited.ptr, fbm,
+            in_g, sc.unv[unv_cur].ptr, sc.counts.ptr + 4 + unv_cur, sc.visited.ptr, fbm,
             nbm, dist, level + 1, ca, sc.counts.ptr + 2, sc.unv[o].ptr, sc.counts.ptr + 4 + o);
         unv_cur = o;
       }
@@ -622,7 +605,11 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       B2G_CHECK(cudaEventRecord(sc.ev[2 * level + 1], st));
     bfs_feedback_kernel<<<1, 1, 0, st>>>(count_ptr, ca, cb, sc.h_fb, ++sc.seq);
     ws.launches += 1;
+    const double t_enq = trace ? now_us() : 0.0;
     wait_for_sequence(&sc.h_fb->seq, sc.seq, st);
+    if (trace)
+      std::fprintf(stderr, "[b2g] level %d: begin %.1f enqueued %.1f feedback %.1f (n_f=%lld m_f=%llu)\n",
+                   level, t_begin, t_enq, now_us(), n_f, m_f);
     if (sc.h_fb->overflow)
       throw std::runtime_error("bfs: output frontier overflow");
     if (levels)

@@ -170,8 +170,7 @@ static __global__ void part_queue_to_bitmap_kernel(const int* __restrict__ q,
  */
 template <int kThreads, int kSerial>
 __global__ void __launch_bounds__(kThreads)
-part_bottom_up_kernel(partition_t pt, csr_view_t in, const int* __restrict__ first_in,
-                      int words_per_rank,
+part_bottom_up_kernel(partition_t pt, csr_view_t in, int words_per_rank,
                       unsigned* __restrict__ visited, const unsigned* __restrict__ frontier_all,
                       unsigned* __restrict__ next, int* dist, int next_level, ctrl_t* ctrl,
                       int* next_count) {
@@ -203,21 +202,13 @@ part_bottom_up_kernel(partition_t pt, csr_view_t in, const int* __restrict__ fir
     const int v = (wi << 5) + lane;
     bool searching = v < pt.n_local && !((vis >> lane) & 1u);
     bool found = false;
-    if (searching) {  // probe 0: cached first in-neighbour (coalesced)
-      const int u0 = first_in[v];
-      ++scanned;
-      if (u0 >= 0 && in_frontier(u0)) {
-        found = true;
-        searching = false;
-      }
-    }
     int start = 0, end = 0;
-    if (searching || found) {
+    if (searching) {
       start = ro[v];
       end = ro[v + 1];
     }
     const int deg = end - start;
-    int e = start + 1;
+    int e = start;
     for (int k = 0; k < kSerial; ++k) {
       if (searching && e < end) {
         int u = ci[e++];
@@ -306,7 +297,6 @@ static __global__ void part_seed_kernel(partition_t pt, int source, int* dist, u
 struct part_bfs_state_t {
   partition_t pt;
   dbuf_t<unsigned> visited, sent, fbm, nbm, unreachable;
-  dbuf_t<int> first_in;
   const int* unreachable_for = nullptr;
   dbuf_t<int> q[2], counts, send_count, overflow, dist;
   dbuf_t<int> send_buf;

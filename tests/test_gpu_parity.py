@@ -150,6 +150,31 @@ def test_edge_cases(gb):
         G.close()
 
 
+def test_many_deferred_rows_and_small_tickets(gb):
+    """Every vertex has 40 out-edges and hub_threshold is 32, so whole frontiers (hundreds of
+    thousands of rows) are deferred to the TMA slab kernel: exercises the 'more batches than CTAs'
+    ownership path of advance_hub_kernel, and the CTA-scan kernel with tiny / full tickets."""
+    rng = np.random.default_rng(2024)
+    V, d = 600_000, 40
+    ci = rng.integers(0, V, V * d).astype(np.int32)
+    ro = (np.arange(V + 1, dtype=np.int64) * d).astype(np.int32)
+    ci = np.sort(ci.reshape(V, d), axis=1).reshape(-1)          # sorted rows (duplicates allowed)
+    w = (1.0 + rng.random(V * d)).astype(np.float32)
+    G = gb.graph_t.from_csr(ro, ci, w, symmetric=False)
+    exp = oracle.bfs(ro, ci, 7)
+    exp_s = oracle.sssp(ro, ci, w, 7)
+    for hub in (32, 4096):
+        for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
+            dd = np.empty(V, np.int32)
+            st = gb.bfs(G, 7, dd, options=gb.options_t(advance_load_balance=lb, hub_threshold=hub))
+            assert np.array_equal(dd, exp), (hub, lb)
+            assert st.edges_touched == int((exp < INT_MAX).sum()) * d
+        f = np.empty(V, np.float32)
+        gb.sssp(G, 7, f, options=gb.options_t(hub_threshold=hub))
+        assert np.array_equal(f.view(np.uint32), exp_s.view(np.uint32)), hub
+    G.close()
+
+
 def test_device_tensor_results_and_stream(gb):
     import torch
     ro, ci = oracle.rmat_csr(12, 16, 9)
