@@ -19,6 +19,8 @@ GPU tests), and (c) on CPU under gloo with a numpy stand-in engine (tests only).
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -444,6 +446,25 @@ def bfs_rank(engine, comm, source: int, total_edges: int, direction: int = advan
     return engine.distances(), st
 
 
+class _phase_marker:
+    """B2G_TRACE: CUDA-event stamps between the phases of one level (device time, this rank)."""
+
+    def __init__(self, torch, enabled):
+        self.torch, self.on, self.ev = torch, enabled is not None, []
+        if self.on:
+            self("start")
+
+    def __call__(self, name):
+        if self.on:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.ev.append((name, e))
+
+    def report(self):
+        self.torch.cuda.current_stream().synchronize()
+        return [(n, 1e3 * self.ev[i - 1][1].elapsed_time(e)) for i, (n, e) in enumerate(self.ev) if i]
+
+
 def bfs_rank_async(engine, comm, source: int, total_edges: int,
                    direction: int = advance_direction_t.optimized, alpha: float = 14.0, beta: float = 24.0,
                    cap_s: int = 0):
@@ -460,6 +481,7 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
     stream = engine.use_stream()
     st = part_bfs_stats_t()
     overflowed = False
+    trace = [] if os.environ.get("B2G_TRACE") else None   # per-level phase times (CUDA events), rank 0 prints
     with torch.cuda.stream(stream):
         msg = torch.zeros((P, cap_s + 1), dtype=torch.int32, device="cuda")
         msgs_in = torch.zeros_like(msg)
@@ -470,18 +492,31 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
                             alpha, beta)
             if level > 0:
                 explored += m_f
+            mark = _phase_marker(torch, trace)
             if go_up:
                 allbm = comm.all_gather_bitmap(engine.frontier_bitmap_async())
+                mark("gather")
                 engine.bottomup_async(level, allbm)
+                mark("sweep")
             else:
-                engine.topdown_async(level, msg, cap_s)
+                # no rank can forward more ids than the frontier has out-edges (unknown for the source)
+                cap_l = cap_s if level == 0 else min(cap_s, max(256, m_f))
+                row = P * (cap_l + 1)
+                out_l, in_l = msg.view(-1)[:row].view(P, cap_l + 1), msgs_in.view(-1)[:row].view(P, cap_l + 1)
+                engine.topdown_async(level, out_l, cap_l)
+                mark("advance")
                 if P > 1:
-                    dist.all_to_all_single(msgs_in, msg, group=comm.group)
-                    engine.claim_packed_async(level, msgs_in, cap_s)
+                    dist.all_to_all_single(in_l, out_l, group=comm.group)
+                    mark("all_to_all")
+                    engine.claim_packed_async(level, in_l, cap_l)
+                    mark("claim")
             engine.end_level_async(stats)
             if P > 1:
                 dist.all_reduce(stats, group=comm.group)
+            mark("stats")
             g = [int(x) for x in stats.tolist()]          # the level's only host synchronisation
+            if trace is not None:
+                trace.append((level, "up" if go_up else "down", n_f, mark.report()))
             if g[3]:
                 overflowed = True
                 break
@@ -495,6 +530,9 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
             level += 1
         stream.synchronize()
     engine.L.b2g_part_set_stream(engine.G._h, None)
+    if trace and comm.rank == 0:
+        for lv, d, nf, rep in trace:
+            print(f"[b2g-part] level {lv} {d} n_f={nf}: " + " ".join(f"{k}={v:.1f}us" for k, v in rep), file=sys.stderr)
     if overflowed:
         return bfs_rank(engine, comm, source, total_edges, direction, alpha, beta)
     st.levels = level
