@@ -225,8 +225,15 @@ def run_partitioned(args, wl, name, rank, world, local):
     eng = mg.CudaRankEngine(G, opt)
     direction = getattr(gb.advance_direction_t, wl["direction"])
 
-    def step():
-        return mg.bfs_rank_async(eng, comm, src, total_edges, direction=direction)
+    exchange = args.exchange
+    if exchange == "p2p":     # the kernels exchange frontiers over NVLink peer memory (bfs_p2p.cuh)
+        mg.p2p_connect(eng, comm)
+
+        def step():
+            return mg.bfs_rank_p2p(eng, src, total_edges, direction)
+    else:                     # NCCL all-to-all / all-gather / all-reduce between the per-rank kernels
+        def step():
+            return mg.bfs_rank_async(eng, comm, src, total_edges, direction=direction)
 
     for _ in range(max(args.warmup, 3)):
         dloc, st = step()
@@ -270,7 +277,9 @@ def run_partitioned(args, wl, name, rank, world, local):
         line = {"metric": f"MTEPS ({name})", "value": value, "unit": "MTEPS", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": wl["desc"], "vertices": G.n_global, "edges": total_edges, "source": src,
+                "config": {"workload": wl["desc"], "exchange": "kernels over NVLink peer memory (CUDA IPC windows)"
+                           if exchange == "p2p" else "NCCL all_to_all_single / all_gather / all_reduce",
+                           "vertices": G.n_global, "edges": total_edges, "source": src,
                            "levels": st.levels, "level_direction": st.level_direction,
                            "level_frontier": st.level_frontier, "level_edges": st.level_edges,
                            "ids_exchanged_per_step_rank0": st.exchanged_ids, "reached_vertices": int(reached.item()),
@@ -279,13 +288,15 @@ def run_partitioned(args, wl, name, rank, world, local):
                            "graph500_mteps": total_edges / (ms / args.steps) / 1e3},
                 "e2e": {"value": edges / ms2 / 1e3, "unit": "MTEPS", "h2d_bytes_per_step": 4,
                         "d2h_bytes_per_step": G.n_local * 4, "ms_per_step": ms2 / args.steps},
-                "gpu_launches": None,
+                "gpu_launches": (st.kernel_launches * args.steps) if exchange == "p2p" else None,
                 "roofline": {"bound": "hbm", "achieved": 4.0 * edges / world / (ms * 1e-3) / 1e9, "peak": peak,
                              "unit": "GB/s", "frac": 4.0 * edges / world / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                              "peak_kind": peak_kind, "kernel": "whole step per rank (advance + sweep + exchange)",
                              "bytes_per_edge": 4},
                 "cpu_baseline": None, "clocks": clocks}
         print(json.dumps(line), flush=True)
+    if exchange == "p2p":
+        mg.p2p_disconnect(eng, comm)
     G.close()
     dist.destroy_process_group()
 
@@ -302,6 +313,8 @@ def main():
     ap.add_argument("--direction", default=None, choices=["forward", "backward", "optimized"])
     ap.add_argument("--hub-threshold", type=int, default=4096)
     ap.add_argument("--ctas-per-sm", type=int, default=8)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="partitioned workloads: frontier exchange by our kernels over peer memory, or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()

@@ -116,6 +116,8 @@ _SYMBOLS = [
     "b2g_part_pr_pull", "b2g_part_pr_ranks",
     "b2g_graph_create_csr_part_weighted", "b2g_part_sssp_begin", "b2g_part_sssp_relax_async",
     "b2g_part_sssp_apply_packed_async", "b2g_part_sssp_end_iteration_async", "b2g_part_sssp_distances",
+    # peer-memory (NVLink) exchange
+    "b2g_part_p2p_window_create", "b2g_part_p2p_attach", "b2g_part_p2p_detach", "b2g_part_bfs_p2p",
 ]
 
 

@@ -12,11 +12,13 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include <gunrock/b200/advance.cuh>
 #include <gunrock/b200/bfs.cuh>
 #include <gunrock/b200/bfs_partitioned.cuh>
+#include <gunrock/b200/bfs_p2p.cuh>
 #include <gunrock/b200/filter.cuh>
 #include <gunrock/b200/pr.cuh>
 #include <gunrock/b200/sssp.cuh>
@@ -58,6 +60,32 @@ bool have_device() {
 
 }  // namespace
 
+/// Peer-memory exchange state of one rank (bfs_p2p.cuh): its own window, the peers' mappings.
+struct p2p_state_t {
+  p2p_window_t w;
+  void* own = nullptr;
+  size_t own_bytes = 0;
+  void* opened[kMaxPeers] = {};  // cudaIpcOpenMemHandle mappings to close
+  bool attached = false;
+  unsigned epoch = 0;
+  int seq = 0;
+  p2p_feedback_t* h_fb = nullptr;
+  void release() {
+    for (auto& o : opened)
+      if (o) {
+        cudaIpcCloseMemHandle(o);
+        o = nullptr;
+      }
+    if (own)
+      cudaFree(own);
+    own = nullptr;
+    if (h_fb)
+      cudaFreeHost(h_fb);
+    h_fb = nullptr;
+    attached = false;
+  }
+};
+
 struct b2g_graph {
   int n_vertices = 0;
   int n_edges = 0;
@@ -81,6 +109,7 @@ struct b2g_graph {
   part_bfs_state_t part;
   part_pr_state_t ppr;
   part_sssp_state_t psssp;
+  p2p_state_t p2p;
   dbuf_t<unsigned long long> part_deg;
   ctrl_t* part_ctrl = nullptr;
   int part_level_dir = 0;
@@ -89,6 +118,7 @@ struct b2g_graph {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   ~b2g_graph() {
+    p2p.release();
     if (ev0)
       cudaEventDestroy(ev0);
     if (ev1)
@@ -998,7 +1028,7 @@ int b2g_part_bfs_bottomup(b2g_graph_t* g, int level, const unsigned* frontier_al
     // padding words of the next map (beyond local_words) must stay clear for the all-gather
     B2G_CHECK(cudaMemsetAsync(S.nbm.ptr, 0, sizeof(unsigned) * S.words_per_rank(), st));
     part_bottom_up_kernel<256, 8><<<device_info_t::get().sm_count * 8, 256, 0, st>>>(
-        g->pt, g->t_view, S.words_per_rank(), S.visited.ptr, frontier_all, S.nbm.ptr, S.dist.ptr,
+        g->pt, g->t_view, S.words_per_rank(), S.visited.ptr, frontier_all, local_word_sink_t{S.nbm.ptr}, S.dist.ptr,
         level + 1, c, S.counts.ptr + 2);
     g->part_ctrl = c;
     part_feedback_kernel<<<1, 1, 0, st>>>(S.counts.ptr + 2, c, S.send_count.ptr, S.overflow.ptr, 0,
@@ -1143,7 +1173,7 @@ int b2g_part_bfs_bottomup_async(b2g_graph_t* g, int level, const unsigned* front
     B2G_CHECK(cudaMemsetAsync(S.counts.ptr + 2, 0, sizeof(int), st));
     B2G_CHECK(cudaMemsetAsync(S.nbm.ptr, 0, sizeof(unsigned) * S.words_per_rank(), st));
     part_bottom_up_kernel<256, 8><<<device_info_t::get().sm_count * 8, 256, 0, st>>>(
-        g->pt, g->t_view, S.words_per_rank(), S.visited.ptr, frontier_all, S.nbm.ptr, S.dist.ptr,
+        g->pt, g->t_view, S.words_per_rank(), S.visited.ptr, frontier_all, local_word_sink_t{S.nbm.ptr}, S.dist.ptr,
         level + 1, c, S.counts.ptr + 2);
     g->part_ctrl = c;
     g->ws.launches += 1;
@@ -1416,6 +1446,258 @@ int b2g_part_sssp_distances(b2g_graph_t* g, float* distances, int loc) {
                               loc == B2G_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
                               g->ws.stream));
     B2G_CHECK(cudaStreamSynchronize(g->ws.stream));
+    return 0;
+  });
+}
+
+// ---- peer-memory (NVLink) exchange: bfs_p2p.cuh ----------------------------------------------------
+int b2g_part_p2p_window_create(b2g_graph_t* g, void** window, unsigned long long* bytes,
+                               unsigned char* ipc_handle) {
+  if (!g || !g->partitioned)
+    return fail(B2G_ERR_INVALID, "b2g_part_p2p_window_create: not a partitioned graph");
+  if (g->pt.nparts > kMaxPeers)
+    return fail(B2G_ERR_INVALID, "b2g_part_p2p_window_create: at most 16 ranks");
+  return guarded([&] {
+    auto& P = g->p2p;
+    if (!P.own) {  // one window per graph handle, kept until the handle is destroyed
+      P.w = p2p_window_t{};
+      P.w.nparts = g->pt.nparts;
+      P.w.me = g->pt.part;
+      P.w.words = (g->pt.rows_of(0) + 31) / 32;
+      // a global id is forwarded at most once per rank, so a row never holds more than the owner's rows
+      P.w.cap = g->pt.rows_of(0) + 64;
+      P.own_bytes = P.w.bytes();
+      B2G_CHECK(cudaMalloc(&P.own, P.own_bytes));
+      B2G_CHECK(cudaMemset(P.own, 0, P.own_bytes));
+      B2G_CHECK(cudaMallocHost(&P.h_fb, sizeof(p2p_feedback_t)));
+      memset(P.h_fb, 0, sizeof(p2p_feedback_t));
+      B2G_CHECK(cudaDeviceSynchronize());
+    }
+    if (ipc_handle) {
+      cudaIpcMemHandle_t h;
+      B2G_CHECK(cudaIpcGetMemHandle(&h, P.own));
+      static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+      memcpy(ipc_handle, &h, 64);
+    }
+    if (window)
+      *window = P.own;
+    if (bytes)
+      *bytes = P.own_bytes;
+    return 0;
+  });
+}
+
+int b2g_part_p2p_attach(b2g_graph_t* g, const unsigned char* ipc_handles, void* const* windows) {
+  if (!g || !g->partitioned || !g->p2p.own || (!ipc_handles && !windows))
+    return fail(B2G_ERR_INVALID, "b2g_part_p2p_attach: create the window first, pass handles or pointers");
+  return guarded([&] {
+    auto& P = g->p2p;
+    if (P.attached)  // idempotent: the mappings (and the epoch the ranks share) stay
+      return 0;
+    for (int r = 0; r < P.w.nparts; ++r) {
+      if (r == P.w.me) {
+        P.w.base[r] = static_cast<char*>(P.own);
+      } else if (windows) {
+        P.w.base[r] = static_cast<char*>(windows[r]);
+      } else {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handles + 64 * static_cast<size_t>(r), 64);
+        void* p = nullptr;
+        B2G_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        P.opened[r] = p;
+        P.w.base[r] = static_cast<char*>(p);
+      }
+    }
+    P.attached = true;
+    return 0;
+  });
+}
+
+int b2g_part_p2p_detach(b2g_graph_t* g) {
+  if (!g)
+    return fail(B2G_ERR_INVALID, "null graph");
+  return guarded([&] {
+    auto& P = g->p2p;
+    B2G_CHECK(cudaStreamSynchronize(g->ws.stream));
+    for (auto& o : P.opened)
+      if (o) {
+        B2G_CHECK(cudaIpcCloseMemHandle(o));
+        o = nullptr;
+      }
+    P.attached = false;
+    return 0;
+  });
+}
+
+int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2g_options_t* opt,
+                     b2g_stats_t* stats) {
+  if (!g || !g->partitioned || !g->p2p.attached || source < 0 || source >= g->pt.n_global)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_p2p: attach the peer windows first / bad source");
+  return guarded([&] {
+    b2g_options_t o = resolved(opt);
+    cudaStream_t st = g->pick_stream(&o);
+    auto& S = g->part;
+    auto& P = g->p2p;
+    const p2p_window_t w = P.w;
+    const int np = w.nparts;
+    const int sms = device_info_t::get().sm_count;
+    const bool can_pull = g->symmetric && o.advance_direction != B2G_DIR_FORWARD;
+    const double alpha = o.do_alpha > 0 ? o.do_alpha : 14.0;
+    const double beta = o.do_beta > 0 ? o.do_beta : 24.0;
+    static const bool fused_sink = std::getenv("B2G_P2P_FUSED_SINK") != nullptr;
+    static const bool trace = std::getenv("B2G_TRACE") != nullptr;
+    const unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+
+    // ---- reset (the part of b2g_part_bfs_begin that matters here; no send buffer) ----------------
+    S.ensure(g->pt, 1);
+    g->part_deg.ensure(2);
+    const int sent_words = (g->pt.n_global + 31) / 32;
+    const unsigned* premark = nullptr;
+    if (can_pull) {
+      build_transpose(g);
+      if (S.unreachable_for != g->t_view.row_offsets) {
+        S.unreachable.ensure(static_cast<size_t>(S.words_per_rank()) + 4);
+        bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(g->t_view.row_offsets, g->pt.n_local,
+                                                            S.unreachable.ptr);
+        S.unreachable_for = g->t_view.row_offsets;
+      }
+      premark = S.unreachable.ptr;
+    }
+    const int launches0 = g->ws.launches;
+    B2G_CHECK(cudaEventRecord(g->ev0, st));
+    part_reset_kernel<<<sms * 8, 256, 0, st>>>(g->pt, source, S.dist.ptr, S.visited.ptr, S.sent.ptr,
+                                                sent_words, S.q[0].ptr, S.counts.ptr, premark);
+    part_seed_kernel<<<1, 1, 0, st>>>(g->pt, source, S.dist.ptr, S.visited.ptr);
+    B2G_CHECK(cudaMemsetAsync(S.overflow.ptr, 0, sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(g->part_deg.ptr, 0, 16, st));
+    g->ws.launches += 2;
+    P.h_fb->timed_out = 0;
+
+    int cur = 0, level = 0, parity = 0;  // parity: which `front` buffer holds the current frontier
+    bool is_bitmap = false, bottom_up = false;
+    long long n_f = 1, m_f = 0, explored = 0;
+    unsigned long long edges_total = 0, verts_total = 0;
+    if (stats)
+      memset(stats, 0, sizeof *stats);
+    const auto t0 = std::chrono::steady_clock::now();
+    auto sync = [&](bool with_stats, const int* send_count, const int* count_ptr, const ctrl_t* c) {
+      ++P.epoch;
+      if (with_stats)
+        p2p_sync_kernel<true><<<1, 32, 0, st>>>(w, P.epoch, send_count, count_ptr, c, g->part_deg.ptr,
+                                                 S.overflow.ptr, P.h_fb, ++P.seq, timeout_ns);
+      else
+        p2p_sync_kernel<false><<<1, 32, 0, st>>>(w, P.epoch, send_count, nullptr, nullptr, nullptr,
+                                                  nullptr, P.h_fb, 0, timeout_ns);
+      g->ws.launches += 1;
+    };
+    while (n_f > 0) {
+      bool go_up = false;
+      if (can_pull && level > 0) {
+        if (o.advance_direction == B2G_DIR_BACKWARD)
+          go_up = true;
+        else if (!bottom_up)
+          go_up = static_cast<double>(m_f) > static_cast<double>(total_edges - explored) / alpha;
+        else
+          go_up = !(static_cast<double>(n_f) < static_cast<double>(g->pt.n_global) / beta);
+      }
+      if (level > 0)
+        explored += m_f;
+      ctrl_t* c = nullptr;
+      const int* count_ptr = nullptr;
+      unsigned* my_front = w.front(w.me, parity) + static_cast<size_t>(w.me) * w.words;
+      if (go_up) {
+        if (!is_bitmap) {  // queue -> bitmap in my segment, pushed to every peer, barrier
+          B2G_CHECK(cudaMemsetAsync(my_front, 0, sizeof(unsigned) * w.words, st));
+          part_queue_to_bitmap_kernel<<<sms * 4, 256, 0, st>>>(S.q[cur].ptr, S.counts.ptr + cur, my_front);
+          if (np > 1) {
+            p2p_push_segment_kernel<<<dim3(64, np), 256, 0, st>>>(w, parity);
+            sync(false, nullptr, nullptr, nullptr);
+          }
+          g->ws.launches += 2;
+          is_bitmap = true;
+        }
+        c = g->ws.next_ctrl();
+        B2G_CHECK(cudaMemsetAsync(S.counts.ptr + 2, 0, sizeof(int), st));
+        const unsigned* all = w.front(w.me, parity);
+        if (fused_sink || np == 1) {
+          part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
+              g->pt, g->t_view, w.words, S.visited.ptr, all, peer_word_sink_t{w, parity ^ 1}, S.dist.ptr,
+              level + 1, c, S.counts.ptr + 2);
+        } else {
+          unsigned* nxt_seg = w.front(w.me, parity ^ 1) + static_cast<size_t>(w.me) * w.words;
+          part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
+              g->pt, g->t_view, w.words, S.visited.ptr, all, local_word_sink_t{nxt_seg}, S.dist.ptr,
+              level + 1, c, S.counts.ptr + 2);
+          p2p_push_segment_kernel<<<dim3(64, np), 256, 0, st>>>(w, parity ^ 1);
+          g->ws.launches += 1;
+        }
+        g->ws.launches += 1;
+        parity ^= 1;
+        count_ptr = S.counts.ptr + 2;
+      } else {
+        if (is_bitmap) {  // bitmap -> queue (my segment of the current frontier map)
+          B2G_CHECK(cudaMemsetAsync(S.counts.ptr + cur, 0, sizeof(int), st));
+          bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(my_front, S.local_words(), S.q[cur].ptr,
+                                                          S.counts.ptr + cur);
+          g->ws.launches += 1;
+          is_bitmap = false;
+        }
+        const int nxt = cur ^ 1;
+        B2G_CHECK(cudaMemsetAsync(S.counts.ptr + nxt, 0, sizeof(int), st));
+        B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
+        p2p_claim_op op{g->pt, w, S.visited.ptr, S.sent.ptr, S.dist.ptr, level + 1, S.send_count.ptr,
+                        S.overflow.ptr};
+        advance_launch_t lcfg = to_launch(o);
+        if (level == 0)
+          lcfg.lb = lb_t::block_mapped;  // one row of unknown length
+        launch_advance<advance_output_t::vertices, true, false>(
+            g->ws, g->view, S.q[cur].ptr, S.counts.ptr + cur, g->pt.n_local, S.q[nxt].ptr,
+            S.counts.ptr + nxt, g->pt.n_local, op, lcfg, &c);
+        if (np > 1) {
+          sync(false, S.send_count.ptr, nullptr, nullptr);
+          part_claim_packed_kernel<<<dim3(64, np), 256, 0, st>>>(
+              g->pt, w.inbox(w.me, 0), static_cast<int>(w.inbox_row_ints()) - 1, S.visited.ptr, S.dist.ptr,
+              level + 1, g->view.row_offsets, S.q[nxt].ptr, S.counts.ptr + nxt, g->part_deg.ptr,
+              S.overflow.ptr);
+          g->ws.launches += 1;
+        }
+        cur = nxt;
+        count_ptr = S.counts.ptr + cur;
+      }
+      sync(true, nullptr, count_ptr, c);
+      wait_for_sequence(&P.h_fb->seq, P.seq, st);
+      if (P.h_fb->timed_out)
+        throw std::runtime_error("b2g_part_bfs_p2p: a peer did not reach the barrier (time-out)");
+      if (P.h_fb->overflow)
+        throw std::runtime_error("b2g_part_bfs_p2p: frontier / inbox overflow");
+      if (trace && w.me == 0)
+        std::fprintf(stderr, "[b2g-p2p] level %d %s n_f=%lld m_f=%lld edges=%lld t=%.1f us\n", level,
+                     go_up ? "up" : "down", n_f, m_f, P.h_fb->edges,
+                     std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+      if (stats && level < 64) {
+        stats->level_direction[level] = go_up ? 1 : 0;
+        stats->level_frontier[level] = static_cast<int>(n_f);
+        stats->level_edges[level] = static_cast<unsigned long long>(P.h_fb->edges);
+      }
+      edges_total += static_cast<unsigned long long>(P.h_fb->edges);
+      verts_total += static_cast<unsigned long long>(n_f);
+      if (level == 0)
+        explored += P.h_fb->edges;
+      n_f = P.h_fb->count;
+      m_f = P.h_fb->deg_sum;
+      bottom_up = go_up;
+      ++level;
+    }
+    B2G_CHECK(cudaEventRecord(g->ev1, st));
+    B2G_CHECK(cudaStreamSynchronize(st));
+    S.cur = cur;
+    S.frontier_is_bitmap = false;
+    if (stats) {
+      fill_stats_common(g, stats, launches0);
+      stats->iterations = stats->n_levels = level;
+      stats->edges_touched = edges_total;
+      stats->vertices_touched = verts_total;
+    }
     return 0;
   });
 }

@@ -65,6 +65,10 @@ def _bind():
     L.b2g_part_sssp_apply_packed_async.argtypes = [vp, ip, vp, ip]
     L.b2g_part_sssp_end_iteration_async.argtypes = [vp, vp]
     L.b2g_part_sssp_distances.argtypes = [vp, vp, ip]
+    L.b2g_part_p2p_window_create.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_ulonglong), vp]
+    L.b2g_part_p2p_attach.argtypes = [vp, vp, vp]
+    L.b2g_part_p2p_detach.argtypes = [vp]
+    L.b2g_part_bfs_p2p.argtypes = [vp, ip, C.c_longlong, C.POINTER(_Options), C.POINTER(_Stats)]
     L._mg_bound = True
     return L
 
@@ -262,6 +266,40 @@ class CudaRankEngine:
     def end_level_async(self, stats):
         _check(self.L.b2g_part_bfs_end_level_async(self.G._h, stats.data_ptr()), "b2g_part_bfs_end_level_async")
 
+    # ---- peer-memory (NVLink) exchange: the kernels do the communication (bfs_p2p.cuh) ---------------
+    def p2p_window(self):
+        """Allocate this rank's window; returns (device pointer, bytes, 64-byte CUDA IPC handle)."""
+        ptr, nbytes = C.c_void_p(), C.c_ulonglong()
+        handle = (C.c_ubyte * 64)()
+        _check(self.L.b2g_part_p2p_window_create(self.G._h, C.byref(ptr), C.byref(nbytes), handle),
+               "b2g_part_p2p_window_create")
+        return ptr.value, int(nbytes.value), bytes(handle)
+
+    def p2p_attach(self, handles: Optional[Sequence[bytes]] = None, windows: Optional[Sequence[int]] = None):
+        if windows is not None:
+            arr = (C.c_void_p * self.nparts)(*[C.c_void_p(int(x)) for x in windows])
+            _check(self.L.b2g_part_p2p_attach(self.G._h, None, arr), "b2g_part_p2p_attach")
+        else:
+            blob = b"".join(handles)
+            assert len(blob) == 64 * self.nparts
+            _check(self.L.b2g_part_p2p_attach(self.G._h, blob, None), "b2g_part_p2p_attach")
+
+    def bfs_p2p(self, source: int, total_edges: int):
+        """COLLECTIVE over the ranks.  Returns the run's stats_t (global level statistics)."""
+        st = _Stats()
+        _check(self.L.b2g_part_bfs_p2p(self.G._h, int(source), int(total_edges), C.byref(self.opt), C.byref(st)),
+               "b2g_part_bfs_p2p")
+        n = min(st.n_levels, 64)
+        out = part_bfs_stats_t()
+        out.levels = st.n_levels
+        out.level_direction = list(st.level_direction[:n])
+        out.level_frontier = list(st.level_frontier[:n])
+        out.level_edges = list(st.level_edges[:n])
+        out.edges_touched = int(st.edges_touched)
+        out.elapsed_ms = float(st.elapsed_ms)
+        out.kernel_launches = int(st.kernel_launches)
+        return out
+
     # ---- partitioned SSSP steps ---------------------------------------------------------------------
     def sssp_begin(self, source: int, send_capacity: int):
         _check(self.L.b2g_part_sssp_begin(self.G._h, int(source), int(send_capacity)), "b2g_part_sssp_begin")
@@ -395,6 +433,8 @@ class part_bfs_stats_t:
     level_edges: List[int] = field(default_factory=list)          # global, inspected
     edges_touched: int = 0
     exchanged_ids: int = 0                                        # ids this rank sent
+    elapsed_ms: float = 0.0                                       # p2p path: CUDA events around the loop
+    kernel_launches: int = 0
 
 
 def _decide(direction: int, level: int, bottom_up: bool, n_f: int, m_f: int, explored: int, n_global: int,
@@ -537,6 +577,61 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
         return bfs_rank(engine, comm, source, total_edges, direction, alpha, beta)
     st.levels = level
     return engine.distances(), st
+
+
+def p2p_connect(engine, comm) -> None:
+    """One process per GPU: allocate the rank's window, exchange the CUDA IPC handles over the
+    communicator (the only use of torch.distributed on this path) and map every peer's window."""
+    _, _, handle = engine.p2p_window()
+    handles = [None] * comm.world
+    comm.dist.all_gather_object(handles, handle, group=comm.group)
+    engine.p2p_attach(handles=handles)
+    comm.dist.barrier(group=comm.group)
+
+
+def p2p_disconnect(engine, comm) -> None:
+    """Unmap the peers' windows on every rank before any graph handle is destroyed."""
+    _check(engine.L.b2g_part_p2p_detach(engine.G._h), "b2g_part_p2p_detach")
+    comm.dist.barrier(group=comm.group)
+
+
+def p2p_connect_simulated(engines: Sequence) -> None:
+    """Several ranks inside one process (tests on one GPU): peers are plain device pointers."""
+    ptrs = [e.p2p_window()[0] for e in engines]
+    for e in engines:
+        e.p2p_attach(windows=ptrs)
+
+
+def bfs_rank_p2p(engine, source: int, total_edges: int, direction: int = advance_direction_t.optimized,
+                 alpha: float = 14.0, beta: float = 24.0):
+    """This rank's part of the partitioned BFS with the exchange done by the kernels over peer memory
+    (collective: every rank calls it).  Returns (owned distances, stats)."""
+    engine.opt.advance_direction = direction
+    engine.opt.do_alpha, engine.opt.do_beta = alpha, beta
+    st = engine.bfs_p2p(source, total_edges)
+    return engine.distances(), st
+
+
+def bfs_threads_p2p(engines: Sequence, source: int, total_edges: int,
+                    direction: int = advance_direction_t.optimized):
+    """Simulated ranks on one GPU: one host thread per rank (each call blocks in its level loop while
+    the barrier kernels of the ranks wait for each other on separate streams)."""
+    import threading
+    out, err = [None] * len(engines), []
+
+    def work(i, e):
+        try:
+            out[i] = bfs_rank_p2p(e, source, total_edges, direction)
+        except BaseException as ex:   # noqa: BLE001 - surfaced below
+            err.append(ex)
+    ts = [threading.Thread(target=work, args=(i, e)) for i, e in enumerate(engines)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if err:
+        raise err[0]
+    return [o[0] for o in out], out[0][1]
 
 
 def sssp_rank(engine, comm, source: int, cap_s: int = 0):

@@ -163,17 +163,27 @@ static __global__ void part_queue_to_bitmap_kernel(const int* __restrict__ q,
   }
 }
 
+/// Where the bottom-up sweep puts the words of the next frontier: the local bitmap (NCCL variant; the
+/// peer-memory variant in bfs_p2p.cuh stores them into every rank's copy instead).
+struct local_word_sink_t {
+  unsigned* next;
+  __device__ __forceinline__ void zero(int wi) const { next[wi] = 0; }  // lanes hold different words
+  __device__ __forceinline__ void word(int wi, unsigned v) const {      // warp-uniform word
+    if (lane_id() == 0)
+      next[wi] = v;
+  }
+};
+
 /**
  * @brief Bottom-up sweep over the rows this rank owns.  `frontier_all` is the all-gathered frontier
  * bitmap, laid out rank-major: words [r * words_per_rank, (r+1) * words_per_rank) hold rank r's
  * local rows.  Same structure as bfs_bottom_up_kernel (one warp per visited word).
  */
-template <int kThreads, int kSerial>
+template <int kThreads, int kSerial, typename Sink>
 __global__ void __launch_bounds__(kThreads)
 part_bottom_up_kernel(partition_t pt, csr_view_t in, int words_per_rank,
                       unsigned* __restrict__ visited, const unsigned* __restrict__ frontier_all,
-                      unsigned* __restrict__ next, int* dist, int next_level, ctrl_t* ctrl,
-                      int* next_count) {
+                      Sink sink, int* dist, int next_level, ctrl_t* ctrl, int* next_count) {
   const int lane = lane_id();
   const int words = (pt.n_local + 31) / 32;
   const int warps = (gridDim.x * kThreads) >> 5;
@@ -192,7 +202,7 @@ part_bottom_up_kernel(partition_t pt, csr_view_t in, int words_per_rank,
     const int my_wi = w0 + lane;
     const unsigned my_vis = my_wi < words ? visited[my_wi] : 0xffffffffu;
     if (my_wi < words && my_vis == 0xffffffffu)
-      next[my_wi] = 0;
+      sink.zero(my_wi);
     unsigned todo = __ballot_sync(kFull, my_vis != 0xffffffffu);
     while (todo) {
     const int src_lane = __ffs(todo) - 1;
@@ -245,11 +255,9 @@ part_bottom_up_kernel(partition_t pt, csr_view_t in, int words_per_rank,
       dist[v] = next_level;
       found_deg += static_cast<unsigned>(deg);
     }
-    if (lane == 0) {
-      next[wi] = fm;
-      if (fm)
-        visited[wi] = vis | fm;
-    }
+    sink.word(wi, fm);  // warp-uniform arguments, every lane calls
+    if (lane == 0 && fm)
+      visited[wi] = vis | fm;
     found_cnt += found ? 1 : 0;
     }
   }

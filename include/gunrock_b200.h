@@ -209,6 +209,28 @@ int b2g_part_bfs_frontier_bitmap_async(b2g_graph_t* g, unsigned* out);
 int b2g_part_bfs_bottomup_async(b2g_graph_t* g, int level, const unsigned* frontier_all);
 /* stats (device, int64[4]) = {next frontier size, its out-degree sum, edges inspected, overflow}. */
 int b2g_part_bfs_end_level_async(b2g_graph_t* g, long long* stats);
+
+/* ---- peer-memory exchange over NVLink (include/gunrock/b200/bfs_p2p.cuh) ---------------------------
+ * The kernels themselves write forwarded ids / next-frontier words / statistics into windows of device
+ * memory that every rank maps; no NCCL call and no host code between the phases of a level.  Stands
+ * where gcuda::multi_context_t (cuda/context.hxx:146-216) would drive several devices.
+ *  1. b2g_part_p2p_window_create: allocate this rank's window; returns its device pointer, size and
+ *     (ipc_handle != NULL) the 64-byte CUDA IPC handle to hand to the other processes;
+ *  2. b2g_part_p2p_attach: ipc_handles = nparts x 64 bytes gathered from all ranks (processes), or
+ *     windows = nparts device pointers (ranks simulated inside one process);
+ *  3. b2g_part_bfs_p2p: COLLECTIVE -- every rank calls it with the same source / options; returns when
+ *     the traversal is complete (owned distances: b2g_part_bfs_distances).  total_edges = global
+ *     directed edge count (direction heuristic).  Bottom-up levels need a symmetric graph.
+ * Both calls are idempotent per graph handle (one window, one set of mappings, one shared epoch).
+ * At most 16 ranks.  A peer that never arrives raises an error after 20 s instead of hanging. */
+int b2g_part_p2p_window_create(b2g_graph_t* g, void** window, unsigned long long* bytes,
+                               unsigned char* ipc_handle);
+int b2g_part_p2p_attach(b2g_graph_t* g, const unsigned char* ipc_handles, void* const* windows);
+/* Unmap the peers' windows (every rank calls it, then a barrier, before any rank destroys its graph:
+ * a window must not be freed while another process still maps it).  The own window stays. */
+int b2g_part_p2p_detach(b2g_graph_t* g);
+int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2g_options_t* opt,
+                     b2g_stats_t* stats);
 /* ---- multi-GPU PageRank (pull): the rank owns the DESTINATION vertices v % nparts == part and their
  * in-edges (a partitioned graph whose rows are in-edge lists: any symmetric partitioned graph, or
  * one created with by_destination != 0).  Per iteration the host side all-gathers c = plast*iweights,

@@ -36,6 +36,16 @@ def main():
                     t = torch.tensor([int(ok)], device="cuda")
                     dist.all_reduce(t, op=dist.ReduceOp.MIN)
                     results[f"{name}/{direction}/{lb}/{variant}"] = [int(t.item()), st.level_direction]
+                # exchange done by the kernels over NVLink peer memory (CUDA IPC windows), twice per window
+                mg.p2p_connect(eng, mg.TorchDistComm())
+                for rep in range(2):
+                    d, st = mg.bfs_rank_p2p(eng, src, len(ci), direction)
+                    ok = bool(np.array_equal(d.cpu().numpy(), exp[rank::world]))
+                    t = torch.tensor([int(ok)], device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    results[f"{name}/{direction}/{lb}/p2p{rep}"] = [int(t.item()), st.level_direction]
+                dist.barrier()
+        mg.p2p_disconnect(eng, mg.TorchDistComm())
         G.close()
     # partitioned PageRank over NCCL (directed graph, in-edge partition)
     dro, dci = oracle.rmat_csr(13, 8, 99, mirror=False)

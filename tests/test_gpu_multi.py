@@ -48,6 +48,35 @@ def test_simulated_ranks_on_one_gpu(gb, P):
             g.close()
 
 
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 8])
+def test_peer_memory_exchange_simulated_ranks(gb, P):
+    """bfs_p2p.cuh: the kernels write forwarded ids / frontier words / statistics straight into the
+    peers' windows and synchronise with epoch flags -- here the peers are P handles on one GPU (one
+    host thread and one stream per rank), the kernels and the protocol are the multi-GPU ones."""
+    from gunrock_b200 import multi_gpu as mg
+    for scale, ef, seed in ((11, 16, 5), (14, 8, 0x5EED22)):
+        ro, ci = oracle.rmat_csr(scale, ef, seed, mirror=True)
+        deg = np.diff(ro)
+        graphs = [mg.PartitionedGraph.from_global_csr(ro, ci, P, r) for r in range(P)]
+        for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
+            engines = [mg.CudaRankEngine(g, gb.options_t(advance_load_balance=lb, hub_threshold=256))
+                       for g in graphs]
+            mg.p2p_connect_simulated(engines)
+            for src in (int(deg.argmax()), int(np.flatnonzero(deg > 0)[-1])):
+                exp = oracle.bfs(ro, ci, src)
+                for direction in (gb.advance_direction_t.forward, gb.advance_direction_t.optimized,
+                                  gb.advance_direction_t.backward):
+                    dists, st = mg.bfs_threads_p2p(engines, src, len(ci), direction)   # reuses the windows
+                    got = mg.gather_distances([d.cpu().numpy() for d in dists], len(ro) - 1)
+                    assert np.array_equal(got, exp), (P, scale, src, direction, lb)
+                    if direction == gb.advance_direction_t.forward:
+                        assert st.edges_touched == int(deg[exp < 2**31 - 1].sum())
+                    if direction == gb.advance_direction_t.optimized and src == int(deg.argmax()):
+                        assert 1 in st.level_direction          # the pull path (peer sweep) really ran
+        for g in graphs:
+            g.close()
+
+
 def test_partitioned_rmat_generator_matches_global(gb):
     from gunrock_b200 import multi_gpu as mg
     scale, ef, seed, P = 13, 8, 99, 4
@@ -72,7 +101,7 @@ def test_nccl_two_or_more_gpus(gb):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("MG_RESULT ")][-1]
     res = json.loads(line[len("MG_RESULT "):])
-    assert len(res) == 26 and all(v[0] == 1 for v in res.values()), res
+    assert len(res) == 42 and all(v[0] == 1 for v in res.values()), res
 
 
 def test_async_driver_single_rank(gb):
