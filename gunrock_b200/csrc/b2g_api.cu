@@ -1471,6 +1471,15 @@ int b2g_part_p2p_window_create(b2g_graph_t* g, void** window, unsigned long long
       B2G_CHECK(cudaMemset(P.own, 0, P.own_bytes));
       B2G_CHECK(cudaMallocHost(&P.h_fb, sizeof(p2p_feedback_t)));
       memset(P.h_fb, 0, sizeof(p2p_feedback_t));
+      // everything the traversal allocates, now: the run itself must not call cudaMalloc / cudaFree
+      // (device-wide synchronisation while a peer's barrier kernel is spinning)
+      g->part.ensure(g->pt, 1);
+      g->part_deg.ensure(2);
+      reserve_advance_workspace(g->ws, g->view, g->pt.n_local);
+      if (g->symmetric) {
+        build_transpose(g);
+        g->part.unreachable.ensure(static_cast<size_t>(g->part.words_per_rank()) + 4);
+      }
       B2G_CHECK(cudaDeviceSynchronize());
     }
     if (ipc_handle) {
@@ -1546,7 +1555,9 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
     const double beta = o.do_beta > 0 ? o.do_beta : 24.0;
     static const bool fused_sink = std::getenv("B2G_P2P_FUSED_SINK") != nullptr;
     static const bool trace = std::getenv("B2G_TRACE") != nullptr;
-    const unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    static const char* timeout_env = std::getenv("B2G_P2P_TIMEOUT_MS");
+    const unsigned long long timeout_ns =
+        (timeout_env ? std::strtoull(timeout_env, nullptr, 10) : 20000ull) * 1000ull * 1000ull;
 
     // ---- reset (the part of b2g_part_bfs_begin that matters here; no send buffer) ----------------
     S.ensure(g->pt, 1);
@@ -1667,12 +1678,15 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
       sync(true, nullptr, count_ptr, c);
       wait_for_sequence(&P.h_fb->seq, P.seq, st);
       if (P.h_fb->timed_out)
-        throw std::runtime_error("b2g_part_bfs_p2p: a peer did not reach the barrier (time-out)");
+        throw std::runtime_error("b2g_part_bfs_p2p: rank " + std::to_string(w.me) + " level " +
+                                 std::to_string(level) + ": peer " + std::to_string(P.h_fb->late_peer) +
+                                 " did not reach barrier epoch " + std::to_string(P.h_fb->late_epoch) +
+                                 " (published " + std::to_string(P.h_fb->late_seen) + ", time-out)");
       if (P.h_fb->overflow)
         throw std::runtime_error("b2g_part_bfs_p2p: frontier / inbox overflow");
-      if (trace && w.me == 0)
-        std::fprintf(stderr, "[b2g-p2p] level %d %s n_f=%lld m_f=%lld edges=%lld t=%.1f us\n", level,
-                     go_up ? "up" : "down", n_f, m_f, P.h_fb->edges,
+      if (trace)
+        std::fprintf(stderr, "[b2g-p2p] rank %d epoch %u level %d %s n_f=%lld m_f=%lld edges=%lld t=%.1f us\n",
+                     w.me, P.epoch, level, go_up ? "up" : "down", n_f, m_f, P.h_fb->edges,
                      std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
       if (stats && level < 64) {
         stats->level_direction[level] = go_up ? 1 : 0;

@@ -26,7 +26,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from . import (DEVICE, HOST, GunrockB200Error, _check, _Options, advance_direction_t, lib,
+from . import (DEVICE, HOST, GunrockB200Error, _check, _Options, _Stats, advance_direction_t, lib,
                options_t)
 
 
@@ -596,7 +596,13 @@ def p2p_disconnect(engine, comm) -> None:
 
 
 def p2p_connect_simulated(engines: Sequence) -> None:
-    """Several ranks inside one process (tests on one GPU): peers are plain device pointers."""
+    """Several ranks inside one process (tests on one GPU): peers are plain device pointers.
+    Their barrier kernels spin while the other ranks' kernels must be able to START; CUDA's lazy module
+    loading synchronises the context at a kernel's first launch and dead-locks against that, so this
+    mode needs CUDA_MODULE_LOADING=EAGER (one process per GPU has no such constraint)."""
+    if len(engines) > 1 and os.environ.get("CUDA_MODULE_LOADING", "").upper() != "EAGER":
+        raise GunrockB200Error("simulated p2p ranks in one process need CUDA_MODULE_LOADING=EAGER "
+                               "set before CUDA is initialised")
     ptrs = [e.p2p_window()[0] for e in engines]
     for e in engines:
         e.p2p_attach(windows=ptrs)

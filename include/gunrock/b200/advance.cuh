@@ -893,6 +893,20 @@ struct advance_launch_t {
   double avg_degree = 0.0;
 };
 
+/// Allocate, once, everything launch_advance may need for frontiers of up to `n_upper_bound` rows of
+/// `g`, so that a later run performs no cudaMalloc / cudaFree (both synchronise the device, which a
+/// run that overlaps with other streams' spinning barrier kernels must not do -- bfs_p2p.cuh).
+inline void reserve_advance_workspace(workspace_t& ws, const csr_view_t& g, int n_upper_bound) {
+  ws.scanned.ensure(2 * static_cast<size_t>(n_upper_bound) + 4);
+  ws.tile_rows.ensure((static_cast<size_t>(1) << 31) / 2048 + 4);
+  ws.hubs.ensure(static_cast<size_t>(g.n_edges / 256 + 1024));
+  const int max_tiles = (n_upper_bound + 256 * 8 - 1) / (256 * 8) + 1;
+  const size_t had = ws.tile_state.cap;
+  ws.tile_state.ensure(max_tiles);
+  if (ws.tile_state.cap != had)
+    B2G_CHECK(cudaMemsetAsync(ws.tile_state.ptr, 0, ws.tile_state.cap * 8, ws.stream));
+}
+
 /// Degree scan of the frontier for merge_path (replaces helpers.hxx:41-111): scanned[0..n],
 /// scanned[n] = total, all written by the one look-back scan kernel.
 inline const int* frontier_degree_scan(workspace_t& ws,

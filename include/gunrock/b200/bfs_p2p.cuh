@@ -160,6 +160,9 @@ struct p2p_feedback_t {
   long long edges;     // edges inspected by the level (all ranks)
   int overflow;
   int timed_out;
+  int late_peer;            // diagnostics of a time-out: which peer, the epoch it had published,
+  unsigned late_seen;       // and the epoch that was awaited
+  unsigned late_epoch;
   volatile int seq;
 };
 
@@ -193,6 +196,9 @@ __global__ void p2p_sync_kernel(p2p_window_t w, unsigned epoch, const int* send_
     while (static_cast<int>(ld_acquire_sys(mine) - epoch) < 0) {
       if (global_timer_ns() - t0 > timeout_ns) {
         late = true;
+        fb->late_peer = lane;
+        fb->late_seen = ld_acquire_sys(mine);
+        fb->late_epoch = epoch;
         break;
       }
     }
