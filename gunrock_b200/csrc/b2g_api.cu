@@ -7,6 +7,7 @@
 // the timed path (the reference builds its CSR on the host, include/gunrock/formats/csr.hxx:81-140).
 #include <gunrock_b200.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cstring>
@@ -70,7 +71,11 @@ struct p2p_state_t {
   unsigned epoch = 0;
   int seq = 0;
   p2p_feedback_t* h_fb = nullptr;
+  p2p_tail_report_t* h_tail = nullptr;
   void release() {
+    if (h_tail)
+      cudaFreeHost(h_tail);
+    h_tail = nullptr;
     for (auto& o : opened)
       if (o) {
         cudaIpcCloseMemHandle(o);
@@ -1463,7 +1468,7 @@ int b2g_part_p2p_window_create(b2g_graph_t* g, void** window, unsigned long long
       P.w = p2p_window_t{};
       P.w.nparts = g->pt.nparts;
       P.w.me = g->pt.part;
-      P.w.words = (g->pt.rows_of(0) + 31) / 32;
+      P.w.words = (((g->pt.rows_of(0) + 31) / 32) + 3) & ~3;  // 16-byte aligned segments
       // a global id is forwarded at most once per rank, so a row never holds more than the owner's rows
       P.w.cap = g->pt.rows_of(0) + 64;
       P.own_bytes = P.w.bytes();
@@ -1471,6 +1476,8 @@ int b2g_part_p2p_window_create(b2g_graph_t* g, void** window, unsigned long long
       B2G_CHECK(cudaMemset(P.own, 0, P.own_bytes));
       B2G_CHECK(cudaMallocHost(&P.h_fb, sizeof(p2p_feedback_t)));
       memset(P.h_fb, 0, sizeof(p2p_feedback_t));
+      B2G_CHECK(cudaMallocHost(&P.h_tail, sizeof(p2p_tail_report_t)));
+      memset(P.h_tail, 0, sizeof(p2p_tail_report_t));
       // everything the traversal allocates, now: the run itself must not call cudaMalloc / cudaFree
       // (device-wide synchronisation while a peer's barrier kernel is spinning)
       g->part.ensure(g->pt, 1);
@@ -1584,6 +1591,20 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
     g->ws.launches += 2;
     P.h_fb->timed_out = 0;
 
+    static const bool use_tail = std::getenv("B2G_P2P_NO_TAIL") == nullptr;
+    const long long tail_budget = 1 << 16;  // global frontier out-degree below which the tail kernel runs
+    const int push_ctas = std::max(8, std::min(sms * 4 / np, (w.words / 4 + 255) / 256));
+    // B2G_TRACE: CUDA-event stamps between the phases of every level (device time of this rank)
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    auto mark = [&](const std::string& name) {
+      if (!trace)
+        return;
+      cudaEvent_t e;
+      B2G_CHECK(cudaEventCreate(&e));
+      B2G_CHECK(cudaEventRecord(e, st));
+      marks.emplace_back(name, e);
+    };
+    mark("begin");
     int cur = 0, level = 0, parity = 0;  // parity: which `front` buffer holds the current frontier
     bool is_bitmap = false, bottom_up = false;
     long long n_f = 1, m_f = 0, explored = 0;
@@ -1602,6 +1623,7 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
       g->ws.launches += 1;
     };
     while (n_f > 0) {
+      mark("L" + std::to_string(level) + ":");
       bool go_up = false;
       if (can_pull && level > 0) {
         if (o.advance_direction == B2G_DIR_BACKWARD)
@@ -1611,17 +1633,57 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
         else
           go_up = !(static_cast<double>(n_f) < static_cast<double>(g->pt.n_global) / beta);
       }
+      unsigned* my_front = w.front(w.me, parity) + static_cast<size_t>(w.me) * w.words;
+      // ---- tiny global frontier: the distributed tail kernel runs level after level on its own ------
+      if (!go_up && level > 0 && use_tail && m_f < tail_budget) {
+        if (is_bitmap) {
+          B2G_CHECK(cudaMemsetAsync(S.counts.ptr + cur, 0, sizeof(int), st));
+          bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(my_front, S.local_words(), S.q[cur].ptr,
+                                                          S.counts.ptr + cur);
+          g->ws.launches += 1;
+          is_bitmap = false;
+        }
+        P.h_tail->timed_out = 0;
+        p2p_tail_kernel<1024><<<1, 1024, 0, st>>>(
+            g->view, g->pt, w, P.epoch + 1, S.q[0].ptr, S.q[1].ptr, S.counts.ptr, cur, level, n_f, 16,
+            tail_budget, S.visited.ptr, S.sent.ptr, S.dist.ptr, S.overflow.ptr, P.h_tail, ++P.seq, timeout_ns);
+        g->ws.launches += 1;
+        mark("tail");
+        wait_for_sequence(&P.h_tail->seq, P.seq, st);
+        const p2p_tail_report_t& t = *P.h_tail;
+        P.epoch += 2u * static_cast<unsigned>(t.levels);
+        if (t.timed_out)
+          throw std::runtime_error("b2g_part_bfs_p2p: a peer did not reach a barrier of the tail kernel (time-out)");
+        for (int k = 0; k < t.levels; ++k) {
+          if (stats && level + k < 64) {
+            stats->level_direction[level + k] = 0;
+            stats->level_frontier[level + k] = static_cast<int>(t.frontier[k]);
+            stats->level_edges[level + k] = static_cast<unsigned long long>(t.edges[k]);
+          }
+          edges_total += static_cast<unsigned long long>(t.edges[k]);
+          verts_total += static_cast<unsigned long long>(t.frontier[k]);
+          explored += t.edges[k];
+        }
+        if (trace)
+          std::fprintf(stderr, "[b2g-p2p] rank %d epoch %u levels %d..%d in the tail kernel, n_f=%lld m_f=%lld\n",
+                       w.me, P.epoch, level, level + t.levels - 1, t.count, t.deg_sum);
+        level += t.levels;
+        cur = t.cur;
+        n_f = t.count;
+        m_f = t.deg_sum;
+        bottom_up = false;
+        continue;
+      }
       if (level > 0)
         explored += m_f;
       ctrl_t* c = nullptr;
       const int* count_ptr = nullptr;
-      unsigned* my_front = w.front(w.me, parity) + static_cast<size_t>(w.me) * w.words;
       if (go_up) {
         if (!is_bitmap) {  // queue -> bitmap in my segment, pushed to every peer, barrier
           B2G_CHECK(cudaMemsetAsync(my_front, 0, sizeof(unsigned) * w.words, st));
           part_queue_to_bitmap_kernel<<<sms * 4, 256, 0, st>>>(S.q[cur].ptr, S.counts.ptr + cur, my_front);
           if (np > 1) {
-            p2p_push_segment_kernel<<<dim3(64, np), 256, 0, st>>>(w, parity);
+            p2p_push_segment_kernel<<<dim3(push_ctas, np), 256, 0, st>>>(w, parity);
             sync(false, nullptr, nullptr, nullptr);
           }
           g->ws.launches += 2;
@@ -1639,9 +1701,11 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
           part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
               g->pt, g->t_view, w.words, S.visited.ptr, all, local_word_sink_t{nxt_seg}, S.dist.ptr,
               level + 1, c, S.counts.ptr + 2);
-          p2p_push_segment_kernel<<<dim3(64, np), 256, 0, st>>>(w, parity ^ 1);
+          mark("sweep");
+          p2p_push_segment_kernel<<<dim3(push_ctas, np), 256, 0, st>>>(w, parity ^ 1);
           g->ws.launches += 1;
         }
+        mark("push");
         g->ws.launches += 1;
         parity ^= 1;
         count_ptr = S.counts.ptr + 2;
@@ -1658,24 +1722,37 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
         B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
         p2p_claim_op op{g->pt, w, S.visited.ptr, S.sent.ptr, S.dist.ptr, level + 1, S.send_count.ptr,
                         S.overflow.ptr};
+        // same path selection as the single-GPU enactor (bfs.cuh), on this rank's share of the frontier
         advance_launch_t lcfg = to_launch(o);
-        if (level == 0)
+        const long long m_rank = m_f / np;
+        lcfg.avg_degree = (level > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
+        if (level == 0) {
           lcfg.lb = lb_t::block_mapped;  // one row of unknown length
+        } else if (m_rank < lcfg.small_frontier_edges) {
+          lcfg.lb = lb_t::block_mapped;  // one kernel: warp / thread bins only
+          lcfg.hub_threshold = 1 << 30;
+        } else if (lcfg.lb == lb_t::merge_path && m_rank < lcfg.mid_frontier_edges) {
+          lcfg.lb = lb_t::block_mapped;  // skip the scan + partition launches
+        }
         launch_advance<advance_output_t::vertices, true, false>(
             g->ws, g->view, S.q[cur].ptr, S.counts.ptr + cur, g->pt.n_local, S.q[nxt].ptr,
             S.counts.ptr + nxt, g->pt.n_local, op, lcfg, &c);
+        mark("advance");
         if (np > 1) {
           sync(false, S.send_count.ptr, nullptr, nullptr);
-          part_claim_packed_kernel<<<dim3(64, np), 256, 0, st>>>(
+          mark("barrier");
+          part_claim_packed_kernel<<<dim3(std::max(16, sms * 2 / np), np), 256, 0, st>>>(
               g->pt, w.inbox(w.me, 0), static_cast<int>(w.inbox_row_ints()) - 1, S.visited.ptr, S.dist.ptr,
               level + 1, g->view.row_offsets, S.q[nxt].ptr, S.counts.ptr + nxt, g->part_deg.ptr,
               S.overflow.ptr);
           g->ws.launches += 1;
+          mark("claim");
         }
         cur = nxt;
         count_ptr = S.counts.ptr + cur;
       }
       sync(true, nullptr, count_ptr, c);
+      mark("stats");
       wait_for_sequence(&P.h_fb->seq, P.seq, st);
       if (P.h_fb->timed_out)
         throw std::runtime_error("b2g_part_bfs_p2p: rank " + std::to_string(w.me) + " level " +
@@ -1704,6 +1781,19 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
     }
     B2G_CHECK(cudaEventRecord(g->ev1, st));
     B2G_CHECK(cudaStreamSynchronize(st));
+    if (trace) {
+      std::string line = "[b2g-p2p] rank " + std::to_string(w.me) + " phases (us):";
+      for (size_t i = 1; i < marks.size(); ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+        char buf[64];
+        std::snprintf(buf, sizeof buf, " %s=%.1f", marks[i].first.c_str(), ms * 1e3f);
+        line += buf;
+      }
+      std::fprintf(stderr, "%s\n", line.c_str());
+      for (auto& m : marks)
+        cudaEventDestroy(m.second);
+    }
     S.cur = cur;
     S.frontier_is_bitmap = false;
     if (stats) {

@@ -227,15 +227,205 @@ __global__ void p2p_sync_kernel(p2p_window_t w, unsigned epoch, const int* send_
   }
 }
 
-/// push this rank's segment of front[parity] (already complete in its own window) to every peer
+/// Report of p2p_tail_kernel (pinned host memory).
+struct p2p_tail_report_t {
+  int levels;     // levels executed by this launch (each consumed two barrier epochs)
+  int cur;        // which local queue holds the frontier it stopped at
+  int timed_out;
+  int pad;
+  long long count;    // GLOBAL size of that frontier
+  long long deg_sum;  // its GLOBAL out-degree sum
+  long long edges[16];     // global edges inspected per level
+  long long frontier[16];  // global frontier size per level
+  volatile int seq;
+};
+
+/**
+ * @brief Distributed tail of the traversal in ONE launch per rank: while the global frontier stays
+ * tiny, a single CTA per GPU runs level after level -- expand (remote neighbours stored into the
+ * owners' inboxes), barrier, claim the inbox, statistics barrier -- without a host round trip or a
+ * kernel boundary between levels (a top-down level otherwise costs ~5 launches and ~60 us of fixed
+ * latency per rank).  All ranks enter and leave it on the same global statistics.
+ */
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads)
+p2p_tail_kernel(csr_view_t g, partition_t pt, p2p_window_t w, unsigned epoch0, int* q0, int* q1, int* counts,
+                int cur, int first_level, long long first_frontier, int max_levels, long long edge_budget,
+                unsigned* visited, unsigned* sent, int* dist, int* overflow, p2p_tail_report_t* rep, int seq,
+                unsigned long long timeout_ns) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ int s_cnt, s_late;
+  __shared__ int s_send[kMaxPeers];
+  __shared__ unsigned long long s_deg, s_edges;
+  __shared__ long long s_glob[4];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int* __restrict__ ro = g.row_offsets;
+  const int* __restrict__ ci = g.column_indices;
+  int* q[2] = {q0, q1};
+  int n = counts[cur];
+  int level = first_level, done = 0;
+  unsigned epoch = epoch0;
+  long long glob_n = first_frontier, glob_m = 0;
+  if (threadIdx.x == 0)
+    s_late = 0;
+  auto barrier = [&](unsigned e) {  // threads r < P: publish epoch e to peer r, wait for peer r
+    if (threadIdx.x < w.nparts) {
+      const int r = threadIdx.x;
+      __threadfence_system();
+      st_release_sys(w.flags(r) + w.me, e);
+      const unsigned* mine = w.flags(w.me) + r;
+      const unsigned long long t0 = global_timer_ns();
+      while (static_cast<int>(ld_acquire_sys(mine) - e) < 0)
+        if (global_timer_ns() - t0 > timeout_ns) {
+          s_late = 1;
+          break;
+        }
+    }
+  };
+  for (;;) {
+    if (threadIdx.x == 0) {
+      s_cnt = 0;
+      s_deg = 0;
+      s_edges = 0;
+    }
+    if (threadIdx.x < kMaxPeers)
+      s_send[threadIdx.x] = 0;
+    __syncthreads();
+    p2p_claim_op op{pt, w, visited, sent, dist, level + 1, s_send, overflow};
+    const int* in = q[cur];
+    int* out = q[cur ^ 1];
+    unsigned long long my_deg = 0, my_edges = 0;
+    // ---- expand: warp per frontier row --------------------------------------------------------
+    for (int i = warp; i < n; i += kWarps) {
+      const int v = in[i];
+      const int s = ro[v], d = ro[v + 1] - s;
+      if (lane == 0)
+        my_edges += static_cast<unsigned>(d);
+      for (int off = 0; off < d; off += 32) {
+        bool keep = false;
+        int nb = -1;
+        if (off + lane < d) {
+          nb = ci[s + off + lane];
+          keep = op(v, nb, s + off + lane, 1.0f);
+        }
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (m) {
+          int base = 0;
+          if (lane == 0)
+            base = atomicAdd(&s_cnt, __popc(m));
+          base = __shfl_sync(kFull, base, 0);
+          if (keep) {
+            const int x = pt.local(nb);
+            out[base + __popc(m & lanemask_lt())] = x;
+            my_deg += static_cast<unsigned>(ro[x + 1] - ro[x]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // every peer store of this CTA is ordered before the flags below
+    // ---- barrier A: publish the inbox counts ------------------------------------------------------
+    if (threadIdx.x < w.nparts)
+      w.inbox(threadIdx.x, w.me)[0] = threadIdx.x == w.me ? 0 : min(s_send[threadIdx.x], w.cap);
+    barrier(epoch);
+    __syncthreads();
+    // ---- claim what the peers forwarded (their stores bypass this SM's L1: read through L2) -------
+    for (int src = 0; src < w.nparts; ++src) {
+      if (src == w.me)
+        continue;
+      const int* row = w.inbox(w.me, src);
+      const int n_in = __ldcg(row);
+      for (int i0 = warp * 32; i0 < n_in; i0 += kThreads) {
+        const int i = i0 + lane;
+        bool won = false;
+        int l = 0;
+        if (i < n_in) {
+          l = pt.local(__ldcg(row + 1 + i));
+          won = bitmap_test_and_set(visited, l);
+          if (won) {
+            dist[l] = level + 1;
+            my_deg += static_cast<unsigned>(ro[l + 1] - ro[l]);
+          }
+        }
+        const unsigned m = __ballot_sync(kFull, won);
+        if (m) {
+          int base = 0;
+          if (lane == 0)
+            base = atomicAdd(&s_cnt, __popc(m));
+          base = __shfl_sync(kFull, base, 0);
+          if (won)
+            out[base + __popc(m & lanemask_lt())] = l;
+        }
+      }
+    }
+    my_deg = warp_sum(my_deg);
+    my_edges = warp_sum(my_edges);
+    if (lane == 0) {
+      if (my_deg)
+        atomicAdd(&s_deg, my_deg);
+      if (my_edges)
+        atomicAdd(&s_edges, my_edges);
+    }
+    __syncthreads();
+    // ---- statistics barrier: every rank writes its numbers into every peer, then sums ------------
+    const int parity = (epoch + 1) & 1;
+    if (threadIdx.x < w.nparts) {
+      long long* st = w.stats(threadIdx.x, parity) + 4 * w.me;
+      st[0] = s_cnt;
+      st[1] = static_cast<long long>(s_deg);
+      st[2] = static_cast<long long>(s_edges);
+      st[3] = 0;
+    }
+    barrier(epoch + 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long t[3] = {0, 0, 0};
+      const long long* st = w.stats(w.me, parity);
+      for (int r = 0; r < w.nparts; ++r)
+        for (int k = 0; k < 3; ++k)
+          t[k] += __ldcg(st + 4 * r + k);
+      s_glob[0] = t[0];
+      s_glob[1] = t[1];
+      s_glob[2] = t[2];
+      if (done < 16) {
+        rep->edges[done] = t[2];
+        rep->frontier[done] = glob_n;
+      }
+    }
+    __syncthreads();
+    glob_n = s_glob[0];
+    glob_m = s_glob[1];
+    n = s_cnt;
+    cur ^= 1;
+    ++level;
+    ++done;
+    epoch += 2;
+    if (glob_n == 0 || glob_m >= edge_budget || done >= max_levels || s_late)
+      break;
+    __syncthreads();  // s_cnt / s_glob were read by everyone before they are cleared
+  }
+  if (threadIdx.x == 0) {
+    counts[cur] = n;
+    rep->levels = done;
+    rep->cur = cur;
+    rep->count = glob_n;
+    rep->deg_sum = glob_m;
+    rep->timed_out = s_late;
+    __threadfence_system();
+    rep->seq = seq;
+  }
+}
+
+/// push this rank's segment of front[parity] (already complete in its own window) to every peer:
+/// 16-byte stores, enough CTAs to keep NVLink busy (segments are 16-byte aligned: words % 4 == 0)
 static __global__ void p2p_push_segment_kernel(p2p_window_t w, int parity) {
   const size_t at = static_cast<size_t>(w.me) * w.words;
-  const unsigned* src = w.front(w.me, parity) + at;
+  const uint4* src = reinterpret_cast<const uint4*>(w.front(w.me, parity) + at);
+  const int n4 = w.words >> 2;
   for (int r = blockIdx.y; r < w.nparts; r += gridDim.y) {
     if (r == w.me)
       continue;
-    unsigned* dst = w.front(r, parity) + at;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.words; i += gridDim.x * blockDim.x)
+    uint4* dst = reinterpret_cast<uint4*>(w.front(r, parity) + at);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
       dst[i] = src[i];
   }
 }
