@@ -789,10 +789,9 @@ __global__ void __launch_bounds__(kThreads)
 advance_tail_kernel(csr_view_t g, int* q0, int* q1, int* counts, int cur, int first_level,
                     int max_levels, unsigned long long edge_budget, OpMaker make_op,
                     tail_report_t* rep, int seq) {
-  constexpr int kWarps = kThreads / 32;
   __shared__ int s_cnt;
   __shared__ unsigned long long s_deg, s_edges;
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int lane = lane_id();
   const int* __restrict__ ro = g.row_offsets;
   const int* __restrict__ ci = g.column_indices;
   const float* __restrict__ vals = g.values;
@@ -811,31 +810,56 @@ advance_tail_kernel(csr_view_t g, int* q0, int* q1, int* counts, int cur, int fi
     const int* in = q[cur];
     int* out = q[cur ^ 1];
     unsigned long long my_deg = 0, my_edges = 0;
-    for (int i = warp; i < n; i += kWarps) {
-      const int v = in[i];
-      if (v < 0)
-        continue;
-      const int s = ro[v], d = ro[v + 1] - s;
-      if (lane == 0)
-        my_edges += static_cast<unsigned>(d);
-      for (int off = 0; off < d; off += 32) {
-        const int e = s + off + lane;
-        bool keep = false;
-        int nb = -1;
-        if (off + lane < d) {
-          nb = ci[e];
-          float w = (kWeights && vals) ? vals[e] : 1.0f;
-          keep = op(v, nb, e, w);
+    // one lane per frontier row (late levels: thousands of rows of a few edges each); rows of 32+
+    // edges are walked by the whole warp, one coalesced chunk at a time
+    for (int base = 0; base < n; base += kThreads) {
+      const int i = base + static_cast<int>(threadIdx.x);
+      int v = -1, s = 0, d = 0;
+      if (i < n) {
+        v = in[i];
+        if (v >= 0) {
+          s = ro[v];
+          d = ro[v + 1] - s;
         }
-        const unsigned m = __ballot_sync(kFull, keep);
-        if (m) {
-          int base = 0;
-          if (lane == 0)
-            base = atomicAdd(&s_cnt, __popc(m));
-          base = __shfl_sync(kFull, base, 0);
-          if (keep) {
+      }
+      my_edges += static_cast<unsigned>(d);
+      unsigned big = __ballot_sync(kFull, d >= 32);
+      while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int bv = __shfl_sync(kFull, v, src), bs = __shfl_sync(kFull, s, src),
+                  bd = __shfl_sync(kFull, d, src);
+        for (int off = 0; off < bd; off += 32) {
+          const int e = bs + off + lane;
+          bool keep = false;
+          int nb = -1;
+          if (off + lane < bd) {
+            nb = ci[e];
+            float w = (kWeights && vals) ? vals[e] : 1.0f;
+            keep = op(bv, nb, e, w);
+          }
+          const unsigned m = __ballot_sync(kFull, keep);
+          if (m) {
+            int at = 0;
+            if (lane == 0)
+              at = atomicAdd(&s_cnt, __popc(m));
+            at = __shfl_sync(kFull, at, 0);
+            if (keep) {
+              int x = op_emit(op, nb);
+              out[at + __popc(m & lanemask_lt())] = x;
+              my_deg += static_cast<unsigned>(ro[x + 1] - ro[x]);
+            }
+          }
+        }
+      }
+      if (d < 32) {
+        for (int k = 0; k < d; ++k) {
+          const int e = s + k;
+          const int nb = ci[e];
+          float w = (kWeights && vals) ? vals[e] : 1.0f;
+          if (op(v, nb, e, w)) {
             int x = op_emit(op, nb);
-            out[base + __popc(m & lanemask_lt())] = x;
+            out[atomicAdd(&s_cnt, 1)] = x;
             my_deg += static_cast<unsigned>(ro[x + 1] - ro[x]);
           }
         }

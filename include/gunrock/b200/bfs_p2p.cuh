@@ -253,7 +253,6 @@ p2p_tail_kernel(csr_view_t g, partition_t pt, p2p_window_t w, unsigned epoch0, i
                 int cur, int first_level, long long first_frontier, int max_levels, long long edge_budget,
                 unsigned* visited, unsigned* sent, int* dist, int* overflow, p2p_tail_report_t* rep, int seq,
                 unsigned long long timeout_ns) {
-  constexpr int kWarps = kThreads / 32;
   __shared__ int s_cnt, s_late;
   __shared__ int s_send[kMaxPeers];
   __shared__ unsigned long long s_deg, s_edges;
@@ -295,28 +294,49 @@ p2p_tail_kernel(csr_view_t g, partition_t pt, p2p_window_t w, unsigned epoch0, i
     const int* in = q[cur];
     int* out = q[cur ^ 1];
     unsigned long long my_deg = 0, my_edges = 0;
-    // ---- expand: warp per frontier row --------------------------------------------------------
-    for (int i = warp; i < n; i += kWarps) {
-      const int v = in[i];
-      const int s = ro[v], d = ro[v + 1] - s;
-      if (lane == 0)
-        my_edges += static_cast<unsigned>(d);
-      for (int off = 0; off < d; off += 32) {
-        bool keep = false;
-        int nb = -1;
-        if (off + lane < d) {
-          nb = ci[s + off + lane];
-          keep = op(v, nb, s + off + lane, 1.0f);
+    // ---- expand: one lane per frontier row, rows of 32+ edges walked by the whole warp -----------
+    for (int base = 0; base < n; base += kThreads) {
+      const int i = base + static_cast<int>(threadIdx.x);
+      int v = -1, s = 0, d = 0;
+      if (i < n) {
+        v = in[i];
+        s = ro[v];
+        d = ro[v + 1] - s;
+      }
+      my_edges += static_cast<unsigned>(d);
+      unsigned big = __ballot_sync(kFull, d >= 32);
+      while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int bv = __shfl_sync(kFull, v, src), bs = __shfl_sync(kFull, s, src),
+                  bd = __shfl_sync(kFull, d, src);
+        for (int off = 0; off < bd; off += 32) {
+          bool keep = false;
+          int nb = -1;
+          if (off + lane < bd) {
+            nb = ci[bs + off + lane];
+            keep = op(bv, nb, bs + off + lane, 1.0f);
+          }
+          const unsigned m = __ballot_sync(kFull, keep);
+          if (m) {
+            int at = 0;
+            if (lane == 0)
+              at = atomicAdd(&s_cnt, __popc(m));
+            at = __shfl_sync(kFull, at, 0);
+            if (keep) {
+              const int x = pt.local(nb);
+              out[at + __popc(m & lanemask_lt())] = x;
+              my_deg += static_cast<unsigned>(ro[x + 1] - ro[x]);
+            }
+          }
         }
-        const unsigned m = __ballot_sync(kFull, keep);
-        if (m) {
-          int base = 0;
-          if (lane == 0)
-            base = atomicAdd(&s_cnt, __popc(m));
-          base = __shfl_sync(kFull, base, 0);
-          if (keep) {
+      }
+      if (d < 32) {
+        for (int k = 0; k < d; ++k) {
+          const int nb = ci[s + k];
+          if (op(v, nb, s + k, 1.0f)) {
             const int x = pt.local(nb);
-            out[base + __popc(m & lanemask_lt())] = x;
+            out[atomicAdd(&s_cnt, 1)] = x;
             my_deg += static_cast<unsigned>(ro[x + 1] - ro[x]);
           }
         }

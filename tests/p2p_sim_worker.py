@@ -20,7 +20,7 @@ from gunrock_b200 import multi_gpu as mg  # noqa: E402
 
 def main():
     results = {}
-    for P in (1, 2, 3, 4, 8):
+    for P in (1, 2, 3, 8):
         for scale, ef, seed in ((11, 16, 5), (14, 8, 0x5EED22)):
             ro, ci = oracle.rmat_csr(scale, ef, seed, mirror=True)
             deg = np.diff(ro)
@@ -29,7 +29,8 @@ def main():
                 engines = [mg.CudaRankEngine(g, gb.options_t(advance_load_balance=lb, hub_threshold=256))
                            for g in graphs]
                 mg.p2p_connect_simulated(engines)          # idempotent: the windows are reused
-                for src in (int(deg.argmax()), int(np.flatnonzero(deg > 0)[-1])):
+                srcs = (int(deg.argmax()), int(np.flatnonzero(deg > 0)[-1])) if scale < 14 else (int(deg.argmax()),)
+                for src in srcs:
                     exp = oracle.bfs(ro, ci, src)
                     for direction in (gb.advance_direction_t.forward, gb.advance_direction_t.optimized,
                                       gb.advance_direction_t.backward):
