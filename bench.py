@@ -270,6 +270,12 @@ def run_partitioned(args, wl, name, rank, world, local):
     ms2 = float(ms2.item())
     reached = torch.tensor([int((dloc < 2**31 - 1).sum())], device="cuda")
     dist.all_reduce(reached)
+    agree = None
+    if exchange == "p2p":     # outside the timed region: same depths as the NCCL-exchange path, on every rank
+        d_nccl, _ = mg.bfs_rank_async(eng, comm, src, total_edges, direction=direction)
+        same = torch.tensor([int(torch.equal(dloc, d_nccl))], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        agree = bool(same.item())
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         peak, peak_kind = peaks()
@@ -283,6 +289,7 @@ def run_partitioned(args, wl, name, rank, world, local):
                            "levels": st.levels, "level_direction": st.level_direction,
                            "level_frontier": st.level_frontier, "level_edges": st.level_edges,
                            "ids_exchanged_per_step_rank0": st.exchanged_ids, "reached_vertices": int(reached.item()),
+                           "depths_equal_nccl_path": agree,
                            "l2_policy": "inputs larger than L2 per rank" if total_edges * 4 / world > 126e6 else
                                         "per-rank column indices %.0f MB" % (total_edges * 4 / world / 1e6),
                            "graph500_mteps": total_edges / (ms / args.steps) / 1e3},
