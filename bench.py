@@ -378,12 +378,13 @@ def main():
     h_out = torch.empty(V, dtype=out_dtype).pin_memory()
 
     # N > 1: a batch of sources, sharded over ranks (replicated graph, no collective on the data path)
-    rng = np.random.default_rng(1)
+    # The unit of work is one traversal from a hub: N = 1 runs the highest-degree vertex (the bench source
+    # of the reference arm and of the CPU baseline); N > 1 runs the 4 N highest-degree vertices, 4 per
+    # rank, so that every rank's traversals have the same level profile as the N = 1 unit.
     sources = [src]
     if world > 1:
-        ro_host = G.download()[0]
-        cand = np.flatnonzero(np.diff(ro_host) > 0)
-        batch = [src] + [int(x) for x in rng.choice(cand, world * 4 - 1, replace=False)]
+        deg_host = np.diff(G.download()[0])
+        batch = [int(x) for x in np.argsort(-deg_host.astype(np.int64), kind="stable")[:world * 4]]
         sources = batch[rank::world]
 
     def step(out):
@@ -487,6 +488,7 @@ def main():
         "config": {"workload": wl["desc"], "vertices": V, "edges": G.n_edges, "source": src,
                    "source_degree": src_deg, "load_balance": wl["lb"], "direction": wl["direction"],
                    "filter": "compact (fused into advance)", "sources_per_step": len(sources) * world if world > 1 else 1,
+                   "sources": "highest-degree vertex" if world == 1 else "the 4 N highest-degree vertices, 4 per rank",
                    "l2_policy": "inputs larger than L2 (column indices %.0f MB > 126 MB)" % (G.n_edges * 4 / 1e6),
                    "levels": last.iterations, "level_direction": last.level_direction,
                    "level_frontier": last.level_frontier, "level_edges": last.level_edges[:last.iterations],
