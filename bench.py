@@ -460,6 +460,21 @@ def main():
         dist.destroy_process_group()
         return
 
+    # DRAM traffic per launch of the dominant kernel: from the committed ncu capture of this very
+    # configuration (profiles/r1_traffic.json), never measured under the profiler here
+    lbk = "merge_path" if wl["lb"] == "merge_path" else "binned"
+    traffic, traffic_detail = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            entry = json.load(f).get(f"{name}/{wl['lb']}")
+        if entry and wl["direction"] == "forward" and not args.scale:
+            per = [l["dram_read_bytes"] + l["dram_write_bytes"] for l in entry["launches"]]
+            traffic = sum(per) / len(per)
+            traffic_detail = {"source": entry["source"], "launches": entry["launches"],
+                              "note": "mean over the capture's launches; compare with their algorithmic_bytes"}
+    except (OSError, ValueError, KeyError):
+        pass
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -----------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -499,9 +514,9 @@ def main():
                 "d2h_bytes_per_step": out_bytes * (len(sources) if world > 1 else 1), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": agg["launches"],
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": None, "peak_kind": peak_kind,
-                     "kernel": {"bfs": "advance_%s_kernel<bfs_claim_op>" % ("merge_path" if wl["lb"] == "merge_path" else "binned"),
-                                "sssp": "advance_binned_kernel<sssp_relax_op>", "pr": "pr_pull_kernel"}[wl["alg"]],
+                     "traffic": traffic, "traffic_detail": traffic_detail, "peak_kind": peak_kind,
+                     "kernel": {"bfs": "advance_%s_kernel<bfs_claim_op>" % lbk,
+                                "sssp": "advance_%s_kernel<sssp_relax_op>" % lbk, "pr": "pr_pull_tile_kernel"}[wl["alg"]],
                      "bytes_per_edge": bytes_per_edge, "launches": agg["kern_launches"],
                      "kernel_ms_total": agg["kern_ms"]},
         "cpu_baseline": cpu, "clocks": clocks, "wall_ms": wall_ms,
