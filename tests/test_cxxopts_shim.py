@@ -1,0 +1,52 @@
+"""include/cxxopts.hpp: our own stand-in for the cxxopts subset Gunrock's example programs use
+(examples/algorithms/tc/tc.cu:23-45 is the pattern compiled here).  Host-only, g++."""
+import subprocess
+
+from conftest import ROOT
+
+SRC = r"""
+#include <cxxopts.hpp>
+#include <iostream>
+int main(int argc, char** argv) {
+  cxxopts::Options options(argv[0], "Triangle Counting example");
+  options.add_options()("help", "Print help")(
+      "validate", "CPU validation", cxxopts::value<bool>()->default_value("false"))(
+      "m,market", "Matrix file", cxxopts::value<std::string>())(
+      "n,num_runs", "runs", cxxopts::value<int>()->default_value("1"))(
+      "p,uniquify_percent", "percent", cxxopts::value<float>());
+  try {
+    auto result = options.parse(argc, argv);
+    if (result.count("help") || (result.count("market") == 0)) {
+      std::cout << options.help({""}) << std::endl;
+      return 0;
+    }
+    std::cout << result["market"].as<std::string>() << "|" << result["validate"].as<bool>() << "|"
+              << result["num_runs"].as<int>() << "|" << result.count("uniquify_percent");
+    if (result.count("uniquify_percent") == 1) std::cout << "|" << result["uniquify_percent"].as<float>();
+    std::cout << std::endl;
+  } catch (const cxxopts::OptionException& e) {
+    std::cout << "EXC " << e.what() << std::endl;
+    return 3;
+  }
+}
+"""
+
+
+def test_cxxopts_subset(tmp_path):
+    src = tmp_path / "t.cpp"
+    src.write_text(SRC)
+    exe = tmp_path / "t"
+    subprocess.run(["g++", "-std=c++17", f"-I{ROOT}/include", str(src), "-o", str(exe)], check=True)
+
+    def run(*a):
+        r = subprocess.run([str(exe), *a], capture_output=True, text=True)
+        return r.returncode, r.stdout.strip()
+
+    assert run("-m", "a.mtx") == (0, "a.mtx|0|1|0")
+    assert run("--market=b.mtx", "--validate", "-n", "7", "--uniquify_percent", "12.5") == (0, "b.mtx|1|7|1|12.5")
+    assert run("--market", "c.mtx", "--validate=false", "-n3") == (0, "c.mtx|0|3|0")
+    rc, out = run("--help")
+    assert rc == 0 and "--market arg" in out and "(default: false)" in out
+    rc, out = run()
+    assert rc == 0 and "Usage:" in out            # no --market: help, like the examples
+    assert run("--nope")[0] == 3 and run("-m")[0] == 3
