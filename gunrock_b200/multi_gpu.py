@@ -18,6 +18,7 @@ GPU tests), and (c) on CPU under gloo with a numpy stand-in engine (tests only).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import sys
@@ -246,6 +247,10 @@ class CudaRankEngine:
         _check(self.L.b2g_part_set_stream(self.G._h, stream.cuda_stream), "b2g_part_set_stream")
         return stream
 
+    def release_stream(self):
+        """Back to the handle's own stream (waits for what was enqueued on the borrowed one)."""
+        _check(self.L.b2g_part_set_stream(self.G._h, None), "b2g_part_set_stream")
+
     def topdown_async(self, level: int, msg, cap_s: int):
         _check(self.L.b2g_part_bfs_topdown_async(self.G._h, level, C.byref(self.opt), msg.data_ptr(), cap_s),
                "b2g_part_bfs_topdown_async")
@@ -419,6 +424,16 @@ class TorchDistComm:
                                    input_split_sizes=list(send_counts), group=self.group)
         return recv
 
+    def all_to_all_rows(self, out, inp):
+        """Fixed-split all-to-all of a [world, k] tensor: out[p] = rank p's inp[this rank]."""
+        if self.backend == "gloo":   # no all_to_all_single in gloo: gather everything, keep my column
+            everything = [self.torch.empty_like(inp) for _ in range(self.world)]
+            self.dist.all_gather(everything, inp.contiguous(), group=self.group)
+            for p in range(self.world):
+                out[p].copy_(everything[p][self.rank])
+        else:
+            self.dist.all_to_all_single(out, inp, group=self.group)
+
     def all_gather_bitmap(self, local):
         out = self.torch.empty(self.world * local.numel(), dtype=local.dtype, device=local.device)
         self.dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
@@ -518,14 +533,16 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
     P = comm.world
     cap_s = cap_s or min(rows_of(engine.n_global, P, 0) + 64, 1 << 20)
     engine.begin(source)
-    stream = engine.use_stream()
+    stream = engine.use_stream()              # None for a host stand-in engine (gloo tests)
+    dev = "cpu" if comm.backend == "gloo" else "cuda"
     st = part_bfs_stats_t()
     overflowed = False
-    trace = [] if os.environ.get("B2G_TRACE") else None   # per-level phase times (CUDA events), rank 0 prints
-    with torch.cuda.stream(stream):
-        msg = torch.zeros((P, cap_s + 1), dtype=torch.int32, device="cuda")
+    # per-level phase times (CUDA events), rank 0 prints
+    trace = [] if (os.environ.get("B2G_TRACE") and stream is not None) else None
+    with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+        msg = torch.zeros((P, cap_s + 1), dtype=torch.int32, device=dev)
         msgs_in = torch.zeros_like(msg)
-        stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+        stats = torch.zeros(4, dtype=torch.int64, device=dev)
         n_f, m_f, explored, level, bottom_up = 1, 0, 0, 0, False
         while n_f > 0:
             go_up = _decide(direction, level, bottom_up, n_f, m_f, explored, engine.n_global, total_edges,
@@ -546,7 +563,7 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
                 engine.topdown_async(level, out_l, cap_l)
                 mark("advance")
                 if P > 1:
-                    dist.all_to_all_single(in_l, out_l, group=comm.group)
+                    comm.all_to_all_rows(in_l, out_l)
                     mark("all_to_all")
                     engine.claim_packed_async(level, in_l, cap_l)
                     mark("claim")
@@ -568,8 +585,9 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
                 explored += g[2]
             n_f, m_f, bottom_up = g[0], g[1], go_up
             level += 1
-        stream.synchronize()
-    engine.L.b2g_part_set_stream(engine.G._h, None)
+        if stream is not None:
+            stream.synchronize()
+    engine.release_stream()
     if trace and comm.rank == 0:
         for lv, d, nf, rep in trace:
             print(f"[b2g-part] level {lv} {d} n_f={nf}: " + " ".join(f"{k}={v:.1f}us" for k, v in rep), file=sys.stderr)

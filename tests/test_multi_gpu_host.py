@@ -97,6 +97,42 @@ class NumpyRankEngine:
     def empty_ids(self, n):
         return torch.empty(n, dtype=torch.int32)
 
+    # ---- the sync-free steps (b2g_part_bfs_*_async), on host tensors --------------------------------
+    def use_stream(self, stream=None):
+        return None
+
+    def release_stream(self):
+        pass
+
+    def topdown_async(self, level, msg, cap_s):
+        counts, self._edges = self.topdown(level)
+        msg.zero_()
+        for o, ids in enumerate(self._send):
+            msg[o, 0] = len(ids)                                  # the true count, even if it does not fit
+            k = min(len(ids), cap_s)
+            msg[o, 1:1 + k] = torch.from_numpy(ids[:k].astype(np.int32))
+        self._overflow = 0
+
+    def claim_packed_async(self, level, msgs, cap_s):
+        for src in range(self.nparts):
+            if src == self.part:
+                continue
+            n = int(msgs[src, 0])
+            if n > cap_s:
+                self._overflow, n = 1, cap_s
+            if n:
+                self.claim(level, msgs[src, 1:1 + n])
+
+    def frontier_bitmap_async(self):
+        return self.frontier_bitmap()
+
+    def bottomup_async(self, level, frontier_all):
+        self._edges, self._overflow = self.bottomup(level, frontier_all), 0
+
+    def end_level_async(self, stats):
+        n, deg = self.end_level()
+        stats.copy_(torch.tensor([n, deg, self._edges, self._overflow], dtype=torch.int64))
+
 
 def _worker(rank, world, port, ro, ci, source, direction, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -107,6 +143,13 @@ def _worker(rank, world, port, ro, ci, source, direction, out_dir):
     d, st = mg.bfs_rank(eng, comm, source, total_edges=len(ci), direction=direction)
     np.save(os.path.join(out_dir, f"d{rank}.npy"), d.numpy())
     np.save(os.path.join(out_dir, f"s{rank}.npy"), np.array(st.level_direction))
+    # the sync-free driver (packed fixed-split rows, rows sized by the frontier's out-degree bound), and
+    # its fall-back to the two-phase exchange when a packed row overflows (cap_s = 2 ids)
+    for tag, cap in (("a", 0), ("o", 2)):
+        d2, st2 = mg.bfs_rank_async(eng, comm, source, total_edges=len(ci), direction=direction, cap_s=cap)
+        np.save(os.path.join(out_dir, f"d{tag}{rank}.npy"), d2.numpy().copy())
+        np.save(os.path.join(out_dir, f"s{tag}{rank}.npy"), np.array(st2.level_direction))
+        np.save(os.path.join(out_dir, f"e{tag}{rank}.npy"), np.array([st2.edges_touched, st.edges_touched]))
     dist.destroy_process_group()
 
 
@@ -125,6 +168,13 @@ def test_partitioned_bfs_over_gloo(tmp_path, world, direction):
         assert 1 in dirs and dirs[0] == 0          # the switch fired, level 0 stayed top-down
     else:
         assert not dirs.any()
+    # sync-free driver ("a") and its overflow fall-back ("o"): same depths, same level plan, same edge count
+    for tag in ("a", "o"):
+        locs = [np.load(tmp_path / f"d{tag}{r}.npy") for r in range(world)]
+        assert np.array_equal(mg.gather_distances(locs, len(ro) - 1), got), tag
+        assert np.array_equal(np.load(tmp_path / f"s{tag}0.npy"), dirs), tag
+        e = np.load(tmp_path / f"e{tag}0.npy")
+        assert e[0] == e[1], tag
 
 
 def test_partition_helpers():
