@@ -669,17 +669,18 @@ def sssp_rank(engine, comm, source: int, cap_s: int = 0):
     cap_s = cap_s or min(rows, 1 << 20)
     while True:
         engine.sssp_begin(source, max(cap_s, rows))
-        stream = engine.use_stream()
+        stream = engine.use_stream()              # None for a host stand-in engine (gloo tests)
+        dev = "cpu" if comm.backend == "gloo" else "cuda"
         overflowed, it, relaxed = False, 0, 0
-        with torch.cuda.stream(stream):
-            msg = torch.zeros((P, 2 * cap_s + 1), dtype=torch.int32, device="cuda")
+        with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+            msg = torch.zeros((P, 2 * cap_s + 1), dtype=torch.int32, device=dev)
             msgs_in = torch.zeros_like(msg)
-            stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+            stats = torch.zeros(4, dtype=torch.int64, device=dev)
             n_f = 1
             while n_f > 0:
                 engine.sssp_relax_async(it, msg, cap_s)
                 if P > 1:
-                    dist.all_to_all_single(msgs_in, msg, group=comm.group)
+                    comm.all_to_all_rows(msgs_in, msg)
                     engine.sssp_apply_packed_async(it, msgs_in, cap_s)
                 engine.sssp_end_iteration_async(stats)
                 if P > 1:
@@ -691,8 +692,9 @@ def sssp_rank(engine, comm, source: int, cap_s: int = 0):
                 n_f = g[0]
                 relaxed += g[2]
                 it += 1
-            stream.synchronize()
-        engine.L.b2g_part_set_stream(engine.G._h, None)
+            if stream is not None:
+                stream.synchronize()
+        engine.release_stream()
         if not overflowed:
             return engine.sssp_distances(), it, relaxed
         cap_s *= 4
@@ -744,17 +746,18 @@ def pr_rank(engine, comm, alpha: float = 0.85, tol: float = 1e-6, max_iter: int 
     include/gunrock/algorithms/pr.hxx:107-195.  Returns (owned ranks, iterations)."""
     torch, dist = comm.torch, comm.dist
     P = comm.world
-    stream = engine.use_stream()
+    stream = engine.use_stream()                  # None for a host stand-in engine (gloo tests)
+    dev = "cpu" if comm.backend == "gloo" else "cuda"
     R = rows_of(engine.n_global, P, 0)
-    with torch.cuda.stream(stream):
+    with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
         outdeg = engine.pr_outdegrees()
         if P > 1:
             dist.all_reduce(outdeg, group=comm.group)
         engine.pr_begin(alpha, outdeg)
-        c_local = torch.zeros(R, dtype=torch.float32, device="cuda")
-        c_all = torch.zeros(P * R, dtype=torch.float32, device="cuda") if P > 1 else c_local
-        dsum = torch.zeros(1, dtype=torch.float64, device="cuda")
-        err = torch.zeros(1, dtype=torch.float32, device="cuda")
+        c_local = torch.zeros(R, dtype=torch.float32, device=dev)
+        c_all = torch.zeros(P * R, dtype=torch.float32, device=dev) if P > 1 else c_local
+        dsum = torch.zeros(1, dtype=torch.float64, device=dev)
+        err = torch.zeros(1, dtype=torch.float32, device=dev)
         it = 0
         while True:
             if it > 0 and float(err.item()) < tol:          # the iteration's only host synchronisation
@@ -769,8 +772,9 @@ def pr_rank(engine, comm, alpha: float = 0.85, tol: float = 1e-6, max_iter: int 
             if P > 1:
                 dist.all_reduce(err, op=dist.ReduceOp.MAX, group=comm.group)
             it += 1
-        stream.synchronize()
-    engine.L.b2g_part_set_stream(engine.G._h, None)
+        if stream is not None:
+            stream.synchronize()
+    engine.release_stream()
     return engine.pr_ranks(), it
 
 
