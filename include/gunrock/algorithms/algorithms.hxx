@@ -12,11 +12,15 @@ namespace gunrock {
 /// Runtime operator selection shared by all algorithms; defaults as the reference
 /// (block_mapped advance, predicated filter, filter and uniquify off, best-effort uniquify).
 struct options_t {
-  operators::load_balance_t advance_load_balance = operators::load_balance_t::block_mapped;
-  operators::filter_algorithm_t filter_algorithm = operators::filter_algorithm_t::predicated;
+  using lb_t = operators::load_balance_t;
+  using filter_t = operators::filter_algorithm_t;
+  using uniq_t = operators::uniquify_algorithm_t;
+
+  lb_t advance_load_balance = lb_t::block_mapped;
+  filter_t filter_algorithm = filter_t::predicated;
   bool enable_filter = false;
   bool enable_uniquify = false;
-  operators::uniquify_algorithm_t uniquify_algorithm = operators::uniquify_algorithm_t::unique;
+  uniq_t uniquify_algorithm = uniq_t::unique;
   bool best_effort_uniquify = true;
   float uniquify_percent = 100.0f;
   /// B200 addition (the reference's advance_direction_t is a dead template parameter, SURVEY.md
@@ -24,22 +28,20 @@ struct options_t {
   operators::advance_direction_t advance_direction = operators::advance_direction_t::forward;
 
   options_t() = default;
-  options_t(operators::load_balance_t _advance_load_balance,
-            operators::filter_algorithm_t _filter_algorithm =
-                operators::filter_algorithm_t::predicated,
-            bool _enable_filter = false,
-            bool _enable_uniquify = false,
-            operators::uniquify_algorithm_t _uniquify_algorithm =
-                operators::uniquify_algorithm_t::unique,
-            bool _best_effort_uniquify = true,
-            float _uniquify_percent = 100.0f)
-      : advance_load_balance(_advance_load_balance),
-        filter_algorithm(_filter_algorithm),
-        enable_filter(_enable_filter),
-        enable_uniquify(_enable_uniquify),
-        uniquify_algorithm(_uniquify_algorithm),
-        best_effort_uniquify(_best_effort_uniquify),
-        uniquify_percent(_uniquify_percent) {}
+
+  /// Positional form used by the reference's callers: (load balance, filter, filter on/off,
+  /// uniquify on/off, uniquify algorithm, best effort, percent) -- trailing ones optional.
+  options_t(lb_t lb, filter_t filter = filter_t::predicated, bool with_filter = false,
+            bool with_uniquify = false, uniq_t uniquify = uniq_t::unique, bool best_effort = true,
+            float percent = 100.0f) {
+    advance_load_balance = lb;
+    filter_algorithm = filter;
+    enable_filter = with_filter;
+    enable_uniquify = with_uniquify;
+    uniquify_algorithm = uniquify;
+    best_effort_uniquify = best_effort;
+    uniquify_percent = percent;
+  }
 };
 
 }  // namespace gunrock
