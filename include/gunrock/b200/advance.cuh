@@ -785,7 +785,7 @@ struct tail_report_t {
  * few hundred edges each).  `make_op(level)` builds the level's edge functor.
  */
 template <int kThreads, bool kWeights, typename OpMaker>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)  // one CTA per launch: take the registers
 advance_tail_kernel(csr_view_t g, int* q0, int* q1, int* counts, int cur, int first_level,
                     int max_levels, unsigned long long edge_budget, OpMaker make_op,
                     tail_report_t* rep, int seq) {

@@ -248,7 +248,7 @@ struct p2p_tail_report_t {
  * latency per rank).  All ranks enter and leave it on the same global statistics.
  */
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)  // one CTA per launch: take the registers
 p2p_tail_kernel(csr_view_t g, partition_t pt, p2p_window_t w, unsigned epoch0, int* q0, int* q1, int* counts,
                 int cur, int first_level, long long first_frontier, int max_levels, long long edge_budget,
                 unsigned* visited, unsigned* sent, int* dist, int* overflow, p2p_tail_report_t* rep, int seq,
