@@ -71,7 +71,11 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(base, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "libgunrock_oracle" not in text and "orc_" not in text, f
-    for base, _, files in os.walk(os.path.join(ROOT, "include")):
-        for f in files:
-            text = open(os.path.join(base, f)).read()
-            assert "libgunrock_oracle" not in text and "orc_" not in text, f
+    for top in ("include", "python"):
+        for base, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith(".pyc"):
+                    continue
+                text = open(os.path.join(base, f)).read()
+                assert "libgunrock_oracle" not in text and "orc_" not in text, f
+                assert "import oracle" not in text and "from oracle" not in text, f
