@@ -703,7 +703,12 @@ int b2g_sssp(b2g_graph_t* g, int source, const b2g_options_t* opt, float* distan
     std::vector<sssp_level_stat_t> levels;
     int launches0 = g->ws.launches;
     B2G_CHECK(cudaEventRecord(g->ev0, st));
-    int iters = sssp_run(g->ws, g->sssp, g->view, source, d_dist, to_launch(o), &levels);
+    // experimental near/far schedule (sssp.cuh), off unless B2G_SSSP_DELTA is set to a positive width
+    static const char* delta_env = std::getenv("B2G_SSSP_DELTA");
+    const float delta = delta_env ? static_cast<float>(std::atof(delta_env)) : 0.0f;
+    int iters = delta > 0.0f
+                    ? sssp_run_near_far(g->ws, g->sssp, g->view, source, d_dist, to_launch(o), delta, &levels)
+                    : sssp_run(g->ws, g->sssp, g->view, source, d_dist, to_launch(o), &levels);
     B2G_CHECK(cudaEventRecord(g->ev1, st));
     if (dist_loc == B2G_HOST)
       B2G_CHECK(cudaMemcpyAsync(distances, d_dist, sizeof(float) * static_cast<size_t>(V),
