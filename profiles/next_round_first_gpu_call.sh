@@ -1,0 +1,19 @@
+#!/bin/bash
+# What was left unmeasured when round 1's GPU budget ran out -- one 1-GPU gpurun call (~6 min on the box):
+#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash profiles/next_round_first_gpu_call.sh'
+# Results land in gpurun_out/next_round/.  Nothing printed under a profiler is a bench value.
+set -u
+OUT=gpurun_out/next_round
+mkdir -p "$OUT"
+# 1. GPU tests written after the last GPU run (pygunrock surface) + the whole suite
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -5 | tee "$OUT/pytest_gpu.txt"
+# 2. experimental near/far SSSP: bit-exactness first, then its time against the default schedule
+B2G_RUN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -m gpu -q 2>&1 | tail -5 | tee "$OUT/pytest_experimental.txt"
+for d in "" 8 16; do
+  B2G_SSSP_DELTA=$d python bench.py --workload sssp_rmat24 --lb merge_path --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/sssp_delta_${d:-off}.json"
+done
+# 3. design input for the on-chip visited map: probe rates of L1 / L2 / shared / DSMEM
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o "$OUT/probe_rates" profiles/micro/probe_rates.cu && "$OUT/probe_rates" | tee "$OUT/probe_rates.txt"
+# 4. the default bench line (hub sources for N > 1 are measured by the 2-GPU call of the round)
+python bench.py --steps 10 --warmup 3 2>&1 | tail -1 > "$OUT/bench_default.json"
+cut -c1-300 "$OUT/bench_default.json"
