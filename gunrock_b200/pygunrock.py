@@ -239,6 +239,10 @@ def _check_tensor(t, dtype_name: str, n: int, what: str):
         raise GunrockB200Error(f"{what} must be {dtype_name}, got {t.dtype}")
     if t.numel() < n or not t.is_contiguous():
         raise GunrockB200Error(f"{what} must be contiguous with at least {n} elements")
+    # the library runs on its own non-blocking stream: whatever torch still has queued for this tensor
+    # (a fill_ on the caller's stream) must have landed before the enactor initialises it
+    import torch
+    torch.cuda.current_stream(t.device).synchronize()
 
 
 class sssp_param_t:                        # algorithms/sssp.hxx:26-35 (bindings.cu:178-183)
