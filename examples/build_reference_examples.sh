@@ -29,10 +29,11 @@ nvcc $FLAGS -I"$REF/examples/algorithms/bfs" -I"$REF/examples/algorithms/sssp" \
   -o "$OUT/ref_algorithms" "$ROOT/examples/ref_algorithms_driver.cu" & pids+=($!)
 #  4. widening: the reference's OTHER algorithms -- their own algorithm headers and
 #     unchanged example TUs -- on our framework/operator headers -> bin/ext_<alg>
-#     (mst: compile gate only so far -- its example needs <cxxopts.hpp>, served by include/cxxopts.hpp)
+#     (mst / tc need <cxxopts.hpp>: served by include/cxxopts.hpp; tc runs with uint32_t vertex / edge ids;
+#      spgemm uses the csr + csc multi-view graph and the view-tagged accessors of graph/graph.hxx)
 SHIM="$OUT/shim/gunrock/algorithms"
 mkdir -p "$SHIM"
-for alg in bc color geo hits kcore ppr spmv mst; do
+for alg in bc color geo hits kcore ppr spmv mst tc spgemm; do
   echo "#include \"$REF/include/gunrock/algorithms/$alg.hxx\"" > "$SHIM/$alg.hxx"
   nvcc $FLAGS -I"$OUT/shim" -I"$REF/examples/algorithms/$alg" -o "$OUT/ext_$alg" "$REF/examples/algorithms/$alg/$alg.cu" & pids+=($!)
 done

@@ -7,7 +7,11 @@
  *
  * One concrete view class replaces the reference's variadic-inheritance views: the CSR arrays
  * are always present; CSC arrays (the transpose, for pull traversal) are attached when built
- * from a csr+csc pair.  Accessor names and semantics are the reference's.
+ * from a csr+csc pair.  Accessor names and semantics are the reference's.  The reference selects
+ * one of several attached views with an explicit template argument
+ * (`B.template get_number_of_neighbors<graph_csc_t<...>>(col)`, algorithms/spgemm.hxx:94-190);
+ * here `graph_csr_t` / `graph_csc_t` are tag types and every accessor takes the tag as a defaulted
+ * template parameter (CSR when omitted, graph/graph.hxx:225-339 "first view" rule).
  */
 #pragma once
 
@@ -36,6 +40,21 @@ struct vertex_pair_t {
   vertex_t destination;
 };
 
+/// View tags (graph/csr.hxx:33, graph/csc.hxx:30, graph/coo.hxx:30 are full classes in the reference).
+template <memory_space_t space, typename vertex_t, typename edge_t, typename weight_t>
+struct graph_csr_t {};
+template <memory_space_t space, typename vertex_t, typename edge_t, typename weight_t>
+struct graph_csc_t {};
+template <memory_space_t space, typename vertex_t, typename edge_t, typename weight_t>
+struct graph_coo_t {};
+
+namespace detail {
+template <typename T>
+struct is_csc_view : std::false_type {};
+template <memory_space_t space, typename vertex_t, typename edge_t, typename weight_t>
+struct is_csc_view<graph_csc_t<space, vertex_t, edge_t, weight_t>> : std::true_type {};
+}  // namespace detail
+
 template <memory_space_t space, typename vertex_t, typename edge_t, typename weight_t>
 class graph_t {
  public:
@@ -46,6 +65,8 @@ class graph_t {
   using edge_pointer_t = edge_t*;
   using weight_pointer_t = weight_t*;
   using vertex_pair_type = vertex_pair_t<vertex_t>;
+  using csr_view_type = graph_csr_t<space, vertex_t, edge_t, weight_t>;
+  using csc_view_type = graph_csc_t<space, vertex_t, edge_t, weight_t>;
 
   __host__ __device__ graph_t() {}
   __host__ __device__ graph_t(std::nullptr_t) {}
@@ -53,43 +74,74 @@ class graph_t {
   graph_properties_t properties;
 
   // --- sizes ---------------------------------------------------------------------------
-  __host__ __device__ __forceinline__ vertex_t get_number_of_vertices() const { return n_rows; }
-  __host__ __device__ __forceinline__ edge_t get_number_of_edges() const { return n_nonzeros; }
+  template <typename view_t = csr_view_type>
+  __host__ __device__ __forceinline__ vertex_t get_number_of_vertices() const {
+    if constexpr (detail::is_csc_view<view_t>::value)
+      return n_columns;  // one "vertex" per column of the CSC view (graph/csc.hxx:118-120)
+    else
+      return n_rows;
+  }
+  template <typename view_t = csr_view_type>
+  __host__ __device__ __forceinline__ edge_t get_number_of_edges() const {
+    return n_nonzeros;
+  }
   __host__ __device__ __forceinline__ vertex_t get_number_of_rows() const { return n_rows; }
   __host__ __device__ __forceinline__ vertex_t get_number_of_columns() const { return n_columns; }
   __host__ __device__ __forceinline__ edge_t get_number_of_nonzeros() const { return n_nonzeros; }
   bool is_directed() { return properties.directed; }
   bool is_symmetric() { return properties.symmetric; }
   bool is_weighted() { return properties.weighted; }
+  /// Which views are attached (graph/graph.hxx:284-296 `contains_representation`).
+  template <typename view_t>
+  __host__ __device__ __forceinline__ constexpr bool contains_representation() const {
+    return true;
+  }
 
-  // --- CSR accessors (graph/csr.hxx:61-178) ---------------------------------------------
+  // --- accessors (graph/csr.hxx:61-178; CSC flavour graph/csc.hxx:42-100) -----------------
+  // CSR view: a vertex is a row, its neighbours are the row's column indices.
+  // CSC view: a vertex is a column, its "neighbours" are the column's row indices (in-edges), the
+  // stored index of an edge is its SOURCE and the destination is found by searching the offsets.
+  template <typename view_t = csr_view_type>
   __host__ __device__ __forceinline__ edge_t get_starting_edge(vertex_t const& v) const {
-    return offsets[v];
+    if constexpr (detail::is_csc_view<view_t>::value)
+      return t_offsets[v];
+    else
+      return offsets[v];
   }
+  template <typename view_t = csr_view_type>
   __host__ __device__ __forceinline__ edge_t get_number_of_neighbors(vertex_t const& v) const {
-    return offsets[v + 1] - offsets[v];
+    if constexpr (detail::is_csc_view<view_t>::value)
+      return t_offsets[v + 1] - t_offsets[v];
+    else
+      return offsets[v + 1] - offsets[v];
   }
+  template <typename view_t = csr_view_type>
   __host__ __device__ __forceinline__ vertex_t get_destination_vertex(edge_t const& e) const {
-    return indices[e];
+    if constexpr (detail::is_csc_view<view_t>::value)
+      return owner_of(t_offsets, n_columns, e);
+    else
+      return indices[e];
   }
+  template <typename view_t = csr_view_type>
   __host__ __device__ __forceinline__ weight_t get_edge_weight(edge_t const& e) const {
-    return values[e];
+    if constexpr (detail::is_csc_view<view_t>::value)
+      return t_values[e];
+    else
+      return values[e];
   }
-  /// Largest row r with offsets[r] <= e (binary search, O(log V); graph/csr.hxx:66-81).
+  /// CSR: largest row r with offsets[r] <= e (binary search, O(log V); graph/csr.hxx:66-81).
+  /// CSC: the stored row index (graph/csc.hxx:50-55).
+  template <typename view_t = csr_view_type>
   __host__ __device__ __forceinline__ vertex_t get_source_vertex(edge_t const& e) const {
-    vertex_t lo = 0, hi = n_rows;
-    while (hi - lo > 1) {
-      vertex_t mid = lo + ((hi - lo) >> 1);
-      if (offsets[mid] <= e)
-        lo = mid;
-      else
-        hi = mid;
-    }
-    return lo;
+    if constexpr (detail::is_csc_view<view_t>::value)
+      return t_indices[e];
+    else
+      return owner_of(offsets, n_rows, e);
   }
+  template <typename view_t = csr_view_type>
   __host__ __device__ __forceinline__ vertex_pair_type
   get_source_and_destination_vertices(edge_t const& e) const {
-    return {get_source_vertex(e), get_destination_vertex(e)};
+    return {get_source_vertex<view_t>(e), get_destination_vertex<view_t>(e)};
   }
   /// Edge id of (source, destination) or the invalid id; rows are searched linearly unless sorted.
   __host__ __device__ __forceinline__ edge_t get_edge(vertex_t const& source,
@@ -151,30 +203,53 @@ class graph_t {
   }
 
   /// The B200 kernels' view of the CSR / CSC arrays.
+  /// The kernels index with int32.  Unsigned 32-bit ids / offsets (examples/algorithms/tc/tc.cu:52-54
+  /// uses uint32_t) share the representation for every value a graph that fits the int32 kernels can
+  /// hold, so such a view is reinterpreted, not converted; sizes beyond INT_MAX are rejected.
   b200::csr_view_t csr_view() const {
-    static_assert(std::is_same<vertex_t, int>::value && std::is_same<edge_t, int>::value &&
-                      std::is_same<weight_t, float>::value,
-                  "the sm_100a kernels are built for vertex_t = edge_t = int, weight_t = float "
-                  "(examples/algorithms/bfs/bfs.cu:15-17)");
+    check_kernel_types();
     b200::csr_view_t v;
-    v.n_vertices = n_rows;
-    v.n_edges = n_nonzeros;
-    v.row_offsets = offsets;
-    v.column_indices = indices;
+    v.n_vertices = static_cast<int>(n_rows);
+    v.n_edges = static_cast<int>(n_nonzeros);
+    v.row_offsets = reinterpret_cast<const int*>(offsets);
+    v.column_indices = reinterpret_cast<const int*>(indices);
     v.values = values;
     return v;
   }
   b200::csr_view_t csc_view() const {
+    check_kernel_types();
     b200::csr_view_t v;
-    v.n_vertices = n_columns;
-    v.n_edges = n_nonzeros;
-    v.row_offsets = t_offsets;
-    v.column_indices = t_indices;
+    v.n_vertices = static_cast<int>(n_columns);
+    v.n_edges = static_cast<int>(n_nonzeros);
+    v.row_offsets = reinterpret_cast<const int*>(t_offsets);
+    v.column_indices = reinterpret_cast<const int*>(t_indices);
     v.values = t_values;
     return v;
   }
 
  private:
+  void check_kernel_types() const {
+    static_assert(std::is_integral<vertex_t>::value && sizeof(vertex_t) == 4 &&
+                      std::is_integral<edge_t>::value && sizeof(edge_t) == 4 &&
+                      std::is_same<weight_t, float>::value,
+                  "the sm_100a kernels are built for 32-bit vertex_t / edge_t and weight_t = float "
+                  "(examples/algorithms/bfs/bfs.cu:15-17)");
+    assert(static_cast<unsigned long long>(n_rows) <= 0x7fffffffull &&
+           static_cast<unsigned long long>(n_nonzeros) <= 0x7fffffffull);
+  }
+  /// Largest segment s with offs[s] <= e (e is a valid position, so offs[0] <= e < offs[n]).
+  __host__ __device__ __forceinline__ static vertex_t owner_of(const edge_t* offs, vertex_t n,
+                                                               edge_t const& e) {
+    vertex_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+      vertex_t mid = lo + ((hi - lo) >> 1);
+      if (offs[mid] <= e)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    return lo;
+  }
   vertex_t n_rows = 0, n_columns = 0;
   edge_t n_nonzeros = 0;
   edge_t* offsets = nullptr;
@@ -204,6 +279,14 @@ auto build(graph_properties_t properties,
   G.set(csr);
   G.set_csc(csc);
   return G;
+}
+
+/// csc + csr overload, in the argument order examples/algorithms/spgemm/spgemm.cu:60 uses.
+template <memory_space_t space, typename edge_t, typename vertex_t, typename weight_t>
+auto build(graph_properties_t properties,
+           format::csc_t<space, vertex_t, edge_t, weight_t>& csc,
+           format::csr_t<space, vertex_t, edge_t, weight_t>& csr) {
+  return build<space>(properties, csr, csc);
 }
 
 template <typename graph_type>
