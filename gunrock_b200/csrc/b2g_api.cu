@@ -177,6 +177,10 @@ advance_launch_t to_launch(const b2g_options_t& o) {
   }
   a.hub_threshold = o.hub_threshold > 0 ? o.hub_threshold : 4096;
   a.ctas_per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 8;
+  // experimental merge_path kernels (advance.cuh advance_launch_t::variant), off unless asked for;
+  // read on every call so that one process can compare them
+  if (const char* v = std::getenv("B2G_ADVANCE_VARIANT"))
+    a.variant = std::atoi(v);
   return a;
 }
 

@@ -90,6 +90,24 @@ struct op_needs_source<Op, std::void_t<decltype(Op::kNeedsSource)>>
     : std::integral_constant<bool, Op::kNeedsSource> {};
 constexpr int kBatch = 4;  // 32-edge chunks whose loads are issued back to back per warp
 
+/// Optional `static constexpr bool kVariants = true`: also instantiate the EXPERIMENTAL merge_path
+/// variants (advance_launch_t::variant) for this functor.  Off for user lambdas and for the functors of
+/// the partitioned paths: every variant multiplies the instantiations of the hottest kernel.
+template <typename Op, typename = void>
+struct op_wants_variants : std::false_type {};
+template <typename Op>
+struct op_wants_variants<Op, std::void_t<decltype(Op::kVariants)>>
+    : std::integral_constant<bool, Op::kVariants> {};
+/// Optional snapshot protocol (advance_warp_path_kernel with kSnap): the functor's test-and-set map has
+/// an on-chip copy of its first `snap_bits` bits in shared memory --
+///     const unsigned* snapshot_source() const;                 // the global map the copy is taken from
+///     token_t prefetch_snap(int dst, const unsigned* snap, int snap_bits) const;
+///     bool    commit_snap(int src, int dst, int edge, float w, token_t, unsigned* snap, int snap_bits) const;
+template <typename Op, typename = void>
+struct op_has_snapshot : std::false_type {};
+template <typename Op>
+struct op_has_snapshot<Op, std::void_t<decltype(&Op::prefetch_snap)>> : std::true_type {};
+
 /// Per-warp staging buffer: ballot-compacted appends, flushed with one global atomic.
 template <int kCap, bool kDegSum>
 struct warp_emitter_t {
@@ -765,6 +783,162 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
     atomicAdd(&p.ctrl->edges, static_cast<unsigned long long>(total));
 }
 
+/**
+ * @brief EXPERIMENTAL (advance_launch_t::variant 1 / 2, off by default): merge_path with WARP-PRIVATE
+ * spans -- no block barrier anywhere.
+ *
+ * Why: the ncu capture of advance_merge_path_kernel on the bench graph (profiles/r1_b_merge_path_v5_ncu.md)
+ * shows a latency-bound kernel -- issue slots 43 % busy, L1 40 %, DRAM 12 % -- whose two largest stall
+ * reasons are the scoreboard (10.9 warps per issue) and the three block barriers of every 2048-edge
+ * tile (8.9 warps per issue): whenever one warp of a CTA waits for its probes, the other seven end up
+ * waiting for it at the next barrier.  Here the unit of work is a SPAN of kSpan consecutive edge ranks
+ * owned by one warp: the partition kernel gives the first frontier row of every span, the warp stages
+ * the (at most kSpan) rows that overlap its span in its own slice of shared memory, then walks the span
+ * with the same REDUX row-mask walk as the CTA kernel.  Warps never wait for each other; a warp draws
+ * kTicket spans per atomic.
+ *
+ * kSnap (variant 2, functors with the snapshot protocol only): one 1024-thread CTA per SM keeps the
+ * first `snap_bits` bits of the functor's visited map in shared memory (128 KiB = 2^20 vertices: 58 % of
+ * the edge targets of an RMAT graph, whose low ids are the hubs).  A probe that finds its bit set there
+ * costs a shared-memory access (bank conflicts ~3 cycles per warp) instead of 32 L1 tag lookups; a
+ * probe that does not falls through to the global path and ORs the whole 32-vertex word it read back
+ * into the copy.  Bits only go 0 -> 1, so a stale copy can only send an edge to the global test-and-set
+ * that decides today as well.
+ */
+template <int kThreads, int kMinCtas, int kSpan, int kB, bool kSnap, advance_input_t kIn,
+          advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
+advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, int snap_bits, Op op) {
+  constexpr int kRows = kSpan + 36;  // kSpan ranks overlap at most kSpan non-empty rows (+ 33 sentinels)
+  constexpr int kTicket = 8;         // spans per work-cursor atomic (lanes 0..kTicket hold their first rows)
+  constexpr bool kSrc = op_needs_source<Op>::value;
+  constexpr int kWarpInts = kEmitCap + kRows + (kSrc ? kRows : 0) + kRows / 2;
+  static_assert(kSpan % 32 == 0 && kSpan < 65536 - 64 && kRows % 2 == 0, "span layout");
+  static_assert(!kSnap || op_has_snapshot<Op>::value, "kSnap needs the functor's snapshot protocol");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [snapshot words] then per warp [emit | base | (vert) | rank (16 bit)]
+  unsigned* s_snap = reinterpret_cast<unsigned*>(smem_raw);
+  const int snap_words = kSnap ? (snap_bits >> 5) : 0;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  int* mine = reinterpret_cast<int*>(smem_raw) + snap_words + warp * kWarpInts;
+  int* s_base = mine + kEmitCap;  // (CSR offset of the row's first edge) - (its first rank)
+  int* s_vert = s_base + kRows;   // only when the functor reads its source
+  unsigned short* s_rank =        // first rank of each staged row, relative to the span start
+      reinterpret_cast<unsigned short*>(s_base + kRows + (kSrc ? kRows : 0));
+  const int* __restrict__ ro = p.g.row_offsets;
+  const int* __restrict__ ci = p.g.column_indices;
+  const float* __restrict__ vals = p.g.values;
+  const int n = (kIn == advance_input_t::graph) ? p.g.n_vertices : *p.in_count;
+  if (n == 0)
+    return;  // uniform over the grid: nobody reaches the barrier below
+  if constexpr (kSnap) {
+    const unsigned* gmap = op.snapshot_source();
+    for (int i = threadIdx.x; i < snap_words; i += kThreads)
+      s_snap[i] = ld_relaxed(gmap + i);
+    __syncthreads();  // the only block barrier of the kernel
+  }
+  const int total = scanned[n];
+  const int nspans = (total + kSpan - 1) / kSpan;
+  warp_emitter_t<kEmitCap, kDegSum> em;
+  em.init(mine, p.out, p.out_count, p.out_capacity, ro, p.ctrl);
+
+  for (;;) {
+    int first = 0;
+    if (lane == 0)
+      first = atomicAdd(&p.ctrl->work, kTicket);
+    first = __shfl_sync(kFull, first, 0);
+    if (first >= nspans)
+      break;
+    const int last = min(nspans, first + kTicket);
+    // p.tile_rows[k] = row holding rank k * kSpan (n past the end): entries 0 .. nspans exist
+    const int my_row = (first + lane <= last) ? p.tile_rows[first + lane] : 0;
+    for (int sp = first; sp < last; ++sp) {
+      const int row0 = __shfl_sync(kFull, my_row, sp - first);
+      const int row1 = min(n - 1, __shfl_sync(kFull, my_row, sp - first + 1));
+      const int r_begin = sp * kSpan;
+      const int r_end = min(total, r_begin + kSpan);
+      // ---- stage the rows that overlap [r_begin, r_end) ------------------------------------
+      int nrows = 0;  // warp-uniform
+      for (int i0 = row0; i0 <= row1; i0 += 32) {
+        const int i = i0 + lane;
+        int sc = 0, rb = 0, vv = 0;
+        bool live = false;
+        if (i <= row1) {
+          sc = scanned[i];
+          const int sc_next = scanned[i + 1];
+          rb = p.row_base[i];
+          if (kSrc)
+            vv = (kIn == advance_input_t::graph) ? i : p.in[i];
+          live = sc_next > sc && sc < r_end && sc_next > r_begin;
+        }
+        const unsigned m = __ballot_sync(kFull, live);
+        if (live) {
+          const int slot = nrows + __popc(m & lanemask_lt());
+          s_rank[slot] = static_cast<unsigned short>(max(sc, r_begin) - r_begin);
+          s_base[slot] = rb - sc;
+          if (kSrc)
+            s_vert[slot] = vv;
+        }
+        nrows += __popc(m);
+      }
+      s_rank[nrows + lane] = static_cast<unsigned short>(r_end - r_begin);  // sentinels
+      if (lane == 0)
+        s_rank[nrows + 32] = static_cast<unsigned short>(r_end - r_begin);
+      __syncwarp();
+      // ---- walk: slot 0 is the row that holds rank r_begin, the cursor only moves forward ----
+      int a = 0;
+      for (int r0 = r_begin; r0 < r_end; r0 += 32 * kB) {
+        int row[kB], e[kB], nb[kB], u[kB];
+        float w[kB];
+        bool valid[kB], keep[kB];
+        typename op_traits<Op>::token_t tok[kB];
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+          const int rk = r0 + 32 * k;
+          int nxt = static_cast<int>(s_rank[min(a + 1 + lane, nrows + 32)]) + r_begin - rk;
+          unsigned bit = (nxt >= 0 && nxt < 32) ? (1u << nxt) : 0u;
+          unsigned starts = __reduce_or_sync(kFull, bit);
+          row[k] = min(a + __popc(starts & (0xffffffffu >> (31 - lane))), nrows - 1);
+          valid[k] = rk + lane < r_end;
+          a += __popc(starts);
+        }
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+          u[k] = kSrc ? s_vert[row[k]] : -1;
+          e[k] = s_base[row[k]] + r0 + 32 * k + lane;
+          nb[k] = valid[k] ? ld_stream(ci + e[k]) : -1;
+          w[k] = (kWeights && vals && valid[k]) ? ld_stream(vals + e[k]) : 1.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < kB; ++k)
+          if (valid[k]) {
+            if constexpr (kSnap)
+              tok[k] = op.prefetch_snap(nb[k], s_snap, snap_bits);
+            else
+              tok[k] = op_prefetch(op, nb[k]);
+          }
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+          if constexpr (kSnap)
+            keep[k] = valid[k] && op.commit_snap(u[k], nb[k], e[k], w[k], tok[k], s_snap, snap_bits);
+          else
+            keep[k] = valid[k] && op_commit(op, u[k], nb[k], e[k], w[k], tok[k]);
+        }
+        if (kOut != advance_output_t::none) {
+#pragma unroll
+          for (int k = 0; k < kB; ++k)
+            em.push(keep[k], kOut == advance_output_t::edges ? e[k] : op_emit(op, nb[k]));
+        }
+      }
+      __syncwarp();  // every lane is done with this span's rows before the next span restages them
+    }
+  }
+  if (kOut != advance_output_t::none)
+    em.flush();
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&p.ctrl->edges, static_cast<unsigned long long>(total));
+}
+
 /// Report of advance_tail_kernel (written to pinned host memory by the kernel).
 struct tail_report_t {
   int levels;    // levels executed by this launch
@@ -915,7 +1089,22 @@ struct advance_launch_t {
   long long mid_frontier_edges = 1 << 20;
   /// block_mapped: average out-degree of the frontier if the caller knows it (0 = unknown).
   double avg_degree = 0.0;
+  /// EXPERIMENTAL merge_path variants (0 = the measured default kernel).  Only functors that opt in
+  /// (`kVariants`) have them; everything else ignores the field.
+  ///   1  warp-private spans (advance_warp_path_kernel), 256-thread CTAs, 4 chunks in flight, registers
+  ///      capped for 6 CTAs per SM (the occupancy of the default kernel); variant 4: capped for 4
+  ///   2  warp-private spans, one 1024-thread CTA per SM, 8 chunks in flight, shared-memory snapshot of
+  ///      the visited map (functors with the snapshot protocol; others run variant 1)
+  ///   3  the default CTA kernel with 4096-edge tiles (half the block barriers per edge)
+  ///   4  warp-private spans, 256-thread CTAs, 8 chunks in flight
+  int variant = 0;
 };
+
+/// Shared-memory ints one warp of advance_warp_path_kernel owns (must match the kernel's layout).
+template <int kSpan, bool kSrc>
+constexpr int warp_path_ints() {
+  return kEmitCap + (kSpan + 36) + (kSrc ? (kSpan + 36) : 0) + (kSpan + 36) / 2;
+}
 
 /// Allocate, once, everything launch_advance may need for frontiers of up to `n_upper_bound` rows of
 /// `g`, so that a later run performs no cudaMalloc / cudaFree (both synchronise the device, which a
@@ -958,6 +1147,85 @@ inline const int* frontier_degree_scan(workspace_t& ws,
 
 inline bool aligned16(const void* p) {
   return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+/// merge_path proper: partition into kTile-edge tiles, then the CTA kernel.
+/// Ranks are int32 (as in the reference, merge_path.hxx:325-327), so 2^31/kTile tiles bound every
+/// possible frontier, duplicates included.
+template <int kTile, advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
+inline void launch_merge_path_tiles(workspace_t& ws, advance_params_t& p, const int* scanned,
+                                    bool graph_in, int grid, Op op) {
+  constexpr int kThreads = 256;
+  const int sms = device_info_t::get().sm_count;
+  int* tile_rows = ws.tile_rows.ensure((static_cast<size_t>(1) << 31) / kTile + 4);
+  merge_path_partition_kernel<kTile><<<sms, 256, 0, ws.stream>>>(scanned, p.in_count, p.g.n_vertices,
+                                                                 tile_rows);
+  p.tile_rows = tile_rows;
+  p.ctrl = ws.next_ctrl();
+  if (graph_in)
+    advance_merge_path_kernel<kThreads, kTile, advance_input_t::graph, kOut, kDegSum, kWeights>
+        <<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
+  else
+    advance_merge_path_kernel<kThreads, kTile, advance_input_t::vertices, kOut, kDegSum, kWeights>
+        <<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
+}
+
+/// EXPERIMENTAL variants 1 / 2 / 4: span partition + advance_warp_path_kernel.
+template <advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
+inline void launch_warp_path(workspace_t& ws, advance_params_t& p, const int* scanned, bool graph_in,
+                             const advance_launch_t& cfg, Op op) {
+  constexpr int kSpan = 256;
+  constexpr bool kSrc = op_needs_source<Op>::value;
+  constexpr int kWarpBytes = warp_path_ints<kSpan, kSrc>() * 4;
+  const int sms = device_info_t::get().sm_count;
+  int* span_rows = ws.tile_rows.ensure((static_cast<size_t>(1) << 31) / kSpan + 4);
+  // 8x the tiles of the CTA kernel: a full wave of searchers instead of one CTA per SM
+  merge_path_partition_kernel<kSpan><<<sms * 8, 256, 0, ws.stream>>>(scanned, p.in_count,
+                                                                     p.g.n_vertices, span_rows);
+  p.tile_rows = span_rows;
+  p.ctrl = ws.next_ctrl();
+  constexpr auto kGraph = advance_input_t::graph;
+  constexpr auto kVerts = advance_input_t::vertices;
+  if constexpr (op_has_snapshot<Op>::value) {
+    if (cfg.variant == 2) {
+      constexpr int kThreads = 1024;
+      const int v_bits = ((p.g.n_vertices + 31) / 32) * 32;
+      const int snap_bits = v_bits < (1 << 20) ? v_bits : (1 << 20);
+      const int smem = (snap_bits / 32) * 4 + (kThreads / 32) * kWarpBytes;
+      auto kg = advance_warp_path_kernel<kThreads, 1, kSpan, 8, true, kGraph, kOut, kDegSum, kWeights, Op>;
+      auto kv = advance_warp_path_kernel<kThreads, 1, kSpan, 8, true, kVerts, kOut, kDegSum, kWeights, Op>;
+      static thread_local int attr_device = -1;  // opt in to > 48 KiB of dynamic shared memory, once per device
+      if (attr_device != device_info_t::get().device) {
+        const int most = device_info_t::get().max_smem_optin;
+        B2G_CHECK(cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+        B2G_CHECK(cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+        attr_device = device_info_t::get().device;
+      }
+      if (graph_in)
+        kg<<<sms, kThreads, smem, ws.stream>>>(p, scanned, snap_bits, op);
+      else
+        kv<<<sms, kThreads, smem, ws.stream>>>(p, scanned, snap_bits, op);
+      return;
+    }
+  }
+  constexpr int kThreads = 256;
+  const int smem = (kThreads / 32) * kWarpBytes;
+  const int grid = sms * cfg.ctas_per_sm;
+  if (cfg.variant == 4) {
+    if (graph_in)
+      advance_warp_path_kernel<kThreads, 4, kSpan, 8, false, kGraph, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, op);
+    else
+      advance_warp_path_kernel<kThreads, 4, kSpan, 8, false, kVerts, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, op);
+  } else {
+    if (graph_in)
+      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, false, kGraph, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, op);
+    else
+      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, false, kVerts, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, op);
+  }
 }
 
 /**
@@ -1003,19 +1271,18 @@ inline void launch_advance(workspace_t& ws,
     const int* scanned = graph_in ? g.row_offsets
                                   : frontier_degree_scan(ws, g, in, in_count, in_upper_bound, &row_base);
     p.row_base = row_base;
-    // ranks are int32 (as in the reference, merge_path.hxx:325-327), so 2^31/kTile tiles bound
-    // every possible frontier, duplicates included.
-    int* tile_rows = ws.tile_rows.ensure((static_cast<size_t>(1) << 31) / kTile + 4);
-    merge_path_partition_kernel<kTile><<<sms, 256, 0, ws.stream>>>(scanned, in_count, g.n_vertices,
-                                                                   tile_rows);
-    p.tile_rows = tile_rows;
-    p.ctrl = ws.next_ctrl();
-    if (graph_in)
-      advance_merge_path_kernel<kThreads, kTile, advance_input_t::graph, kOut, kDegSum, kWeights>
-          <<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
-    else
-      advance_merge_path_kernel<kThreads, kTile, advance_input_t::vertices, kOut, kDegSum,
-                                kWeights><<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
+    bool launched = false;
+    if constexpr (op_wants_variants<Op>::value) {
+      if (cfg.variant == 3) {
+        launch_merge_path_tiles<4096, kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, grid, op);
+        launched = true;
+      } else if (cfg.variant != 0) {
+        launch_warp_path<kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, cfg, op);
+        launched = true;
+      }
+    }
+    if (!launched)
+      launch_merge_path_tiles<kTile, kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, grid, op);
   } else {
     p.ctrl = ws.next_ctrl();
     p.hub_threshold = cfg.hub_threshold < 32 ? 32 : cfg.hub_threshold;

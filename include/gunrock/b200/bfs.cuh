@@ -53,6 +53,34 @@ struct bfs_claim_op {
     dist[dst] = next_level;
     return true;
   }
+  // ---- experimental kernel variants (advance_launch_t::variant; off by default) --------------------
+  static constexpr bool kVariants = true;
+  /// snapshot protocol (advance.cuh op_has_snapshot): the first `snap_bits` bits of `visited` have a
+  /// copy in shared memory.  A bit found set there needs no global probe; the token is then just that
+  /// bit, so that commit neither claims nor learns anything from it.
+  __device__ __forceinline__ const unsigned* snapshot_source() const { return visited; }
+  __device__ __forceinline__ unsigned prefetch_snap(int dst, const unsigned* snap, int snap_bits) const {
+    const unsigned bit = 1u << (dst & 31);
+    if (dst < snap_bits && (snap[dst >> 5] & bit))
+      return bit;
+    return ld_cached(visited + (dst >> 5));
+  }
+  __device__ __forceinline__ bool commit_snap(int, int dst, int, float, unsigned word, unsigned* snap,
+                                              int snap_bits) const {
+    const unsigned bit = 1u << (dst & 31);
+    bool won = false;
+    if (!(word & bit)) {
+      word = atomicOr(visited + (dst >> 5), bit);  // the word as it was: 32 vertices' worth of news
+      won = !(word & bit);
+      word |= bit;
+      if (won)
+        dist[dst] = next_level;
+    }
+    // whatever global state this edge saw goes into the on-chip copy (monotone: bits only get set)
+    if (dst < snap_bits && (word & ~snap[dst >> 5]))
+      atomicOr(snap + (dst >> 5), word);
+    return won;
+  }
 };
 
 /// Builds the claim functor of a given level (advance_tail_kernel runs several levels per launch).

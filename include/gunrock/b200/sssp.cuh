@@ -40,6 +40,7 @@ __device__ __forceinline__ float atomic_min_float(float* addr, float value) {
 }
 
 struct sssp_relax_op {
+  static constexpr bool kVariants = true;  // experimental merge_path variants (advance_launch_t::variant)
   float* dist;
   int* stamp;
   int iteration;

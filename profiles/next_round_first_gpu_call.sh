@@ -5,13 +5,30 @@
 set -u
 OUT=gpurun_out/next_round
 mkdir -p "$OUT"
-# 1. GPU tests written after the last GPU run (pygunrock surface) + the whole suite
+# 1. GPU tests written after the last GPU run (pygunrock surface, tc / spgemm / mst examples) + the whole suite
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -5 | tee "$OUT/pytest_gpu.txt"
 # 2. experimental near/far SSSP: bit-exactness first, then its time against the default schedule
 B2G_RUN_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -m gpu -q 2>&1 | tail -5 | tee "$OUT/pytest_experimental.txt"
 for d in "" 8 16; do
   B2G_SSSP_DELTA=$d python bench.py --workload sssp_rmat24 --lb merge_path --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/sssp_delta_${d:-off}.json"
 done
+# 2b. experimental merge_path kernels (advance.cuh advance_launch_t::variant): default vs warp-private spans
+#     (1: 6 CTAs/SM, 4: more loads in flight), warp-private + shared-memory visited snapshot (2), 4096-edge tiles (3)
+for v in 0 1 2 3 4; do
+  B2G_ADVANCE_VARIANT=$v python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/bfs_push_variant_$v.json"
+  B2G_ADVANCE_VARIANT=$v python bench.py --workload sssp_rmat24 --lb merge_path --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/sssp_variant_$v.json"
+  python - "$OUT" $v <<'PY'
+import json, sys
+out, v = sys.argv[1], sys.argv[2]
+for w in ("bfs_push", "sssp"):
+    try:
+        j = json.loads(open(f"{out}/{w}_variant_{v}.json").read())
+        print(f"variant {v} {w}: {j['value']:.0f} MTEPS, {j['ms_per_step']:.3f} ms/step, roofline {j['roofline']['frac']:.3f}, "
+              f"level ms {j['config']['level_kernel_ms'][:6]}")
+    except Exception as ex:
+        print(f"variant {v} {w}: no line ({ex})")
+PY
+done | tee "$OUT/variants.txt"
 # 3. design input for the on-chip visited map: probe rates of L1 / L2 / shared / DSMEM
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o "$OUT/probe_rates" profiles/micro/probe_rates.cu && "$OUT/probe_rates" | tee "$OUT/probe_rates.txt"
 # 4. the default bench line (hub sources for N > 1 are measured by the 2-GPU call of the round)

@@ -57,3 +57,94 @@ def test_sssp_near_far_schedule_is_bit_exact(built, delta):
     if float(delta) <= 8:
         big = [k for k in out[delta] if k.startswith("s14") or k.startswith("s15")]
         assert sum(out[delta][k][2] for k in big) < sum(out[""][k][2] for k in big)     # less work
+
+
+# ---- experimental merge_path kernels (B2G_ADVANCE_VARIANT, read on every call) ------------------------
+@pytest.fixture
+def variant_env():
+    old = os.environ.get("B2G_ADVANCE_VARIANT")
+    yield lambda v: os.environ.__setitem__("B2G_ADVANCE_VARIANT", str(v))
+    if old is None:
+        os.environ.pop("B2G_ADVANCE_VARIANT", None)
+    else:
+        os.environ["B2G_ADVANCE_VARIANT"] = old
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+def test_merge_path_variants_one_level_exact(built, variant_env, variant):
+    """One advance level with the BFS claim functor through b2g_advance_bfs, merge_path, for frontiers that
+    stress the span staging: two hubs, every vertex (degree-0 rows included), duplicates, a single short
+    row, vertices beyond the 2^20-bit snapshot.  Each unvisited neighbour is claimed exactly once."""
+    import numpy as np
+    import torch
+    import oracle
+    import gunrock_b200 as gb
+    variant_env(variant)
+    INT_MAX = 2**31 - 1
+    rng = np.random.default_rng(variant)
+    for scale, ef, seed in ((12, 8, 13), (16, 16, 5), (21, 2, 99)):     # 2^21 vertices: ids past the snapshot
+        ro, ci = oracle.rmat_csr(scale, ef, seed)
+        V = 1 << scale
+        G = gb.graph_t.from_csr(ro, ci, None, symmetric=True)
+        deg = np.diff(ro)
+        frontiers = [np.argsort(-deg)[:2], np.arange(V), np.flatnonzero(deg == 0)[:100],
+                     np.flatnonzero(deg == 1)[:1], np.repeat(np.argsort(-deg)[:50], 3),
+                     rng.integers(V // 2, V, 5000)]
+        for f0 in frontiers:
+            f0 = f0.astype(np.int32)
+            if len(f0) == 0:
+                continue
+            vis = np.zeros((V + 31) // 32 + 4, np.uint32)
+            pre = rng.integers(0, V, V // 7)                             # some vertices already visited
+            np.bitwise_or.at(vis, pre >> 5, (np.uint32(1) << (pre & 31).astype(np.uint32)))
+            t_vis = torch.from_numpy(vis.view(np.int32).copy()).cuda()
+            t_lab = torch.full((V,), INT_MAX, dtype=torch.int32, device="cuda")
+            t_f = torch.from_numpy(f0).cuda()
+            t_fc = torch.tensor([len(f0)], dtype=torch.int32, device="cuda")
+            cap = int(min(deg[f0].astype(np.int64).sum(), V)) + 64
+            t_o = torch.empty(cap, dtype=torch.int32, device="cuda")
+            t_oc = torch.zeros(1, dtype=torch.int32, device="cuda")
+            e = gb.advance_bfs(G, t_f, t_fc, t_o, t_oc, t_vis, t_lab, 7,
+                               gb.options_t(advance_load_balance=gb.load_balance_t.merge_path))
+            assert e == int(deg[f0].astype(np.int64).sum())
+            in_f = np.zeros(V, bool)
+            in_f[f0] = True
+            nb = np.unique(ci[np.repeat(in_f, deg)]).astype(np.int64)   # neighbours of the frontier's rows
+            was = (vis[nb >> 5] >> (nb & 31).astype(np.uint32)) & 1
+            exp = nb[was == 0]
+            n = int(t_oc.item())
+            got = np.sort(t_o[:n].cpu().numpy())
+            assert np.array_equal(got, exp), (scale, len(f0), n, len(exp))
+            lab = t_lab.cpu().numpy()
+            assert (lab == 7).sum() == len(exp) and np.all(lab[exp] == 7)
+            vis2 = t_vis.cpu().numpy().view(np.uint32)
+            np.bitwise_or.at(vis, exp >> 5, (np.uint32(1) << (exp & 31).astype(np.uint32)))
+            assert np.array_equal(vis2, vis)
+        G.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+def test_merge_path_variants_full_runs_bit_exact(built, variant_env, variant):
+    """Whole BFS / SSSP runs at a size where the enactors really pick merge_path (frontier out-degree
+    above 2^20): depths / distances equal to the default kernels' bit for bit, and to the oracle."""
+    import numpy as np
+    import oracle
+    import gunrock_b200 as gb
+    ro, ci = oracle.rmat_csr(18, 16, 0x5EED22)
+    w = oracle.edge_weights(3, ro, ci, True)
+    G = gb.graph_t.from_csr(ro, ci, w, symmetric=True)
+    src = int(np.diff(ro).argmax())
+    opt = gb.options_t(advance_load_balance=gb.load_balance_t.merge_path)
+    d0, f0 = np.empty(G.n_vertices, np.int32), np.empty(G.n_vertices, np.float32)
+    os.environ.pop("B2G_ADVANCE_VARIANT", None)
+    gb.bfs(G, src, d0, options=opt)
+    gb.sssp(G, src, f0, options=opt)
+    variant_env(variant)
+    d1, f1 = np.empty_like(d0), np.empty_like(f0)
+    st = gb.bfs(G, src, d1, options=opt)
+    gb.sssp(G, src, f1, options=opt)
+    assert max(st.level_edges) > (1 << 20)                     # merge_path was in play
+    assert np.array_equal(d0, d1) and np.array_equal(d1, oracle.bfs(ro, ci, src))
+    assert np.array_equal(f0.view(np.uint32), f1.view(np.uint32))
+    assert np.array_equal(f1.view(np.uint32), oracle.sssp(ro, ci, w, src).view(np.uint32))
+    G.close()
