@@ -173,6 +173,39 @@ def bench_source(ro):
     return int(deg.argmax())
 
 
+def reference_gpu_leg(G, wl, src, edges_per_run, runs=5):
+    """Times oracle/_ref/gunrock_ref_gpu (the unmodified reference GPU path) on the bench graph."""
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "gunrock_ref_gpu")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/gunrock_ref_gpu not built (needs /root/reference at build time)"}
+    ro, ci, w = G.download()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "graph.csr")
+        with open(path, "wb") as f:               # formats/csr.hxx:193-228: rows, cols, nnz, offsets, indices, values
+            np.array([len(ro) - 1, len(ro) - 1, len(ci)], np.int32).tofile(f)
+            ro.tofile(f)
+            ci.tofile(f)
+            (w if w is not None else np.ones(len(ci), np.float32)).tofile(f)
+        out = {}
+        for lb in ("block_mapped", "merge_path"):
+            cmd = [exe, wl["alg"], path, str(src), str(runs), lb]
+            if wl["alg"] != "pr" and len(ci) <= 200_000_000 and lb == "block_mapped":
+                cmd.append("validate")            # its own CPU validator, once
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
+            if r.returncode != 0:
+                out[lb] = {"error": (r.stderr or r.stdout)[-300:]}
+                continue
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            ms = sorted(j["ms"][1:] or j["ms"])   # first run pays the lazy module load
+            out[lb] = {"ms_median": statistics.median(ms), "ms_best": ms[0], "runs": len(j["ms"]),
+                       "errors_vs_reference_cpu": j["errors"],
+                       "mteps": (edges_per_run / statistics.median(ms) / 1e3) if wl["alg"] != "pr" else None}
+    return {"kind": "unmodified reference GPU kernels, nvcc sm_100a, -include oracle/ref_gpu_fix.h, SM_TARGET=90",
+            "numerator": "edges touched by OUR run of the same traversal (bfs / sssp); pr: time per solve only",
+            **out}
+
+
 def run_reference(args, wl, name):
     """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -323,6 +356,9 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="partitioned workloads: frontier exchange by our kernels over peer memory, or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-gpu", action="store_true",
+                    help="also time the UNMODIFIED reference GPU kernels (oracle/_ref/gunrock_ref_gpu, built for "
+                         "sm_100a with the atomics fix of SURVEY.md F2) on the same graph and GPU; N = 1 only")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -496,6 +532,15 @@ def main():
         except Exception as ex:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": "MTEPS", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 
+    # Optional second baseline row: the reference's own GPU implementation on this GPU,
+    # same graph (written once in the reference's .csr layout), same source, its own enactor timer.
+    ref_gpu = None
+    if args.reference_gpu and world == 1:
+        try:
+            ref_gpu = reference_gpu_leg(G, wl, src, agg["edges"] // args.steps)
+        except Exception as ex:
+            ref_gpu = {"error": str(ex)}
+
     # best / median of the runs (the reference's timed region: CUDA events around enact()),
     # and the mean over 16 random sources of degree > 0 (RNG seed 1).  Extras: they never take the line down.
     runs = None
@@ -546,6 +591,8 @@ def main():
                      "kernel_ms_total": agg["kern_ms"]},
         "cpu_baseline": cpu, "clocks": clocks, "wall_ms": wall_ms,
     }
+    if ref_gpu is not None:
+        line["reference_gpu"] = ref_gpu
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

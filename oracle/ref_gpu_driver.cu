@@ -1,0 +1,110 @@
+// oracle/ref_gpu_driver.cu -- TEST INFRASTRUCTURE ONLY (never shipped, never on the product path).
+//
+// The UNMODIFIED reference GPU implementation (gunrock::{bfs,sssp,pr}::run and the operators under
+// /root/reference/include) compiled for sm_100a from where its sources lie, behind a small command
+// line so that bench.py can time "the reference's own kernels on this very GPU" next to ours
+// (optional second baseline row).  Built by `make -C oracle ref_gpu` into
+// oracle/_ref/gunrock_ref_gpu with -include ref_gpu_fix.h and -DSM_TARGET=90 (F3).
+//
+//   gunrock_ref_gpu <bfs|sssp|pr> <graph.csr> <source> <runs> <load_balance> [validate]
+//
+// graph.csr is the reference's own binary layout (formats/csr.hxx:142-228).  Prints one JSON line:
+// per-run milliseconds as returned by run() (the enactor's own timer, enactor.hxx:266-288) and, with
+// `validate`, the number of mismatches against the reference CPU validators.
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include <gunrock/algorithms/bfs.hxx>
+#include <gunrock/algorithms/pr.hxx>
+#include <gunrock/algorithms/sssp.hxx>
+
+#include "bfs_cpu.hxx"
+#include "sssp_cpu.hxx"
+
+using namespace gunrock;
+using namespace memory;
+
+using vertex_t = int;
+using edge_t = int;
+using weight_t = float;
+
+int main(int argc, char** argv) {
+  if (argc < 6) {
+    std::fprintf(stderr, "usage: %s <bfs|sssp|pr> <graph.csr> <source> <runs> <load_balance> [validate]\n", argv[0]);
+    return 2;
+  }
+  const std::string alg = argv[1], file = argv[2], lb_name = argv[5];
+  vertex_t source = std::atoi(argv[3]);  // the validators take it by non-const reference
+  const int runs = std::atoi(argv[4]);
+  const bool validate = argc > 6 && std::string(argv[6]) == "validate";
+
+  using csr_t = format::csr_t<memory_space_t::device, vertex_t, edge_t, weight_t>;
+  csr_t csr;
+  csr.read_binary(file);
+  graph::graph_properties_t properties;
+  auto G = graph::build<memory_space_t::device>(properties, csr);
+  const vertex_t V = G.get_number_of_vertices();
+
+  gunrock::options_t options;
+  if (lb_name == "merge_path")
+    options.advance_load_balance = operators::load_balance_t::merge_path;
+  else if (lb_name == "thread_mapped")
+    options.advance_load_balance = operators::load_balance_t::thread_mapped;
+  else
+    options.advance_load_balance = operators::load_balance_t::block_mapped;
+
+  auto context = std::make_shared<gcuda::multi_context_t>(0);
+  std::vector<float> ms;
+  long long errors = -1;
+  if (alg == "bfs") {
+    thrust::device_vector<vertex_t> distances(V), predecessors(V);
+    for (int r = 0; r < runs; ++r) {
+      bfs::param_t<vertex_t> param(source, options);
+      bfs::result_t<vertex_t> result(distances.data().get(), predecessors.data().get());
+      ms.push_back(bfs::run(G, param, result, context));
+    }
+    if (validate) {
+      thrust::host_vector<vertex_t> h(distances), exp(V), pred(V);
+      bfs_cpu::run<csr_t, vertex_t, edge_t>(csr, source, exp.data(), pred.data());
+      errors = 0;
+      for (vertex_t v = 0; v < V; ++v)
+        errors += h[v] != exp[v];
+    }
+  } else if (alg == "sssp") {
+    thrust::device_vector<weight_t> distances(V);
+    thrust::device_vector<vertex_t> predecessors(V);
+    for (int r = 0; r < runs; ++r) {
+      sssp::param_t<vertex_t> param(source, options);
+      sssp::result_t<vertex_t, weight_t> result(distances.data().get(), predecessors.data().get(), V);
+      ms.push_back(sssp::run(G, param, result, context));
+    }
+    if (validate) {
+      thrust::host_vector<weight_t> h(distances), exp(V);
+      thrust::host_vector<vertex_t> pred(V);
+      sssp_cpu::run<csr_t, vertex_t, edge_t, weight_t>(csr, source, exp.data(), pred.data());
+      errors = 0;
+      for (vertex_t v = 0; v < V; ++v)
+        errors += h[v] != exp[v];
+    }
+  } else if (alg == "pr") {
+    thrust::device_vector<weight_t> p(V);
+    for (int r = 0; r < runs; ++r) {
+      pr::param_t<weight_t> param(0.85f, 1e-6f, options);
+      pr::result_t<weight_t> result(p.data().get());
+      ms.push_back(pr::run(G, param, result, context));
+    }
+  } else {
+    std::fprintf(stderr, "unknown algorithm %s\n", alg.c_str());
+    return 2;
+  }
+  context->get_context(0)->synchronize();
+  std::printf("{\"impl\": \"reference_gpu\", \"algorithm\": \"%s\", \"load_balance\": \"%s\", \"vertices\": %d, "
+              "\"edges\": %d, \"source\": %d, \"errors\": %lld, \"ms\": [",
+              alg.c_str(), lb_name.c_str(), (int)V, (int)G.get_number_of_edges(), (int)source, errors);
+  for (size_t i = 0; i < ms.size(); ++i)
+    std::printf("%s%.4f", i ? ", " : "", ms[i]);
+  std::printf("]}\n");
+  return 0;
+}

@@ -29,6 +29,9 @@ for w in ("bfs_push", "sssp"):
         print(f"variant {v} {w}: no line ({ex})")
 PY
 done | tee "$OUT/variants.txt"
+# 2c. same-GPU baseline: the UNMODIFIED reference GPU kernels (oracle/_ref/gunrock_ref_gpu) on the bench graph
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --reference-gpu 2>&1 | tail -1 > "$OUT/bench_with_reference_gpu.json"
+python -c "import json,sys; j=json.load(open('$OUT/bench_with_reference_gpu.json')); print('ours', round(j['value']), 'MTEPS; reference GPU:', json.dumps(j.get('reference_gpu'))[:600])" | tee "$OUT/reference_gpu.txt"
 # 3. design input for the on-chip visited map: probe rates of L1 / L2 / shared / DSMEM
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o "$OUT/probe_rates" profiles/micro/probe_rates.cu && "$OUT/probe_rates" | tee "$OUT/probe_rates.txt"
 # 4. the default bench line (hub sources for N > 1 are measured by the 2-GPU call of the round)
