@@ -7,7 +7,8 @@
 #     instead of the fused enactors)                        -> bin/{bfs,sssp,pr}_ops
 #  3. the reference's own algorithm headers (algorithms/{bfs,sssp,pr}.hxx) on our framework /
 #     operator headers                                      -> bin/ref_algorithms
-#  0. (no reference needed) examples/api_selftest.cu -> bin/api_selftest
+#  0. (no reference needed) examples/api_selftest.cu -> bin/api_selftest,
+#     examples/dense_frontier_selftest.cu (bitmap / boolmap frontier views) -> bin/dense_frontier_selftest
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 REF=${REF:-/root/reference}
@@ -16,6 +17,7 @@ mkdir -p "$OUT"
 FLAGS="-std=c++17 -O3 -lineinfo --extended-lambda --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -I$ROOT/include -diag-suppress 20050"
 pids=()
 nvcc $FLAGS -o "$OUT/api_selftest" "$ROOT/examples/api_selftest.cu" & pids+=($!)
+nvcc $FLAGS -o "$OUT/dense_frontier_selftest" "$ROOT/examples/dense_frontier_selftest.cu" & pids+=($!)
 if [ ! -d "$REF" ]; then
   rc=0; for p in "${pids[@]}"; do wait $p || rc=1; done; exit $rc
 fi

@@ -274,3 +274,6 @@ class frontier_t {
 
 }  // namespace frontier
 }  // namespace gunrock
+
+// bitmap / boolmap views: partial specialisations of frontier_t
+#include <gunrock/framework/frontier/dense_frontier.hxx>

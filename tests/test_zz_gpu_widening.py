@@ -1,6 +1,6 @@
 """Widening rows that were built after the round's last GPU run (tc, spgemm, mst -- the
 reference's own algorithm headers and UNCHANGED example programs on this repository's framework /
-operator headers).  The file sorts last on purpose: `pytest -x` reaches it only after every parity test
+operator headers; N3: the dense bitmap / boolmap frontier views).  The file sorts last on purpose: `pytest -x` reaches it only after every parity test
 of the hot path has run."""
 import os
 import re
@@ -27,6 +27,13 @@ def run(cmd, timeout=120):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout
+
+
+def test_dense_frontier_views_selftest():
+    """frontier_t<..., bitmap> / <..., boolmap> (host operations, device accessors,
+    conversion from / to the vector view, one BFS level with a bitmap output frontier)."""
+    out = run([need("dense_frontier_selftest")])
+    assert "ALL OK" in out, out[-2000:]
 
 
 def write_symmetric_mtx(path, ro, ci, w=None):
