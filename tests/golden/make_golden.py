@@ -81,6 +81,26 @@ def main():
                          weights_sha256=sha(w), sources=srcs,
                          bfs={str(s): g.bfs(s)[0].tolist() for s in srcs},
                          sssp={str(s): f32_hex(g.sssp(s)[0]) for s in srcs})
+    # 5. the reference's second vendored dataset: bips98_606.mtx (real general, 7135 vertices, 34738
+    #    entries, DIRECTED, explicit diagonal, negative values).  Loader + from_coo + bfs_cpu as they are;
+    #    for SSSP the weights are |value| (the validator, like the GPU algorithm, needs weights >= 0).
+    #    Stored as a compressed .npz next to this file (the arrays would triple golden.json).
+    path = os.path.join(REF, "datasets/bips98_606/bips98_606.mtx")
+    m = oracle.ref_load_mtx(path)
+    ro, ci, v = oracle.ref_csr_from_coo(m["n_rows"], m["n_cols"], m["I"], m["J"], m["V"])
+    wabs = np.abs(v).astype(np.float32)
+    g = oracle.RefGraph(ro, ci, wabs)
+    deg = np.diff(ro)
+    srcs = [0, int(deg.argmax()), int(m["n_rows"] - 1)]
+    arrays = dict(row_offsets=ro, column_indices=ci, values_bits=v.view(np.uint32),
+                  props=np.array([m["directed"], m["weighted"], m["symmetric"]], np.int32),
+                  sources=np.array(srcs, np.int32))
+    for s in srcs:
+        arrays[f"bfs_{s}"] = g.bfs(s)[0]
+        arrays[f"sssp_abs_bits_{s}"] = np.ascontiguousarray(g.sssp(s)[0], np.float32).view(np.uint32)
+    np.savez_compressed(os.path.join(HERE, "bips98_606.npz"), **arrays)
+    print("wrote bips98_606.npz", os.path.getsize(os.path.join(HERE, "bips98_606.npz")), "bytes; sources", srcs)
+
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print("wrote", os.path.join(HERE, "golden.json"), os.path.getsize(os.path.join(HERE, "golden.json")), "bytes")

@@ -3,6 +3,7 @@ unmodified reference (tests/golden/make_golden.py) and, where oracle/_ref exists
 compiled reference itself."""
 import hashlib
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -189,3 +190,43 @@ def test_restatement_matches_compiled_reference():
     b = oracle.ref_csr_from_coo(n, n, I, J, V)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+# ---- the reference's second vendored dataset: bips98_606.mtx (directed, real, negative values) ----------
+@pytest.fixture(scope="module")
+def bips98():
+    return np.load(os.path.join(ROOT, "tests", "golden", "bips98_606.npz"))
+
+
+def test_bips98_restatement_matches_the_reference_outputs(bips98):
+    """tests/golden/bips98_606.npz was minted by the compiled reference (loader, from_coo, bfs_cpu, sssp_cpu
+    on |value|); the C restatement must reproduce every stored depth / distance bit for bit."""
+    ro, ci = bips98["row_offsets"], bips98["column_indices"]
+    w = np.abs(bips98["values_bits"].view(np.float32))
+    assert bips98["props"].tolist() == [1, 1, 0] and len(ro) == 7136 and len(ci) == 34738
+    for s in bips98["sources"].tolist():
+        assert np.array_equal(oracle.bfs(ro, ci, s), bips98[f"bfs_{s}"])
+        assert np.array_equal(oracle.sssp(ro, ci, w, s).view(np.uint32), bips98[f"sssp_abs_bits_{s}"])
+    d = bips98["bfs_0"]
+    assert d[0] == 0 and (d == 2**31 - 1).any() and (d < 2**31 - 1).sum() > 1000    # directed: not all reachable
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/datasets/bips98_606/bips98_606.mtx"),
+                    reason="the reference tree is only present in the authoring container")
+def test_bips98_loader_restatements_on_the_real_file(bips98):
+    """The oracle's loader / from_coo and the pygunrock-surface loader read the real file (header comments,
+    `.987`-style reals, negative values, explicit diagonal) into exactly the reference's CSR."""
+    path = "/root/reference/datasets/bips98_606/bips98_606.mtx"
+    m = oracle.load_mtx(path)
+    ro, ci, v = oracle.csr_from_coo(m["n_rows"], m["I"], m["J"], m["V"])
+    assert np.array_equal(ro, bips98["row_offsets"]) and np.array_equal(ci, bips98["column_indices"])
+    assert np.array_equal(v.view(np.uint32), bips98["values_bits"])
+    assert [int(m["directed"]), int(m["weighted"]), int(m["symmetric"])] == bips98["props"].tolist()
+    sys.path.insert(0, os.path.join(ROOT, "python"))
+    import gunrock
+    props, coo = gunrock.matrix_market_t().load(path)
+    csr = gunrock.csr_t()
+    csr.from_coo(coo)
+    assert np.array_equal(csr.row_offsets, ro) and np.array_equal(csr.column_indices, ci)
+    assert np.array_equal(csr.nonzero_values.view(np.uint32), v.view(np.uint32))
+    assert (props.directed, props.weighted, props.symmetric) == (True, True, False)
