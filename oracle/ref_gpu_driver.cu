@@ -6,7 +6,11 @@
 // (optional second baseline row).  Built by `make -C oracle ref_gpu` into
 // oracle/_ref/gunrock_ref_gpu with -include ref_gpu_fix.h and -DSM_TARGET=90 (F3).
 //
-//   gunrock_ref_gpu <bfs|sssp|pr> <graph.csr> <source> <runs> <load_balance> [validate]
+//   gunrock_ref_gpu <bfs|sssp|pr> <graph.csr> <source> <runs> <load_balance> [validate] [dump=<file>]
+//
+// `dump=<file>` writes the result array of the last run (int32 depths / fp32 distances / fp32 ranks) as raw
+// bytes: tests/test_zz_gpu_widening.py compares our results with what the reference's OWN GPU kernels
+// produce on the same GPU (the only PageRank output of the reference there is).
 //
 // graph.csr is the reference's own binary layout (formats/csr.hxx:142-228).  Prints one JSON line:
 // per-run milliseconds as returned by run() (the enactor's own timer, enactor.hxx:266-288) and, with
@@ -38,7 +42,25 @@ int main(int argc, char** argv) {
   const std::string alg = argv[1], file = argv[2], lb_name = argv[5];
   vertex_t source = std::atoi(argv[3]);  // the validators take it by non-const reference
   const int runs = std::atoi(argv[4]);
-  const bool validate = argc > 6 && std::string(argv[6]) == "validate";
+  bool validate = false;
+  std::string dump_path;
+  for (int i = 6; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "validate")
+      validate = true;
+    else if (a.rfind("dump=", 0) == 0)
+      dump_path = a.substr(5);
+  }
+  auto dump = [&](const void* host_ptr, size_t bytes) {
+    if (dump_path.empty())
+      return;
+    FILE* f = std::fopen(dump_path.c_str(), "wb");
+    if (!f || std::fwrite(host_ptr, 1, bytes, f) != bytes) {
+      std::fprintf(stderr, "cannot write %s\n", dump_path.c_str());
+      std::exit(3);
+    }
+    std::fclose(f);
+  };
 
   using csr_t = format::csr_t<memory_space_t::device, vertex_t, edge_t, weight_t>;
   csr_t csr;
@@ -65,6 +87,10 @@ int main(int argc, char** argv) {
       bfs::result_t<vertex_t> result(distances.data().get(), predecessors.data().get());
       ms.push_back(bfs::run(G, param, result, context));
     }
+    {
+      thrust::host_vector<vertex_t> h(distances);
+      dump(h.data(), sizeof(vertex_t) * (size_t)V);
+    }
     if (validate) {
       thrust::host_vector<vertex_t> h(distances), exp(V), pred(V);
       bfs_cpu::run<csr_t, vertex_t, edge_t>(csr, source, exp.data(), pred.data());
@@ -79,6 +105,10 @@ int main(int argc, char** argv) {
       sssp::param_t<vertex_t> param(source, options);
       sssp::result_t<vertex_t, weight_t> result(distances.data().get(), predecessors.data().get(), V);
       ms.push_back(sssp::run(G, param, result, context));
+    }
+    {
+      thrust::host_vector<weight_t> h(distances);
+      dump(h.data(), sizeof(weight_t) * (size_t)V);
     }
     if (validate) {
       thrust::host_vector<weight_t> h(distances), exp(V);
@@ -95,6 +125,8 @@ int main(int argc, char** argv) {
       pr::result_t<weight_t> result(p.data().get());
       ms.push_back(pr::run(G, param, result, context));
     }
+    thrust::host_vector<weight_t> h(p);
+    dump(h.data(), sizeof(weight_t) * (size_t)V);
   } else {
     std::fprintf(stderr, "unknown algorithm %s\n", alg.c_str());
     return 2;

@@ -150,3 +150,58 @@ def test_bips98_directed_real_world_graph_bit_exact():
             gb.sssp(G, s, f, options=gb.options_t(advance_load_balance=lb, hub_threshold=64))
             assert np.array_equal(f.view(np.uint32), z[f"sssp_abs_bits_{s}"]), (s, lb)
     G.close()
+
+
+def test_against_the_reference_gpu_kernels_on_this_gpu(tmp_path):
+    """oracle/_ref/gunrock_ref_gpu = the UNMODIFIED reference GPU implementation built for sm_100a (with the
+    device atomics nvcc compiles out restored).  Same graph, same GPU:
+      * its BFS / SSSP must first pass the reference's own CPU validators (otherwise the reference GPU path is
+        not usable on this box and the comparison is skipped, not failed);
+      * our depths / distances equal its output bit for bit;
+      * PageRank -- the only PageRank output of the reference there is (no CPU validator): both runs
+        stop on `max |p - plast| < 1e-6`, so they agree to that absolute tolerance (stated here: 2e-6), and the
+        iteration counts differ by at most one."""
+    import json
+    import gunrock_b200 as gb
+    exe = os.path.join(ROOT, "oracle", "_ref", "gunrock_ref_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gunrock_ref_gpu not built (needs /root/reference at build time)")
+    ro, ci = oracle.rmat_csr(12, 8, 0xBEEF)
+    w = oracle.edge_weights(21, ro, ci, True)
+    n = len(ro) - 1
+    path = str(tmp_path / "g.csr")
+    with open(path, "wb") as f:                       # formats/csr.hxx:193-228
+        np.array([n, n, len(ci)], np.int32).tofile(f)
+        ro.tofile(f)
+        ci.tofile(f)
+        w.tofile(f)
+    src = int(np.diff(ro).argmax())
+
+    def ref(alg, extra=()):
+        dump = str(tmp_path / f"{alg}.bin")
+        r = subprocess.run([exe, alg, path, str(src), "1", "block_mapped", f"dump={dump}", *extra],
+                           capture_output=True, text=True, timeout=300)
+        if r.returncode != 0:
+            pytest.skip(f"reference GPU binary failed on this box: {(r.stderr or r.stdout)[-300:]}")
+        return json.loads(r.stdout.strip().splitlines()[-1]), dump
+
+    G = gb.graph_t.from_csr(ro, ci, w, symmetric=True)
+    j, dump = ref("bfs", ("validate",))
+    if j["errors"] != 0:
+        pytest.skip(f"the reference's GPU BFS disagrees with its own CPU validator here ({j['errors']} vertices)")
+    d = np.empty(n, np.int32)
+    gb.bfs(G, src, d)
+    assert np.array_equal(d, np.fromfile(dump, np.int32))
+    j, dump = ref("sssp", ("validate",))
+    if j["errors"] != 0:
+        pytest.skip(f"the reference's GPU SSSP disagrees with its own CPU validator here ({j['errors']} vertices)")
+    f32 = np.empty(n, np.float32)
+    gb.sssp(G, src, f32)
+    assert np.array_equal(f32.view(np.uint32), np.fromfile(dump, np.uint32))
+    j, dump = ref("pr")
+    p_ref = np.fromfile(dump, np.float32)
+    p = np.empty(n, np.float32)
+    gb.pr(G, p, 0.85, 1e-6)
+    assert abs(float(p_ref.sum()) - 1.0) < 1e-3 and abs(float(p.sum()) - 1.0) < 1e-3
+    assert float(np.abs(p - p_ref).max()) <= 2e-6, float(np.abs(p - p_ref).max())
+    G.close()
