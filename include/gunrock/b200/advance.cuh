@@ -98,15 +98,74 @@ struct op_wants_variants : std::false_type {};
 template <typename Op>
 struct op_wants_variants<Op, std::void_t<decltype(Op::kVariants)>>
     : std::integral_constant<bool, Op::kVariants> {};
-/// Optional snapshot protocol (advance_warp_path_kernel with kSnap): the functor's test-and-set map has
-/// an on-chip copy of its first `snap_bits` bits in shared memory --
+/// Optional snapshot protocol (advance_warp_path_kernel with kSnapCluster > 0; the functor declares
+/// `static constexpr bool kHasSnapshot = true`): the functor's monotone test-and-set bitmap has an on-chip
+/// copy of its first `snap.bits` bits in (distributed) shared memory --
 ///     const unsigned* snapshot_source() const;                 // the global map the copy is taken from
-///     token_t prefetch_snap(int dst, const unsigned* snap, int snap_bits) const;
-///     bool    commit_snap(int src, int dst, int edge, float w, token_t, unsigned* snap, int snap_bits) const;
+///     template <class Snap> token_t prefetch_snap(int dst, const Snap& snap) const;
+///     template <class Snap> bool    commit_snap(int src, int dst, int edge, float w, token_t, const Snap& snap) const;
 template <typename Op, typename = void>
 struct op_has_snapshot : std::false_type {};
 template <typename Op>
-struct op_has_snapshot<Op, std::void_t<decltype(&Op::prefetch_snap)>> : std::true_type {};
+struct op_has_snapshot<Op, std::void_t<decltype(Op::kHasSnapshot)>>
+    : std::integral_constant<bool, Op::kHasSnapshot> {};
+
+/**
+ * On-chip copy of the first `bits` bits of a monotone (0 -> 1 only) bitmap, handed to the functor.
+ * kCluster == 1: the whole copy lives in this CTA's shared memory.  kCluster > 1: the copy is spread over
+ * the CTAs of a thread-block cluster in 128-byte lines (line L of the map lives in CTA L % kCluster, so the
+ * hot low-id lines of a power-law graph are served by all the SMs of the cluster); a word of another CTA
+ * is read / updated through distributed shared memory (mapa + ld / red .shared::cluster).
+ */
+template <int kCluster>
+struct snapshot_t {
+  uint32_t base;  // shared-window address of this CTA's slice
+  unsigned rank;  // this CTA's rank in the cluster
+  int bits;       // vertices covered (all CTAs together)
+  __device__ __forceinline__ bool covers(int v) const { return v < bits; }
+  __device__ __forceinline__ void locate(int v, unsigned& owner, uint32_t& addr) const {
+    const unsigned wi = static_cast<unsigned>(v) >> 5, line = wi >> 5;
+    owner = kCluster == 1 ? 0u : line % kCluster;
+    addr = base + ((((line / kCluster) << 5) | (wi & 31u)) << 2);
+  }
+  /// The copy's 32-bit word that holds vertex v.
+  __device__ __forceinline__ unsigned load(int v) const {
+    unsigned owner, out;
+    uint32_t addr;
+    locate(v, owner, addr);
+    if (kCluster == 1 || owner == rank) {
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(out) : "r"(addr));
+    } else {
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(owner));
+      asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(out) : "r"(remote));
+    }
+    return out;
+  }
+  /// OR `word` (global state just observed for v's word) into the copy.
+  __device__ __forceinline__ void merge(int v, unsigned word) const {
+    unsigned owner;
+    uint32_t addr;
+    locate(v, owner, addr);
+    if (kCluster == 1 || owner == rank) {
+      asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(word) : "memory");
+    } else {
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(owner));
+      asm volatile("red.shared::cluster.or.b32 [%0], %1;" ::"r"(remote), "r"(word) : "memory");
+    }
+  }
+};
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+/// Full cluster barrier (every thread of every CTA of the cluster).
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 /// Per-warp staging buffer: ballot-compacted appends, flushed with one global atomic.
 template <int kCap, bool kDegSum>
@@ -798,27 +857,31 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
  * kTicket spans per atomic.
  *
  * kSnap (variant 2, functors with the snapshot protocol only): one 1024-thread CTA per SM keeps the
- * first `snap_bits` bits of the functor's visited map in shared memory (128 KiB = 2^20 vertices: 58 % of
- * the edge targets of an RMAT graph, whose low ids are the hubs).  A probe that finds its bit set there
+ * first `snap_bits` bits of the functor's visited map in shared memory (all the shared memory the warps'
+ * staging leaves: ~155 KiB = 1.27 M vertices, about 2/3 of the edge targets of an RMAT graph, whose low
+ * ids are the hubs).  A probe that finds its bit set there
  * costs a shared-memory access (bank conflicts ~3 cycles per warp) instead of 32 L1 tag lookups; a
  * probe that does not falls through to the global path and ORs the whole 32-vertex word it read back
  * into the copy.  Bits only go 0 -> 1, so a stale copy can only send an edge to the global test-and-set
  * that decides today as well.
  */
-template <int kThreads, int kMinCtas, int kSpan, int kB, bool kSnap, advance_input_t kIn,
+template <int kThreads, int kMinCtas, int kSpan, int kB, int kSnapCluster, advance_input_t kIn,
           advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
 __global__ void __launch_bounds__(kThreads, kMinCtas)
-advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, int snap_bits, Op op) {
+advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, int snap_bits, int map_words,
+                         Op op) {
+  constexpr bool kSnap = kSnapCluster > 0;
+  constexpr int kClusterN = kSnap ? kSnapCluster : 1;
   constexpr int kRows = kSpan + 36;  // kSpan ranks overlap at most kSpan non-empty rows (+ 33 sentinels)
   constexpr int kTicket = 8;         // spans per work-cursor atomic (lanes 0..kTicket hold their first rows)
   constexpr bool kSrc = op_needs_source<Op>::value;
   constexpr int kWarpInts = kEmitCap + kRows + (kSrc ? kRows : 0) + kRows / 2;
   static_assert(kSpan % 32 == 0 && kSpan < 65536 - 64 && kRows % 2 == 0, "span layout");
-  static_assert(!kSnap || op_has_snapshot<Op>::value, "kSnap needs the functor's snapshot protocol");
+  static_assert(!kSnap || op_has_snapshot<Op>::value, "a snapshot needs the functor's snapshot protocol");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [snapshot words] then per warp [emit | base | (vert) | rank (16 bit)]
   unsigned* s_snap = reinterpret_cast<unsigned*>(smem_raw);
-  const int snap_words = kSnap ? (snap_bits >> 5) : 0;
+  const int snap_words = kSnap ? (snap_bits >> 5) / kClusterN : 0;  // this CTA's slice (whole 128-byte lines)
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   int* mine = reinterpret_cast<int*>(smem_raw) + snap_words + warp * kWarpInts;
   int* s_base = mine + kEmitCap;  // (CSR offset of the row's first edge) - (its first rank)
@@ -831,11 +894,20 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
   const int n = (kIn == advance_input_t::graph) ? p.g.n_vertices : *p.in_count;
   if (n == 0)
     return;  // uniform over the grid: nobody reaches the barrier below
+  snapshot_t<kClusterN> snap{smem_u32(s_snap), 0u, snap_bits};
   if constexpr (kSnap) {
+    if (kClusterN > 1)
+      snap.rank = cluster_cta_rank();
     const unsigned* gmap = op.snapshot_source();
-    for (int i = threadIdx.x; i < snap_words; i += kThreads)
-      s_snap[i] = ld_relaxed(gmap + i);
-    __syncthreads();  // the only block barrier of the kernel
+    for (int li = threadIdx.x; li < snap_words; li += kThreads) {
+      // local line li/32 is line (li/32)*kClusterN + rank of the map
+      const int wi = ((((li >> 5) * kClusterN) + static_cast<int>(snap.rank)) << 5) | (li & 31);
+      s_snap[li] = wi < map_words ? ld_relaxed(gmap + wi) : 0u;
+    }
+    if (kClusterN > 1)
+      cluster_barrier();  // every slice of the copy is in place before anybody probes it
+    else
+      __syncthreads();    // the only block barrier of the kernel
   }
   const int total = scanned[n];
   const int nspans = (total + kSpan - 1) / kSpan;
@@ -913,14 +985,14 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
         for (int k = 0; k < kB; ++k)
           if (valid[k]) {
             if constexpr (kSnap)
-              tok[k] = op.prefetch_snap(nb[k], s_snap, snap_bits);
+              tok[k] = op.prefetch_snap(nb[k], snap);
             else
               tok[k] = op_prefetch(op, nb[k]);
           }
 #pragma unroll
         for (int k = 0; k < kB; ++k) {
           if constexpr (kSnap)
-            keep[k] = valid[k] && op.commit_snap(u[k], nb[k], e[k], w[k], tok[k], s_snap, snap_bits);
+            keep[k] = valid[k] && op.commit_snap(u[k], nb[k], e[k], w[k], tok[k], snap);
           else
             keep[k] = valid[k] && op_commit(op, u[k], nb[k], e[k], w[k], tok[k]);
         }
@@ -937,6 +1009,8 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
     em.flush();
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&p.ctrl->edges, static_cast<unsigned long long>(total));
+  if constexpr (kSnap && kClusterN > 1)
+    cluster_barrier();  // nobody leaves while a peer may still read / update its slice of the copy
 }
 
 /// Report of advance_tail_kernel (written to pinned host memory by the kernel).
@@ -1097,6 +1171,8 @@ struct advance_launch_t {
   ///      the visited map (functors with the snapshot protocol; others run variant 1)
   ///   3  the default CTA kernel with 4096-edge tiles (half the block barriers per edge)
   ///   4  warp-private spans, 256-thread CTAs, 8 chunks in flight
+  ///   5  as 2, the copy spread over a CLUSTER of 2 CTAs (distributed shared memory): twice the coverage
+  ///   6  as 2, cluster of 4: 5 M vertices on chip (the whole visited map of a scale-22 graph)
   int variant = 0;
 };
 
@@ -1170,7 +1246,70 @@ inline void launch_merge_path_tiles(workspace_t& ws, advance_params_t& p, const 
         <<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
 }
 
-/// EXPERIMENTAL variants 1 / 2 / 4: span partition + advance_warp_path_kernel.
+/// EXPERIMENTAL variants 2 / 5 / 6: warp-private spans + on-chip copy of the functor's visited map, held by
+/// one 1024-thread CTA per SM (kCluster == 1) or spread over a cluster of kCluster such CTAs.
+/// `p.tile_rows` / `p.ctrl` are already set by launch_warp_path.
+template <int kCluster, advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
+inline void launch_warp_path_snapshot(workspace_t& ws, advance_params_t& p, const int* scanned, bool graph_in,
+                                      Op op) {
+  constexpr int kSpan = 256, kThreads = 1024;
+  constexpr int kWarpBytes = warp_path_ints<kSpan, op_needs_source<Op>::value>() * 4;
+  const int sms = device_info_t::get().sm_count;
+  // every CTA's slice takes the shared memory the 32 warps' staging leaves (227 KiB opt-in on B200: ~155 KiB =
+  // 1.27 M vertices per CTA; the low ids of an RMAT graph are its hubs, so one slice already holds ~2/3 of all
+  // edge targets, two ~5/6, four the whole map of a scale-22 graph)
+  const int map_words = (p.g.n_vertices + 31) / 32;
+  const int room = device_info_t::get().max_smem_optin - 1024 - (kThreads / 32) * kWarpBytes;
+  const long long lines_cta = room > 0 ? room / 128 : 0;                      // 128-byte lines per CTA
+  const long long lines_map = (static_cast<long long>(map_words) + 31) / 32;  // lines of the whole map
+  long long lines = lines_cta * kCluster;
+  if (lines > lines_map)
+    lines = ((lines_map + kCluster - 1) / kCluster) * kCluster;               // same number of lines per CTA
+  const int snap_bits = static_cast<int>(lines * 1024);
+  const int smem = static_cast<int>(lines / kCluster) * 128 + (kThreads / 32) * kWarpBytes;
+  auto kg = advance_warp_path_kernel<kThreads, 1, kSpan, 8, kCluster, advance_input_t::graph, kOut, kDegSum,
+                                     kWeights, Op>;
+  auto kv = advance_warp_path_kernel<kThreads, 1, kSpan, 8, kCluster, advance_input_t::vertices, kOut, kDegSum,
+                                     kWeights, Op>;
+  cudaLaunchConfig_t lc{};
+  lc.blockDim = dim3(kThreads);
+  lc.dynamicSmemBytes = static_cast<size_t>(smem);
+  lc.stream = ws.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = kCluster > 1 ? 1 : 0;
+  // opt in to > 48 KiB of dynamic shared memory and size the grid, once per device: as many whole clusters
+  // as can be resident together (148 CTAs for pairs, fewer for clusters of four), work comes by ticket
+  static thread_local int for_device = -1;
+  static thread_local int grid_ctas = 0;
+  if (for_device != device_info_t::get().device) {
+    const int most = device_info_t::get().max_smem_optin;
+    B2G_CHECK(cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+    B2G_CHECK(cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+    grid_ctas = (sms / kCluster) * kCluster;
+    if (kCluster > 1) {
+      lc.gridDim = dim3(grid_ctas);
+      int clusters = 0;
+      B2G_CHECK(cudaOccupancyMaxActiveClusters(&clusters, kv, &lc));
+      if (clusters < 1)
+        throw std::runtime_error("advance variant: no cluster of this shape fits the device");
+      if (clusters * kCluster < grid_ctas)
+        grid_ctas = clusters * kCluster;
+    }
+    for_device = device_info_t::get().device;
+  }
+  lc.gridDim = dim3(grid_ctas);
+  if (graph_in)
+    B2G_CHECK(cudaLaunchKernelEx(&lc, kg, p, scanned, snap_bits, map_words, op));
+  else
+    B2G_CHECK(cudaLaunchKernelEx(&lc, kv, p, scanned, snap_bits, map_words, op));
+}
+
+/// EXPERIMENTAL variants 1 / 2 / 4 / 5 / 6: span partition + advance_warp_path_kernel.
 template <advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
 inline void launch_warp_path(workspace_t& ws, advance_params_t& p, const int* scanned, bool graph_in,
                              const advance_launch_t& cfg, Op op) {
@@ -1188,23 +1327,15 @@ inline void launch_warp_path(workspace_t& ws, advance_params_t& p, const int* sc
   constexpr auto kVerts = advance_input_t::vertices;
   if constexpr (op_has_snapshot<Op>::value) {
     if (cfg.variant == 2) {
-      constexpr int kThreads = 1024;
-      const int v_bits = ((p.g.n_vertices + 31) / 32) * 32;
-      const int snap_bits = v_bits < (1 << 20) ? v_bits : (1 << 20);
-      const int smem = (snap_bits / 32) * 4 + (kThreads / 32) * kWarpBytes;
-      auto kg = advance_warp_path_kernel<kThreads, 1, kSpan, 8, true, kGraph, kOut, kDegSum, kWeights, Op>;
-      auto kv = advance_warp_path_kernel<kThreads, 1, kSpan, 8, true, kVerts, kOut, kDegSum, kWeights, Op>;
-      static thread_local int attr_device = -1;  // opt in to > 48 KiB of dynamic shared memory, once per device
-      if (attr_device != device_info_t::get().device) {
-        const int most = device_info_t::get().max_smem_optin;
-        B2G_CHECK(cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-        B2G_CHECK(cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-        attr_device = device_info_t::get().device;
-      }
-      if (graph_in)
-        kg<<<sms, kThreads, smem, ws.stream>>>(p, scanned, snap_bits, op);
-      else
-        kv<<<sms, kThreads, smem, ws.stream>>>(p, scanned, snap_bits, op);
+      launch_warp_path_snapshot<1, kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, op);
+      return;
+    }
+    if (cfg.variant == 5) {
+      launch_warp_path_snapshot<2, kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, op);
+      return;
+    }
+    if (cfg.variant == 6) {
+      launch_warp_path_snapshot<4, kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, op);
       return;
     }
   }
@@ -1213,18 +1344,18 @@ inline void launch_warp_path(workspace_t& ws, advance_params_t& p, const int* sc
   const int grid = sms * cfg.ctas_per_sm;
   if (cfg.variant == 4) {
     if (graph_in)
-      advance_warp_path_kernel<kThreads, 4, kSpan, 8, false, kGraph, kOut, kDegSum, kWeights>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, op);
+      advance_warp_path_kernel<kThreads, 4, kSpan, 8, 0, kGraph, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
     else
-      advance_warp_path_kernel<kThreads, 4, kSpan, 8, false, kVerts, kOut, kDegSum, kWeights>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, op);
+      advance_warp_path_kernel<kThreads, 4, kSpan, 8, 0, kVerts, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
   } else {
     if (graph_in)
-      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, false, kGraph, kOut, kDegSum, kWeights>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, op);
+      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, 0, kGraph, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
     else
-      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, false, kVerts, kOut, kDegSum, kWeights>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, op);
+      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, 0, kVerts, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
   }
 }
 

@@ -55,18 +55,20 @@ struct bfs_claim_op {
   }
   // ---- experimental kernel variants (advance_launch_t::variant; off by default) --------------------
   static constexpr bool kVariants = true;
-  /// snapshot protocol (advance.cuh op_has_snapshot): the first `snap_bits` bits of `visited` have a
-  /// copy in shared memory.  A bit found set there needs no global probe; the token is then just that
+  /// snapshot protocol (advance.cuh snapshot_t): the first `snap.bits` bits of `visited` have a copy in
+  /// (distributed) shared memory.  A bit found set there needs no global probe; the token is then just that
   /// bit, so that commit neither claims nor learns anything from it.
+  static constexpr bool kHasSnapshot = true;
   __device__ __forceinline__ const unsigned* snapshot_source() const { return visited; }
-  __device__ __forceinline__ unsigned prefetch_snap(int dst, const unsigned* snap, int snap_bits) const {
+  template <typename Snap>
+  __device__ __forceinline__ unsigned prefetch_snap(int dst, const Snap& snap) const {
     const unsigned bit = 1u << (dst & 31);
-    if (dst < snap_bits && (snap[dst >> 5] & bit))
+    if (snap.covers(dst) && (snap.load(dst) & bit))
       return bit;
     return ld_cached(visited + (dst >> 5));
   }
-  __device__ __forceinline__ bool commit_snap(int, int dst, int, float, unsigned word, unsigned* snap,
-                                              int snap_bits) const {
+  template <typename Snap>
+  __device__ __forceinline__ bool commit_snap(int, int dst, int, float, unsigned word, const Snap& snap) const {
     const unsigned bit = 1u << (dst & 31);
     bool won = false;
     if (!(word & bit)) {
@@ -76,9 +78,12 @@ struct bfs_claim_op {
       if (won)
         dist[dst] = next_level;
     }
-    // whatever global state this edge saw goes into the on-chip copy (monotone: bits only get set)
-    if (dst < snap_bits && (word & ~snap[dst >> 5]))
-      atomicOr(snap + (dst >> 5), word);
+    // Whatever global state this edge saw goes into the on-chip copy (monotone: bits only get set).  A token
+    // that is exactly `bit` either came from the copy or carries nothing the copy needs besides that one bit;
+    // only the second case loses anything (that vertex keeps probing the global map) and it needs a word in
+    // which a single vertex is visited.
+    if (snap.covers(dst) && (won || word != bit))
+      snap.merge(dst, word);
     return won;
   }
 };
