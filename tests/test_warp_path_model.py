@@ -125,3 +125,25 @@ def test_every_edge_of_the_frontier_is_walked_exactly_once(kind, kb):
             got += walk_span(scanned, row_base, n, total, span_rows, sp, kb)
         exp = [(i, int(row_base[i]) + j) for i in range(n) for j in range(int(deg[i]))]
         assert sorted(got) == exp
+
+
+@pytest.mark.parametrize("k_cluster", [1, 2, 4])
+def test_snapshot_interleave_is_consistent_between_fill_and_probe(k_cluster):
+    """snapshot_t::locate (probe side) and the kernel's fill loop (advance_warp_path_kernel) must agree on where
+    word `wi` of the visited map lives: CTA (wi / 32) % k, local word ((wi / 32) / k) * 32 + wi % 32."""
+    lines_per_cta = 5
+    snap_words_cta = lines_per_cta * 32
+    map_words = lines_per_cta * k_cluster * 32 - 40          # the map ends inside the last lines
+    slices = [dict() for _ in range(k_cluster)]
+    for rank in range(k_cluster):                            # fill, as each CTA does it
+        for li in range(snap_words_cta):
+            wi = ((((li >> 5) * k_cluster) + rank) << 5) | (li & 31)
+            slices[rank][li] = wi if wi < map_words else None
+    seen = set()
+    for v in range(0, map_words * 32, 7):                    # probe
+        wi, line = v >> 5, v >> 10
+        owner = 0 if k_cluster == 1 else line % k_cluster
+        local = ((line // k_cluster) << 5) | (wi & 31)
+        assert slices[owner][local] == wi
+        seen.add((owner, local))
+    assert len(seen) == len({v >> 5 for v in range(0, map_words * 32, 7)})
