@@ -63,8 +63,35 @@ int main(int argc, char** argv) {
   };
 
   using csr_t = format::csr_t<memory_space_t::device, vertex_t, edge_t, weight_t>;
+  // The file is in the layout of the reference's csr_t::write_binary (formats/csr.hxx:193-228) but is read
+  // here, not by csr_t::read_binary: that function wraps every fread in `throw_if_exception(fread(...) != 0)`
+  // (formats/csr.hxx:146-151), i.e. it throws exactly when a read SUCCEEDS.
   csr_t csr;
-  csr.read_binary(file);
+  {
+    FILE* f = std::fopen(file.c_str(), "rb");
+    int header[3];
+    if (!f || std::fread(header, sizeof(int), 3, f) != 3) {
+      std::fprintf(stderr, "cannot read %s\n", file.c_str());
+      return 2;
+    }
+    thrust::host_vector<edge_t> ro((size_t)header[0] + 1);
+    thrust::host_vector<vertex_t> ci((size_t)header[2]);
+    thrust::host_vector<weight_t> vals((size_t)header[2]);
+    bool ok = std::fread(ro.data(), sizeof(edge_t), ro.size(), f) == ro.size() &&
+              std::fread(ci.data(), sizeof(vertex_t), ci.size(), f) == ci.size() &&
+              std::fread(vals.data(), sizeof(weight_t), vals.size(), f) == vals.size();
+    std::fclose(f);
+    if (!ok) {
+      std::fprintf(stderr, "truncated %s\n", file.c_str());
+      return 2;
+    }
+    csr.number_of_rows = header[0];
+    csr.number_of_columns = header[1];
+    csr.number_of_nonzeros = header[2];
+    csr.row_offsets = ro;
+    csr.column_indices = ci;
+    csr.nonzero_values = vals;
+  }
   graph::graph_properties_t properties;
   auto G = graph::build<memory_space_t::device>(properties, csr);
   const vertex_t V = G.get_number_of_vertices();

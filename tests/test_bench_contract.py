@@ -35,3 +35,45 @@ def test_reference_arm_line(built):
 
 def test_reference_arm_other_ranks_are_silent(built):
     assert run_bench(env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_reference_gpu_leg_plumbing(tmp_path, monkeypatch):
+    """bench.py --reference-gpu (the unmodified reference GPU kernels as a same-GPU baseline) cannot run without
+    a GPU, but its plumbing can: the graph file must be in the reference's .csr layout (formats/csr.hxx:193-228)
+    and the binary's JSON line must come back as MTEPS.  A stand-in executable checks the file it is given."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    fake_root = tmp_path / "repo"
+    (fake_root / "oracle" / "_ref").mkdir(parents=True)
+    exe = fake_root / "oracle" / "_ref" / "gunrock_ref_gpu"
+    exe.write_text(f"""#!{sys.executable}
+import json, sys
+import numpy as np
+alg, path, src, runs, lb = sys.argv[1:6]
+raw = np.fromfile(path, np.int32)
+n, m, nnz = raw[:3]
+ro = raw[3:3 + n + 1]
+ci = raw[4 + n:4 + n + nnz]
+vals = raw[4 + n + nnz:].view(np.float32)
+assert n == m and ro[0] == 0 and ro[-1] == nnz and len(ci) == nnz and len(vals) == nnz and ci.max() < n
+print("some library chatter")
+print(json.dumps({{"impl": "reference_gpu", "algorithm": alg, "load_balance": lb, "vertices": int(n), "edges": int(nnz),
+                  "source": int(src), "errors": 0 if "validate" in sys.argv else -1, "ms": [9.0] + [2.0] * (int(runs) - 1)}}))
+""")
+    exe.chmod(0o755)
+    monkeypatch.setattr(bench, "ROOT", str(fake_root))
+
+    class FakeGraph:
+        def download(self):
+            ro = np.array([0, 2, 3, 3, 5], np.int32)
+            return ro, np.array([1, 2, 0, 0, 1], np.int32), None
+
+    out = bench.reference_gpu_leg(FakeGraph(), {"alg": "bfs"}, 0, edges_per_run=4000, runs=4)
+    assert out["block_mapped"]["errors_vs_reference_cpu"] == 0 and out["merge_path"]["errors_vs_reference_cpu"] == -1
+    assert out["block_mapped"]["ms_median"] == 2.0 and out["block_mapped"]["runs"] == 4      # first run dropped
+    assert abs(out["block_mapped"]["mteps"] - 4000 / 2.0 / 1e3) < 1e-12
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path / "nowhere"))
+    assert "unavailable" in bench.reference_gpu_leg(FakeGraph(), {"alg": "bfs"}, 0, 1)
