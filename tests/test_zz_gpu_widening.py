@@ -205,3 +205,39 @@ def test_against_the_reference_gpu_kernels_on_this_gpu(tmp_path):
     assert abs(float(p_ref.sum()) - 1.0) < 1e-3 and abs(float(p.sum()) - 1.0) < 1e-3
     assert float(np.abs(p - p_ref).max()) <= 2e-6, float(np.abs(p - p_ref).max())
     G.close()
+
+
+def test_reference_geo_example_runs(golden, tmp_path):
+    """geo.cu (the one example test_gpu_examples.py skips: it needs a coordinates file).  Chesapeake with known
+    coordinates on three quarters of the vertices: the program must finish, leave the known coordinates alone and
+    place the predicted ones inside the bounding box of the known ones (spatial median of the neighbours, geo.hxx)."""
+    g = golden["chesapeake"]
+    I, J = np.array(g["coo_I"]), np.array(g["coo_J"])
+    n = g["n_rows"]
+    mtx = tmp_path / "chesapeake.mtx"
+    with open(mtx, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate pattern symmetric\n{n} {n} {len(I) // 2}\n")
+        for k in range(0, len(I), 2):
+            f.write(f"{I[k] + 1} {J[k] + 1}\n")
+    rng = np.random.default_rng(4)
+    lat, lon = rng.uniform(30, 45, n).round(3), rng.uniform(-120, -75, n).round(3)
+    known = np.ones(n, bool)
+    known[::4] = False
+    labels = tmp_path / "chesapeake.labels"
+    with open(labels, "w") as f:
+        f.write(f"%%Labels Formatted File\n% test\n{n} 2 2\n")
+        for v in range(n):
+            f.write(f"{v} {lat[v]} {lon[v]}\n" if known[v] else f"{v}\n")
+    out = run([need("ext_geo"), str(mtx), str(labels)])
+    assert "GPU Elapsed Time" in out, out[-1500:]
+    rows = re.findall(r"Node \((\d+)\) = (\S+), (\S+)", out)
+    assert len(rows) == min(n, 40)
+    predicted = 0
+    for v, a, b in rows:
+        v = int(v)
+        if known[v]:
+            assert abs(float(a) - lat[v]) < 1e-2 and abs(float(b) - lon[v]) < 1e-2, (v, a, b)
+        elif np.isfinite(float(a)) and np.isfinite(float(b)):
+            predicted += 1
+            assert 29.0 < float(a) < 46.0 and -121.0 < float(b) < -74.0, (v, a, b)   # inside the hull of the known ones
+    assert predicted >= 1
