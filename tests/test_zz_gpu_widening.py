@@ -29,13 +29,6 @@ def run(cmd, timeout=120):
     return r.stdout
 
 
-def test_dense_frontier_views_selftest():
-    """SURVEY.md 8f N3: frontier_t<..., bitmap> / <..., boolmap> (host operations, device accessors,
-    conversion from / to the vector view, one BFS level with a bitmap output frontier)."""
-    out = run([need("dense_frontier_selftest")])
-    assert "ALL OK" in out, out[-2000:]
-
-
 def write_symmetric_mtx(path, ro, ci, w=None):
     """Lower triangle in (row, column) order: the reference loader mirrors every entry in place and
     from_coo is a stable sort by row, so every CSR row comes out with ascending column indices (what the
@@ -60,6 +53,30 @@ def triangles_per_vertex(ro, ci):
     A = np.zeros((n, n), np.int64)
     A[np.repeat(np.arange(n), np.diff(ro)), ci] = 1
     return np.einsum("ij,jk,ki->i", A, A, A) // 2
+
+
+def test_bips98_directed_real_world_graph_bit_exact():
+    """The reference's second vendored dataset (bips98_606.mtx: directed, 7135 vertices, explicit diagonal):
+    depths and |value|-weighted distances minted by the compiled reference (tests/golden/bips98_606.npz),
+    through the C ABI with every load balancer and direction (pull needs the transpose: the graph is not
+    symmetric)."""
+    import gunrock_b200 as gb
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bips98_606.npz"))
+    ro, ci = z["row_offsets"], z["column_indices"]
+    w = np.abs(z["values_bits"].view(np.float32))
+    G = gb.graph_t.from_csr(ro, ci, w, symmetric=False)
+    LB, DIR = gb.load_balance_t, gb.advance_direction_t
+    for s in z["sources"].tolist():
+        for lb in (LB.thread_mapped, LB.block_mapped, LB.merge_path):
+            for direction in (DIR.forward, DIR.optimized, DIR.backward):
+                d = np.empty(G.n_vertices, np.int32)
+                gb.bfs(G, s, d, options=gb.options_t(advance_load_balance=lb, advance_direction=direction,
+                                                     hub_threshold=64))
+                assert np.array_equal(d, z[f"bfs_{s}"]), (s, lb, direction)
+            f = np.empty(G.n_vertices, np.float32)
+            gb.sssp(G, s, f, options=gb.options_t(advance_load_balance=lb, hub_threshold=64))
+            assert np.array_equal(f.view(np.uint32), z[f"sssp_abs_bits_{s}"]), (s, lb)
+    G.close()
 
 
 def test_reference_tc_validates_with_uint32_ids(tmp_path):
@@ -101,55 +118,48 @@ def test_reference_spgemm_on_the_multi_view_graph(tmp_path):
     assert vals == C.data[:10].tolist()
 
 
-def test_reference_mst_matches_its_cpu_run(tmp_path):
-    """mst.cu (filter::remove + advance on our operators): GPU and CPU spanning-tree weights agree.
-    Distinct integer weights make the tree unique; a connected graph is what the example expects."""
-    ro, ci = oracle.rmat_csr(8, 8, 11)
-    n = len(ro) - 1
-    src = np.repeat(np.arange(n), np.diff(ro))
-    # keep the giant component only (depths from the hub), relabelled densely
-    d = oracle.bfs(ro, ci, int(np.diff(ro).argmax()))
-    alive = d < 2**31 - 1
-    new_id = np.cumsum(alive) - 1
-    keep = alive[src] & alive[ci]
-    s2, c2 = new_id[src[keep]], new_id[ci[keep]]
-    lower = c2 < s2
-    s2, c2 = s2[lower], c2[lower]
-    order = np.lexsort((c2, s2))
-    s2, c2 = s2[order], c2[order]
-    w = (np.random.default_rng(3).permutation(len(s2)) + 1).astype(np.float32)   # distinct, exact in fp32
-    mtx = str(tmp_path / "mst.mtx")
+def test_reference_geo_example_runs(golden, tmp_path):
+    """geo.cu (the one example test_gpu_examples.py skips: it needs a coordinates file).  Chesapeake with known
+    coordinates on three quarters of the vertices: the program must finish, leave the known coordinates alone and
+    place the predicted ones inside the bounding box of the known ones (spatial median of the neighbours, geo.hxx)."""
+    g = golden["chesapeake"]
+    I, J = np.array(g["coo_I"]), np.array(g["coo_J"])
+    n = g["n_rows"]
+    mtx = tmp_path / "chesapeake.mtx"
     with open(mtx, "w") as f:
-        f.write(f"%%MatrixMarket matrix coordinate real symmetric\n{int(alive.sum())} {int(alive.sum())} {len(s2)}\n")
-        f.write("\n".join(f"{a + 1} {b + 1} {float(v)!r}" for a, b, v in zip(s2, c2, w)) + "\n")
-    out = run([need("ext_mst"), "-m", mtx, "--validate"], timeout=60)
-    g = float(re.search(r"GPU MST Weight: ([\d.]+)", out).group(1))
-    c = float(re.search(r"CPU MST Weight: ([\d.]+)", out).group(1))
-    assert g == c, out[-1500:]
+        f.write(f"%%MatrixMarket matrix coordinate pattern symmetric\n{n} {n} {len(I) // 2}\n")
+        for k in range(0, len(I), 2):
+            f.write(f"{I[k] + 1} {J[k] + 1}\n")
+    rng = np.random.default_rng(4)
+    lat, lon = rng.uniform(30, 45, n).round(3), rng.uniform(-120, -75, n).round(3)
+    known = np.ones(n, bool)
+    known[::4] = False
+    labels = tmp_path / "chesapeake.labels"
+    with open(labels, "w") as f:
+        f.write(f"%%Labels Formatted File\n% test\n{n} 2 2\n")
+        for v in range(n):
+            f.write(f"{v} {lat[v]} {lon[v]}\n" if known[v] else f"{v}\n")
+    out = run([need("ext_geo"), str(mtx), str(labels)])
+    assert "GPU Elapsed Time" in out, out[-1500:]
+    rows = re.findall(r"Node \((\d+)\) = (\S+), (\S+)", out)
+    assert len(rows) == min(n, 40)
+    predicted = 0
+    for v, a, b in rows:
+        v = int(v)
+        if known[v]:
+            assert abs(float(a) - lat[v]) < 1e-2 and abs(float(b) - lon[v]) < 1e-2, (v, a, b)
+        elif np.isfinite(float(a)) and np.isfinite(float(b)):
+            predicted += 1
+            assert 29.0 < float(a) < 46.0 and -121.0 < float(b) < -74.0, (v, a, b)   # inside the hull of the known ones
+    assert predicted >= 1
 
 
-def test_bips98_directed_real_world_graph_bit_exact():
-    """The reference's second vendored dataset (bips98_606.mtx: directed, 7135 vertices, explicit diagonal):
-    depths and |value|-weighted distances minted by the compiled reference (tests/golden/bips98_606.npz),
-    through the C ABI with every load balancer and direction (pull needs the transpose: the graph is not
-    symmetric)."""
-    import gunrock_b200 as gb
-    z = np.load(os.path.join(ROOT, "tests", "golden", "bips98_606.npz"))
-    ro, ci = z["row_offsets"], z["column_indices"]
-    w = np.abs(z["values_bits"].view(np.float32))
-    G = gb.graph_t.from_csr(ro, ci, w, symmetric=False)
-    LB, DIR = gb.load_balance_t, gb.advance_direction_t
-    for s in z["sources"].tolist():
-        for lb in (LB.thread_mapped, LB.block_mapped, LB.merge_path):
-            for direction in (DIR.forward, DIR.optimized, DIR.backward):
-                d = np.empty(G.n_vertices, np.int32)
-                gb.bfs(G, s, d, options=gb.options_t(advance_load_balance=lb, advance_direction=direction,
-                                                     hub_threshold=64))
-                assert np.array_equal(d, z[f"bfs_{s}"]), (s, lb, direction)
-            f = np.empty(G.n_vertices, np.float32)
-            gb.sssp(G, s, f, options=gb.options_t(advance_load_balance=lb, hub_threshold=64))
-            assert np.array_equal(f.view(np.uint32), z[f"sssp_abs_bits_{s}"]), (s, lb)
-    G.close()
+
+def test_dense_frontier_views_selftest():
+    """SURVEY.md 8f N3: frontier_t<..., bitmap> / <..., boolmap> (host operations, device accessors,
+    conversion from / to the vector view, one BFS level with a bitmap output frontier)."""
+    out = run([need("dense_frontier_selftest")])
+    assert "ALL OK" in out, out[-2000:]
 
 
 def test_against_the_reference_gpu_kernels_on_this_gpu(tmp_path):
@@ -207,37 +217,28 @@ def test_against_the_reference_gpu_kernels_on_this_gpu(tmp_path):
     G.close()
 
 
-def test_reference_geo_example_runs(golden, tmp_path):
-    """geo.cu (the one example test_gpu_examples.py skips: it needs a coordinates file).  Chesapeake with known
-    coordinates on three quarters of the vertices: the program must finish, leave the known coordinates alone and
-    place the predicted ones inside the bounding box of the known ones (spatial median of the neighbours, geo.hxx)."""
-    g = golden["chesapeake"]
-    I, J = np.array(g["coo_I"]), np.array(g["coo_J"])
-    n = g["n_rows"]
-    mtx = tmp_path / "chesapeake.mtx"
+def test_reference_mst_matches_its_cpu_run(tmp_path):
+    """mst.cu (filter::remove + advance on our operators): GPU and CPU spanning-tree weights agree.
+    Distinct integer weights make the tree unique; a connected graph is what the example expects."""
+    ro, ci = oracle.rmat_csr(8, 8, 11)
+    n = len(ro) - 1
+    src = np.repeat(np.arange(n), np.diff(ro))
+    # keep the giant component only (depths from the hub), relabelled densely
+    d = oracle.bfs(ro, ci, int(np.diff(ro).argmax()))
+    alive = d < 2**31 - 1
+    new_id = np.cumsum(alive) - 1
+    keep = alive[src] & alive[ci]
+    s2, c2 = new_id[src[keep]], new_id[ci[keep]]
+    lower = c2 < s2
+    s2, c2 = s2[lower], c2[lower]
+    order = np.lexsort((c2, s2))
+    s2, c2 = s2[order], c2[order]
+    w = (np.random.default_rng(3).permutation(len(s2)) + 1).astype(np.float32)   # distinct, exact in fp32
+    mtx = str(tmp_path / "mst.mtx")
     with open(mtx, "w") as f:
-        f.write(f"%%MatrixMarket matrix coordinate pattern symmetric\n{n} {n} {len(I) // 2}\n")
-        for k in range(0, len(I), 2):
-            f.write(f"{I[k] + 1} {J[k] + 1}\n")
-    rng = np.random.default_rng(4)
-    lat, lon = rng.uniform(30, 45, n).round(3), rng.uniform(-120, -75, n).round(3)
-    known = np.ones(n, bool)
-    known[::4] = False
-    labels = tmp_path / "chesapeake.labels"
-    with open(labels, "w") as f:
-        f.write(f"%%Labels Formatted File\n% test\n{n} 2 2\n")
-        for v in range(n):
-            f.write(f"{v} {lat[v]} {lon[v]}\n" if known[v] else f"{v}\n")
-    out = run([need("ext_geo"), str(mtx), str(labels)])
-    assert "GPU Elapsed Time" in out, out[-1500:]
-    rows = re.findall(r"Node \((\d+)\) = (\S+), (\S+)", out)
-    assert len(rows) == min(n, 40)
-    predicted = 0
-    for v, a, b in rows:
-        v = int(v)
-        if known[v]:
-            assert abs(float(a) - lat[v]) < 1e-2 and abs(float(b) - lon[v]) < 1e-2, (v, a, b)
-        elif np.isfinite(float(a)) and np.isfinite(float(b)):
-            predicted += 1
-            assert 29.0 < float(a) < 46.0 and -121.0 < float(b) < -74.0, (v, a, b)   # inside the hull of the known ones
-    assert predicted >= 1
+        f.write(f"%%MatrixMarket matrix coordinate real symmetric\n{int(alive.sum())} {int(alive.sum())} {len(s2)}\n")
+        f.write("\n".join(f"{a + 1} {b + 1} {float(v)!r}" for a, b, v in zip(s2, c2, w)) + "\n")
+    out = run([need("ext_mst"), "-m", mtx, "--validate"], timeout=60)
+    g = float(re.search(r"GPU MST Weight: ([\d.]+)", out).group(1))
+    c = float(re.search(r"CPU MST Weight: ([\d.]+)", out).group(1))
+    assert g == c, out[-1500:]
