@@ -169,6 +169,9 @@ class dense_frontier_t {
     }
     s.universe = universe;
     clear();
+    // (re)allocation is rare and the caller may bind another -- possibly non-blocking -- stream right after:
+    // the zero fill must have landed before anything enqueued there touches the words
+    error::throw_if_exception(cudaStreamSynchronize(s.stream), "dense frontier resize");
     sync_view();
   }
   void reserve(std::size_t universe) {
