@@ -33,6 +33,14 @@ done | tee "$OUT/variants.txt"
 # 2c. same-GPU baseline: the UNMODIFIED reference GPU kernels (oracle/_ref/gunrock_ref_gpu) on the bench graph
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --reference-gpu 2>&1 | tail -1 > "$OUT/bench_with_reference_gpu.json"
 python -c "import json,sys; j=json.load(open('$OUT/bench_with_reference_gpu.json')); print('ours', round(j['value']), 'MTEPS; reference GPU:', json.dumps(j.get('reference_gpu'))[:600])" | tee "$OUT/reference_gpu.txt"
+# 2d. ncu --set full of the two big levels (launches after the warm-up runs) for the default kernel and the two
+#     on-chip-map variants; summaries go next to the reports (copy the interesting ones into profiles/)
+for v in 0 2 6; do
+  B2G_ADVANCE_VARIANT=$v timeout 600 ncu --set full --clock-control none --import-source on \
+    -k regex:'advance_(merge|warp)_path_kernel' --launch-skip 6 --launch-count 2 -f -o "$OUT/ncu_bfs_push_variant_$v" \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_variant_$v.log" 2>&1
+  python profiles/summarize_ncu.py "$OUT/ncu_bfs_push_variant_$v.ncu-rep" "$OUT/ncu_bfs_push_variant_$v.md" >/dev/null 2>&1 || true
+done
 # 3. design input for the on-chip visited map: probe rates of L1 / L2 / shared / DSMEM
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o "$OUT/probe_rates" profiles/micro/probe_rates.cu && "$OUT/probe_rates" | tee "$OUT/probe_rates.txt"
 # 4. the default bench line (hub sources for N > 1 are measured by the 2-GPU call of the round)
