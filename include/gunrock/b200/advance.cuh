@@ -130,42 +130,22 @@ struct snapshot_t {
   }
   /// The copy's 32-bit word that holds vertex v.
   __device__ __forceinline__ unsigned load(int v) const {
-    unsigned owner, out;
+    unsigned owner;
     uint32_t addr;
     locate(v, owner, addr);
-    if (kCluster == 1 || owner == rank) {
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(out) : "r"(addr));
-    } else {
-      uint32_t remote;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(owner));
-      asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(out) : "r"(remote));
-    }
-    return out;
+    return (kCluster == 1 || owner == rank) ? ld_shared_u32(addr) : ld_dsmem_u32(addr, owner);
   }
   /// OR `word` (global state just observed for v's word) into the copy.
   __device__ __forceinline__ void merge(int v, unsigned word) const {
     unsigned owner;
     uint32_t addr;
     locate(v, owner, addr);
-    if (kCluster == 1 || owner == rank) {
-      asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(word) : "memory");
-    } else {
-      uint32_t remote;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(owner));
-      asm volatile("red.shared::cluster.or.b32 [%0], %1;" ::"r"(remote), "r"(word) : "memory");
-    }
+    if (kCluster == 1 || owner == rank)
+      red_shared_or(addr, word);
+    else
+      red_dsmem_or(addr, owner, word);
   }
 };
-__device__ __forceinline__ unsigned cluster_cta_rank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-/// Full cluster barrier (every thread of every CTA of the cluster).
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 /// Per-warp staging buffer: ballot-compacted appends, flushed with one global atomic.
 template <int kCap, bool kDegSum>
@@ -878,7 +858,7 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
   constexpr int kWarpInts = kEmitCap + kRows + (kSrc ? kRows : 0) + kRows / 2;
   static_assert(kSpan % 32 == 0 && kSpan < 65536 - 64 && kRows % 2 == 0, "span layout");
   static_assert(!kSnap || op_has_snapshot<Op>::value, "a snapshot needs the functor's snapshot protocol");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem_raw = dynamic_smem();
   // layout: [snapshot words] then per warp [emit | base | (vert) | rank (16 bit)]
   unsigned* s_snap = reinterpret_cast<unsigned*>(smem_raw);
   const int snap_words = kSnap ? (snap_bits >> 5) / kClusterN : 0;  // this CTA's slice (whole 128-byte lines)

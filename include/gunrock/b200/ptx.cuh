@@ -150,6 +150,47 @@ __device__ __forceinline__ void fence_proxy_async() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-window accesses by address, thread-block clusters and distributed shared memory (DSMEM).
+// `addr` is a shared-window address (smem_u32) valid in the calling CTA; `rank` names the CTA of the cluster
+// whose copy of that address is meant (mapa), read / updated over the SM-to-SM network.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_shared_u32(uint32_t addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void red_shared_or(uint32_t addr, unsigned value) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(value) : "memory");
+}
+__device__ __forceinline__ unsigned ld_dsmem_u32(uint32_t addr, unsigned rank) {
+  uint32_t remote;
+  unsigned v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote));
+  return v;
+}
+__device__ __forceinline__ void red_dsmem_or(uint32_t addr, unsigned rank, unsigned value) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+  asm volatile("red.shared::cluster.or.b32 [%0], %1;" ::"r"(remote), "r"(value) : "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+/// Full cluster barrier (every thread of every CTA of the cluster).
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+/// Base of the dynamic shared memory of this CTA (`extern __shared__`), 16-byte aligned.
+__device__ __forceinline__ unsigned char* dynamic_smem() {
+  extern __shared__ __align__(16) unsigned char b2g_dynamic_smem[];
+  return b2g_dynamic_smem;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Bitmap helpers (32 vertices per word).
 // ---------------------------------------------------------------------------------------------
 /// L1-cacheable weak load.  Used for the visited / frontier bitmaps: bits only ever go 0 -> 1, so
