@@ -228,6 +228,12 @@ struct advance_params_t {
 
 constexpr int kEmitCap = 128;  // ints per warp in the staging buffer
 
+/// Shared-memory ints one warp of advance_warp_path_kernel owns (must match the kernel's layout).
+template <int kSpan, bool kSrc>
+constexpr int warp_path_ints() {
+  return kEmitCap + (kSpan + 36) + (kSpan + 36) / 2 + (kSrc ? (kSpan + 36) : 0);
+}
+
 /**
  * @brief "block_mapped": equal number of frontier entries per CTA, as in the reference
  * (block_mapped.hxx:67-191: CTA loads 256 entries, block-scans their degrees, threads stride over
@@ -855,7 +861,7 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
   constexpr int kRows = kSpan + 36;  // kSpan ranks overlap at most kSpan non-empty rows (+ 33 sentinels)
   constexpr int kTicket = 8;         // spans per work-cursor atomic (lanes 0..kTicket hold their first rows)
   constexpr bool kSrc = op_needs_source<Op>::value;
-  constexpr int kWarpInts = kEmitCap + kRows + (kSrc ? kRows : 0) + kRows / 2;
+  constexpr int kWarpInts = warp_path_ints<kSpan, kSrc>();
   static_assert(kSpan % 32 == 0 && kSpan < 65536 - 64 && kRows % 2 == 0, "span layout");
   static_assert(!kSnap || op_has_snapshot<Op>::value, "a snapshot needs the functor's snapshot protocol");
   unsigned char* smem_raw = dynamic_smem();
@@ -1156,11 +1162,6 @@ struct advance_launch_t {
   int variant = 0;
 };
 
-/// Shared-memory ints one warp of advance_warp_path_kernel owns (must match the kernel's layout).
-template <int kSpan, bool kSrc>
-constexpr int warp_path_ints() {
-  return kEmitCap + (kSpan + 36) + (kSrc ? (kSpan + 36) : 0) + (kSpan + 36) / 2;
-}
 
 /// Allocate, once, everything launch_advance may need for frontiers of up to `n_upper_bound` rows of
 /// `g`, so that a later run performs no cudaMalloc / cudaFree (both synchronise the device, which a
