@@ -21,6 +21,7 @@
 
 #include "advance_kernels.gen.cuh"
 #include "functors.gen.cuh"
+#include "dense_kernels.gen.cuh"
 
 using namespace gunrock::b200;
 
@@ -330,6 +331,116 @@ static void run_and_check_tail(const graph_t& g, int start, int max_levels) {
   std::printf("tail: %d levels from %d, frontier left %d\n", rep.levels, start, rep.count);
 }
 
+/// A whole traversal: the level loop of the enactor on the host (degree scan + partition + advance per level),
+/// the kernels under emulation, the visited map and -- for the snapshot kinds -- its on-chip copies evolving
+/// from level to level.  Depths must equal a plain BFS.
+static void run_and_check_whole_bfs(const graph_t& g, int source, kind_t kind, const char* name) {
+  std::vector<unsigned> visited((g.V + 31) / 32 + 4, 0u);
+  std::vector<int> dist(g.V, 0x7fffffff);
+  visited[source >> 5] |= 1u << (source & 31);
+  dist[source] = 0;
+  std::vector<int> frontier{source};
+  int level = 0;
+  while (!frontier.empty()) {
+    const frontier_case_t f = make_frontier(g, frontier);
+    run_out_t r;
+    {  // run_bfs labels with 5: relabel through a scratch copy, keep the visited map
+      r = run_bfs(g, f, visited, kind, 3);
+      visited = r.visited;
+      for (int v : r.out)
+        dist[v] = level + 1;
+    }
+    frontier = r.out;
+    ++level;
+  }
+  std::vector<int> ref(g.V, 0x7fffffff), cur{source}, nxt;
+  ref[source] = 0;
+  for (int l = 0; !cur.empty(); ++l) {
+    nxt.clear();
+    for (int v : cur)
+      for (int e = g.ro[v]; e < g.ro[v + 1]; ++e)
+        if (ref[g.ci[e]] == 0x7fffffff) {
+          ref[g.ci[e]] = l + 1;
+          nxt.push_back(g.ci[e]);
+        }
+    cur.swap(nxt);
+  }
+  CHECK(dist == ref);
+  std::printf("whole bfs %-6s from %d: %d levels\n", name, source, level);
+}
+
+/// Kernels of the dense frontier views (framework/frontier/dense_frontier.hxx), bitmap (1 bit) and boolmap (8).
+static void run_and_check_dense_frontier(std::mt19937& rng) {
+  using namespace gunrock::frontier::detail;
+  for (int bits : {1, 8})
+    for (int universe : {1, 31, 32, 33, 1000, 4099}) {
+      const size_t n_words = bits == 1 ? (universe + 31) / 32 : (universe + 3) / 4;
+      std::vector<unsigned> words(n_words + 8, 0u);
+      std::set<int> expect;
+      std::vector<int> list;
+      for (int k = 0; k < 300; ++k) {
+        int v = static_cast<int>(rng() % universe);
+        list.push_back(k % 50 == 7 ? -1 : v);  // invalid slots are skipped
+        if (k % 50 != 7)
+          expect.insert(v);
+      }
+      const int n_list = static_cast<int>(list.size());
+      cuemu::launch(2, 64, 0, 1, [&] { dense_from_list_kernel(words.data(), bits, list.data(), &n_list); });
+      if (universe > 40) {
+        cuemu::launch(2, 64, 0, 1, [&] { dense_set_range_kernel(words.data(), bits, size_t(universe - 9), size_t(9)); });
+        for (int v = universe - 9; v < universe; ++v)
+          expect.insert(v);
+      }
+      int count = 0;
+      cuemu::launch(2, 64, 0, 1, [&] { dense_count_kernel(words.data(), n_words, bits, &count); });
+      CHECK(count == static_cast<int>(expect.size()));
+      std::vector<int> out(static_cast<size_t>(universe) + 8, -5);
+      int out_count = 0, overflow = 0;
+      cuemu::launch(2, 64, 0, 1, [&] {
+        dense_to_list_kernel(words.data(), bits, size_t(universe), out.data(), &out_count, universe, &overflow); });
+      out.resize(out_count);
+      std::sort(out.begin(), out.end());
+      CHECK(out == std::vector<int>(expect.begin(), expect.end()) && overflow == 0);
+    }
+  std::printf("dense frontier kernels ok\n");
+}
+
+/// Bucket selection of the experimental near/far SSSP schedule (sssp.cuh).
+static void run_and_check_bucket_select(const graph_t& g, std::mt19937& rng) {
+  std::vector<float> dist(g.V);
+  for (auto& d : dist) {
+    unsigned r = rng() % 100;
+    d = r < 10 ? 3.402823466e+38f : static_cast<float>(rng() % 4000) * 0.25f;  // some unreachable
+  }
+  for (auto [lo, hi] : {std::pair<float, float>{0.0f, 8.0f}, {8.0f, 16.0f}, {990.0f, 1000.25f}, {5000.0f, 5008.0f}}) {
+    std::vector<int> out(static_cast<size_t>(g.V) + 8, -1);
+    int out_count = 0;
+    unsigned long long deg_sum = 0;
+    unsigned min_far = 0xffffffffu;
+    cuemu::launch(3, 64, 0, 1, [&] {
+      sssp_select_bucket_kernel(dist.data(), g.ro.data(), g.V, lo, hi, out.data(), &out_count, &deg_sum, &min_far); });
+    std::set<int> expect;
+    unsigned long long eds = 0;
+    float far = 3.402823466e+38f;
+    for (int v = 0; v < g.V; ++v) {
+      if (dist[v] >= lo && dist[v] < hi) {
+        expect.insert(v);
+        eds += static_cast<unsigned>(g.ro[v + 1] - g.ro[v]);
+      }
+      if (dist[v] >= hi && dist[v] < 3.402823466e+38f)
+        far = std::min(far, dist[v]);
+    }
+    out.resize(out_count);
+    std::sort(out.begin(), out.end());
+    CHECK(out == std::vector<int>(expect.begin(), expect.end()));
+    CHECK(deg_sum == eds);
+    unsigned far_bits;
+    std::memcpy(&far_bits, &far, 4);
+    CHECK(far == 3.402823466e+38f ? min_far >= 0x7f7fffffu : min_far == far_bits);
+  }
+  std::printf("near/far bucket selection ok\n");
+}
+
 int main(int argc, char** argv) {
   std::mt19937 rng(argc > 1 ? std::atoi(argv[1]) : 1);
   const int seed = argc > 1 ? std::atoi(argv[1]) : 1;
@@ -367,6 +478,12 @@ int main(int argc, char** argv) {
     run_and_check_sssp(g, f, false, 2);
     run_and_check_sssp(g, f, true, 3);
   }
+  for (auto& k : kinds)
+    if (k.k == kind_t::cta2048 || k.k == kind_t::warp8 || k.k == kind_t::snap1 || k.k == kind_t::snap4)
+      run_and_check_whole_bfs(g, 0, k.k, k.name);
+  run_and_check_whole_bfs(g, g.V - 2, kind_t::snap2, "snap2");
+  run_and_check_dense_frontier(rng);
+  run_and_check_bucket_select(g, rng);
   run_and_check_tail(g, 0, 2);
   run_and_check_tail(g, g.V - 2, 16);
   if (failures == 0)
