@@ -1,7 +1,9 @@
 // tests/cuemu/emu_more.cpp -- TEST INFRASTRUCTURE: more product kernels under the CPU emulator (see cuemu.h):
 //   * lookback_scan_kernel (scan.cuh): single-pass exclusive scan / stable select with decoupled look-back;
 //   * one PageRank iteration (pr.cuh): reset, prepare (deterministic dangling sum, last-CTA fold), the TMA-tiled
-//     pull kernel and the fix-up of rows that cross tiles -- against a float64 evaluation of the same formula.
+//     pull kernel and the fix-up of rows that cross tiles -- against a float64 evaluation of the same formula;
+//   * the pull side of the direction-optimised BFS (bfs.cuh): reset, map of vertices without in-edges, queue <->
+//     bitmap, one bottom-up sweep over the visited words and one over the list of still-unvisited vertices.
 // Usage: emu_more <seed>; prints "EMU OK <checks>".
 #include <cmath>
 #include <cstdio>
@@ -11,11 +13,13 @@
 
 #include <cuemu.h>
 
-#include <gunrock/b200/ptx.cuh>
-#include <gunrock/b200/runtime.cuh>
+#include <climits>
+#include <set>
 
+#include "advance_kernels.gen.cuh"
 #include "scan_kernels.gen.cuh"
 #include "pr_kernels.gen.cuh"
+#include "bfs_kernels.gen.cuh"
 
 using namespace gunrock::b200;
 
@@ -163,10 +167,128 @@ static void check_pagerank_iteration(std::mt19937& rng) {
   }
 }
 
+/// The pull side of the direction-optimised BFS (bfs.cuh): queue <-> bitmap conversion, the map of vertices
+/// without in-edges, one bottom-up sweep over every visited word and one over the list of still-unvisited vertices.
+static void check_bottom_up(std::mt19937& rng) {
+  const int V = 5000;
+  std::vector<std::vector<int>> adj(V);
+  for (int e = 0; e < 30000; ++e) {
+    int a = static_cast<int>(V * std::pow((rng() % 100000) / 100000.0, 3.0)), b = static_cast<int>(rng() % V);
+    if (a == b || a % 9 == 4 || b % 9 == 4)
+      continue;  // vertices = 4 mod 9 stay isolated
+    adj[a].push_back(b);
+    adj[b].push_back(a);
+  }
+  std::vector<int> ro(V + 1, 0), ci;
+  for (int v = 0; v < V; ++v) {
+    std::sort(adj[v].begin(), adj[v].end());
+    adj[v].erase(std::unique(adj[v].begin(), adj[v].end()), adj[v].end());
+    ro[v + 1] = ro[v] + static_cast<int>(adj[v].size());
+    ci.insert(ci.end(), adj[v].begin(), adj[v].end());
+  }
+  ci.resize(ci.size() + 16, 0);
+  csr_view_t g;
+  g.n_vertices = V;
+  g.n_edges = ro[V];
+  g.row_offsets = ro.data();
+  g.column_indices = ci.data();
+  const int words = (V + 31) / 32;
+  // map of vertices without in-edges (symmetric graph: the isolated ones, plus the tail bits past V)
+  std::vector<unsigned> dead(words + 4, 0u);
+  cuemu::launch(2, 64, 0, 1, [&] { bfs_unreachable_map_kernel(ro.data(), V, dead.data()); });
+  bool ok = true;
+  for (int v = 0; v < words * 32; ++v)
+    ok = ok && (((dead[v >> 5] >> (v & 31)) & 1u) == (v >= V || adj[v].empty()));
+  CHECK(ok);
+  // reset from a source, then two levels top-down on the host to get a frontier worth pulling from
+  const int source = 0;
+  std::vector<int> dist(V), q0(V + 64), counts(8, 0);
+  std::vector<unsigned> visited(words + 4), fbm(words + 4, 0xdeadbeefu), nbm(words + 4, 0u);
+  cuemu::launch(2, 64, 0, 1, [&] {
+    bfs_reset_kernel(dist.data(), visited.data(), fbm.data(), V, source, q0.data(), counts.data(), dead.data()); });
+  CHECK(dist[source] == 0 && dist[1] == INT_MAX && counts[0] == 1 && q0[0] == source && fbm[3] == 0u);
+  std::vector<int> ref(V, INT_MAX), frontier{source};
+  ref[source] = 0;
+  for (int level = 0; level < 2; ++level) {
+    std::vector<int> next;
+    for (int v : frontier)
+      for (int u : adj[v])
+        if (ref[u] == INT_MAX) {
+          ref[u] = level + 1;
+          next.push_back(u);
+        }
+    frontier.swap(next);
+  }
+  for (int v = 0; v < V; ++v)
+    if (ref[v] != INT_MAX) {
+      dist[v] = ref[v];
+      visited[v >> 5] |= 1u << (v & 31);
+    }
+  // frontier queue -> bitmap
+  std::vector<int> q(frontier);
+  q.resize(V + 64);
+  int q_count = static_cast<int>(frontier.size());
+  std::fill(fbm.begin(), fbm.end(), 0u);
+  cuemu::launch(2, 64, 0, 1, [&] { queue_to_bitmap_kernel(q.data(), &q_count, fbm.data()); });
+  // level 3, bottom-up over every word; the still-unvisited vertices are collected into a list
+  ctrl_t ctrl;
+  std::memset(&ctrl, 0, sizeof ctrl);
+  std::vector<int> unv0(V + 64, -1), unv1(V + 64, -1);
+  int next_count = 0, unv_count[2] = {0, 0};
+  cuemu::launch(3, 256, 0, 1, [&] {
+    bfs_bottom_up_kernel<256, 8>(g, visited.data(), fbm.data(), nbm.data(), dist.data(), 3, &ctrl, &next_count,
+                                 unv0.data(), &unv_count[0]); });
+  std::set<int> in_frontier(frontier.begin(), frontier.end()), found, still;
+  for (int v = 0; v < V; ++v)
+    if (ref[v] == INT_MAX && !adj[v].empty()) {
+      bool hit = false;
+      for (int u : adj[v])
+        hit = hit || in_frontier.count(u);
+      (hit ? found : still).insert(v);
+    }
+  ok = next_count == static_cast<int>(found.size());
+  for (int v = 0; v < V; ++v) {
+    const bool f = found.count(v) != 0;
+    ok = ok && (((nbm[v >> 5] >> (v & 31)) & 1u) == f) && (dist[v] == (f ? 3 : ref[v]));
+    ok = ok && (((visited[v >> 5] >> (v & 31)) & 1u) == (f || ref[v] != INT_MAX || adj[v].empty()));
+  }
+  CHECK(ok);
+  std::set<int> listed(unv0.begin(), unv0.begin() + unv_count[0]);
+  CHECK(listed == still && static_cast<int>(listed.size()) == unv_count[0]);
+  CHECK(ctrl.edges > 0 && ctrl.edges <= static_cast<unsigned long long>(ro[V]));
+  // bitmap -> queue of the new frontier
+  std::vector<int> q2(V + 64, -1);
+  int q2_count = 0;
+  cuemu::launch(2, 64, 0, 1, [&] { bitmap_to_queue_kernel(nbm.data(), words, q2.data(), &q2_count); });
+  CHECK(std::set<int>(q2.begin(), q2.begin() + q2_count) == found && q2_count == static_cast<int>(found.size()));
+  // level 4, bottom-up over the LIST of unvisited vertices with the level-3 vertices as the frontier
+  std::vector<unsigned> nbm2(words + 4, 0u);
+  std::memset(&ctrl, 0, sizeof ctrl);
+  int next_count2 = 0;
+  cuemu::launch(3, 256, 0, 1, [&] {
+    bfs_bottom_up_list_kernel<256, 8>(g, unv0.data(), &unv_count[0], visited.data(), nbm.data(), nbm2.data(),
+                                      dist.data(), 4, &ctrl, &next_count2, unv1.data(), &unv_count[1]); });
+  std::set<int> found2, still2;
+  for (int v : still) {
+    bool hit = false;
+    for (int u : adj[v])
+      hit = hit || found.count(u);
+    (hit ? found2 : still2).insert(v);
+  }
+  ok = next_count2 == static_cast<int>(found2.size());
+  for (int v : found2)
+    ok = ok && dist[v] == 4 && ((nbm2[v >> 5] >> (v & 31)) & 1u) && ((visited[v >> 5] >> (v & 31)) & 1u);
+  CHECK(ok);
+  CHECK(std::set<int>(unv1.begin(), unv1.begin() + unv_count[1]) == still2);
+  std::printf("bottom-up: level 3 found %zu (sweep), level 4 found %zu (list), %zu still unvisited\n", found.size(),
+              found2.size(), still2.size());
+}
+
 int main(int argc, char** argv) {
   std::mt19937 rng(argc > 1 ? std::atoi(argv[1]) : 1);
   check_scan(rng);
   check_pagerank_iteration(rng);
+  check_bottom_up(rng);
   if (failures == 0)
     std::printf("EMU OK %d\n", checks);
   return failures == 0 ? 0 : 1;
