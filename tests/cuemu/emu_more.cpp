@@ -172,12 +172,23 @@ static void check_pagerank_iteration(std::mt19937& rng) {
 static void check_bottom_up(std::mt19937& rng) {
   const int V = 5000;
   std::vector<std::vector<int>> adj(V);
-  for (int e = 0; e < 30000; ++e) {
-    int a = static_cast<int>(V * std::pow((rng() % 100000) / 100000.0, 3.0)), b = static_cast<int>(rng() % V);
+  for (int e = 0; e < 7000; ++e) {  // a sparse, skewed core on the ids below 3000 ...
+    int a = static_cast<int>(3000 * std::pow((rng() % 100000) / 100000.0, 3.0)), b = static_cast<int>(rng() % 3000);
     if (a == b || a % 9 == 4 || b % 9 == 4)
       continue;  // vertices = 4 mod 9 stay isolated
     adj[a].push_back(b);
     adj[b].push_back(a);
+  }
+  int prev = 0;  // ... and a comb hanging off the source: discovered a few vertices per level, for many levels
+  for (int v = 3000; v < V; ++v) {
+    if (v % 9 == 4)
+      continue;
+    int parent = (v % 3 == 0) ? prev : std::max(0, v - 40);
+    if (parent % 9 == 4)
+      parent = prev;
+    adj[v].push_back(parent);
+    adj[parent].push_back(v);
+    prev = v;
   }
   std::vector<int> ro(V + 1, 0), ci;
   for (int v = 0; v < V; ++v) {
@@ -280,6 +291,7 @@ static void check_bottom_up(std::mt19937& rng) {
     ok = ok && dist[v] == 4 && ((nbm2[v >> 5] >> (v & 31)) & 1u) && ((visited[v >> 5] >> (v & 31)) & 1u);
   CHECK(ok);
   CHECK(std::set<int>(unv1.begin(), unv1.begin() + unv_count[1]) == still2);
+  CHECK(!found2.empty() && !still2.empty());  // the list kernel had something to find and something to pass on
   std::printf("bottom-up: level 3 found %zu (sweep), level 4 found %zu (list), %zu still unvisited\n", found.size(),
               found2.size(), still2.size());
 }
