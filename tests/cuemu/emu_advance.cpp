@@ -106,7 +106,7 @@ static frontier_case_t make_frontier(const graph_t& g, std::vector<int> ids) {
   return f;
 }
 
-enum class kind_t { cta2048, cta4096, warp4, warp8, snap1, snap2, snap4, binned, thread };
+enum class kind_t { cta2048, cta4096, warp4, warp8, snap1, snap2, snap4, binned, binned_plain_loads, thread };
 
 struct run_out_t {
   std::vector<int> out;
@@ -151,11 +151,13 @@ static run_out_t run_bfs(const graph_t& g, const frontier_case_t& f, const std::
   std::vector<int> rows, hubs(static_cast<size_t>(g.V) + 16, -1);
   if (kind == kind_t::thread) {
     cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_thread_mapped_kernel<256, kV, kO, true, false>(p, op); });
-  } else if (kind == kind_t::binned) {  // "block_mapped": CTA walk + the TMA-slab kernel for the deferred hub rows
+  } else if (kind == kind_t::binned || kind == kind_t::binned_plain_loads) {
+    // "block_mapped": CTA walk + the slab kernel for the deferred hub rows (cp.async.bulk staging, or -- arrays not
+    // 16-byte aligned -- plain coalesced loads)
     p.hub_threshold = 64;
     p.hubs = hubs.data();
     p.hub_capacity = static_cast<int>(hubs.size());
-    p.tma_ok = (reinterpret_cast<uintptr_t>(g.ci.data()) & 15u) == 0;
+    p.tma_ok = kind == kind_t::binned && (reinterpret_cast<uintptr_t>(g.ci.data()) & 15u) == 0;
     p.entries_per_ticket = 64;
     cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_binned_kernel<256, kV, kO, true, false>(p, op); });
     cuemu::launch(2, 256, 0, 1, [&] { advance_hub_kernel<256, 2048, kO, true, false>(p, op); });
@@ -242,7 +244,8 @@ static void check_bfs(const graph_t& g, const frontier_case_t& f, const std::vec
 }
 
 /// One relaxation sweep with the SSSP functor (reads the source id and the weights).
-static void run_and_check_sssp(const graph_t& g, const frontier_case_t& f, bool warp_path, int grid_ctas) {
+static void run_and_check_sssp(const graph_t& g, const frontier_case_t& f, int mode, int grid_ctas) {
+  const bool warp_path = mode == 1;
   const int n = static_cast<int>(f.in.size());
   std::vector<float> dist(g.V, 3.0e38f), dist0;
   for (int i = 0; i < n; ++i)
@@ -271,6 +274,15 @@ static void run_and_check_sssp(const graph_t& g, const frontier_case_t& f, bool 
     constexpr int kWarpBytes = warp_path_ints<256, true>() * 4;
     cuemu::launch(grid_ctas, 64, 2 * kWarpBytes, 1, [&] {
       advance_warp_path_kernel<64, 1, 256, 4, 0, kV, kO, true, true>(p, f.scanned.data(), 0, 0, op); });
+  } else if (mode == 2) {  // block_mapped: hub rows staged with TWO bulk copies per slab (indices + weights)
+    std::vector<int> hubs(static_cast<size_t>(g.V) + 16, -1);
+    p.hub_threshold = 64;
+    p.hubs = hubs.data();
+    p.hub_capacity = static_cast<int>(hubs.size());
+    p.tma_ok = (reinterpret_cast<uintptr_t>(g.ci.data()) & 15u) == 0 && (reinterpret_cast<uintptr_t>(g.w.data()) & 15u) == 0;
+    p.entries_per_ticket = 128;
+    cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_binned_kernel<256, kV, kO, true, true>(p, op); });
+    cuemu::launch(2, 256, 0, 1, [&] { advance_hub_kernel<256, 2048, kO, true, true>(p, op); });
   } else {
     rows = partition<2048>(f);
     p.tile_rows = rows.data();
@@ -466,7 +478,8 @@ int main(int argc, char** argv) {
   const struct { kind_t k; const char* name; int grid; } kinds[] = {
       {kind_t::cta2048, "cta2048", 3}, {kind_t::cta4096, "cta4096", 2}, {kind_t::warp4, "warp4", 3},
       {kind_t::warp8, "warp8", 2},     {kind_t::snap1, "snap1", 3},     {kind_t::snap2, "snap2", 4},
-      {kind_t::snap4, "snap4", 4},     {kind_t::binned, "binned", 3},   {kind_t::thread, "thread", 2}};
+      {kind_t::snap4, "snap4", 4},     {kind_t::binned, "binned", 3},   {kind_t::binned_plain_loads, "binned-ld", 2},
+      {kind_t::thread, "thread", 2}};
   for (auto& ids : frontiers) {
     const frontier_case_t f = make_frontier(g, ids);
     for (auto& k : kinds) {
@@ -475,8 +488,9 @@ int main(int argc, char** argv) {
       std::printf("bfs %-8s frontier %4zu rows %7d edges -> %5zu claimed\n", k.name, f.in.size(), f.scanned.back(),
                   r.out.size());
     }
-    run_and_check_sssp(g, f, false, 2);
-    run_and_check_sssp(g, f, true, 3);
+    run_and_check_sssp(g, f, 0, 2);
+    run_and_check_sssp(g, f, 1, 3);
+    run_and_check_sssp(g, f, 2, 2);
   }
   for (auto& k : kinds)
     if (k.k == kind_t::cta2048 || k.k == kind_t::warp8 || k.k == kind_t::snap1 || k.k == kind_t::snap4)
