@@ -2,9 +2,10 @@
 //
 // It exists so that kernel LOGIC (index arithmetic, work distribution, compaction, functor protocols) can be
 // exercised by the CPU test suite: a kernel template from include/gunrock/b200/*.cuh is compiled by g++ with the
-// CUDA keywords defined away and run with one OS thread per CUDA thread.  Warp collectives (__shfl*, __ballot,
-// __reduce_or, __syncwarp) exchange through a per-warp barrier, __syncthreads is a per-CTA barrier, atomics are
-// the compiler's, `__shared__` arrays are function statics (CTAs run one after the other) and dynamic shared
+// CUDA keywords defined away and run with one OS thread per WARP, the 32 lanes being cooperatively scheduled
+// fibers on it: a lane runs until it reaches a warp collective (__shfl*, __ballot, __reduce_or, __syncwarp) or a
+// barrier, then its warp mates get the thread -- lanes are never in lockstep, so a missing __syncwarp shows.
+// __syncthreads / barrier.cluster are OS barriers between the warps' threads, atomics are the compiler's, `__shared__` arrays are function statics (CTAs run one after the other) and dynamic shared
 // memory is a per-CTA buffer -- the CTAs of a thread-block cluster run concurrently and reach each other's
 // buffer for the distributed-shared-memory helpers.  Inline PTX is confined to gunrock/b200/ptx.cuh, which this
 // directory shadows with a plain C++ version (tests/cuemu/gunrock/b200/ptx.cuh).
@@ -25,6 +26,8 @@
 #include <thread>
 #include <vector>
 
+#include <ucontext.h>
+
 #define __global__
 #define __device__
 #define __host__
@@ -42,22 +45,38 @@ struct dim3_t {
   unsigned x = 1, y = 1, z = 1;
 };
 
-struct warp_ctx {
-  std::barrier<> bar{32};
-  unsigned long long slot[32];
-};
 struct cluster_ctx;
+struct cta_ctx;
+
+/// One warp = one OS thread that runs its 32 lanes as cooperatively scheduled fibers (ucontext): a lane runs
+/// until it reaches a warp collective or a barrier, then the next runnable lane gets the thread.  Warp
+/// collectives therefore cost a user-space context switch, not a futex.
+struct warp_ctx {
+  static constexpr std::size_t kStack = 256 * 1024;
+  ucontext_t scheduler;
+  ucontext_t lane_ctx[32];
+  std::vector<unsigned char> stacks;
+  bool done[32];
+  int alive = 32;    // lanes that have not left the kernel
+  int arrived = 0;   // lanes waiting at the current warp-level rendezvous
+  unsigned gen = 0;  // rendezvous generation
+  unsigned long long slot[32];
+  unsigned index = 0;  // warp index in the CTA
+  cta_ctx* cta = nullptr;
+  const std::function<void()>* body = nullptr;
+};
 struct cta_ctx {
   unsigned nthreads = 0;
-  std::unique_ptr<std::barrier<>> bar;
+  std::unique_ptr<std::barrier<>> bar;  // one participant per warp (its OS thread)
   std::vector<std::unique_ptr<warp_ctx>> warps;
   std::vector<unsigned char> smem;  // dynamic shared memory
   unsigned rank = 0;                // rank in the cluster
+  unsigned block = 0;               // blockIdx.x
   cluster_ctx* cluster = nullptr;
 };
 struct cluster_ctx {
   std::vector<cta_ctx*> ctas;
-  std::unique_ptr<std::barrier<>> bar;  // every thread of every CTA
+  std::unique_ptr<std::barrier<>> bar;  // one participant per warp of every CTA
 };
 
 inline thread_local cta_ctx* t_cta = nullptr;
@@ -71,6 +90,67 @@ inline cuemu::dim3_t blockDim, gridDim;
 
 namespace cuemu {
 
+/// Give the OS thread to the next lane of this warp (called by a lane that has to wait for its warp mates).
+inline void yield() {
+  warp_ctx* w = t_warp;
+  swapcontext(&w->lane_ctx[t_lane], &w->scheduler);
+}
+/// All lanes of the warp that are still inside the kernel meet here.
+inline void warp_rendezvous() {
+  warp_ctx* w = t_warp;
+  if (++w->arrived == w->alive) {
+    w->arrived = 0;
+    ++w->gen;
+    return;
+  }
+  const unsigned my_gen = w->gen;
+  while (w->gen == my_gen)
+    yield();
+}
+/// The first lane still alive does the OS-level part of a block / cluster barrier for its warp.
+inline bool is_warp_leader() {
+  warp_ctx* w = t_warp;
+  for (unsigned l = 0; l < 32; ++l)
+    if (!w->done[l])
+      return l == t_lane;
+  return false;
+}
+inline void lane_trampoline(unsigned lane) {
+  warp_ctx* w = t_warp;
+  (*w->body)();
+  w->done[lane] = true;
+  --w->alive;
+  if (w->alive > 0 && w->arrived == w->alive) {  // the others were only waiting for this lane
+    w->arrived = 0;
+    ++w->gen;
+  }
+  swapcontext(&w->lane_ctx[lane], &w->scheduler);  // never resumed
+}
+inline void run_warp(warp_ctx* w) {
+  t_warp = w;
+  t_cta = w->cta;
+  ::blockIdx.x = w->cta->block;
+  w->stacks.resize(32 * warp_ctx::kStack);
+  for (unsigned l = 0; l < 32; ++l) {
+    w->done[l] = false;
+    getcontext(&w->lane_ctx[l]);
+    w->lane_ctx[l].uc_stack.ss_sp = w->stacks.data() + l * warp_ctx::kStack;
+    w->lane_ctx[l].uc_stack.ss_size = warp_ctx::kStack;
+    w->lane_ctx[l].uc_link = &w->scheduler;
+    makecontext(&w->lane_ctx[l], reinterpret_cast<void (*)()>(lane_trampoline), 1, l);
+  }
+  while (w->alive > 0)
+    for (unsigned l = 0; l < 32; ++l)
+      if (!w->done[l]) {
+        t_lane = l;
+        ::threadIdx.x = w->index * 32 + l;
+        swapcontext(&w->scheduler, &w->lane_ctx[l]);
+      }
+  // a warp that has left the kernel no longer takes part in block / cluster barriers (as on the GPU)
+  w->cta->bar->arrive_and_drop();
+  w->cta->cluster->bar->arrive_and_drop();
+}
+
 /// Run `body` as a kernel: grid x block threads, `cluster` consecutive CTAs at a time (1 = plain launch).
 /// blockDim.x must be a multiple of 32.
 inline void launch(unsigned grid, unsigned block, std::size_t dynamic_smem_bytes, unsigned cluster,
@@ -81,38 +161,32 @@ inline void launch(unsigned grid, unsigned block, std::size_t dynamic_smem_bytes
   }
   ::blockDim.x = block;
   ::gridDim.x = grid;
+  const unsigned warps = block / 32;
   for (unsigned first = 0; first < grid; first += cluster) {
     cluster_ctx cl;
-    cl.bar = std::make_unique<std::barrier<>>(static_cast<std::ptrdiff_t>(cluster) * block);
+    cl.bar = std::make_unique<std::barrier<>>(static_cast<std::ptrdiff_t>(cluster) * warps);
     std::vector<std::unique_ptr<cta_ctx>> ctas;
     for (unsigned r = 0; r < cluster; ++r) {
       auto c = std::make_unique<cta_ctx>();
       c->nthreads = block;
-      c->bar = std::make_unique<std::barrier<>>(static_cast<std::ptrdiff_t>(block));
-      for (unsigned w = 0; w < block / 32; ++w)
+      c->bar = std::make_unique<std::barrier<>>(static_cast<std::ptrdiff_t>(warps));
+      for (unsigned w = 0; w < warps; ++w) {
         c->warps.push_back(std::make_unique<warp_ctx>());
+        c->warps.back()->index = w;
+        c->warps.back()->cta = c.get();
+        c->warps.back()->body = &body;
+      }
       c->smem.assign(dynamic_smem_bytes + 64, 0xCD);  // poison: nothing may rely on zeroed shared memory
       c->rank = r;
+      c->block = first + r;
       c->cluster = &cl;
       cl.ctas.push_back(c.get());
       ctas.push_back(std::move(c));
     }
     std::vector<std::thread> threads;
     for (unsigned r = 0; r < cluster; ++r)
-      for (unsigned t = 0; t < block; ++t)
-        threads.emplace_back([&, r, t] {
-          cta_ctx* c = ctas[r].get();
-          t_cta = c;
-          t_warp = c->warps[t / 32].get();
-          t_lane = t % 32;
-          ::threadIdx.x = t;
-          ::blockIdx.x = first + r;
-          body();
-          // a thread that has left the kernel no longer takes part in any barrier (as on the GPU)
-          t_warp->bar.arrive_and_drop();
-          c->bar->arrive_and_drop();
-          cl.bar->arrive_and_drop();
-        });
+      for (unsigned w = 0; w < warps; ++w)
+        threads.emplace_back(run_warp, ctas[r]->warps[w].get());
     for (auto& th : threads)
       th.join();
   }
@@ -125,9 +199,9 @@ inline T exchange(T v, unsigned src_lane) {
   unsigned long long raw = 0;
   std::memcpy(&raw, &v, sizeof v);
   w->slot[t_lane] = raw;
-  w->bar.arrive_and_wait();
+  warp_rendezvous();
   raw = w->slot[src_lane & 31];
-  w->bar.arrive_and_wait();  // nobody overwrites a slot somebody still reads
+  warp_rendezvous();  // nobody overwrites a slot somebody still reads
   T out;
   std::memcpy(&out, &raw, sizeof out);
   return out;
@@ -135,12 +209,25 @@ inline T exchange(T v, unsigned src_lane) {
 inline unsigned gather_or(unsigned mine) {
   warp_ctx* w = t_warp;
   w->slot[t_lane] = mine;
-  w->bar.arrive_and_wait();
+  warp_rendezvous();
   unsigned all = 0;
   for (int l = 0; l < 32; ++l)
-    all |= static_cast<unsigned>(w->slot[l]);
-  w->bar.arrive_and_wait();
+    if (!w->done[l])
+      all |= static_cast<unsigned>(w->slot[l]);
+  warp_rendezvous();
   return all;
+}
+/// Block-level (cluster == false) or cluster-level barrier: lanes meet in their warp, the warp's leader meets
+/// the other warps at the OS barrier, then the lanes are released.
+inline void wide_barrier(bool cluster) {
+  warp_rendezvous();
+  if (is_warp_leader()) {
+    if (cluster)
+      t_cta->cluster->bar->arrive_and_wait();
+    else
+      t_cta->bar->arrive_and_wait();
+  }
+  warp_rendezvous();
 }
 
 }  // namespace cuemu
@@ -169,10 +256,10 @@ inline unsigned __reduce_or_sync(unsigned, unsigned v) {
   return cuemu::gather_or(v);
 }
 inline void __syncwarp(unsigned = 0xffffffffu) {
-  cuemu::t_warp->bar.arrive_and_wait();
+  cuemu::warp_rendezvous();
 }
 inline void __syncthreads() {
-  cuemu::t_cta->bar->arrive_and_wait();
+  cuemu::wide_barrier(false);
 }
 
 // ---- scalar intrinsics ------------------------------------------------------------------------------------

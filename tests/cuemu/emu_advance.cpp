@@ -456,7 +456,7 @@ static void run_and_check_bucket_select(const graph_t& g, std::mt19937& rng) {
 int main(int argc, char** argv) {
   std::mt19937 rng(argc > 1 ? std::atoi(argv[1]) : 1);
   const int seed = argc > 1 ? std::atoi(argv[1]) : 1;
-  const graph_t g = make_graph(seed % 2 ? 6000 : 8000, seed % 2 ? 6 : 7, rng);
+  const graph_t g = make_graph(seed % 2 ? 6000 : 20000, seed % 2 ? 6 : 9, rng);
   std::vector<unsigned> visited0((g.V + 31) / 32 + 4, 0u);
   for (int i = 0; i < g.V / 5; ++i) {
     int v = static_cast<int>(rng() % g.V);

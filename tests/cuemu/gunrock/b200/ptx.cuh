@@ -88,7 +88,7 @@ inline void red_dsmem_or(uint32_t addr, unsigned rank, unsigned value) {
   __atomic_fetch_or(cuemu_word(cuemu_peer(rank), addr), value, __ATOMIC_SEQ_CST);
 }
 inline unsigned cluster_cta_rank() { return cuemu::t_cta->rank; }
-inline void cluster_barrier() { cuemu::t_cta->cluster->bar->arrive_and_wait(); }
+inline void cluster_barrier() { cuemu::wide_barrier(true); }
 
 // ---- mbarrier + bulk copy: the copy happens at issue, the barrier word keeps (phase, pending bytes) --------
 inline void mbar_init(uint64_t* bar, uint32_t) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
@@ -108,7 +108,7 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity))
-    std::this_thread::yield();
+    cuemu::yield();  // the copy may be issued by a warp mate that has not run yet
 }
 inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   std::memcpy(dst_smem, src_gmem, bytes);
