@@ -106,7 +106,7 @@ static frontier_case_t make_frontier(const graph_t& g, std::vector<int> ids) {
   return f;
 }
 
-enum class kind_t { cta2048, cta4096, warp4, warp8, snap1, snap2, snap4, binned, binned_plain_loads, thread };
+enum class kind_t { cta2048, cta4096, warp4, warp8, snap1, snap2, snap4, snap1_full, snap4_full, binned, binned_plain_loads, thread };
 
 struct run_out_t {
   std::vector<int> out;
@@ -197,6 +197,21 @@ static run_out_t run_bfs(const graph_t& g, const frontier_case_t& f, const std::
         const int bits = snap_bits_for(2);
         cuemu::launch((grid_ctas + 1) / 2 * 2, kThreads, stage + bits / 8 / 2, 2, [&] {
           advance_warp_path_kernel<kThreads, 1, 256, 8, 2, kV, kO, true, false>(p, f.scanned.data(), bits, map_words, op); });
+        break;
+      }
+      case kind_t::snap1_full:
+      case kind_t::snap4_full: {
+        // the launcher's shapes: 1024-thread CTAs (32 warps), 8 chunks in flight, a copy of 24 lines per CTA
+        constexpr int kFull = 1024;
+        const int k = kind == kind_t::snap1_full ? 1 : 4;
+        const int bits = 24 * 1024 * k;
+        const size_t smem = (kFull / 32) * kWarpBytes + static_cast<size_t>(bits) / 8 / k;
+        if (k == 1)
+          cuemu::launch(2, kFull, smem, 1, [&] {
+            advance_warp_path_kernel<kFull, 1, 256, 8, 1, kV, kO, true, false>(p, f.scanned.data(), bits, map_words, op); });
+        else
+          cuemu::launch(4, kFull, smem, 4, [&] {
+            advance_warp_path_kernel<kFull, 1, 256, 8, 4, kV, kO, true, false>(p, f.scanned.data(), bits, map_words, op); });
         break;
       }
       default: {
@@ -478,7 +493,8 @@ int main(int argc, char** argv) {
   const struct { kind_t k; const char* name; int grid; } kinds[] = {
       {kind_t::cta2048, "cta2048", 3}, {kind_t::cta4096, "cta4096", 2}, {kind_t::warp4, "warp4", 3},
       {kind_t::warp8, "warp8", 2},     {kind_t::snap1, "snap1", 3},     {kind_t::snap2, "snap2", 4},
-      {kind_t::snap4, "snap4", 4},     {kind_t::binned, "binned", 3},   {kind_t::binned_plain_loads, "binned-ld", 2},
+      {kind_t::snap4, "snap4", 4},     {kind_t::snap1_full, "snap1-1024", 2}, {kind_t::snap4_full, "snap4-1024", 4},
+      {kind_t::binned, "binned", 3},   {kind_t::binned_plain_loads, "binned-ld", 2},
       {kind_t::thread, "thread", 2}};
   for (auto& ids : frontiers) {
     const frontier_case_t f = make_frontier(g, ids);
@@ -493,7 +509,8 @@ int main(int argc, char** argv) {
     run_and_check_sssp(g, f, 2, 2);
   }
   for (auto& k : kinds)
-    if (k.k == kind_t::cta2048 || k.k == kind_t::warp8 || k.k == kind_t::snap1 || k.k == kind_t::snap4)
+    if (k.k == kind_t::cta2048 || k.k == kind_t::warp8 || k.k == kind_t::snap1 || k.k == kind_t::snap4 ||
+        k.k == kind_t::snap4_full)
       run_and_check_whole_bfs(g, 0, k.k, k.name);
   run_and_check_whole_bfs(g, g.V - 2, kind_t::snap2, "snap2");
   run_and_check_dense_frontier(rng);
