@@ -852,7 +852,7 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
  * that decides today as well.
  */
 template <int kThreads, int kMinCtas, int kSpan, int kB, int kSnapCluster, advance_input_t kIn,
-          advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
+          advance_output_t kOut, bool kDegSum, bool kWeights, typename Op, bool kPrefetch = false>
 __global__ void __launch_bounds__(kThreads, kMinCtas)
 advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, int snap_bits, int map_words,
                          Op op) {
@@ -910,25 +910,44 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
     const int last = min(nspans, first + kTicket);
     // p.tile_rows[k] = row holding rank k * kSpan (n past the end): entries 0 .. nspans exist
     const int my_row = (first + lane <= last) ? p.tile_rows[first + lane] : 0;
+    // kPrefetch: the first 32 rows of the NEXT span's window are loaded before the current span is walked, so
+    // a span whose window has at most 32 rows (any frontier of average degree >= 8) starts without a round of
+    // memory latency; further rows of a longer window are loaded as before.
+    int pf_sc = 0, pf_next = 0, pf_rb = 0, pf_vv = 0;
+    auto load_row = [&](int i, int row_hi, int& sc, int& sc_next, int& rb, int& vv) {
+      if (i <= row_hi) {
+        sc = scanned[i];
+        sc_next = scanned[i + 1];
+        rb = p.row_base[i];
+        if (kSrc)
+          vv = (kIn == advance_input_t::graph) ? i : p.in[i];
+      }
+    };
+    if (kPrefetch)
+      load_row(__shfl_sync(kFull, my_row, 0) + lane, min(n - 1, __shfl_sync(kFull, my_row, 1)), pf_sc, pf_next,
+               pf_rb, pf_vv);
     for (int sp = first; sp < last; ++sp) {
       const int row0 = __shfl_sync(kFull, my_row, sp - first);
       const int row1 = min(n - 1, __shfl_sync(kFull, my_row, sp - first + 1));
       const int r_begin = sp * kSpan;
       const int r_end = min(total, r_begin + kSpan);
+      const int cur_sc = pf_sc, cur_next = pf_next, cur_rb = pf_rb, cur_vv = pf_vv;
+      if (kPrefetch && sp + 1 < last)  // uniform: the whole warp takes the branch
+        load_row(__shfl_sync(kFull, my_row, sp - first + 1) + lane,
+                 min(n - 1, __shfl_sync(kFull, my_row, sp - first + 2)), pf_sc, pf_next, pf_rb, pf_vv);
       // ---- stage the rows that overlap [r_begin, r_end) ------------------------------------
       int nrows = 0;  // warp-uniform
       for (int i0 = row0; i0 <= row1; i0 += 32) {
         const int i = i0 + lane;
-        int sc = 0, rb = 0, vv = 0;
+        int sc = 0, sc_next = 0, rb = 0, vv = 0;
         bool live = false;
-        if (i <= row1) {
-          sc = scanned[i];
-          const int sc_next = scanned[i + 1];
-          rb = p.row_base[i];
-          if (kSrc)
-            vv = (kIn == advance_input_t::graph) ? i : p.in[i];
-          live = sc_next > sc && sc < r_end && sc_next > r_begin;
+        if (kPrefetch && i0 == row0) {
+          sc = cur_sc, sc_next = cur_next, rb = cur_rb, vv = cur_vv;
+        } else {
+          load_row(i, row1, sc, sc_next, rb, vv);
         }
+        if (i <= row1)
+          live = sc_next > sc && sc < r_end && sc_next > r_begin;
         const unsigned m = __ballot_sync(kFull, live);
         if (live) {
           const int slot = nrows + __popc(m & lanemask_lt());
@@ -1159,6 +1178,7 @@ struct advance_launch_t {
   ///   4  warp-private spans, 256-thread CTAs, 8 chunks in flight
   ///   5  as 2, the copy spread over a CLUSTER of 2 CTAs (distributed shared memory): twice the coverage
   ///   6  as 2, cluster of 4: 5 M vertices on chip (the whole visited map of a scale-22 graph)
+  ///   7  as 4, the next span's row window prefetched while the current span is walked
   int variant = 0;
 };
 
@@ -1290,7 +1310,7 @@ inline void launch_warp_path_snapshot(workspace_t& ws, advance_params_t& p, cons
     B2G_CHECK(cudaLaunchKernelEx(&lc, kv, p, scanned, snap_bits, map_words, op));
 }
 
-/// EXPERIMENTAL variants 1 / 2 / 4 / 5 / 6: span partition + advance_warp_path_kernel.
+/// EXPERIMENTAL variants 1 / 2 / 4 / 5 / 6 / 7: span partition + advance_warp_path_kernel.
 template <advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
 inline void launch_warp_path(workspace_t& ws, advance_params_t& p, const int* scanned, bool graph_in,
                              const advance_launch_t& cfg, Op op) {
@@ -1323,7 +1343,14 @@ inline void launch_warp_path(workspace_t& ws, advance_params_t& p, const int* sc
   constexpr int kThreads = 256;
   const int smem = (kThreads / 32) * kWarpBytes;
   const int grid = sms * cfg.ctas_per_sm;
-  if (cfg.variant == 4) {
+  if (cfg.variant == 7) {
+    if (graph_in)
+      advance_warp_path_kernel<kThreads, 4, kSpan, 8, 0, kGraph, kOut, kDegSum, kWeights, Op, true>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
+    else
+      advance_warp_path_kernel<kThreads, 4, kSpan, 8, 0, kVerts, kOut, kDegSum, kWeights, Op, true>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
+  } else if (cfg.variant == 4) {
     if (graph_in)
       advance_warp_path_kernel<kThreads, 4, kSpan, 8, 0, kGraph, kOut, kDegSum, kWeights>
           <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);

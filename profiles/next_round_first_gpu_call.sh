@@ -15,7 +15,7 @@ done
 # 2b. experimental merge_path kernels (advance.cuh advance_launch_t::variant): default vs warp-private spans
 #     (1: 6 CTAs/SM, 4: more loads in flight), warp-private + shared-memory visited snapshot (2; 5 / 6: spread over a
 #     cluster of 2 / 4 CTAs through distributed shared memory), 4096-edge tiles (3)
-for v in 0 1 2 3 4 5 6; do
+for v in 0 1 2 3 4 5 6 7; do
   B2G_ADVANCE_VARIANT=$v python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/bfs_push_variant_$v.json"
   B2G_ADVANCE_VARIANT=$v python bench.py --workload sssp_rmat24 --lb merge_path --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/sssp_variant_$v.json"
   python - "$OUT" $v <<'PY'

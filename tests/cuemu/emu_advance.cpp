@@ -106,7 +106,7 @@ static frontier_case_t make_frontier(const graph_t& g, std::vector<int> ids) {
   return f;
 }
 
-enum class kind_t { cta2048, cta4096, warp4, warp8, snap1, snap2, snap4, snap1_full, snap4_full, binned, binned_plain_loads, thread };
+enum class kind_t { cta2048, cta4096, warp4, warp8, warp8pf, snap1, snap2, snap4, snap1_full, snap4_full, binned, binned_plain_loads, thread };
 
 struct run_out_t {
   std::vector<int> out;
@@ -186,6 +186,11 @@ static run_out_t run_bfs(const graph_t& g, const frontier_case_t& f, const std::
       case kind_t::warp8:
         cuemu::launch(grid_ctas, kThreads, stage, 1, [&] {
           advance_warp_path_kernel<kThreads, 1, 256, 8, 0, kV, kO, true, false>(p, f.scanned.data(), 0, 0, op); });
+        break;
+      case kind_t::warp8pf:  // + the next span's row window prefetched during the walk
+        cuemu::launch(grid_ctas, kThreads, stage, 1, [&] {
+          advance_warp_path_kernel<kThreads, 1, 256, 8, 0, kV, kO, true, false, bfs_claim_op, true>(
+              p, f.scanned.data(), 0, 0, op); });
         break;
       case kind_t::snap1: {
         const int bits = snap_bits_for(1);
@@ -287,8 +292,12 @@ static void run_and_check_sssp(const graph_t& g, const frontier_case_t& f, int m
     rows = partition<256>(f);
     p.tile_rows = rows.data();
     constexpr int kWarpBytes = warp_path_ints<256, true>() * 4;
-    cuemu::launch(grid_ctas, 64, 2 * kWarpBytes, 1, [&] {
-      advance_warp_path_kernel<64, 1, 256, 4, 0, kV, kO, true, true>(p, f.scanned.data(), 0, 0, op); });
+    if (grid_ctas % 2)
+      cuemu::launch(grid_ctas, 64, 2 * kWarpBytes, 1, [&] {
+        advance_warp_path_kernel<64, 1, 256, 4, 0, kV, kO, true, true>(p, f.scanned.data(), 0, 0, op); });
+    else  // with the row-window prefetch (source ids travel with the prefetched rows)
+      cuemu::launch(grid_ctas, 64, 2 * kWarpBytes, 1, [&] {
+        advance_warp_path_kernel<64, 1, 256, 4, 0, kV, kO, true, true, sssp_relax_op, true>(p, f.scanned.data(), 0, 0, op); });
   } else if (mode == 2) {  // block_mapped: hub rows staged with TWO bulk copies per slab (indices + weights)
     std::vector<int> hubs(static_cast<size_t>(g.V) + 16, -1);
     p.hub_threshold = 64;
@@ -492,7 +501,7 @@ int main(int argc, char** argv) {
   frontiers.push_back(everyone);  // every row, the isolated ones included: many rows per span, many spans
   const struct { kind_t k; const char* name; int grid; } kinds[] = {
       {kind_t::cta2048, "cta2048", 3}, {kind_t::cta4096, "cta4096", 2}, {kind_t::warp4, "warp4", 3},
-      {kind_t::warp8, "warp8", 2},     {kind_t::snap1, "snap1", 3},     {kind_t::snap2, "snap2", 4},
+      {kind_t::warp8, "warp8", 2},     {kind_t::warp8pf, "warp8pf", 3}, {kind_t::snap1, "snap1", 3},     {kind_t::snap2, "snap2", 4},
       {kind_t::snap4, "snap4", 4},     {kind_t::snap1_full, "snap1-1024", 2}, {kind_t::snap4_full, "snap4-1024", 4},
       {kind_t::binned, "binned", 3},   {kind_t::binned_plain_loads, "binned-ld", 2},
       {kind_t::thread, "thread", 2}};
@@ -506,10 +515,11 @@ int main(int argc, char** argv) {
     }
     run_and_check_sssp(g, f, 0, 2);
     run_and_check_sssp(g, f, 1, 3);
+    run_and_check_sssp(g, f, 1, 2);
     run_and_check_sssp(g, f, 2, 2);
   }
   for (auto& k : kinds)
-    if (k.k == kind_t::cta2048 || k.k == kind_t::warp8 || k.k == kind_t::snap1 || k.k == kind_t::snap4 ||
+    if (k.k == kind_t::cta2048 || k.k == kind_t::warp8 || k.k == kind_t::warp8pf || k.k == kind_t::snap1 || k.k == kind_t::snap4 ||
         k.k == kind_t::snap4_full)
       run_and_check_whole_bfs(g, 0, k.k, k.name);
   run_and_check_whole_bfs(g, g.V - 2, kind_t::snap2, "snap2");

@@ -70,7 +70,7 @@ def variant_env():
         os.environ["B2G_ADVANCE_VARIANT"] = old
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
 def test_merge_path_variants_one_level_exact(built, variant_env, variant):
     """One advance level with the BFS claim functor through b2g_advance_bfs, merge_path, for frontiers that
     stress the span staging: two hubs, every vertex (degree-0 rows included), duplicates, a single short
@@ -123,7 +123,7 @@ def test_merge_path_variants_one_level_exact(built, variant_env, variant):
         G.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
 def test_merge_path_variants_full_runs_bit_exact(built, variant_env, variant):
     """Whole BFS / SSSP runs at a size where the enactors really pick merge_path (frontier out-degree
     above 2^20): depths / distances equal to the default kernels' bit for bit, and to the oracle."""
