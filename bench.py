@@ -579,6 +579,8 @@ def main():
                    "level_frontier": last.level_frontier, "level_edges": last.level_edges[:last.iterations],
                    "level_kernel_ms": [round(x, 4) for x in last.level_kernel_ms[:last.iterations]],
                    "edges_touched_per_step": agg["edges"] // args.steps, "runs": runs,
+                   "experimental": {"B2G_ADVANCE_VARIANT": os.environ.get("B2G_ADVANCE_VARIANT", "0"),
+                                    "B2G_SSSP_DELTA": os.environ.get("B2G_SSSP_DELTA", "")},
                    "graph500_mteps": (G.n_edges * (len(sources) * world if world > 1 else 1)) / (ms / args.steps) / 1e3},
         "e2e": {"value": e2e, "unit": "MTEPS", "h2d_bytes_per_step": 4 * (len(sources) if world > 1 else 1),
                 "d2h_bytes_per_step": out_bytes * (len(sources) if world > 1 else 1), "ms_per_step": ms_e2e / args.steps},
