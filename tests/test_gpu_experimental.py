@@ -70,8 +70,16 @@ def variant_env():
         os.environ["B2G_ADVANCE_VARIANT"] = old
 
 
+@pytest.fixture(scope="module")
+def level_graphs():
+    """Host CSRs shared by every variant (2^21 / 2^23 vertices: ids past the on-chip copies)."""
+    import oracle
+    return [(scale, *oracle.rmat_csr(scale, ef, seed))
+            for scale, ef, seed in ((5, 4, 1), (12, 8, 13), (16, 16, 5), (21, 2, 99), (23, 1, 7))]
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
-def test_merge_path_variants_one_level_exact(built, variant_env, variant):
+def test_merge_path_variants_one_level_exact(built, variant_env, level_graphs, variant):
     """One advance level with the BFS claim functor through b2g_advance_bfs, merge_path, for frontiers that
     stress the span staging: two hubs, every vertex (degree-0 rows included), duplicates, a single short
     row, vertices beyond the on-chip copy of the visited map (variant 2: 1.27 M bits; 5 / 6: a cluster's 2x / 4x).  Each unvisited neighbour is claimed exactly once."""
@@ -82,8 +90,7 @@ def test_merge_path_variants_one_level_exact(built, variant_env, variant):
     variant_env(variant)
     INT_MAX = 2**31 - 1
     rng = np.random.default_rng(variant)
-    for scale, ef, seed in ((5, 4, 1), (12, 8, 13), (16, 16, 5), (21, 2, 99), (23, 1, 7)):   # 2^21 / 2^23 vertices: ids past the copy
-        ro, ci = oracle.rmat_csr(scale, ef, seed)
+    for scale, ro, ci in level_graphs:
         V = 1 << scale
         G = gb.graph_t.from_csr(ro, ci, None, symmetric=True)
         deg = np.diff(ro)
