@@ -12,6 +12,17 @@ namespace b200 {
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
+/// Event counters (relaxed, approximate under concurrency): how often each memory path was taken.
+struct cuemu_counters_t {
+  unsigned long long cached_probes = 0;   // ld_cached: L1-cached global probes (visited / frontier bitmaps)
+  unsigned long long shared_probes = 0;   // ld_shared_u32: on-chip copy, own CTA
+  unsigned long long dsmem_probes = 0;    // ld_dsmem_u32: on-chip copy, another CTA of the cluster
+  unsigned long long shared_merges = 0;   // red_shared_or + red_dsmem_or
+  unsigned long long stream_loads = 0;    // ld_stream (column indices / weights)
+};
+inline cuemu_counters_t cuemu_counters;
+inline void cuemu_count(unsigned long long& c) { __atomic_fetch_add(&c, 1ull, __ATOMIC_RELAXED); }
+
 inline int lane_id() { return static_cast<int>(threadIdx.x & 31); }
 inline unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 
@@ -36,7 +47,10 @@ inline float warp_max(float x) {
   return x;
 }
 
-inline int ld_stream(const int* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline int ld_stream(const int* p) {
+  cuemu_count(cuemu_counters.stream_loads);
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+}
 inline float ld_stream(const float* p) { return *p; }
 inline unsigned ld_relaxed(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 inline int ld_relaxed(const int* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
@@ -68,9 +82,11 @@ inline unsigned* cuemu_word(cuemu::cta_ctx* c, uint32_t addr) {
   return reinterpret_cast<unsigned*>(c->smem.data() + addr);
 }
 inline unsigned ld_shared_u32(uint32_t addr) {
+  cuemu_count(cuemu_counters.shared_probes);
   return __atomic_load_n(cuemu_word(cuemu::t_cta, addr), __ATOMIC_RELAXED);
 }
 inline void red_shared_or(uint32_t addr, unsigned value) {
+  cuemu_count(cuemu_counters.shared_merges);
   __atomic_fetch_or(cuemu_word(cuemu::t_cta, addr), value, __ATOMIC_SEQ_CST);
 }
 inline cuemu::cta_ctx* cuemu_peer(unsigned rank) {
@@ -82,9 +98,11 @@ inline cuemu::cta_ctx* cuemu_peer(unsigned rank) {
   return cl->ctas[rank];
 }
 inline unsigned ld_dsmem_u32(uint32_t addr, unsigned rank) {
+  cuemu_count(cuemu_counters.dsmem_probes);
   return __atomic_load_n(cuemu_word(cuemu_peer(rank), addr), __ATOMIC_RELAXED);
 }
 inline void red_dsmem_or(uint32_t addr, unsigned rank, unsigned value) {
+  cuemu_count(cuemu_counters.shared_merges);
   __atomic_fetch_or(cuemu_word(cuemu_peer(rank), addr), value, __ATOMIC_SEQ_CST);
 }
 inline unsigned cluster_cta_rank() { return cuemu::t_cta->rank; }
@@ -117,7 +135,10 @@ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint6
 inline void fence_proxy_async() {}
 
 // ---- bitmap helpers ----------------------------------------------------------------------------------------
-inline unsigned ld_cached(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline unsigned ld_cached(const unsigned* p) {
+  cuemu_count(cuemu_counters.cached_probes);
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+}
 inline bool bitmap_test(const unsigned* bm, int v) { return (ld_cached(bm + (v >> 5)) >> (v & 31)) & 1u; }
 inline bool bitmap_test_and_set(unsigned* bm, int v) {
   unsigned bit = 1u << (v & 31);
