@@ -477,6 +477,92 @@ static void run_and_check_bucket_select(const graph_t& g, std::mt19937& rng) {
   std::printf("near/far bucket selection ok\n");
 }
 
+/// The near/far SSSP schedule end to end: the level loop of sssp_run_near_far (sssp.cuh) restated on the host, its
+/// kernels and functor (sssp_near_far_op, sssp_select_bucket_kernel, merge_path advance) under emulation; the
+/// distances must be those of Dijkstra's algorithm in fp32, bit for bit.
+static void run_and_check_near_far(const graph_t& g, int source, float delta) {
+  std::vector<float> dist(g.V, 3.402823466e+38f);
+  std::vector<int> stamp(g.V, -1), q[2] = {std::vector<int>(g.V + 64), std::vector<int>(g.V + 64)};
+  dist[source] = 0.0f;
+  q[0][0] = source;
+  int cur = 0, iteration = 0, n_f = 1;
+  float hi = delta;
+  unsigned long long relaxed = 0;
+  for (;;) {
+    while (n_f > 0) {
+      const frontier_case_t f = make_frontier(g, std::vector<int>(q[cur].begin(), q[cur].begin() + n_f));
+      int out_count = 0;
+      ctrl_t ctrl;
+      std::memset(&ctrl, 0, sizeof ctrl);
+      advance_params_t p;
+      p.g = g.view();
+      p.in = f.in.data();
+      p.in_count = &n_f;
+      p.out = q[cur ^ 1].data();
+      p.out_count = &out_count;
+      p.out_capacity = static_cast<int>(q[cur ^ 1].size());
+      p.ctrl = &ctrl;
+      p.row_base = f.row_base.data();
+      sssp_near_far_op op{dist.data(), stamp.data(), iteration, hi};
+      std::vector<int> rows = partition<2048>(f);
+      p.tile_rows = rows.data();
+      cuemu::launch(2, 256, 0, 1, [&] {
+        advance_merge_path_kernel<256, 2048, advance_input_t::vertices, advance_output_t::vertices, true, true>(
+            p, f.scanned.data(), op); });
+      relaxed += ctrl.edges;
+      n_f = out_count;
+      cur ^= 1;
+      ++iteration;
+    }
+    float lo = hi;
+    for (int attempt = 0; attempt < 2 && n_f == 0; ++attempt) {
+      float up = lo + delta;
+      if (!(up > lo))
+        up = std::nextafterf(lo, 3.402823466e+38f);
+      int count = 0;
+      unsigned long long deg_sum = 0;
+      unsigned min_far = 0xffffffffu;
+      cuemu::launch(2, 64, 0, 1, [&] {
+        sssp_select_bucket_kernel(dist.data(), g.ro.data(), g.V, lo, up, q[cur].data(), &count, &deg_sum, &min_far); });
+      n_f = count;
+      hi = up;
+      if (n_f == 0) {
+        if (min_far >= 0x7f7fffffu)
+          goto done;
+        std::memcpy(&lo, &min_far, 4);
+      }
+    }
+    CHECK(n_f > 0);
+    if (n_f == 0)
+      break;
+  }
+done:
+  // Dijkstra in fp32 (the least fixed point of d[v] = min fl(d[u] + w))
+  std::vector<float> ref(g.V, 3.402823466e+38f);
+  std::multimap<float, int> heap{{0.0f, source}};
+  ref[source] = 0.0f;
+  while (!heap.empty()) {
+    auto [d, v] = *heap.begin();
+    heap.erase(heap.begin());
+    if (d > ref[v])
+      continue;
+    for (int e = g.ro[v]; e < g.ro[v + 1]; ++e) {
+      float nd = d + g.w[e];
+      if (nd < ref[g.ci[e]]) {
+        ref[g.ci[e]] = nd;
+        heap.insert({nd, g.ci[e]});
+      }
+    }
+  }
+  CHECK(std::memcmp(ref.data(), dist.data(), sizeof(float) * g.V) == 0);
+  unsigned long long reached_edges = 0;
+  for (int v = 0; v < g.V; ++v)
+    if (ref[v] < 3.402823466e+38f)
+      reached_edges += static_cast<unsigned>(g.ro[v + 1] - g.ro[v]);
+  std::printf("near/far delta %.1f: %d advance iterations, %.2f relaxations per reached edge\n", delta, iteration,
+              static_cast<double>(relaxed) / static_cast<double>(reached_edges));
+}
+
 int main(int argc, char** argv) {
   std::mt19937 rng(argc > 1 ? std::atoi(argv[1]) : 1);
   const int seed = argc > 1 ? std::atoi(argv[1]) : 1;
@@ -523,6 +609,8 @@ int main(int argc, char** argv) {
         k.k == kind_t::snap4_full)
       run_and_check_whole_bfs(g, 0, k.k, k.name);
   run_and_check_whole_bfs(g, g.V - 2, kind_t::snap2, "snap2");
+  for (float delta : {4.0f, 16.5f, 1000.0f})
+    run_and_check_near_far(g, 0, delta);
   run_and_check_dense_frontier(rng);
   run_and_check_bucket_select(g, rng);
   run_and_check_tail(g, 0, 2);
