@@ -99,9 +99,9 @@ static frontier_case_t make_frontier(const graph_t& g, std::vector<int> ids) {
   f.scanned.assign(n + 1, 0);
   f.row_base.assign(n + 2, 0);
   for (int i = 0; i < n; ++i) {
-    int v = f.in[i];
-    f.scanned[i + 1] = f.scanned[i] + (g.ro[v + 1] - g.ro[v]);
-    f.row_base[i] = g.ro[v];
+    int v = f.in[i];  // -1 = invalid slot of a bypass-filtered frontier: no edges (advance.cuh frontier_degree_scan)
+    f.scanned[i + 1] = f.scanned[i] + (v >= 0 ? g.ro[v + 1] - g.ro[v] : 0);
+    f.row_base[i] = v >= 0 ? g.ro[v] : 0;
   }
   return f;
 }
@@ -235,6 +235,8 @@ static void check_bfs(const graph_t& g, const frontier_case_t& f, const std::vec
   std::set<int> expect;
   unsigned long long total = 0, deg_sum = 0;
   for (int v : f.in) {
+    if (v < 0)
+      continue;
     total += static_cast<unsigned>(g.ro[v + 1] - g.ro[v]);
     for (int e = g.ro[v]; e < g.ro[v + 1]; ++e) {
       int d = g.ci[e];
@@ -261,6 +263,59 @@ static void check_bfs(const graph_t& g, const frontier_case_t& f, const std::vec
   }
   CHECK(labels);
   CHECK(bits);
+}
+
+/// Robustness of the default kernels: an output frontier that is too small must raise ctrl.overflow and never
+/// write past its capacity; a full hub list keeps the rows in the CTA walk.
+static void run_and_check_limits(const graph_t& g, const frontier_case_t& f, const std::vector<unsigned>& visited0) {
+  const int n = static_cast<int>(f.in.size());
+  constexpr auto kV = advance_input_t::vertices;
+  constexpr auto kO = advance_output_t::vertices;
+  for (int which = 0; which < 3; ++which) {
+    std::vector<unsigned> visited = visited0;
+    std::vector<int> dist(g.V, 0x7fffffff), out(static_cast<size_t>(g.V) + 64, -7), hubs(8, -1);
+    const int cap = which == 2 ? static_cast<int>(out.size()) : 100;  // 0, 1: too small on purpose
+    int out_count = 0;
+    ctrl_t ctrl;
+    std::memset(&ctrl, 0, sizeof ctrl);
+    advance_params_t p;
+    p.g = g.view();
+    p.in = f.in.data();
+    p.in_count = &n;
+    p.out = out.data();
+    p.out_count = &out_count;
+    p.out_capacity = cap;
+    p.ctrl = &ctrl;
+    p.row_base = f.row_base.data();
+    bfs_claim_op op{visited.data(), dist.data(), 5};
+    if (which == 0) {
+      std::vector<int> rows = partition<2048>(f);
+      p.tile_rows = rows.data();
+      cuemu::launch(2, 256, 0, 1, [&] { advance_merge_path_kernel<256, 2048, kV, kO, true, false>(p, f.scanned.data(), op); });
+    } else {
+      p.hub_threshold = 64;
+      p.hubs = hubs.data();
+      p.hub_capacity = which == 2 ? 2 : static_cast<int>(hubs.size());  // 2: the hub list overflows
+      p.tma_ok = 1;
+      cuemu::launch(2, 256, 0, 1, [&] { advance_binned_kernel<256, kV, kO, true, false>(p, op); });
+      cuemu::launch(2, 256, 0, 1, [&] { advance_hub_kernel<256, 2048, kO, true, false>(p, op); });
+    }
+    if (which == 2) {  // nothing may be lost when the hub list is full
+      run_out_t r;
+      r.out.assign(out.begin(), out.begin() + out_count);
+      r.visited = visited;
+      r.dist = dist;
+      r.ctrl = ctrl;
+      r.ctrl.hub_count = 0;
+      check_bfs(g, f, visited0, r, "hub list full");
+    } else {
+      CHECK(ctrl.overflow == 1);
+      bool untouched = true;
+      for (size_t i = cap; i < out.size(); ++i)
+        untouched = untouched && out[i] == -7;
+      CHECK(untouched);
+    }
+  }
 }
 
 /// One relaxation sweep with the SSSP functor (reads the source id and the weights).
@@ -582,6 +637,10 @@ int main(int argc, char** argv) {
   mixed.push_back(3);
   frontiers.push_back(mixed);
   frontiers.push_back({g.V - 2});
+  std::vector<int> holes = mixed;  // a bypass-filtered frontier: invalid slots between the ids
+  for (size_t i = 0; i < holes.size(); i += 3)
+    holes[i] = -1;
+  frontiers.push_back(holes);
   std::vector<int> everyone(g.V);
   std::iota(everyone.begin(), everyone.end(), 0);
   frontiers.push_back(everyone);  // every row, the isolated ones included: many rows per span, many spans
@@ -599,6 +658,10 @@ int main(int argc, char** argv) {
       std::printf("bfs %-8s frontier %4zu rows %7d edges -> %5zu claimed\n", k.name, f.in.size(), f.scanned.back(),
                   r.out.size());
     }
+    if (f.scanned.back() > 2000)
+      run_and_check_limits(g, f, visited0);
+    if (std::find(f.in.begin(), f.in.end(), -1) != f.in.end())
+      continue;  // the SSSP sweep below labels its sources
     run_and_check_sssp(g, f, 0, 2);
     run_and_check_sssp(g, f, 1, 3);
     run_and_check_sssp(g, f, 1, 2);
