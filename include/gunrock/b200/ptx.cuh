@@ -98,6 +98,22 @@ __device__ __forceinline__ void st_release(unsigned long long* p, unsigned long 
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+/// System-scope release / acquire on a 32-bit flag (peer-memory barriers between GPUs, bfs_p2p.cuh).
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+/// Nanosecond wall clock of the GPU (time-outs of spinning barriers).
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (cp.async.bulk, executed by the TMA unit; SASS UBLKCP).
 // ---------------------------------------------------------------------------------------------

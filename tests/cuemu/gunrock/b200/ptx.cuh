@@ -4,6 +4,8 @@
 // path, so the kernel headers pick this file up unchanged.
 #pragma once
 
+#include <chrono>
+
 #include <cuemu.h>
 
 namespace gunrock {
@@ -62,6 +64,13 @@ inline float ld_relaxed(const float* p) {
 }
 inline unsigned long long ld_acquire(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void st_release(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+
+inline void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned ld_acquire_sys(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline unsigned long long global_timer_ns() {
+  return static_cast<unsigned long long>(std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                             std::chrono::steady_clock::now().time_since_epoch()).count());
+}
 
 // ---- shared-window addresses: offsets into the CTA's dynamic shared memory --------------------------------
 inline unsigned char* dynamic_smem() { return cuemu::t_cta->smem.data(); }
