@@ -1,6 +1,6 @@
 #!/bin/bash
-# What was left unmeasured when round 1's GPU budget ran out -- one 1-GPU gpurun call (~6 min on the box):
-#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash profiles/next_round_first_gpu_call.sh'
+# What was left unmeasured when round 1's GPU budget ran out -- one 1-GPU gpurun call:
+#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash profiles/next_round_first_gpu_call.sh'   (about 25-30 GPU-minutes)
 # Results land in gpurun_out/next_round/.  Nothing printed under a profiler is a bench value.
 set -u
 OUT=gpurun_out/next_round
