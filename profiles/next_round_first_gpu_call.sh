@@ -13,6 +13,8 @@ want() { [[ "$SECTIONS" == all || " $SECTIONS " == *" $1 "* ]]; }
 # variants: the experimental merge_path kernels (advance.cuh advance_launch_t::variant) on the headline workload:
 #   0 default | 1 warp-private spans (6 CTAs/SM) | 4 same, 8 chunks in flight | 7 = 4 + row-window prefetch
 #   2 warp-private + on-chip visited copy (one CTA) | 5 / 6 copy over a cluster of 2 / 4 CTAs (DSMEM) | 3 4096-edge tiles
+# A variant's number counts only once its bit-exactness tests (section "tests") pass; a first sanity check is
+# printed here: edges touched (the out-degree sum of the reached vertices) must not depend on the variant.
 if want variants; then
   for v in 0 1 4 7 2 5 6 3; do
     B2G_ADVANCE_VARIANT=$v python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/bfs_push_variant_$v.json"
@@ -22,7 +24,8 @@ out, v = sys.argv[1], sys.argv[2]
 try:
     j = json.loads(open(f"{out}/bfs_push_variant_{v}.json").read())
     print(f"variant {v} bfs_push: {j['value']:.0f} MTEPS, {j['ms_per_step']:.3f} ms/step, roofline {j['roofline']['frac']:.3f}, "
-          f"level ms {j['config']['level_kernel_ms'][:6]}")
+          f"level ms {j['config']['level_kernel_ms'][:6]}, edges touched {j['config']['edges_touched_per_step']} "
+          f"(must equal variant 0's), levels {j['config']['levels']}")
 except Exception as ex:
     print(f"variant {v} bfs_push: no line ({ex})")
 PY
