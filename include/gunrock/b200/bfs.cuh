@@ -182,6 +182,37 @@ static __global__ void bitmap_to_queue_kernel(const unsigned* __restrict__ bm, i
   }
 }
 
+/// Enumerate the CLEAR bits of the visited map below n_vertices (the still-unvisited vertices) into a queue.
+/// EXPERIMENTAL (B2G_BFS_PULL_LIST_FIRST): lets the FIRST pull level run on the dense list kernel as well.
+static __global__ void bfs_unvisited_list_kernel(const unsigned* __restrict__ visited, int n_vertices, int* q,
+                                                 int* count) {
+  const int lane = lane_id();
+  const int words = (n_vertices + 31) / 32;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int w0 = gw * 32; w0 < words; w0 += warps * 32) {
+    const int wi = w0 + lane;
+    unsigned w = wi < words ? ~visited[wi] : 0u;
+    if (wi == words - 1 && (n_vertices & 31))
+      w &= (1u << (n_vertices & 31)) - 1u;  // bits past the last vertex are not vertices
+    const int c = __popc(w);
+    const int incl = warp_inclusive_sum(c);
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (!total)
+      continue;
+    int base = 0;
+    if (lane == 0)
+      base = atomicAdd(count, total);
+    base = __shfl_sync(kFull, base, 0) + incl - c;
+    const int vb = wi << 5;
+    while (w) {
+      const int b = __ffs(w) - 1;
+      w &= w - 1;
+      q[base++] = vb + b;
+    }
+  }
+}
+
 /**
  * @brief Bottom-up sweep.  One warp owns one 32-vertex word of the visited map, so the map and
  * the next-frontier map are updated with plain stores (no atomics).  Each lane walks its
@@ -575,6 +606,17 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       sc.unv[0].ensure(static_cast<size_t>(V) + 64);
       sc.unv[1].ensure(static_cast<size_t>(V) + 64);
       B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 2, 0, sizeof(int), st));
+      // EXPERIMENTAL, off unless B2G_BFS_PULL_LIST_FIRST is set: list the unvisited vertices first (one pass over
+      // the visited map) so that the first pull level runs with every lane busy too, instead of sweeping words in
+      // which most lanes hold visited or edge-less vertices
+      static const bool list_first = std::getenv("B2G_BFS_PULL_LIST_FIRST") != nullptr;
+      if (!unv_valid && list_first) {
+        B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));
+        bfs_unvisited_list_kernel<<<sms * 8, 256, 0, st>>>(sc.visited.ptr, V, sc.unv[0].ptr, sc.counts.ptr + 4);
+        ws.launches += 1;
+        unv_cur = 0;
+        unv_valid = true;
+      }
       if (!unv_valid) {  // first pull level of a run of pull levels: sweep every visited word
         B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));
         bfs_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(

@@ -58,6 +58,23 @@ for f in sorted(glob.glob(sys.argv[1] + "/sssp_*.json")):
 PY
 fi
 
+# do: direction-optimised BFS (configs[4] at one GPU): default pull levels vs the unvisited list from the first one
+if want do; then
+  for wl in bfs_do_rmat22 bfs_do_rmat26; do
+    python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/${wl}_default.json"
+    B2G_BFS_PULL_LIST_FIRST=1 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/${wl}_list_first.json"
+  done
+  python - "$OUT" <<'PY' | tee "$OUT/do.txt"
+import glob, json, sys
+for f in sorted(glob.glob(sys.argv[1] + "/bfs_do_*.json")):
+    try:
+        j = json.loads(open(f).read())
+        print(f"{f.split('/')[-1]}: {j['ms_per_step']:.3f} ms/step, level ms {j['config']['level_kernel_ms'][:8]}, directions {j['config']['level_direction'][:8]}")
+    except Exception as ex:
+        print(f"{f}: no line ({ex})")
+PY
+fi
+
 # refgpu: same-GPU baseline, the UNMODIFIED reference GPU kernels (oracle/_ref/gunrock_ref_gpu) on the bench graph
 if want refgpu; then
   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --reference-gpu 2>&1 | tail -1 > "$OUT/bench_with_reference_gpu.json"

@@ -264,6 +264,32 @@ static void check_bottom_up(std::mt19937& rng) {
     ok = ok && (((visited[v >> 5] >> (v & 31)) & 1u) == (f || ref[v] != INT_MAX || adj[v].empty()));
   }
   CHECK(ok);
+  {  // the same level through the experimental route: list the unvisited vertices first, then the list kernel
+    std::vector<unsigned> visited_b(words + 4, 0u), nbm_b(words + 4, 0u);
+    std::vector<int> dist_b(V);
+    for (int v = 0; v < V; ++v) {
+      dist_b[v] = ref[v];
+      if (ref[v] != INT_MAX || adj[v].empty())
+        visited_b[v >> 5] |= 1u << (v & 31);
+    }
+    std::vector<int> todo(V + 64, -1), left(V + 64, -1);
+    int todo_count = 0, left_count = 0, found_b = 0;
+    cuemu::launch(3, 64, 0, 1, [&] { bfs_unvisited_list_kernel(visited_b.data(), V, todo.data(), &todo_count); });
+    std::set<int> want_todo(found.begin(), found.end());
+    want_todo.insert(still.begin(), still.end());
+    CHECK(std::set<int>(todo.begin(), todo.begin() + todo_count) == want_todo && todo_count == static_cast<int>(want_todo.size()));
+    ctrl_t ctrl_b;
+    std::memset(&ctrl_b, 0, sizeof ctrl_b);
+    cuemu::launch(3, 256, 0, 1, [&] {
+      bfs_bottom_up_list_kernel<256, 8>(g, todo.data(), &todo_count, visited_b.data(), fbm.data(), nbm_b.data(),
+                                        dist_b.data(), 3, &ctrl_b, &found_b, left.data(), &left_count); });
+    CHECK(found_b == next_count && dist_b == dist && std::set<int>(left.begin(), left.begin() + left_count) == still);
+    bool same_maps = true;  // (bits past V differ: the reset kernel pre-marks them, this route never looks at them)
+    for (int v = 0; v < V; ++v)
+      same_maps = same_maps && (((nbm_b[v >> 5] ^ nbm[v >> 5]) >> (v & 31)) & 1u) == 0 &&
+                  (((visited_b[v >> 5] ^ visited[v >> 5]) >> (v & 31)) & 1u) == 0;
+    CHECK(same_maps);
+  }
   std::set<int> listed(unv0.begin(), unv0.begin() + unv_count[0]);
   CHECK(listed == still && static_cast<int>(listed.size()) == unv_count[0]);
   CHECK(ctrl.edges > 0 && ctrl.edges <= static_cast<unsigned long long>(ro[V]));

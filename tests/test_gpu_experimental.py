@@ -155,3 +155,36 @@ def test_merge_path_variants_full_runs_bit_exact(built, variant_env, variant):
     assert np.array_equal(f0.view(np.uint32), f1.view(np.uint32))
     assert np.array_equal(f1.view(np.uint32), oracle.sssp(ro, ci, w, src).view(np.uint32))
     G.close()
+
+
+DO_WORKER = r"""
+import json, sys
+sys.path.insert(0, %r)
+import numpy as np
+import oracle
+import gunrock_b200 as gb
+res = {}
+for scale, ef, seed in ((10, 8, 3), (15, 16, 0x5EED26), (17, 8, 9)):
+    ro, ci = oracle.rmat_csr(scale, ef, seed)
+    G = gb.graph_t.from_csr(ro, ci, None, symmetric=True)
+    deg = np.diff(ro)
+    for src in (int(deg.argmax()), int(np.flatnonzero(deg > 0)[-1])):
+        exp = oracle.bfs(ro, ci, src)
+        for direction in (gb.advance_direction_t.optimized, gb.advance_direction_t.backward):
+            d = np.empty(G.n_vertices, np.int32)
+            st = gb.bfs(G, src, d, options=gb.options_t(advance_direction=direction))
+            res[f"s{scale}/src{src}/dir{direction}"] = [bool(np.array_equal(d, exp)), st.level_direction]
+    G.close()
+print("RESULT " + json.dumps(res))
+"""
+
+
+def test_pull_levels_on_the_unvisited_list_from_the_first_one(built):
+    """B2G_BFS_PULL_LIST_FIRST: the first pull level lists the unvisited vertices (bfs_unvisited_list_kernel) and runs
+    the dense list kernel instead of the word sweep -- same depths (env read once per process: subprocess)."""
+    env = dict(os.environ, B2G_BFS_PULL_LIST_FIRST="1")
+    r = subprocess.run([sys.executable, "-c", DO_WORKER % ROOT], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert all(v[0] for v in out.values()), {k: v for k, v in out.items() if not v[0]}
+    assert any(1 in v[1] for v in out.values())            # pull levels did run
