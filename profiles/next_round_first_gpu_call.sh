@@ -47,6 +47,10 @@ if want sssp; then
   for v in 1 4 7 3; do
     B2G_ADVANCE_VARIANT=$v python bench.py --workload sssp_rmat24 --lb merge_path --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/sssp_variant_$v.json"
   done
+  # configs[2] proper (block_mapped): which rows should go to the TMA hub bin?
+  for h in 1024 4096 16384 65536; do
+    python bench.py --workload sssp_rmat24 --hub-threshold $h --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/sssp_block_mapped_hub_$h.json"
+  done
   python - "$OUT" <<'PY' | tee "$OUT/sssp.txt"
 import glob, json, sys
 for f in sorted(glob.glob(sys.argv[1] + "/sssp_*.json")):
