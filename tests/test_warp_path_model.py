@@ -245,3 +245,18 @@ def test_snapshot_protocol_claims_every_vertex_exactly_once(k):
     exp = oracle.bfs(ro, ci, src)
     assert np.array_equal(np.where(depth < 0, 2**31 - 1, depth), exp)
     assert probes < edges                                        # the copies did answer some probes
+
+
+def test_probe_line_locality_script_runs():
+    """profiles/micro/probe_line_locality.py (the host count behind DESIGN.md 9.2: a warp-wide probe of 32 consecutive
+    sorted neighbours touches far fewer than 32 bitmap lines) stays runnable."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "profiles", "micro", "probe_line_locality.py"), "14"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = re.search(r"A row-major: ([\d.]+) probe wavefronts per edge \(([\d.]+) lines per 32-edge chunk", r.stdout)
+    assert m and float(m.group(2)) < 16.0
