@@ -278,6 +278,58 @@ int main() {
     CHECK(std::equal(ref.begin(), ref.end(), hd.begin()));
   }
 
+  // ---- multi-hop expansion with an always-true functor: frontiers full of duplicates whose expansion
+  //      exceeds max(E, V) slots (the reference sizes every output from the degree scan,
+  //      block_mapped.hxx:205-217; here the degree sum is read only for frontiers that may hold duplicates)
+  for (auto lb_case : {0, 1, 2}) {
+    frontier_t a, b;
+    thrust::device_vector<int> segments;
+    a.push_back(0);
+    a.push_back(0);
+    a.push_back(0);  // the hub three times: 1497 slots after one hop
+    auto all = [] __host__ __device__(vertex_t const&, vertex_t const&, edge_t const&, weight_t const&) -> bool {
+      return true;
+    };
+    frontier_t* cur = &a;
+    frontier_t* nxt = &b;
+    std::vector<long long> want_sizes;
+    std::vector<long long> cnt(n, 0), nxt_cnt(n, 0);
+    cnt[0] = 3;
+    for (int hop = 0; hop < 4; ++hop) {
+      if (lb_case == 0)
+        operators::advance::execute<operators::load_balance_t::merge_path, operators::advance_direction_t::forward,
+                                    operators::advance_io_type_t::vertices, operators::advance_io_type_t::vertices>(
+            G, all, cur, nxt, segments, ctx);
+      else if (lb_case == 1)
+        operators::advance::execute<operators::load_balance_t::block_mapped, operators::advance_direction_t::forward,
+                                    operators::advance_io_type_t::vertices, operators::advance_io_type_t::vertices>(
+            G, all, cur, nxt, segments, ctx);
+      else
+        operators::advance::execute<operators::load_balance_t::thread_mapped, operators::advance_direction_t::forward,
+                                    operators::advance_io_type_t::vertices, operators::advance_io_type_t::vertices>(
+            G, all, cur, nxt, segments, ctx);
+      std::swap(cur, nxt);
+      // host model: multiplicity of every vertex after the hop
+      std::fill(nxt_cnt.begin(), nxt_cnt.end(), 0);
+      long long total = 0;
+      for (int v = 0; v < n; ++v)
+        for (int e = ro[v]; e < ro[v + 1]; ++e) {
+          nxt_cnt[ci[e]] += cnt[v];
+          total += cnt[v];
+        }
+      cnt.swap(nxt_cnt);
+      CHECK(static_cast<long long>(cur->get_number_of_elements()) == total);
+      if (hop == 3) {
+        CHECK(total > static_cast<long long>(G.get_number_of_edges()));  // the case max(E,V) cannot hold
+        auto h = to_host(*cur);
+        std::vector<long long> got(n, 0);
+        for (int x : h)
+          ++got[x];
+        CHECK(got == cnt);
+      }
+    }
+  }
+
   // ---- launch_box_t --------------------------------------------------------------------------------
   {
     using namespace gcuda;

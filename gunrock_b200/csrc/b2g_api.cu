@@ -138,6 +138,8 @@ struct b2g_graph {
     ws.init(own_stream);
   }
   void set_views() {
+    if (!view.uid)
+      view.uid = next_graph_uid();  // identity for the per-graph caches (graph_key_t)
     view.n_vertices = n_vertices;
     view.n_edges = n_edges;
     if (owns) {
@@ -913,11 +915,11 @@ int b2g_part_bfs_begin(b2g_graph_t* g, int source, int send_capacity) {
     const unsigned* premark = nullptr;
     if (g->symmetric) {  // the local CSR doubles as the local CSC only for symmetric graphs
       build_transpose(g);
-      if (S.unreachable_for != g->t_view.row_offsets) {
+      if (!S.unreachable_for.matches(g->t_view)) {
         S.unreachable.ensure(static_cast<size_t>(S.words_per_rank()) + 4);
         bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(g->t_view.row_offsets, g->pt.n_local,
                                                             S.unreachable.ptr);
-        S.unreachable_for = g->t_view.row_offsets;
+        S.unreachable_for.set(g->t_view);
         g->ws.launches += 1;
       }
       premark = S.unreachable.ptr;
@@ -1286,10 +1288,11 @@ int b2g_part_pr_begin(b2g_graph_t* g, float alpha, const int* outdeg_global) {
       S.t.row_offsets = g->view.row_offsets;
       S.t.column_indices = S.remapped.ptr;
       S.t.values = nullptr;
+      S.t.uid = next_graph_uid();
       const int ntiles = g->n_edges > 0 ? (g->n_edges + kPrTile - 1) / kPrTile : 1;
       pr_tile_table_kernel<<<sms * 2, 256, 0, st>>>(S.t.row_offsets, S.n_local, ntiles,
                                                     S.sc.first_owned.ptr);
-      S.sc.tiled_offsets = S.t.row_offsets;
+      S.sc.tiled_for.set(S.t);
       g->ws.launches += 2;
     }
     part_pr_reset_kernel<<<sms * 8, 256, 0, st>>>(S.n_local, S.nparts, S.part, S.n_global, alpha,
@@ -1582,11 +1585,11 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
     const unsigned* premark = nullptr;
     if (can_pull) {
       build_transpose(g);
-      if (S.unreachable_for != g->t_view.row_offsets) {
+      if (!S.unreachable_for.matches(g->t_view)) {
         S.unreachable.ensure(static_cast<size_t>(S.words_per_rank()) + 4);
         bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(g->t_view.row_offsets, g->pt.n_local,
                                                             S.unreachable.ptr);
-        S.unreachable_for = g->t_view.row_offsets;
+        S.unreachable_for.set(g->t_view);
       }
       premark = S.unreachable.ptr;
     }

@@ -107,18 +107,6 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
   }
 };
 
-namespace detail {
-/// Per-context scratch of the fused enactor, created on first use and kept for later runs.
-inline b200::bfs_scratch_t& scratch_for(gcuda::standard_context_t* ctx) {
-  thread_local std::vector<std::pair<gcuda::standard_context_t*, std::unique_ptr<b200::bfs_scratch_t>>> pool;
-  for (auto& e : pool)
-    if (e.first == ctx)
-      return *e.second;
-  pool.emplace_back(ctx, std::unique_ptr<b200::bfs_scratch_t>(new b200::bfs_scratch_t()));
-  return *pool.back().second;
-}
-}  // namespace detail
-
 template <typename graph_t>
 float run(graph_t& G,
           param_t<typename graph_t::vertex_type>& param,
@@ -157,7 +145,7 @@ float run(graph_t& G,
   auto& timer = ctx->timer();
   timer.reset();
   timer.begin(ctx->stream());
-  int depth = b200::bfs_run(ws, detail::scratch_for(ctx), out_view, in_view,
+  int depth = b200::bfs_run(ws, ctx->template scratch<b200::bfs_scratch_t>(), out_view, in_view,
                             static_cast<int>(param.single_source), result.distances, cfg, &levels);
   float ms = timer.end(ctx->stream());
   auto& bench = benchmark::detail::current();

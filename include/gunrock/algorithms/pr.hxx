@@ -145,19 +145,12 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
 };
 
 namespace detail {
+/// Per-context cache of the fused PageRank (owned by the context: gcuda::standard_context_t::scratch).
 struct pr_cache_t {
   b200::pr_scratch_t scratch;
   b200::transpose_t transpose;
-  const void* transposed_offsets = nullptr;  // identity of the CSR the cached transpose belongs to
+  b200::graph_key_t transposed_for;  // the CSR the cached transpose was built from (identity, not address)
 };
-inline pr_cache_t& cache_for(gcuda::standard_context_t* ctx) {
-  thread_local std::vector<std::pair<gcuda::standard_context_t*, std::unique_ptr<pr_cache_t>>> pool;
-  for (auto& e : pool)
-    if (e.first == ctx)
-      return *e.second;
-  pool.emplace_back(ctx, std::unique_ptr<pr_cache_t>(new pr_cache_t()));
-  return *pool.back().second;
-}
 }  // namespace detail
 
 template <typename graph_t>
@@ -183,7 +176,7 @@ float run(graph_t& G,
   error::throw_if_exception(context->size() != 1, "`context.size() != 1` not supported");
   auto ctx = context->get_context(0);
   auto& ws = ctx->workspace();
-  auto& cache = detail::cache_for(ctx);
+  auto& cache = ctx->template scratch<detail::pr_cache_t>();
   b200::csr_view_t out_view = G.csr_view();
   b200::csr_view_t in_view;
   if (G.has_csc()) {
@@ -191,9 +184,9 @@ float run(graph_t& G,
   } else if (G.properties.symmetric) {
     in_view = out_view;
   } else {
-    if (cache.transposed_offsets != out_view.row_offsets) {  // ingest step, outside the timed loop
-      cache.transpose.build(ws, out_view);
-      cache.transposed_offsets = out_view.row_offsets;
+    if (!cache.transposed_for.matches(out_view)) {  // ingest step, outside the timed loop
+      cache.transpose.build(ws, out_view);            // (gives the transpose a fresh identity, so the
+      cache.transposed_for.set(out_view);             //  tile table keyed on it is rebuilt as well)
     }
     in_view = cache.transpose.view;
   }

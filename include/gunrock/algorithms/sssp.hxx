@@ -113,17 +113,6 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
   }
 };
 
-namespace detail {
-inline b200::sssp_scratch_t& scratch_for(gcuda::standard_context_t* ctx) {
-  thread_local std::vector<std::pair<gcuda::standard_context_t*, std::unique_ptr<b200::sssp_scratch_t>>> pool;
-  for (auto& e : pool)
-    if (e.first == ctx)
-      return *e.second;
-  pool.emplace_back(ctx, std::unique_ptr<b200::sssp_scratch_t>(new b200::sssp_scratch_t()));
-  return *pool.back().second;
-}
-}  // namespace detail
-
 template <typename graph_t>
 float run(graph_t& G,
           param_t<typename graph_t::vertex_type>& param,
@@ -152,7 +141,7 @@ float run(graph_t& G,
   auto& timer = ctx->timer();
   timer.reset();
   timer.begin(ctx->stream());
-  int iters = b200::sssp_run(ws, detail::scratch_for(ctx), G.csr_view(),
+  int iters = b200::sssp_run(ws, ctx->template scratch<b200::sssp_scratch_t>(), G.csr_view(),
                              static_cast<int>(param.single_source), result.distances, cfg, &levels);
   float ms = timer.end(ctx->stream());
   auto& bench = benchmark::detail::current();

@@ -1222,6 +1222,48 @@ inline const int* frontier_degree_scan(workspace_t& ws,
   return scanned;
 }
 
+/// Sum of the out-degrees of a vertex frontier (invalid entries count 0), for exact output sizing.
+static __global__ void frontier_degree_total_kernel(csr_view_t g, const int* __restrict__ in,
+                                                    const int* __restrict__ in_count, ctrl_t* ctrl) {
+  const int n = *in_count;
+  unsigned long long sum = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int v = in[i];
+    if (v >= 0 && v < g.n_vertices)
+      sum += static_cast<unsigned>(g.row_offsets[v + 1] - g.row_offsets[v]);
+  }
+  sum = warp_sum(sum);
+  if (lane_id() == 0 && sum)
+    atomicAdd(&ctrl->deg_sum, sum);
+}
+static __global__ void publish_degree_total_kernel(const ctrl_t* ctrl, workspace_t::host_value_t* h, int seq) {
+  h->value = ctrl->deg_sum;
+  __threadfence_system();
+  h->seq = seq;
+}
+
+/**
+ * @brief The exact number of output slots an advance over `in` can produce: the out-degree sum of the
+ * frontier, read back through pinned memory (one cheap poll, no stream synchronise).  This is what the
+ * reference computes -- and blocks on -- before EVERY advance (advance/helpers.hxx:127-161,
+ * block_mapped.hxx:205-217); here it is only needed for frontiers that may hold the same vertex more than
+ * once, whose expansion is not bounded by the number of edges of the graph.
+ */
+inline unsigned long long frontier_degree_total(workspace_t& ws, const csr_view_t& g, const int* in,
+                                                const int* in_count, int in_upper_bound) {
+  const int sms = device_info_t::get().sm_count;
+  ctrl_t* c = ws.next_ctrl();
+  auto* h = ws.host_value();
+  int blocks = (in_upper_bound + 255) / 256;
+  blocks = blocks < 1 ? 1 : (blocks > sms * 8 ? sms * 8 : blocks);
+  frontier_degree_total_kernel<<<blocks, 256, 0, ws.stream>>>(g, in, in_count, c);
+  publish_degree_total_kernel<<<1, 1, 0, ws.stream>>>(c, h, ++ws.value_seq);
+  ws.launches += 2;
+  B2G_CHECK(cudaGetLastError());
+  wait_for_sequence(&h->seq, ws.value_seq, ws.stream);
+  return h->value;
+}
+
 inline bool aligned16(const void* p) {
   return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }

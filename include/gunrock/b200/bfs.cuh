@@ -437,7 +437,7 @@ struct bfs_config_t {
 struct bfs_scratch_t {
   dbuf_t<unsigned> visited, fbm, nbm, unreachable;
   dbuf_t<int> unv[2];                    // still-unvisited vertices (consecutive bottom-up levels)
-  const int* unreachable_for = nullptr;  // in-offsets array the unreachable map was built from
+  graph_key_t unreachable_for;           // the (in-edge) graph the unreachable map was built from
   dbuf_t<int> q[2];
   dbuf_t<int> counts;  // [0],[1] queue sizes
   struct host_fb_t {
@@ -516,10 +516,10 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       in_g.row_offsets != nullptr && cfg.direction != 0 && !cfg.use_atomic_min_op;
   const unsigned* premark = nullptr;
   if (can_pull) {  // per-graph map of vertices without in-edges (built once, like the transpose)
-    if (sc.unreachable_for != in_g.row_offsets) {
+    if (!sc.unreachable_for.matches(in_g)) {  // keyed on graph identity + addresses + sizes, not an address
       sc.unreachable.ensure(static_cast<size_t>(words) + 4);
       bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(in_g.row_offsets, V, sc.unreachable.ptr);
-      sc.unreachable_for = in_g.row_offsets;
+      sc.unreachable_for.set(in_g);
       ws.launches += 1;
     }
     premark = sc.unreachable.ptr;

@@ -305,7 +305,7 @@ static __global__ void part_seed_kernel(partition_t pt, int source, int* dist, u
 struct part_bfs_state_t {
   partition_t pt;
   dbuf_t<unsigned> visited, sent, fbm, nbm, unreachable;
-  const int* unreachable_for = nullptr;
+  graph_key_t unreachable_for;
   dbuf_t<int> q[2], counts, send_count, overflow, dist;
   dbuf_t<int> send_buf;
   int send_cap = 0;

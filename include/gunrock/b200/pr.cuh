@@ -38,7 +38,7 @@ struct pr_scratch_t {
   dbuf_t<int> tail_row;              // per tile: row left incomplete at the tile end, or -1
   dbuf_t<unsigned> err;              // [0] fp32 bits of max|p - plast|, [1] prepare ticket
   dbuf_t<float> base;                // (1 - alpha + dangling) / V of the current iteration
-  const int* tiled_offsets = nullptr;  // CSC offsets the tile table was built for
+  graph_key_t tiled_for;             // the in-edge graph the tile table was built for
   float* h_err = nullptr;
   cudaEvent_t ev[128] = {};
   ~pr_scratch_t() {
@@ -463,9 +463,9 @@ inline int pr_run(workspace_t& ws, pr_scratch_t& sc, const csr_view_t& g, const 
   sc.ensure(V, E);
   cudaStream_t st = ws.stream;
   const int ntiles = E > 0 ? (E + kPrTile - 1) / kPrTile : 1;
-  if (sc.tiled_offsets != t.row_offsets) {  // per-graph table (ingest-like, not per iteration)
+  if (!sc.tiled_for.matches(t)) {  // per-graph table (ingest-like, not per iteration); keyed on identity
     pr_tile_table_kernel<<<sms * 2, 256, 0, st>>>(t.row_offsets, V, ntiles, sc.first_owned.ptr);
-    sc.tiled_offsets = t.row_offsets;
+    sc.tiled_for.set(t);
     ws.launches += 1;
   }
   pr_reset_kernel<<<sms * 8, 256, 0, st>>>(g, alpha, p, sc.plast.ptr, sc.iw.ptr);

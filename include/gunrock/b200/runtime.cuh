@@ -8,6 +8,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -57,7 +58,38 @@ struct csr_view_t {
   const int* __restrict__ row_offsets = nullptr;
   const int* __restrict__ column_indices = nullptr;
   const float* __restrict__ values = nullptr;  // may be null (pattern graph => 1.0f)
+  /// Identity of the graph object this view was taken from (graph::build / graph_t::set draw a fresh one
+  /// from a process-wide counter).  Per-graph caches (transpose, PageRank tile table, map of vertices
+  /// without in-edges) are keyed on it TOGETHER with the array addresses and sizes: an address alone is
+  /// reused by cudaMalloc after a free and by grow-only buffers.  0 = unknown: nothing is cached.
+  unsigned long long uid = 0;
 };
+
+/// Key of a per-graph cache entry.  `matches` is false for views of unknown identity (uid 0).
+struct graph_key_t {
+  unsigned long long uid = 0;
+  const void* offsets = nullptr;
+  const void* indices = nullptr;
+  int n_vertices = -1, n_edges = -1;
+  bool matches(const csr_view_t& v) const {
+    return v.uid != 0 && uid == v.uid && offsets == v.row_offsets && indices == v.column_indices &&
+           n_vertices == v.n_vertices && n_edges == v.n_edges;
+  }
+  void set(const csr_view_t& v) {
+    uid = v.uid;
+    offsets = v.row_offsets;
+    indices = v.column_indices;
+    n_vertices = v.n_vertices;
+    n_edges = v.n_edges;
+  }
+  void clear() { *this = graph_key_t(); }
+};
+
+/// Fresh graph identity (host only; never 0).
+inline unsigned long long next_graph_uid() {
+  static std::atomic<unsigned long long> counter{0};
+  return ++counter;
+}
 
 /// A frontier as kernels see it: ids (or -1) plus a device-resident element count.
 struct frontier_ref_t {
@@ -144,6 +176,29 @@ struct workspace_t {
   int launches = 0;         // kernels launched through this workspace (reported as gpu_launches)
   unsigned long long edges_accounted = 0;  // host-side sum of ctrl_t::edges folded in so far
   static constexpr int kCtrlRing = 256;
+  /// One pinned record a kernel can publish a 64-bit value through (wait_for_sequence on `seq`).
+  struct host_value_t {
+    unsigned long long value;
+    volatile int seq;
+  };
+  host_value_t* h_value = nullptr;
+  int value_seq = 0;
+
+  workspace_t() = default;
+  workspace_t(const workspace_t&) = delete;
+  workspace_t& operator=(const workspace_t&) = delete;
+  ~workspace_t() {
+    if (h_value)
+      cudaFreeHost(h_value);
+  }
+  host_value_t* host_value() {
+    if (!h_value) {
+      B2G_CHECK(cudaMallocHost(&h_value, sizeof(host_value_t)));
+      h_value->value = 0;
+      h_value->seq = 0;
+    }
+    return h_value;
+  }
 
   void init(cudaStream_t s) {
     stream = s;

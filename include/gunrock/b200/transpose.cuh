@@ -112,6 +112,7 @@ struct transpose_t {
     view.row_offsets = ro.ptr;
     view.column_indices = ci.ptr;
     view.values = g.values ? vals.ptr : nullptr;
+    view.uid = next_graph_uid();  // the buffers are grow-only: same addresses, different graph
   }
 };
 

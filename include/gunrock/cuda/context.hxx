@@ -9,6 +9,8 @@
 #pragma once
 
 #include <memory>
+#include <typeindex>
+#include <typeinfo>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -49,6 +51,16 @@ class standard_context_t : public context_t {
   event_t _event = nullptr;
   util::timer_t _timer;
   b200::workspace_t _workspace;
+  bool _owns_stream = false;
+  /// Scratch of the fused enactors (bfs / sssp / pr ...), one object per type, created on first use and
+  /// destroyed WITH the context (device buffers, pinned blocks, events).  Nothing outside the context
+  /// keeps a pointer-keyed table of contexts, so a freed-and-reallocated context can never alias
+  /// another one's scratch.
+  struct slot_t {
+    std::type_index type;
+    std::shared_ptr<void> object;
+  };
+  std::vector<slot_t> _scratch;
 
  public:
   standard_context_t(device_id_t device = 0) : context_t(), _ordinal(device) {
@@ -56,6 +68,7 @@ class standard_context_t : public context_t {
     error::throw_if_exception(cudaGetDeviceProperties(&_props, _ordinal), "cudaGetDeviceProperties");
     error::throw_if_exception(cudaStreamCreateWithFlags(&_stream, cudaStreamNonBlocking),
                               "cudaStreamCreate");
+    _owns_stream = true;
     error::throw_if_exception(cudaEventCreateWithFlags(&_event, cudaEventDisableTiming),
                               "cudaEventCreate");
     _workspace.init(_stream);
@@ -69,7 +82,16 @@ class standard_context_t : public context_t {
     _workspace.init(_stream);
   }
   ~standard_context_t() {
+    int before = 0;
+    cudaGetDevice(&before);
+    cudaSetDevice(_ordinal);
+    if (_stream)
+      cudaStreamSynchronize(_stream);  // nothing of ours is still in flight when the scratch goes
+    _scratch.clear();
     cudaEventDestroy(_event);
+    if (_owns_stream && _stream)
+      cudaStreamDestroy(_stream);      // only a stream this context created itself
+    cudaSetDevice(before);
   }
 
   const device_properties_t& props() const override { return _props; }
@@ -89,6 +111,16 @@ class standard_context_t : public context_t {
   auto execution_policy() { return thrust::cuda::par_nosync.on(_stream); }
   /// B200 operator scratch bound to this context's stream.
   b200::workspace_t& workspace() { return _workspace; }
+  /// The context-owned scratch object of type T (default-constructed on first use).
+  template <typename T>
+  T& scratch() {
+    const std::type_index key(typeid(T));
+    for (auto& s : _scratch)
+      if (s.type == key)
+        return *static_cast<T*>(s.object.get());
+    _scratch.push_back({key, std::shared_ptr<void>(new T(), [](void* p) { delete static_cast<T*>(p); })});
+    return *static_cast<T*>(_scratch.back().object.get());
+  }
 };
 
 class multi_context_t {

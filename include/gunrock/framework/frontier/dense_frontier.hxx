@@ -239,7 +239,7 @@ class dense_frontier_t {
     dense_to_list_kernel<<<512, 256, 0, s.stream>>>(s.words, kBits, s.universe, reinterpret_cast<int*>(out.get()),
                                                     out.count_ptr(), static_cast<int>(out.get_capacity()),
                                                     s.d_scratch + 1);
-    out.mark_produced(s.stream);
+    out.mark_produced(s.stream, nullptr, /*unique=*/true);  // one id per set bit
   }
 
   // ---- device side (the object is passed to kernels by value) --------------------------------------

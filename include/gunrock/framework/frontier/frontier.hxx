@@ -54,17 +54,17 @@ template <typename type_t>
 struct storage_t {
   type_t* data = nullptr;
   std::size_t capacity = 0;
-  int* d_count = nullptr;  // number of elements, device resident
-  int* h_count = nullptr;  // pinned staging for count read-back
+  int* d_count = nullptr;  // [0] number of elements, [1] overflow flag of the producing operator; device resident
+  int* h_count = nullptr;  // pinned: [0..1] read-back of both, [2..3] staging of set_count
   std::size_t host_count = 0;
   bool dirty = false;                      // a kernel may have changed *d_count
+  bool unique_known = true;                // no vertex is known to occur twice (an empty frontier qualifies)
   cudaStream_t stream = nullptr;           // stream of the last device-side writer
-  const b200::ctrl_t* last_ctrl = nullptr; // control block of the producing operator (overflow flag)
 
   storage_t() {
-    error::throw_if_exception(cudaMalloc(&d_count, sizeof(int)), "frontier count alloc");
-    error::throw_if_exception(cudaMallocHost(&h_count, 2 * sizeof(int)), "frontier pinned alloc");
-    error::throw_if_exception(cudaMemset(d_count, 0, sizeof(int)), "frontier count init");
+    error::throw_if_exception(cudaMalloc(&d_count, 2 * sizeof(int)), "frontier count alloc");
+    error::throw_if_exception(cudaMallocHost(&h_count, 4 * sizeof(int)), "frontier pinned alloc");
+    error::throw_if_exception(cudaMemset(d_count, 0, 2 * sizeof(int)), "frontier count init");
   }
   storage_t(const storage_t&) = delete;
   storage_t& operator=(const storage_t&) = delete;
@@ -89,19 +89,14 @@ struct storage_t {
   /// Bring the host copy of the count up to date (one stream sync when a kernel wrote it).
   std::size_t refresh() {
     if (dirty) {
-      if (last_ctrl) {
-        error::throw_if_exception(
-            cudaMemcpyAsync(h_count + 1, &last_ctrl->overflow, sizeof(int), cudaMemcpyDeviceToHost, stream),
-            "frontier overflow read-back");
-      } else {
-        h_count[1] = 0;
-      }
+      // count and overflow flag live side by side in THIS frontier's storage (the producing operator copied
+      // its flag here in-stream, mark_produced), so the answer does not depend on how many operator launches
+      // happened since -- the workspace's control blocks are a ring that gets recycled
       error::throw_if_exception(
-          cudaMemcpyAsync(h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, stream),
+          cudaMemcpyAsync(h_count, d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream),
           "frontier count read-back");
       error::throw_if_exception(cudaStreamSynchronize(stream), "frontier count sync");
       dirty = false;
-      last_ctrl = nullptr;
       error::throw_if_exception(h_count[1] != 0,
                                 "output frontier exceeded its capacity; reserve() a larger frontier");
       host_count = static_cast<std::size_t>(h_count[0]);
@@ -111,10 +106,10 @@ struct storage_t {
   void set_count(std::size_t n) {
     host_count = n;
     dirty = false;
-    last_ctrl = nullptr;
-    int v = static_cast<int>(n);
+    unique_known = n <= 1;
+    int v[2] = {static_cast<int>(n), 0};  // pageable source: the runtime stages it before returning
     error::throw_if_exception(
-        cudaMemcpyAsync(d_count, &v, sizeof(int), cudaMemcpyHostToDevice, stream),
+        cudaMemcpyAsync(d_count, v, 2 * sizeof(int), cudaMemcpyHostToDevice, stream),
         "frontier count write");
   }
 };
@@ -195,6 +190,7 @@ class frontier_t {
     if (n)
       detail::fill_kernel<<<256, 256, 0, p_storage->stream>>>(
           reinterpret_cast<int*>(p_storage->data), static_cast<int>(value), static_cast<int>(n));
+    p_storage->unique_known = n <= 1;
   }
 
   void sequence(type_t const initial_value, std::size_t const& size, cudaStream_t stream = 0) {
@@ -205,6 +201,7 @@ class frontier_t {
       detail::iota_kernel<<<256, 256, 0, p_storage->stream>>>(
           reinterpret_cast<int*>(p_storage->data), static_cast<int>(initial_value),
           static_cast<int>(size));
+    p_storage->unique_known = true;  // consecutive ids
   }
 
   void resize(std::size_t const& size,
@@ -250,12 +247,24 @@ class frontier_t {
   int* count_ptr() const { return p_storage->d_count; }
   /// Bind the stream device-side operations on this frontier are ordered on.
   void bind_stream(cudaStream_t s) { p_storage->stream = s; }
-  /// Called by an operator after it enqueued kernels that rewrite this frontier.
-  void mark_produced(cudaStream_t s, const b200::ctrl_t* ctrl = nullptr) {
+  /// Called by an operator after it enqueued kernels that rewrite this frontier.  `ctrl` is the operator's
+  /// control block: its overflow flag is copied into the frontier's own storage in-stream.
+  /// `unique` says whether the operator guarantees that no vertex occurs twice in what it wrote.
+  void mark_produced(cudaStream_t s, const b200::ctrl_t* ctrl = nullptr, bool unique = false) {
     p_storage->stream = s;
     p_storage->dirty = true;
-    p_storage->last_ctrl = ctrl;
+    p_storage->unique_known = unique;
+    if (ctrl)
+      error::throw_if_exception(cudaMemcpyAsync(p_storage->d_count + 1, &ctrl->overflow, sizeof(int),
+                                                cudaMemcpyDeviceToDevice, s),
+                                "frontier overflow flag");
+    else  // an operator that cannot overflow (its output is sized from the input's bound)
+      error::throw_if_exception(cudaMemsetAsync(p_storage->d_count + 1, 0, sizeof(int), s),
+                                "frontier overflow flag");
   }
+  /// False when the same vertex may occur more than once (the expansion of such a frontier is not bounded
+  /// by the number of edges of the graph: advance sizes its output from the degree sum then).
+  bool is_known_unique() const { return p_storage->unique_known; }
   /// Upper bound on the element count known without a sync (capacity when a kernel wrote it).
   std::size_t size_upper_bound() const {
     return p_storage->dirty ? p_storage->capacity : p_storage->host_count;

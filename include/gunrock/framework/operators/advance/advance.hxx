@@ -96,10 +96,20 @@ void execute(graph_t& G,
     b200::launch_advance<b200::advance_output_t::none, false, true>(
         ws, view, in, in_count, in_bound, nullptr, nullptr, 0, f, cfg, &ctrl);
   } else {
-    // Size the output for the duplicate-free worst case, as the reference's enactor does
-    // (enactor.hxx:161-193); a kernel that would overflow raises on the next size query.
+    // A duplicate-free frontier expands into at most E slots (the reference's enactor reserves
+    // max(E,V)*1.5 up front, enactor.hxx:161-193), so nothing has to visit the host.  A frontier that may
+    // hold the same vertex several times (the output of an earlier advance, a user-filled list) is not
+    // bounded by E: its output is sized from the degree sum, as the reference does before every advance
+    // (block_mapped.hxx:205-217) -- one pinned-memory poll, no stream synchronise.  The overflow flag the
+    // kernels raise stays as the backstop (it reaches the frontier's own storage, mark_produced).
     std::size_t want = static_cast<std::size_t>(
         view.n_edges > view.n_vertices ? view.n_edges : view.n_vertices);
+    if (input_type != advance_io_type_t::graph && !input->is_known_unique()) {
+      const unsigned long long total = b200::frontier_degree_total(ws, view, in, in_count, in_bound);
+      error::throw_if_exception(total > 0x7fffffffull, "advance: the output frontier would exceed 2^31 entries");
+      if (static_cast<std::size_t>(total) > want)
+        want = static_cast<std::size_t>(total);
+    }
     if (output->get_capacity() < want)
       output->reserve(want);
     output->bind_stream(ws.stream);

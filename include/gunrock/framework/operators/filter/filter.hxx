@@ -41,6 +41,7 @@ void execute(graph_t& G,
   using type_t = typename frontier_t::type_t;
   detail::pred_adapter_t<type_t, operator_t> f{op};
   std::size_t bound = input->size_upper_bound();
+  const bool unique_in = input->is_known_unique();
   if (output->get_capacity() < bound || output->get_capacity() == 0)
     output->reserve(bound ? bound : 1);
   output->bind_stream(ws.stream);
@@ -53,7 +54,7 @@ void execute(graph_t& G,
     b200::launch_filter_select(ws, in, input->count_ptr(), static_cast<int>(bound), out,
                                output->count_ptr(), f);
   }
-  output->mark_produced(ws.stream);
+  output->mark_produced(ws.stream, nullptr, /*unique=*/unique_in);  // a filter never adds an occurrence
 }
 
 template <filter_algorithm_t alg_type, typename graph_t, typename enactor_type, typename operator_t>

@@ -38,6 +38,7 @@ void execute(frontier_t* input,
   output->bind_stream(ws.stream);
   const int* in = reinterpret_cast<const int*>(input->get());
   int* out = reinterpret_cast<int*>(output->get());
+  bool unique_out = input->is_known_unique();
   if (best_effort_uniquification || n_vertices == 0) {
     b200::launch_unique_adjacent(ws, in, input->count_ptr(), static_cast<int>(bound), out,
                                  output->count_ptr());
@@ -52,8 +53,9 @@ void execute(frontier_t* input,
     int* has_invalid = reinterpret_cast<int*>(ws.uniq_bitmap.ptr + words);
     b200::launch_unique_exact(ws, in, input->count_ptr(), static_cast<int>(n_vertices),
                               ws.uniq_bitmap.ptr, has_invalid, out, output->count_ptr());
+    unique_out = true;  // exact: every vertex at most once
   }
-  output->mark_produced(ws.stream);
+  output->mark_produced(ws.stream, nullptr, unique_out);
 }
 
 template <uniquify_algorithm_t type = uniquify_algorithm_t::unique, typename enactor_type>

@@ -194,12 +194,14 @@ class graph_t {
     offsets = memory::raw_pointer_cast(csr.row_offsets.data());
     indices = memory::raw_pointer_cast(csr.column_indices.data());
     values = memory::raw_pointer_cast(csr.nonzero_values.data());
+    uid = b200::next_graph_uid();  // a rebuilt graph is a new graph, whatever addresses its arrays got
   }
   template <typename csc_type>
   void set_csc(csc_type& csc) {
     t_offsets = memory::raw_pointer_cast(csc.column_offsets.data());
     t_indices = memory::raw_pointer_cast(csc.row_indices.data());
     t_values = memory::raw_pointer_cast(csc.nonzero_values.data());
+    uid = b200::next_graph_uid();
   }
 
   /// The B200 kernels' view of the CSR / CSC arrays.
@@ -214,6 +216,7 @@ class graph_t {
     v.row_offsets = reinterpret_cast<const int*>(offsets);
     v.column_indices = reinterpret_cast<const int*>(indices);
     v.values = values;
+    v.uid = uid;
     return v;
   }
   b200::csr_view_t csc_view() const {
@@ -224,6 +227,7 @@ class graph_t {
     v.row_offsets = reinterpret_cast<const int*>(t_offsets);
     v.column_indices = reinterpret_cast<const int*>(t_indices);
     v.values = t_values;
+    v.uid = uid;
     return v;
   }
 
@@ -258,6 +262,8 @@ class graph_t {
   edge_t* t_offsets = nullptr;
   vertex_t* t_indices = nullptr;
   weight_t* t_values = nullptr;
+  /// Identity for the per-graph caches of the fused enactors (b200::graph_key_t); copied with the view.
+  unsigned long long uid = 0;
 };
 
 /// graph::build<space>(properties, csr) (graph/build.hxx:29-36): pointer capture only.

@@ -57,6 +57,11 @@ def lib() -> C.CDLL:
         L.orc_edge_weights.argtypes = [C.c_uint64, C.c_int, _i32p, _i32p, C.c_int, _f32p]
         L.orc_build_csr_from_pairs.restype = C.c_int64
         L.orc_build_csr_from_pairs.argtypes = [C.c_int, C.c_int64, _i32p, _i32p, C.c_int, _i32p, _i32p]
+        L.orc_rmat_csr_parallel.restype = C.c_int64
+        L.orc_rmat_csr_parallel.argtypes = [C.c_int, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.c_int, _i32p, _i32p,
+                                            C.c_int64]
+        L.orc_edge_weights_parallel.argtypes = [C.c_uint64, C.c_int, _i32p, _i32p, C.c_int, _f32p]
+        L.orc_num_threads.restype = C.c_int
         L.orc_hash3_export.restype = C.c_uint64
         L.orc_hash3_export.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         _LIB = L
@@ -199,6 +204,33 @@ def rmat_csr(scale: int, edge_factor: int, seed: int, mirror: bool = True):
     V = 1 << scale
     s, d = rmat_edges(scale, edge_factor * V, seed)
     return build_csr_from_pairs(V, s, d, mirror)
+
+
+def num_threads() -> int:
+    """Host threads the parallel builders use (OpenMP)."""
+    return int(lib().orc_num_threads())
+
+
+def rmat_csr_parallel(scale: int, n_pairs: int, seed: int, mirror: bool = True, fold: int = 0):
+    """Same CSR as rmat_edges (+ optional `id % fold`) + build_csr_from_pairs, built with all host threads
+    (the bench's reference arm and CPU baseline at RMAT-24/26; tests pin it against the serial path)."""
+    V = fold or (1 << scale)
+    ro = np.zeros(V + 1, np.int32)
+    cap = max(1, n_pairs * (2 if mirror else 1))
+    ci = np.empty(cap, np.int32)
+    nnz = lib().orc_rmat_csr_parallel(scale, n_pairs, seed, int(mirror), int(fold), V, ro, ci, cap)
+    if nnz == -1:
+        raise OverflowError("nnz exceeds int32")
+    if nnz < 0:
+        raise MemoryError(f"orc_rmat_csr_parallel failed ({nnz})")
+    return ro, ci[:nnz].copy() if nnz < cap // 2 else ci[:nnz]
+
+
+def edge_weights_parallel(seed: int, ro, ci, non_integer: bool = False) -> np.ndarray:
+    n = len(ro) - 1
+    w = np.empty(max(len(ci), 1), np.float32)
+    lib().orc_edge_weights_parallel(seed, n, np.ascontiguousarray(ro, np.int32), _ci(ci), int(non_integer), w)
+    return w[:len(ci)]
 
 
 def edge_weights(seed: int, ro, ci, non_integer: bool = False) -> np.ndarray:

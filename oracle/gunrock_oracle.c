@@ -536,3 +536,210 @@ ORC_API int64_t orc_build_csr_from_pairs(int n_vertices,
   free(tmp);
   return nnz;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * Parallel host build of the same workload (OpenMP): identical output to
+ * orc_rmat_edges + (optional fold) + orc_build_csr_from_pairs, for the bench's reference arm at
+ * RMAT-26 where the serial build takes minutes.  Keys are generated in parallel, partitioned by
+ * the top bits of the source id (MSD pass), every bucket is LSD-radix-sorted and deduplicated by
+ * one thread, buckets are taken largest first.  Workload definition, NOT reference code.
+ * ------------------------------------------------------------------------------------------ */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static void orc_lsd_sort_u64(uint64_t* keys, uint64_t* tmp, size_t m, int key_bits) {
+  uint64_t* a = keys;
+  uint64_t* b = tmp;
+  for (int sh = 0; sh < key_bits; sh += 8) {
+    size_t cnt[257];
+    memset(cnt, 0, sizeof cnt);
+    for (size_t i = 0; i < m; ++i) ++cnt[((a[i] >> sh) & 0xFF) + 1];
+    int trivial = 0;
+    for (int q = 0; q < 256; ++q)
+      if (cnt[q + 1] == m)
+        trivial = 1;
+    if (trivial)
+      continue;
+    for (int q = 0; q < 256; ++q) cnt[q + 1] += cnt[q];
+    for (size_t i = 0; i < m; ++i) b[cnt[(a[i] >> sh) & 0xFF]++] = a[i];
+    uint64_t* t = a;
+    a = b;
+    b = t;
+  }
+  if (a != keys)
+    memcpy(keys, a, m * sizeof(uint64_t));
+}
+
+ORC_API int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ro: n_vertices + 1 ints; ci: capacity ci_cap ints.  fold > 0: ids are taken modulo fold
+ * (n_vertices must then equal fold).  Returns nnz, -1 if nnz > INT_MAX, -2 if ci_cap is too small. */
+ORC_API int64_t orc_rmat_csr_parallel(int scale,
+                                      int64_t n_pairs,
+                                      uint64_t seed,
+                                      int mirror,
+                                      int fold,
+                                      int n_vertices,
+                                      int* ro,
+                                      int* ci,
+                                      int64_t ci_cap) {
+  const size_t per = mirror ? 2 : 1;
+  const size_t cap = (size_t)n_pairs * per;
+  uint64_t* keys = (uint64_t*)malloc((cap ? cap : 1) * sizeof(uint64_t));
+  uint64_t* tmp = (uint64_t*)malloc((cap ? cap : 1) * sizeof(uint64_t));
+  if (!keys || !tmp) {
+    free(keys);
+    free(tmp);
+    return -3;
+  }
+  /* vertex ids need vbits bits; buckets = top kB bits of the source id */
+  int vbits = 1;
+  while (((int64_t)1 << vbits) < (int64_t)n_vertices) ++vbits;
+  const int kB = vbits > 12 ? 12 : vbits;
+  const int nb = 1 << kB;
+  const int bshift = 32 + vbits - kB; /* key >> bshift = bucket */
+  const int64_t chunk = 1 << 16;
+  const int64_t nchunks = (n_pairs + chunk - 1) / chunk;
+  int nthreads = orc_num_threads();
+  size_t* hist = (size_t*)calloc((size_t)nthreads * (nb + 1), sizeof(size_t));
+  const uint64_t DEAD = ~0ull; /* self loop: sorts nowhere, dropped at the partition */
+  /* 1. generate (static chunk ownership so that the histogram pass and the scatter pass agree) */
+#pragma omp parallel num_threads(nthreads)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+    size_t* h = hist + (size_t)t * (nb + 1);
+    int32_t* sbuf = (int32_t*)malloc(sizeof(int32_t) * chunk);
+    int32_t* dbuf = (int32_t*)malloc(sizeof(int32_t) * chunk);
+    for (int64_t c = t; c < nchunks; c += nthreads) {
+      const int64_t first = c * chunk;
+      const int64_t cnt = (first + chunk <= n_pairs) ? chunk : n_pairs - first;
+      orc_rmat_edges(scale, first, cnt, seed, sbuf, dbuf);
+      for (int64_t i = 0; i < cnt; ++i) {
+        uint32_t u = (uint32_t)sbuf[i], v = (uint32_t)dbuf[i];
+        if (fold > 0) {
+          u %= (uint32_t)fold;
+          v %= (uint32_t)fold;
+        }
+        uint64_t* out = keys + (size_t)(first + i) * per;
+        if (u == v) {
+          out[0] = DEAD;
+          if (mirror)
+            out[1] = DEAD;
+          continue;
+        }
+        out[0] = ((uint64_t)u << 32) | v;
+        ++h[out[0] >> bshift];
+        if (mirror) {
+          out[1] = ((uint64_t)v << 32) | u;
+          ++h[out[1] >> bshift];
+        }
+      }
+    }
+    free(sbuf);
+    free(dbuf);
+  }
+  /* 2. bucket offsets: bucket-major, thread-minor */
+  size_t* bstart = (size_t*)malloc(sizeof(size_t) * (nb + 1));
+  size_t run = 0;
+  for (int q = 0; q < nb; ++q) {
+    bstart[q] = run;
+    for (int t = 0; t < nthreads; ++t) {
+      size_t x = hist[(size_t)t * (nb + 1) + q];
+      hist[(size_t)t * (nb + 1) + q] = run;
+      run += x;
+    }
+  }
+  bstart[nb] = run;
+  /* 3. scatter into buckets (same chunk ownership) */
+#pragma omp parallel num_threads(nthreads)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+    size_t* h = hist + (size_t)t * (nb + 1);
+    for (int64_t c = t; c < nchunks; c += nthreads) {
+      const size_t lo = (size_t)(c * chunk) * per;
+      const size_t hi = (size_t)((c + 1) * chunk <= n_pairs ? (c + 1) * chunk : n_pairs) * per;
+      for (size_t i = lo; i < hi; ++i)
+        if (keys[i] != DEAD)
+          tmp[h[keys[i] >> bshift]++] = keys[i];
+    }
+  }
+  /* 4. per bucket: sort the low bits, dedup in place; order buckets by size (largest first) */
+  int* order = (int*)malloc(sizeof(int) * nb);
+  for (int q = 0; q < nb; ++q) order[q] = q;
+  for (int i = 1; i < nb; ++i) { /* insertion sort on 4096 entries: negligible */
+    int x = order[i];
+    size_t sx = bstart[x + 1] - bstart[x];
+    int j = i - 1;
+    while (j >= 0 && bstart[order[j] + 1] - bstart[order[j]] < sx) {
+      order[j + 1] = order[j];
+      --j;
+    }
+    order[j + 1] = x;
+  }
+  size_t* uniq = (size_t*)calloc((size_t)nb + 1, sizeof(size_t));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (int k = 0; k < nb; ++k) {
+    const int q = order[k];
+    uint64_t* a = tmp + bstart[q];
+    const size_t m = bstart[q + 1] - bstart[q];
+    orc_lsd_sort_u64(a, keys + bstart[q], m, bshift); /* bits above bshift are equal inside a bucket */
+    size_t w = 0;
+    for (size_t i = 0; i < m; ++i)
+      if (i == 0 || a[i] != a[i - 1])
+        a[w++] = a[i];
+    uniq[q + 1] = w;
+  }
+  for (int q = 0; q < nb; ++q) uniq[q + 1] += uniq[q];
+  const size_t nnz = uniq[nb];
+  int64_t rc = (int64_t)nnz;
+  if (nnz > (size_t)INT_MAX)
+    rc = -1;
+  else if ((int64_t)nnz > ci_cap)
+    rc = -2;
+  if (rc >= 0) {
+    memset(ro, 0, sizeof(int) * ((size_t)n_vertices + 1));
+    /* 5. emit: a bucket owns a contiguous range of source ids, so row counts never collide */
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nthreads)
+    for (int q = 0; q < nb; ++q) {
+      const uint64_t* a = tmp + bstart[q];
+      const size_t w = uniq[q + 1] - uniq[q];
+      int* out = ci + uniq[q];
+      for (size_t i = 0; i < w; ++i) {
+        out[i] = (int)(a[i] & 0xFFFFFFFFu);
+        ++ro[(a[i] >> 32) + 1];
+      }
+    }
+    for (int i = 0; i < n_vertices; ++i) ro[i + 1] += ro[i];
+  }
+  free(uniq);
+  free(order);
+  free(bstart);
+  free(hist);
+  free(keys);
+  free(tmp);
+  return rc;
+}
+
+/* Parallel edge weights (rows are independent). */
+ORC_API void orc_edge_weights_parallel(uint64_t seed, int n_vertices, const int* ro, const int* ci,
+                                       int non_integer, float* w) {
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int u = 0; u < n_vertices; ++u)
+    for (int e = ro[u]; e < ro[u + 1]; ++e) w[e] = orc_edge_weight(seed, u, ci[e], non_integer);
+}

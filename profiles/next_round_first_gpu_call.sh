@@ -17,7 +17,7 @@ want() { [[ "$SECTIONS" == all || " $SECTIONS " == *" $1 "* ]]; }
 # printed here: edges touched (the out-degree sum of the reached vertices) must not depend on the variant.
 if want variants; then
   for v in 0 1 4 7 2 5 6 3; do
-    B2G_ADVANCE_VARIANT=$v python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/bfs_push_variant_$v.json"
+    B2G_ADVANCE_VARIANT=$v python bench.py --workload bfs_push_rmat22 --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > "$OUT/bfs_push_variant_$v.json"
     python - "$OUT" $v <<'PY'
 import json, sys
 out, v = sys.argv[1], sys.argv[2]
@@ -81,7 +81,7 @@ fi
 
 # refgpu: same-GPU baseline, the UNMODIFIED reference GPU kernels (oracle/_ref/gunrock_ref_gpu) on the bench graph
 if want refgpu; then
-  python bench.py --steps 5 --warmup 3 --no-cpu-baseline --reference-gpu 2>&1 | tail -1 > "$OUT/bench_with_reference_gpu.json"
+  python bench.py --workload bfs_push_rmat22 --steps 5 --warmup 3 --no-cpu-baseline --reference-gpu 2>&1 | tail -1 > "$OUT/bench_with_reference_gpu.json"
   python -c "import json,sys; j=json.load(open('$OUT/bench_with_reference_gpu.json')); print('ours', round(j['value']), 'MTEPS; reference GPU:', json.dumps(j.get('reference_gpu'))[:600])" | tee "$OUT/reference_gpu.txt"
 fi
 
@@ -91,7 +91,7 @@ if want ncu; then
   for v in 0 4 6; do
     B2G_ADVANCE_VARIANT=$v timeout 600 ncu --set full --clock-control none --import-source on \
       -k regex:'advance_(merge|warp)_path_kernel' --launch-skip 6 --launch-count 2 -f -o "$OUT/ncu_bfs_push_variant_$v" \
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_variant_$v.log" 2>&1
+      python bench.py --workload bfs_push_rmat22 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_variant_$v.log" 2>&1
     python profiles/summarize_ncu.py "$OUT/ncu_bfs_push_variant_$v.ncu-rep" "$OUT/ncu_bfs_push_variant_$v.md" >/dev/null 2>&1 || true
   done
 fi

@@ -26,3 +26,6 @@ inline cudaError_t cudaFree(void*) { return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void*, int, std::size_t, cudaStream_t) { cuemu_no_runtime("cudaMemsetAsync"); return 1; }
 inline cudaError_t cudaStreamQuery(cudaStream_t) { cuemu_no_runtime("cudaStreamQuery"); return 1; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { cuemu_no_runtime("cudaStreamSynchronize"); return 1; }
+template <typename T>
+inline cudaError_t cudaMallocHost(T**, std::size_t) { cuemu_no_runtime("cudaMallocHost"); return 1; }
+inline cudaError_t cudaFreeHost(void*) { return cudaSuccess; }

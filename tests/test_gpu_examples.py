@@ -131,6 +131,14 @@ def test_header_api_selftest():
     assert "ALL OK" in out, out
 
 
+def test_per_graph_caches_across_graphs_and_contexts():
+    """One context, direction-optimised BFS + PageRank on two different directed graphs refilled into the
+    SAME device allocations, then a recreated context: the transpose, the PageRank tile table and the map of
+    vertices without in-edges are keyed on graph identity, the scratch is owned by the context."""
+    out = run([need("cache_selftest")])
+    assert "ALL OK" in out, out
+
+
 @pytest.mark.parametrize("alg", ["color", "kcore", "ppr", "spmv"])
 def test_other_reference_algorithms_validate_on_our_operators(alg, chesapeake_mtx, rmat_mtx, tmp_path):
     """Widening: the reference's own color / kcore / ppr / spmv algorithm headers and

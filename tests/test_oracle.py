@@ -101,6 +101,24 @@ def test_rmat_structure():
     assert np.array_equal(w[order], w)
 
 
+@pytest.mark.parametrize("scale,ef,seed,mirror,fold", [(12, 16, 5, True, 0), (14, 8, 7, True, 0),
+                                                        (13, 17, 9, False, 5000), (10, 4, 3, True, 0), (4, 2, 1, True, 0)])
+def test_parallel_host_build_equals_the_serial_one(scale, ef, seed, mirror, fold):
+    """The OpenMP builder the bench's reference arm uses at RMAT-24/26 (orc_rmat_csr_parallel) gives the same
+    CSR, bit for bit, as rmat_edges (+ fold) + build_csr_from_pairs -- which the device generator is pinned to."""
+    n = ef * (1 << scale)
+    s, d = oracle.rmat_edges(scale, n, seed)
+    V = fold or (1 << scale)
+    if fold:
+        s, d = (s % fold).astype(np.int32), (d % fold).astype(np.int32)
+    ro, ci = oracle.build_csr_from_pairs(V, s, d, mirror)
+    ro2, ci2 = oracle.rmat_csr_parallel(scale, n, seed, mirror, fold)
+    assert np.array_equal(ro, ro2) and np.array_equal(ci, ci2)
+    for non_integer in (False, True):
+        assert np.array_equal(oracle.edge_weights(3, ro, ci, non_integer),
+                              oracle.edge_weights_parallel(3, ro, ci, non_integer))
+
+
 def test_empty_and_degenerate():
     # single vertex, no edges
     ro = np.zeros(2, np.int32)
