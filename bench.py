@@ -1,23 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- MTEPS of the frontier hot path on synthetic RMAT graphs (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path (one JSON line)
-    python bench.py --impl reference --gpus 1 --steps K ...  # the reference's CPU path, same config
+    python bench.py [--gpus 1] --steps K --warmup W           # our CUDA path: ONE JSON line
+    torchrun ... bench.py --gpus N --steps K --warmup W       # N > 1: the same traversal, 1-D partitioned
+    python bench.py --impl reference ...                      # the reference's CPU path, same config
 
-A "step" is one full run of the workload's algorithm (one BFS / SSSP from the bench source, one
-PageRank solve) over the graph already resident in HBM.  Default workload at N=1 is BASELINE.json
-configs[1]: BFS push on RMAT-22 (ef 16), merge_path advance + in-kernel compact filter.
-  value   : MTEPS, device-resident result, CUDA events on the launching stream, max over ranks
-  e2e     : same metric through the C-ABI call with HOST buffers (source in, distances out to
-            pinned host memory inside the timed region)
-  roofline: dominant kernel's algorithmic bytes (4 B x column indices read; 8 B for SSSP) divided by
-            its device time (per-level CUDA events recorded on the launching stream by the enactor)
-  cpu_baseline: the reference's own CPU validator (oracle/_ref, compiled from /root/reference) or,
-            when that binary is absent, the oracle's C port, timed on this box's host cores.
-N > 1 (torchrun): every rank holds the same RMAT graph and runs BFS from its own shard of a batch of
-sources (independent objects, no data-path collective) -> "scaling": "weak".
+The headline workload is the one BASELINE.json's metric is quoted on: direction-optimised BFS on RMAT-26
+(scale 26, 16 directed edges per vertex) from the highest-degree vertex.
+  N = 1 : the fused single-GPU enactor (`bfs_do_rmat26`).
+  N > 1 : ONE traversal over the graph 1-D (cyclic) vertex-cut across the N ranks (`bfs_part_rmat26`), the
+          per-level frontier exchange done by our kernels over NVLink peer memory (default) or by NCCL
+          (`--exchange nccl`; its time is also reported beside the default) -> "scaling": "strong".
+A "step" is one full traversal over the graph already resident in HBM.
+  value    : MTEPS with the SAME numerator at every N and for the CPU arm: the sum of out-degrees of the
+             reached vertices (= the edges the reference's CPU BFS traverses, graph500 convention) per second;
+             `config.edges_inspected_per_step` is what the direction-optimised run actually read.
+  e2e      : same metric through the C-ABI call with HOST buffers (source in, the V x 4 B result copied to
+             pinned host memory inside the timed region)
+  roofline : the dominant kernel class's algorithmic bytes (4 B per column index actually read; 8 B for SSSP)
+             over its device time (per-level CUDA events recorded on the launching stream by the enactor)
+  cpu_baseline : the reference's own CPU validator (oracle/_ref, compiled from /root/reference; the oracle's
+             C port where that binary is absent) on this box's host cores, with a full-size parity check
+  configs  : (N = 1, default run) the other BASELINE.json configurations as sub-records of the same line --
+             bfs_push_rmat22 (merge_path), sssp_rmat24 (block_mapped), pr_lj -- each with value / roofline /
+             cpu_baseline / full-size parity.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -33,7 +42,6 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (algorithm, scale, pairs-per-vertex, seed, mirror, fold, weights, lb, direction)
     "bfs_push_rmat22": dict(alg="bfs", scale=22, ef=16, seed=0x5EED22, mirror=True, fold=0, weights=0,
                             lb="merge_path", direction="forward",
                             desc="BFS push, RMAT-22 ef16 symmetrised+dedup, merge_path advance + in-kernel compact filter"),
@@ -49,22 +57,26 @@ WORKLOADS = {
     "bfs_do_rmat26": dict(alg="bfs", scale=26, ef=8, seed=0x5EED26, mirror=True, fold=0, weights=0,
                           lb="block_mapped", direction="optimized",
                           desc="BFS direction-optimised, RMAT-26 with 16 directed edges/vertex (int32-safe)"),
-    # config 5: 1-D vertex partition over the ranks + NCCL frontier exchange (strong scaling)
+    # BASELINE.json configs[4]: 1-D vertex partition over the ranks + per-level frontier exchange (strong scaling)
     "bfs_part_rmat26": dict(alg="bfs", scale=26, ef=8, seed=0x5EED26, mirror=True, fold=0, weights=0,
                             lb="block_mapped", direction="optimized", partitioned=True,
                             desc="BFS direction-optimised, RMAT-26 (16 directed edges/vertex), 1-D cyclic vertex "
-                                 "partition across the ranks, NCCL all-to-all / all-gather frontier exchange"),
+                                 "partition across the ranks, per-level frontier exchange"),
     "bfs_part_rmat22": dict(alg="bfs", scale=22, ef=16, seed=0x5EED22, mirror=True, fold=0, weights=0,
                             lb="block_mapped", direction="optimized", partitioned=True,
-                            desc="BFS direction-optimised, RMAT-22 ef16, 1-D partition + NCCL exchange"),
+                            desc="BFS direction-optimised, RMAT-22 ef16, 1-D partition + per-level frontier exchange"),
 }
+HEADLINE_1, HEADLINE_N = "bfs_do_rmat26", "bfs_part_rmat26"
+SUB_CONFIGS = ["bfs_push_rmat22", "sssp_rmat24", "pr_lj"]
+INT_MAX = 2**31 - 1
+FLT_MAX = float(np.finfo(np.float32).max)
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
-    return 6650.0, "fallback"
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -118,17 +130,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ---------------------------------------------------------------------------------------------
+# host side: the checker's graph build and the CPU runs (oracle / oracle/_ref -- never the product)
+# ---------------------------------------------------------------------------------------------
 def host_graph(wl):
-    """The workload's CSR built on the HOST by the checker's generator (reference arm / CPU baseline
-    when no device copy is at hand).  Bit-identical to the device generator (tests/test_gpu_parity)."""
+    """The workload's CSR built on the HOST by the checker's generator with all host threads (reference arm).
+    Bit-identical to the device generator (tests/test_gpu_parity) and to the serial builder (tests/test_oracle)."""
     import oracle
-    V = wl["fold"] or (1 << wl["scale"])
     n_pairs = wl.get("pairs") or wl["ef"] * (1 << wl["scale"])
-    s, d = oracle.rmat_edges(wl["scale"], n_pairs, wl["seed"])
-    if wl["fold"]:
-        s, d = (s % wl["fold"]).astype(np.int32), (d % wl["fold"]).astype(np.int32)
-    ro, ci = oracle.build_csr_from_pairs(V, s, d, wl["mirror"])
-    w = oracle.edge_weights(wl["seed"] + 1, ro, ci, wl["weights"] == 2) if wl["weights"] else None
+    ro, ci = oracle.rmat_csr_parallel(wl["scale"], n_pairs, wl["seed"], wl["mirror"], wl["fold"])
+    w = oracle.edge_weights_parallel(wl["seed"] + 1, ro, ci, wl["weights"] == 2) if wl["weights"] else None
     return ro, ci, w
 
 
@@ -158,19 +169,32 @@ def cpu_run_factory(wl, ro, ci, w):
     return run, "port", 1
 
 
-def edges_touched_cpu(wl, ro, result):
+def reached_degree_sum(wl, ro, result, iters=None):
+    """The TEPS numerator shared by every arm: sum of out-degrees of the reached vertices (BFS, SSSP);
+    E x iterations for PageRank (performance.hxx:225-229 counts edges visited)."""
     deg = np.diff(ro).astype(np.int64)
     if wl["alg"] == "bfs":
-        return int(deg[result < 2**31 - 1].sum())
+        return int(deg[np.asarray(result) < INT_MAX].sum())
     if wl["alg"] == "sssp":
-        return int(deg[result < np.finfo(np.float32).max].sum())  # each reached vertex popped >= once
-    p, iters = result
+        return int(deg[np.asarray(result) < FLT_MAX].sum())
     return int(deg.sum()) * int(iters)
 
 
 def bench_source(ro):
-    deg = np.diff(ro)
-    return int(deg.argmax())
+    return int(np.diff(ro).argmax())
+
+
+def parity(wl, got, want):
+    """Full-size check of the product's result against the checker's (bit-exact for BFS / SSSP, 1e-6 relative
+    for PageRank).  Returns (ok, detail)."""
+    if wl["alg"] == "pr":
+        want_p = np.asarray(want[0], np.float64)
+        rel = np.abs(np.asarray(got, np.float64) - want_p) / np.maximum(np.abs(want_p), 1e-300)
+        return bool(rel.max() <= 1e-6), {"max_rel_err": float(rel.max()), "tolerance": 1e-6}
+    a = np.asarray(got).view(np.uint32)
+    b = np.asarray(want).view(np.uint32)
+    bad = int((a != b).sum())
+    return bad == 0, {"mismatches": bad, "rule": "bit-exact"}
 
 
 def reference_gpu_leg(G, wl, src, edges_per_run, runs=5):
@@ -192,7 +216,11 @@ def reference_gpu_leg(G, wl, src, edges_per_run, runs=5):
             cmd = [exe, wl["alg"], path, str(src), str(runs), lb]
             if wl["alg"] != "pr" and len(ci) <= 200_000_000 and lb == "block_mapped":
                 cmd.append("validate")            # its own CPU validator, once
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            except subprocess.TimeoutExpired:
+                out[lb] = {"error": "timed out after 900 s"}
+                continue
             if r.returncode != 0:
                 out[lb] = {"error": (r.stderr or r.stdout)[-300:]}
                 continue
@@ -200,9 +228,10 @@ def reference_gpu_leg(G, wl, src, edges_per_run, runs=5):
             ms = sorted(j["ms"][1:] or j["ms"])   # first run pays the lazy module load
             out[lb] = {"ms_median": statistics.median(ms), "ms_best": ms[0], "runs": len(j["ms"]),
                        "errors_vs_reference_cpu": j["errors"],
-                       "mteps": (edges_per_run / statistics.median(ms) / 1e3) if wl["alg"] != "pr" else None}
+                       "mteps": (edges_per_run / statistics.median(ms) / 1e3) if edges_per_run else None}
     return {"kind": "unmodified reference GPU kernels, nvcc sm_100a, -include oracle/ref_gpu_fix.h, SM_TARGET=90",
-            "numerator": "edges touched by OUR run of the same traversal (bfs / sssp); pr: time per solve only",
+            "timed_region": "the reference enactor's own timer (enactor.hxx:266-288), reset excluded",
+            "numerator": "sum of out-degrees of the reached vertices (bfs / sssp); E x our iteration count (pr)",
             **out}
 
 
@@ -211,8 +240,10 @@ def run_reference(args, wl, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import oracle
     t0 = time.time()
     ro, ci, w = host_graph(wl)
+    build_s = time.time() - t0
     run, kind, cores = cpu_run_factory(wl, ro, ci, w)
     src = bench_source(ro)
     for _ in range(args.warmup):
@@ -221,25 +252,239 @@ def run_reference(args, wl, name):
     for _ in range(args.steps):
         res, t = run(src)
         ms.append(t)
-    et = edges_touched_cpu(wl, ro, res)
+    et = reached_degree_sum(wl, ro, res[0] if wl["alg"] == "pr" else res, res[1] if wl["alg"] == "pr" else None)
     total_ms = sum(ms)
     value = et * len(ms) / total_ms / 1e3
     line = {"impl": "reference", "metric": f"MTEPS ({name})", "value": value, "unit": "MTEPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / max(len(ms), 1), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": total_ms / max(len(ms), 1), "higher_is_better": True,
+            "scaling": "strong" if wl.get("partitioned") else "weak",
             "vs_baseline": None, "dtype": "int32" if wl["alg"] == "bfs" else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "vertices": int(len(ro) - 1), "edges": int(len(ci)),
-                       "source": src, "edges_touched_per_step": et},
+                       "source": src, "edges_touched_per_step": et,
+                       "numerator": "sum of out-degrees of the reached vertices"},
             "cpu_baseline": {"value": value, "unit": "MTEPS", "cores": cores, "kind": kind,
                              "sample": f"{len(ms)} full {wl['alg']} run(s) from the bench source, "
-                                       f"validator's own timer; host cores available: {os.cpu_count()}"},
+                                       f"validator's own timer; host cores available: {os.cpu_count()}; "
+                                       f"the graph was built on the host with {oracle.num_threads()} threads "
+                                       f"in {build_s:.1f} s (untimed)"},
             "e2e": {"value": value, "unit": "MTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "setup_s": round(time.time() - t0 - total_ms / 1e3, 1)}
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------
+# one workload on one GPU through the C ABI
+# ---------------------------------------------------------------------------------------------
+def load_traffic(name, wl):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very configuration
+    (profiles/r2_traffic.json, falling back to round 1's file) -- never measured under the profiler here."""
+    for fn in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                entry = json.load(f).get(f"{name}/{wl['lb']}")
+        except (OSError, ValueError):
+            continue
+        if entry:
+            per = [l["dram_read_bytes"] + l["dram_write_bytes"] for l in entry["launches"]]
+            return sum(per) / len(per), {"source": entry["source"], "launches": entry["launches"],
+                                         "note": "mean over the capture's launches; compare with their algorithmic_bytes"}
+    return None, None
+
+
+def bench_single(args, name, wl, steps, warmup, local, cpu_baseline=True, background_cpu=False, extras=True):
+    """Returns (record, finish) -- `record` is the JSON object of this workload; when `background_cpu` is set
+    the CPU baseline + parity run on a host thread and `finish()` joins it and fills them in."""
+    import torch
+    import gunrock_b200 as gb
+
+    t_setup = time.time()
+    n_pairs = wl.get("pairs") or wl["ef"] * (1 << wl["scale"])
+    G = gb.graph_t.rmat(wl["scale"], n_pairs, wl["seed"], mirror=wl["mirror"], fold_vertices=wl["fold"],
+                        weights=wl["weights"], weight_seed=wl["seed"] + 1)
+    src, src_deg = G.max_degree_vertex()
+    if wl["alg"] == "pr" or wl["direction"] != "forward":
+        G.build_transpose()
+    stream = torch.cuda.Stream()
+    opt = gb.options_t(advance_load_balance=getattr(gb.load_balance_t, wl["lb"]),
+                       advance_direction=getattr(gb.advance_direction_t, wl["direction"]),
+                       filter_algorithm=gb.filter_algorithm_t.compact, enable_filter=True,
+                       hub_threshold=args.hub_threshold, ctas_per_sm=args.ctas_per_sm,
+                       stream=stream.cuda_stream)
+    V = G.n_vertices
+    out_dtype = torch.int32 if wl["alg"] == "bfs" else torch.float32
+    d_out = torch.empty(V, dtype=out_dtype, device="cuda")
+    h_out = torch.empty(V, dtype=out_dtype).pin_memory()
+    bytes_per_edge = 8 if wl["alg"] == "sssp" else 4
+
+    def step(out):
+        if wl["alg"] == "bfs":
+            return gb.bfs(G, src, out, options=opt)
+        if wl["alg"] == "sssp":
+            return gb.sssp(G, src, out, options=opt)
+        return gb.pr(G, out, 0.85, 1e-6, options=opt)
+
+    def timed(out, k):
+        """K steps bracketed by synchronize; CUDA events on the launching stream."""
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        agg = dict(inspected=0, launches=0, run_ms=[], lv=[])
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(k):
+                st = step(out)
+                agg["inspected"] += st.edges_touched
+                agg["launches"] += st.kernel_launches
+                agg["run_ms"].append(float(st.elapsed_ms))   # the library's own events around enact()
+                agg["lv"].append((list(st.level_direction), list(st.level_edges), list(st.level_kernel_ms)))
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), (time.perf_counter() - t_wall) * 1e3, agg, st
+
+    for _ in range(warmup):
+        step(d_out)
+    ms, wall_ms, agg, last = timed(d_out, steps)
+    step(h_out)
+    ms_e2e, _, agg_e2e, _ = timed(h_out, steps)
+    result = h_out.numpy().copy()
+
+    # ---- numerator (same for every arm): needs the row offsets on the host ------------------------
+    ro, ci, w = G.download()
+    iters = last.iterations
+    touched = reached_degree_sum(wl, ro, result, iters)
+    value = touched * steps / ms / 1e3                    # edges / ms / 1000 = MTEPS (performance.hxx:225-229)
+    e2e = touched * steps / ms_e2e / 1e3
+    peak, peak_kind = peaks()
+
+    # ---- roofline of the dominant kernel class ----------------------------------------------------
+    # per-level CUDA events recorded by the enactor on the launching stream; a level's kernel time covers its
+    # advance / sweep launches.  BFS direction-optimised: the pull sweeps dominate; otherwise the advances.
+    dom_dir = 1 if (wl["alg"] == "bfs" and wl["direction"] != "forward") else 0
+    kb = km = 0.0
+    kl = 0
+    other_b = other_ms = 0.0
+    for dirs, edges, kms in agg["lv"]:
+        for i, (e, t) in enumerate(zip(edges, kms)):
+            d = dirs[i] if i < len(dirs) else 0
+            if wl["alg"] != "bfs" or d == dom_dir:
+                kb += e * bytes_per_edge
+                km += t
+                kl += 1
+            else:
+                other_b += e * bytes_per_edge
+                other_ms += t
+    ach = kb / (km * 1e-3) / 1e9 if km > 0 else 0.0
+    lbk = "merge_path" if wl["lb"] == "merge_path" else "binned"
+    kernel = {"bfs": "bfs_bottom_up_kernel + bfs_bottom_up_list_kernel (pull levels)" if dom_dir else
+              "advance_%s_kernel<bfs_claim_op>" % lbk,
+              "sssp": "advance_%s_kernel<sssp_relax_op>%s" % (lbk, " + advance_hub_kernel" if lbk == "binned" else ""),
+              "pr": "pr_pull_tile_kernel"}[wl["alg"]]
+    traffic, traffic_detail = load_traffic(name, wl) if not args.scale else (None, None)
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "traffic_detail": traffic_detail, "peak_kind": peak_kind, "kernel": kernel,
+                "bytes_per_edge": bytes_per_edge, "launches": kl, "kernel_ms_total": km,
+                "algorithmic_bytes_total": kb,
+                "whole_step": {"achieved": agg["inspected"] * bytes_per_edge / (ms * 1e-3) / 1e9,
+                               "frac": agg["inspected"] * bytes_per_edge / (ms * 1e-3) / 1e9 / peak}}
+    if other_ms > 0:
+        roofline["other_levels"] = {"kernel": "advance kernels of the push levels", "achieved":
+                                    other_b / (other_ms * 1e-3) / 1e9, "kernel_ms_total": other_ms}
+
+    r_sorted = sorted(agg["run_ms"])
+    runs = {"best_ms": r_sorted[0], "median_ms": statistics.median(r_sorted), "worst_ms": r_sorted[-1],
+            "best_mteps": touched / r_sorted[0] / 1e3, "median_mteps": touched / statistics.median(r_sorted) / 1e3,
+            "region": "CUDA events around the enactor loop of each run (enactor.hxx:266-288)"}
+    sum_kernel_ms = sum(sum(k) for _, _, k in agg["lv"]) / steps
+    record = {
+        "metric": f"MTEPS ({name})", "value": value, "unit": "MTEPS", "n_gpus": 1, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32" if wl["alg"] == "bfs" else "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "vertices": V, "edges": G.n_edges, "source": src,
+                   "source_degree": src_deg, "load_balance": wl["lb"], "direction": wl["direction"],
+                   "filter": "compact (fused into advance)",
+                   "numerator": "sum of out-degrees of the reached vertices (PageRank: E x iterations)",
+                   "edges_touched_per_step": touched, "edges_inspected_per_step": agg["inspected"] // steps,
+                   "inspected_mteps": agg["inspected"] / ms / 1e3,
+                   "l2_policy": "inputs larger than L2 (column indices %.0f MB > 126 MB)" % (G.n_edges * 4 / 1e6),
+                   "levels": last.iterations, "level_direction": last.level_direction,
+                   "level_frontier": last.level_frontier, "level_edges": last.level_edges[:last.iterations],
+                   "level_kernel_ms": [round(x, 4) for x in last.level_kernel_ms[:last.iterations]],
+                   "kernel_ms_per_step": sum_kernel_ms, "outside_kernels_frac": 1.0 - sum_kernel_ms / (ms / steps),
+                   "runs": runs,
+                   "experimental": {k: os.environ[k] for k in os.environ if k.startswith("B2G_")}},
+        "e2e": {"value": e2e, "unit": "MTEPS", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": V * 4,
+                "ms_per_step": ms_e2e / steps},
+        "gpu_launches": agg["launches"], "roofline": roofline, "cpu_baseline": None, "wall_ms": wall_ms,
+    }
+
+    # 16 random sources of degree > 0 (SURVEY.md 8d), device-resident results; never takes the line down
+    if extras and wl["alg"] in ("bfs", "sssp"):
+        try:
+            picks = np.random.default_rng(1).choice(np.flatnonzero(np.diff(ro) > 0), 16, replace=False)
+            per = []
+            fn = gb.bfs if wl["alg"] == "bfs" else gb.sssp
+            with torch.cuda.stream(stream):
+                for s16 in picks:
+                    st16 = fn(G, int(s16), d_out, options=opt)
+                    per.append(st16.elapsed_ms)
+            record["config"]["runs"]["random16_mean_ms"] = float(np.mean(per))
+            record["config"]["runs"]["random16_max_ms"] = float(np.max(per))
+        except Exception as ex:
+            record["config"]["runs"]["random16_error"] = str(ex)
+        step(d_out)  # leave the bench source's result in place
+
+    if args.reference_gpu:
+        try:
+            record["reference_gpu"] = reference_gpu_leg(G, wl, src, touched)
+            for lb in ("block_mapped", "merge_path"):
+                r = record["reference_gpu"].get(lb)
+                if r and r.get("ms_median"):
+                    r["ours_over_reference_gpu"] = r["ms_median"] / runs["median_ms"]
+        except Exception as ex:
+            record["reference_gpu"] = {"error": str(ex)}
+    G.close()
+    del G
+    record["setup_s"] = round(time.time() - t_setup, 1)
+
+    # ---- CPU baseline on this box's host cores + full-size parity -----------------------------------
+    def cpu_leg():
+        try:
+            run, kind, cores = cpu_run_factory(wl, ro, ci, w)
+            res, cms = run(src)
+            et = reached_degree_sum(wl, ro, res[0] if wl["alg"] == "pr" else res, res[1] if wl["alg"] == "pr" else None)
+            cpu = {"value": et / cms / 1e3, "unit": "MTEPS", "cores": cores, "kind": kind,
+                   "sample": f"1 full {wl['alg']} run from the bench source ({cms / 1e3:.1f} s, validator's own "
+                             f"timer); host cores available: {os.cpu_count()}"}
+            ok, detail = parity(wl, result, res)
+            if wl["alg"] == "pr":
+                detail["iterations_equal"] = bool(int(res[1]) == int(iters))
+                ok = ok and detail["iterations_equal"]
+            cpu["parity_full_size"] = ok
+            cpu["parity_detail"] = detail
+        except Exception as ex:  # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": "MTEPS", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        record["cpu_baseline"] = cpu
+
+    if not cpu_baseline:
+        return record, (lambda: record)
+    if background_cpu:
+        th = threading.Thread(target=cpu_leg, daemon=True)   # ctypes releases the GIL during the CPU run
+        th.start()
+
+        def finish():
+            th.join()
+            return record
+        return record, finish
+    cpu_leg()
+    return record, (lambda: record)
+
+
+# ---------------------------------------------------------------------------------------------
+# N > 1: ONE traversal over the 1-D partitioned graph (BASELINE.json configs[4], strong scaling)
+# ---------------------------------------------------------------------------------------------
 def run_partitioned(args, wl, name, rank, world, local):
-    """BASELINE.json configs[4]: one BFS over a graph 1-D partitioned across the ranks (strong scaling)."""
     import torch
     import torch.distributed as dist
     import gunrock_b200 as gb
@@ -257,87 +502,125 @@ def run_partitioned(args, wl, name, rank, world, local):
                        hub_threshold=args.hub_threshold, ctas_per_sm=args.ctas_per_sm)
     eng = mg.CudaRankEngine(G, opt)
     direction = getattr(gb.advance_direction_t, wl["direction"])
+    mg.p2p_connect(eng, comm)
 
-    exchange = args.exchange
-    if exchange == "p2p":     # the kernels exchange frontiers over NVLink peer memory (bfs_p2p.cuh)
-        mg.p2p_connect(eng, comm)
+    def step_p2p():   # the kernels exchange frontiers over NVLink peer memory (bfs_p2p.cuh)
+        return mg.bfs_rank_p2p(eng, src, total_edges, direction)
 
-        def step():
-            return mg.bfs_rank_p2p(eng, src, total_edges, direction)
-    else:                     # NCCL all-to-all / all-gather / all-reduce between the per-rank kernels
-        def step():
-            return mg.bfs_rank_async(eng, comm, src, total_edges, direction=direction)
+    def step_nccl():  # NCCL all-to-all / all-gather / all-reduce between the per-rank kernels
+        return mg.bfs_rank_async(eng, comm, src, total_edges, direction=direction)
 
-    for _ in range(max(args.warmup, 3)):
-        dloc, st = step()
+    primary, other = (step_p2p, step_nccl) if args.exchange == "p2p" else (step_nccl, step_p2p)
+
+    def timed(step, k, copy_out=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        inspected = 0
+        for _ in range(k):
+            dloc, st = step()
+            inspected += st.edges_touched
+            if copy_out is not None:
+                copy_out.copy_(dloc, non_blocking=False)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), inspected, dloc, st
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        primary()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    edges = 0
-    for _ in range(args.steps):
-        dloc, st = step()
-        edges += st.edges_touched
-    e1.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+    ms, inspected, dloc, st = timed(primary, args.steps)
     # e2e: the rank's slice of the result is copied to pinned host memory inside the timed region
     h = torch.empty(G.n_local, dtype=torch.int32).pin_memory()
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        dloc, st2 = step()
-        h.copy_(dloc, non_blocking=False)
-    e1.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms2 = float(ms2.item())
-    reached = torch.tensor([int((dloc < 2**31 - 1).sum())], device="cuda")
-    dist.all_reduce(reached)
-    agree = None
-    if exchange == "p2p":     # outside the timed region: same depths as the NCCL-exchange path, on every rank
-        d_nccl, _ = mg.bfs_rank_async(eng, comm, src, total_edges, direction=direction)
-        same = torch.tensor([int(torch.equal(dloc, d_nccl))], device="cuda")
-        dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        agree = bool(same.item())
+    ms2, _, dloc, _ = timed(primary, args.steps, copy_out=h)
     clocks = sampler.stop() if rank == 0 else None
+    # the other exchange, same graph, same source, outside the headline's timed region
+    other_rec = None
+    try:
+        for _ in range(2):
+            other()
+        k2 = min(args.steps, 5)
+        ms_o, _, d_other, st_o = timed(other, k2)
+        same = torch.tensor([int(torch.equal(dloc, d_other))], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        other_rec = {"exchange": "nccl" if args.exchange == "p2p" else "p2p", "ms_per_step": ms_o / k2,
+                     "depths_equal_primary": bool(same.item())}
+    except Exception as ex:
+        other_rec = {"error": str(ex)[:300]}
+
+    # ---- numerator + full-size parity over the GATHERED depths ----------------------------------------
+    # vertex v lives on rank v % P at row v // P: gather the slices on rank 0 and interleave
+    rows0 = mg.rows_of(G.n_global, world, 0)
+    pad = torch.full((rows0,), INT_MAX, dtype=torch.int32, device="cuda")
+    pad[:G.n_local] = dloc
+    gathered = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, gathered, dst=0)
+    line = None
     if rank == 0:
+        full = torch.stack(gathered, dim=1).reshape(-1)[:G.n_global].contiguous()   # [row, rank] -> v = row*P + rank
+        del gathered
         peak, peak_kind = peaks()
-        value = edges / ms / 1e3
+        par = {}
+        touched = None
+        try:
+            # the same graph, whole, on this GPU: the single-GPU fused enactor's depths (bit-exact) ...
+            G1 = gb.graph_t.rmat(wl["scale"], n_pairs, wl["seed"], mirror=wl["mirror"])
+            d1 = torch.empty(G.n_global, dtype=torch.int32, device="cuda")
+            gb.bfs(G1, src, d1, options=gb.options_t(advance_direction=gb.advance_direction_t.optimized))
+            par["equal_single_gpu_enactor"] = bool(torch.equal(d1, full))
+            ro, ci, w = G1.download()
+            G1.close()
+            del d1
+            touched = reached_degree_sum(wl, ro, full.cpu().numpy())
+            if not args.no_cpu_baseline:   # ... and the reference's CPU validator on this box's host cores
+                run, kind, cores = cpu_run_factory(wl, ro, ci, None)
+                res, cms = run(src)
+                ok, detail = parity(wl, full.cpu().numpy(), res)
+                par.update({"parity_full_size": ok, "parity_detail": detail})
+                par["cpu_baseline"] = {"value": touched / cms / 1e3, "unit": "MTEPS", "cores": cores, "kind": kind,
+                                       "sample": f"1 full bfs run from the bench source ({cms / 1e3:.1f} s); host "
+                                                 f"cores available: {os.cpu_count()}", "parity_full_size": ok,
+                                       "parity_detail": detail}
+        except Exception as ex:
+            par["error"] = str(ex)[:300]
+        if touched is None:
+            touched = total_edges
+        value = touched * args.steps / ms / 1e3
+        ach = 4.0 * inspected / world / (ms * 1e-3) / 1e9
         line = {"metric": f"MTEPS ({name})", "value": value, "unit": "MTEPS", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": wl["desc"], "exchange": "kernels over NVLink peer memory (CUDA IPC windows)"
-                           if exchange == "p2p" else "NCCL all_to_all_single / all_gather / all_reduce",
+                "config": {"workload": wl["desc"],
+                           "exchange": "kernels over NVLink peer memory (CUDA IPC windows)" if args.exchange == "p2p"
+                           else "NCCL all_to_all_single / all_gather / all_reduce",
+                           "other_exchange": other_rec,
+                           "numerator": "sum of out-degrees of the reached vertices (identical at every N)",
                            "vertices": G.n_global, "edges": total_edges, "source": src,
+                           "edges_touched_per_step": touched, "edges_inspected_per_step": inspected // args.steps,
                            "levels": st.levels, "level_direction": st.level_direction,
                            "level_frontier": st.level_frontier, "level_edges": st.level_edges,
-                           "ids_exchanged_per_step_rank0": st.exchanged_ids, "reached_vertices": int(reached.item()),
-                           "depths_equal_nccl_path": agree,
+                           "ids_exchanged_per_step_rank0": st.exchanged_ids,
+                           "parity": {k: v for k, v in par.items() if k != "cpu_baseline"},
                            "l2_policy": "inputs larger than L2 per rank" if total_edges * 4 / world > 126e6 else
-                                        "per-rank column indices %.0f MB" % (total_edges * 4 / world / 1e6),
-                           "graph500_mteps": total_edges / (ms / args.steps) / 1e3},
-                "e2e": {"value": edges / ms2 / 1e3, "unit": "MTEPS", "h2d_bytes_per_step": 4,
+                                        "per-rank column indices %.0f MB" % (total_edges * 4 / world / 1e6)},
+                "e2e": {"value": touched * args.steps / ms2 / 1e3, "unit": "MTEPS", "h2d_bytes_per_step": 4,
                         "d2h_bytes_per_step": G.n_local * 4, "ms_per_step": ms2 / args.steps},
-                "gpu_launches": (st.kernel_launches * args.steps) if exchange == "p2p" else None,
-                "roofline": {"bound": "hbm", "achieved": 4.0 * edges / world / (ms * 1e-3) / 1e9, "peak": peak,
-                             "unit": "GB/s", "frac": 4.0 * edges / world / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                             "peak_kind": peak_kind, "kernel": "whole step per rank (advance + sweep + exchange)",
-                             "bytes_per_edge": 4},
-                "cpu_baseline": None, "clocks": clocks}
+                "gpu_launches": (st.kernel_launches * args.steps) if args.exchange == "p2p" else None,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": None, "peak_kind": peak_kind,
+                             "kernel": "whole step per rank (advance + sweep + exchange)", "bytes_per_edge": 4},
+                "cpu_baseline": par.get("cpu_baseline"), "clocks": clocks}
         print(json.dumps(line), flush=True)
-    if exchange == "p2p":
-        mg.p2p_disconnect(eng, comm)
+    mg.p2p_disconnect(eng, comm)
     G.close()
+    dist.barrier()
     dist.destroy_process_group()
 
 
@@ -347,7 +630,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bfs_push_rmat22", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: bfs_do_rmat26 at N = 1, bfs_part_rmat26 (same graph, partitioned) at N > 1")
+    ap.add_argument("--configs", default=None, choices=["all", "none"],
+                    help="N = 1: also run the other BASELINE.json configurations as sub-records "
+                         "(default: all when --workload is not given)")
     ap.add_argument("--scale", type=int, default=0, help="override the RMAT scale (testing only)")
     ap.add_argument("--lb", default=None, choices=["thread_mapped", "block_mapped", "merge_path"])
     ap.add_argument("--direction", default=None, choices=["forward", "backward", "optimized"])
@@ -358,18 +645,28 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reference-gpu", action="store_true",
                     help="also time the UNMODIFIED reference GPU kernels (oracle/_ref/gunrock_ref_gpu, built for "
-                         "sm_100a with the atomics fix of SURVEY.md F2) on the same graph and GPU; N = 1 only")
+                         "sm_100a with the atomics fix of SURVEY.md F2) on the same graphs and GPU; N = 1 only")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    name = args.workload
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    explicit = args.workload is not None
+    name = args.workload or (HEADLINE_N if world > 1 else HEADLINE_1)
+    if args.impl == "reference" and not explicit:
+        name = HEADLINE_N if args.gpus > 1 else HEADLINE_1
     wl = dict(WORKLOADS[name])
-    if args.scale:
-        wl["scale"] = args.scale
-        if wl.get("pairs"):
-            wl["pairs"] = 17 * (1 << args.scale)
-        if wl["fold"]:
-            wl["fold"] = int(0.578 * (1 << args.scale))
+
+    def scaled(w):
+        w = dict(w)
+        if args.scale:
+            w["scale"] = args.scale
+            if w.get("pairs"):
+                w["pairs"] = 17 * (1 << args.scale)
+            if w["fold"]:
+                w["fold"] = int(0.578 * (1 << args.scale))
+        return w
+
+    wl = scaled(wl)
     if args.lb:
         wl["lb"] = args.lb
     if args.direction:
@@ -383,7 +680,6 @@ def main():
     import gunrock_b200 as gb
 
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if gb.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; libgunrock_b200 has no CPU fallback")
@@ -394,210 +690,37 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), rank=rank, world_size=world)
     if wl.get("partitioned"):
         return run_partitioned(args, wl, name, rank, world, local)
-
-    # ---- graph, generated on the device (ingest is untimed, as in the reference) ----------------
-    n_pairs = wl.get("pairs") or wl["ef"] * (1 << wl["scale"])
-    G = gb.graph_t.rmat(wl["scale"], n_pairs, wl["seed"], mirror=wl["mirror"], fold_vertices=wl["fold"],
-                        weights=wl["weights"], weight_seed=wl["seed"] + 1)
-    src, src_deg = G.max_degree_vertex()
-    if wl["alg"] == "pr" or wl["direction"] != "forward":
-        G.build_transpose()
-    stream = torch.cuda.Stream()
-    opt = gb.options_t(advance_load_balance=getattr(gb.load_balance_t, wl["lb"]),
-                       advance_direction=getattr(gb.advance_direction_t, wl["direction"]),
-                       filter_algorithm=gb.filter_algorithm_t.compact, enable_filter=True,
-                       hub_threshold=args.hub_threshold, ctas_per_sm=args.ctas_per_sm,
-                       stream=stream.cuda_stream)
-    V = G.n_vertices
-    out_dtype = torch.int32 if wl["alg"] == "bfs" else torch.float32
-    d_out = torch.empty(V, dtype=out_dtype, device="cuda")
-    h_out = torch.empty(V, dtype=out_dtype).pin_memory()
-
-    # N > 1: a batch of sources, sharded over ranks (replicated graph, no collective on the data path)
-    # The unit of work is one traversal from a hub: N = 1 runs the highest-degree vertex (the bench source
-    # of the reference arm and of the CPU baseline); N > 1 runs the 4 N highest-degree vertices, 4 per
-    # rank, so that every rank's traversals have the same level profile as the N = 1 unit.
-    sources = [src]
     if world > 1:
-        deg_host = np.diff(G.download()[0])
-        batch = [int(x) for x in np.argsort(-deg_host.astype(np.int64), kind="stable")[:world * 4]]
-        sources = batch[rank::world]
+        raise SystemExit(f"bench.py: workload {name} is a single-GPU configuration; N > 1 runs bfs_part_*")
 
-    def step(out):
-        tot = None
-        for s in (sources if world > 1 else [src]):
-            if wl["alg"] == "bfs":
-                st = gb.bfs(G, s, out, options=opt)
-            elif wl["alg"] == "sssp":
-                st = gb.sssp(G, s, out, options=opt)
-            else:
-                st = gb.pr(G, out, 0.85, 1e-6, options=opt)
-            if tot is None:
-                tot = st
-            else:
-                tot.edges_touched += st.edges_touched
-                tot.kernel_launches += st.kernel_launches
-                tot.level_edges += st.level_edges
-                tot.level_kernel_ms += st.level_kernel_ms
-        return tot
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(out, steps):
-        """K steps bracketed by barrier+sync; CUDA events on the launching stream; max over ranks."""
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        agg = dict(edges=0, launches=0, kern_bytes=0.0, kern_ms=0.0, kern_launches=0, run_ms=[])
-        barrier()
-        t_wall = time.perf_counter()
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(steps):
-                st = step(out)
-                agg["edges"] += st.edges_touched
-                agg["launches"] += st.kernel_launches
-                agg["run_ms"].append(float(st.elapsed_ms))   # the library's own events around enact() (first source)
-                for e, ms in zip(st.level_edges, st.level_kernel_ms):
-                    agg["kern_bytes"] += e * bytes_per_edge
-                    agg["kern_ms"] += ms
-                    agg["kern_launches"] += 1
-            e1.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - t_wall) * 1e3
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms, float(agg["edges"]), float(agg["launches"])], device="cuda", dtype=torch.float64)
-            mx = t.clone()
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            ms, agg["edges"], agg["launches"] = float(mx[0]), int(t[1]), int(t[2])
-        return ms, wall_ms, agg, st
-
-    bytes_per_edge = 8 if wl["alg"] == "sssp" else 4
-    for _ in range(args.warmup):
-        step(d_out)
+    # ---- N = 1: the headline first (nothing else running), then the other configurations -------------
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms, wall_ms, agg, last = timed(d_out, args.steps)
-    for _ in range(1):
-        step(h_out)
-    ms_e2e, wall_e2e, agg_e2e, _ = timed(h_out, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
-
-    value = agg["edges"] / ms / 1e3                       # edges / ms / 1000 = MTEPS (performance.hxx:225-229)
-    e2e = agg_e2e["edges"] / ms_e2e / 1e3
-    peak, peak_kind = peaks()
-    # roofline for the dominant kernel (this rank): algorithmic bytes per launch / mean launch time
-    ach = agg["kern_bytes"] / (agg["kern_ms"] * 1e-3) / 1e9 if agg["kern_ms"] > 0 else 0.0
-    if world > 1 and rank != 0:
-        dist.destroy_process_group()
-        return
-
-    # DRAM traffic per launch of the dominant kernel: from the committed ncu capture of this very
-    # configuration (profiles/r1_traffic.json), never measured under the profiler here
-    lbk = "merge_path" if wl["lb"] == "merge_path" else "binned"
-    traffic, traffic_detail = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            entry = json.load(f).get(f"{name}/{wl['lb']}")
-        if entry and wl["direction"] == "forward" and not args.scale:
-            per = [l["dram_read_bytes"] + l["dram_write_bytes"] for l in entry["launches"]]
-            traffic = sum(per) / len(per)
-            traffic_detail = {"source": entry["source"], "launches": entry["launches"],
-                              "note": "mean over the capture's launches; compare with their algorithmic_bytes"}
-    except (OSError, ValueError, KeyError):
-        pass
-
-    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -----------------------------
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            ro, ci, w = G.download()
-            run, kind, cores = cpu_run_factory(wl, ro, ci, w)
-            res, cms = run(src)
-            et = edges_touched_cpu(wl, ro, res)
-            cpu = {"value": et / cms / 1e3, "unit": "MTEPS", "cores": cores, "kind": kind,
-                   "sample": f"1 full {wl['alg']} run from the bench source ({cms / 1e3:.1f} s, validator's own timer); "
-                             f"host cores available: {os.cpu_count()}"}
-            # parity spot check on the full-size result (the checker checking the product, not the reverse)
-            if wl["alg"] == "pr":
-                ok = bool(np.allclose(h_out.numpy(), res[0], rtol=1e-6, atol=0))
-            else:
-                ok = bool(np.array_equal(h_out.numpy().view(np.uint32), np.asarray(res).view(np.uint32)))
-            cpu["parity_full_size"] = ok
-        except Exception as ex:  # the baseline must never take the bench line down
-            cpu = {"value": None, "unit": "MTEPS", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
-
-    # Optional second baseline row (SURVEY.md 8d): the reference's own GPU implementation on this GPU,
-    # same graph (written once in the reference's .csr layout), same source, its own enactor timer.
-    ref_gpu = None
-    if args.reference_gpu and world == 1:
-        try:
-            ref_gpu = reference_gpu_leg(G, wl, src, agg["edges"] // args.steps)
-        except Exception as ex:
-            ref_gpu = {"error": str(ex)}
-
-    # SURVEY.md 8d: best / median of the runs (the reference's timed region: CUDA events around enact()),
-    # and the mean over 16 random sources of degree > 0 (RNG seed 1).  Extras: they never take the line down.
-    runs = None
-    try:
-        if world == 1 and agg["run_ms"]:
-            r = sorted(agg["run_ms"])
-            per_run_edges = agg["edges"] / args.steps
-            runs = {"best_ms": r[0], "median_ms": statistics.median(r), "worst_ms": r[-1],
-                    "best_mteps": per_run_edges / r[0] / 1e3, "median_mteps": per_run_edges / statistics.median(r) / 1e3,
-                    "region": "CUDA events around the enactor loop of each run (enactor.hxx:266-288)"}
-            if wl["alg"] in ("bfs", "sssp") and not args.no_cpu_baseline:
-                deg_host = np.diff(G.download()[0])
-                picks = np.random.default_rng(1).choice(np.flatnonzero(deg_host > 0), 16, replace=False)
-                per = []
-                with torch.cuda.stream(stream):
-                    for s16 in picks:
-                        fn = gb.bfs if wl["alg"] == "bfs" else gb.sssp
-                        st16 = fn(G, int(s16), d_out, options=opt)
-                        per.append(st16.edges_touched / max(st16.elapsed_ms, 1e-6) / 1e3)
-                runs["random16_mean_mteps"] = float(np.mean(per))
-                runs["random16_min_mteps"] = float(np.min(per))
-    except Exception as ex:
-        runs = {"error": str(ex)}
-
-    out_bytes = V * 4
-    line = {
-        "metric": f"MTEPS ({name})", "value": value, "unit": "MTEPS", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int32" if wl["alg"] == "bfs" else "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "vertices": V, "edges": G.n_edges, "source": src,
-                   "source_degree": src_deg, "load_balance": wl["lb"], "direction": wl["direction"],
-                   "filter": "compact (fused into advance)", "sources_per_step": len(sources) * world if world > 1 else 1,
-                   "sources": "highest-degree vertex" if world == 1 else "the 4 N highest-degree vertices, 4 per rank",
-                   "l2_policy": "inputs larger than L2 (column indices %.0f MB > 126 MB)" % (G.n_edges * 4 / 1e6),
-                   "levels": last.iterations, "level_direction": last.level_direction,
-                   "level_frontier": last.level_frontier, "level_edges": last.level_edges[:last.iterations],
-                   "level_kernel_ms": [round(x, 4) for x in last.level_kernel_ms[:last.iterations]],
-                   "edges_touched_per_step": agg["edges"] // args.steps, "runs": runs,
-                   "experimental": {"B2G_ADVANCE_VARIANT": os.environ.get("B2G_ADVANCE_VARIANT", "0"),
-                                    "B2G_SSSP_DELTA": os.environ.get("B2G_SSSP_DELTA", "")},
-                   "graph500_mteps": (G.n_edges * (len(sources) * world if world > 1 else 1)) / (ms / args.steps) / 1e3},
-        "e2e": {"value": e2e, "unit": "MTEPS", "h2d_bytes_per_step": 4 * (len(sources) if world > 1 else 1),
-                "d2h_bytes_per_step": out_bytes * (len(sources) if world > 1 else 1), "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": agg["launches"],
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": traffic, "traffic_detail": traffic_detail, "peak_kind": peak_kind,
-                     "kernel": {"bfs": "advance_%s_kernel<bfs_claim_op>" % lbk,
-                                "sssp": "advance_%s_kernel<sssp_relax_op>" % lbk, "pr": "pr_pull_tile_kernel"}[wl["alg"]],
-                     "bytes_per_edge": bytes_per_edge, "launches": agg["kern_launches"],
-                     "kernel_ms_total": agg["kern_ms"]},
-        "cpu_baseline": cpu, "clocks": clocks, "wall_ms": wall_ms,
-    }
-    if ref_gpu is not None:
-        line["reference_gpu"] = ref_gpu
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    sampler.start()
+    head, finish_head = bench_single(args, name, wl, args.steps, args.warmup, local,
+                                     cpu_baseline=not args.no_cpu_baseline)
+    clocks = sampler.stop()
+    head["clocks"] = clocks
+    run_configs = (args.configs or ("none" if explicit else "all")) == "all"
+    subs = {}
+    if run_configs:
+        pending = []
+        for sub in SUB_CONFIGS:
+            if sub == name:
+                continue
+            try:
+                k = min(args.steps, 10)
+                rec, fin = bench_single(args, sub, scaled(WORKLOADS[sub]), k, args.warmup, local,
+                                        cpu_baseline=not args.no_cpu_baseline,
+                                        background_cpu=(sub == "sssp_rmat24"), extras=False)
+                pending.append((sub, fin))
+            except Exception as ex:
+                subs[sub] = {"error": str(ex)[:400]}
+        for sub, fin in pending:
+            rec = fin()
+            rec["config"].pop("runs", None)
+            subs[sub] = rec
+        head["configs"] = subs
+    print(json.dumps(finish_head()), flush=True)
 
 
 if __name__ == "__main__":

@@ -9,7 +9,8 @@
 #     operator headers                                      -> bin/ref_algorithms
 #  0. (no reference needed) examples/api_selftest.cu -> bin/api_selftest,
 #     examples/dense_frontier_selftest.cu (bitmap / boolmap frontier views) -> bin/dense_frontier_selftest,
-#     examples/cache_selftest.cu (per-graph caches of the fused enactors across graphs / contexts) -> bin/cache_selftest
+#     examples/cache_selftest.cu (per-graph caches of the fused enactors across graphs / contexts) -> bin/cache_selftest,
+#     examples/multi_context_selftest.cu (bfs::run over a multi-device gcuda::multi_context_t) -> bin/multi_context_selftest
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 REF=${REF:-/root/reference}
@@ -20,6 +21,7 @@ pids=()
 nvcc $FLAGS -o "$OUT/api_selftest" "$ROOT/examples/api_selftest.cu" & pids+=($!)
 nvcc $FLAGS -o "$OUT/dense_frontier_selftest" "$ROOT/examples/dense_frontier_selftest.cu" & pids+=($!)
 nvcc $FLAGS -o "$OUT/cache_selftest" "$ROOT/examples/cache_selftest.cu" & pids+=($!)
+nvcc $FLAGS -o "$OUT/multi_context_selftest" "$ROOT/examples/multi_context_selftest.cu" & pids+=($!)
 if [ ! -d "$REF" ]; then
   rc=0; for p in "${pids[@]}"; do wait $p || rc=1; done; exit $rc
 fi

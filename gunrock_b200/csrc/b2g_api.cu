@@ -61,36 +61,6 @@ bool have_device() {
 
 }  // namespace
 
-/// Peer-memory exchange state of one rank (bfs_p2p.cuh): its own window, the peers' mappings.
-struct p2p_state_t {
-  p2p_window_t w;
-  void* own = nullptr;
-  size_t own_bytes = 0;
-  void* opened[kMaxPeers] = {};  // cudaIpcOpenMemHandle mappings to close
-  bool attached = false;
-  unsigned epoch = 0;
-  int seq = 0;
-  p2p_feedback_t* h_fb = nullptr;
-  p2p_tail_report_t* h_tail = nullptr;
-  void release() {
-    if (h_tail)
-      cudaFreeHost(h_tail);
-    h_tail = nullptr;
-    for (auto& o : opened)
-      if (o) {
-        cudaIpcCloseMemHandle(o);
-        o = nullptr;
-      }
-    if (own)
-      cudaFree(own);
-    own = nullptr;
-    if (h_fb)
-      cudaFreeHost(h_fb);
-    h_fb = nullptr;
-    attached = false;
-  }
-};
-
 struct b2g_graph {
   int n_vertices = 0;
   int n_edges = 0;
@@ -1477,29 +1447,9 @@ int b2g_part_p2p_window_create(b2g_graph_t* g, void** window, unsigned long long
   return guarded([&] {
     auto& P = g->p2p;
     if (!P.own) {  // one window per graph handle, kept until the handle is destroyed
-      P.w = p2p_window_t{};
-      P.w.nparts = g->pt.nparts;
-      P.w.me = g->pt.part;
-      P.w.words = (((g->pt.rows_of(0) + 31) / 32) + 3) & ~3;  // 16-byte aligned segments
-      // a global id is forwarded at most once per rank, so a row never holds more than the owner's rows
-      P.w.cap = g->pt.rows_of(0) + 64;
-      P.own_bytes = P.w.bytes();
-      B2G_CHECK(cudaMalloc(&P.own, P.own_bytes));
-      B2G_CHECK(cudaMemset(P.own, 0, P.own_bytes));
-      B2G_CHECK(cudaMallocHost(&P.h_fb, sizeof(p2p_feedback_t)));
-      memset(P.h_fb, 0, sizeof(p2p_feedback_t));
-      B2G_CHECK(cudaMallocHost(&P.h_tail, sizeof(p2p_tail_report_t)));
-      memset(P.h_tail, 0, sizeof(p2p_tail_report_t));
-      // everything the traversal allocates, now: the run itself must not call cudaMalloc / cudaFree
-      // (device-wide synchronisation while a peer's barrier kernel is spinning)
-      g->part.ensure(g->pt, 1);
-      g->part_deg.ensure(2);
-      reserve_advance_workspace(g->ws, g->view, g->pt.n_local);
-      if (g->symmetric) {
+      if (g->symmetric)
         build_transpose(g);
-        g->part.unreachable.ensure(static_cast<size_t>(g->part.words_per_rank()) + 4);
-      }
-      B2G_CHECK(cudaDeviceSynchronize());
+      part_p2p_prepare(g->ws, g->view, g->pt, g->part, g->part_deg, P, g->symmetric != 0);
     }
     if (ipc_handle) {
       cudaIpcMemHandle_t h;
@@ -1564,255 +1514,33 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
   return guarded([&] {
     b2g_options_t o = resolved(opt);
     cudaStream_t st = g->pick_stream(&o);
-    auto& S = g->part;
-    auto& P = g->p2p;
-    const p2p_window_t w = P.w;
-    const int np = w.nparts;
-    const int sms = device_info_t::get().sm_count;
-    const bool can_pull = g->symmetric && o.advance_direction != B2G_DIR_FORWARD;
-    const double alpha = o.do_alpha > 0 ? o.do_alpha : 14.0;
-    const double beta = o.do_beta > 0 ? o.do_beta : 24.0;
-    static const bool fused_sink = std::getenv("B2G_P2P_FUSED_SINK") != nullptr;
-    static const bool trace = std::getenv("B2G_TRACE") != nullptr;
-    static const char* timeout_env = std::getenv("B2G_P2P_TIMEOUT_MS");
-    const unsigned long long timeout_ns =
-        (timeout_env ? std::strtoull(timeout_env, nullptr, 10) : 20000ull) * 1000ull * 1000ull;
-
-    // ---- reset (the part of b2g_part_bfs_begin that matters here; no send buffer) ----------------
-    S.ensure(g->pt, 1);
-    g->part_deg.ensure(2);
-    const int sent_words = (g->pt.n_global + 31) / 32;
-    const unsigned* premark = nullptr;
-    if (can_pull) {
-      build_transpose(g);
-      if (!S.unreachable_for.matches(g->t_view)) {
-        S.unreachable.ensure(static_cast<size_t>(S.words_per_rank()) + 4);
-        bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(g->t_view.row_offsets, g->pt.n_local,
-                                                            S.unreachable.ptr);
-        S.unreachable_for.set(g->t_view);
-      }
-      premark = S.unreachable.ptr;
+    part_bfs_config_t cfg;
+    cfg.advance = to_launch(o);
+    cfg.direction = o.advance_direction;
+    cfg.alpha = o.do_alpha > 0 ? o.do_alpha : 14.0;
+    cfg.beta = o.do_beta > 0 ? o.do_beta : 24.0;
+    csr_view_t in_view;  // row_offsets == nullptr: no pull
+    if (g->symmetric && o.advance_direction != B2G_DIR_FORWARD) {
+      build_transpose(g);  // symmetric: the local CSR doubles as the local CSC
+      in_view = g->t_view;
     }
     const int launches0 = g->ws.launches;
+    part_bfs_report_t rep;
     B2G_CHECK(cudaEventRecord(g->ev0, st));
-    part_reset_kernel<<<sms * 8, 256, 0, st>>>(g->pt, source, S.dist.ptr, S.visited.ptr, S.sent.ptr,
-                                                sent_words, S.q[0].ptr, S.counts.ptr, premark);
-    part_seed_kernel<<<1, 1, 0, st>>>(g->pt, source, S.dist.ptr, S.visited.ptr);
-    B2G_CHECK(cudaMemsetAsync(S.overflow.ptr, 0, sizeof(int), st));
-    B2G_CHECK(cudaMemsetAsync(g->part_deg.ptr, 0, 16, st));
-    g->ws.launches += 2;
-    P.h_fb->timed_out = 0;
-
-    static const bool use_tail = std::getenv("B2G_P2P_NO_TAIL") == nullptr;
-    const long long tail_budget = 1 << 16;  // global frontier out-degree below which the tail kernel runs
-    const int push_ctas = std::max(8, std::min(sms * 4 / np, (w.words / 4 + 255) / 256));
-    // B2G_TRACE: CUDA-event stamps between the phases of every level (device time of this rank)
-    std::vector<std::pair<std::string, cudaEvent_t>> marks;
-    auto mark = [&](const std::string& name) {
-      if (!trace)
-        return;
-      cudaEvent_t e;
-      B2G_CHECK(cudaEventCreate(&e));
-      B2G_CHECK(cudaEventRecord(e, st));
-      marks.emplace_back(name, e);
-    };
-    mark("begin");
-    int cur = 0, level = 0, parity = 0;  // parity: which `front` buffer holds the current frontier
-    bool is_bitmap = false, bottom_up = false;
-    long long n_f = 1, m_f = 0, explored = 0;
-    unsigned long long edges_total = 0, verts_total = 0;
-    if (stats)
-      memset(stats, 0, sizeof *stats);
-    const auto t0 = std::chrono::steady_clock::now();
-    auto sync = [&](bool with_stats, const int* send_count, const int* count_ptr, const ctrl_t* c) {
-      ++P.epoch;
-      if (with_stats)
-        p2p_sync_kernel<true><<<1, 32, 0, st>>>(w, P.epoch, send_count, count_ptr, c, g->part_deg.ptr,
-                                                 S.overflow.ptr, P.h_fb, ++P.seq, timeout_ns);
-      else
-        p2p_sync_kernel<false><<<1, 32, 0, st>>>(w, P.epoch, send_count, nullptr, nullptr, nullptr,
-                                                  nullptr, P.h_fb, 0, timeout_ns);
-      g->ws.launches += 1;
-    };
-    while (n_f > 0) {
-      mark("L" + std::to_string(level) + ":");
-      bool go_up = false;
-      if (can_pull && level > 0) {
-        if (o.advance_direction == B2G_DIR_BACKWARD)
-          go_up = true;
-        else if (!bottom_up)
-          go_up = static_cast<double>(m_f) > static_cast<double>(total_edges - explored) / alpha;
-        else
-          go_up = !(static_cast<double>(n_f) < static_cast<double>(g->pt.n_global) / beta);
-      }
-      unsigned* my_front = w.front(w.me, parity) + static_cast<size_t>(w.me) * w.words;
-      // ---- tiny global frontier: the distributed tail kernel runs level after level on its own ------
-      if (!go_up && level > 0 && use_tail && m_f < tail_budget) {
-        if (is_bitmap) {
-          B2G_CHECK(cudaMemsetAsync(S.counts.ptr + cur, 0, sizeof(int), st));
-          bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(my_front, S.local_words(), S.q[cur].ptr,
-                                                          S.counts.ptr + cur);
-          g->ws.launches += 1;
-          is_bitmap = false;
-        }
-        P.h_tail->timed_out = 0;
-        p2p_tail_kernel<1024><<<1, 1024, 0, st>>>(
-            g->view, g->pt, w, P.epoch + 1, S.q[0].ptr, S.q[1].ptr, S.counts.ptr, cur, level, n_f, 16,
-            tail_budget, S.visited.ptr, S.sent.ptr, S.dist.ptr, S.overflow.ptr, P.h_tail, ++P.seq, timeout_ns);
-        g->ws.launches += 1;
-        mark("tail");
-        wait_for_sequence(&P.h_tail->seq, P.seq, st);
-        const p2p_tail_report_t& t = *P.h_tail;
-        P.epoch += 2u * static_cast<unsigned>(t.levels);
-        if (t.timed_out)
-          throw std::runtime_error("b2g_part_bfs_p2p: a peer did not reach a barrier of the tail kernel (time-out)");
-        for (int k = 0; k < t.levels; ++k) {
-          if (stats && level + k < 64) {
-            stats->level_direction[level + k] = 0;
-            stats->level_frontier[level + k] = static_cast<int>(t.frontier[k]);
-            stats->level_edges[level + k] = static_cast<unsigned long long>(t.edges[k]);
-          }
-          edges_total += static_cast<unsigned long long>(t.edges[k]);
-          verts_total += static_cast<unsigned long long>(t.frontier[k]);
-          explored += t.edges[k];
-        }
-        if (trace)
-          std::fprintf(stderr, "[b2g-p2p] rank %d epoch %u levels %d..%d in the tail kernel, n_f=%lld m_f=%lld\n",
-                       w.me, P.epoch, level, level + t.levels - 1, t.count, t.deg_sum);
-        level += t.levels;
-        cur = t.cur;
-        n_f = t.count;
-        m_f = t.deg_sum;
-        bottom_up = false;
-        continue;
-      }
-      if (level > 0)
-        explored += m_f;
-      ctrl_t* c = nullptr;
-      const int* count_ptr = nullptr;
-      if (go_up) {
-        if (!is_bitmap) {  // queue -> bitmap in my segment, pushed to every peer, barrier
-          B2G_CHECK(cudaMemsetAsync(my_front, 0, sizeof(unsigned) * w.words, st));
-          part_queue_to_bitmap_kernel<<<sms * 4, 256, 0, st>>>(S.q[cur].ptr, S.counts.ptr + cur, my_front);
-          if (np > 1) {
-            p2p_push_segment_kernel<<<dim3(push_ctas, np), 256, 0, st>>>(w, parity);
-            sync(false, nullptr, nullptr, nullptr);
-          }
-          g->ws.launches += 2;
-          is_bitmap = true;
-        }
-        c = g->ws.next_ctrl();
-        B2G_CHECK(cudaMemsetAsync(S.counts.ptr + 2, 0, sizeof(int), st));
-        const unsigned* all = w.front(w.me, parity);
-        if (fused_sink || np == 1) {
-          part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
-              g->pt, g->t_view, w.words, S.visited.ptr, all, peer_word_sink_t{w, parity ^ 1}, S.dist.ptr,
-              level + 1, c, S.counts.ptr + 2);
-        } else {
-          unsigned* nxt_seg = w.front(w.me, parity ^ 1) + static_cast<size_t>(w.me) * w.words;
-          part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
-              g->pt, g->t_view, w.words, S.visited.ptr, all, local_word_sink_t{nxt_seg}, S.dist.ptr,
-              level + 1, c, S.counts.ptr + 2);
-          mark("sweep");
-          p2p_push_segment_kernel<<<dim3(push_ctas, np), 256, 0, st>>>(w, parity ^ 1);
-          g->ws.launches += 1;
-        }
-        mark("push");
-        g->ws.launches += 1;
-        parity ^= 1;
-        count_ptr = S.counts.ptr + 2;
-      } else {
-        if (is_bitmap) {  // bitmap -> queue (my segment of the current frontier map)
-          B2G_CHECK(cudaMemsetAsync(S.counts.ptr + cur, 0, sizeof(int), st));
-          bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(my_front, S.local_words(), S.q[cur].ptr,
-                                                          S.counts.ptr + cur);
-          g->ws.launches += 1;
-          is_bitmap = false;
-        }
-        const int nxt = cur ^ 1;
-        B2G_CHECK(cudaMemsetAsync(S.counts.ptr + nxt, 0, sizeof(int), st));
-        B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
-        p2p_claim_op op{g->pt, w, S.visited.ptr, S.sent.ptr, S.dist.ptr, level + 1, S.send_count.ptr,
-                        S.overflow.ptr};
-        // same path selection as the single-GPU enactor (bfs.cuh), on this rank's share of the frontier
-        advance_launch_t lcfg = to_launch(o);
-        const long long m_rank = m_f / np;
-        lcfg.avg_degree = (level > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
-        if (level == 0) {
-          lcfg.lb = lb_t::block_mapped;  // one row of unknown length
-        } else if (m_rank < lcfg.small_frontier_edges) {
-          lcfg.lb = lb_t::block_mapped;  // one kernel: warp / thread bins only
-          lcfg.hub_threshold = 1 << 30;
-        } else if (lcfg.lb == lb_t::merge_path && m_rank < lcfg.mid_frontier_edges) {
-          lcfg.lb = lb_t::block_mapped;  // skip the scan + partition launches
-        }
-        launch_advance<advance_output_t::vertices, true, false>(
-            g->ws, g->view, S.q[cur].ptr, S.counts.ptr + cur, g->pt.n_local, S.q[nxt].ptr,
-            S.counts.ptr + nxt, g->pt.n_local, op, lcfg, &c);
-        mark("advance");
-        if (np > 1) {
-          sync(false, S.send_count.ptr, nullptr, nullptr);
-          mark("barrier");
-          part_claim_packed_kernel<<<dim3(std::max(16, sms * 2 / np), np), 256, 0, st>>>(
-              g->pt, w.inbox(w.me, 0), static_cast<int>(w.inbox_row_ints()) - 1, S.visited.ptr, S.dist.ptr,
-              level + 1, g->view.row_offsets, S.q[nxt].ptr, S.counts.ptr + nxt, g->part_deg.ptr,
-              S.overflow.ptr);
-          g->ws.launches += 1;
-          mark("claim");
-        }
-        cur = nxt;
-        count_ptr = S.counts.ptr + cur;
-      }
-      sync(true, nullptr, count_ptr, c);
-      mark("stats");
-      wait_for_sequence(&P.h_fb->seq, P.seq, st);
-      if (P.h_fb->timed_out)
-        throw std::runtime_error("b2g_part_bfs_p2p: rank " + std::to_string(w.me) + " level " +
-                                 std::to_string(level) + ": peer " + std::to_string(P.h_fb->late_peer) +
-                                 " did not reach barrier epoch " + std::to_string(P.h_fb->late_epoch) +
-                                 " (published " + std::to_string(P.h_fb->late_seen) + ", time-out)");
-      if (P.h_fb->overflow)
-        throw std::runtime_error("b2g_part_bfs_p2p: frontier / inbox overflow");
-      if (trace)
-        std::fprintf(stderr, "[b2g-p2p] rank %d epoch %u level %d %s n_f=%lld m_f=%lld edges=%lld t=%.1f us\n",
-                     w.me, P.epoch, level, go_up ? "up" : "down", n_f, m_f, P.h_fb->edges,
-                     std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
-      if (stats && level < 64) {
-        stats->level_direction[level] = go_up ? 1 : 0;
-        stats->level_frontier[level] = static_cast<int>(n_f);
-        stats->level_edges[level] = static_cast<unsigned long long>(P.h_fb->edges);
-      }
-      edges_total += static_cast<unsigned long long>(P.h_fb->edges);
-      verts_total += static_cast<unsigned long long>(n_f);
-      if (level == 0)
-        explored += P.h_fb->edges;
-      n_f = P.h_fb->count;
-      m_f = P.h_fb->deg_sum;
-      bottom_up = go_up;
-      ++level;
-    }
+    part_bfs_p2p_run(g->ws, g->view, in_view, g->pt, g->part, g->part_deg, g->p2p, source, total_edges, cfg, &rep);
     B2G_CHECK(cudaEventRecord(g->ev1, st));
     B2G_CHECK(cudaStreamSynchronize(st));
-    if (trace) {
-      std::string line = "[b2g-p2p] rank " + std::to_string(w.me) + " phases (us):";
-      for (size_t i = 1; i < marks.size(); ++i) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
-        char buf[64];
-        std::snprintf(buf, sizeof buf, " %s=%.1f", marks[i].first.c_str(), ms * 1e3f);
-        line += buf;
-      }
-      std::fprintf(stderr, "%s\n", line.c_str());
-      for (auto& m : marks)
-        cudaEventDestroy(m.second);
-    }
-    S.cur = cur;
-    S.frontier_is_bitmap = false;
     if (stats) {
+      memset(stats, 0, sizeof *stats);
       fill_stats_common(g, stats, launches0);
-      stats->iterations = stats->n_levels = level;
-      stats->edges_touched = edges_total;
-      stats->vertices_touched = verts_total;
+      stats->iterations = stats->n_levels = rep.levels;
+      stats->edges_touched = rep.edges_total;
+      stats->vertices_touched = rep.verts_total;
+      for (int l = 0; l < rep.levels && l < 64; ++l) {
+        stats->level_direction[l] = rep.level_direction[l];
+        stats->level_frontier[l] = rep.level_frontier[l];
+        stats->level_edges[l] = rep.level_edges[l];
+      }
     }
     return 0;
   });

@@ -19,6 +19,7 @@
 
 #include <gunrock/algorithms/algorithms.hxx>
 #include <gunrock/b200/bfs.cuh>
+#include <gunrock/b200/bfs_multi.cuh>
 
 namespace gunrock {
 namespace bfs {
@@ -107,6 +108,52 @@ struct enactor_t : gunrock::enactor_t<problem_t> {
   }
 };
 
+namespace detail {
+/**
+ * @brief `bfs::run` over a `gcuda::multi_context_t` of several devices (the reference throws here,
+ * include/gunrock/framework/operators/advance/advance.hxx:129-132).  The graph and `result.distances` live on
+ * the FIRST context's device, as for a single-device run; the graph is cut 1-D across the devices once (cached
+ * on the context), every device runs its rank of the level loop on its own context's stream with the frontier
+ * exchange done by the kernels over peer memory, and the depths are gathered back into `result.distances`.
+ * Same result contract as the single-device run (bit-identical depths).
+ */
+template <typename graph_t>
+float run_multi(graph_t& G,
+                param_t<typename graph_t::vertex_type>& param,
+                result_t<typename graph_t::vertex_type>& result,
+                gcuda::multi_context_t& context) {
+  auto ctx = context.get_context(0);
+  b200::part_bfs_config_t cfg;
+  cfg.advance.lb = operators::advance::detail::to_lb(param.options.advance_load_balance);
+  cfg.direction = static_cast<int>(param.options.advance_direction);
+  b200::csr_view_t out_view = G.csr_view();
+  b200::csr_view_t in_view;  // row_offsets == nullptr: pull disabled
+  if (cfg.direction != 0) {
+    if (G.has_csc())
+      in_view = G.csc_view();
+    else if (G.properties.symmetric)
+      in_view = out_view;
+    else
+      cfg.direction = 0;  // no transpose available: stay top-down
+  }
+  auto& cache = ctx->template scratch<b200::multi_bfs_cache_t>();
+  b200::part_bfs_report_t report;
+  b200::bfs_prepare_multi(context, cache, out_view, in_view);  // ingest: outside the timed region
+  auto& timer = ctx->timer();
+  timer.reset();
+  timer.begin(ctx->stream());
+  int depth = b200::bfs_run_multi(context, cache, out_view, in_view, static_cast<int>(param.single_source),
+                                  reinterpret_cast<int*>(result.distances), cfg, &report);
+  float ms = timer.end(ctx->stream());
+  auto& bench = benchmark::detail::current();
+  bench.search_depth = depth;
+  bench.total_runtime = ms;
+  bench.edges_visited += report.edges_total;
+  bench.vertices_visited += report.verts_total;
+  return ms;
+}
+}  // namespace detail
+
 template <typename graph_t>
 float run(graph_t& G,
           param_t<typename graph_t::vertex_type>& param,
@@ -125,9 +172,11 @@ float run(graph_t& G,
   enactor_type enactor(&problem, context);
   return enactor.enact();
 #else
-  error::throw_if_exception(context->size() != 1, "`context.size() != 1` not supported");
+  error::throw_if_exception(context->size() < 1, "empty multi_context_t");
   auto ctx = context->get_context(0);
   auto& ws = ctx->workspace();
+  if (context->size() > 1)  // several devices: the 1-D partitioned traversal (gunrock/b200/bfs_multi.cuh)
+    return detail::run_multi(G, param, result, *context);
   b200::bfs_config_t cfg;
   cfg.advance.lb = operators::advance::detail::to_lb(param.options.advance_load_balance);
   cfg.direction = static_cast<int>(param.options.advance_direction);

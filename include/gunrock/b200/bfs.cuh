@@ -417,6 +417,314 @@ bfs_bottom_up_list_kernel(csr_view_t in, const int* __restrict__ unv_in,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pull levels, second generation: the FIRST-IN-NEIGHBOUR shortcut.
+//
+// Measured on the bench graph (RMAT-26, profiles/r2_*): the first bottom-up level inspects 33 M column indices
+// for 27 M unvisited vertices -- almost every vertex finds its parent with its FIRST probe, because in-neighbour
+// lists are sorted and the low ids are the hubs.  Yet the sweep above pays, per vertex, a pair of row offsets
+// and a whole 32-byte sector of column indices fetched from HBM to use 4 bytes of it (1.37 GB of DRAM traffic
+// for 132 MB of useful indices), one dependent chain per lane.  So the graph carries one more per-vertex array,
+// built once like the transpose:
+//     first_nb[v] = v's first in-neighbour, bit 31 set when it is the ONLY one, -1 without in-edges
+// and a pull level becomes two kernels:
+//   K1 (bfs_pull_first_*): one probe per unvisited vertex straight from first_nb -- coalesced 4 B per vertex in
+//       the sweep form (first pull level of a run), kUnroll independent probes in flight per lane -- which
+//       settles ~80 % of the vertices without touching row offsets or column indices.  A miss goes to the
+//       `retry` list, or, when that neighbour was the only one, straight to the next level's unvisited list.
+//   K2 (bfs_pull_rest_kernel): the full search from the SECOND in-neighbour on, for the retry list only.
+// Depths are those of the sweep above: a vertex is labelled at the first level at which ANY in-neighbour is
+// in the frontier; which neighbour is probed first does not matter.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kOnlyNeighbor = static_cast<int>(0x80000000u);
+
+static __global__ void bfs_first_neighbor_kernel(csr_view_t in, int* __restrict__ first_nb) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < in.n_vertices; v += gridDim.x * blockDim.x) {
+    const int s = in.row_offsets[v], e = in.row_offsets[v + 1];
+    int x = -1;
+    if (e > s)
+      x = in.column_indices[s] | (e - s == 1 ? kOnlyNeighbor : 0);
+    first_nb[v] = x;
+  }
+}
+
+/// "is u in the current frontier" for the single-GPU enactor: one bit per vertex.
+struct bitmap_frontier_t {
+  const unsigned* bm;
+  __device__ __forceinline__ bool operator()(int u) const { return bitmap_test(bm, u); }
+};
+/// where K1's sweep form puts the words of the next frontier (the partitioned variants store them elsewhere)
+struct bitmap_word_sink_t {
+  unsigned* next;
+  __device__ __forceinline__ void zero(int wi) const { next[wi] = 0; }  // lanes hold different words
+  __device__ __forceinline__ void word(int wi, unsigned v) const {      // warp-uniform word
+    if (lane_id() == 0)
+      next[wi] = v;
+  }
+};
+
+/**
+ * @brief K1, sweep form (first pull level of a run of pull levels): one warp owns 32 consecutive words of the
+ * visited map per pass and settles kUnroll of them at a time -- kUnroll coalesced loads of first_nb, then kUnroll
+ * frontier probes in flight per lane -- writing the next-frontier / visited words with plain stores.
+ */
+template <int kThreads, int kUnroll, typename FrontierTest, typename Sink>
+__global__ void __launch_bounds__(kThreads)
+bfs_pull_first_sweep_kernel(int n_vertices, const int* __restrict__ first_nb, unsigned* __restrict__ visited,
+                            FrontierTest in_frontier, Sink sink, int* dist, int next_level, ctrl_t* ctrl,
+                            int* next_count, int* retry, int* retry_count, int* unv, int* unv_count) {
+  __shared__ int s_emit[kThreads / 32][2][kEmitCap];
+  warp_emitter_t<kEmitCap, false> em_retry, em_unv;
+  em_retry.init(s_emit[threadIdx.x >> 5][0], retry, retry_count, n_vertices, nullptr, ctrl);
+  em_unv.init(s_emit[threadIdx.x >> 5][1], unv, unv_count, n_vertices, nullptr, ctrl);
+  const int lane = lane_id();
+  const int words = (n_vertices + 31) / 32;
+  const int warps = (gridDim.x * kThreads) >> 5;
+  const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+  unsigned long long probes = 0;
+  int found_cnt = 0;
+  for (int w0 = gw * 32; w0 < words; w0 += warps * 32) {
+    const int my_wi = w0 + lane;
+    const unsigned my_vis = my_wi < words ? visited[my_wi] : 0xffffffffu;
+    if (my_wi < words && my_vis == 0xffffffffu)
+      sink.zero(my_wi);
+    unsigned todo = __ballot_sync(kFull, my_vis != 0xffffffffu);
+    while (todo) {
+      int wi[kUnroll], nb[kUnroll];
+      unsigned vis[kUnroll];
+      bool act[kUnroll], hit[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        wi[k] = -1;
+        vis[k] = 0xffffffffu;
+        if (todo) {
+          const int src_lane = __ffs(todo) - 1;
+          todo &= todo - 1;
+          wi[k] = w0 + src_lane;
+          vis[k] = __shfl_sync(kFull, my_vis, src_lane);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        const int v = (wi[k] << 5) + lane;
+        act[k] = wi[k] >= 0 && v < n_vertices && !((vis[k] >> lane) & 1u);
+        nb[k] = act[k] ? ld_stream(first_nb + v) : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        hit[k] = false;
+        if (act[k] && nb[k] != -1) {
+          ++probes;
+          hit[k] = in_frontier(nb[k] & ~kOnlyNeighbor);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        if (wi[k] < 0)
+          continue;  // warp-uniform
+        const int v = (wi[k] << 5) + lane;
+        const unsigned fm = __ballot_sync(kFull, hit[k]);
+        if (hit[k])
+          dist[v] = next_level;
+        sink.word(wi[k], fm);
+        if (lane == 0 && fm)
+          visited[wi[k]] = vis[k] | fm;
+        found_cnt += hit[k] ? 1 : 0;
+        const bool miss = act[k] && !hit[k] && nb[k] != -1;
+        em_retry.push(miss && !(nb[k] & kOnlyNeighbor), v);
+        em_unv.push(miss && (nb[k] & kOnlyNeighbor), v);
+      }
+    }
+  }
+  em_retry.flush();
+  em_unv.flush();
+  probes = warp_sum(probes);
+  found_cnt = warp_sum(found_cnt);
+  if (lane == 0) {
+    if (probes)
+      atomicAdd(&ctrl->edges, probes);
+    if (found_cnt)
+      atomicAdd(next_count, found_cnt);
+  }
+}
+
+/// Set v's bit in `map` (found vertices of the list kernels; RED.OR, no return value).
+__device__ __forceinline__ void bitmap_set(unsigned* map, bool on, int v) {
+  if (on)
+    atomicOr(map + (v >> 5), 1u << (v & 31));
+}
+
+/**
+ * @brief K1, list form (later pull levels): the same single probe for the vertices of the unvisited list,
+ * kUnroll vertices per lane.  Found vertices set their bits with atomicOr (no return value: RED).
+ */
+template <int kThreads, int kUnroll, typename FrontierTest>
+__global__ void __launch_bounds__(kThreads)
+bfs_pull_first_list_kernel(int n_vertices, const int* __restrict__ first_nb, const int* __restrict__ list,
+                           const int* __restrict__ list_count, unsigned* visited, FrontierTest in_frontier,
+                           unsigned* next, int* dist, int next_level, ctrl_t* ctrl, int* next_count, int* retry,
+                           int* retry_count, int* unv, int* unv_count) {
+  __shared__ int s_emit[kThreads / 32][2][kEmitCap];
+  warp_emitter_t<kEmitCap, false> em_retry, em_unv;
+  em_retry.init(s_emit[threadIdx.x >> 5][0], retry, retry_count, n_vertices, nullptr, ctrl);
+  em_unv.init(s_emit[threadIdx.x >> 5][1], unv, unv_count, n_vertices, nullptr, ctrl);
+  const int lane = lane_id();
+  const int n = *list_count;
+  unsigned long long probes = 0;
+  int found_cnt = 0;
+  for (;;) {
+    int base = 0;
+    if (lane == 0)
+      base = atomicAdd(&ctrl->work, 32 * kUnroll);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= n)
+      break;
+    int v[kUnroll], nb[kUnroll];
+    bool hit[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const int i = base + 32 * k + lane;
+      v[k] = i < n ? list[i] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k)
+      nb[k] = v[k] >= 0 ? first_nb[v[k]] : -1;
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      hit[k] = false;
+      if (nb[k] != -1) {
+        ++probes;
+        hit[k] = in_frontier(nb[k] & ~kOnlyNeighbor);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      if (hit[k]) {
+        dist[v[k]] = next_level;
+        ++found_cnt;
+      }
+      bitmap_set(next, hit[k], v[k]);
+      bitmap_set(visited, hit[k], v[k]);
+      const bool miss = nb[k] != -1 && !hit[k];
+      em_retry.push(miss && !(nb[k] & kOnlyNeighbor), v[k]);
+      em_unv.push(miss && (nb[k] & kOnlyNeighbor), v[k]);
+    }
+  }
+  em_retry.flush();
+  em_unv.flush();
+  probes = warp_sum(probes);
+  found_cnt = warp_sum(found_cnt);
+  if (lane == 0) {
+    if (probes)
+      atomicAdd(&ctrl->edges, probes);
+    if (found_cnt)
+      atomicAdd(next_count, found_cnt);
+  }
+}
+
+/**
+ * @brief K2: full search from the SECOND in-neighbour on, over the retry list (the vertices whose first
+ * in-neighbour is not in the frontier and that have more).  Two vertices per lane, their serial probes
+ * interleaved (two independent chains); rows still open after kSerial probes are finished by the whole warp.
+ * Not found -> the next level's unvisited list.
+ */
+template <int kThreads, int kSerial, typename FrontierTest>
+__global__ void __launch_bounds__(kThreads)
+bfs_pull_rest_kernel(csr_view_t in, const int* __restrict__ list, const int* __restrict__ list_count,
+                     unsigned* visited, FrontierTest in_frontier, unsigned* next, int* dist, int next_level,
+                     ctrl_t* ctrl, int* next_count, int* unv, int* unv_count) {
+  __shared__ int s_emit[kThreads / 32][kEmitCap];
+  warp_emitter_t<kEmitCap, false> em;
+  em.init(s_emit[threadIdx.x >> 5], unv, unv_count, in.n_vertices, nullptr, ctrl);
+  const int lane = lane_id();
+  const int n = *list_count;
+  const int* __restrict__ ro = in.row_offsets;
+  const int* __restrict__ ci = in.column_indices;
+  unsigned long long scanned = 0;
+  int found_cnt = 0;
+  for (;;) {
+    int base = 0;
+    if (lane == 0)
+      base = atomicAdd(&ctrl->work, 64);
+    base = __shfl_sync(kFull, base, 0);
+    if (base >= n)
+      break;
+    int v[2], e[2], end[2];
+    bool searching[2], found[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = base + 32 * k + lane;
+      v[k] = i < n ? list[i] : -1;
+      found[k] = false;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      e[k] = end[k] = 0;
+      if (v[k] >= 0) {
+        e[k] = ro[v[k]] + 1;  // the first in-neighbour was K1's probe
+        end[k] = ro[v[k] + 1];
+      }
+      searching[k] = e[k] < end[k];
+    }
+    for (int s = 0; s < kSerial; ++s) {
+      int u[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        u[k] = (searching[k] && e[k] < end[k]) ? ci[e[k]] : -1;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (u[k] >= 0) {
+          ++e[k];
+          ++scanned;
+          if (in_frontier(u[k])) {
+            found[k] = true;
+            searching[k] = false;
+          }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (e[k] >= end[k])
+        searching[k] = false;
+      unsigned rest = __ballot_sync(kFull, searching[k]);
+      while (rest) {
+        const int leader = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int s0 = __shfl_sync(kFull, e[k], leader);
+        const int t = __shfl_sync(kFull, end[k], leader);
+        bool any = false;
+        for (int off = s0; off < t && !any; off += 32) {
+          const int idx = off + lane;
+          bool mine = false;
+          if (idx < t) {
+            ++scanned;
+            mine = in_frontier(ci[idx]);
+          }
+          any = __any_sync(kFull, mine);
+        }
+        if (lane == leader)
+          found[k] = any;
+      }
+      if (found[k]) {
+        dist[v[k]] = next_level;
+        ++found_cnt;
+      }
+      bitmap_set(next, found[k], v[k]);
+      bitmap_set(visited, found[k], v[k]);
+      em.push(v[k] >= 0 && !found[k], v[k]);
+    }
+  }
+  em.flush();
+  scanned = warp_sum(scanned);
+  found_cnt = warp_sum(found_cnt);
+  if (lane == 0) {
+    if (scanned)
+      atomicAdd(&ctrl->edges, scanned);
+    if (found_cnt)
+      atomicAdd(next_count, found_cnt);
+  }
+}
+
 struct bfs_level_stat_t {
   int direction;  // 0 = top-down (push), 1 = bottom-up (pull)
   int frontier;   // vertices in the input frontier
@@ -437,7 +745,10 @@ struct bfs_config_t {
 struct bfs_scratch_t {
   dbuf_t<unsigned> visited, fbm, nbm, unreachable;
   dbuf_t<int> unv[2];                    // still-unvisited vertices (consecutive bottom-up levels)
+  dbuf_t<int> retry;                     // pull levels: vertices whose first in-neighbour missed (K2's input)
+  dbuf_t<int> first_nb;                  // per vertex: first in-neighbour (bfs_first_neighbor_kernel)
   graph_key_t unreachable_for;           // the (in-edge) graph the unreachable map was built from
+  graph_key_t first_nb_for;              // ... and the one first_nb was built from
   dbuf_t<int> q[2];
   dbuf_t<int> counts;  // [0],[1] queue sizes
   struct host_fb_t {
@@ -515,6 +826,8 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   const bool can_pull =
       in_g.row_offsets != nullptr && cfg.direction != 0 && !cfg.use_atomic_min_op;
   const unsigned* premark = nullptr;
+  // B2G_BFS_PULL_LEGACY=1: the first-generation pull kernels (one sweep / list kernel per level), kept for A/B runs
+  static const bool legacy_pull = std::getenv("B2G_BFS_PULL_LEGACY") != nullptr;
   if (can_pull) {  // per-graph map of vertices without in-edges (built once, like the transpose)
     if (!sc.unreachable_for.matches(in_g)) {  // keyed on graph identity + addresses + sizes, not an address
       sc.unreachable.ensure(static_cast<size_t>(words) + 4);
@@ -523,6 +836,12 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       ws.launches += 1;
     }
     premark = sc.unreachable.ptr;
+    if (!legacy_pull && !sc.first_nb_for.matches(in_g)) {  // per-graph shortcut array of the pull levels
+      sc.first_nb.ensure(static_cast<size_t>(V) + 64);
+      bfs_first_neighbor_kernel<<<sms * 8, 256, 0, st>>>(in_g, sc.first_nb.ptr);
+      sc.first_nb_for.set(in_g);
+      ws.launches += 1;
+    }
   }
   bfs_reset_kernel<<<sms * 8, 256, 0, st>>>(dist, sc.visited.ptr, sc.fbm.ptr, V, source,
                                              sc.q[0].ptr, sc.counts.ptr, premark);
@@ -534,6 +853,8 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   // frontier out-degree sum.  Not known for the source (probing it would cost a host round trip);
   // level 0 always runs top-down on the small path and reports it.
   unsigned long long m_f = 0;
+  bool m_known = false;  // the pull kernels do not report the new frontier's out-degree sum (it would cost a pair
+                         // of row offsets per found vertex); the first push level after them runs like level 0
   unsigned long long explored = 0;
   unsigned* fbm = sc.fbm.ptr;
   unsigned* nbm = sc.nbm.ptr;
@@ -548,7 +869,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   while (n_f > 0) {
     const double t_begin = trace ? now_us() : 0.0;
     // ---- tiny queue frontier: run the tail of the traversal in one single-CTA launch ------------
-    if (level > 0 && !bottom_up && !cfg.use_atomic_min_op &&
+    if (level > 0 && !bottom_up && m_known && !cfg.use_atomic_min_op &&
         static_cast<long long>(m_f) < cfg.advance.small_frontier_edges) {
       if (level < 64)
         B2G_CHECK(cudaEventRecord(sc.ev[2 * level], st));
@@ -575,6 +896,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       cur = t.cur;
       n_f = t.count;
       m_f = t.deg_sum;
+      m_known = true;
       unv_valid = false;
       continue;
     }
@@ -585,7 +907,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       if (cfg.direction == 1)
         want_bottom_up = level > 0;
       else if (!bottom_up)
-        want_bottom_up = static_cast<double>(m_f) > static_cast<double>(m_u) / cfg.alpha;
+        want_bottom_up = m_known && static_cast<double>(m_f) > static_cast<double>(m_u) / cfg.alpha;
       else
         want_bottom_up = !(static_cast<double>(n_f) < static_cast<double>(V) / cfg.beta);
     }
@@ -617,7 +939,34 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
         unv_cur = 0;
         unv_valid = true;
       }
-      if (!unv_valid) {  // first pull level of a run of pull levels: sweep every visited word
+      if (!legacy_pull) {
+        // K1 (one probe per unvisited vertex, from first_nb) + K2 (full search for K1's misses): see above
+        cb = ws.next_ctrl();
+        sc.retry.ensure(static_cast<size_t>(V) + 64);
+        B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 6, 0, sizeof(int), st));
+        const bitmap_frontier_t in_frontier{fbm};
+        if (!unv_valid) {
+          B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));
+          bfs_pull_first_sweep_kernel<256, 4><<<sms * 8, 256, 0, st>>>(
+              V, sc.first_nb.ptr, sc.visited.ptr, in_frontier, bitmap_word_sink_t{nbm}, dist, level + 1, ca,
+              sc.counts.ptr + 2, sc.retry.ptr, sc.counts.ptr + 6, sc.unv[0].ptr, sc.counts.ptr + 4);
+          unv_cur = 0;
+          unv_valid = true;
+        } else {
+          const int o = unv_cur ^ 1;
+          B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4 + o, 0, sizeof(int), st));
+          B2G_CHECK(cudaMemsetAsync(nbm, 0, sizeof(unsigned) * words, st));
+          bfs_pull_first_list_kernel<256, 4><<<sms * 8, 256, 0, st>>>(
+              V, sc.first_nb.ptr, sc.unv[unv_cur].ptr, sc.counts.ptr + 4 + unv_cur, sc.visited.ptr, in_frontier,
+              nbm, dist, level + 1, ca, sc.counts.ptr + 2, sc.retry.ptr, sc.counts.ptr + 6, sc.unv[o].ptr,
+              sc.counts.ptr + 4 + o);
+          unv_cur = o;
+        }
+        bfs_pull_rest_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
+            in_g, sc.retry.ptr, sc.counts.ptr + 6, sc.visited.ptr, in_frontier, nbm, dist, level + 1, cb,
+            sc.counts.ptr + 2, sc.unv[unv_cur].ptr, sc.counts.ptr + 4 + unv_cur);
+        ws.launches += 1;
+      } else if (!unv_valid) {  // first pull level of a run of pull levels: sweep every visited word
         B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));
         bfs_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
             in_g, sc.visited.ptr, fbm, nbm, dist, level + 1, ca, sc.counts.ptr + 2,
@@ -652,9 +1001,9 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
       int ub = static_cast<int>(n_f < V ? n_f : V);
       advance_launch_t lcfg = cfg.advance;
-      lcfg.avg_degree = (level > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
-      if (level == 0) {
-        lcfg.lb = lb_t::block_mapped;  // one row of unknown length: binned kernel + hub slabs
+      lcfg.avg_degree = (level > 0 && m_known && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
+      if (level == 0 || !m_known) {
+        lcfg.lb = lb_t::block_mapped;  // rows of unknown total length: binned kernel + hub slabs
       } else if (lcfg.lb == lb_t::merge_path &&
                  static_cast<long long>(m_f) < cfg.advance.mid_frontier_edges) {
         lcfg.lb = lb_t::block_mapped;  // mid-size frontier: skip the scan + partition launches
@@ -693,6 +1042,9 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       explored += sc.h_fb->edges;  // the source's degree, learnt from the level it just ran
     n_f = sc.h_fb->count;
     m_f = sc.h_fb->deg_sum;
+    m_known = !want_bottom_up || legacy_pull;  // pull levels (second generation) report no out-degree sum
+    if (!m_known)
+      m_f = sc.h_fb->edges;  // a stand-in for the `explored` estimate of the direction heuristic only
     ++level;
   }
   if (levels)

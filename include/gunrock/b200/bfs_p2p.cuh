@@ -29,6 +29,12 @@
  */
 #pragma once
 
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
 #include <gunrock/b200/bfs_partitioned.cuh>
 
 namespace gunrock {
@@ -433,6 +439,352 @@ static __global__ void p2p_push_segment_kernel(p2p_window_t w, int parity) {
     uint4* dst = reinterpret_cast<uint4*>(w.front(r, parity) + at);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
       dst[i] = src[i];
+  }
+}
+
+
+/// How one rank runs its share of a partitioned BFS (same meaning as bfs_config_t of the single-GPU enactor).
+struct part_bfs_config_t {
+  advance_launch_t advance;
+  int direction = 2;    // 0 push only, 1 pull after the first level, 2 optimised (Beamer on GLOBAL counts)
+  double alpha = 14.0;
+  double beta = 24.0;
+};
+
+/// What a rank reports about a run (global per-level statistics: every rank sees the same numbers).
+struct part_bfs_report_t {
+  int levels = 0;
+  unsigned long long edges_total = 0, verts_total = 0;
+  int level_direction[64] = {};
+  int level_frontier[64] = {};
+  unsigned long long level_edges[64] = {};
+};
+
+/// Peer-memory exchange state of one rank: its own window, the peers' mappings (CUDA IPC between processes,
+/// plain peer pointers between the devices of one process).
+struct p2p_state_t {
+  p2p_window_t w;
+  void* own = nullptr;
+  size_t own_bytes = 0;
+  void* opened[kMaxPeers] = {};  // cudaIpcOpenMemHandle mappings to close
+  bool attached = false;
+  unsigned epoch = 0;
+  int seq = 0;
+  p2p_feedback_t* h_fb = nullptr;
+  p2p_tail_report_t* h_tail = nullptr;
+  void release() {
+    if (h_tail)
+      cudaFreeHost(h_tail);
+    h_tail = nullptr;
+    for (auto& o : opened)
+      if (o) {
+        cudaIpcCloseMemHandle(o);
+        o = nullptr;
+      }
+    if (own)
+      cudaFree(own);
+    own = nullptr;
+    if (h_fb)
+      cudaFreeHost(h_fb);
+    h_fb = nullptr;
+    attached = false;
+  }
+};
+
+
+/**
+ * @brief Allocate (once) this rank's window and everything a traversal needs, so that the run itself never
+ * calls cudaMalloc / cudaFree (a device-wide synchronisation while a peer's barrier kernel is spinning).
+ */
+inline void part_p2p_prepare(workspace_t& ws, const csr_view_t& view, const partition_t& pt, part_bfs_state_t& S,
+                             dbuf_t<unsigned long long>& part_deg, p2p_state_t& P, bool may_pull) {
+  if (P.own)
+    return;
+  if (pt.nparts > kMaxPeers)
+    throw std::runtime_error("peer-memory exchange: at most 16 ranks");
+  P.w = p2p_window_t{};
+  P.w.nparts = pt.nparts;
+  P.w.me = pt.part;
+  P.w.words = (((pt.rows_of(0) + 31) / 32) + 3) & ~3;  // 16-byte aligned segments
+  // a global id is forwarded at most once per rank, so a row never holds more than the owner's rows
+  P.w.cap = pt.rows_of(0) + 64;
+  P.own_bytes = P.w.bytes();
+  B2G_CHECK(cudaMalloc(&P.own, P.own_bytes));
+  B2G_CHECK(cudaMemset(P.own, 0, P.own_bytes));
+  B2G_CHECK(cudaMallocHost(&P.h_fb, sizeof(p2p_feedback_t)));
+  memset(P.h_fb, 0, sizeof(p2p_feedback_t));
+  B2G_CHECK(cudaMallocHost(&P.h_tail, sizeof(p2p_tail_report_t)));
+  memset(P.h_tail, 0, sizeof(p2p_tail_report_t));
+  S.ensure(pt, 1);
+  part_deg.ensure(2);
+  reserve_advance_workspace(ws, view, pt.n_local);
+  if (may_pull)
+    S.unreachable.ensure(static_cast<size_t>(S.words_per_rank()) + 4);
+  B2G_CHECK(cudaDeviceSynchronize());
+}
+
+/// Map the peers' windows: plain device pointers (ranks of one process with peer access enabled) ...
+inline void part_p2p_attach_pointers(p2p_state_t& P, void* const* windows) {
+  for (int r = 0; r < P.w.nparts; ++r)
+    P.w.base[r] = r == P.w.me ? static_cast<char*>(P.own) : static_cast<char*>(windows[r]);
+  P.attached = true;
+}
+
+/**
+ * @brief One rank's level loop of the direction-optimised BFS over a 1-D (cyclic) partitioned graph, the
+ * frontier exchange done by the kernels over peer memory (file header).  COLLECTIVE: every rank calls it
+ * with the same source / total_edges / cfg; the host reads one pinned feedback record per level.  Used by
+ * the C ABI (`b2g_part_bfs_p2p`, one process per GPU) and by the header API (`bfs::run` with a multi-device
+ * `gcuda::multi_context_t`, one host thread per device).  `in_view` = this rank's in-edge lists (the CSR
+ * itself for a symmetric graph; row_offsets == nullptr disables pull).  Everything is enqueued on ws.stream.
+ */
+inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_view_t& in_view,
+                             const partition_t& pt, part_bfs_state_t& S, dbuf_t<unsigned long long>& part_deg,
+                             p2p_state_t& P, int source, long long total_edges, const part_bfs_config_t& cfg,
+                             part_bfs_report_t* out) {
+  {
+    cudaStream_t st = ws.stream;
+    const p2p_window_t w = P.w;
+    const int np = w.nparts;
+    const int sms = device_info_t::get().sm_count;
+    const bool can_pull = in_view.row_offsets != nullptr && cfg.direction != 0;
+    const double alpha = cfg.alpha;
+    const double beta = cfg.beta;
+    static const bool fused_sink = std::getenv("B2G_P2P_FUSED_SINK") != nullptr;
+    static const bool trace = std::getenv("B2G_TRACE") != nullptr;
+    static const char* timeout_env = std::getenv("B2G_P2P_TIMEOUT_MS");
+    const unsigned long long timeout_ns =
+        (timeout_env ? std::strtoull(timeout_env, nullptr, 10) : 20000ull) * 1000ull * 1000ull;
+
+    // ---- reset (the part of b2g_part_bfs_begin that matters here; no send buffer) ----------------
+    S.ensure(pt, 1);
+    part_deg.ensure(2);
+    const int sent_words = (pt.n_global + 31) / 32;
+    const unsigned* premark = nullptr;
+    if (can_pull) {
+      if (!S.unreachable_for.matches(in_view)) {
+        S.unreachable.ensure(static_cast<size_t>(S.words_per_rank()) + 4);
+        bfs_unreachable_map_kernel<<<sms * 8, 256, 0, st>>>(in_view.row_offsets, pt.n_local,
+                                                            S.unreachable.ptr);
+        S.unreachable_for.set(in_view);
+      }
+      premark = S.unreachable.ptr;
+    }
+    part_reset_kernel<<<sms * 8, 256, 0, st>>>(pt, source, S.dist.ptr, S.visited.ptr, S.sent.ptr,
+                                                sent_words, S.q[0].ptr, S.counts.ptr, premark);
+    part_seed_kernel<<<1, 1, 0, st>>>(pt, source, S.dist.ptr, S.visited.ptr);
+    B2G_CHECK(cudaMemsetAsync(S.overflow.ptr, 0, sizeof(int), st));
+    B2G_CHECK(cudaMemsetAsync(part_deg.ptr, 0, 16, st));
+    ws.launches += 2;
+    P.h_fb->timed_out = 0;
+
+    static const bool use_tail = std::getenv("B2G_P2P_NO_TAIL") == nullptr;
+    const long long tail_budget = 1 << 16;  // global frontier out-degree below which the tail kernel runs
+    const int push_ctas = std::max(8, std::min(sms * 4 / np, (w.words / 4 + 255) / 256));
+    // B2G_TRACE: CUDA-event stamps between the phases of every level (device time of this rank)
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    auto mark = [&](const std::string& name) {
+      if (!trace)
+        return;
+      cudaEvent_t e;
+      B2G_CHECK(cudaEventCreate(&e));
+      B2G_CHECK(cudaEventRecord(e, st));
+      marks.emplace_back(name, e);
+    };
+    mark("begin");
+    int cur = 0, level = 0, parity = 0;  // parity: which `front` buffer holds the current frontier
+    bool is_bitmap = false, bottom_up = false;
+    long long n_f = 1, m_f = 0, explored = 0;
+    unsigned long long edges_total = 0, verts_total = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto sync = [&](bool with_stats, const int* send_count, const int* count_ptr, const ctrl_t* c) {
+      ++P.epoch;
+      if (with_stats)
+        p2p_sync_kernel<true><<<1, 32, 0, st>>>(w, P.epoch, send_count, count_ptr, c, part_deg.ptr,
+                                                 S.overflow.ptr, P.h_fb, ++P.seq, timeout_ns);
+      else
+        p2p_sync_kernel<false><<<1, 32, 0, st>>>(w, P.epoch, send_count, nullptr, nullptr, nullptr,
+                                                  nullptr, P.h_fb, 0, timeout_ns);
+      ws.launches += 1;
+    };
+    while (n_f > 0) {
+      mark("L" + std::to_string(level) + ":");
+      bool go_up = false;
+      if (can_pull && level > 0) {
+        if (cfg.direction == 1)
+          go_up = true;
+        else if (!bottom_up)
+          go_up = static_cast<double>(m_f) > static_cast<double>(total_edges - explored) / alpha;
+        else
+          go_up = !(static_cast<double>(n_f) < static_cast<double>(pt.n_global) / beta);
+      }
+      unsigned* my_front = w.front(w.me, parity) + static_cast<size_t>(w.me) * w.words;
+      // ---- tiny global frontier: the distributed tail kernel runs level after level on its own ------
+      if (!go_up && level > 0 && use_tail && m_f < tail_budget) {
+        if (is_bitmap) {
+          B2G_CHECK(cudaMemsetAsync(S.counts.ptr + cur, 0, sizeof(int), st));
+          bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(my_front, S.local_words(), S.q[cur].ptr,
+                                                          S.counts.ptr + cur);
+          ws.launches += 1;
+          is_bitmap = false;
+        }
+        P.h_tail->timed_out = 0;
+        p2p_tail_kernel<1024><<<1, 1024, 0, st>>>(
+            view, pt, w, P.epoch + 1, S.q[0].ptr, S.q[1].ptr, S.counts.ptr, cur, level, n_f, 16,
+            tail_budget, S.visited.ptr, S.sent.ptr, S.dist.ptr, S.overflow.ptr, P.h_tail, ++P.seq, timeout_ns);
+        ws.launches += 1;
+        mark("tail");
+        wait_for_sequence(&P.h_tail->seq, P.seq, st);
+        const p2p_tail_report_t& t = *P.h_tail;
+        P.epoch += 2u * static_cast<unsigned>(t.levels);
+        if (t.timed_out)
+          throw std::runtime_error("b2g_part_bfs_p2p: a peer did not reach a barrier of the tail kernel (time-out)");
+        for (int k = 0; k < t.levels; ++k) {
+          if (out && level + k < 64) {
+            out->level_direction[level + k] = 0;
+            out->level_frontier[level + k] = static_cast<int>(t.frontier[k]);
+            out->level_edges[level + k] = static_cast<unsigned long long>(t.edges[k]);
+          }
+          edges_total += static_cast<unsigned long long>(t.edges[k]);
+          verts_total += static_cast<unsigned long long>(t.frontier[k]);
+          explored += t.edges[k];
+        }
+        if (trace)
+          std::fprintf(stderr, "[b2g-p2p] rank %d epoch %u levels %d..%d in the tail kernel, n_f=%lld m_f=%lld\n",
+                       w.me, P.epoch, level, level + t.levels - 1, t.count, t.deg_sum);
+        level += t.levels;
+        cur = t.cur;
+        n_f = t.count;
+        m_f = t.deg_sum;
+        bottom_up = false;
+        continue;
+      }
+      if (level > 0)
+        explored += m_f;
+      ctrl_t* c = nullptr;
+      const int* count_ptr = nullptr;
+      if (go_up) {
+        if (!is_bitmap) {  // queue -> bitmap in my segment, pushed to every peer, barrier
+          B2G_CHECK(cudaMemsetAsync(my_front, 0, sizeof(unsigned) * w.words, st));
+          part_queue_to_bitmap_kernel<<<sms * 4, 256, 0, st>>>(S.q[cur].ptr, S.counts.ptr + cur, my_front);
+          if (np > 1) {
+            p2p_push_segment_kernel<<<dim3(push_ctas, np), 256, 0, st>>>(w, parity);
+            sync(false, nullptr, nullptr, nullptr);
+          }
+          ws.launches += 2;
+          is_bitmap = true;
+        }
+        c = ws.next_ctrl();
+        B2G_CHECK(cudaMemsetAsync(S.counts.ptr + 2, 0, sizeof(int), st));
+        const unsigned* all = w.front(w.me, parity);
+        if (fused_sink || np == 1) {
+          part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
+              pt, in_view, w.words, S.visited.ptr, all, peer_word_sink_t{w, parity ^ 1}, S.dist.ptr,
+              level + 1, c, S.counts.ptr + 2);
+        } else {
+          unsigned* nxt_seg = w.front(w.me, parity ^ 1) + static_cast<size_t>(w.me) * w.words;
+          part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
+              pt, in_view, w.words, S.visited.ptr, all, local_word_sink_t{nxt_seg}, S.dist.ptr,
+              level + 1, c, S.counts.ptr + 2);
+          mark("sweep");
+          p2p_push_segment_kernel<<<dim3(push_ctas, np), 256, 0, st>>>(w, parity ^ 1);
+          ws.launches += 1;
+        }
+        mark("push");
+        ws.launches += 1;
+        parity ^= 1;
+        count_ptr = S.counts.ptr + 2;
+      } else {
+        if (is_bitmap) {  // bitmap -> queue (my segment of the current frontier map)
+          B2G_CHECK(cudaMemsetAsync(S.counts.ptr + cur, 0, sizeof(int), st));
+          bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(my_front, S.local_words(), S.q[cur].ptr,
+                                                          S.counts.ptr + cur);
+          ws.launches += 1;
+          is_bitmap = false;
+        }
+        const int nxt = cur ^ 1;
+        B2G_CHECK(cudaMemsetAsync(S.counts.ptr + nxt, 0, sizeof(int), st));
+        B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
+        p2p_claim_op op{pt, w, S.visited.ptr, S.sent.ptr, S.dist.ptr, level + 1, S.send_count.ptr,
+                        S.overflow.ptr};
+        // same path selection as the single-GPU enactor (bfs.cuh), on this rank's share of the frontier
+        advance_launch_t lcfg = cfg.advance;
+        const long long m_rank = m_f / np;
+        lcfg.avg_degree = (level > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
+        if (level == 0) {
+          lcfg.lb = lb_t::block_mapped;  // one row of unknown length
+        } else if (m_rank < lcfg.small_frontier_edges) {
+          lcfg.lb = lb_t::block_mapped;  // one kernel: warp / thread bins only
+          lcfg.hub_threshold = 1 << 30;
+        } else if (lcfg.lb == lb_t::merge_path && m_rank < lcfg.mid_frontier_edges) {
+          lcfg.lb = lb_t::block_mapped;  // skip the scan + partition launches
+        }
+        launch_advance<advance_output_t::vertices, true, false>(
+            ws, view, S.q[cur].ptr, S.counts.ptr + cur, pt.n_local, S.q[nxt].ptr,
+            S.counts.ptr + nxt, pt.n_local, op, lcfg, &c);
+        mark("advance");
+        if (np > 1) {
+          sync(false, S.send_count.ptr, nullptr, nullptr);
+          mark("barrier");
+          part_claim_packed_kernel<<<dim3(std::max(16, sms * 2 / np), np), 256, 0, st>>>(
+              pt, w.inbox(w.me, 0), static_cast<int>(w.inbox_row_ints()) - 1, S.visited.ptr, S.dist.ptr,
+              level + 1, view.row_offsets, S.q[nxt].ptr, S.counts.ptr + nxt, part_deg.ptr,
+              S.overflow.ptr);
+          ws.launches += 1;
+          mark("claim");
+        }
+        cur = nxt;
+        count_ptr = S.counts.ptr + cur;
+      }
+      sync(true, nullptr, count_ptr, c);
+      mark("stats");
+      wait_for_sequence(&P.h_fb->seq, P.seq, st);
+      if (P.h_fb->timed_out)
+        throw std::runtime_error("b2g_part_bfs_p2p: rank " + std::to_string(w.me) + " level " +
+                                 std::to_string(level) + ": peer " + std::to_string(P.h_fb->late_peer) +
+                                 " did not reach barrier epoch " + std::to_string(P.h_fb->late_epoch) +
+                                 " (published " + std::to_string(P.h_fb->late_seen) + ", time-out)");
+      if (P.h_fb->overflow)
+        throw std::runtime_error("b2g_part_bfs_p2p: frontier / inbox overflow");
+      if (trace)
+        std::fprintf(stderr, "[b2g-p2p] rank %d epoch %u level %d %s n_f=%lld m_f=%lld edges=%lld t=%.1f us\n",
+                     w.me, P.epoch, level, go_up ? "up" : "down", n_f, m_f, P.h_fb->edges,
+                     std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+      if (out && level < 64) {
+        out->level_direction[level] = go_up ? 1 : 0;
+        out->level_frontier[level] = static_cast<int>(n_f);
+        out->level_edges[level] = static_cast<unsigned long long>(P.h_fb->edges);
+      }
+      edges_total += static_cast<unsigned long long>(P.h_fb->edges);
+      verts_total += static_cast<unsigned long long>(n_f);
+      if (level == 0)
+        explored += P.h_fb->edges;
+      n_f = P.h_fb->count;
+      m_f = P.h_fb->deg_sum;
+      bottom_up = go_up;
+      ++level;
+    }
+    B2G_CHECK(cudaStreamSynchronize(st));
+    if (trace) {
+      std::string line = "[b2g-p2p] rank " + std::to_string(w.me) + " phases (us):";
+      for (size_t i = 1; i < marks.size(); ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+        char buf[64];
+        std::snprintf(buf, sizeof buf, " %s=%.1f", marks[i].first.c_str(), ms * 1e3f);
+        line += buf;
+      }
+      std::fprintf(stderr, "%s\n", line.c_str());
+      for (auto& m : marks)
+        cudaEventDestroy(m.second);
+    }
+    S.cur = cur;
+    S.frontier_is_bitmap = false;
+    if (out) {
+      out->levels = level;
+      out->edges_total = edges_total;
+      out->verts_total = verts_total;
+    }
   }
 }
 

@@ -22,12 +22,20 @@ def test_reference_arm_line(built):
     assert len(lines) == 1
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["unit"] == "MTEPS" and j["higher_is_better"] is True
-    assert j["metric"] == "MTEPS (bfs_push_rmat22)" and j["steps"] == 2 and j["warmup"] == 1 and j["n_gpus"] == 1
+    # default = the configuration BASELINE.json's metric is quoted on (direction-optimised BFS, RMAT-26)
+    assert j["metric"] == "MTEPS (bfs_do_rmat26)" and j["steps"] == 2 and j["warmup"] == 1 and j["n_gpus"] == 1
     assert j["value"] > 0 and j["ms_per_step"] > 0
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
     assert j["cpu_baseline"]["value"] == j["value"] == j["e2e"]["value"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
-    assert j["config"]["workload"].startswith("BFS push")
+    assert j["config"]["workload"].startswith("BFS direction-optimised, RMAT-26")
+    assert j["config"]["numerator"].startswith("sum of out-degrees") and j["scaling"] == "weak"
+    # N > 1 names the partitioned traversal of the same graph (strong scaling); the CPU arm times the same BFS
+    j8 = json.loads(run_bench("--gpus", "8")[0])
+    assert j8["metric"] == "MTEPS (bfs_part_rmat26)" and j8["scaling"] == "strong" and j8["n_gpus"] == 8
+    assert j8["config"]["edges_touched_per_step"] == j["config"]["edges_touched_per_step"]
+    j = json.loads(run_bench("--workload", "bfs_push_rmat22")[0])
+    assert j["metric"] == "MTEPS (bfs_push_rmat22)" and j["config"]["workload"].startswith("BFS push")
     # other algorithms of the path
     j = json.loads(run_bench("--workload", "sssp_rmat24")[0])
     assert j["metric"] == "MTEPS (sssp_rmat24)" and j["dtype"] == "f32" and j["value"] > 0

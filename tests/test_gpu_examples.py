@@ -139,6 +139,21 @@ def test_per_graph_caches_across_graphs_and_contexts():
     assert "ALL OK" in out, out
 
 
+@pytest.mark.parametrize("ranks", [2, 3, 4])
+def test_bfs_run_over_a_multi_device_context(ranks):
+    """`gunrock::bfs::run(G, param, result, context)` with a gcuda::multi_context_t of several contexts runs the
+    1-D partitioned traversal (frontier exchange by the kernels over peer memory) and returns the depths of the
+    host BFS and of the single-device run, bit for bit.  With fewer GPUs than ranks the ranks share devices
+    (eager module loading then: see examples/multi_context_selftest.cu)."""
+    import torch
+    n = torch.cuda.device_count()
+    devices = [str(r % max(n, 1)) for r in range(ranks)]
+    env = dict(os.environ, CUDA_MODULE_LOADING="EAGER", B2G_P2P_TIMEOUT_MS="20000")
+    r = subprocess.run([need("multi_context_selftest"), "15"] + devices, capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("alg", ["color", "kcore", "ppr", "spmv"])
 def test_other_reference_algorithms_validate_on_our_operators(alg, chesapeake_mtx, rmat_mtx, tmp_path):
     """Widening: the reference's own color / kcore / ppr / spmv algorithm headers and
