@@ -149,8 +149,8 @@ advance_launch_t to_launch(const b2g_options_t& o) {
   }
   a.hub_threshold = o.hub_threshold > 0 ? o.hub_threshold : 4096;
   a.ctas_per_sm = o.ctas_per_sm > 0 ? o.ctas_per_sm : 8;
-  // experimental merge_path kernels (advance.cuh advance_launch_t::variant), off unless asked for;
-  // read on every call so that one process can compare them
+  // A/B switch for the merge_path kernel (advance.cuh advance_launch_t::variant: 0 CTA tiles, 1 / 4 warp-private
+  // spans; unset = the functor's own default); read on every call so that one process can compare them
   if (const char* v = std::getenv("B2G_ADVANCE_VARIANT"))
     a.variant = std::atoi(v);
   return a;
@@ -679,12 +679,7 @@ int b2g_sssp(b2g_graph_t* g, int source, const b2g_options_t* opt, float* distan
     std::vector<sssp_level_stat_t> levels;
     int launches0 = g->ws.launches;
     B2G_CHECK(cudaEventRecord(g->ev0, st));
-    // experimental near/far schedule (sssp.cuh), off unless B2G_SSSP_DELTA is set to a positive width
-    static const char* delta_env = std::getenv("B2G_SSSP_DELTA");
-    const float delta = delta_env ? static_cast<float>(std::atof(delta_env)) : 0.0f;
-    int iters = delta > 0.0f
-                    ? sssp_run_near_far(g->ws, g->sssp, g->view, source, d_dist, to_launch(o), delta, &levels)
-                    : sssp_run(g->ws, g->sssp, g->view, source, d_dist, to_launch(o), &levels);
+    int iters = sssp_run(g->ws, g->sssp, g->view, source, d_dist, to_launch(o), &levels);
     B2G_CHECK(cudaEventRecord(g->ev1, st));
     if (dist_loc == B2G_HOST)
       B2G_CHECK(cudaMemcpyAsync(distances, d_dist, sizeof(float) * static_cast<size_t>(V),

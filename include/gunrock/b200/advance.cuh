@@ -90,62 +90,17 @@ struct op_needs_source<Op, std::void_t<decltype(Op::kNeedsSource)>>
     : std::integral_constant<bool, Op::kNeedsSource> {};
 constexpr int kBatch = 4;  // 32-edge chunks whose loads are issued back to back per warp
 
-/// Optional `static constexpr bool kVariants = true`: also instantiate the EXPERIMENTAL merge_path
-/// variants (advance_launch_t::variant) for this functor.  Off for user lambdas and for the functors of
-/// the partitioned paths: every variant multiplies the instantiations of the hottest kernel.
+/// Optional `static constexpr int kMergePathKernel = 1 | 4`: which merge_path kernel serves this functor when the
+/// caller does not say (advance_launch_t::variant < 0): 0 = the CTA-tile kernel (advance_merge_path_kernel),
+/// 1 / 4 = warp-private spans (advance_warp_path_kernel) with 4 / 8 chunks in flight.  Functors that do not
+/// declare it (user lambdas, the partitioned paths' functors) get the CTA-tile kernel and do not instantiate the
+/// others.  Measured on the bench graphs (profiles/r2_bench_matrix.md): BFS push RMAT-22 0.776 -> 0.718 ms with 1,
+/// SSSP RMAT-24 7.49 -> 7.06 ms with 4.
 template <typename Op, typename = void>
-struct op_wants_variants : std::false_type {};
+struct op_merge_path_kernel : std::integral_constant<int, 0> {};
 template <typename Op>
-struct op_wants_variants<Op, std::void_t<decltype(Op::kVariants)>>
-    : std::integral_constant<bool, Op::kVariants> {};
-/// Optional snapshot protocol (advance_warp_path_kernel with kSnapCluster > 0; the functor declares
-/// `static constexpr bool kHasSnapshot = true`): the functor's monotone test-and-set bitmap has an on-chip
-/// copy of its first `snap.bits` bits in (distributed) shared memory --
-///     const unsigned* snapshot_source() const;                 // the global map the copy is taken from
-///     template <class Snap> token_t prefetch_snap(int dst, const Snap& snap) const;
-///     template <class Snap> bool    commit_snap(int src, int dst, int edge, float w, token_t, const Snap& snap) const;
-template <typename Op, typename = void>
-struct op_has_snapshot : std::false_type {};
-template <typename Op>
-struct op_has_snapshot<Op, std::void_t<decltype(Op::kHasSnapshot)>>
-    : std::integral_constant<bool, Op::kHasSnapshot> {};
-
-/**
- * On-chip copy of the first `bits` bits of a monotone (0 -> 1 only) bitmap, handed to the functor.
- * kCluster == 1: the whole copy lives in this CTA's shared memory.  kCluster > 1: the copy is spread over
- * the CTAs of a thread-block cluster in 128-byte lines (line L of the map lives in CTA L % kCluster, so the
- * hot low-id lines of a power-law graph are served by all the SMs of the cluster); a word of another CTA
- * is read / updated through distributed shared memory (mapa + ld / red .shared::cluster).
- */
-template <int kCluster>
-struct snapshot_t {
-  uint32_t base;  // shared-window address of this CTA's slice
-  unsigned rank;  // this CTA's rank in the cluster
-  int bits;       // vertices covered (all CTAs together)
-  __device__ __forceinline__ bool covers(int v) const { return v < bits; }
-  __device__ __forceinline__ void locate(int v, unsigned& owner, uint32_t& addr) const {
-    const unsigned wi = static_cast<unsigned>(v) >> 5, line = wi >> 5;
-    owner = kCluster == 1 ? 0u : line % kCluster;
-    addr = base + ((((line / kCluster) << 5) | (wi & 31u)) << 2);
-  }
-  /// The copy's 32-bit word that holds vertex v.
-  __device__ __forceinline__ unsigned load(int v) const {
-    unsigned owner;
-    uint32_t addr;
-    locate(v, owner, addr);
-    return (kCluster == 1 || owner == rank) ? ld_shared_u32(addr) : ld_dsmem_u32(addr, owner);
-  }
-  /// OR `word` (global state just observed for v's word) into the copy.
-  __device__ __forceinline__ void merge(int v, unsigned word) const {
-    unsigned owner;
-    uint32_t addr;
-    locate(v, owner, addr);
-    if (kCluster == 1 || owner == rank)
-      red_shared_or(addr, word);
-    else
-      red_dsmem_or(addr, owner, word);
-  }
-};
+struct op_merge_path_kernel<Op, std::void_t<decltype(Op::kMergePathKernel)>>
+    : std::integral_constant<int, Op::kMergePathKernel> {};
 
 /// Per-warp staging buffer: ballot-compacted appends, flushed with one global atomic.
 template <int kCap, bool kDegSum>
@@ -209,6 +164,14 @@ struct warp_emitter_t {
   }
 };
 
+/// One slab of a deferred hub row: kChunk (or fewer) consecutive edges of one row.
+struct __align__(16) hub_slab_t {
+  int e0;   // CSR position of the slab's first edge
+  int cnt;  // edges in the slab (<= kChunk); <= 0 marks "no more work" in the kernels' shared-memory ring
+  int src;  // the row's vertex
+  int pad;
+};
+
 struct advance_params_t {
   csr_view_t g;
   const int* in = nullptr;        // input frontier (null when input is the whole graph)
@@ -222,6 +185,8 @@ struct advance_params_t {
   int hub_threshold = 1 << 30;
   int tma_ok = 0;                  // column_indices / values are 16-byte aligned
   int entries_per_ticket = 256;    // block_mapped: frontier entries a CTA draws at a time (<= 256)
+  int hub_slab_capacity = 0;
+  hub_slab_t* hub_slabs = nullptr;  // block_mapped: slab table of the deferred rows (advance_hub_table_kernel)
   const int* tile_rows = nullptr;  // merge_path: first row of every tile
   const int* row_base = nullptr;   // merge_path: CSR offset of every frontier row (next to the scan)
 };
@@ -397,26 +362,64 @@ advance_binned_kernel(advance_params_t p, Op op) {
 }
 
 /**
- * @brief Grid bin: every deferred hub row is cut into kChunk-edge slabs; slabs are dealt
- * round-robin to a persistent grid; each slab is staged into shared memory by ONE thread issuing
- * a cp.async.bulk (TMA engine, double buffered on two mbarriers) and then walked by the CTA.
- * When the CSR arrays are not 16-byte aligned (p.tma_ok == 0) the slab is read with plain
- * coalesced loads instead.
+ * @brief Grid bin, step 1: cut every deferred hub row into kChunk-edge slabs.  One warp per hub row reserves
+ * a range of the slab table with ONE atomic and writes the row's descriptors; the running total stays in
+ * ctrl->pad[0].  (The first version dealt batches of 512 hub rows to fixed groups of CTAs: on a power-law
+ * frontier the first batches hold the rows with hundreds of slabs and the last ones rows with two, so most
+ * CTAs idled -- SSSP RMAT-24 block_mapped ran 11.1 ms against merge_path's 7.5.  A table of slabs can be dealt
+ * evenly whatever the degrees are.)
+ */
+template <int kChunk>
+__global__ void advance_hub_table_kernel(advance_params_t p) {
+  const int lane = lane_id();
+  const int n_hubs = min(p.ctrl->hub_count, p.hub_capacity);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int* __restrict__ ro = p.g.row_offsets;
+  for (int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < n_hubs; h += warps) {
+    const int v = p.hubs[h];
+    const int s = ro[v], e = ro[v + 1];
+    const int c = (e - s + kChunk - 1) / kChunk;
+    int base = 0;
+    if (lane == 0) {
+      base = atomicAdd(&p.ctrl->pad[0], c);
+      if (base + c > p.hub_slab_capacity) {  // a frontier with the same hub many times over: the host sized the
+        atomicAdd(&p.ctrl->pad[0], -c);     // table from the graph's edge count (edges_upper_bound says better)
+        p.ctrl->overflow = 1;
+        base = -1;
+      }
+    }
+    base = __shfl_sync(kFull, base, 0);
+    if (base < 0)
+      continue;
+    for (int j = lane; j < c; j += 32) {
+      hub_slab_t d;
+      d.e0 = s + j * kChunk;
+      d.cnt = min(kChunk, e - d.e0);
+      d.src = v;
+      d.pad = 0;
+      p.hub_slabs[base + j] = d;
+    }
+  }
+}
+
+/**
+ * @brief Grid bin, step 2: a persistent grid walks the slab table.  A CTA draws kRange consecutive slabs per
+ * atomic (warp 0 fetches the NEXT range's descriptors into a two-deep ring in shared memory while the CTA
+ * walks the current one), and every slab is staged HBM -> shared memory by ONE thread issuing a cp.async.bulk
+ * (TMA engine, double buffered on two mbarriers: slab i+1 is in flight while slab i is walked) and then walked
+ * by the CTA, kHB edges per thread with all their loads in flight at once (two-phase functors).
+ * When the CSR arrays are not 16-byte aligned (p.tma_ok == 0) the slab is read with plain coalesced loads.
  */
 template <int kThreads, int kChunk, advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
 __global__ void __launch_bounds__(kThreads, kWeights ? 4 : 5)
 advance_hub_kernel(advance_params_t p, Op op) {
   constexpr int kWarps = kThreads / 32;
   constexpr int kHB = kChunk / kThreads;  // slab edges per thread: all of them in flight at once
-  constexpr int kHubs = 512;         // hub descriptors resident in shared memory at once
-  constexpr int kSlab = kChunk + 4;  // +4: slabs start at a 16-byte aligned column index
-  static_assert(kChunk % 4 == 0, "slab size must keep 16-byte granularity");
+  constexpr int kRange = 8;               // slabs per ticket
+  constexpr int kSlab = kChunk + 4;       // +4: slabs start at a 16-byte aligned column index
+  static_assert(kChunk % 4 == 0 && kRange <= 32, "slab size must keep 16-byte granularity");
   __shared__ int s_emit[kWarps][kEmitCap];
-  __shared__ int s_start[kHubs];
-  __shared__ int s_end[kHubs];
-  __shared__ int s_vertex[kHubs];
-  __shared__ int s_prefix[kHubs + 1];
-  __shared__ int s_scan[kWarps];
+  __shared__ hub_slab_t s_desc[2][kRange];
   __shared__ __align__(16) int s_idx[2][kSlab];
   __shared__ __align__(16) float s_val[kWeights ? 2 : 1][kWeights ? kSlab : 4];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -427,8 +430,8 @@ advance_hub_kernel(advance_params_t p, Op op) {
   const float* __restrict__ vals = p.g.values;
   const bool use_vals = kWeights && vals != nullptr;
   const bool tma = p.tma_ok != 0;
-  const int n_hubs = min(p.ctrl->hub_count, p.hub_capacity);
-  if (n_hubs == 0)
+  const int total = p.ctrl->pad[0];  // slabs in the table (advance_hub_table_kernel)
+  if (total == 0)
     return;
 
   warp_emitter_t<kEmitCap, kDegSum> em;
@@ -439,138 +442,99 @@ advance_hub_kernel(advance_params_t p, Op op) {
     mbar_init(&s_bar[1], 1);
     mbar_fence_init();
   }
-  __syncthreads();
-  unsigned phase_bits = 0;
-
-  // owner hub of slab g inside the resident batch: largest h with s_prefix[h] <= g
-  auto find_hub = [&](int g, int nb) {
-    int lo = 0, hi = nb;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (s_prefix[mid] <= g)
-        lo = mid;
-      else
-        hi = mid;
+  // warp 0: draw a range of slabs and put its descriptors (or end markers) into ring slot `slot`
+  auto fetch_range = [&](int slot) {
+    int base = 0;
+    if (lane == 0)
+      base = atomicAdd(&p.ctrl->tile, kRange);
+    base = __shfl_sync(kFull, base, 0);
+    if (lane < kRange) {
+      hub_slab_t d;
+      d.e0 = 0, d.cnt = -1, d.src = -1, d.pad = 0;
+      if (base + lane < total)
+        d = p.hub_slabs[base + lane];
+      s_desc[slot][lane] = d;
     }
-    return lo;
   };
-  auto issue = [&](int g, int nb, int buf) {
-    int h = find_hub(g, nb);
-    int e0 = s_start[h] + (g - s_prefix[h]) * kChunk;
-    int cnt = min(kChunk, s_end[h] - e0);
-    int a0 = e0 & ~3;
-    int a1 = (e0 + cnt + 3) & ~3;
-    uint32_t bytes = static_cast<uint32_t>(a1 - a0) * 4u;
+  auto issue = [&](const hub_slab_t& d, int buf) {  // one thread
+    const int a0 = d.e0 & ~3;
+    const int a1 = (d.e0 + d.cnt + 3) & ~3;
+    const uint32_t bytes = static_cast<uint32_t>(a1 - a0) * 4u;
     mbar_expect_tx(&s_bar[buf], use_vals ? 2 * bytes : bytes);
     bulk_g2s(&s_idx[buf][0], ci + a0, bytes, &s_bar[buf]);
     if (use_vals)
       bulk_g2s(&s_val[kWeights ? buf : 0][0], vals + a0, bytes, &s_bar[buf]);
   };
-
-  // Batches of kHubs rows are OWNED by groups of CTAs (a CTA stages only the descriptors of its own
-  // batches): with many deferred rows every CTA re-reading every descriptor would dominate.
-  const int nbatches = (n_hubs + kHubs - 1) / kHubs;
-  const bool many = nbatches >= static_cast<int>(gridDim.x);
-  const int first_batch = many ? blockIdx.x : static_cast<int>(blockIdx.x) % nbatches;
-  const int batch_step = many ? gridDim.x : (1 << 30);
-  const int member = many ? 0 : static_cast<int>(blockIdx.x) / nbatches;            // my index in the group
-  const int members = many ? 1 : (static_cast<int>(gridDim.x) - first_batch + nbatches - 1) / nbatches;
-  for (int bi = first_batch; bi < nbatches; bi += batch_step) {
-    const int b0 = bi * kHubs;
-    const int nb = min(kHubs, n_hubs - b0);
-    // descriptors + exclusive slab-count prefix of this batch
-    int carry = 0;
-    for (int i0 = 0; i0 < nb; i0 += kThreads) {
-      int i = i0 + threadIdx.x;
-      int chunks = 0;
-      if (i < nb) {
-        int v = p.hubs[b0 + i];
-        int s = ro[v], e = ro[v + 1];
-        s_start[i] = s;
-        s_end[i] = e;
-        s_vertex[i] = v;
-        chunks = (e - s + kChunk - 1) / kChunk;
-      }
-      int incl = warp_inclusive_sum(chunks);
-      if (lane == 31)
-        s_scan[warp] = incl;
-      __syncthreads();
-      int woff = 0, tot = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
-        int x = s_scan[w];
-        if (w < warp)
-          woff += x;
-        tot += x;
-      }
-      if (i < nb)
-        s_prefix[i] = carry + woff + incl - chunks;
-      carry += tot;
-      __syncthreads();
+  if (warp == 0)
+    fetch_range(0);
+  __syncthreads();  // mbarriers initialised, first range visible
+  if (tma && threadIdx.x == 0 && s_desc[0][0].cnt > 0)
+    issue(s_desc[0][0], 0);
+  unsigned phase_bits = 0;
+  int ring = 0, i = 0, buf = 0;
+  for (;;) {
+    if (i == 0 && warp == 0)
+      fetch_range(ring ^ 1);  // visible to everybody after this slab's closing barrier (kRange >= 2 of them follow)
+    const hub_slab_t d = s_desc[ring][i];
+    if (d.cnt <= 0)
+      break;  // uniform: every thread reads the same descriptor
+    if (tma && threadIdx.x == 0) {
+      // the next slab's descriptor: in this range, or the first of the next one (fetched kRange - 1 barriers ago;
+      // with kRange == 1 it would not be visible yet)
+      const hub_slab_t nd = (i + 1 < kRange) ? s_desc[ring][i + 1] : s_desc[ring ^ 1][0];
+      if (nd.cnt > 0)
+        issue(nd, buf ^ 1);
     }
-    if (threadIdx.x == 0)
-      s_prefix[nb] = carry;
-    __syncthreads();
-    const int total = carry;
-
-    int g = member;
-    if (tma && g < total && threadIdx.x == 0)
-      issue(g, nb, 0);
-    int buf = 0;
-    for (; g < total; g += members) {
-      int gn = g + members;
-      if (tma && gn < total && threadIdx.x == 0)
-        issue(gn, nb, buf ^ 1);
-      const int h = find_hub(g, nb);
-      const int u = s_vertex[h];
-      const int e0 = s_start[h] + (g - s_prefix[h]) * kChunk;
-      const int cnt = min(kChunk, s_end[h] - e0);
-      const int a0 = e0 & ~3;
-      if (tma) {
-        mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
-        phase_bits ^= 1u << buf;
-      }
-      for (int i0 = 0; i0 < cnt; i0 += kThreads * kHB) {
-        int e[kHB], nbv[kHB];
-        float w[kHB];
-        bool valid[kHB], keep[kHB];
-        typename op_traits<Op>::token_t tok[kHB];
+    const int u = d.src;
+    const int e0 = d.e0, cnt = d.cnt;
+    const int a0 = e0 & ~3;
+    if (tma) {
+      mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
+      phase_bits ^= 1u << buf;
+    }
+    for (int i0 = 0; i0 < cnt; i0 += kThreads * kHB) {
+      int e[kHB], nbv[kHB];
+      float w[kHB];
+      bool valid[kHB], keep[kHB];
+      typename op_traits<Op>::token_t tok[kHB];
 #pragma unroll
-        for (int k = 0; k < kHB; ++k) {
-          int i = i0 + k * kThreads + threadIdx.x;
-          e[k] = e0 + i;
-          valid[k] = i < cnt;
-          nbv[k] = -1;
-          w[k] = 1.0f;
-          if (valid[k]) {
-            if (tma) {
-              nbv[k] = s_idx[buf][e[k] - a0];
-              if (use_vals)
-                w[k] = s_val[kWeights ? buf : 0][e[k] - a0];
-            } else {
-              nbv[k] = ld_stream(ci + e[k]);
-              if (use_vals)
-                w[k] = ld_stream(vals + e[k]);
-            }
+      for (int k = 0; k < kHB; ++k) {
+        int j = i0 + k * kThreads + threadIdx.x;
+        e[k] = e0 + j;
+        valid[k] = j < cnt;
+        nbv[k] = -1;
+        w[k] = 1.0f;
+        if (valid[k]) {
+          if (tma) {
+            nbv[k] = s_idx[buf][e[k] - a0];
+            if (use_vals)
+              w[k] = s_val[kWeights ? buf : 0][e[k] - a0];
+          } else {
+            nbv[k] = ld_stream(ci + e[k]);
+            if (use_vals)
+              w[k] = ld_stream(vals + e[k]);
           }
         }
-#pragma unroll
-        for (int k = 0; k < kHB; ++k)
-          if (valid[k])
-            tok[k] = op_prefetch(op, nbv[k]);
-#pragma unroll
-        for (int k = 0; k < kHB; ++k)
-          keep[k] = valid[k] && op_commit(op, u, nbv[k], e[k], w[k], tok[k]);
-        if (kOut != advance_output_t::none) {
-#pragma unroll
-          for (int k = 0; k < kHB; ++k)
-            em.push(keep[k], kOut == advance_output_t::edges ? e[k] : op_emit(op, nbv[k]));
-        }
       }
-      __syncthreads();  // all reads of s_idx[buf] retire before it is refilled
-      buf ^= 1;
+#pragma unroll
+      for (int k = 0; k < kHB; ++k)
+        if (valid[k])
+          tok[k] = op_prefetch(op, nbv[k]);
+#pragma unroll
+      for (int k = 0; k < kHB; ++k)
+        keep[k] = valid[k] && op_commit(op, u, nbv[k], e[k], w[k], tok[k]);
+      if (kOut != advance_output_t::none) {
+#pragma unroll
+        for (int k = 0; k < kHB; ++k)
+          em.push(keep[k], kOut == advance_output_t::edges ? e[k] : op_emit(op, nbv[k]));
+      }
     }
-    __syncthreads();  // descriptors of this batch are dead; phase bits carry over per buffer
+    __syncthreads();  // all reads of s_idx[buf] / s_desc[ring][i] retire before they are refilled
+    buf ^= 1;
+    if (++i == kRange) {
+      i = 0;
+      ring ^= 1;
+    }
   }
   if (kOut != advance_output_t::none)
     em.flush();
@@ -829,8 +793,8 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
 }
 
 /**
- * @brief EXPERIMENTAL (advance_launch_t::variant 1 / 2, off by default): merge_path with WARP-PRIVATE
- * spans -- no block barrier anywhere.
+ * @brief merge_path with WARP-PRIVATE spans -- no block barrier anywhere (the default for the fused BFS / SSSP
+ * functors, see op_merge_path_kernel).
  *
  * Why: the ncu capture of advance_merge_path_kernel on the bench graph (profiles/r1_b_merge_path_v5_ncu.md)
  * shows a latency-bound kernel -- issue slots 43 % busy, L1 40 %, DRAM 12 % -- whose two largest stall
@@ -841,35 +805,22 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
  * the (at most kSpan) rows that overlap its span in its own slice of shared memory, then walks the span
  * with the same REDUX row-mask walk as the CTA kernel.  Warps never wait for each other; a warp draws
  * kTicket spans per atomic.
- *
- * kSnap (variant 2, functors with the snapshot protocol only): one 1024-thread CTA per SM keeps the
- * first `snap_bits` bits of the functor's visited map in shared memory (all the shared memory the warps'
- * staging leaves: ~155 KiB = 1.27 M vertices, about 2/3 of the edge targets of an RMAT graph, whose low
- * ids are the hubs).  A probe that finds its bit set there
- * costs a shared-memory access (bank conflicts ~3 cycles per warp) instead of 32 L1 tag lookups; a
- * probe that does not falls through to the global path and ORs the whole 32-vertex word it read back
- * into the copy.  Bits only go 0 -> 1, so a stale copy can only send an edge to the global test-and-set
- * that decides today as well.
+ * (Round 2 also measured copies of the visited map in shared memory / distributed shared memory in front of
+ * the probes: 1.3x - 2x SLOWER -- a probe through DSMEM runs at 52 G/s against 362 G/s through L1 -- removed.)
  */
-template <int kThreads, int kMinCtas, int kSpan, int kB, int kSnapCluster, advance_input_t kIn,
-          advance_output_t kOut, bool kDegSum, bool kWeights, typename Op, bool kPrefetch = false>
+template <int kThreads, int kMinCtas, int kSpan, int kB, advance_input_t kIn, advance_output_t kOut, bool kDegSum,
+          bool kWeights, typename Op>
 __global__ void __launch_bounds__(kThreads, kMinCtas)
-advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, int snap_bits, int map_words,
-                         Op op) {
-  constexpr bool kSnap = kSnapCluster > 0;
-  constexpr int kClusterN = kSnap ? kSnapCluster : 1;
+advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, Op op) {
   constexpr int kRows = kSpan + 36;  // kSpan ranks overlap at most kSpan non-empty rows (+ 33 sentinels)
   constexpr int kTicket = 8;         // spans per work-cursor atomic (lanes 0..kTicket hold their first rows)
   constexpr bool kSrc = op_needs_source<Op>::value;
   constexpr int kWarpInts = warp_path_ints<kSpan, kSrc>();
   static_assert(kSpan % 32 == 0 && kSpan < 65536 - 64 && kRows % 2 == 0, "span layout");
-  static_assert(!kSnap || op_has_snapshot<Op>::value, "a snapshot needs the functor's snapshot protocol");
   unsigned char* smem_raw = dynamic_smem();
-  // layout: [snapshot words] then per warp [emit | base | (vert) | rank (16 bit)]
-  unsigned* s_snap = reinterpret_cast<unsigned*>(smem_raw);
-  const int snap_words = kSnap ? (snap_bits >> 5) / kClusterN : 0;  // this CTA's slice (whole 128-byte lines)
+  // layout per warp: [emit | base | (vert) | rank (16 bit)]
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  int* mine = reinterpret_cast<int*>(smem_raw) + snap_words + warp * kWarpInts;
+  int* mine = reinterpret_cast<int*>(smem_raw) + warp * kWarpInts;
   int* s_base = mine + kEmitCap;  // (CSR offset of the row's first edge) - (its first rank)
   int* s_vert = s_base + kRows;   // only when the functor reads its source
   unsigned short* s_rank =        // first rank of each staged row, relative to the span start
@@ -879,22 +830,7 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
   const float* __restrict__ vals = p.g.values;
   const int n = (kIn == advance_input_t::graph) ? p.g.n_vertices : *p.in_count;
   if (n == 0)
-    return;  // uniform over the grid: nobody reaches the barrier below
-  snapshot_t<kClusterN> snap{smem_u32(s_snap), 0u, snap_bits};
-  if constexpr (kSnap) {
-    if (kClusterN > 1)
-      snap.rank = cluster_cta_rank();
-    const unsigned* gmap = op.snapshot_source();
-    for (int li = threadIdx.x; li < snap_words; li += kThreads) {
-      // local line li/32 is line (li/32)*kClusterN + rank of the map
-      const int wi = ((((li >> 5) * kClusterN) + static_cast<int>(snap.rank)) << 5) | (li & 31);
-      s_snap[li] = wi < map_words ? ld_relaxed(gmap + wi) : 0u;
-    }
-    if (kClusterN > 1)
-      cluster_barrier();  // every slice of the copy is in place before anybody probes it
-    else
-      __syncthreads();    // the only block barrier of the kernel
-  }
+    return;
   const int total = scanned[n];
   const int nspans = (total + kSpan - 1) / kSpan;
   warp_emitter_t<kEmitCap, kDegSum> em;
@@ -910,44 +846,25 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
     const int last = min(nspans, first + kTicket);
     // p.tile_rows[k] = row holding rank k * kSpan (n past the end): entries 0 .. nspans exist
     const int my_row = (first + lane <= last) ? p.tile_rows[first + lane] : 0;
-    // kPrefetch: the first 32 rows of the NEXT span's window are loaded before the current span is walked, so
-    // a span whose window has at most 32 rows (any frontier of average degree >= 8) starts without a round of
-    // memory latency; further rows of a longer window are loaded as before.
-    int pf_sc = 0, pf_next = 0, pf_rb = 0, pf_vv = 0;
-    auto load_row = [&](int i, int row_hi, int& sc, int& sc_next, int& rb, int& vv) {
-      if (i <= row_hi) {
-        sc = scanned[i];
-        sc_next = scanned[i + 1];
-        rb = p.row_base[i];
-        if (kSrc)
-          vv = (kIn == advance_input_t::graph) ? i : p.in[i];
-      }
-    };
-    if (kPrefetch)
-      load_row(__shfl_sync(kFull, my_row, 0) + lane, min(n - 1, __shfl_sync(kFull, my_row, 1)), pf_sc, pf_next,
-               pf_rb, pf_vv);
     for (int sp = first; sp < last; ++sp) {
       const int row0 = __shfl_sync(kFull, my_row, sp - first);
       const int row1 = min(n - 1, __shfl_sync(kFull, my_row, sp - first + 1));
       const int r_begin = sp * kSpan;
       const int r_end = min(total, r_begin + kSpan);
-      const int cur_sc = pf_sc, cur_next = pf_next, cur_rb = pf_rb, cur_vv = pf_vv;
-      if (kPrefetch && sp + 1 < last)  // uniform: the whole warp takes the branch
-        load_row(__shfl_sync(kFull, my_row, sp - first + 1) + lane,
-                 min(n - 1, __shfl_sync(kFull, my_row, sp - first + 2)), pf_sc, pf_next, pf_rb, pf_vv);
       // ---- stage the rows that overlap [r_begin, r_end) ------------------------------------
       int nrows = 0;  // warp-uniform
       for (int i0 = row0; i0 <= row1; i0 += 32) {
         const int i = i0 + lane;
         int sc = 0, sc_next = 0, rb = 0, vv = 0;
         bool live = false;
-        if (kPrefetch && i0 == row0) {
-          sc = cur_sc, sc_next = cur_next, rb = cur_rb, vv = cur_vv;
-        } else {
-          load_row(i, row1, sc, sc_next, rb, vv);
-        }
-        if (i <= row1)
+        if (i <= row1) {
+          sc = scanned[i];
+          sc_next = scanned[i + 1];
+          rb = p.row_base[i];
+          if (kSrc)
+            vv = (kIn == advance_input_t::graph) ? i : p.in[i];
           live = sc_next > sc && sc < r_end && sc_next > r_begin;
+        }
         const unsigned m = __ballot_sync(kFull, live);
         if (live) {
           const int slot = nrows + __popc(m & lanemask_lt());
@@ -988,19 +905,11 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
         }
 #pragma unroll
         for (int k = 0; k < kB; ++k)
-          if (valid[k]) {
-            if constexpr (kSnap)
-              tok[k] = op.prefetch_snap(nb[k], snap);
-            else
-              tok[k] = op_prefetch(op, nb[k]);
-          }
+          if (valid[k])
+            tok[k] = op_prefetch(op, nb[k]);
 #pragma unroll
-        for (int k = 0; k < kB; ++k) {
-          if constexpr (kSnap)
-            keep[k] = valid[k] && op.commit_snap(u[k], nb[k], e[k], w[k], tok[k], snap);
-          else
-            keep[k] = valid[k] && op_commit(op, u[k], nb[k], e[k], w[k], tok[k]);
-        }
+        for (int k = 0; k < kB; ++k)
+          keep[k] = valid[k] && op_commit(op, u[k], nb[k], e[k], w[k], tok[k]);
         if (kOut != advance_output_t::none) {
 #pragma unroll
           for (int k = 0; k < kB; ++k)
@@ -1014,8 +923,6 @@ advance_warp_path_kernel(advance_params_t p, const int* __restrict__ scanned, in
     em.flush();
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&p.ctrl->edges, static_cast<unsigned long long>(total));
-  if constexpr (kSnap && kClusterN > 1)
-    cluster_barrier();  // nobody leaves while a peer may still read / update its slice of the copy
 }
 
 /// Report of advance_tail_kernel (written to pinned host memory by the kernel).
@@ -1168,18 +1075,14 @@ struct advance_launch_t {
   long long mid_frontier_edges = 1 << 20;
   /// block_mapped: average out-degree of the frontier if the caller knows it (0 = unknown).
   double avg_degree = 0.0;
-  /// EXPERIMENTAL merge_path variants (0 = the measured default kernel).  Only functors that opt in
-  /// (`kVariants`) have them; everything else ignores the field.
-  ///   1  warp-private spans (advance_warp_path_kernel), 256-thread CTAs, 4 chunks in flight, registers
-  ///      capped for 6 CTAs per SM (the occupancy of the default kernel); variant 4: capped for 4
-  ///   2  warp-private spans, one 1024-thread CTA per SM, 8 chunks in flight, shared-memory snapshot of
-  ///      the visited map (functors with the snapshot protocol; others run variant 1)
-  ///   3  the default CTA kernel with 4096-edge tiles (half the block barriers per edge)
-  ///   4  warp-private spans, 256-thread CTAs, 8 chunks in flight
-  ///   5  as 2, the copy spread over a CLUSTER of 2 CTAs (distributed shared memory): twice the coverage
-  ///   6  as 2, cluster of 4: 5 M vertices on chip (the whole visited map of a scale-22 graph)
-  ///   7  as 4, the next span's row window prefetched while the current span is walked
-  int variant = 0;
+  /// merge_path kernel: < 0 = the functor's own choice (op_merge_path_kernel), 0 = CTA tiles of 2048 edges
+  /// (advance_merge_path_kernel), 1 = warp-private spans, 256-thread CTAs, 4 chunks in flight, registers capped for
+  /// 6 CTAs per SM, 4 = the same with 8 chunks in flight, capped for 4 CTAs per SM (advance_warp_path_kernel).
+  /// Functors without a choice of their own always run 0.
+  int variant = -1;
+  /// Upper bound on the out-degree sum of the input frontier when the caller knows one above the graph's edge
+  /// count (a frontier that holds vertices several times); sizes the hub slab table.  0 = the edge count.
+  long long edges_upper_bound = 0;
 };
 
 
@@ -1190,6 +1093,7 @@ inline void reserve_advance_workspace(workspace_t& ws, const csr_view_t& g, int 
   ws.scanned.ensure(2 * static_cast<size_t>(n_upper_bound) + 4);
   ws.tile_rows.ensure((static_cast<size_t>(1) << 31) / 2048 + 4);
   ws.hubs.ensure(static_cast<size_t>(g.n_edges / 256 + 1024));
+  ws.hub_slabs.ensure(2 * (static_cast<size_t>(g.n_edges) / 2048 + static_cast<size_t>(g.n_edges / 256 + 1024) + 64));
   const int max_tiles = (n_upper_bound + 256 * 8 - 1) / (256 * 8) + 1;
   const size_t had = ws.tile_state.cap;
   ws.tile_state.ensure(max_tiles);
@@ -1289,73 +1193,10 @@ inline void launch_merge_path_tiles(workspace_t& ws, advance_params_t& p, const 
         <<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
 }
 
-/// EXPERIMENTAL variants 2 / 5 / 6: warp-private spans + on-chip copy of the functor's visited map, held by
-/// one 1024-thread CTA per SM (kCluster == 1) or spread over a cluster of kCluster such CTAs.
-/// `p.tile_rows` / `p.ctrl` are already set by launch_warp_path.
-template <int kCluster, advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
-inline void launch_warp_path_snapshot(workspace_t& ws, advance_params_t& p, const int* scanned, bool graph_in,
-                                      Op op) {
-  constexpr int kSpan = 256, kThreads = 1024;
-  constexpr int kWarpBytes = warp_path_ints<kSpan, op_needs_source<Op>::value>() * 4;
-  const int sms = device_info_t::get().sm_count;
-  // every CTA's slice takes the shared memory the 32 warps' staging leaves (227 KiB opt-in on B200: ~155 KiB =
-  // 1.27 M vertices per CTA; the low ids of an RMAT graph are its hubs, so one slice already holds ~2/3 of all
-  // edge targets, two ~5/6, four the whole map of a scale-22 graph)
-  const int map_words = (p.g.n_vertices + 31) / 32;
-  const int room = device_info_t::get().max_smem_optin - 1024 - (kThreads / 32) * kWarpBytes;
-  const long long lines_cta = room > 0 ? room / 128 : 0;                      // 128-byte lines per CTA
-  const long long lines_map = (static_cast<long long>(map_words) + 31) / 32;  // lines of the whole map
-  long long lines = lines_cta * kCluster;
-  if (lines > lines_map)
-    lines = ((lines_map + kCluster - 1) / kCluster) * kCluster;               // same number of lines per CTA
-  const int snap_bits = static_cast<int>(lines * 1024);
-  const int smem = static_cast<int>(lines / kCluster) * 128 + (kThreads / 32) * kWarpBytes;
-  auto kg = advance_warp_path_kernel<kThreads, 1, kSpan, 8, kCluster, advance_input_t::graph, kOut, kDegSum,
-                                     kWeights, Op>;
-  auto kv = advance_warp_path_kernel<kThreads, 1, kSpan, 8, kCluster, advance_input_t::vertices, kOut, kDegSum,
-                                     kWeights, Op>;
-  cudaLaunchConfig_t lc{};
-  lc.blockDim = dim3(kThreads);
-  lc.dynamicSmemBytes = static_cast<size_t>(smem);
-  lc.stream = ws.stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  lc.attrs = attr;
-  lc.numAttrs = kCluster > 1 ? 1 : 0;
-  // opt in to > 48 KiB of dynamic shared memory and size the grid, once per device: as many whole clusters
-  // as can be resident together (148 CTAs for pairs, fewer for clusters of four), work comes by ticket
-  static thread_local int for_device = -1;
-  static thread_local int grid_ctas = 0;
-  if (for_device != device_info_t::get().device) {
-    const int most = device_info_t::get().max_smem_optin;
-    B2G_CHECK(cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-    B2G_CHECK(cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-    grid_ctas = (sms / kCluster) * kCluster;
-    if (kCluster > 1) {
-      lc.gridDim = dim3(grid_ctas);
-      int clusters = 0;
-      B2G_CHECK(cudaOccupancyMaxActiveClusters(&clusters, kv, &lc));
-      if (clusters < 1)
-        throw std::runtime_error("advance variant: no cluster of this shape fits the device");
-      if (clusters * kCluster < grid_ctas)
-        grid_ctas = clusters * kCluster;
-    }
-    for_device = device_info_t::get().device;
-  }
-  lc.gridDim = dim3(grid_ctas);
-  if (graph_in)
-    B2G_CHECK(cudaLaunchKernelEx(&lc, kg, p, scanned, snap_bits, map_words, op));
-  else
-    B2G_CHECK(cudaLaunchKernelEx(&lc, kv, p, scanned, snap_bits, map_words, op));
-}
-
-/// EXPERIMENTAL variants 1 / 2 / 4 / 5 / 6 / 7: span partition + advance_warp_path_kernel.
+/// merge_path with warp-private spans: span partition + advance_warp_path_kernel (variant 1 or 4).
 template <advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
-inline void launch_warp_path(workspace_t& ws, advance_params_t& p, const int* scanned, bool graph_in,
-                             const advance_launch_t& cfg, Op op) {
+inline void launch_warp_path(workspace_t& ws, advance_params_t& p, const int* scanned, bool graph_in, int variant,
+                             int ctas_per_sm, Op op) {
   constexpr int kSpan = 256;
   constexpr bool kSrc = op_needs_source<Op>::value;
   constexpr int kWarpBytes = warp_path_ints<kSpan, kSrc>() * 4;
@@ -1368,44 +1209,23 @@ inline void launch_warp_path(workspace_t& ws, advance_params_t& p, const int* sc
   p.ctrl = ws.next_ctrl();
   constexpr auto kGraph = advance_input_t::graph;
   constexpr auto kVerts = advance_input_t::vertices;
-  if constexpr (op_has_snapshot<Op>::value) {
-    if (cfg.variant == 2) {
-      launch_warp_path_snapshot<1, kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, op);
-      return;
-    }
-    if (cfg.variant == 5) {
-      launch_warp_path_snapshot<2, kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, op);
-      return;
-    }
-    if (cfg.variant == 6) {
-      launch_warp_path_snapshot<4, kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, op);
-      return;
-    }
-  }
   constexpr int kThreads = 256;
   const int smem = (kThreads / 32) * kWarpBytes;
-  const int grid = sms * cfg.ctas_per_sm;
-  if (cfg.variant == 7) {
+  const int grid = sms * ctas_per_sm;
+  if (variant == 4) {
     if (graph_in)
-      advance_warp_path_kernel<kThreads, 4, kSpan, 8, 0, kGraph, kOut, kDegSum, kWeights, Op, true>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
+      advance_warp_path_kernel<kThreads, 4, kSpan, 8, kGraph, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, op);
     else
-      advance_warp_path_kernel<kThreads, 4, kSpan, 8, 0, kVerts, kOut, kDegSum, kWeights, Op, true>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
-  } else if (cfg.variant == 4) {
-    if (graph_in)
-      advance_warp_path_kernel<kThreads, 4, kSpan, 8, 0, kGraph, kOut, kDegSum, kWeights>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
-    else
-      advance_warp_path_kernel<kThreads, 4, kSpan, 8, 0, kVerts, kOut, kDegSum, kWeights>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
+      advance_warp_path_kernel<kThreads, 4, kSpan, 8, kVerts, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, op);
   } else {
     if (graph_in)
-      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, 0, kGraph, kOut, kDegSum, kWeights>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
+      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, kGraph, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, op);
     else
-      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, 0, kVerts, kOut, kDegSum, kWeights>
-          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, 0, 0, op);
+      advance_warp_path_kernel<kThreads, 6, kSpan, kBatch, kVerts, kOut, kDegSum, kWeights>
+          <<<grid, kThreads, smem, ws.stream>>>(p, scanned, op);
   }
 }
 
@@ -1453,12 +1273,10 @@ inline void launch_advance(workspace_t& ws,
                                   : frontier_degree_scan(ws, g, in, in_count, in_upper_bound, &row_base);
     p.row_base = row_base;
     bool launched = false;
-    if constexpr (op_wants_variants<Op>::value) {
-      if (cfg.variant == 3) {
-        launch_merge_path_tiles<4096, kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, grid, op);
-        launched = true;
-      } else if (cfg.variant != 0) {
-        launch_warp_path<kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, cfg, op);
+    if constexpr (op_merge_path_kernel<Op>::value != 0) {
+      const int variant = cfg.variant < 0 ? op_merge_path_kernel<Op>::value : cfg.variant;
+      if (variant == 1 || variant == 4) {
+        launch_warp_path<kOut, kDegSum, kWeights>(ws, p, scanned, graph_in, variant, cfg.ctas_per_sm, op);
         launched = true;
       }
     }
@@ -1469,6 +1287,11 @@ inline void launch_advance(workspace_t& ws,
     p.hub_threshold = cfg.hub_threshold < 32 ? 32 : cfg.hub_threshold;
     p.hub_capacity = cfg.hub_threshold < (1 << 30) ? g.n_edges / 256 + 1024 : 16;
     p.hubs = ws.hubs.ensure(static_cast<size_t>(p.hub_capacity));
+    // every deferred row has >= 1 slab and at most one partial one: E / 2048 + rows bounds the table
+    const size_t edge_bound = cfg.edges_upper_bound > g.n_edges ? static_cast<size_t>(cfg.edges_upper_bound)
+                                                                : static_cast<size_t>(g.n_edges);
+    p.hub_slab_capacity = static_cast<int>(edge_bound / 2048 + static_cast<size_t>(p.hub_capacity) + 64);
+    p.hub_slabs = reinterpret_cast<hub_slab_t*>(ws.hub_slabs.ensure(2 * static_cast<size_t>(p.hub_slab_capacity)));
     p.tma_ok = aligned16(g.column_indices) && (!kWeights || !g.values || aligned16(g.values));
     if (cfg.avg_degree > 0.0) {
       int want = static_cast<int>(16384.0 / cfg.avg_degree);
@@ -1483,11 +1306,14 @@ inline void launch_advance(workspace_t& ws,
     else
       advance_binned_kernel<kThreads, advance_input_t::vertices, kOut, kDegSum, kWeights>
           <<<grid, kThreads, 0, ws.stream>>>(p, op);
-    if (cfg.hub_threshold < (1 << 30))
+    if (cfg.hub_threshold < (1 << 30)) {
+      advance_hub_table_kernel<2048><<<sms * 2, 256, 0, ws.stream>>>(p);
       advance_hub_kernel<kThreads, 2048, kOut, kDegSum, kWeights>
           <<<sms * (kWeights ? 4 : 5), kThreads, 0, ws.stream>>>(p, op);
-    else
+      ws.launches += 1;
+    } else {
       ws.launches -= 1;
+    }
   }
   ws.launches += (cfg.lb == lb_t::thread_mapped) ? 1 : 2;
   if (ctrl_out)

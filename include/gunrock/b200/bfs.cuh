@@ -53,39 +53,8 @@ struct bfs_claim_op {
     dist[dst] = next_level;
     return true;
   }
-  // ---- experimental kernel variants (advance_launch_t::variant; off by default) --------------------
-  static constexpr bool kVariants = true;
-  /// snapshot protocol (advance.cuh snapshot_t): the first `snap.bits` bits of `visited` have a copy in
-  /// (distributed) shared memory.  A bit found set there needs no global probe; the token is then just that
-  /// bit, so that commit neither claims nor learns anything from it.
-  static constexpr bool kHasSnapshot = true;
-  __device__ __forceinline__ const unsigned* snapshot_source() const { return visited; }
-  template <typename Snap>
-  __device__ __forceinline__ unsigned prefetch_snap(int dst, const Snap& snap) const {
-    const unsigned bit = 1u << (dst & 31);
-    if (snap.covers(dst) && (snap.load(dst) & bit))
-      return bit;
-    return ld_cached(visited + (dst >> 5));
-  }
-  template <typename Snap>
-  __device__ __forceinline__ bool commit_snap(int, int dst, int, float, unsigned word, const Snap& snap) const {
-    const unsigned bit = 1u << (dst & 31);
-    bool won = false;
-    if (!(word & bit)) {
-      word = atomicOr(visited + (dst >> 5), bit);  // the word as it was: 32 vertices' worth of news
-      won = !(word & bit);
-      word |= bit;
-      if (won)
-        dist[dst] = next_level;
-    }
-    // Whatever global state this edge saw goes into the on-chip copy (monotone: bits only get set).  A token
-    // that is exactly `bit` either came from the copy or carries nothing the copy needs besides that one bit;
-    // only the second case loses anything (that vertex keeps probing the global map) and it needs a word in
-    // which a single vertex is visited.
-    if (snap.covers(dst) && (won || word != bit))
-      snap.merge(dst, word);
-    return won;
-  }
+  /// merge_path runs on the warp-private-span kernel, 4 chunks in flight (advance.cuh op_merge_path_kernel)
+  static constexpr int kMergePathKernel = 1;
 };
 
 /// Builds the claim functor of a given level (advance_tail_kernel runs several levels per launch).
@@ -176,37 +145,6 @@ static __global__ void bitmap_to_queue_kernel(const unsigned* __restrict__ bm, i
     int vb = wi << 5;
     while (w) {
       int b = __ffs(w) - 1;
-      w &= w - 1;
-      q[base++] = vb + b;
-    }
-  }
-}
-
-/// Enumerate the CLEAR bits of the visited map below n_vertices (the still-unvisited vertices) into a queue.
-/// EXPERIMENTAL (B2G_BFS_PULL_LIST_FIRST): lets the FIRST pull level run on the dense list kernel as well.
-static __global__ void bfs_unvisited_list_kernel(const unsigned* __restrict__ visited, int n_vertices, int* q,
-                                                 int* count) {
-  const int lane = lane_id();
-  const int words = (n_vertices + 31) / 32;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  for (int w0 = gw * 32; w0 < words; w0 += warps * 32) {
-    const int wi = w0 + lane;
-    unsigned w = wi < words ? ~visited[wi] : 0u;
-    if (wi == words - 1 && (n_vertices & 31))
-      w &= (1u << (n_vertices & 31)) - 1u;  // bits past the last vertex are not vertices
-    const int c = __popc(w);
-    const int incl = warp_inclusive_sum(c);
-    const int total = __shfl_sync(kFull, incl, 31);
-    if (!total)
-      continue;
-    int base = 0;
-    if (lane == 0)
-      base = atomicAdd(count, total);
-    base = __shfl_sync(kFull, base, 0) + incl - c;
-    const int vb = wi << 5;
-    while (w) {
-      const int b = __ffs(w) - 1;
       w &= w - 1;
       q[base++] = vb + b;
     }
@@ -427,12 +365,12 @@ bfs_bottom_up_list_kernel(csr_view_t in, const int* __restrict__ unv_in,
 // for 132 MB of useful indices), one dependent chain per lane.  So the graph carries one more per-vertex array,
 // built once like the transpose:
 //     first_nb[v] = v's first in-neighbour, bit 31 set when it is the ONLY one, -1 without in-edges
-// and a pull level becomes two kernels:
-//   K1 (bfs_pull_first_*): one probe per unvisited vertex straight from first_nb -- coalesced 4 B per vertex in
-//       the sweep form (first pull level of a run), kUnroll independent probes in flight per lane -- which
-//       settles ~80 % of the vertices without touching row offsets or column indices.  A miss goes to the
-//       `retry` list, or, when that neighbour was the only one, straight to the next level's unvisited list.
-//   K2 (bfs_pull_rest_kernel): the full search from the SECOND in-neighbour on, for the retry list only.
+// and a pull level becomes two kernels, both sweeps over 32-vertex words:
+//   K1 (bfs_pull_first_kernel): one probe per unvisited vertex straight from first_nb -- coalesced 4 B per
+//       vertex, kUnroll independent probes in flight per lane -- which settles ~75 % of the vertices without
+//       touching row offsets or column indices.  A miss with more in-neighbours to look at sets its bit in the
+//       `retry` map; a miss whose only in-neighbour that was cannot be found at this level and costs nothing more.
+//   K2 (bfs_pull_rest_kernel): the full search from the SECOND in-neighbour on, for the retry map's vertices.
 // Depths are those of the sweep above: a vertex is labelled at the first level at which ANY in-neighbour is
 // in the frontier; which neighbour is probed first does not matter.
 // ---------------------------------------------------------------------------------------------------------
@@ -464,35 +402,34 @@ struct bitmap_word_sink_t {
 };
 
 /**
- * @brief K1, sweep form (first pull level of a run of pull levels): one warp owns 32 consecutive words of the
- * visited map per pass and settles kUnroll of them at a time -- kUnroll coalesced loads of first_nb, then kUnroll
- * frontier probes in flight per lane -- writing the next-frontier / visited words with plain stores.
+ * @brief K1: one warp owns 32 consecutive words of the visited map per pass and settles kUnroll of them at a
+ * time -- kUnroll coalesced loads of first_nb, then kUnroll frontier probes in flight per lane.  Everything it
+ * produces is a WORD written with a plain store by one lane: the next-frontier word, the visited word, and the
+ * word of vertices that need K2 (first in-neighbour not in the frontier, more in-neighbours to look at).  No
+ * lists, no atomics: measured on RMAT-26 the list forms of these kernels ran at the DRAM's random-sector rate
+ * (~72 G sectors/s, 29 % of the copy bandwidth) while this sweep reads first_nb sequentially.
  */
 template <int kThreads, int kUnroll, typename FrontierTest, typename Sink>
 __global__ void __launch_bounds__(kThreads)
-bfs_pull_first_sweep_kernel(int n_vertices, const int* __restrict__ first_nb, unsigned* __restrict__ visited,
-                            FrontierTest in_frontier, Sink sink, int* dist, int next_level, ctrl_t* ctrl,
-                            int* next_count, int* retry, int* retry_count, int* unv, int* unv_count) {
-  __shared__ int s_emit[kThreads / 32][2][kEmitCap];
-  warp_emitter_t<kEmitCap, false> em_retry, em_unv;
-  em_retry.init(s_emit[threadIdx.x >> 5][0], retry, retry_count, n_vertices, nullptr, ctrl);
-  em_unv.init(s_emit[threadIdx.x >> 5][1], unv, unv_count, n_vertices, nullptr, ctrl);
+bfs_pull_first_kernel(int n_vertices, const int* __restrict__ first_nb, unsigned* __restrict__ visited,
+                      FrontierTest in_frontier, Sink sink, unsigned* __restrict__ retry_map, int* dist,
+                      int next_level, ctrl_t* ctrl, int* next_count) {
   const int lane = lane_id();
   const int words = (n_vertices + 31) / 32;
   const int warps = (gridDim.x * kThreads) >> 5;
   const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
-  unsigned long long probes = 0;
-  int found_cnt = 0;
+  unsigned probes = 0, found_cnt = 0, retry_cnt = 0;  // lane 0 only
   for (int w0 = gw * 32; w0 < words; w0 += warps * 32) {
     const int my_wi = w0 + lane;
     const unsigned my_vis = my_wi < words ? visited[my_wi] : 0xffffffffu;
-    if (my_wi < words && my_vis == 0xffffffffu)
+    if (my_wi < words && my_vis == 0xffffffffu) {
       sink.zero(my_wi);
+      retry_map[my_wi] = 0;
+    }
     unsigned todo = __ballot_sync(kFull, my_vis != 0xffffffffu);
     while (todo) {
       int wi[kUnroll], nb[kUnroll];
       unsigned vis[kUnroll];
-      bool act[kUnroll], hit[kUnroll];
 #pragma unroll
       for (int k = 0; k < kUnroll; ++k) {
         wi[k] = -1;
@@ -507,191 +444,116 @@ bfs_pull_first_sweep_kernel(int n_vertices, const int* __restrict__ first_nb, un
 #pragma unroll
       for (int k = 0; k < kUnroll; ++k) {
         const int v = (wi[k] << 5) + lane;
-        act[k] = wi[k] >= 0 && v < n_vertices && !((vis[k] >> lane) & 1u);
-        nb[k] = act[k] ? ld_stream(first_nb + v) : -1;
+        nb[k] = -1;
+        if (wi[k] >= 0 && v < n_vertices && !((vis[k] >> lane) & 1u))
+          nb[k] = ld_stream(first_nb + v);
       }
+      bool hit[kUnroll];
 #pragma unroll
-      for (int k = 0; k < kUnroll; ++k) {
-        hit[k] = false;
-        if (act[k] && nb[k] != -1) {
-          ++probes;
-          hit[k] = in_frontier(nb[k] & ~kOnlyNeighbor);
-        }
-      }
+      for (int k = 0; k < kUnroll; ++k)
+        hit[k] = nb[k] != -1 && in_frontier(nb[k] & ~kOnlyNeighbor);
 #pragma unroll
       for (int k = 0; k < kUnroll; ++k) {
         if (wi[k] < 0)
           continue;  // warp-uniform
-        const int v = (wi[k] << 5) + lane;
+        const unsigned pm = __ballot_sync(kFull, nb[k] != -1);
         const unsigned fm = __ballot_sync(kFull, hit[k]);
+        const unsigned rm = __ballot_sync(kFull, nb[k] != -1 && !hit[k] && !(nb[k] & kOnlyNeighbor));
         if (hit[k])
-          dist[v] = next_level;
+          dist[(wi[k] << 5) + lane] = next_level;
         sink.word(wi[k], fm);
-        if (lane == 0 && fm)
-          visited[wi[k]] = vis[k] | fm;
-        found_cnt += hit[k] ? 1 : 0;
-        const bool miss = act[k] && !hit[k] && nb[k] != -1;
-        em_retry.push(miss && !(nb[k] & kOnlyNeighbor), v);
-        em_unv.push(miss && (nb[k] & kOnlyNeighbor), v);
+        if (lane == 0) {
+          retry_map[wi[k]] = rm;
+          if (fm)
+            visited[wi[k]] = vis[k] | fm;
+          probes += __popc(pm);
+          found_cnt += __popc(fm);
+          retry_cnt += __popc(rm);
+        }
       }
     }
   }
-  em_retry.flush();
-  em_unv.flush();
-  probes = warp_sum(probes);
-  found_cnt = warp_sum(found_cnt);
   if (lane == 0) {
     if (probes)
-      atomicAdd(&ctrl->edges, probes);
+      atomicAdd(&ctrl->edges, static_cast<unsigned long long>(probes));
     if (found_cnt)
-      atomicAdd(next_count, found_cnt);
+      atomicAdd(next_count, static_cast<int>(found_cnt));
+    if (retry_cnt)
+      atomicAdd(&ctrl->hub_count, static_cast<int>(retry_cnt));  // K2's population (statistics only)
   }
 }
 
-/// Set v's bit in `map` (found vertices of the list kernels; RED.OR, no return value).
+/// Set v's bit in `map` (RED.OR, no return value).
 __device__ __forceinline__ void bitmap_set(unsigned* map, bool on, int v) {
   if (on)
     atomicOr(map + (v >> 5), 1u << (v & 31));
 }
 
 /**
- * @brief K1, list form (later pull levels): the same single probe for the vertices of the unvisited list,
- * kUnroll vertices per lane.  Found vertices set their bits with atomicOr (no return value: RED).
+ * @brief K2: the full search from the SECOND in-neighbour on, for the vertices K1 marked in `retry_map`
+ * (~15 % of the unvisited vertices of the first pull level, 2-3 set bits per word).  A warp takes kWords words
+ * per pass, expands their set bits into its own queue in shared memory (warp scan of the popcounts), and
+ * walks the queue 32 vertices at a time: kSerial interleaved probes per lane, rows still open after that are
+ * finished by the whole warp.  Found vertices set their bits with RED.OR.
  */
-template <int kThreads, int kUnroll, typename FrontierTest>
+template <int kThreads, int kWords, int kSerial, typename FrontierTest>
 __global__ void __launch_bounds__(kThreads)
-bfs_pull_first_list_kernel(int n_vertices, const int* __restrict__ first_nb, const int* __restrict__ list,
-                           const int* __restrict__ list_count, unsigned* visited, FrontierTest in_frontier,
-                           unsigned* next, int* dist, int next_level, ctrl_t* ctrl, int* next_count, int* retry,
-                           int* retry_count, int* unv, int* unv_count) {
-  __shared__ int s_emit[kThreads / 32][2][kEmitCap];
-  warp_emitter_t<kEmitCap, false> em_retry, em_unv;
-  em_retry.init(s_emit[threadIdx.x >> 5][0], retry, retry_count, n_vertices, nullptr, ctrl);
-  em_unv.init(s_emit[threadIdx.x >> 5][1], unv, unv_count, n_vertices, nullptr, ctrl);
+bfs_pull_rest_kernel(csr_view_t in, const unsigned* __restrict__ retry_map, unsigned* visited,
+                     FrontierTest in_frontier, unsigned* next, int* dist, int next_level, ctrl_t* ctrl,
+                     int* next_count) {
+  static_assert(kWords <= 32, "one lane per word");
+  __shared__ int s_q[kThreads / 32][kWords * 32];
+  int* q = s_q[threadIdx.x >> 5];
   const int lane = lane_id();
-  const int n = *list_count;
-  unsigned long long probes = 0;
-  int found_cnt = 0;
-  for (;;) {
-    int base = 0;
-    if (lane == 0)
-      base = atomicAdd(&ctrl->work, 32 * kUnroll);
-    base = __shfl_sync(kFull, base, 0);
-    if (base >= n)
-      break;
-    int v[kUnroll], nb[kUnroll];
-    bool hit[kUnroll];
-#pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      const int i = base + 32 * k + lane;
-      v[k] = i < n ? list[i] : -1;
-    }
-#pragma unroll
-    for (int k = 0; k < kUnroll; ++k)
-      nb[k] = v[k] >= 0 ? first_nb[v[k]] : -1;
-#pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      hit[k] = false;
-      if (nb[k] != -1) {
-        ++probes;
-        hit[k] = in_frontier(nb[k] & ~kOnlyNeighbor);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      if (hit[k]) {
-        dist[v[k]] = next_level;
-        ++found_cnt;
-      }
-      bitmap_set(next, hit[k], v[k]);
-      bitmap_set(visited, hit[k], v[k]);
-      const bool miss = nb[k] != -1 && !hit[k];
-      em_retry.push(miss && !(nb[k] & kOnlyNeighbor), v[k]);
-      em_unv.push(miss && (nb[k] & kOnlyNeighbor), v[k]);
-    }
-  }
-  em_retry.flush();
-  em_unv.flush();
-  probes = warp_sum(probes);
-  found_cnt = warp_sum(found_cnt);
-  if (lane == 0) {
-    if (probes)
-      atomicAdd(&ctrl->edges, probes);
-    if (found_cnt)
-      atomicAdd(next_count, found_cnt);
-  }
-}
-
-/**
- * @brief K2: full search from the SECOND in-neighbour on, over the retry list (the vertices whose first
- * in-neighbour is not in the frontier and that have more).  Two vertices per lane, their serial probes
- * interleaved (two independent chains); rows still open after kSerial probes are finished by the whole warp.
- * Not found -> the next level's unvisited list.
- */
-template <int kThreads, int kSerial, typename FrontierTest>
-__global__ void __launch_bounds__(kThreads)
-bfs_pull_rest_kernel(csr_view_t in, const int* __restrict__ list, const int* __restrict__ list_count,
-                     unsigned* visited, FrontierTest in_frontier, unsigned* next, int* dist, int next_level,
-                     ctrl_t* ctrl, int* next_count, int* unv, int* unv_count) {
-  __shared__ int s_emit[kThreads / 32][kEmitCap];
-  warp_emitter_t<kEmitCap, false> em;
-  em.init(s_emit[threadIdx.x >> 5], unv, unv_count, in.n_vertices, nullptr, ctrl);
-  const int lane = lane_id();
-  const int n = *list_count;
+  const int words = (in.n_vertices + 31) / 32;
+  const int warps = (gridDim.x * kThreads) >> 5;
+  const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
   const int* __restrict__ ro = in.row_offsets;
   const int* __restrict__ ci = in.column_indices;
   unsigned long long scanned = 0;
   int found_cnt = 0;
-  for (;;) {
-    int base = 0;
-    if (lane == 0)
-      base = atomicAdd(&ctrl->work, 64);
-    base = __shfl_sync(kFull, base, 0);
-    if (base >= n)
-      break;
-    int v[2], e[2], end[2];
-    bool searching[2], found[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int i = base + 32 * k + lane;
-      v[k] = i < n ? list[i] : -1;
-      found[k] = false;
+  for (int w0 = gw * kWords; w0 < words; w0 += warps * kWords) {
+    const int my_wi = w0 + lane;
+    unsigned m = (lane < kWords && my_wi < words) ? retry_map[my_wi] : 0u;
+    const int c = __popc(m);
+    const int incl = warp_inclusive_sum(c);
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (!total)
+      continue;
+    int at = incl - c;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      q[at++] = (my_wi << 5) + b;
     }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      e[k] = end[k] = 0;
-      if (v[k] >= 0) {
-        e[k] = ro[v[k]] + 1;  // the first in-neighbour was K1's probe
-        end[k] = ro[v[k] + 1];
+    __syncwarp();
+    for (int i0 = 0; i0 < total; i0 += 32) {
+      const int i = i0 + lane;
+      const int v = i < total ? q[i] : -1;
+      int e = 0, end = 0;
+      if (v >= 0) {
+        e = ro[v] + 1;  // the first in-neighbour was K1's probe
+        end = ro[v + 1];
       }
-      searching[k] = e[k] < end[k];
-    }
-    for (int s = 0; s < kSerial; ++s) {
-      int u[2];
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        u[k] = (searching[k] && e[k] < end[k]) ? ci[e[k]] : -1;
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        if (u[k] >= 0) {
-          ++e[k];
+      bool searching = e < end, found = false;
+      for (int s = 0; s < kSerial; ++s) {
+        if (searching) {
+          const int u = ci[e++];
           ++scanned;
-          if (in_frontier(u[k])) {
-            found[k] = true;
-            searching[k] = false;
+          if (in_frontier(u)) {
+            found = true;
+            searching = false;
+          } else if (e >= end) {
+            searching = false;
           }
         }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (e[k] >= end[k])
-        searching[k] = false;
-      unsigned rest = __ballot_sync(kFull, searching[k]);
+      }
+      unsigned rest = __ballot_sync(kFull, searching);
       while (rest) {
         const int leader = __ffs(rest) - 1;
         rest &= rest - 1;
-        const int s0 = __shfl_sync(kFull, e[k], leader);
-        const int t = __shfl_sync(kFull, end[k], leader);
+        const int s0 = __shfl_sync(kFull, e, leader);
+        const int t = __shfl_sync(kFull, end, leader);
         bool any = false;
         for (int off = s0; off < t && !any; off += 32) {
           const int idx = off + lane;
@@ -703,18 +565,17 @@ bfs_pull_rest_kernel(csr_view_t in, const int* __restrict__ list, const int* __r
           any = __any_sync(kFull, mine);
         }
         if (lane == leader)
-          found[k] = any;
+          found = any;
       }
-      if (found[k]) {
-        dist[v[k]] = next_level;
+      if (found) {
+        dist[v] = next_level;
         ++found_cnt;
       }
-      bitmap_set(next, found[k], v[k]);
-      bitmap_set(visited, found[k], v[k]);
-      em.push(v[k] >= 0 && !found[k], v[k]);
+      bitmap_set(next, found, v);
+      bitmap_set(visited, found, v);
     }
+    __syncwarp();  // the queue is rewritten by the next pass
   }
-  em.flush();
   scanned = warp_sum(scanned);
   found_cnt = warp_sum(found_cnt);
   if (lane == 0) {
@@ -745,7 +606,7 @@ struct bfs_config_t {
 struct bfs_scratch_t {
   dbuf_t<unsigned> visited, fbm, nbm, unreachable;
   dbuf_t<int> unv[2];                    // still-unvisited vertices (consecutive bottom-up levels)
-  dbuf_t<int> retry;                     // pull levels: vertices whose first in-neighbour missed (K2's input)
+  dbuf_t<unsigned> retry_map;            // pull levels: vertices whose first in-neighbour missed (K2's input)
   dbuf_t<int> first_nb;                  // per vertex: first in-neighbour (bfs_first_neighbor_kernel)
   graph_key_t unreachable_for;           // the (in-edge) graph the unreachable map was built from
   graph_key_t first_nb_for;              // ... and the one first_nb was built from
@@ -925,46 +786,21 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
         ws.launches += 1;
       }
       ca = ws.next_ctrl();
-      sc.unv[0].ensure(static_cast<size_t>(V) + 64);
-      sc.unv[1].ensure(static_cast<size_t>(V) + 64);
-      B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 2, 0, sizeof(int), st));
-      // EXPERIMENTAL, off unless B2G_BFS_PULL_LIST_FIRST is set: list the unvisited vertices first (one pass over
-      // the visited map) so that the first pull level runs with every lane busy too, instead of sweeping words in
-      // which most lanes hold visited or edge-less vertices
-      static const bool list_first = std::getenv("B2G_BFS_PULL_LIST_FIRST") != nullptr;
-      if (!unv_valid && list_first) {
-        B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));
-        bfs_unvisited_list_kernel<<<sms * 8, 256, 0, st>>>(sc.visited.ptr, V, sc.unv[0].ptr, sc.counts.ptr + 4);
-        ws.launches += 1;
-        unv_cur = 0;
-        unv_valid = true;
+      if (legacy_pull) {
+        sc.unv[0].ensure(static_cast<size_t>(V) + 64);
+        sc.unv[1].ensure(static_cast<size_t>(V) + 64);
       }
+      B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 2, 0, sizeof(int), st));
       if (!legacy_pull) {
         // K1 (one probe per unvisited vertex, from first_nb) + K2 (full search for K1's misses): see above
         cb = ws.next_ctrl();
-        sc.retry.ensure(static_cast<size_t>(V) + 64);
-        B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 6, 0, sizeof(int), st));
+        sc.retry_map.ensure(static_cast<size_t>(words) + 4);
         const bitmap_frontier_t in_frontier{fbm};
-        if (!unv_valid) {
-          B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));
-          bfs_pull_first_sweep_kernel<256, 4><<<sms * 8, 256, 0, st>>>(
-              V, sc.first_nb.ptr, sc.visited.ptr, in_frontier, bitmap_word_sink_t{nbm}, dist, level + 1, ca,
-              sc.counts.ptr + 2, sc.retry.ptr, sc.counts.ptr + 6, sc.unv[0].ptr, sc.counts.ptr + 4);
-          unv_cur = 0;
-          unv_valid = true;
-        } else {
-          const int o = unv_cur ^ 1;
-          B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4 + o, 0, sizeof(int), st));
-          B2G_CHECK(cudaMemsetAsync(nbm, 0, sizeof(unsigned) * words, st));
-          bfs_pull_first_list_kernel<256, 4><<<sms * 8, 256, 0, st>>>(
-              V, sc.first_nb.ptr, sc.unv[unv_cur].ptr, sc.counts.ptr + 4 + unv_cur, sc.visited.ptr, in_frontier,
-              nbm, dist, level + 1, ca, sc.counts.ptr + 2, sc.retry.ptr, sc.counts.ptr + 6, sc.unv[o].ptr,
-              sc.counts.ptr + 4 + o);
-          unv_cur = o;
-        }
-        bfs_pull_rest_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
-            in_g, sc.retry.ptr, sc.counts.ptr + 6, sc.visited.ptr, in_frontier, nbm, dist, level + 1, cb,
-            sc.counts.ptr + 2, sc.unv[unv_cur].ptr, sc.counts.ptr + 4 + unv_cur);
+        bfs_pull_first_kernel<256, 4><<<sms * 8, 256, 0, st>>>(V, sc.first_nb.ptr, sc.visited.ptr, in_frontier,
+                                                               bitmap_word_sink_t{nbm}, sc.retry_map.ptr, dist,
+                                                               level + 1, ca, sc.counts.ptr + 2);
+        bfs_pull_rest_kernel<256, 32, 8><<<sms * 6, 256, 0, st>>>(in_g, sc.retry_map.ptr, sc.visited.ptr, in_frontier,
+                                                                  nbm, dist, level + 1, cb, sc.counts.ptr + 2);
         ws.launches += 1;
       } else if (!unv_valid) {  // first pull level of a run of pull levels: sweep every visited word
         B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));

@@ -167,6 +167,7 @@ struct workspace_t {
   cudaStream_t stream = nullptr;
   dbuf_t<ctrl_t> ctrl;                    // ring of control blocks
   dbuf_t<int> hubs;                       // hub (CTA-bin) row list
+  dbuf_t<unsigned long long> hub_slabs;   // slab table of the hub rows (16 bytes per slab: advance.cuh hub_slab_t)
   dbuf_t<int> scanned;                    // degree scan for merge_path
   dbuf_t<int> tile_rows;                  // merge_path tile -> first row
   dbuf_t<unsigned long long> tile_state;  // look-back status words

@@ -40,7 +40,7 @@ __device__ __forceinline__ float atomic_min_float(float* addr, float value) {
 }
 
 struct sssp_relax_op {
-  static constexpr bool kVariants = true;  // experimental merge_path variants (advance_launch_t::variant)
+  static constexpr int kMergePathKernel = 4;  // warp-private spans, 8 chunks in flight (advance.cuh)
   float* dist;
   int* stamp;
   int iteration;
@@ -238,190 +238,6 @@ inline int sssp_run(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, in
     for (int l = 0; l < iteration && l < 64; ++l)
       cudaEventElapsedTime(&(*levels)[l].kernel_ms, sc.ev[2 * l], sc.ev[2 * l + 1]);
   return iteration;
-}
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (off by default, B2G_SSSP_DELTA=<delta> selects it in b2g_sssp): near / far schedule.
-// Same relaxations, same atomics, same least fixed point -- only the ORDER changes: vertices are
-// expanded bucket by bucket of width delta (Bellman-Ford inside a bucket), so a vertex is rarely
-// expanded with a distance that is lowered again later.  Host model of the work saved:
-// profiles/micro/sssp_work_model.py (frontier Bellman-Ford relaxes ~2.5x the reached edges,
-// delta = 8 about 1.45x).  No far pile is kept: a vertex whose distance lies at or above the
-// current threshold has, by construction, never been expanded at that distance, so the next
-// bucket is simply { v : lo <= dist[v] < hi }, selected by one pass over dist[].
-// ---------------------------------------------------------------------------------------------
-struct sssp_near_far_op {
-  float* dist;
-  int* stamp;
-  int iteration;
-  float threshold;  // candidates at or above it are recorded in dist[] but not queued
-  __device__ __forceinline__ float prefetch(int dst) const { return ld_relaxed(dist + dst); }
-  __device__ __forceinline__ bool commit(int src, int dst, int, float w, float current) const {
-    float nd = __fadd_rn(ld_relaxed(dist + src), w);
-    if (!(nd < current))
-      return false;
-    float old = atomic_min_float(dist + dst, nd);
-    if (!(nd < old) || !(nd < threshold))
-      return false;
-    return atomicExch(stamp + dst, iteration) != iteration;
-  }
-  __device__ __forceinline__ bool operator()(int src, int dst, int e, float w) const {
-    return commit(src, dst, e, w, prefetch(dst));
-  }
-};
-
-/// near = { v : lo <= dist[v] < hi } (ballot-compacted append), plus the smallest distance >= hi
-static __global__ void sssp_select_bucket_kernel(const float* __restrict__ dist, const int* __restrict__ ro,
-                                                 int n_vertices, float lo, float hi, int* out, int* out_count,
-                                                 unsigned long long* deg_sum, unsigned* min_far_bits) {
-  const int lane = lane_id();
-  unsigned long long ds = 0;
-  unsigned far_min = 0x7f7fffffu;  // bits of FLT_MAX
-  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n_vertices;
-       base += gridDim.x * blockDim.x) {
-    const int v = base + lane;
-    bool take = false;
-    if (v < n_vertices) {
-      const float d = dist[v];
-      take = d >= lo && d < hi;
-      if (d >= hi && d < FLT_MAX)
-        far_min = min(far_min, __float_as_uint(d));  // non-negative floats order like their bits
-      if (take)
-        ds += static_cast<unsigned>(ro[v + 1] - ro[v]);
-    }
-    const unsigned m = __ballot_sync(kFull, take);
-    if (m) {
-      int at = 0;
-      if (lane == 0)
-        at = atomicAdd(out_count, __popc(m));
-      at = __shfl_sync(kFull, at, 0);
-      if (take)
-        out[at + __popc(m & lanemask_lt())] = v;
-    }
-  }
-  ds = warp_sum(ds);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    far_min = min(far_min, __shfl_xor_sync(kFull, far_min, o));
-  if (lane == 0) {
-    if (ds)
-      atomicAdd(deg_sum, ds);
-    if (far_min != 0x7f7fffffu)
-      atomicMin(min_far_bits, far_min);
-  }
-}
-
-static __global__ void sssp_bucket_feedback_kernel(const int* count, const unsigned long long* deg_sum,
-                                                   const unsigned* min_far_bits, sssp_bucket_report_t* rep,
-                                                   int seq) {
-  rep->count = *count;
-  rep->deg_sum = *deg_sum;
-  rep->min_far_bits = *min_far_bits;
-  __threadfence_system();
-  rep->seq = seq;
-}
-
-inline int iteration_count(const std::vector<sssp_level_stat_t>* levels) {
-  return levels ? static_cast<int>(levels->size()) : 0;
-}
-
-/// Near/far SSSP for non-negative weights.  Returns the number of advance iterations.
-inline int sssp_run_near_far(workspace_t& ws, sssp_scratch_t& sc, const csr_view_t& g, int source, float* dist,
-                             const advance_launch_t& cfg, float delta,
-                             std::vector<sssp_level_stat_t>* levels = nullptr) {
-  const int V = g.n_vertices;
-  const int sms = device_info_t::get().sm_count;
-  sc.ensure(V);
-  sc.bucket.ensure(4);
-  if (!sc.h_bucket) {
-    B2G_CHECK(cudaMallocHost(&sc.h_bucket, sizeof(sssp_bucket_report_t)));
-    sc.h_bucket->seq = 0;
-  }
-  unsigned long long* bucket_scratch = sc.bucket.ptr;
-  sssp_bucket_report_t* h_rep = sc.h_bucket;
-  cudaStream_t st = ws.stream;
-  auto finish = [&]() {
-    if (levels)
-      for (int l = 0; l < iteration_count(levels) && l < 64; ++l)
-        cudaEventElapsedTime(&(*levels)[l].kernel_ms, sc.ev[2 * l], sc.ev[2 * l + 1]);
-  };
-  sssp_reset_kernel<<<sms * 8, 256, 0, st>>>(dist, sc.stamp.ptr, V, source, sc.q[0].ptr, sc.counts.ptr);
-  ws.launches += 1;
-  int cur = 0, iteration = 0;
-  long long n_f = 1;
-  unsigned long long m_f = 0;
-  float hi = delta;  // current bucket = [hi - delta, hi); the source (distance 0) is in the first one
-  for (;;) {
-    while (n_f > 0) {  // Bellman-Ford inside the bucket
-      const int nxt = cur ^ 1;
-      B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
-      sssp_near_far_op op{dist, sc.stamp.ptr, iteration, hi};
-      ctrl_t* c = nullptr;
-      if (iteration < 64)
-        B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration], st));
-      advance_launch_t lcfg = cfg;
-      lcfg.avg_degree = (m_f > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
-      if (m_f == 0) {
-        lcfg.lb = lb_t::block_mapped;  // degrees unknown (the source)
-      } else if (lcfg.lb == lb_t::merge_path && static_cast<long long>(m_f) < cfg.mid_frontier_edges) {
-        lcfg.lb = lb_t::block_mapped;
-      } else if (static_cast<long long>(m_f) < cfg.small_frontier_edges) {
-        lcfg.lb = lb_t::block_mapped;
-        lcfg.hub_threshold = 1 << 30;
-      }
-      launch_advance<advance_output_t::vertices, true, true>(
-          ws, g, sc.q[cur].ptr, sc.counts.ptr + cur, static_cast<int>(n_f < V ? n_f : V), sc.q[nxt].ptr,
-          sc.counts.ptr + nxt, V, op, lcfg, &c);
-      if (iteration < 64)
-        B2G_CHECK(cudaEventRecord(sc.ev[2 * iteration + 1], st));
-      sssp_feedback_kernel<<<1, 1, 0, st>>>(sc.counts.ptr + nxt, c, sc.h_fb, ++sc.seq);
-      ws.launches += 1;
-      wait_for_sequence(&sc.h_fb->seq, sc.seq, st);
-      if (sc.h_fb->overflow)
-        throw std::runtime_error("sssp: output frontier overflow");
-      if (levels)
-        levels->push_back({static_cast<int>(n_f), sc.h_fb->edges});
-      n_f = sc.h_fb->count;
-      m_f = sc.h_fb->deg_sum;
-      cur = nxt;
-      ++iteration;
-    }
-    // bucket exhausted: the next one is [hi, hi + delta), or starts at the smallest remaining distance
-    float lo = hi;
-    for (int attempt = 0; attempt < 2 && n_f == 0; ++attempt) {
-      B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + cur, 0, sizeof(int), st));
-      B2G_CHECK(cudaMemsetAsync(bucket_scratch, 0, sizeof(unsigned long long), st));
-      B2G_CHECK(cudaMemsetAsync(bucket_scratch + 1, 0xff, sizeof(unsigned long long), st));  // above any finite bits
-      float up = lo + delta;
-      if (!(up > lo))  // delta vanishes next to a huge distance: take the next representable value
-        up = nextafterf(lo, FLT_MAX);
-      sssp_select_bucket_kernel<<<sms * 8, 256, 0, st>>>(
-          dist, g.row_offsets, V, lo, up, sc.q[cur].ptr, sc.counts.ptr + cur, bucket_scratch,
-          reinterpret_cast<unsigned*>(bucket_scratch + 1));
-      sssp_bucket_feedback_kernel<<<1, 1, 0, st>>>(sc.counts.ptr + cur, bucket_scratch,
-                                                   reinterpret_cast<const unsigned*>(bucket_scratch + 1),
-                                                   h_rep, ++sc.seq);
-      ws.launches += 2;
-      wait_for_sequence(&h_rep->seq, sc.seq, st);
-      n_f = h_rep->count;
-      m_f = h_rep->deg_sum;
-      hi = up;
-      if (n_f == 0) {
-        if (h_rep->min_far_bits >= 0x7f7fffffu) {
-          finish();
-          return iteration;  // nothing finite is left above the threshold: done
-        }
-        unsigned bits = h_rep->min_far_bits;
-        float next_lo;
-        memcpy(&next_lo, &bits, sizeof next_lo);
-        lo = next_lo;  // jump over the empty buckets
-      }
-    }
-    if (n_f == 0)
-      throw std::runtime_error("sssp near/far: bucket selection made no progress");
-    if (m_f == 0)
-      m_f = 1;  // selected vertices without out-edges: still one (empty) advance to drain the queue
-  }
 }
 
 }  // namespace b200

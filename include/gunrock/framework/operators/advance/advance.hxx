@@ -109,6 +109,7 @@ void execute(graph_t& G,
       error::throw_if_exception(total > 0x7fffffffull, "advance: the output frontier would exceed 2^31 entries");
       if (static_cast<std::size_t>(total) > want)
         want = static_cast<std::size_t>(total);
+      cfg.edges_upper_bound = static_cast<long long>(total);
     }
     if (output->get_capacity() < want)
       output->reserve(want);

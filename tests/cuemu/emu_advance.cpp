@@ -1,10 +1,9 @@
 // tests/cuemu/emu_advance.cpp -- TEST INFRASTRUCTURE: runs the advance kernels of include/gunrock/b200/advance.cuh
 // (kernel section only; generated header advance_kernels.gen.cuh, see tests/test_cuemu_kernels.py) under the CPU
 // emulator and checks every launch against a straightforward expansion of the same frontier:
-//   * merge_path_partition_kernel + advance_merge_path_kernel (the GPU-proven default, 2048- and 4096-edge tiles):
-//     validates the emulator itself and the 4096-edge-tile variant;
-//   * advance_warp_path_kernel: warp-private spans, 4 / 8 chunks in flight, with the on-chip copy of the visited
-//     map in one CTA and spread over clusters of 2 and 4 CTAs (distributed shared memory);
+//   * merge_path_partition_kernel + advance_merge_path_kernel (CTA tiles of 2048 edges; the kernel user lambdas get):
+//     also validates the emulator itself;
+//   * advance_warp_path_kernel: warp-private spans, 4 / 8 chunks in flight (the fused BFS / SSSP functors' default);
 //   * advance_binned_kernel + advance_hub_kernel ("block_mapped"; the hub kernel's cp.async.bulk + mbarrier staging is
 //     emulated as an immediate copy), advance_thread_mapped_kernel, advance_tail_kernel (several levels per launch);
 //   * both with the BFS claim functor (bitmap test-and-set) and the SSSP relax functor (needs the source id,
@@ -106,7 +105,7 @@ static frontier_case_t make_frontier(const graph_t& g, std::vector<int> ids) {
   return f;
 }
 
-enum class kind_t { cta2048, cta4096, warp4, warp8, warp8pf, snap1, snap2, snap4, snap1_full, snap4_full, binned, binned_plain_loads, thread };
+enum class kind_t { cta2048, warp4, warp8, binned, binned_plain_loads, thread };
 
 struct run_out_t {
   std::vector<int> out;
@@ -147,7 +146,6 @@ static run_out_t run_bfs(const graph_t& g, const frontier_case_t& f, const std::
   bfs_claim_op op{r.visited.data(), r.dist.data(), 5};
   constexpr auto kV = advance_input_t::vertices;
   constexpr auto kO = advance_output_t::vertices;
-  const int map_words = (g.V + 31) / 32;
   std::vector<int> rows, hubs(static_cast<size_t>(g.V) + 16, -1);
   if (kind == kind_t::thread) {
     cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_thread_mapped_kernel<256, kV, kO, true, false>(p, op); });
@@ -160,71 +158,27 @@ static run_out_t run_bfs(const graph_t& g, const frontier_case_t& f, const std::
     p.tma_ok = kind == kind_t::binned && (reinterpret_cast<uintptr_t>(g.ci.data()) & 15u) == 0;
     p.entries_per_ticket = 64;
     cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_binned_kernel<256, kV, kO, true, false>(p, op); });
+    std::vector<hub_slab_t> slabs(static_cast<size_t>(g.ro[g.V]) / 2048 + hubs.size() + 64);
+    p.hub_slabs = slabs.data();
+    p.hub_slab_capacity = static_cast<int>(slabs.size());
+    cuemu::launch(2, 64, 0, 1, [&] { advance_hub_table_kernel<2048>(p); });
     cuemu::launch(2, 256, 0, 1, [&] { advance_hub_kernel<256, 2048, kO, true, false>(p, op); });
-  } else if (kind == kind_t::cta2048 || kind == kind_t::cta4096) {
-    rows = kind == kind_t::cta2048 ? partition<2048>(f) : partition<4096>(f);
+  } else if (kind == kind_t::cta2048) {
+    rows = partition<2048>(f);
     p.tile_rows = rows.data();
-    if (kind == kind_t::cta2048)
-      cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_merge_path_kernel<256, 2048, kV, kO, true, false>(p, f.scanned.data(), op); });
-    else
-      cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_merge_path_kernel<256, 4096, kV, kO, true, false>(p, f.scanned.data(), op); });
+    cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_merge_path_kernel<256, 2048, kV, kO, true, false>(p, f.scanned.data(), op); });
   } else {
     rows = partition<256>(f);
     p.tile_rows = rows.data();
-    constexpr int kThreads = 64;  // two warps per CTA keep the thread count of a cluster manageable
+    constexpr int kThreads = 64;  // two warps per CTA
     constexpr int kWarpBytes = warp_path_ints<256, false>() * 4;
     const size_t stage = (kThreads / 32) * kWarpBytes;
-    auto snap_bits_for = [&](int k) {  // a copy that covers only part of the ids: both probe paths are taken
-      long long lines = 2LL * k;      // two 128-byte lines (2048 vertices) per CTA
-      return static_cast<int>(lines * 1024);
-    };
-    switch (kind) {
-      case kind_t::warp4:
-        cuemu::launch(grid_ctas, kThreads, stage, 1, [&] {
-          advance_warp_path_kernel<kThreads, 1, 256, 4, 0, kV, kO, true, false>(p, f.scanned.data(), 0, 0, op); });
-        break;
-      case kind_t::warp8:
-        cuemu::launch(grid_ctas, kThreads, stage, 1, [&] {
-          advance_warp_path_kernel<kThreads, 1, 256, 8, 0, kV, kO, true, false>(p, f.scanned.data(), 0, 0, op); });
-        break;
-      case kind_t::warp8pf:  // + the next span's row window prefetched during the walk
-        cuemu::launch(grid_ctas, kThreads, stage, 1, [&] {
-          advance_warp_path_kernel<kThreads, 1, 256, 8, 0, kV, kO, true, false, bfs_claim_op, true>(
-              p, f.scanned.data(), 0, 0, op); });
-        break;
-      case kind_t::snap1: {
-        const int bits = snap_bits_for(1);
-        cuemu::launch(grid_ctas, kThreads, stage + bits / 8, 1, [&] {
-          advance_warp_path_kernel<kThreads, 1, 256, 8, 1, kV, kO, true, false>(p, f.scanned.data(), bits, map_words, op); });
-        break;
-      }
-      case kind_t::snap2: {
-        const int bits = snap_bits_for(2);
-        cuemu::launch((grid_ctas + 1) / 2 * 2, kThreads, stage + bits / 8 / 2, 2, [&] {
-          advance_warp_path_kernel<kThreads, 1, 256, 8, 2, kV, kO, true, false>(p, f.scanned.data(), bits, map_words, op); });
-        break;
-      }
-      case kind_t::snap1_full:
-      case kind_t::snap4_full: {
-        // the launcher's shapes: 1024-thread CTAs (32 warps), 8 chunks in flight, a copy of 24 lines per CTA
-        constexpr int kFull = 1024;
-        const int k = kind == kind_t::snap1_full ? 1 : 4;
-        const int bits = 24 * 1024 * k;
-        const size_t smem = (kFull / 32) * kWarpBytes + static_cast<size_t>(bits) / 8 / k;
-        if (k == 1)
-          cuemu::launch(2, kFull, smem, 1, [&] {
-            advance_warp_path_kernel<kFull, 1, 256, 8, 1, kV, kO, true, false>(p, f.scanned.data(), bits, map_words, op); });
-        else
-          cuemu::launch(4, kFull, smem, 4, [&] {
-            advance_warp_path_kernel<kFull, 1, 256, 8, 4, kV, kO, true, false>(p, f.scanned.data(), bits, map_words, op); });
-        break;
-      }
-      default: {
-        const int bits = snap_bits_for(4);
-        cuemu::launch((grid_ctas + 3) / 4 * 4, kThreads, stage + bits / 8 / 4, 4, [&] {
-          advance_warp_path_kernel<kThreads, 1, 256, 8, 4, kV, kO, true, false>(p, f.scanned.data(), bits, map_words, op); });
-      }
-    }
+    if (kind == kind_t::warp4)
+      cuemu::launch(grid_ctas, kThreads, stage, 1, [&] {
+        advance_warp_path_kernel<kThreads, 1, 256, 4, kV, kO, true, false>(p, f.scanned.data(), op); });
+    else
+      cuemu::launch(grid_ctas, kThreads, stage, 1, [&] {
+        advance_warp_path_kernel<kThreads, 1, 256, 8, kV, kO, true, false>(p, f.scanned.data(), op); });
   }
   r.out.resize(out_count);
   return r;
@@ -298,7 +252,11 @@ static void run_and_check_limits(const graph_t& g, const frontier_case_t& f, con
       p.hub_capacity = which == 2 ? 2 : static_cast<int>(hubs.size());  // 2: the hub list overflows
       p.tma_ok = 1;
       cuemu::launch(2, 256, 0, 1, [&] { advance_binned_kernel<256, kV, kO, true, false>(p, op); });
-      cuemu::launch(2, 256, 0, 1, [&] { advance_hub_kernel<256, 2048, kO, true, false>(p, op); });
+      std::vector<hub_slab_t> slabs(static_cast<size_t>(g.ro[g.V]) / 2048 + hubs.size() + 64);
+    p.hub_slabs = slabs.data();
+    p.hub_slab_capacity = static_cast<int>(slabs.size());
+    cuemu::launch(2, 64, 0, 1, [&] { advance_hub_table_kernel<2048>(p); });
+    cuemu::launch(2, 256, 0, 1, [&] { advance_hub_kernel<256, 2048, kO, true, false>(p, op); });
     }
     if (which == 2) {  // nothing may be lost when the hub list is full
       run_out_t r;
@@ -349,10 +307,10 @@ static void run_and_check_sssp(const graph_t& g, const frontier_case_t& f, int m
     constexpr int kWarpBytes = warp_path_ints<256, true>() * 4;
     if (grid_ctas % 2)
       cuemu::launch(grid_ctas, 64, 2 * kWarpBytes, 1, [&] {
-        advance_warp_path_kernel<64, 1, 256, 4, 0, kV, kO, true, true>(p, f.scanned.data(), 0, 0, op); });
-    else  // with the row-window prefetch (source ids travel with the prefetched rows)
+        advance_warp_path_kernel<64, 1, 256, 4, kV, kO, true, true>(p, f.scanned.data(), op); });
+    else  // 8 chunks in flight: what the SSSP functor runs by default
       cuemu::launch(grid_ctas, 64, 2 * kWarpBytes, 1, [&] {
-        advance_warp_path_kernel<64, 1, 256, 4, 0, kV, kO, true, true, sssp_relax_op, true>(p, f.scanned.data(), 0, 0, op); });
+        advance_warp_path_kernel<64, 1, 256, 8, kV, kO, true, true>(p, f.scanned.data(), op); });
   } else if (mode == 2) {  // block_mapped: hub rows staged with TWO bulk copies per slab (indices + weights)
     std::vector<int> hubs(static_cast<size_t>(g.V) + 16, -1);
     p.hub_threshold = 64;
@@ -361,6 +319,10 @@ static void run_and_check_sssp(const graph_t& g, const frontier_case_t& f, int m
     p.tma_ok = (reinterpret_cast<uintptr_t>(g.ci.data()) & 15u) == 0 && (reinterpret_cast<uintptr_t>(g.w.data()) & 15u) == 0;
     p.entries_per_ticket = 128;
     cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_binned_kernel<256, kV, kO, true, true>(p, op); });
+    std::vector<hub_slab_t> slabs(static_cast<size_t>(g.ro[g.V]) / 2048 + hubs.size() + 64);
+    p.hub_slabs = slabs.data();
+    p.hub_slab_capacity = static_cast<int>(slabs.size());
+    cuemu::launch(2, 64, 0, 1, [&] { advance_hub_table_kernel<2048>(p); });
     cuemu::launch(2, 256, 0, 1, [&] { advance_hub_kernel<256, 2048, kO, true, true>(p, op); });
   } else {
     rows = partition<2048>(f);
@@ -423,7 +385,7 @@ static void run_and_check_tail(const graph_t& g, int start, int max_levels) {
 }
 
 /// A whole traversal: the level loop of the enactor on the host (degree scan + partition + advance per level),
-/// the kernels under emulation, the visited map and -- for the snapshot kinds -- its on-chip copies evolving
+/// the kernels under emulation, the visited map evolving
 /// from level to level.  Depths must equal a plain BFS.
 static void run_and_check_whole_bfs(const graph_t& g, int source, kind_t kind, const char* name) {
   std::vector<unsigned> visited((g.V + 31) / 32 + 4, 0u);
@@ -496,127 +458,6 @@ static void run_and_check_dense_frontier(std::mt19937& rng) {
   std::printf("dense frontier kernels ok\n");
 }
 
-/// Bucket selection of the experimental near/far SSSP schedule (sssp.cuh).
-static void run_and_check_bucket_select(const graph_t& g, std::mt19937& rng) {
-  std::vector<float> dist(g.V);
-  for (auto& d : dist) {
-    unsigned r = rng() % 100;
-    d = r < 10 ? 3.402823466e+38f : static_cast<float>(rng() % 4000) * 0.25f;  // some unreachable
-  }
-  for (auto [lo, hi] : {std::pair<float, float>{0.0f, 8.0f}, {8.0f, 16.0f}, {990.0f, 1000.25f}, {5000.0f, 5008.0f}}) {
-    std::vector<int> out(static_cast<size_t>(g.V) + 8, -1);
-    int out_count = 0;
-    unsigned long long deg_sum = 0;
-    unsigned min_far = 0xffffffffu;
-    cuemu::launch(3, 64, 0, 1, [&] {
-      sssp_select_bucket_kernel(dist.data(), g.ro.data(), g.V, lo, hi, out.data(), &out_count, &deg_sum, &min_far); });
-    std::set<int> expect;
-    unsigned long long eds = 0;
-    float far = 3.402823466e+38f;
-    for (int v = 0; v < g.V; ++v) {
-      if (dist[v] >= lo && dist[v] < hi) {
-        expect.insert(v);
-        eds += static_cast<unsigned>(g.ro[v + 1] - g.ro[v]);
-      }
-      if (dist[v] >= hi && dist[v] < 3.402823466e+38f)
-        far = std::min(far, dist[v]);
-    }
-    out.resize(out_count);
-    std::sort(out.begin(), out.end());
-    CHECK(out == std::vector<int>(expect.begin(), expect.end()));
-    CHECK(deg_sum == eds);
-    unsigned far_bits;
-    std::memcpy(&far_bits, &far, 4);
-    CHECK(far == 3.402823466e+38f ? min_far >= 0x7f7fffffu : min_far == far_bits);
-  }
-  std::printf("near/far bucket selection ok\n");
-}
-
-/// The near/far SSSP schedule end to end: the level loop of sssp_run_near_far (sssp.cuh) restated on the host, its
-/// kernels and functor (sssp_near_far_op, sssp_select_bucket_kernel, merge_path advance) under emulation; the
-/// distances must be those of Dijkstra's algorithm in fp32, bit for bit.
-static void run_and_check_near_far(const graph_t& g, int source, float delta) {
-  std::vector<float> dist(g.V, 3.402823466e+38f);
-  std::vector<int> stamp(g.V, -1), q[2] = {std::vector<int>(g.V + 64), std::vector<int>(g.V + 64)};
-  dist[source] = 0.0f;
-  q[0][0] = source;
-  int cur = 0, iteration = 0, n_f = 1;
-  float hi = delta;
-  unsigned long long relaxed = 0;
-  for (;;) {
-    while (n_f > 0) {
-      const frontier_case_t f = make_frontier(g, std::vector<int>(q[cur].begin(), q[cur].begin() + n_f));
-      int out_count = 0;
-      ctrl_t ctrl;
-      std::memset(&ctrl, 0, sizeof ctrl);
-      advance_params_t p;
-      p.g = g.view();
-      p.in = f.in.data();
-      p.in_count = &n_f;
-      p.out = q[cur ^ 1].data();
-      p.out_count = &out_count;
-      p.out_capacity = static_cast<int>(q[cur ^ 1].size());
-      p.ctrl = &ctrl;
-      p.row_base = f.row_base.data();
-      sssp_near_far_op op{dist.data(), stamp.data(), iteration, hi};
-      std::vector<int> rows = partition<2048>(f);
-      p.tile_rows = rows.data();
-      cuemu::launch(2, 256, 0, 1, [&] {
-        advance_merge_path_kernel<256, 2048, advance_input_t::vertices, advance_output_t::vertices, true, true>(
-            p, f.scanned.data(), op); });
-      relaxed += ctrl.edges;
-      n_f = out_count;
-      cur ^= 1;
-      ++iteration;
-    }
-    float lo = hi;
-    for (int attempt = 0; attempt < 2 && n_f == 0; ++attempt) {
-      float up = lo + delta;
-      if (!(up > lo))
-        up = std::nextafterf(lo, 3.402823466e+38f);
-      int count = 0;
-      unsigned long long deg_sum = 0;
-      unsigned min_far = 0xffffffffu;
-      cuemu::launch(2, 64, 0, 1, [&] {
-        sssp_select_bucket_kernel(dist.data(), g.ro.data(), g.V, lo, up, q[cur].data(), &count, &deg_sum, &min_far); });
-      n_f = count;
-      hi = up;
-      if (n_f == 0) {
-        if (min_far >= 0x7f7fffffu)
-          goto done;
-        std::memcpy(&lo, &min_far, 4);
-      }
-    }
-    CHECK(n_f > 0);
-    if (n_f == 0)
-      break;
-  }
-done:
-  // Dijkstra in fp32 (the least fixed point of d[v] = min fl(d[u] + w))
-  std::vector<float> ref(g.V, 3.402823466e+38f);
-  std::multimap<float, int> heap{{0.0f, source}};
-  ref[source] = 0.0f;
-  while (!heap.empty()) {
-    auto [d, v] = *heap.begin();
-    heap.erase(heap.begin());
-    if (d > ref[v])
-      continue;
-    for (int e = g.ro[v]; e < g.ro[v + 1]; ++e) {
-      float nd = d + g.w[e];
-      if (nd < ref[g.ci[e]]) {
-        ref[g.ci[e]] = nd;
-        heap.insert({nd, g.ci[e]});
-      }
-    }
-  }
-  CHECK(std::memcmp(ref.data(), dist.data(), sizeof(float) * g.V) == 0);
-  unsigned long long reached_edges = 0;
-  for (int v = 0; v < g.V; ++v)
-    if (ref[v] < 3.402823466e+38f)
-      reached_edges += static_cast<unsigned>(g.ro[v + 1] - g.ro[v]);
-  std::printf("near/far delta %.1f: %d advance iterations, %.2f relaxations per reached edge\n", delta, iteration,
-              static_cast<double>(relaxed) / static_cast<double>(reached_edges));
-}
 
 int main(int argc, char** argv) {
   std::mt19937 rng(argc > 1 ? std::atoi(argv[1]) : 1);
@@ -645,9 +486,7 @@ int main(int argc, char** argv) {
   std::iota(everyone.begin(), everyone.end(), 0);
   frontiers.push_back(everyone);  // every row, the isolated ones included: many rows per span, many spans
   const struct { kind_t k; const char* name; int grid; } kinds[] = {
-      {kind_t::cta2048, "cta2048", 3}, {kind_t::cta4096, "cta4096", 2}, {kind_t::warp4, "warp4", 3},
-      {kind_t::warp8, "warp8", 2},     {kind_t::warp8pf, "warp8pf", 3}, {kind_t::snap1, "snap1", 3},     {kind_t::snap2, "snap2", 4},
-      {kind_t::snap4, "snap4", 4},     {kind_t::snap1_full, "snap1-1024", 2}, {kind_t::snap4_full, "snap4-1024", 4},
+      {kind_t::cta2048, "cta2048", 3}, {kind_t::warp4, "warp4", 3}, {kind_t::warp8, "warp8", 2},
       {kind_t::binned, "binned", 3},   {kind_t::binned_plain_loads, "binned-ld", 2},
       {kind_t::thread, "thread", 2}};
   for (auto& ids : frontiers) {
@@ -668,14 +507,10 @@ int main(int argc, char** argv) {
     run_and_check_sssp(g, f, 2, 2);
   }
   for (auto& k : kinds)
-    if (k.k == kind_t::cta2048 || k.k == kind_t::warp8 || k.k == kind_t::warp8pf || k.k == kind_t::snap1 || k.k == kind_t::snap4 ||
-        k.k == kind_t::snap4_full)
+    if (k.k == kind_t::cta2048 || k.k == kind_t::warp4 || k.k == kind_t::warp8)
       run_and_check_whole_bfs(g, 0, k.k, k.name);
-  run_and_check_whole_bfs(g, g.V - 2, kind_t::snap2, "snap2");
-  for (float delta : {4.0f, 16.5f, 1000.0f})
-    run_and_check_near_far(g, 0, delta);
+  run_and_check_whole_bfs(g, g.V - 2, kind_t::warp4, "warp4");
   run_and_check_dense_frontier(rng);
-  run_and_check_bucket_select(g, rng);
   run_and_check_tail(g, 0, 2);
   run_and_check_tail(g, g.V - 2, 16);
   if (failures == 0)

@@ -264,41 +264,15 @@ static void check_bottom_up(std::mt19937& rng) {
     ok = ok && (((visited[v >> 5] >> (v & 31)) & 1u) == (f || ref[v] != INT_MAX || adj[v].empty()));
   }
   CHECK(ok);
-  {  // the same level through the experimental route: list the unvisited vertices first, then the list kernel
-    std::vector<unsigned> visited_b(words + 4, 0u), nbm_b(words + 4, 0u);
-    std::vector<int> dist_b(V);
-    for (int v = 0; v < V; ++v) {
-      dist_b[v] = ref[v];
-      if (ref[v] != INT_MAX || adj[v].empty())
-        visited_b[v >> 5] |= 1u << (v & 31);
-    }
-    std::vector<int> todo(V + 64, -1), left(V + 64, -1);
-    int todo_count = 0, left_count = 0, found_b = 0;
-    cuemu::launch(3, 64, 0, 1, [&] { bfs_unvisited_list_kernel(visited_b.data(), V, todo.data(), &todo_count); });
-    std::set<int> want_todo(found.begin(), found.end());
-    want_todo.insert(still.begin(), still.end());
-    CHECK(std::set<int>(todo.begin(), todo.begin() + todo_count) == want_todo && todo_count == static_cast<int>(want_todo.size()));
-    ctrl_t ctrl_b;
-    std::memset(&ctrl_b, 0, sizeof ctrl_b);
-    cuemu::launch(3, 256, 0, 1, [&] {
-      bfs_bottom_up_list_kernel<256, 8>(g, todo.data(), &todo_count, visited_b.data(), fbm.data(), nbm_b.data(),
-                                        dist_b.data(), 3, &ctrl_b, &found_b, left.data(), &left_count); });
-    CHECK(found_b == next_count && dist_b == dist && std::set<int>(left.begin(), left.begin() + left_count) == still);
-    bool same_maps = true;  // (bits past V differ: the reset kernel pre-marks them, this route never looks at them)
-    for (int v = 0; v < V; ++v)
-      same_maps = same_maps && (((nbm_b[v >> 5] ^ nbm[v >> 5]) >> (v & 31)) & 1u) == 0 &&
-                  (((visited_b[v >> 5] ^ visited[v >> 5]) >> (v & 31)) & 1u) == 0;
-    CHECK(same_maps);
-  }
-  {  // the same two levels through the second-generation pull kernels: K1 (one probe from first_nb; sweep form,
-     // then list form) + K2 (full search from the second in-neighbour for K1's misses)
+  {  // the same two levels through the second-generation pull kernels: K1 (one probe from first_nb per
+     // unvisited vertex, words out) + K2 (full search from the second in-neighbour for K1's retry map)
     std::vector<int> first_nb(V + 64, 12345);
     cuemu::launch(3, 64, 0, 1, [&] { bfs_first_neighbor_kernel(g, first_nb.data()); });
     bool fn_ok = true;
     for (int v = 0; v < V; ++v)
       fn_ok = fn_ok && first_nb[v] == (adj[v].empty() ? -1 : (adj[v][0] | (adj[v].size() == 1 ? kOnlyNeighbor : 0)));
     CHECK(fn_ok);
-    std::vector<unsigned> visited_c(words + 4, 0u), nbm_c(words + 4, 0xdeadbeefu);
+    std::vector<unsigned> visited_c(words + 4, 0u), nbm_c(words + 4, 0xdeadbeefu), retry_map(words + 4, 0xdeadbeefu);
     std::vector<int> dist_c(V);
     for (int v = 0; v < words * 32; ++v) {
       if (v < V)
@@ -306,17 +280,15 @@ static void check_bottom_up(std::mt19937& rng) {
       if (v >= V || ref[v] != INT_MAX || adj[v].empty())
         visited_c[v >> 5] |= 1u << (v & 31);
     }
-    std::vector<int> retry(V + 64, -1), u0(V + 64, -1), u1(V + 64, -1);
-    int retry_count = 0, u_count[2] = {0, 0}, found_c = 0;
+    int found_c = 0;
     ctrl_t ca, cb;
     std::memset(&ca, 0, sizeof ca);
     std::memset(&cb, 0, sizeof cb);
     const bitmap_frontier_t in_f{fbm.data()};
     cuemu::launch(3, 256, 0, 1, [&] {
-      bfs_pull_first_sweep_kernel<256, 4>(V, first_nb.data(), visited_c.data(), in_f, bitmap_word_sink_t{nbm_c.data()},
-                                          dist_c.data(), 3, &ca, &found_c, retry.data(), &retry_count, u0.data(),
-                                          &u_count[0]); });
-    // K1 alone: exactly the vertices whose FIRST in-neighbour is in the frontier; misses split by in-degree
+      bfs_pull_first_kernel<256, 4>(V, first_nb.data(), visited_c.data(), in_f, bitmap_word_sink_t{nbm_c.data()},
+                                    retry_map.data(), dist_c.data(), 3, &ca, &found_c); });
+    // K1 alone: exactly the vertices whose FIRST in-neighbour is in the frontier; misses with more to look at -> map
     std::set<int> k1_found, k1_retry, k1_single;
     for (int v = 0; v < V; ++v)
       if (ref[v] == INT_MAX && !adj[v].empty()) {
@@ -326,21 +298,23 @@ static void check_bottom_up(std::mt19937& rng) {
           (adj[v].size() == 1 ? k1_single : k1_retry).insert(v);
       }
     CHECK(found_c == static_cast<int>(k1_found.size()));
-    CHECK(std::set<int>(retry.begin(), retry.begin() + retry_count) == k1_retry && retry_count == static_cast<int>(k1_retry.size()));
-    CHECK(std::set<int>(u0.begin(), u0.begin() + u_count[0]) == k1_single);
-    CHECK(ca.edges == k1_found.size() + k1_retry.size() + k1_single.size());
+    bool maps_ok = true;
+    for (int v = 0; v < V; ++v)
+      maps_ok = maps_ok && (((retry_map[v >> 5] >> (v & 31)) & 1u) == (k1_retry.count(v) != 0)) &&
+                (((nbm_c[v >> 5] >> (v & 31)) & 1u) == (k1_found.count(v) != 0));
+    CHECK(maps_ok);
+    CHECK(ca.edges == k1_found.size() + k1_retry.size() + k1_single.size() && ca.hub_count == static_cast<int>(k1_retry.size()));
     cuemu::launch(3, 256, 0, 1, [&] {
-      bfs_pull_rest_kernel<256, 8>(g, retry.data(), &retry_count, visited_c.data(), in_f, nbm_c.data(), dist_c.data(), 3,
-                                   &cb, &found_c, u0.data(), &u_count[0]); });
+      bfs_pull_rest_kernel<256, 32, 8>(g, retry_map.data(), visited_c.data(), in_f, nbm_c.data(), dist_c.data(), 3, &cb,
+                                       &found_c); });
     CHECK(found_c == next_count && dist_c == dist);
-    CHECK(std::set<int>(u0.begin(), u0.begin() + u_count[0]) == still && u_count[0] == static_cast<int>(still.size()));
     bool same_maps = true;
     for (int v = 0; v < V; ++v)
       same_maps = same_maps && (((nbm_c[v >> 5] ^ nbm[v >> 5]) >> (v & 31)) & 1u) == 0 &&
                   (((visited_c[v >> 5] ^ visited[v >> 5]) >> (v & 31)) & 1u) == 0;
     CHECK(same_maps);
     CHECK(ca.edges + cb.edges <= ctrl.edges + static_cast<unsigned long long>(V));  // never more probes than the sweep (+ slack)
-    // next level, list form: frontier = the level-3 vertices (nbm_c), input = u0
+    // next level: frontier = the level-3 vertices (nbm_c)
     std::set<int> f2, s2;
     for (int v : still) {
       bool hit = false;
@@ -348,26 +322,24 @@ static void check_bottom_up(std::mt19937& rng) {
         hit = hit || found.count(u);
       (hit ? f2 : s2).insert(v);
     }
-    std::vector<unsigned> nbm_d(words + 4, 0u);
+    std::vector<unsigned> nbm_d(words + 4, 0xdeadbeefu);
     int found_d = 0;
-    retry_count = 0;
     std::memset(&ca, 0, sizeof ca);
     std::memset(&cb, 0, sizeof cb);
     const bitmap_frontier_t in_f2{nbm_c.data()};
     cuemu::launch(3, 256, 0, 1, [&] {
-      bfs_pull_first_list_kernel<256, 4>(V, first_nb.data(), u0.data(), &u_count[0], visited_c.data(), in_f2, nbm_d.data(),
-                                         dist_c.data(), 4, &ca, &found_d, retry.data(), &retry_count, u1.data(),
-                                         &u_count[1]); });
+      bfs_pull_first_kernel<256, 4>(V, first_nb.data(), visited_c.data(), in_f2, bitmap_word_sink_t{nbm_d.data()},
+                                    retry_map.data(), dist_c.data(), 4, &ca, &found_d); });
     cuemu::launch(3, 256, 0, 1, [&] {
-      bfs_pull_rest_kernel<256, 8>(g, retry.data(), &retry_count, visited_c.data(), in_f2, nbm_d.data(), dist_c.data(), 4,
-                                   &cb, &found_d, u1.data(), &u_count[1]); });
+      bfs_pull_rest_kernel<256, 32, 8>(g, retry_map.data(), visited_c.data(), in_f2, nbm_d.data(), dist_c.data(), 4, &cb,
+                                       &found_d); });
     bool ok2 = found_d == static_cast<int>(f2.size());
     for (int v = 0; v < V; ++v) {
       const bool f = f2.count(v) != 0;
       ok2 = ok2 && (((nbm_d[v >> 5] >> (v & 31)) & 1u) == f) && (dist_c[v] == (f ? 4 : (found.count(v) ? 3 : ref[v])));
+      ok2 = ok2 && (((visited_c[v >> 5] >> (v & 31)) & 1u) == (f || found.count(v) || ref[v] != INT_MAX || adj[v].empty()));
     }
     CHECK(ok2);
-    CHECK(std::set<int>(u1.begin(), u1.begin() + u_count[1]) == s2 && u_count[1] == static_cast<int>(s2.size()));
     CHECK(!f2.empty() && !s2.empty() && !k1_retry.empty() && !k1_single.empty());
   }
   std::set<int> listed(unv0.begin(), unv0.begin() + unv_count[0]);

@@ -1,7 +1,13 @@
-"""Experimental paths that are OFF by default and were written without GPU time left in round 1.
-They only run when B2G_RUN_EXPERIMENTAL=1 is set (first thing to do on a GPU box next round):
+"""The A/B switches the library keeps (all read from the environment, none needed in normal use):
 
-    B2G_RUN_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q
+  B2G_ADVANCE_VARIANT=0|1|4   which merge_path kernel serves the fused BFS / SSSP functors (default: the functor's
+                              own choice -- warp-private spans, advance.cuh op_merge_path_kernel)
+  B2G_BFS_PULL_LEGACY=1       the first-generation pull kernels of the direction-optimised BFS (one sweep / list
+                              kernel per level) instead of the first-in-neighbour pair K1 + K2 (bfs.cuh)
+
+Every choice must give the same bits.  (Round 1's other experiments -- on-chip copies of the visited map, 4096-edge
+tiles, span prefetch, near/far SSSP, list-first pull -- were measured at the start of round 2, lost, and are gone:
+profiles/r2_bench_matrix.md.)
 """
 import json
 import os
@@ -12,54 +18,10 @@ import pytest
 
 from conftest import ROOT
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B2G_RUN_EXPERIMENTAL") != "1", reason="experimental, opt-in")]
-
-WORKER = r"""
-import json, os, sys
-sys.path.insert(0, %r)
-import numpy as np
-import oracle
-import gunrock_b200 as gb
-res = {}
-for scale, ef, seed, mode in ((10, 8, 3, False), (14, 16, 0x5EED24, False), (15, 8, 9, True)):
-    ro, ci = oracle.rmat_csr(scale, ef, seed)
-    w = oracle.edge_weights(seed + 1, ro, ci, mode)
-    G = gb.graph_t.from_csr(ro, ci, w, symmetric=True)
-    deg = np.diff(ro)
-    for src in (int(deg.argmax()), int(np.flatnonzero(deg > 0)[-1])):
-        exp = oracle.sssp(ro, ci, w, src)
-        for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
-            d = np.empty(G.n_vertices, np.float32)
-            st = gb.sssp(G, src, d, options=gb.options_t(advance_load_balance=lb, hub_threshold=256))
-            res[f"s{scale}/src{src}/lb{lb}"] = [bool(np.array_equal(d.view(np.uint32), exp.view(np.uint32))),
-                                               st.iterations, int(st.edges_touched)]
-    G.close()
-print("RESULT " + json.dumps(res))
-"""
+pytestmark = [pytest.mark.gpu]
 
 
-@pytest.mark.parametrize("delta", ["4", "8", "16.5", "1000"])
-def test_sssp_near_far_schedule_is_bit_exact(built, delta):
-    """sssp_run_near_far (B2G_SSSP_DELTA): same least fixed point as the oracle, fewer relaxations than the
-    default schedule for small delta (the env var is read once per process, hence the subprocess)."""
-    out = {}
-    for d in (delta, ""):
-        env = dict(os.environ)
-        env.pop("B2G_SSSP_DELTA", None)
-        if d:
-            env["B2G_SSSP_DELTA"] = d
-        r = subprocess.run([sys.executable, "-c", WORKER % ROOT], capture_output=True, text=True, timeout=900, env=env)
-        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-        out[d] = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
-    assert all(v[0] for v in out[delta].values()), {k: v for k, v in out[delta].items() if not v[0]}
-    assert all(v[0] for v in out[""].values())
-    if float(delta) <= 8:
-        big = [k for k in out[delta] if k.startswith("s14") or k.startswith("s15")]
-        assert sum(out[delta][k][2] for k in big) < sum(out[""][k][2] for k in big)     # less work
-
-
-# ---- experimental merge_path kernels (B2G_ADVANCE_VARIANT, read on every call) ------------------------
+# ---- the merge_path kernels (B2G_ADVANCE_VARIANT: 0 CTA tiles, 1 / 4 warp-private spans; read on every call) ---
 @pytest.fixture
 def variant_env():
     old = os.environ.get("B2G_ADVANCE_VARIANT")
@@ -72,17 +34,17 @@ def variant_env():
 
 @pytest.fixture(scope="module")
 def level_graphs():
-    """Host CSRs shared by every variant (2^21 / 2^23 vertices: ids past the on-chip copies)."""
+    """Host CSRs shared by every kernel choice (up to 2^23 vertices)."""
     import oracle
     return [(scale, *oracle.rmat_csr(scale, ef, seed))
             for scale, ef, seed in ((5, 4, 1), (12, 8, 13), (16, 16, 5), (21, 2, 99), (23, 1, 7))]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 4])
 def test_merge_path_variants_one_level_exact(built, variant_env, level_graphs, variant):
     """One advance level with the BFS claim functor through b2g_advance_bfs, merge_path, for frontiers that
     stress the span staging: two hubs, every vertex (degree-0 rows included), duplicates, a single short
-    row, vertices beyond the on-chip copy of the visited map (variant 2: 1.27 M bits; 5 / 6: a cluster's 2x / 4x).  Each unvisited neighbour is claimed exactly once."""
+    row, high vertex ids.  Each unvisited neighbour is claimed exactly once."""
     import numpy as np
     import torch
     import oracle
@@ -130,10 +92,10 @@ def test_merge_path_variants_one_level_exact(built, variant_env, level_graphs, v
         G.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 4])
 def test_merge_path_variants_full_runs_bit_exact(built, variant_env, variant):
     """Whole BFS / SSSP runs at a size where the enactors really pick merge_path (frontier out-degree
-    above 2^20): depths / distances equal to the default kernels' bit for bit, and to the oracle."""
+    above 2^20): depths / distances equal to the functors' default kernels' bit for bit, and to the oracle."""
     import numpy as np
     import oracle
     import gunrock_b200 as gb
@@ -179,10 +141,14 @@ print("RESULT " + json.dumps(res))
 """
 
 
-def test_pull_levels_on_the_unvisited_list_from_the_first_one(built):
-    """B2G_BFS_PULL_LIST_FIRST: the first pull level lists the unvisited vertices (bfs_unvisited_list_kernel) and runs
-    the dense list kernel instead of the word sweep -- same depths (env read once per process: subprocess)."""
-    env = dict(os.environ, B2G_BFS_PULL_LIST_FIRST="1")
+@pytest.mark.parametrize("legacy", [False, True])
+def test_pull_kernel_generations_give_the_same_depths(built, legacy):
+    """Direction-optimised and pull-only BFS with the first-in-neighbour kernels (default) and with the
+    first-generation sweep / list kernels (B2G_BFS_PULL_LEGACY=1; env read once per process: subprocess)."""
+    env = dict(os.environ)
+    env.pop("B2G_BFS_PULL_LEGACY", None)
+    if legacy:
+        env["B2G_BFS_PULL_LEGACY"] = "1"
     r = subprocess.run([sys.executable, "-c", DO_WORKER % ROOT], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])

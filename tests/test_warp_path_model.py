@@ -1,5 +1,5 @@
 """Executable model of the index arithmetic of advance_warp_path_kernel (include/gunrock/b200/advance.cuh,
-the experimental warp-private merge_path).  The kernel itself only runs on a GPU; what can be checked on
+the warp-private-span merge_path the fused BFS / SSSP functors run).  The kernel itself only runs on a GPU; what can be checked on
 the CPU is the part that is easy to get wrong by one: the span partition, the staging of the rows that
 overlap a span (live-row test, 16-bit relative starts, 33 sentinels) and the REDUX row-mask walk whose
 cursor starts at slot 0.  The model follows the kernel statement by statement with 32 explicit lanes and
@@ -125,126 +125,6 @@ def test_every_edge_of_the_frontier_is_walked_exactly_once(kind, kb):
             got += walk_span(scanned, row_base, n, total, span_rows, sp, kb)
         exp = [(i, int(row_base[i]) + j) for i in range(n) for j in range(int(deg[i]))]
         assert sorted(got) == exp
-
-
-@pytest.mark.parametrize("k_cluster", [1, 2, 4])
-def test_snapshot_interleave_is_consistent_between_fill_and_probe(k_cluster):
-    """snapshot_t::locate (probe side) and the kernel's fill loop (advance_warp_path_kernel) must agree on where
-    word `wi` of the visited map lives: CTA (wi / 32) % k, local word ((wi / 32) / k) * 32 + wi % 32."""
-    lines_per_cta = 5
-    snap_words_cta = lines_per_cta * 32
-    map_words = lines_per_cta * k_cluster * 32 - 40          # the map ends inside the last lines
-    slices = [dict() for _ in range(k_cluster)]
-    for rank in range(k_cluster):                            # fill, as each CTA does it
-        for li in range(snap_words_cta):
-            wi = ((((li >> 5) * k_cluster) + rank) << 5) | (li & 31)
-            slices[rank][li] = wi if wi < map_words else None
-    seen = set()
-    for v in range(0, map_words * 32, 7):                    # probe
-        wi, line = v >> 5, v >> 10
-        owner = 0 if k_cluster == 1 else line % k_cluster
-        local = ((line // k_cluster) << 5) | (wi & 31)
-        assert slices[owner][local] == wi
-        seen.add((owner, local))
-    assert len(seen) == len({v >> 5 for v in range(0, map_words * 32, 7)})
-
-
-# ---- protocol model of the on-chip visited copy (snapshot_t + bfs_claim_op::{prefetch,commit}_snap) --------
-class SnapshotModel:
-    """One cluster's copy of the first `bits` bits of the visited map, interleaved over k CTAs in 32-word lines."""
-
-    def __init__(self, visited_words, bits, k):
-        self.k, self.bits = k, bits
-        words_cta = bits // 32 // k
-        self.slices = [np.zeros(words_cta, np.uint32) for _ in range(k)]
-        for rank in range(k):                                   # the kernel's fill loop
-            for li in range(words_cta):
-                wi = ((((li >> 5) * k) + rank) << 5) | (li & 31)
-                self.slices[rank][li] = visited_words[wi] if wi < len(visited_words) else 0
-
-    def _locate(self, v):
-        wi, line = v >> 5, v >> 10
-        return (0 if self.k == 1 else line % self.k), ((line // self.k) << 5) | (wi & 31)
-
-    def covers(self, v):
-        return v < self.bits
-
-    def load(self, v):
-        o, li = self._locate(v)
-        return int(self.slices[o][li])
-
-    def merge(self, v, word):
-        o, li = self._locate(v)
-        self.slices[o][li] |= np.uint32(word)
-
-
-def claim_level_with_snapshots(ro, ci, frontier, visited, n_clusters, k, bits, kb, rng):
-    """One top-down level as the snapshot variants run it: spans dealt to clusters in random order, every
-    cluster probing through ITS OWN copy (taken at kernel start, never refreshed except by what its own edges
-    learn), tokens of a whole batch read before any of the batch's commits (two-phase protocol)."""
-    visited = visited.copy()
-    snaps = [SnapshotModel(visited, bits, k) for _ in range(n_clusters)]
-    edges = np.concatenate([ci[ro[v]:ro[v + 1]] for v in frontier]) if len(frontier) else np.empty(0, np.int64)
-    emitted, global_probes = [], 0
-    batches = [edges[i:i + 32 * kb] for i in range(0, len(edges), 32 * kb)]
-    for b in rng.permutation(len(batches)):
-        snap = snaps[rng.integers(n_clusters)]
-        toks = []
-        for dst in batches[b]:                                   # prefetch_snap
-            dst = int(dst)
-            bit = 1 << (dst & 31)
-            if snap.covers(dst) and (snap.load(dst) & bit):
-                toks.append(bit)
-            else:
-                toks.append(int(visited[dst >> 5]))
-                global_probes += 1
-        for dst, word in zip(batches[b], toks):                  # commit_snap
-            dst = int(dst)
-            bit = 1 << (dst & 31)
-            won = False
-            if not (word & bit):
-                old = int(visited[dst >> 5])                     # atomicOr returns the word as it was
-                visited[dst >> 5] |= np.uint32(bit)
-                won = not (old & bit)
-                word = old | bit
-                if won:
-                    emitted.append(dst)
-            if snap.covers(dst) and (won or word != bit):
-                snap.merge(dst, word)
-        for s in snaps:                                          # a copy never claims what the map does not hold
-            for rank in range(s.k):
-                for li in np.flatnonzero(s.slices[rank]):
-                    wi = ((((li >> 5) * s.k) + rank) << 5) | (li & 31)
-                    assert wi < len(visited) and not (int(s.slices[rank][li]) & ~int(visited[wi]))
-            break                                                # (checking one copy per batch keeps the test fast)
-    return visited, emitted, global_probes, len(edges)
-
-
-@pytest.mark.parametrize("k", [1, 2, 4])
-def test_snapshot_protocol_claims_every_vertex_exactly_once(k):
-    import oracle
-    ro, ci = oracle.rmat_csr(11, 8, 77)
-    V = len(ro) - 1
-    rng = np.random.default_rng(k)
-    words = (V + 31) // 32
-    bits = 1024 * k                       # covers only the low ids: probes beyond it take the global path
-    src = int(np.diff(ro).argmax())
-    visited = np.zeros(words, np.uint32)
-    visited[src >> 5] |= np.uint32(1 << (src & 31))
-    depth = np.full(V, -1)
-    depth[src] = 0
-    frontier, level, probes, edges = [src], 0, 0, 0
-    while frontier:
-        visited, emitted, gp, ne = claim_level_with_snapshots(ro, ci, frontier, visited, 3, k, bits, 4, rng)
-        assert len(emitted) == len(set(emitted))                 # nobody is claimed twice
-        for v in emitted:
-            assert depth[v] == -1
-            depth[v] = level + 1
-        probes, edges = probes + gp, edges + ne
-        frontier, level = emitted, level + 1
-    exp = oracle.bfs(ro, ci, src)
-    assert np.array_equal(np.where(depth < 0, 2**31 - 1, depth), exp)
-    assert probes < edges                                        # the copies did answer some probes
 
 
 def test_probe_line_locality_script_runs():
