@@ -80,23 +80,66 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    In-process NVML (pynvml) from a host thread every 10 ms: two cheap queries per sample.  The first version spawned
+    `nvidia-smi --query-gpu=<9 fields> -lms 100`; every one of its queries takes the driver's lock for milliseconds,
+    and one in ten timed runs of a few milliseconds came out twice as long (profiles/r2_bench_matrix.md).  nvidia-smi
+    remains the fallback when NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device_index):
+    def __init__(self, device_index, period_s=0.01):
         self.idx = device_index
+        self.period = period_s
         self.lines = []
         self.proc = None
+        self.samples = []          # (sm_mhz, reasons bit mask)
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.kind = None
 
     def start(self):
+        if os.environ.get("B2G_BENCH_NO_SAMPLER"):
+            return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.idx
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:   # NVML counts physical devices
+                try:
+                    idx = int(vis.split(",")[self.idx])
+                except (ValueError, IndexError):
+                    pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(self.period)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.kind = "nvml"
+            return
+        except Exception:
+            self.kind = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            self.kind = "nvidia-smi"
         except Exception:
             self.proc = None
 
@@ -105,8 +148,20 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.kind == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            reasons = set()
+            for _, mask in self.samples:
+                for bit, nm in names.items():
+                    if mask & bit:
+                        reasons.add(nm)
+            sm = [x for x, _ in self.samples]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(sm), "reasons": sorted(reasons), "source": "NVML, in-process, every 10 ms"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sampler"]}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -127,7 +182,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -507,8 +562,16 @@ def run_partitioned(args, wl, name, rank, world, local):
     def step_p2p():   # the kernels exchange frontiers over NVLink peer memory (bfs_p2p.cuh)
         return mg.bfs_rank_p2p(eng, src, total_edges, direction)
 
-    def step_nccl():  # NCCL all-to-all / all-gather / all-reduce between the per-rank kernels
-        return mg.bfs_rank_async(eng, comm, src, total_edges, direction=direction)
+    nccl_ready = [False]
+
+    def ensure_nccl():  # the C++ level loop's own communicator (ncclCommInitRank inside the library)
+        if not nccl_ready[0]:
+            mg.nccl_connect(eng, comm)
+            nccl_ready[0] = True
+
+    def step_nccl():  # ncclSend/Recv all-to-all, ncclAllGather, ncclAllReduce -- enqueued by the C++ level loop
+        ensure_nccl()
+        return mg.bfs_rank_nccl(eng, src, total_edges, direction)
 
     primary, other = (step_p2p, step_nccl) if args.exchange == "p2p" else (step_nccl, step_p2p)
 
@@ -599,7 +662,7 @@ def run_partitioned(args, wl, name, rank, world, local):
                 "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": wl["desc"],
                            "exchange": "kernels over NVLink peer memory (CUDA IPC windows)" if args.exchange == "p2p"
-                           else "NCCL all_to_all_single / all_gather / all_reduce",
+                           else "NCCL from the C++ level loop: grouped ncclSend/ncclRecv, ncclAllGather, ncclAllReduce",
                            "other_exchange": other_rec,
                            "numerator": "sum of out-degrees of the reached vertices (identical at every N)",
                            "vertices": G.n_global, "edges": total_edges, "source": src,
@@ -612,7 +675,7 @@ def run_partitioned(args, wl, name, rank, world, local):
                                         "per-rank column indices %.0f MB" % (total_edges * 4 / world / 1e6)},
                 "e2e": {"value": touched * args.steps / ms2 / 1e3, "unit": "MTEPS", "h2d_bytes_per_step": 4,
                         "d2h_bytes_per_step": G.n_local * 4, "ms_per_step": ms2 / args.steps},
-                "gpu_launches": (st.kernel_launches * args.steps) if args.exchange == "p2p" else None,
+                "gpu_launches": st.kernel_launches * args.steps,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": None, "peak_kind": peak_kind,
                              "kernel": "whole step per rank (advance + sweep + exchange)", "bytes_per_edge": 4},

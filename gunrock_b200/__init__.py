@@ -118,6 +118,8 @@ _SYMBOLS = [
     "b2g_part_sssp_apply_packed_async", "b2g_part_sssp_end_iteration_async", "b2g_part_sssp_distances",
     # peer-memory (NVLink) exchange
     "b2g_part_p2p_window_create", "b2g_part_p2p_attach", "b2g_part_p2p_detach", "b2g_part_bfs_p2p",
+    # NCCL exchange driven from C++
+    "b2g_nccl_unique_id", "b2g_part_nccl_init", "b2g_part_bfs_nccl", "b2g_part_nccl_finalize",
 ]
 
 

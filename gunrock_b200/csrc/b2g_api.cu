@@ -20,6 +20,7 @@
 #include <gunrock/b200/bfs.cuh>
 #include <gunrock/b200/bfs_partitioned.cuh>
 #include <gunrock/b200/bfs_p2p.cuh>
+#include <gunrock/b200/bfs_nccl.cuh>
 #include <gunrock/b200/filter.cuh>
 #include <gunrock/b200/pr.cuh>
 #include <gunrock/b200/sssp.cuh>
@@ -85,6 +86,7 @@ struct b2g_graph {
   part_pr_state_t ppr;
   part_sssp_state_t psssp;
   p2p_state_t p2p;
+  nccl_state_t nccl;
   dbuf_t<unsigned long long> part_deg;
   ctrl_t* part_ctrl = nullptr;
   int part_level_dir = 0;
@@ -1537,6 +1539,89 @@ int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2
         stats->level_edges[l] = rep.level_edges[l];
       }
     }
+    return 0;
+  });
+}
+
+// ---- NCCL exchange driven from C++: bfs_nccl.cuh ----------------------------------------------------
+int b2g_nccl_unique_id(unsigned char* id128) {
+  if (!id128)
+    return fail(B2G_ERR_INVALID, "b2g_nccl_unique_id: null buffer");
+  return guarded([&] {
+    const nccl_api_t& nccl = nccl_api_t::get();
+    ncclUniqueId id;
+    static_assert(sizeof(id) == 128, "ncclUniqueId size");
+    nccl.check(nccl.GetUniqueId(&id), "ncclGetUniqueId");
+    memcpy(id128, &id, 128);
+    return 0;
+  });
+}
+
+int b2g_part_nccl_init(b2g_graph_t* g, const unsigned char* id128, int nranks, int rank) {
+  if (!g || !g->partitioned || !id128 || nranks != g->pt.nparts || rank != g->pt.part)
+    return fail(B2G_ERR_INVALID, "b2g_part_nccl_init: the communicator's shape must be the partition's");
+  return guarded([&] {
+    const nccl_api_t& nccl = nccl_api_t::get();
+    auto& N = g->nccl;
+    if (!N.comm) {
+      ncclUniqueId id;
+      memcpy(&id, id128, 128);
+      nccl.check(nccl.CommInitRank(&N.comm, nranks, id, rank), "ncclCommInitRank");
+      N.owns_comm = true;
+    }
+    if (g->symmetric)
+      build_transpose(g);
+    N.prepare(g->ws, g->view, g->pt, g->part, g->part_deg, g->symmetric != 0);
+    B2G_CHECK(cudaDeviceSynchronize());
+    return 0;
+  });
+}
+
+int b2g_part_bfs_nccl(b2g_graph_t* g, int source, long long total_edges, const b2g_options_t* opt,
+                      b2g_stats_t* stats) {
+  if (!g || !g->partitioned || !g->nccl.comm || source < 0 || source >= g->pt.n_global)
+    return fail(B2G_ERR_INVALID, "b2g_part_bfs_nccl: call b2g_part_nccl_init first / bad source");
+  return guarded([&] {
+    b2g_options_t o = resolved(opt);
+    cudaStream_t st = g->pick_stream(&o);
+    part_bfs_config_t cfg;
+    cfg.advance = to_launch(o);
+    cfg.direction = o.advance_direction;
+    cfg.alpha = o.do_alpha > 0 ? o.do_alpha : 14.0;
+    cfg.beta = o.do_beta > 0 ? o.do_beta : 24.0;
+    csr_view_t in_view;  // row_offsets == nullptr: no pull
+    if (g->symmetric && o.advance_direction != B2G_DIR_FORWARD) {
+      build_transpose(g);
+      in_view = g->t_view;
+    }
+    const int launches0 = g->ws.launches;
+    part_bfs_report_t rep;
+    B2G_CHECK(cudaEventRecord(g->ev0, st));
+    part_bfs_nccl_run(g->ws, g->view, in_view, g->pt, g->part, g->part_deg, g->nccl, source, total_edges, cfg, &rep);
+    B2G_CHECK(cudaEventRecord(g->ev1, st));
+    B2G_CHECK(cudaStreamSynchronize(st));
+    if (stats) {
+      memset(stats, 0, sizeof *stats);
+      fill_stats_common(g, stats, launches0);
+      stats->iterations = stats->n_levels = rep.levels;
+      stats->edges_touched = rep.edges_total;
+      stats->vertices_touched = rep.verts_total;
+      for (int l = 0; l < rep.levels && l < 64; ++l) {
+        stats->level_direction[l] = rep.level_direction[l];
+        stats->level_frontier[l] = rep.level_frontier[l];
+        stats->level_edges[l] = rep.level_edges[l];
+      }
+    }
+    return 0;
+  });
+}
+
+int b2g_part_nccl_finalize(b2g_graph_t* g) {
+  if (!g)
+    return fail(B2G_ERR_INVALID, "null graph");
+  return guarded([&] {
+    B2G_CHECK(cudaStreamSynchronize(g->ws.stream));
+    g->nccl.release();
     return 0;
   });
 }

@@ -70,6 +70,10 @@ def _bind():
     L.b2g_part_p2p_attach.argtypes = [vp, vp, vp]
     L.b2g_part_p2p_detach.argtypes = [vp]
     L.b2g_part_bfs_p2p.argtypes = [vp, ip, C.c_longlong, C.POINTER(_Options), C.POINTER(_Stats)]
+    L.b2g_nccl_unique_id.argtypes = [vp]
+    L.b2g_part_nccl_init.argtypes = [vp, vp, ip, ip]
+    L.b2g_part_bfs_nccl.argtypes = [vp, ip, C.c_longlong, C.POINTER(_Options), C.POINTER(_Stats)]
+    L.b2g_part_nccl_finalize.argtypes = [vp]
     L._mg_bound = True
     return L
 
@@ -294,6 +298,29 @@ class CudaRankEngine:
         st = _Stats()
         _check(self.L.b2g_part_bfs_p2p(self.G._h, int(source), int(total_edges), C.byref(self.opt), C.byref(st)),
                "b2g_part_bfs_p2p")
+        n = min(st.n_levels, 64)
+        out = part_bfs_stats_t()
+        out.levels = st.n_levels
+        out.level_direction = list(st.level_direction[:n])
+        out.level_frontier = list(st.level_frontier[:n])
+        out.level_edges = list(st.level_edges[:n])
+        out.edges_touched = int(st.edges_touched)
+        out.elapsed_ms = float(st.elapsed_ms)
+        out.kernel_launches = int(st.kernel_launches)
+        return out
+
+    # ---- NCCL exchange with the level loop in C++ (bfs_nccl.cuh) ---------------------------------------------
+    def nccl_init(self, unique_id: bytes):
+        """COLLECTIVE: create this rank's NCCL communicator (ncclCommInitRank) from rank 0's unique id."""
+        assert len(unique_id) == 128
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        _check(self.L.b2g_part_nccl_init(self.G._h, buf, self.nparts, self.part), "b2g_part_nccl_init")
+
+    def bfs_nccl(self, source: int, total_edges: int):
+        """COLLECTIVE over the ranks.  Returns the run's stats (global level statistics)."""
+        st = _Stats()
+        _check(self.L.b2g_part_bfs_nccl(self.G._h, int(source), int(total_edges), C.byref(self.opt), C.byref(st)),
+               "b2g_part_bfs_nccl")
         n = min(st.n_levels, 64)
         out = part_bfs_stats_t()
         out.levels = st.n_levels
@@ -594,6 +621,30 @@ def bfs_rank_async(engine, comm, source: int, total_edges: int,
     if overflowed:
         return bfs_rank(engine, comm, source, total_edges, direction, alpha, beta)
     st.levels = level
+    return engine.distances(), st
+
+
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it, everybody receives it)."""
+    buf = (C.c_ubyte * 128)()
+    _check(_bind().b2g_nccl_unique_id(buf), "b2g_nccl_unique_id")
+    return bytes(buf)
+
+
+def nccl_connect(engine, comm) -> None:
+    """COLLECTIVE: give every rank's engine its own NCCL communicator for the C++ level loop.  The 128-byte id
+    travels over torch.distributed (plumbing); the communicator itself is created inside the library."""
+    ids = [nccl_unique_id() if comm.rank == 0 else None]
+    comm.dist.broadcast_object_list(ids, src=0, group=comm.group)
+    engine.nccl_init(ids[0])
+
+
+def bfs_rank_nccl(engine, source: int, total_edges: int, direction: int = advance_direction_t.optimized,
+                  alpha: float = 14.0, beta: float = 24.0):
+    """This rank's part of a partitioned BFS, level loop and NCCL exchange in C++ (`b2g_part_bfs_nccl`)."""
+    engine.opt.advance_direction = direction
+    engine.opt.do_alpha, engine.opt.do_beta = alpha, beta
+    st = engine.bfs_nccl(source, total_edges)
     return engine.distances(), st
 
 

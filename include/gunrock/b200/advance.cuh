@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, kWeights ? 4 : 5)
 advance_hub_kernel(advance_params_t p, Op op) {
   constexpr int kWarps = kThreads / 32;
   constexpr int kHB = kChunk / kThreads;  // slab edges per thread: all of them in flight at once
-  constexpr int kRange = 8;               // slabs per ticket
+  constexpr int kRange = 8;               // most slabs per ticket (ring slots)
   constexpr int kSlab = kChunk + 4;       // +4: slabs start at a 16-byte aligned column index
   static_assert(kChunk % 4 == 0 && kRange <= 32, "slab size must keep 16-byte granularity");
   __shared__ int s_emit[kWarps][kEmitCap];
@@ -433,6 +433,9 @@ advance_hub_kernel(advance_params_t p, Op op) {
   const int total = p.ctrl->pad[0];  // slabs in the table (advance_hub_table_kernel)
   if (total == 0)
     return;
+  // slabs per ticket: 8 when there is plenty of work, fewer when the table is short (one hub row of a BFS
+  // source is ~300 slabs: ranges of 8 would leave all but 36 CTAs idle); never below 2 (ring visibility below)
+  const int range = min(kRange, max(2, total / static_cast<int>(gridDim.x)));
 
   warp_emitter_t<kEmitCap, kDegSum> em;
   em.init(s_emit[warp], p.out, p.out_count, p.out_capacity, ro, p.ctrl);
@@ -446,12 +449,12 @@ advance_hub_kernel(advance_params_t p, Op op) {
   auto fetch_range = [&](int slot) {
     int base = 0;
     if (lane == 0)
-      base = atomicAdd(&p.ctrl->tile, kRange);
+      base = atomicAdd(&p.ctrl->tile, range);
     base = __shfl_sync(kFull, base, 0);
-    if (lane < kRange) {
+    if (lane < kRange) {  // slots past `range` hold end markers and are never reached
       hub_slab_t d;
       d.e0 = 0, d.cnt = -1, d.src = -1, d.pad = 0;
-      if (base + lane < total)
+      if (lane < range && base + lane < total)
         d = p.hub_slabs[base + lane];
       s_desc[slot][lane] = d;
     }
@@ -474,14 +477,14 @@ advance_hub_kernel(advance_params_t p, Op op) {
   int ring = 0, i = 0, buf = 0;
   for (;;) {
     if (i == 0 && warp == 0)
-      fetch_range(ring ^ 1);  // visible to everybody after this slab's closing barrier (kRange >= 2 of them follow)
+      fetch_range(ring ^ 1);  // visible to everybody after this slab's closing barrier (range >= 2 of them follow)
     const hub_slab_t d = s_desc[ring][i];
     if (d.cnt <= 0)
       break;  // uniform: every thread reads the same descriptor
     if (tma && threadIdx.x == 0) {
-      // the next slab's descriptor: in this range, or the first of the next one (fetched kRange - 1 barriers ago;
-      // with kRange == 1 it would not be visible yet)
-      const hub_slab_t nd = (i + 1 < kRange) ? s_desc[ring][i + 1] : s_desc[ring ^ 1][0];
+      // the next slab's descriptor: in this range, or the first of the next one (fetched range - 1 barriers ago;
+      // with a range of 1 it would not be visible yet)
+      const hub_slab_t nd = (i + 1 < range) ? s_desc[ring][i + 1] : s_desc[ring ^ 1][0];
       if (nd.cnt > 0)
         issue(nd, buf ^ 1);
     }
@@ -531,7 +534,7 @@ advance_hub_kernel(advance_params_t p, Op op) {
     }
     __syncthreads();  // all reads of s_idx[buf] / s_desc[ring][i] retire before they are refilled
     buf ^= 1;
-    if (++i == kRange) {
+    if (++i == range) {
       i = 0;
       ring ^= 1;
     }

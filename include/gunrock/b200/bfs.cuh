@@ -356,33 +356,37 @@ bfs_bottom_up_list_kernel(csr_view_t in, const int* __restrict__ unv_in,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Pull levels, second generation: the FIRST-IN-NEIGHBOUR shortcut.
+// Pull levels, second generation: the FIRST-IN-NEIGHBOURS shortcut.
 //
 // Measured on the bench graph (RMAT-26, profiles/r2_*): the first bottom-up level inspects 33 M column indices
-// for 27 M unvisited vertices -- almost every vertex finds its parent with its FIRST probe, because in-neighbour
-// lists are sorted and the low ids are the hubs.  Yet the sweep above pays, per vertex, a pair of row offsets
-// and a whole 32-byte sector of column indices fetched from HBM to use 4 bytes of it (1.37 GB of DRAM traffic
-// for 132 MB of useful indices), one dependent chain per lane.  So the graph carries one more per-vertex array,
-// built once like the transpose:
-//     first_nb[v] = v's first in-neighbour, bit 31 set when it is the ONLY one, -1 without in-edges
-// and a pull level becomes two kernels, both sweeps over 32-vertex words:
-//   K1 (bfs_pull_first_kernel): one probe per unvisited vertex straight from first_nb -- coalesced 4 B per
-//       vertex, kUnroll independent probes in flight per lane -- which settles ~75 % of the vertices without
-//       touching row offsets or column indices.  A miss with more in-neighbours to look at sets its bit in the
-//       `retry` map; a miss whose only in-neighbour that was cannot be found at this level and costs nothing more.
-//   K2 (bfs_pull_rest_kernel): the full search from the SECOND in-neighbour on, for the retry map's vertices.
+// for 27 M unvisited vertices -- almost every vertex finds its parent with its first or second probe, because
+// in-neighbour lists are sorted and the low ids are the hubs.  Yet the sweep above pays, per vertex, a pair of row
+// offsets and a whole 32-byte sector of column indices fetched from HBM to use 4 bytes of it (1.37 GB of DRAM
+// traffic for 132 MB of useful indices) at the DRAM's random-sector rate (~72 G sectors/s, 29 % of the copy
+// bandwidth), one dependent chain per lane.  So the graph carries one more per-vertex array, built once like
+// the transpose:
+//     head[v] = { first in-neighbour | -1,  second in-neighbour | -1, bit 31 set when there is no third }
+// and a pull level becomes two kernels over 32-vertex words of the visited map:
+//   K1 (bfs_pull_first_kernel): a warp expands the unvisited bits of 32 words into a queue in shared memory and
+//       walks it 32 vertices at a time: one 8-byte load of head[v] (ascending v: nearly sequential), one probe,
+//       a second probe for those that missed -- which settles ~95 % of the vertices that can be found at this
+//       level without touching row offsets or column indices.  Results are WORDS (next frontier, visited, and
+//       the vertices that need K2) assembled in shared memory and written with coalesced plain stores.
+//   K2 (bfs_pull_rest_kernel): the full search from the THIRD in-neighbour on, for the few vertices K1 marked.
 // Depths are those of the sweep above: a vertex is labelled at the first level at which ANY in-neighbour is
 // in the frontier; which neighbour is probed first does not matter.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kOnlyNeighbor = static_cast<int>(0x80000000u);
+constexpr int kNoMoreNeighbors = static_cast<int>(0x80000000u);
 
-static __global__ void bfs_first_neighbor_kernel(csr_view_t in, int* __restrict__ first_nb) {
+static __global__ void bfs_first_neighbor_kernel(csr_view_t in, int2* __restrict__ head) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < in.n_vertices; v += gridDim.x * blockDim.x) {
     const int s = in.row_offsets[v], e = in.row_offsets[v + 1];
-    int x = -1;
+    int2 h = make_int2(-1, -1);
     if (e > s)
-      x = in.column_indices[s] | (e - s == 1 ? kOnlyNeighbor : 0);
-    first_nb[v] = x;
+      h.x = in.column_indices[s];
+    if (e > s + 1)
+      h.y = in.column_indices[s + 1] | (e - s == 2 ? kNoMoreNeighbors : 0);
+    head[v] = h;
   }
 }
 
@@ -391,88 +395,96 @@ struct bitmap_frontier_t {
   const unsigned* bm;
   __device__ __forceinline__ bool operator()(int u) const { return bitmap_test(bm, u); }
 };
-/// where K1's sweep form puts the words of the next frontier (the partitioned variants store them elsewhere)
-struct bitmap_word_sink_t {
-  unsigned* next;
-  __device__ __forceinline__ void zero(int wi) const { next[wi] = 0; }  // lanes hold different words
-  __device__ __forceinline__ void word(int wi, unsigned v) const {      // warp-uniform word
-    if (lane_id() == 0)
-      next[wi] = v;
-  }
-};
 
 /**
- * @brief K1: one warp owns 32 consecutive words of the visited map per pass and settles kUnroll of them at a
- * time -- kUnroll coalesced loads of first_nb, then kUnroll frontier probes in flight per lane.  Everything it
- * produces is a WORD written with a plain store by one lane: the next-frontier word, the visited word, and the
- * word of vertices that need K2 (first in-neighbour not in the frontier, more in-neighbours to look at).  No
- * lists, no atomics: measured on RMAT-26 the list forms of these kernels ran at the DRAM's random-sector rate
- * (~72 G sectors/s, 29 % of the copy bandwidth) while this sweep reads first_nb sequentially.
+ * @brief K1 (see above).  `next` receives every word of the next frontier this kernel can decide (K2 ORs its
+ * finds in afterwards), `retry_map` the vertices K2 has to search.
  */
-template <int kThreads, int kUnroll, typename FrontierTest, typename Sink>
+template <int kThreads, typename FrontierTest>
 __global__ void __launch_bounds__(kThreads)
-bfs_pull_first_kernel(int n_vertices, const int* __restrict__ first_nb, unsigned* __restrict__ visited,
-                      FrontierTest in_frontier, Sink sink, unsigned* __restrict__ retry_map, int* dist,
-                      int next_level, ctrl_t* ctrl, int* next_count) {
-  const int lane = lane_id();
+bfs_pull_first_kernel(int n_vertices, const int2* __restrict__ head, unsigned* __restrict__ visited,
+                      FrontierTest in_frontier, unsigned* __restrict__ next, unsigned* __restrict__ retry_map,
+                      int* dist, int next_level, ctrl_t* ctrl, int* next_count) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ int s_q[kWarps][1024];
+  __shared__ unsigned s_found[kWarps][32], s_retry[kWarps][32];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  int* q = s_q[warp];
   const int words = (n_vertices + 31) / 32;
   const int warps = (gridDim.x * kThreads) >> 5;
   const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
-  unsigned probes = 0, found_cnt = 0, retry_cnt = 0;  // lane 0 only
+  unsigned probes = 0, found_cnt = 0, retry_cnt = 0;
   for (int w0 = gw * 32; w0 < words; w0 += warps * 32) {
     const int my_wi = w0 + lane;
     const unsigned my_vis = my_wi < words ? visited[my_wi] : 0xffffffffu;
-    if (my_wi < words && my_vis == 0xffffffffu) {
-      sink.zero(my_wi);
-      retry_map[my_wi] = 0;
+    unsigned m = ~my_vis;
+    if (my_wi == words - 1 && (n_vertices & 31))
+      m &= (1u << (n_vertices & 31)) - 1u;  // bits past the last vertex are not vertices
+    const int c = __popc(m);
+    const int incl = warp_inclusive_sum(c);
+    const int total = __shfl_sync(kFull, incl, 31);
+    s_found[warp][lane] = 0;
+    s_retry[warp][lane] = 0;
+    int at = incl - c;
+    while (m) {  // ascending vertex ids: the head[] loads below walk memory forwards
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      q[at++] = (my_wi << 5) + b;
     }
-    unsigned todo = __ballot_sync(kFull, my_vis != 0xffffffffu);
-    while (todo) {
-      int wi[kUnroll], nb[kUnroll];
-      unsigned vis[kUnroll];
+    __syncwarp();
+    for (int i0 = 0; i0 < total; i0 += 64) {
+      int v[2];
+      int2 h[2];
+      bool hit[2], again[2];
 #pragma unroll
-      for (int k = 0; k < kUnroll; ++k) {
-        wi[k] = -1;
-        vis[k] = 0xffffffffu;
-        if (todo) {
-          const int src_lane = __ffs(todo) - 1;
-          todo &= todo - 1;
-          wi[k] = w0 + src_lane;
-          vis[k] = __shfl_sync(kFull, my_vis, src_lane);
+      for (int k = 0; k < 2; ++k) {
+        const int i = i0 + 32 * k + lane;
+        v[k] = i < total ? q[i] : -1;
+        h[k] = make_int2(-1, -1);
+        if (v[k] >= 0)
+          h[k] = __ldg(head + v[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        hit[k] = h[k].x != -1 && in_frontier(h[k].x);
+        again[k] = h[k].x != -1 && !hit[k] && h[k].y != -1;
+        probes += h[k].x != -1 ? 1u : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (again[k]) {
+          ++probes;
+          hit[k] = in_frontier(h[k].y & ~kNoMoreNeighbors);
+        }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (v[k] < 0)
+          continue;
+        const unsigned bit = 1u << (v[k] & 31);
+        const int wl = (v[k] >> 5) - w0;
+        if (hit[k]) {
+          dist[v[k]] = next_level;
+          atomicOr(&s_found[warp][wl], bit);
+        } else if (again[k] && !(h[k].y & kNoMoreNeighbors)) {
+          atomicOr(&s_retry[warp][wl], bit);
         }
       }
-#pragma unroll
-      for (int k = 0; k < kUnroll; ++k) {
-        const int v = (wi[k] << 5) + lane;
-        nb[k] = -1;
-        if (wi[k] >= 0 && v < n_vertices && !((vis[k] >> lane) & 1u))
-          nb[k] = ld_stream(first_nb + v);
-      }
-      bool hit[kUnroll];
-#pragma unroll
-      for (int k = 0; k < kUnroll; ++k)
-        hit[k] = nb[k] != -1 && in_frontier(nb[k] & ~kOnlyNeighbor);
-#pragma unroll
-      for (int k = 0; k < kUnroll; ++k) {
-        if (wi[k] < 0)
-          continue;  // warp-uniform
-        const unsigned pm = __ballot_sync(kFull, nb[k] != -1);
-        const unsigned fm = __ballot_sync(kFull, hit[k]);
-        const unsigned rm = __ballot_sync(kFull, nb[k] != -1 && !hit[k] && !(nb[k] & kOnlyNeighbor));
-        if (hit[k])
-          dist[(wi[k] << 5) + lane] = next_level;
-        sink.word(wi[k], fm);
-        if (lane == 0) {
-          retry_map[wi[k]] = rm;
-          if (fm)
-            visited[wi[k]] = vis[k] | fm;
-          probes += __popc(pm);
-          found_cnt += __popc(fm);
-          retry_cnt += __popc(rm);
-        }
-      }
     }
+    __syncwarp();
+    if (my_wi < words) {
+      const unsigned fm = s_found[warp][lane], rm = s_retry[warp][lane];
+      next[my_wi] = fm;
+      retry_map[my_wi] = rm;
+      if (fm)
+        visited[my_wi] = my_vis | fm;
+      found_cnt += __popc(fm);
+      retry_cnt += __popc(rm);
+    }
+    __syncwarp();  // the queue and the word arrays are rewritten by the next pass
   }
+  probes = warp_sum(probes);
+  found_cnt = warp_sum(found_cnt);
+  retry_cnt = warp_sum(retry_cnt);
   if (lane == 0) {
     if (probes)
       atomicAdd(&ctrl->edges, static_cast<unsigned long long>(probes));
@@ -490,8 +502,8 @@ __device__ __forceinline__ void bitmap_set(unsigned* map, bool on, int v) {
 }
 
 /**
- * @brief K2: the full search from the SECOND in-neighbour on, for the vertices K1 marked in `retry_map`
- * (~15 % of the unvisited vertices of the first pull level, 2-3 set bits per word).  A warp takes kWords words
+ * @brief K2: the full search from the THIRD in-neighbour on, for the vertices K1 marked in `retry_map`
+ * (~4 % of the unvisited vertices of the first pull level, fewer than one set bit per word).  A warp takes kWords words
  * per pass, expands their set bits into its own queue in shared memory (warp scan of the popcounts), and
  * walks the queue 32 vertices at a time: kSerial interleaved probes per lane, rows still open after that are
  * finished by the whole warp.  Found vertices set their bits with RED.OR.
@@ -532,7 +544,7 @@ bfs_pull_rest_kernel(csr_view_t in, const unsigned* __restrict__ retry_map, unsi
       const int v = i < total ? q[i] : -1;
       int e = 0, end = 0;
       if (v >= 0) {
-        e = ro[v] + 1;  // the first in-neighbour was K1's probe
+        e = ro[v] + 2;  // the first two in-neighbours were K1's probes
         end = ro[v + 1];
       }
       bool searching = e < end, found = false;
@@ -607,7 +619,7 @@ struct bfs_scratch_t {
   dbuf_t<unsigned> visited, fbm, nbm, unreachable;
   dbuf_t<int> unv[2];                    // still-unvisited vertices (consecutive bottom-up levels)
   dbuf_t<unsigned> retry_map;            // pull levels: vertices whose first in-neighbour missed (K2's input)
-  dbuf_t<int> first_nb;                  // per vertex: first in-neighbour (bfs_first_neighbor_kernel)
+  dbuf_t<int2> first_nb;                 // per vertex: its first two in-neighbours (bfs_first_neighbor_kernel)
   graph_key_t unreachable_for;           // the (in-edge) graph the unreachable map was built from
   graph_key_t first_nb_for;              // ... and the one first_nb was built from
   dbuf_t<int> q[2];
@@ -796,9 +808,9 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
         cb = ws.next_ctrl();
         sc.retry_map.ensure(static_cast<size_t>(words) + 4);
         const bitmap_frontier_t in_frontier{fbm};
-        bfs_pull_first_kernel<256, 4><<<sms * 8, 256, 0, st>>>(V, sc.first_nb.ptr, sc.visited.ptr, in_frontier,
-                                                               bitmap_word_sink_t{nbm}, sc.retry_map.ptr, dist,
-                                                               level + 1, ca, sc.counts.ptr + 2);
+        bfs_pull_first_kernel<256><<<sms * 6, 256, 0, st>>>(V, sc.first_nb.ptr, sc.visited.ptr, in_frontier, nbm,
+                                                            sc.retry_map.ptr, dist, level + 1, ca,
+                                                            sc.counts.ptr + 2);
         bfs_pull_rest_kernel<256, 32, 8><<<sms * 6, 256, 0, st>>>(in_g, sc.retry_map.ptr, sc.visited.ptr, in_frontier,
                                                                   nbm, dist, level + 1, cb, sc.counts.ptr + 2);
         ws.launches += 1;

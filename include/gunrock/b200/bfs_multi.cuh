@@ -19,12 +19,20 @@
  */
 #pragma once
 
+#include <cstdlib>
 #include <exception>
 #include <memory>
+#include <string>
 #include <thread>
 #include <vector>
 
 #include <gunrock/b200/bfs_p2p.cuh>
+#if defined(__has_include)
+#if __has_include(<nccl.h>)
+#include <gunrock/b200/bfs_nccl.cuh>  // the NCCL exchange (B2G_EXCHANGE=nccl); bound with dlopen, no link dependency
+#define GUNROCK_B200_HAS_NCCL 1
+#endif
+#endif
 
 namespace gunrock {
 namespace b200 {
@@ -66,6 +74,9 @@ struct multi_rank_t {
   part_bfs_state_t S;
   dbuf_t<unsigned long long> part_deg;
   p2p_state_t P;
+#ifdef GUNROCK_B200_HAS_NCCL
+  nccl_state_t N;
+#endif
   ~multi_rank_t() { P.release(); }
 };
 
@@ -74,6 +85,7 @@ struct multi_bfs_cache_t {
   std::vector<int> devices;
   std::vector<std::unique_ptr<multi_rank_t>> ranks;
   long long total_edges = 0;
+  bool use_nccl = false;  // B2G_EXCHANGE=nccl: NCCL collectives instead of the kernels' peer-memory exchange
   bool matches(const csr_view_t& g, const csr_view_t& in_g, const std::vector<int>& devs) const {
     return !ranks.empty() && key.matches(g) && devices == devs &&
            (in_g.row_offsets == nullptr ? in_key.uid == 0 : (in_g.row_offsets == g.row_offsets || in_key.matches(in_g)));
@@ -171,6 +183,27 @@ inline void bfs_prepare_multi(multi_context_type& contexts, multi_bfs_cache_t& c
     }
     for (int r = 0; r < P; ++r)
       part_p2p_attach_pointers(cache.ranks[r]->P, windows);
+    const char* ex = std::getenv("B2G_EXCHANGE");
+    cache.use_nccl = ex != nullptr && std::string(ex) == "nccl";
+    if (cache.use_nccl) {
+#ifdef GUNROCK_B200_HAS_NCCL
+      if (!distinct && P > 1)
+        throw std::runtime_error("B2G_EXCHANGE=nccl needs one distinct device per context (ncclCommInitAll)");
+      const nccl_api_t& nccl = nccl_api_t::get();
+      std::vector<ncclComm_t> comms(P);
+      nccl.check(nccl.CommInitAll(comms.data(), P, devs.data()), "ncclCommInitAll");
+      for (int r = 0; r < P; ++r) {
+        auto& R = *cache.ranks[r];
+        B2G_CHECK(cudaSetDevice(R.device));
+        R.N.comm = comms[r];
+        R.N.owns_comm = true;
+        R.N.prepare(*R.ws, R.view, R.pt, R.S, R.part_deg, R.in_view.row_offsets != nullptr);
+        B2G_CHECK(cudaDeviceSynchronize());
+      }
+#else
+      throw std::runtime_error("B2G_EXCHANGE=nccl: this translation unit was compiled without <nccl.h>");
+#endif
+    }
     B2G_CHECK(cudaSetDevice(home));
     cache.key.set(g);
     if (own_in)
@@ -212,6 +245,13 @@ inline int bfs_run_multi(multi_context_type& contexts, multi_bfs_cache_t& cache,
         auto& R = *cache.ranks[r];
         B2G_CHECK(cudaSetDevice(R.device));
         csr_view_t in_view = cfg.direction != 0 ? R.in_view : csr_view_t();
+#ifdef GUNROCK_B200_HAS_NCCL
+        if (cache.use_nccl) {
+          part_bfs_nccl_run(*R.ws, R.view, in_view, R.pt, R.S, R.part_deg, R.N, source, cache.total_edges, cfg,
+                            &reports[r]);
+          return;
+        }
+#endif
         part_bfs_p2p_run(*R.ws, R.view, in_view, R.pt, R.S, R.part_deg, R.P, source, cache.total_edges, cfg,
                          &reports[r]);
       } catch (...) {

@@ -194,6 +194,10 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
       S.unreachable_for.set(in_view);
     }
     premark = S.unreachable.ptr;
+    if (!S.first_nb_for.matches(in_view)) {  // the pull kernels' per-row shortcut (bfs.cuh), built once per graph
+      bfs_first_neighbor_kernel<<<sms * 8, 256, 0, st>>>(in_view, S.first_nb.ptr);
+      S.first_nb_for.set(in_view);
+    }
   }
   part_reset_kernel<<<sms * 8, 256, 0, st>>>(pt, source, S.dist.ptr, S.visited.ptr, S.sent.ptr, sent_words,
                                               S.q[0].ptr, S.counts.ptr, premark);
@@ -211,6 +215,7 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
   };
   reduce_and_publish();  // every rank learns the source's degree (the size of level 0's exchange)
   long long n_f = N.h_fb->v[0], m_f = N.h_fb->v[1], explored = 0;
+  bool m_known = true;  // false after a pull level: K1 / K2 do not report the new frontier's out-degree sum
   if (n_f != 1)
     throw std::runtime_error("part_bfs_nccl_run: the source is owned by no rank");
 
@@ -226,7 +231,7 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
       if (cfg.direction == 1)
         go_up = true;
       else if (!bottom_up)
-        go_up = static_cast<double>(m_f) > static_cast<double>(total_edges - explored) / cfg.alpha;
+        go_up = m_known && static_cast<double>(m_f) > static_cast<double>(total_edges - explored) / cfg.alpha;
       else
         go_up = !(static_cast<double>(n_f) < static_cast<double>(pt.n_global) / cfg.beta);
     }
@@ -247,12 +252,16 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
         all = N.all.ptr;
       }
       c = ws.next_ctrl();
+      ctrl_t* c2 = ws.next_ctrl();
       B2G_CHECK(cudaMemsetAsync(S.counts.ptr + 2, 0, sizeof(int), st));
-      B2G_CHECK(cudaMemsetAsync(nbm, 0, sizeof(unsigned) * wpr, st));
-      part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(pt, in_view, wpr, S.visited.ptr, all,
-                                                             local_word_sink_t{nbm}, S.dist.ptr, level + 1, c,
-                                                             S.counts.ptr + 2);
-      ws.launches += 1;
+      // K1 + K2 over this rank's rows (bfs.cuh): K1 writes every next-frontier word, K2 ORs its finds in
+      const part_frontier_t in_frontier{pt, all, wpr};
+      bfs_pull_first_kernel<256><<<sms * 6, 256, 0, st>>>(pt.n_local, S.first_nb.ptr, S.visited.ptr, in_frontier, nbm,
+                                                          S.retry_map.ptr, S.dist.ptr, level + 1, c, S.counts.ptr + 2);
+      bfs_pull_rest_kernel<256, 32, 8><<<sms * 6, 256, 0, st>>>(in_view, S.retry_map.ptr, S.visited.ptr, in_frontier, nbm,
+                                                                S.dist.ptr, level + 1, c2, S.counts.ptr + 2);
+      part_fold_edges_kernel<<<1, 1, 0, st>>>(c, c2);
+      ws.launches += 3;
       std::swap(fbm, nbm);
       count_ptr = S.counts.ptr + 2;
     } else {
@@ -264,7 +273,7 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
       }
       const int nxt = cur ^ 1;
       // no rank can forward more ids to a peer than the frontier has out-edges, nor than the peer owns rows
-      long long cap_ll = m_f < 256 ? 256 : m_f;
+      long long cap_ll = !m_known ? static_cast<long long>(N.cap_full) : (m_f < 256 ? 256 : m_f);
       if (cap_ll > static_cast<long long>(N.cap_full))
         cap_ll = static_cast<long long>(N.cap_full);
       const int cap = static_cast<int>(cap_ll);
@@ -276,9 +285,9 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
                        static_cast<int>(row), S.overflow.ptr};
       advance_launch_t lcfg = cfg.advance;
       const long long m_rank = m_f / np;
-      lcfg.avg_degree = (level > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
-      if (level == 0) {
-        lcfg.lb = lb_t::block_mapped;  // one row: binned kernel + hub slabs
+      lcfg.avg_degree = (level > 0 && m_known && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
+      if (level == 0 || !m_known) {
+        lcfg.lb = lb_t::block_mapped;  // rows of unknown total length: binned kernel + hub slabs
       } else if (m_rank < lcfg.small_frontier_edges) {
         lcfg.lb = lb_t::block_mapped;
         lcfg.hub_threshold = 1 << 30;
@@ -324,6 +333,9 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
     verts_total += static_cast<unsigned long long>(n_f);
     n_f = N.h_fb->v[0];
     m_f = N.h_fb->v[1];
+    m_known = !go_up;
+    if (!m_known)
+      m_f = N.h_fb->v[2];  // stand-in for the `explored` estimate only
     bottom_up = go_up;
     ++level;
   }

@@ -427,6 +427,11 @@ p2p_tail_kernel(csr_view_t g, partition_t pt, p2p_window_t w, unsigned epoch0, i
   }
 }
 
+/// K2's edge count joins K1's control block (the statistics barrier reads ONE block)
+static __global__ void part_fold_edges_kernel(ctrl_t* into, const ctrl_t* from) {
+  into->edges += from->edges;
+}
+
 /// push this rank's segment of front[parity] (already complete in its own window) to every peer:
 /// 16-byte stores, enough CTAs to keep NVLink busy (segments are 16-byte aligned: words % 4 == 0)
 static __global__ void p2p_push_segment_kernel(p2p_window_t w, int parity) {
@@ -550,7 +555,6 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
     const bool can_pull = in_view.row_offsets != nullptr && cfg.direction != 0;
     const double alpha = cfg.alpha;
     const double beta = cfg.beta;
-    static const bool fused_sink = std::getenv("B2G_P2P_FUSED_SINK") != nullptr;
     static const bool trace = std::getenv("B2G_TRACE") != nullptr;
     static const char* timeout_env = std::getenv("B2G_P2P_TIMEOUT_MS");
     const unsigned long long timeout_ns =
@@ -569,6 +573,10 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
         S.unreachable_for.set(in_view);
       }
       premark = S.unreachable.ptr;
+      if (!S.first_nb_for.matches(in_view)) {  // the pull kernels' per-row shortcut (bfs.cuh), built once per graph
+        bfs_first_neighbor_kernel<<<sms * 8, 256, 0, st>>>(in_view, S.first_nb.ptr);
+        S.first_nb_for.set(in_view);
+      }
     }
     part_reset_kernel<<<sms * 8, 256, 0, st>>>(pt, source, S.dist.ptr, S.visited.ptr, S.sent.ptr,
                                                 sent_words, S.q[0].ptr, S.counts.ptr, premark);
@@ -595,6 +603,7 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
     int cur = 0, level = 0, parity = 0;  // parity: which `front` buffer holds the current frontier
     bool is_bitmap = false, bottom_up = false;
     long long n_f = 1, m_f = 0, explored = 0;
+    bool m_known = true;  // false after a pull level: K1 / K2 do not report the new frontier's out-degree sum
     unsigned long long edges_total = 0, verts_total = 0;
     const auto t0 = std::chrono::steady_clock::now();
     auto sync = [&](bool with_stats, const int* send_count, const int* count_ptr, const ctrl_t* c) {
@@ -614,13 +623,13 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
         if (cfg.direction == 1)
           go_up = true;
         else if (!bottom_up)
-          go_up = static_cast<double>(m_f) > static_cast<double>(total_edges - explored) / alpha;
+          go_up = m_known && static_cast<double>(m_f) > static_cast<double>(total_edges - explored) / alpha;
         else
           go_up = !(static_cast<double>(n_f) < static_cast<double>(pt.n_global) / beta);
       }
       unsigned* my_front = w.front(w.me, parity) + static_cast<size_t>(w.me) * w.words;
       // ---- tiny global frontier: the distributed tail kernel runs level after level on its own ------
-      if (!go_up && level > 0 && use_tail && m_f < tail_budget) {
+      if (!go_up && level > 0 && use_tail && m_known && m_f < tail_budget) {
         if (is_bitmap) {
           B2G_CHECK(cudaMemsetAsync(S.counts.ptr + cur, 0, sizeof(int), st));
           bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(my_front, S.local_words(), S.q[cur].ptr,
@@ -656,6 +665,7 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
         cur = t.cur;
         n_f = t.count;
         m_f = t.deg_sum;
+        m_known = true;
         bottom_up = false;
         continue;
       }
@@ -677,19 +687,23 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
         c = ws.next_ctrl();
         B2G_CHECK(cudaMemsetAsync(S.counts.ptr + 2, 0, sizeof(int), st));
         const unsigned* all = w.front(w.me, parity);
-        if (fused_sink || np == 1) {
-          part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
-              pt, in_view, w.words, S.visited.ptr, all, peer_word_sink_t{w, parity ^ 1}, S.dist.ptr,
-              level + 1, c, S.counts.ptr + 2);
-        } else {
-          unsigned* nxt_seg = w.front(w.me, parity ^ 1) + static_cast<size_t>(w.me) * w.words;
-          part_bottom_up_kernel<256, 8><<<sms * 8, 256, 0, st>>>(
-              pt, in_view, w.words, S.visited.ptr, all, local_word_sink_t{nxt_seg}, S.dist.ptr,
-              level + 1, c, S.counts.ptr + 2);
-          mark("sweep");
+        // K1 + K2 over this rank's rows (bfs.cuh): next-frontier words land in my segment of front[parity ^ 1] in my
+        // own window (K1 plain stores, K2 RED.OR), then one kernel pushes the segment to every peer
+        unsigned* nxt_seg = w.front(w.me, parity ^ 1) + static_cast<size_t>(w.me) * w.words;
+        const part_frontier_t in_frontier{pt, all, w.words};
+        ctrl_t* c2 = ws.next_ctrl();
+        bfs_pull_first_kernel<256><<<sms * 6, 256, 0, st>>>(pt.n_local, S.first_nb.ptr, S.visited.ptr, in_frontier,
+                                                            nxt_seg, S.retry_map.ptr, S.dist.ptr, level + 1, c,
+                                                            S.counts.ptr + 2);
+        bfs_pull_rest_kernel<256, 32, 8><<<sms * 6, 256, 0, st>>>(in_view, S.retry_map.ptr, S.visited.ptr, in_frontier,
+                                                                  nxt_seg, S.dist.ptr, level + 1, c2, S.counts.ptr + 2);
+        part_fold_edges_kernel<<<1, 1, 0, st>>>(c, c2);
+        mark("sweep");
+        if (np > 1) {
           p2p_push_segment_kernel<<<dim3(push_ctas, np), 256, 0, st>>>(w, parity ^ 1);
           ws.launches += 1;
         }
+        ws.launches += 2;
         mark("push");
         ws.launches += 1;
         parity ^= 1;
@@ -710,9 +724,9 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
         // same path selection as the single-GPU enactor (bfs.cuh), on this rank's share of the frontier
         advance_launch_t lcfg = cfg.advance;
         const long long m_rank = m_f / np;
-        lcfg.avg_degree = (level > 0 && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
-        if (level == 0) {
-          lcfg.lb = lb_t::block_mapped;  // one row of unknown length
+        lcfg.avg_degree = (level > 0 && m_known && n_f > 0) ? static_cast<double>(m_f) / static_cast<double>(n_f) : 0.0;
+        if (level == 0 || !m_known) {
+          lcfg.lb = lb_t::block_mapped;  // rows of unknown total length
         } else if (m_rank < lcfg.small_frontier_edges) {
           lcfg.lb = lb_t::block_mapped;  // one kernel: warp / thread bins only
           lcfg.hub_threshold = 1 << 30;
@@ -761,6 +775,9 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
         explored += P.h_fb->edges;
       n_f = P.h_fb->count;
       m_f = P.h_fb->deg_sum;
+      m_known = !go_up;
+      if (!m_known)
+        m_f = P.h_fb->edges;  // stand-in for the `explored` estimate only
       bottom_up = go_up;
       ++level;
     }

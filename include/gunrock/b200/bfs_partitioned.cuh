@@ -163,6 +163,19 @@ static __global__ void part_queue_to_bitmap_kernel(const int* __restrict__ q,
   }
 }
 
+/// "is global vertex u in the current frontier" against the all-gathered frontier bitmap (rank-major: words
+/// [r * words_per_rank, (r + 1) * words_per_rank) hold rank r's local rows) -- the FrontierTest of the pull
+/// kernels K1 / K2 (bfs.cuh) on a partitioned graph, whose column indices are global ids.
+struct part_frontier_t {
+  partition_t pt;
+  const unsigned* all;
+  int words_per_rank;
+  __device__ __forceinline__ bool operator()(int u) const {
+    const int l = pt.local(u);
+    return (__ldg(all + pt.owner(u) * words_per_rank + (l >> 5)) >> (l & 31)) & 1u;
+  }
+};
+
 /// Where the bottom-up sweep puts the words of the next frontier: the local bitmap (NCCL variant; the
 /// peer-memory variant in bfs_p2p.cuh stores them into every rank's copy instead).
 struct local_word_sink_t {
@@ -304,8 +317,9 @@ static __global__ void part_seed_kernel(partition_t pt, int source, int* dist, u
 /// Device state of one rank's share of a partitioned BFS (allocated once per graph).
 struct part_bfs_state_t {
   partition_t pt;
-  dbuf_t<unsigned> visited, sent, fbm, nbm, unreachable;
-  graph_key_t unreachable_for;
+  dbuf_t<unsigned> visited, sent, fbm, nbm, unreachable, retry_map;
+  dbuf_t<int2> first_nb;                 // per local row: first two in-neighbours (global ids; bfs_first_neighbor_kernel)
+  graph_key_t unreachable_for, first_nb_for;
   dbuf_t<int> q[2], counts, send_count, overflow, dist;
   dbuf_t<int> send_buf;
   int send_cap = 0;
@@ -333,6 +347,8 @@ struct part_bfs_state_t {
     visited.ensure(lw);
     fbm.ensure(lw);
     nbm.ensure(lw);
+    retry_map.ensure(lw);
+    first_nb.ensure(static_cast<size_t>(p.n_local) + 64);
     sent.ensure((static_cast<size_t>(p.n_global) + 31) / 32 + 4);
     q[0].ensure(static_cast<size_t>(p.n_local) + 64);
     q[1].ensure(static_cast<size_t>(p.n_local) + 64);

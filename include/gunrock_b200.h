@@ -231,6 +231,21 @@ int b2g_part_p2p_attach(b2g_graph_t* g, const unsigned char* ipc_handles, void* 
 int b2g_part_p2p_detach(b2g_graph_t* g);
 int b2g_part_bfs_p2p(b2g_graph_t* g, int source, long long total_edges, const b2g_options_t* opt,
                      b2g_stats_t* stats);
+/* ---- NCCL exchange driven from C++ (include/gunrock/b200/bfs_nccl.cuh; SURVEY.md 8e: "NCCL all-to-all =
+ * ncclGroupStart; ncclSend / ncclRecv per peer; ncclGroupEnd", ncclAllGather of the frontier bitmap,
+ * ncclAllReduce of the level statistics).  The whole level loop runs inside b2g_part_bfs_nccl: no Python and no
+ * stream synchronisation inside a level, one pinned-memory poll per level.  NCCL is bound at run time (dlopen of
+ * libnccl.so.2: the copy torch loaded in a torch.distributed process, the system one otherwise).
+ *  1. rank 0: b2g_nccl_unique_id(id) -> 128 bytes, broadcast by the caller (torch.distributed, MPI, a file ...);
+ *  2. every rank: b2g_part_nccl_init(g, id, nranks, rank) -- COLLECTIVE (ncclCommInitRank) -- allocates the
+ *     message buffers once;
+ *  3. b2g_part_bfs_nccl: COLLECTIVE, same arguments and statistics as b2g_part_bfs_p2p;
+ *  4. b2g_part_nccl_finalize (optional; the handle's destructor does it too). */
+int b2g_nccl_unique_id(unsigned char* id128);
+int b2g_part_nccl_init(b2g_graph_t* g, const unsigned char* id128, int nranks, int rank);
+int b2g_part_bfs_nccl(b2g_graph_t* g, int source, long long total_edges, const b2g_options_t* opt,
+                      b2g_stats_t* stats);
+int b2g_part_nccl_finalize(b2g_graph_t* g);
 /* ---- multi-GPU PageRank (pull): the rank owns the DESTINATION vertices v % nparts == part and their
  * in-edges (a partitioned graph whose rows are in-edge lists: any symmetric partitioned graph, or
  * one created with by_destination != 0).  Per iteration the host side all-gathers c = plast*iweights,

@@ -276,6 +276,10 @@ inline float __fdiv_rn(float a, float b) { return a / b; }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+struct int2 {
+  int x, y;
+};
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 template <typename T>

@@ -36,6 +36,14 @@ def main():
                     t = torch.tensor([int(ok)], device="cuda")
                     dist.all_reduce(t, op=dist.ReduceOp.MIN)
                     results[f"{name}/{direction}/{lb}/{variant}"] = [int(t.item()), st.level_direction]
+                # NCCL exchange with the level loop in C++ (bfs_nccl.cuh): own communicator, created once per handle
+                mg.nccl_connect(eng, mg.TorchDistComm())
+                for rep in range(2):
+                    d, st = mg.bfs_rank_nccl(eng, src, len(ci), direction)
+                    ok = bool(np.array_equal(d.cpu().numpy(), exp[rank::world]))
+                    t = torch.tensor([int(ok)], device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    results[f"{name}/{direction}/{lb}/nccl-cxx{rep}"] = [int(t.item()), st.level_direction]
                 # exchange done by the kernels over NVLink peer memory (CUDA IPC windows), twice per window
                 mg.p2p_connect(eng, mg.TorchDistComm())
                 for rep in range(2):

@@ -96,7 +96,28 @@ def test_nccl_two_or_more_gpus(gb):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("MG_RESULT ")][-1]
     res = json.loads(line[len("MG_RESULT "):])
-    assert len(res) == 42 and all(v[0] == 1 for v in res.values()), res
+    assert len(res) == 58 and all(v[0] == 1 for v in res.values()), res
+
+
+def test_cxx_nccl_level_loop_single_rank(gb):
+    """world_size 1: the C++ level loop with the NCCL exchange (b2g_part_bfs_nccl) -- communicator created by
+    ncclCommInitRank inside the library from an id made by the library, all collectives skipped at one rank, the
+    same kernels / statistics / pinned-memory polling as at N ranks.  (N > 1: tests/mg_worker.py under torchrun.)"""
+    from gunrock_b200 import multi_gpu as mg
+    ro, ci = oracle.rmat_csr(15, 16, 77)
+    G = mg.PartitionedGraph.from_global_csr(ro, ci, 1, 0)
+    deg = np.diff(ro)
+    for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
+        eng = mg.CudaRankEngine(G, gb.options_t(advance_load_balance=lb))
+        eng.nccl_init(mg.nccl_unique_id())
+        for src in (int(deg.argmax()), int(np.flatnonzero(deg > 0)[-1])):
+            exp = oracle.bfs(ro, ci, src)
+            for direction in (gb.advance_direction_t.forward, gb.advance_direction_t.optimized,
+                              gb.advance_direction_t.backward):
+                d, st = mg.bfs_rank_nccl(eng, src, len(ci), direction)
+                assert np.array_equal(d.cpu().numpy(), exp), (lb, src, direction)
+                assert st.levels == int(exp[exp < 2**31 - 1].max()) + 1
+    G.close()
 
 
 def test_async_driver_single_rank(gb):
