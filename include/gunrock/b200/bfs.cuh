@@ -125,8 +125,12 @@ static __global__ void queue_to_bitmap_kernel(const int* __restrict__ q, const i
 }
 
 /// Enumerate set bits into a queue (order is irrelevant to BFS; one atomic per warp pass).
+/// `ro` / `deg_sum` (optional): also add up the out-degrees of the enumerated vertices (the first push level after
+/// pull levels needs the frontier's out-degree sum, which the pull kernels do not compute).
 static __global__ void bitmap_to_queue_kernel(const unsigned* __restrict__ bm, int words, int* q,
-                                       int* count) {
+                                       int* count, const int* __restrict__ ro = nullptr,
+                                       unsigned long long* deg_sum = nullptr) {
+  unsigned long long ds = 0;
   const int lane = lane_id();
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -147,7 +151,14 @@ static __global__ void bitmap_to_queue_kernel(const unsigned* __restrict__ bm, i
       int b = __ffs(w) - 1;
       w &= w - 1;
       q[base++] = vb + b;
+      if (ro)
+        ds += static_cast<unsigned>(ro[vb + b + 1] - ro[vb + b]);
     }
+  }
+  if (deg_sum) {
+    ds = warp_sum(ds);
+    if (lane == 0 && ds)
+      atomicAdd(deg_sum, ds);
   }
 }
 
@@ -726,6 +737,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
   // frontier out-degree sum.  Not known for the source (probing it would cost a host round trip);
   // level 0 always runs top-down on the small path and reports it.
   unsigned long long m_f = 0;
+  bool explored_counted = false;
   bool m_known = false;  // the pull kernels do not report the new frontier's out-degree sum (it would cost a pair
                          // of row offsets per found vertex); the first push level after them runs like level 0
   unsigned long long explored = 0;
@@ -784,8 +796,9 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       else
         want_bottom_up = !(static_cast<double>(n_f) < static_cast<double>(V) / cfg.beta);
     }
-    if (level > 0)
+    if (level > 0 && !explored_counted)
       explored += m_f;
+    explored_counted = false;
     if (level < 64)
       B2G_CHECK(cudaEventRecord(sc.ev[2 * level], st));
     ctrl_t* ca = nullptr;
@@ -840,10 +853,25 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       unv_valid = false;  // a push level claims vertices the list does not know about
       if (bottom_up) {  // bitmap -> queue
         B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + cur, 0, sizeof(int), st));
-        bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(fbm, words, sc.q[cur].ptr,
-                                                        sc.counts.ptr + cur);
+        ctrl_t* cq = ws.next_ctrl();
+        bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(fbm, words, sc.q[cur].ptr, sc.counts.ptr + cur,
+                                                        m_known ? nullptr : out_g.row_offsets,
+                                                        m_known ? nullptr : &cq->deg_sum);
         ws.launches += 1;
         bottom_up = false;
+        if (!m_known) {
+          // one more pinned-memory poll, once per run: with the queue's out-degree sum known the tail of the
+          // traversal (usually everything that is left) runs in the single-launch multi-level kernel
+          bfs_feedback_kernel<<<1, 1, 0, st>>>(sc.counts.ptr + cur, cq, nullptr, sc.h_fb, ++sc.seq);
+          ws.launches += 1;
+          wait_for_sequence(&sc.h_fb->seq, sc.seq, st);
+          m_f = sc.h_fb->deg_sum;
+          m_known = true;
+          explored_counted = true;
+          if (level < 64)  // the level's event pair is re-recorded when the loop comes back to this level
+            B2G_CHECK(cudaEventRecord(sc.ev[2 * level + 1], st));
+          continue;
+        }
       }
       int nxt = cur ^ 1;
       B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + nxt, 0, sizeof(int), st));
