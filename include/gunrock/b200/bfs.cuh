@@ -412,15 +412,16 @@ struct bitmap_frontier_t {
  * finds in afterwards), `retry_map` the vertices K2 has to search.
  */
 template <int kThreads, typename FrontierTest>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2048 / kThreads)  // 32 registers: a full SM of warps, latency is the enemy
 bfs_pull_first_kernel(int n_vertices, const int2* __restrict__ head, unsigned* __restrict__ visited,
                       FrontierTest in_frontier, unsigned* __restrict__ next, unsigned* __restrict__ retry_map,
                       int* dist, int next_level, ctrl_t* ctrl, int* next_count) {
   constexpr int kWarps = kThreads / 32;
-  __shared__ int s_q[kWarps][1024];
+  constexpr int kU = 4;  // vertices per lane per step: kU independent head[] loads, then kU probes in flight
+  __shared__ unsigned short s_q[kWarps][1024];  // vertex = (w0 << 5) + entry
   __shared__ unsigned s_found[kWarps][32], s_retry[kWarps][32];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  int* q = s_q[warp];
+  unsigned short* q = s_q[warp];
   const int words = (n_vertices + 31) / 32;
   const int warps = (gridDim.x * kThreads) >> 5;
   const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
@@ -440,35 +441,40 @@ bfs_pull_first_kernel(int n_vertices, const int2* __restrict__ head, unsigned* _
     while (m) {  // ascending vertex ids: the head[] loads below walk memory forwards
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      q[at++] = (my_wi << 5) + b;
+      q[at++] = static_cast<unsigned short>((lane << 5) + b);
     }
     __syncwarp();
-    for (int i0 = 0; i0 < total; i0 += 64) {
-      int v[2];
-      int2 h[2];
-      bool hit[2], again[2];
+    const int vbase = w0 << 5;
+    for (int i0 = 0; i0 < total; i0 += 32 * kU) {
+      int v[kU];
+      int2 h[kU];
+      bool hit[kU], again[kU];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < kU; ++k) {
         const int i = i0 + 32 * k + lane;
-        v[k] = i < total ? q[i] : -1;
+        v[k] = i < total ? vbase + q[i] : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
         h[k] = make_int2(-1, -1);
         if (v[k] >= 0)
           h[k] = __ldg(head + v[k]);
       }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < kU; ++k) {
         hit[k] = h[k].x != -1 && in_frontier(h[k].x);
-        again[k] = h[k].x != -1 && !hit[k] && h[k].y != -1;
         probes += h[k].x != -1 ? 1u : 0u;
       }
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
+      for (int k = 0; k < kU; ++k) {
+        again[k] = h[k].x != -1 && !hit[k] && h[k].y != -1;
         if (again[k]) {
           ++probes;
           hit[k] = in_frontier(h[k].y & ~kNoMoreNeighbors);
         }
+      }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < kU; ++k) {
         if (v[k] < 0)
           continue;
         const unsigned bit = 1u << (v[k] & 31);
@@ -821,7 +827,7 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
         cb = ws.next_ctrl();
         sc.retry_map.ensure(static_cast<size_t>(words) + 4);
         const bitmap_frontier_t in_frontier{fbm};
-        bfs_pull_first_kernel<256><<<sms * 6, 256, 0, st>>>(V, sc.first_nb.ptr, sc.visited.ptr, in_frontier, nbm,
+        bfs_pull_first_kernel<256><<<sms * 8, 256, 0, st>>>(V, sc.first_nb.ptr, sc.visited.ptr, in_frontier, nbm,
                                                             sc.retry_map.ptr, dist, level + 1, ca,
                                                             sc.counts.ptr + 2);
         bfs_pull_rest_kernel<256, 32, 8><<<sms * 6, 256, 0, st>>>(in_g, sc.retry_map.ptr, sc.visited.ptr, in_frontier,

@@ -692,7 +692,7 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
         unsigned* nxt_seg = w.front(w.me, parity ^ 1) + static_cast<size_t>(w.me) * w.words;
         const part_frontier_t in_frontier{pt, all, w.words};
         ctrl_t* c2 = ws.next_ctrl();
-        bfs_pull_first_kernel<256><<<sms * 6, 256, 0, st>>>(pt.n_local, S.first_nb.ptr, S.visited.ptr, in_frontier,
+        bfs_pull_first_kernel<256><<<sms * 8, 256, 0, st>>>(pt.n_local, S.first_nb.ptr, S.visited.ptr, in_frontier,
                                                             nxt_seg, S.retry_map.ptr, S.dist.ptr, level + 1, c,
                                                             S.counts.ptr + 2);
         bfs_pull_rest_kernel<256, 32, 8><<<sms * 6, 256, 0, st>>>(in_view, S.retry_map.ptr, S.visited.ptr, in_frontier,
