@@ -235,6 +235,26 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
       else
         go_up = !(static_cast<double>(n_f) < static_cast<double>(pt.n_global) / cfg.beta);
     }
+    if (!go_up && !m_known) {
+      // first push level after pull levels: learn the frontier's GLOBAL out-degree sum (the pull kernels do not
+      // compute it) with one more all-reduce, once per run -- it sizes the exchange of the coming push levels
+      ctrl_t* cq = ws.next_ctrl();
+      if (is_bitmap) {
+        B2G_CHECK(cudaMemsetAsync(S.counts.ptr + cur, 0, sizeof(int), st));
+        bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(fbm, S.local_words(), S.q[cur].ptr, S.counts.ptr + cur,
+                                                        view.row_offsets, &cq->deg_sum);
+        ws.launches += 1;
+        is_bitmap = false;
+      }
+      part_stats_kernel<<<1, 1, 0, st>>>(S.counts.ptr + cur, cq, part_deg.ptr, S.overflow.ptr, N.stats.ptr);
+      ws.launches += 1;
+      reduce_and_publish();
+      n_f = N.h_fb->v[0];
+      m_f = N.h_fb->v[1];
+      m_known = true;
+      bottom_up = false;
+      continue;
+    }
     explored += m_f;
     ctrl_t* c = nullptr;
     const int* count_ptr = nullptr;

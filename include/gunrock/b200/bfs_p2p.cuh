@@ -628,6 +628,29 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
           go_up = !(static_cast<double>(n_f) < static_cast<double>(pt.n_global) / beta);
       }
       unsigned* my_front = w.front(w.me, parity) + static_cast<size_t>(w.me) * w.words;
+      // ---- first push level after pull levels: learn the frontier's GLOBAL out-degree sum (the pull kernels do
+      //      not compute it) with one more statistics barrier, once per run; the tail kernel below usually takes
+      //      everything that is left
+      if (!go_up && !m_known) {
+        ctrl_t* cq = ws.next_ctrl();
+        if (is_bitmap) {
+          B2G_CHECK(cudaMemsetAsync(S.counts.ptr + cur, 0, sizeof(int), st));
+          bitmap_to_queue_kernel<<<sms * 4, 256, 0, st>>>(my_front, S.local_words(), S.q[cur].ptr, S.counts.ptr + cur,
+                                                          view.row_offsets, &cq->deg_sum);
+          ws.launches += 1;
+          is_bitmap = false;
+        }
+        sync(true, nullptr, S.counts.ptr + cur, cq);
+        wait_for_sequence(&P.h_fb->seq, P.seq, st);
+        if (P.h_fb->timed_out)
+          throw std::runtime_error("b2g_part_bfs_p2p: a peer did not reach the statistics barrier of the pull -> push switch");
+        n_f = P.h_fb->count;
+        m_f = P.h_fb->deg_sum;
+        m_known = true;
+        bottom_up = false;
+        mark("switch");
+        continue;
+      }
       // ---- tiny global frontier: the distributed tail kernel runs level after level on its own ------
       if (!go_up && level > 0 && use_tail && m_known && m_f < tail_budget) {
         if (is_bitmap) {

@@ -11,20 +11,32 @@ namespace util {
 
 struct timer_t {
   float time = 0.0f;
-  timer_t() {
-    cudaEventCreate(&start_);
-    cudaEventCreate(&stop_);
-  }
+  /// The events are created on first use, on the device that is current THEN -- the device of the stream
+  /// they are recorded on.  (Created in the constructor they belong to whatever device was current when the
+  /// owning object was constructed: a `standard_context_t` initialises its members before its body selects
+  /// the device, so the timer of a context built right after a context of another device could not be
+  /// recorded on its own stream -- cudaErrorInvalidResourceHandle.)
+  timer_t() = default;
   ~timer_t() {
-    cudaEventDestroy(start_);
-    cudaEventDestroy(stop_);
+    if (start_)
+      cudaEventDestroy(start_);
+    if (stop_)
+      cudaEventDestroy(stop_);
   }
   timer_t(const timer_t&) = delete;
   timer_t& operator=(const timer_t&) = delete;
 
   void reset() { time = 0.0f; }
-  void begin(cudaStream_t stream = 0) { cudaEventRecord(start_, stream); }
+  void begin(cudaStream_t stream = 0) {
+    if (!start_) {
+      cudaEventCreate(&start_);
+      cudaEventCreate(&stop_);
+    }
+    cudaEventRecord(start_, stream);
+  }
   float end(cudaStream_t stream = 0) {
+    if (!stop_)
+      return 0.0f;  // end() without begin()
     cudaEventRecord(stop_, stream);
     cudaEventSynchronize(stop_);
     cudaEventElapsedTime(&time, start_, stop_);
@@ -34,7 +46,7 @@ struct timer_t {
   float milliseconds() { return time; }
 
  private:
-  cudaEvent_t start_, stop_;
+  cudaEvent_t start_ = nullptr, stop_ = nullptr;
 };
 
 }  // namespace util
