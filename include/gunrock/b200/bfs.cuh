@@ -95,13 +95,21 @@ static __global__ void bfs_unreachable_map_kernel(const int* __restrict__ in_off
   }
 }
 
+/// `fill_dist` == 0: only the source is labelled here; the INT_MAX of everything that stays unreached is written
+/// later, by the first pull level (K1 writes a label for every vertex it looks at anyway) or by
+/// bfs_fill_unreached_kernel when the traversal ends without one -- the 4 x V bytes of labels are then written once
+/// per run instead of twice (268 MB at scale 26: ~45 us of a 0.85 ms traversal).
 static __global__ void bfs_reset_kernel(int* dist, unsigned* visited, unsigned* fbm, int n_vertices,
                                  int source, int* q0, int* counts,
-                                 const unsigned* __restrict__ premark = nullptr) {
+                                 const unsigned* __restrict__ premark = nullptr, int fill_dist = 1) {
   const int words = (n_vertices + 31) / 32;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vertices;
+  const int n = fill_dist ? n_vertices : words;
+  if (!fill_dist && blockIdx.x == 0 && threadIdx.x == 0)
+    dist[source] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += gridDim.x * blockDim.x) {
-    dist[i] = (i == source) ? 0 : INT_MAX;
+    if (fill_dist)
+      dist[i] = (i == source) ? 0 : INT_MAX;
     if (i < words) {
       unsigned bit = (i == (source >> 5)) ? (1u << (source & 31)) : 0u;
       visited[i] = bit | (premark ? premark[i] : 0u);
@@ -112,6 +120,18 @@ static __global__ void bfs_reset_kernel(int* dist, unsigned* visited, unsigned* 
     q0[0] = source;
     counts[0] = 1;
     counts[1] = 0;
+  }
+}
+
+/// The deferred half of the reset (see bfs_reset_kernel): INT_MAX for every vertex that was never labelled --
+/// not visited, or pre-marked as having no in-edges -- except the source.
+static __global__ void bfs_fill_unreached_kernel(int* dist, const unsigned* __restrict__ visited,
+                                                 const unsigned* __restrict__ premark, int n_vertices, int source) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n_vertices; v += gridDim.x * blockDim.x) {
+    const unsigned bit = 1u << (v & 31);
+    const bool labelled = (visited[v >> 5] & bit) && !(premark && (premark[v >> 5] & bit));
+    if (!labelled && v != source)
+      dist[v] = INT_MAX;
   }
 }
 
@@ -415,7 +435,15 @@ template <int kThreads, typename FrontierTest>
 __global__ void __launch_bounds__(kThreads, 2048 / kThreads)  // 32 registers: a full SM of warps, latency is the enemy
 bfs_pull_first_kernel(int n_vertices, const int2* __restrict__ head, unsigned* __restrict__ visited,
                       FrontierTest in_frontier, unsigned* __restrict__ next, unsigned* __restrict__ retry_map,
-                      int* dist, int next_level, ctrl_t* ctrl, int* next_count) {
+                      int* dist, int next_level, ctrl_t* ctrl, int* next_count,
+                      const unsigned* __restrict__ fill_premark = nullptr, int fill = 0, int source = -1,
+                      int batch_words = 32) {
+  // batch_words (8 / 16 / 32): words a warp takes per pass.  32 amortises the bookkeeping best; a graph (or a
+  // rank's share of one) with fewer than a few passes per resident warp takes smaller batches so that every warp
+  // has work -- a pass is a chain of dependent memory round trips, its length is the kernel's floor.
+  // fill != 0 (first pull level of a run whose reset left the labels unwritten): also write INT_MAX for every
+  // vertex that is not found at this level and was not labelled before -- the unvisited ones this kernel looks
+  // at anyway, and the ones pre-marked as having no in-edges.
   constexpr int kWarps = kThreads / 32;
   constexpr int kU = 4;  // vertices per lane per step: kU independent head[] loads, then kU probes in flight
   __shared__ unsigned short s_q[kWarps][1024];  // vertex = (w0 << 5) + entry
@@ -426,9 +454,10 @@ bfs_pull_first_kernel(int n_vertices, const int2* __restrict__ head, unsigned* _
   const int warps = (gridDim.x * kThreads) >> 5;
   const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
   unsigned probes = 0, found_cnt = 0, retry_cnt = 0;
-  for (int w0 = gw * 32; w0 < words; w0 += warps * 32) {
+  for (int w0 = gw * batch_words; w0 < words; w0 += warps * batch_words) {
     const int my_wi = w0 + lane;
-    const unsigned my_vis = my_wi < words ? visited[my_wi] : 0xffffffffu;
+    const bool mine = lane < batch_words && my_wi < words;  // this lane holds a word of the batch
+    const unsigned my_vis = mine ? visited[my_wi] : 0xffffffffu;
     unsigned m = ~my_vis;
     if (my_wi == words - 1 && (n_vertices & 31))
       m &= (1u << (n_vertices & 31)) - 1u;  // bits past the last vertex are not vertices
@@ -445,6 +474,18 @@ bfs_pull_first_kernel(int n_vertices, const int2* __restrict__ head, unsigned* _
     }
     __syncwarp();
     const int vbase = w0 << 5;
+    if (fill && fill_premark) {  // vertices without in-edges: never looked at below, never labelled by anybody
+      const unsigned my_dead = mine ? fill_premark[my_wi] : 0u;
+      unsigned any = __ballot_sync(kFull, my_dead != 0u);
+      while (any) {
+        const int wl = __ffs(any) - 1;
+        any &= any - 1;
+        const unsigned bits = __shfl_sync(kFull, my_dead, wl);
+        const int v = ((w0 + wl) << 5) + lane;
+        if (((bits >> lane) & 1u) && v < n_vertices && v != source)
+          dist[v] = INT_MAX;
+      }
+    }
     for (int i0 = 0; i0 < total; i0 += 32 * kU) {
       int v[kU];
       int2 h[kU];
@@ -482,13 +523,16 @@ bfs_pull_first_kernel(int n_vertices, const int2* __restrict__ head, unsigned* _
         if (hit[k]) {
           dist[v[k]] = next_level;
           atomicOr(&s_found[warp][wl], bit);
-        } else if (again[k] && !(h[k].y & kNoMoreNeighbors)) {
-          atomicOr(&s_retry[warp][wl], bit);
+        } else {
+          if (fill)
+            dist[v[k]] = INT_MAX;  // K2 overwrites it if it finds the vertex after all
+          if (again[k] && !(h[k].y & kNoMoreNeighbors))
+            atomicOr(&s_retry[warp][wl], bit);
         }
       }
     }
     __syncwarp();
-    if (my_wi < words) {
+    if (mine) {
       const unsigned fm = s_found[warp][lane], rm = s_retry[warp][lane];
       next[my_wi] = fm;
       retry_map[my_wi] = rm;
@@ -512,6 +556,14 @@ bfs_pull_first_kernel(int n_vertices, const int2* __restrict__ head, unsigned* _
   }
 }
 
+/// Words per pass of the pull kernels for a map of `words` words swept by `warps` resident warps (K1 / K2).
+inline int pull_batch_words(int words, int warps) {
+  int bw = 32;
+  while (bw > 8 && words / bw < 3 * warps)
+    bw >>= 1;
+  return bw;
+}
+
 /// Set v's bit in `map` (RED.OR, no return value).
 __device__ __forceinline__ void bitmap_set(unsigned* map, bool on, int v) {
   if (on)
@@ -529,7 +581,7 @@ template <int kThreads, int kWords, int kSerial, typename FrontierTest>
 __global__ void __launch_bounds__(kThreads)
 bfs_pull_rest_kernel(csr_view_t in, const unsigned* __restrict__ retry_map, unsigned* visited,
                      FrontierTest in_frontier, unsigned* next, int* dist, int next_level, ctrl_t* ctrl,
-                     int* next_count) {
+                     int* next_count, int batch_words = kWords) {
   static_assert(kWords <= 32, "one lane per word");
   __shared__ int s_q[kThreads / 32][kWords * 32];
   int* q = s_q[threadIdx.x >> 5];
@@ -541,9 +593,9 @@ bfs_pull_rest_kernel(csr_view_t in, const unsigned* __restrict__ retry_map, unsi
   const int* __restrict__ ci = in.column_indices;
   unsigned long long scanned = 0;
   int found_cnt = 0;
-  for (int w0 = gw * kWords; w0 < words; w0 += warps * kWords) {
+  for (int w0 = gw * batch_words; w0 < words; w0 += warps * batch_words) {
     const int my_wi = w0 + lane;
-    unsigned m = (lane < kWords && my_wi < words) ? retry_map[my_wi] : 0u;
+    unsigned m = (lane < batch_words && my_wi < words) ? retry_map[my_wi] : 0u;
     const int c = __popc(m);
     const int incl = warp_inclusive_sum(c);
     const int total = __shfl_sync(kFull, incl, 31);
@@ -733,8 +785,11 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
       ws.launches += 1;
     }
   }
+  // Direction-optimised runs leave the labels of unreached vertices to the first pull level (bfs_reset_kernel)
+  static const bool eager_fill = std::getenv("B2G_BFS_EAGER_FILL") != nullptr;
+  bool dist_filled = !(can_pull && !legacy_pull && !eager_fill);
   bfs_reset_kernel<<<sms * 8, 256, 0, st>>>(dist, sc.visited.ptr, sc.fbm.ptr, V, source,
-                                             sc.q[0].ptr, sc.counts.ptr, premark);
+                                             sc.q[0].ptr, sc.counts.ptr, premark, dist_filled ? 1 : 0);
   ws.launches += 1;
   int cur = 0;
   int level = 0;
@@ -829,9 +884,12 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
         const bitmap_frontier_t in_frontier{fbm};
         bfs_pull_first_kernel<256><<<sms * 8, 256, 0, st>>>(V, sc.first_nb.ptr, sc.visited.ptr, in_frontier, nbm,
                                                             sc.retry_map.ptr, dist, level + 1, ca,
-                                                            sc.counts.ptr + 2);
+                                                            sc.counts.ptr + 2, premark, dist_filled ? 0 : 1, source,
+                                                            pull_batch_words(words, sms * 64));
+        dist_filled = true;
         bfs_pull_rest_kernel<256, 32, 8><<<sms * 6, 256, 0, st>>>(in_g, sc.retry_map.ptr, sc.visited.ptr, in_frontier,
-                                                                  nbm, dist, level + 1, cb, sc.counts.ptr + 2);
+                                                                  nbm, dist, level + 1, cb, sc.counts.ptr + 2,
+                                                                  pull_batch_words(words, sms * 48));
         ws.launches += 1;
       } else if (!unv_valid) {  // first pull level of a run of pull levels: sweep every visited word
         B2G_CHECK(cudaMemsetAsync(sc.counts.ptr + 4, 0, sizeof(int), st));
@@ -928,6 +986,10 @@ inline int bfs_run(workspace_t& ws, bfs_scratch_t& sc, const csr_view_t& out_g,
     if (!m_known)
       m_f = sc.h_fb->edges;  // a stand-in for the `explored` estimate of the direction heuristic only
     ++level;
+  }
+  if (!dist_filled) {  // no pull level happened: write the unreached vertices' labels now
+    bfs_fill_unreached_kernel<<<sms * 8, 256, 0, st>>>(dist, sc.visited.ptr, premark, V, source);
+    ws.launches += 1;
   }
   if (levels)
     for (int l = 0; l < level && l < 64; ++l)

@@ -277,9 +277,11 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
       // K1 + K2 over this rank's rows (bfs.cuh): K1 writes every next-frontier word, K2 ORs its finds in
       const part_frontier_t in_frontier{pt, all, wpr};
       bfs_pull_first_kernel<256><<<sms * 8, 256, 0, st>>>(pt.n_local, S.first_nb.ptr, S.visited.ptr, in_frontier, nbm,
-                                                          S.retry_map.ptr, S.dist.ptr, level + 1, c, S.counts.ptr + 2);
+                                                          S.retry_map.ptr, S.dist.ptr, level + 1, c, S.counts.ptr + 2, nullptr, 0,
+                                                          -1, pull_batch_words(S.local_words(), sms * 64));
       bfs_pull_rest_kernel<256, 32, 8><<<sms * 6, 256, 0, st>>>(in_view, S.retry_map.ptr, S.visited.ptr, in_frontier, nbm,
-                                                                S.dist.ptr, level + 1, c2, S.counts.ptr + 2);
+                                                                S.dist.ptr, level + 1, c2, S.counts.ptr + 2,
+                                                                pull_batch_words(S.local_words(), sms * 48));
       part_fold_edges_kernel<<<1, 1, 0, st>>>(c, c2);
       ws.launches += 3;
       std::swap(fbm, nbm);

@@ -717,9 +717,11 @@ inline void part_bfs_p2p_run(workspace_t& ws, const csr_view_t& view, const csr_
         ctrl_t* c2 = ws.next_ctrl();
         bfs_pull_first_kernel<256><<<sms * 8, 256, 0, st>>>(pt.n_local, S.first_nb.ptr, S.visited.ptr, in_frontier,
                                                             nxt_seg, S.retry_map.ptr, S.dist.ptr, level + 1, c,
-                                                            S.counts.ptr + 2);
+                                                            S.counts.ptr + 2, nullptr, 0, -1,
+                                                            pull_batch_words(S.local_words(), sms * 64));
         bfs_pull_rest_kernel<256, 32, 8><<<sms * 6, 256, 0, st>>>(in_view, S.retry_map.ptr, S.visited.ptr, in_frontier,
-                                                                  nxt_seg, S.dist.ptr, level + 1, c2, S.counts.ptr + 2);
+                                                                  nxt_seg, S.dist.ptr, level + 1, c2, S.counts.ptr + 2,
+                                                                  pull_batch_words(S.local_words(), sms * 48));
         part_fold_edges_kernel<<<1, 1, 0, st>>>(c, c2);
         mark("sweep");
         if (np > 1) {

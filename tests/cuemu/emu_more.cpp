@@ -280,7 +280,7 @@ static void check_bottom_up(std::mt19937& rng) {
     std::vector<int> dist_c(V);
     for (int v = 0; v < words * 32; ++v) {
       if (v < V)
-        dist_c[v] = ref[v];
+        dist_c[v] = ref[v] != INT_MAX ? ref[v] : -5;  // unlabelled so far: the reset left them unwritten (fill mode)
       if (v >= V || ref[v] != INT_MAX || adj[v].empty())
         visited_c[v >> 5] |= 1u << (v & 31);
     }
@@ -291,7 +291,7 @@ static void check_bottom_up(std::mt19937& rng) {
     const bitmap_frontier_t in_f{fbm.data()};
     cuemu::launch(3, 256, 0, 1, [&] {
       bfs_pull_first_kernel<256>(V, first_nb.data(), visited_c.data(), in_f, nbm_c.data(), retry_map.data(),
-                                 dist_c.data(), 3, &ca, &found_c); });
+                                 dist_c.data(), 3, &ca, &found_c, dead.data(), 1, source); });
     // K1 alone: exactly the vertices whose first or second in-neighbour is in the frontier; misses with a third
     // in-neighbour to look at -> retry map; the probe count is 1 per vertex + 1 per first-probe miss with a second
     std::set<int> k1_found, k1_retry, k1_single;
@@ -319,7 +319,22 @@ static void check_bottom_up(std::mt19937& rng) {
     cuemu::launch(3, 256, 0, 1, [&] {
       bfs_pull_rest_kernel<256, 32, 8>(g, retry_map.data(), visited_c.data(), in_f, nbm_c.data(), dist_c.data(), 3, &cb,
                                        &found_c); });
-    CHECK(found_c == next_count && dist_c == dist);
+    CHECK(found_c == next_count && dist_c == dist);  // incl. INT_MAX written by K1's fill mode for the unreached
+    {  // the deferred fill when no pull level happens: every unlabelled vertex except the source
+      std::vector<int> d2(V);
+      std::vector<unsigned> vis2(words + 4, 0u);
+      for (int v = 0; v < words * 32; ++v) {
+        if (v < V)
+          d2[v] = ref[v] != INT_MAX ? ref[v] : -9;
+        if (v >= V || ref[v] != INT_MAX || adj[v].empty())
+          vis2[v >> 5] |= 1u << (v & 31);
+      }
+      cuemu::launch(3, 64, 0, 1, [&] { bfs_fill_unreached_kernel(d2.data(), vis2.data(), dead.data(), V, source); });
+      bool fill_ok = true;
+      for (int v = 0; v < V; ++v)
+        fill_ok = fill_ok && d2[v] == ref[v];
+      CHECK(fill_ok);
+    }
     bool same_maps = true;
     for (int v = 0; v < V; ++v)
       same_maps = same_maps && (((nbm_c[v >> 5] ^ nbm[v >> 5]) >> (v & 31)) & 1u) == 0 &&
@@ -341,10 +356,10 @@ static void check_bottom_up(std::mt19937& rng) {
     const bitmap_frontier_t in_f2{nbm_c.data()};
     cuemu::launch(3, 256, 0, 1, [&] {
       bfs_pull_first_kernel<256>(V, first_nb.data(), visited_c.data(), in_f2, nbm_d.data(), retry_map.data(),
-                                 dist_c.data(), 4, &ca, &found_d); });
+                                 dist_c.data(), 4, &ca, &found_d, nullptr, 0, -1, /*batch_words=*/8); });
     cuemu::launch(3, 256, 0, 1, [&] {
       bfs_pull_rest_kernel<256, 32, 8>(g, retry_map.data(), visited_c.data(), in_f2, nbm_d.data(), dist_c.data(), 4, &cb,
-                                       &found_d); });
+                                       &found_d, /*batch_words=*/16); });
     bool ok2 = found_d == static_cast<int>(f2.size());
     for (int v = 0; v < V; ++v) {
       const bool f = f2.count(v) != 0;
