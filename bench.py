@@ -706,14 +706,18 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="partitioned workloads: frontier exchange by our kernels over peer memory, or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--reference-gpu", action="store_true",
+    ap.add_argument("--reference-gpu", dest="reference_gpu", action="store_true", default=None,
                     help="also time the UNMODIFIED reference GPU kernels (oracle/_ref/gunrock_ref_gpu, built for "
-                         "sm_100a with the atomics fix of SURVEY.md F2) on the same graphs and GPU; N = 1 only")
+                         "sm_100a with the atomics fix of SURVEY.md F2) on the same graphs and GPU; N = 1 only.  "
+                         "Default: on for the default line (no --workload), off otherwise")
+    ap.add_argument("--no-reference-gpu", dest="reference_gpu", action="store_false")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
     explicit = args.workload is not None
+    if args.reference_gpu is None:   # the same-GPU reference row belongs to the default line
+        args.reference_gpu = (not explicit) and not args.scale and not args.no_cpu_baseline
     name = args.workload or (HEADLINE_N if world > 1 else HEADLINE_1)
     if args.impl == "reference" and not explicit:
         name = HEADLINE_N if args.gpus > 1 else HEADLINE_1

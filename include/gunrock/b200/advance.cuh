@@ -459,14 +459,34 @@ advance_hub_kernel(advance_params_t p, Op op) {
       s_desc[slot][lane] = d;
     }
   };
+  // The bulk copy moves whole 16-byte groups.  The group that holds the slab's last edge may reach past the END OF
+  // THE ARRAY (by at most 3 elements, only for the last slab of the last row when E % 4 != 0): owned graphs are
+  // padded, but a view over the caller's arrays (b2g_graph_view_csr, graph::build over a user's csr_t) is not --
+  // so the copy stops at the last whole group inside the array and `tail_fix` loads the rest with plain loads.
+  const int n_edges = p.g.n_edges;
   auto issue = [&](const hub_slab_t& d, int buf) {  // one thread
     const int a0 = d.e0 & ~3;
-    const int a1 = (d.e0 + d.cnt + 3) & ~3;
-    const uint32_t bytes = static_cast<uint32_t>(a1 - a0) * 4u;
-    mbar_expect_tx(&s_bar[buf], use_vals ? 2 * bytes : bytes);
-    bulk_g2s(&s_idx[buf][0], ci + a0, bytes, &s_bar[buf]);
-    if (use_vals)
-      bulk_g2s(&s_val[kWeights ? buf : 0][0], vals + a0, bytes, &s_bar[buf]);
+    const int a1 = min((d.e0 + d.cnt + 3) & ~3, n_edges & ~3);
+    const uint32_t bytes = a1 > a0 ? static_cast<uint32_t>(a1 - a0) * 4u : 0u;
+    mbar_expect_tx(&s_bar[buf], use_vals ? 2 * bytes : bytes);  // 0 bytes: a plain arrival, the phase completes
+    if (bytes) {
+      bulk_g2s(&s_idx[buf][0], ci + a0, bytes, &s_bar[buf]);
+      if (use_vals)
+        bulk_g2s(&s_val[kWeights ? buf : 0][0], vals + a0, bytes, &s_bar[buf]);
+    }
+  };
+  auto tail_fix = [&](const hub_slab_t& d, int buf) {  // all threads; uniform condition
+    const int a0 = d.e0 & ~3;
+    const int covered = n_edges & ~3;  // first element the bulk copy could not bring
+    if (d.e0 + d.cnt > covered) {
+      const int i = covered + static_cast<int>(threadIdx.x);
+      if (threadIdx.x < 3 && i < d.e0 + d.cnt && i >= a0) {
+        s_idx[buf][i - a0] = ci[i];
+        if (use_vals)
+          s_val[kWeights ? buf : 0][i - a0] = vals[i];
+      }
+      __syncthreads();
+    }
   };
   if (warp == 0)
     fetch_range(0);
@@ -494,6 +514,7 @@ advance_hub_kernel(advance_params_t p, Op op) {
     if (tma) {
       mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
       phase_bits ^= 1u << buf;
+      tail_fix(d, buf);
     }
     for (int i0 = 0; i0 < cnt; i0 += kThreads * kHB) {
       int e[kHB], nbv[kHB];

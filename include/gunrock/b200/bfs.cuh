@@ -556,12 +556,18 @@ bfs_pull_first_kernel(int n_vertices, const int2* __restrict__ head, unsigned* _
   }
 }
 
-/// Words per pass of the pull kernels for a map of `words` words swept by `warps` resident warps (K1 / K2).
-inline int pull_batch_words(int words, int warps) {
-  int bw = 32;
-  while (bw > 8 && words / bw < 3 * warps)
-    bw >>= 1;
-  return bw;
+/// Words per pass of the pull kernels (K1 / K2).  32 everywhere: measured on B200 with maps of 131 K words (RMAT-22)
+/// and 262 K words (one of eight ranks of RMAT-26), smaller batches that would keep more warps busy lost -- the first
+/// pull level took 0.058 / 0.055 / 0.049 ms with 8 / 16 / 32 words on RMAT-22 (profiles/r2_l_pull_batch_ab.txt): the
+/// queue walk amortises better over long batches than idle warps cost.  B2G_PULL_BATCH=8|16|32 keeps the A/B.
+inline int pull_batch_words(int /*words*/, int /*warps*/) {
+  static const char* force = std::getenv("B2G_PULL_BATCH");
+  if (force) {
+    const int f = std::atoi(force);
+    if (f == 8 || f == 16 || f == 32)
+      return f;
+  }
+  return 32;
 }
 
 /// Set v's bit in `map` (RED.OR, no return value).

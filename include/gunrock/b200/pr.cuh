@@ -204,16 +204,18 @@ pr_pull_tile_kernel(csr_view_t t, int ntiles, const int* __restrict__ first_owne
     mbar_fence_init();
   }
   __syncthreads();
+  // The bulk copy moves whole 16-byte groups and never reaches past the end of the arrays (a view over the caller's
+  // arrays is not padded): the last tile's trailing E % 4 elements are loaded with plain loads after the wait.
   auto issue = [&](int tile, int buf) {  // thread 0 only
     int t0 = tile * kPrTile;
     int cnt = min(kPrTile, E - t0);
-    uint32_t bytes = static_cast<uint32_t>((cnt + 3) & ~3) * 4u;
-    if (bytes == 0)
-      bytes = 16;  // E == 0: one empty tile, arrays are padded
-    mbar_expect_tx(&s_bar[buf], kWeights ? 2 * bytes : bytes);
-    bulk_g2s(&s_src[buf][0], t.column_indices + t0, bytes, &s_bar[buf]);
-    if (kWeights)
-      bulk_g2s(&s_w[kWeights ? buf : 0][0], t.values + t0, bytes, &s_bar[buf]);
+    uint32_t bytes = static_cast<uint32_t>(max(cnt, 0) & ~3) * 4u;
+    mbar_expect_tx(&s_bar[buf], kWeights ? 2 * bytes : bytes);  // 0 bytes: a plain arrival
+    if (bytes) {
+      bulk_g2s(&s_src[buf][0], t.column_indices + t0, bytes, &s_bar[buf]);
+      if (kWeights)
+        bulk_g2s(&s_w[kWeights ? buf : 0][0], t.values + t0, bytes, &s_bar[buf]);
+    }
   };
   if (threadIdx.x == 0) {
     s_ticket[0] = atomicAdd(&ctrl->work, 1);
@@ -239,6 +241,15 @@ pr_pull_tile_kernel(csr_view_t t, int ntiles, const int* __restrict__ first_owne
     const int cnt = t1 - t0;
     mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
     phase_bits ^= 1u << buf;
+    if (cnt & 3) {  // uniform: only the last tile of a graph with E % 4 != 0
+      const int k = (cnt & ~3) + static_cast<int>(threadIdx.x);
+      if (threadIdx.x < 3 && k < cnt) {
+        s_src[buf][k] = t.column_indices[t0 + k];
+        if (kWeights)
+          s_w[kWeights ? buf : 0][k] = t.values[t0 + k];
+      }
+      __syncthreads();
+    }
     // ---- gather contributions of the slab ------------------------------------------------
 #pragma unroll
     for (int j = 0; j < kPrTile / kThreads; ++j) {

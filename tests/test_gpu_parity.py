@@ -194,6 +194,56 @@ def test_device_tensor_results_and_stream(gb):
     G.close()
 
 
+@pytest.mark.parametrize("tail", [1, 2, 3])
+def test_views_over_unpadded_arrays_whose_last_row_is_a_hub(gb, tail):
+    """A non-owning view (b2g_graph_view_csr) over arrays of EXACTLY E elements with E % 4 != 0 whose last row is
+    a hub: the TMA slab copies of the hub bin and of the PageRank tiles move whole 16-byte groups and must stop at
+    the end of the caller's arrays -- the trailing 1-3 elements arrive through plain loads.  The arrays sit at the
+    very end of one exactly-sized allocation, sentinels behind them would show a read past the end as a wrong
+    neighbour."""
+    import torch
+    n = 9000
+    hub = n - 1
+    deg_hub = 6002 + tail                  # directed star into a chain: hub -> 0..deg_hub-1, v -> v+1
+    src = np.concatenate([np.arange(n - 2), np.full(deg_hub, hub)]).astype(np.int64)
+    dst = np.concatenate([np.arange(1, n - 1), np.arange(deg_hub)]).astype(np.int64)
+    order = np.lexsort((dst, src))
+    src, dst = src[order], dst[order]
+    ro = np.zeros(n + 1, np.int32)
+    np.cumsum(np.bincount(src, minlength=n), out=ro[1:])
+    ci = dst.astype(np.int32)
+    E = len(ci)
+    assert E % 4 == tail
+    w = oracle.edge_weights(3, ro, ci, True)
+    # one allocation: [ro | ci | w | poison]: ci and w end exactly where the next array / the poison begins
+    pad_ro = (-(n + 1)) % 4
+    blob = torch.full((n + 1 + pad_ro + E + (-E) % 4 + E + 64,), -1, dtype=torch.int32, device="cuda")
+    o_ci = n + 1 + pad_ro
+    o_w = o_ci + E + (-E) % 4
+    blob[:n + 1] = torch.from_numpy(ro).cuda()
+    blob[o_ci:o_ci + E] = torch.from_numpy(ci).cuda()
+    blob[o_ci + E:o_w] = 0x7fffffff                      # what an over-read of the column indices would see
+    tw = blob[o_w:o_w + E].view(torch.float32)
+    tw.copy_(torch.from_numpy(w).cuda())
+    blob[o_w + E:] = 0x7fc00000                          # NaN bits behind the weights
+    G = gb.graph_t.view_csr(blob[:n + 1], blob[o_ci:o_ci + E], tw, symmetric=False)
+    for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
+        for thr in (256, 4096):
+            opt = gb.options_t(advance_load_balance=lb, hub_threshold=thr)
+            d = np.empty(n, np.int32)
+            gb.bfs(G, hub, d, options=opt)
+            assert np.array_equal(d, oracle.bfs(ro, ci, hub)), (lb, thr)
+            f = np.empty(n, np.float32)
+            gb.sssp(G, hub, f, options=opt)
+            assert np.array_equal(f.view(np.uint32), oracle.sssp(ro, ci, w, hub).view(np.uint32)), (lb, thr)
+    G.build_transpose()
+    p = np.empty(n, np.float32)
+    st = gb.pr(G, p)
+    pe, it = oracle.pr(ro, ci, w)
+    assert st.iterations == it and np.allclose(p, pe, rtol=1e-6, atol=0)
+    G.close()
+
+
 @pytest.mark.parametrize("mirror,weights", [(True, None), (False, None), (False, True)])
 def test_pagerank_vs_oracle(gb, mirror, weights):
     ro, ci = oracle.rmat_csr(13, 8, 31, mirror=mirror)
