@@ -120,6 +120,7 @@ _SYMBOLS = [
     "b2g_part_p2p_window_create", "b2g_part_p2p_attach", "b2g_part_p2p_detach", "b2g_part_bfs_p2p",
     # NCCL exchange driven from C++
     "b2g_nccl_unique_id", "b2g_part_nccl_init", "b2g_part_bfs_nccl", "b2g_part_nccl_finalize",
+    "b2g_part_sssp_nccl", "b2g_part_pr_nccl", "b2g_part_pr_outweights", "b2g_part_pr_begin_weighted",
 ]
 
 

@@ -74,6 +74,10 @@ def _bind():
     L.b2g_part_nccl_init.argtypes = [vp, vp, ip, ip]
     L.b2g_part_bfs_nccl.argtypes = [vp, ip, C.c_longlong, C.POINTER(_Options), C.POINTER(_Stats)]
     L.b2g_part_nccl_finalize.argtypes = [vp]
+    L.b2g_part_sssp_nccl.argtypes = [vp, ip, ip, C.POINTER(_Options), C.POINTER(_Stats)]
+    L.b2g_part_pr_nccl.argtypes = [vp, C.c_float, C.c_float, ip, C.POINTER(_Stats)]
+    L.b2g_part_pr_outweights.argtypes = [vp, vp]
+    L.b2g_part_pr_begin_weighted.argtypes = [vp, C.c_float, vp]
     L._mg_bound = True
     return L
 
@@ -113,10 +117,11 @@ class PartitionedGraph:
         v = [C.c_int() for _ in range(5)]
         _check(L.b2g_part_info(self._h, *[C.byref(x) for x in v]), "b2g_part_info")
         self.n_global, self.nparts, self.part, self.n_local, self.words_per_rank = (x.value for x in v)
-        ne = C.c_int()
+        ne, hv = C.c_int(), C.c_int()
         L.b2g_graph_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
-        _check(L.b2g_graph_info(self._h, None, C.byref(ne), None, None), "b2g_graph_info")
+        _check(L.b2g_graph_info(self._h, None, C.byref(ne), C.byref(hv), None), "b2g_graph_info")
         self.n_local_edges = ne.value
+        self.has_values = bool(hv.value)
 
     def max_degree_vertex(self):
         """(global id, degree) of this rank's highest-degree vertex."""
@@ -137,8 +142,20 @@ class PartitionedGraph:
         return PartitionedGraph(h.value)
 
     @staticmethod
-    def from_global_csr_weighted(ro, ci, vals, nparts: int, part: int, symmetric: bool = True):
-        lro, lci, lv = partition_csr(np.asarray(ro), np.asarray(ci), nparts, part, vals)
+    def from_global_csr_weighted(ro, ci, vals, nparts: int, part: int, symmetric: bool = True,
+                                 by_destination: bool = False):
+        """by_destination: the rank's rows are the IN-edge lists of its vertices, each in-edge with its own weight
+        (weighted PageRank pulls): the transpose is partitioned even when the graph is symmetric, because
+        w(u -> v) need not equal w(v -> u)."""
+        ro, ci, vals = np.asarray(ro), np.asarray(ci), np.asarray(vals)
+        if by_destination:
+            n = len(ro) - 1
+            src = np.repeat(np.arange(n, dtype=np.int64), np.diff(ro))
+            order = np.lexsort((src, ci))
+            t_ro = np.zeros(n + 1, np.int64)
+            np.cumsum(np.bincount(ci, minlength=n), out=t_ro[1:])
+            ro, ci, vals = t_ro.astype(np.int32), src[order].astype(np.int32), vals[order]
+        lro, lci, lv = partition_csr(ro, ci, nparts, part, vals)
         h = C.c_void_p()
         _check(_bind().b2g_graph_create_csr_part_weighted(
             len(ro) - 1, nparts, part, len(lci), lro.ctypes.data, lci.ctypes.data if len(lci) else None,
@@ -332,6 +349,20 @@ class CudaRankEngine:
         out.kernel_launches = int(st.kernel_launches)
         return out
 
+    def sssp_nccl(self, source: int, send_capacity: int = 0):
+        """COLLECTIVE: the whole partitioned SSSP inside the library (b2g_part_sssp_nccl).  Returns (iterations,
+        relaxed edges)."""
+        st = _Stats()
+        _check(self.L.b2g_part_sssp_nccl(self.G._h, int(source), int(send_capacity), C.byref(self.opt), C.byref(st)),
+               "b2g_part_sssp_nccl")
+        return int(st.iterations), int(st.edges_touched)
+
+    def pr_nccl(self, alpha: float = 0.85, tol: float = 1e-6, max_iter: int = 0) -> int:
+        """COLLECTIVE: the whole partitioned PageRank inside the library (b2g_part_pr_nccl).  Returns iterations."""
+        st = _Stats()
+        _check(self.L.b2g_part_pr_nccl(self.G._h, alpha, tol, int(max_iter), C.byref(st)), "b2g_part_pr_nccl")
+        return int(st.iterations)
+
     # ---- partitioned SSSP steps ---------------------------------------------------------------------
     def sssp_begin(self, source: int, send_capacity: int):
         _check(self.L.b2g_part_sssp_begin(self.G._h, int(source), int(send_capacity)), "b2g_part_sssp_begin")
@@ -361,6 +392,20 @@ class CudaRankEngine:
 
     def pr_begin(self, alpha: float, outdeg_global):
         _check(self.L.b2g_part_pr_begin(self.G._h, alpha, outdeg_global.data_ptr()), "b2g_part_pr_begin")
+
+    @property
+    def weighted(self) -> bool:
+        return bool(self.G.has_values)
+
+    def pr_outweights(self):
+        """fp64 sums of the local in-edges' weights per source vertex (all-reduce them, then pr_begin_weighted)."""
+        t = self.torch.empty(self.n_global, dtype=self.torch.float64, device="cuda")
+        _check(self.L.b2g_part_pr_outweights(self.G._h, t.data_ptr()), "b2g_part_pr_outweights")
+        return t
+
+    def pr_begin_weighted(self, alpha: float, outweight_global):
+        _check(self.L.b2g_part_pr_begin_weighted(self.G._h, alpha, outweight_global.data_ptr()),
+               "b2g_part_pr_begin_weighted")
 
     def pr_prepare(self, alpha: float, c_local, dsum_local):
         _check(self.L.b2g_part_pr_prepare(self.G._h, alpha, c_local.data_ptr(), dsum_local.data_ptr()),
@@ -648,6 +693,20 @@ def bfs_rank_nccl(engine, source: int, total_edges: int, direction: int = advanc
     return engine.distances(), st
 
 
+def sssp_rank_nccl(engine, source: int, cap_s: int = 0):
+    """This rank's part of a partitioned SSSP, iteration loop and NCCL exchange in C++ (`b2g_part_sssp_nccl`).
+    Returns (owned fp32 distances, iterations, relaxed edges)."""
+    it, relaxed = engine.sssp_nccl(source, cap_s)
+    return engine.sssp_distances(), it, relaxed
+
+
+def pr_rank_nccl(engine, alpha: float = 0.85, tol: float = 1e-6, max_iter: int = 0):
+    """This rank's part of a partitioned PageRank, iteration loop and NCCL collectives in C++ (`b2g_part_pr_nccl`);
+    weighted graphs included.  Returns (owned ranks, iterations)."""
+    it = engine.pr_nccl(alpha, tol, max_iter)
+    return engine.pr_ranks(), it
+
+
 def p2p_connect(engine, comm) -> None:
     """One process per GPU: allocate the rank's window, exchange the CUDA IPC handles over the
     communicator (the only use of torch.distributed on this path) and map every peer's window."""
@@ -801,10 +860,16 @@ def pr_rank(engine, comm, alpha: float = 0.85, tol: float = 1e-6, max_iter: int 
     dev = "cpu" if comm.backend == "gloo" else "cuda"
     R = rows_of(engine.n_global, P, 0)
     with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
-        outdeg = engine.pr_outdegrees()
-        if P > 1:
-            dist.all_reduce(outdeg, group=comm.group)
-        engine.pr_begin(alpha, outdeg)
+        if getattr(engine, "weighted", False):
+            outw = engine.pr_outweights()
+            if P > 1:
+                dist.all_reduce(outw, group=comm.group)
+            engine.pr_begin_weighted(alpha, outw)
+        else:
+            outdeg = engine.pr_outdegrees()
+            if P > 1:
+                dist.all_reduce(outdeg, group=comm.group)
+            engine.pr_begin(alpha, outdeg)
         c_local = torch.zeros(R, dtype=torch.float32, device=dev)
         c_all = torch.zeros(P * R, dtype=torch.float32, device=dev) if P > 1 else c_local
         dsum = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -838,9 +903,14 @@ def pr_lockstep(engines: Sequence, alpha: float = 0.85, tol: float = 1e-6, max_i
     for e in engines[1:]:
         e.use_stream(stream)
     with torch.cuda.stream(stream):
-        outdeg = sum(e.pr_outdegrees() for e in engines)
-        for e in engines:
-            e.pr_begin(alpha, outdeg)
+        if engines[0].weighted:
+            outw = sum(e.pr_outweights() for e in engines)
+            for e in engines:
+                e.pr_begin_weighted(alpha, outw)
+        else:
+            outdeg = sum(e.pr_outdegrees() for e in engines)
+            for e in engines:
+                e.pr_begin(alpha, outdeg)
         c_loc = [torch.zeros(R, dtype=torch.float32, device="cuda") for _ in engines]
         ds = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in engines]
         er = [torch.zeros(1, dtype=torch.float32, device="cuda") for _ in engines]

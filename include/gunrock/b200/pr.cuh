@@ -363,6 +363,15 @@ static __global__ void part_pr_outdeg_kernel(const int* __restrict__ src_ids, in
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x)
     atomicAdd(outdeg + src_ids[e], 1);
 }
+/// outweight[src] += w(e) for every local in-edge, in fp64 (global array, all-reduced afterwards): the weighted
+/// graph's row sums.  The single-GPU reset sums a row's weights sequentially in fp32 as the reference's loop does
+/// (pr.hxx:65-93); a vertex's out-edges are spread over the ranks here, so the sum is taken in fp64 and rounded
+/// once -- it can differ from the sequential fp32 sum in the last place, well inside PageRank's 1e-6 tolerance.
+static __global__ void part_pr_outweight_kernel(const int* __restrict__ src_ids, const float* __restrict__ w,
+                                                int n_edges, double* outweight) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x)
+    atomicAdd(outweight + src_ids[e], static_cast<double>(w[e]));
+}
 /// position of global vertex u in the rank-major gathered array: (u % P) * R + u / P
 static __global__ void part_pr_remap_kernel(const int* __restrict__ src_ids, int n_edges, int nparts,
                                             int rows_per_rank, int* __restrict__ out) {
@@ -381,6 +390,18 @@ static __global__ void part_pr_reset_kernel(int n_local, int nparts, int part, i
     plast[l] = 0.0f;
     int d = outdeg[l * nparts + part];
     float val = d <= (1 << 24) ? static_cast<float>(d) : 16777216.0f;
+    iw[l] = val != 0.0f ? __fdiv_rn(alpha, val) : 0.0f;
+  }
+}
+/// The weighted form: iweights from the global fp64 row sums of the weights.
+static __global__ void part_pr_reset_weighted_kernel(int n_local, int nparts, int part, int n_global, float alpha,
+                                                     const double* __restrict__ outweight, float* p, float* plast,
+                                                     float* iw) {
+  const float p0 = static_cast<float>(1.0 / static_cast<double>(n_global));
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n_local; l += gridDim.x * blockDim.x) {
+    p[l] = p0;
+    plast[l] = 0.0f;
+    const float val = static_cast<float>(outweight[l * nparts + part]);
     iw[l] = val != 0.0f ? __fdiv_rn(alpha, val) : 0.0f;
   }
 }
@@ -446,7 +467,9 @@ static __global__ void part_pr_err_kernel(unsigned* err_bits, float* err_out) {
 /// Per-rank state of a partitioned PageRank.
 struct part_pr_state_t {
   int nparts = 1, part = 0, n_global = 0, n_local = 0, rows_per_rank = 0;
-  dbuf_t<int> outdeg;       // global out-degrees (after the host's all-reduce)
+  dbuf_t<int> outdeg;       // global out-degrees (after the all-reduce); the C++ NCCL loop's copy
+  dbuf_t<double> outweight; // weighted graphs: global row sums of the weights (same)
+  dbuf_t<float> c_local, c_all;  // the C++ NCCL loop's gather buffers (b2g_part_pr_nccl)
   dbuf_t<int> remapped;     // column ids -> positions in the gathered c array
   dbuf_t<float> p;          // owned ranks
   dbuf_t<double> dsum;      // [0] local dangling partial (in/out of the all-reduce)

@@ -246,11 +246,24 @@ int b2g_part_nccl_init(b2g_graph_t* g, const unsigned char* id128, int nranks, i
 int b2g_part_bfs_nccl(b2g_graph_t* g, int source, long long total_edges, const b2g_options_t* opt,
                       b2g_stats_t* stats);
 int b2g_part_nccl_finalize(b2g_graph_t* g);
+/* SSSP and PageRank whose iteration loop and NCCL collectives run inside the call (after b2g_part_nccl_init on a
+ * graph of the matching kind: edge values for SSSP, rows = in-edge lists for PageRank).  COLLECTIVE.
+ *  b2g_part_sssp_nccl: per iteration relax -> grouped Send/Recv of the (vertex, distance) rows, sized from the
+ *    frontier's all-reduced out-degree sum -> apply -> all-reduce of 4 x int64; send_capacity 0 = default; a row
+ *    that overflows restarts the run with rows four times as long.  Result: b2g_part_sssp_distances.
+ *  b2g_part_pr_nccl: all-reduce of the out-degrees (or fp64 row sums of the weights) once, then per iteration
+ *    prepare -> ncclAllGather(c) + all-reduce(dangling, fp64 sum) -> pull -> all-reduce(error, max); same
+ *    recurrence and stopping rule as algorithms/pr.hxx:107-195.  Result: b2g_part_pr_ranks, stats->iterations. */
+int b2g_part_sssp_nccl(b2g_graph_t* g, int source, int send_capacity, const b2g_options_t* opt,
+                       b2g_stats_t* stats);
+int b2g_part_pr_nccl(b2g_graph_t* g, float alpha, float tol, int max_iter, b2g_stats_t* stats);
 /* ---- multi-GPU PageRank (pull): the rank owns the DESTINATION vertices v % nparts == part and their
  * in-edges (a partitioned graph whose rows are in-edge lists: any symmetric partitioned graph, or
  * one created with by_destination != 0).  Per iteration the host side all-gathers c = plast*iweights,
- * all-reduces the dangling sum (fp64, sum) and the error (fp32, max) between these calls; unweighted
- * graphs only.  Everything is enqueued on the stream set with b2g_part_set_stream. */
+ * all-reduces the dangling sum (fp64, sum) and the error (fp32, max) between these calls.  A graph with
+ * edge values takes b2g_part_pr_outweights + b2g_part_pr_begin_weighted instead of the out-degree pair (its
+ * in-edge rows must carry the weight of each in-edge: partition the transpose WITH its values).  Everything is
+ * enqueued on the stream set with b2g_part_set_stream. */
 int b2g_graph_create_rmat_part_ex(int scale, long long n_pairs, unsigned long long seed, int mirror,
                                   int fold_vertices, int by_destination, int nparts, int part,
                                   b2g_graph_t** out);
@@ -258,6 +271,12 @@ int b2g_graph_create_rmat_part_ex(int scale, long long n_pairs, unsigned long lo
 int b2g_part_pr_outdegrees(b2g_graph_t* g, int* outdeg);
 /* Reset ranks and derive iweights from the ALL-REDUCED out-degrees (device, n_global ints). */
 int b2g_part_pr_begin(b2g_graph_t* g, float alpha, const int* outdeg_global);
+/* Weighted graphs: fp64 sums of the weights of the local in-edges per SOURCE vertex into outweight (device,
+ * n_global doubles, zeroed by the call); after the all-reduce, iweights = alpha / (float)sum.  The reference and
+ * the single-GPU path add a row's weights sequentially in fp32 (pr.hxx:65-93); a vertex's out-edges are spread
+ * over the ranks here, so the sum is fp64 and rounded once (last-place differences, inside the 1e-6 tolerance). */
+int b2g_part_pr_outweights(b2g_graph_t* g, double* outweight);
+int b2g_part_pr_begin_weighted(b2g_graph_t* g, float alpha, const double* outweight_global);
 /* plast = p, c_local = plast*iweights (device, rows_per_rank floats, zero padded), dsum_local (device
  * double) = this rank's dangling partial. */
 int b2g_part_pr_prepare(b2g_graph_t* g, float alpha, float* c_local, double* dsum_local);

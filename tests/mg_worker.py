@@ -65,6 +65,29 @@ def main():
     t = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     results["pagerank"] = [int(t.item()), iters]
+    # the same PageRank with the iteration loop and the collectives in C++ (b2g_part_pr_nccl)
+    eng = mg.CudaRankEngine(G)
+    mg.nccl_connect(eng, mg.TorchDistComm())
+    p, iters = mg.pr_rank_nccl(eng)
+    ok = iters == eit and bool(np.all(np.abs(p.cpu().numpy() - mine) <= 1e-6 * np.abs(mine)))
+    t = torch.tensor([int(ok)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    results["pagerank/nccl-cxx"] = [int(t.item()), iters]
+    G.close()
+    # weighted PageRank: in-edge rows with their own weights, fp64 row sums reduced over the ranks
+    dw = oracle.edge_weights(31, dro, dci, True)
+    G = mg.PartitionedGraph.from_global_csr_weighted(dro, dci, dw, world, rank, symmetric=False, by_destination=True)
+    pe, eit = oracle.pr(dro, dci, dw, 0.85, 1e-6)
+    mine = pe[rank::world]
+    eng = mg.CudaRankEngine(G)
+    mg.nccl_connect(eng, mg.TorchDistComm())
+    for name, run in (("pagerank-weighted", lambda: mg.pr_rank(eng, mg.TorchDistComm(), tol=0.0, max_iter=eit)),
+                      ("pagerank-weighted/nccl-cxx", lambda: mg.pr_rank_nccl(eng, tol=0.0, max_iter=eit))):
+        p, iters = run()
+        ok = iters == eit and bool(np.all(np.abs(p.cpu().numpy() - mine) <= 1e-6 * np.abs(mine)))
+        t = torch.tensor([int(ok)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        results[name] = [int(t.item()), iters]
     G.close()
     # partitioned SSSP over NCCL
     w = oracle.edge_weights(23, ro, ci, True)
@@ -75,6 +98,15 @@ def main():
     t = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     results["sssp"] = [int(t.item()), iters]
+    # the same SSSP with the iteration loop and the grouped Send / Recv in C++ (b2g_part_sssp_nccl); 8: overflow path
+    eng = mg.CudaRankEngine(G)
+    mg.nccl_connect(eng, mg.TorchDistComm())
+    for cap in (0, 8):
+        d, iters, relaxed = mg.sssp_rank_nccl(eng, src, cap)
+        ok = bool(np.array_equal(d.cpu().numpy().view(np.uint32), es.view(np.uint32)))
+        t = torch.tensor([int(ok)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        results[f"sssp/nccl-cxx/cap{cap}"] = [int(t.item()), iters]
     G.close()
     if rank == 0:
         print("MG_RESULT " + json.dumps(results), flush=True)

@@ -96,7 +96,7 @@ def test_nccl_two_or_more_gpus(gb):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("MG_RESULT ")][-1]
     res = json.loads(line[len("MG_RESULT "):])
-    assert len(res) == 58 and all(v[0] == 1 for v in res.values()), res
+    assert len(res) == 63 and all(v[0] == 1 for v in res.values()), res
 
 
 def test_cxx_nccl_level_loop_single_rank(gb):
@@ -118,6 +118,66 @@ def test_cxx_nccl_level_loop_single_rank(gb):
                 assert np.array_equal(d.cpu().numpy(), exp), (lb, src, direction)
                 assert st.levels == int(exp[exp < 2**31 - 1].max()) + 1
     G.close()
+
+
+def test_cxx_nccl_sssp_and_pagerank_single_rank(gb):
+    """world_size 1: the C++ iteration loops of the partitioned SSSP and PageRank (b2g_part_sssp_nccl,
+    b2g_part_pr_nccl): same kernels, statistics records and stopping rules as at N ranks, collectives skipped.
+    (N > 1: tests/mg_worker.py under torchrun.)"""
+    from gunrock_b200 import multi_gpu as mg
+    ro, ci = oracle.rmat_csr(13, 8, 606)
+    w = oracle.edge_weights(17, ro, ci, True)
+    deg = np.diff(ro)
+    G = mg.PartitionedGraph.from_global_csr_weighted(ro, ci, w, 1, 0)
+    for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
+        eng = mg.CudaRankEngine(G, gb.options_t(advance_load_balance=lb, hub_threshold=256))
+        eng.nccl_init(mg.nccl_unique_id())
+        for src in (int(deg.argmax()), int(np.flatnonzero(deg > 0)[-1])):
+            exp = oracle.sssp(ro, ci, w, src)
+            for cap in (0, 8):    # 8: a message row overflows -> the run restarts with longer rows
+                d, it, relaxed = mg.sssp_rank_nccl(eng, src, cap)
+                assert np.array_equal(d.cpu().numpy().view(np.uint32), exp.view(np.uint32)), (lb, src, cap)
+                assert it > 0 and relaxed > 0
+    G.close()
+    # PageRank: unweighted (in-edge rows of a directed graph) and weighted
+    ro, ci = oracle.rmat_csr(12, 8, 4321, mirror=False)
+    w = oracle.edge_weights(5, ro, ci, True)
+    for weights in (None, w):
+        if weights is None:
+            G = mg.PartitionedGraph.from_global_csr(ro, ci, 1, 0, symmetric=False, by_destination=True)
+        else:
+            G = mg.PartitionedGraph.from_global_csr_weighted(ro, ci, w, 1, 0, symmetric=False, by_destination=True)
+        eng = mg.CudaRankEngine(G)
+        eng.nccl_init(mg.nccl_unique_id())
+        exp, exp_iters = oracle.pr(ro, ci, weights, 0.85, 1e-6)
+        p, it = mg.pr_rank_nccl(eng)
+        assert abs(it - exp_iters) <= (0 if weights is None else 1)
+        p, it = mg.pr_rank_nccl(eng, tol=0.0, max_iter=exp_iters)
+        assert it == exp_iters
+        rel = np.abs(p.cpu().numpy() - exp) / np.maximum(np.abs(exp), np.finfo(np.float32).tiny)
+        assert rel.max() <= 1e-6, (weights is not None, rel.max())
+        G.close()
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_partitioned_weighted_pagerank_simulated_ranks(gb, P):
+    """Weighted PageRank over a partition by destination: every in-edge carries its own weight, the row sums of
+    the weights are reduced over the ranks in fp64 (b2g_part_pr_outweights / b2g_part_pr_begin_weighted)."""
+    from gunrock_b200 import multi_gpu as mg
+    for mirror in (True, False):
+        ro, ci = oracle.rmat_csr(12, 8, 99, mirror=mirror)
+        w = oracle.edge_weights(23, ro, ci, True)      # w(u->v) != w(v->u) in general, also when mirrored
+        graphs = [mg.PartitionedGraph.from_global_csr_weighted(ro, ci, w, P, r, symmetric=mirror, by_destination=True)
+                  for r in range(P)]
+        exp, exp_iters = oracle.pr(ro, ci, w, 0.85, 1e-6)
+        ps, iters = mg.pr_lockstep([mg.CudaRankEngine(g) for g in graphs])
+        assert abs(iters - exp_iters) <= 1
+        ps, iters = mg.pr_lockstep([mg.CudaRankEngine(g) for g in graphs], tol=0.0, max_iter=exp_iters)
+        got = mg.gather_distances([p.cpu().numpy() for p in ps], len(ro) - 1)
+        rel = np.abs(got - exp) / np.maximum(np.abs(exp), np.finfo(np.float32).tiny)
+        assert iters == exp_iters and rel.max() <= 1e-6, (P, mirror, rel.max())
+        for g in graphs:
+            g.close()
 
 
 def test_async_driver_single_rank(gb):

@@ -226,6 +226,7 @@ def test_views_over_unpadded_arrays_whose_last_row_is_a_hub(gb, tail):
     tw = blob[o_w:o_w + E].view(torch.float32)
     tw.copy_(torch.from_numpy(w).cuda())
     blob[o_w + E:] = 0x7fc00000                          # NaN bits behind the weights
+    torch.cuda.synchronize()      # the fills ran on torch's stream; the library launches on its own non-blocking one
     G = gb.graph_t.view_csr(blob[:n + 1], blob[o_ci:o_ci + E], tw, symmetric=False)
     for lb in (gb.load_balance_t.block_mapped, gb.load_balance_t.merge_path):
         for thr in (256, 4096):
