@@ -1,21 +1,27 @@
-// `bfs::run` over a multi-device `gcuda::multi_context_t` (the surface the reference declares in
-// include/gunrock/cuda/context.hxx:146-216 and never runs: its operators throw for size() != 1).
+// `bfs::run`, `sssp::run` and `pr::run` over a multi-device `gcuda::multi_context_t` (the surface the reference
+// declares in include/gunrock/cuda/context.hxx:146-216 and never runs: its operators throw for size() != 1).
 //
 //   multi_context_selftest <scale> <device> <device> ...      e.g.  multi_context_selftest 20 0 1 2 3
 //
 // Builds a symmetric RMAT-like graph of 2^scale vertices and a directed one, runs BFS (push only and
 // direction-optimised) through the UNCHANGED call `gunrock::bfs::run(G, param, result, context)` with a
-// context of the listed devices, and checks the depths against a host BFS and against the single-device run.
+// context of the listed devices, and checks the depths against a host BFS and against the single-device run;
+// then SSSP (fp32 distances bit-equal to the single-device run) and PageRank (ranks within 1e-6 relative of it)
+// through `sssp::run` / `pr::run` with the same context.
 // The same device may be listed several times (ranks then share it: how the single-GPU test box runs this;
 // set CUDA_MODULE_LOADING=EAGER for that case -- lazy module loading synchronises the device at a kernel's
 // first launch, which dead-locks against another rank's spinning barrier kernel on the SAME device).
 // Prints "ALL OK" and returns 0 on success.
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <queue>
 #include <vector>
 
 #include <gunrock/algorithms/bfs.hxx>
+#include <gunrock/algorithms/pr.hxx>
+#include <gunrock/algorithms/sssp.hxx>
 
 using namespace gunrock;
 using namespace memory;
@@ -73,7 +79,7 @@ static coo_host_t make_graph(int scale, int pairs_per_vertex, bool mirror, unsig
   for (size_t k = 0; k < I.size(); ++k) {
     coo.row_indices[k] = I[k];
     coo.column_indices[k] = J[k];
-    coo.nonzero_values[k] = 1.0f;
+    coo.nonzero_values[k] = 1.0f + static_cast<float>(mix(seed ^ (0xABCDull + k)) % 63);
   }
   return coo;
 }
@@ -133,6 +139,59 @@ static void check_runs(graph_type& G, const thrust::host_vector<int>& ro, const 
   }
 }
 
+/// SSSP and PageRank: the multi-device run against the single-device run of the same call.
+template <typename graph_type>
+static void check_sssp_pr(graph_type& G, const thrust::host_vector<int>& ro,
+                          std::shared_ptr<gcuda::multi_context_t> multi, std::shared_ptr<gcuda::multi_context_t> single,
+                          const char* what) {
+  const int n = G.get_number_of_vertices();
+  int hub = 0;
+  for (int v = 1; v < n; ++v)
+    if (ro[v + 1] - ro[v] > ro[hub + 1] - ro[hub])
+      hub = v;
+  for (int src : {hub, n - 1})
+    for (auto lb : {operators::load_balance_t::block_mapped, operators::load_balance_t::merge_path}) {
+      options_t opt;
+      opt.advance_load_balance = lb;
+      thrust::device_vector<float> dist(n, -7.0f), dist1(n, -7.0f);
+      thrust::device_vector<int> pred(n);
+      sssp::param_t<int> param(src, opt);
+      sssp::result_t<int, float> result(dist.data().get(), pred.data().get(), n);
+      float ms = sssp::run(G, param, result, multi);
+      sssp::result_t<int, float> result1(dist1.data().get(), pred.data().get(), n);
+      sssp::run(G, param, result1, single);
+      thrust::host_vector<float> h(dist), h1(dist1);
+      long long bad = 0, reached = 0;
+      for (int v = 0; v < n; ++v) {
+        unsigned a, b;
+        std::memcpy(&a, &h[v], 4);
+        std::memcpy(&b, &h1[v], 4);
+        bad += a != b;
+        reached += h1[v] < std::numeric_limits<float>::max();
+      }
+      std::printf("%s sssp src %d %s: %zu devices %.3f ms, %lld reached, distances differing from the single-device run: %lld\n",
+                  what, src, lb == operators::load_balance_t::merge_path ? "merge_path" : "block_mapped", multi->size(), ms,
+                  reached, bad);
+      CHECK(bad == 0 && reached > 1);
+    }
+  {
+    thrust::device_vector<float> p(n, -1.0f), p1(n, -1.0f);
+    float ms = pr::run(G, 0.85f, 1e-6f, p.data().get(), multi);
+    pr::run(G, 0.85f, 1e-6f, p1.data().get(), single);
+    thrust::host_vector<float> h(p), h1(p1);
+    double worst = 0.0, sum = 0.0;
+    for (int v = 0; v < n; ++v) {
+      const double ref = h1[v] > 0 ? h1[v] : 1e-30;
+      const double rel = std::fabs(static_cast<double>(h[v]) - h1[v]) / ref;
+      worst = rel > worst ? rel : worst;
+      sum += h[v];
+    }
+    std::printf("%s pagerank: %zu devices %.3f ms, sum of ranks %.6f, worst relative difference to the single-device run %.3g\n",
+                what, multi->size(), ms, sum, worst);
+    CHECK(worst <= 1e-6 && std::fabs(sum - 1.0) < 1e-3);
+  }
+}
+
 int main(int argc, char** argv) {
   const int scale = argc > 1 ? std::atoi(argv[1]) : 14;
   thrust::host_vector<gcuda::device_id_t> devices;
@@ -156,6 +215,7 @@ int main(int argc, char** argv) {
     props.symmetric = true;
     auto G = graph::build<memory_space_t::device>(props, csr);
     check_runs(G, ro, ci, multi, single, "symmetric");
+    check_sssp_pr(G, ro, multi, single, "symmetric");
   }
   {  // directed graph with a CSC: both are cut across the devices
     auto coo = make_graph(scale > 12 ? scale - 2 : scale, 12, false, 0xD1CE);
@@ -168,6 +228,7 @@ int main(int argc, char** argv) {
     props.directed = true;
     auto G = graph::build<memory_space_t::device>(props, csr, csc);
     check_runs(G, ro, ci, multi, single, "directed+csc");
+    check_sssp_pr(G, ro, multi, single, "directed+csc");
   }
   if (failures == 0)
     std::printf("ALL OK\n");

@@ -1384,48 +1384,9 @@ int b2g_part_pr_outweights(b2g_graph_t* g, double* outweight) {
 
 namespace {
 /// Shared body of b2g_part_pr_begin / b2g_part_pr_begin_weighted (exactly one of the two arrays is given).
-int part_pr_begin(b2g_graph_t* g, float alpha, const int* outdeg_global, const double* outweight_global) {
+int pr_begin_guarded(b2g_graph_t* g, float alpha, const int* outdeg_global, const double* outweight_global) {
   return guarded([&] {
-    cudaStream_t st = g->ws.stream;
-    auto& S = g->ppr;
-    const int sms = device_info_t::get().sm_count;
-    S.nparts = g->pt.nparts;
-    S.part = g->pt.part;
-    S.n_global = g->pt.n_global;
-    S.n_local = g->pt.n_local;
-    S.rows_per_rank = g->pt.rows_of(0);
-    S.sc.ensure(S.n_local, g->n_edges);
-    S.p.ensure(static_cast<size_t>(S.n_local) + 16);
-    S.dsum.ensure(2);
-    S.err.ensure(2);
-    if (S.remapped.cap < static_cast<size_t>(g->n_edges) + 16 || S.t.row_offsets != g->view.row_offsets) {
-      S.remapped.ensure(static_cast<size_t>(g->n_edges) + 16);
-      if (g->n_edges)
-        part_pr_remap_kernel<<<sms * 8, 256, 0, st>>>(g->view.column_indices, g->n_edges, S.nparts,
-                                                      S.rows_per_rank, S.remapped.ptr);
-      S.t.n_vertices = S.n_local;
-      S.t.n_edges = g->n_edges;
-      S.t.row_offsets = g->view.row_offsets;
-      S.t.column_indices = S.remapped.ptr;
-      S.t.values = outweight_global ? g->view.values : nullptr;  // the remap keeps the edge order
-      S.t.uid = next_graph_uid();
-      const int ntiles = g->n_edges > 0 ? (g->n_edges + kPrTile - 1) / kPrTile : 1;
-      pr_tile_table_kernel<<<sms * 2, 256, 0, st>>>(S.t.row_offsets, S.n_local, ntiles,
-                                                    S.sc.first_owned.ptr);
-      S.sc.tiled_for.set(S.t);
-      g->ws.launches += 2;
-    }
-    S.t.values = outweight_global ? g->view.values : nullptr;
-    if (outweight_global)
-      part_pr_reset_weighted_kernel<<<sms * 8, 256, 0, st>>>(S.n_local, S.nparts, S.part, S.n_global, alpha,
-                                                             outweight_global, S.p.ptr, S.sc.plast.ptr,
-                                                             S.sc.iw.ptr);
-    else
-      part_pr_reset_kernel<<<sms * 8, 256, 0, st>>>(S.n_local, S.nparts, S.part, S.n_global, alpha,
-                                                    outdeg_global, S.p.ptr, S.sc.plast.ptr, S.sc.iw.ptr);
-    B2G_CHECK(cudaMemsetAsync(S.sc.err.ptr, 0, 2 * sizeof(unsigned), st));
-    g->ws.launches += 1;
-    B2G_CHECK(cudaGetLastError());
+    gunrock::b200::part_pr_begin(g->ws, g->view, g->pt, g->ppr, alpha, outdeg_global, outweight_global);
     return 0;
   });
 }
@@ -1437,7 +1398,7 @@ int b2g_part_pr_begin(b2g_graph_t* g, float alpha, const int* outdeg_global) {
   if (g->view.values)
     return fail(B2G_ERR_INVALID,
                 "b2g_part_pr_begin: the graph has edge values -- b2g_part_pr_outweights + b2g_part_pr_begin_weighted");
-  return part_pr_begin(g, alpha, outdeg_global, nullptr);
+  return pr_begin_guarded(g, alpha, outdeg_global, nullptr);
 }
 
 int b2g_part_pr_begin_weighted(b2g_graph_t* g, float alpha, const double* outweight_global) {
@@ -1445,23 +1406,14 @@ int b2g_part_pr_begin_weighted(b2g_graph_t* g, float alpha, const double* outwei
     return fail(B2G_ERR_INVALID, "b2g_part_pr_begin_weighted: bad arguments");
   if (!g->view.values)
     return fail(B2G_ERR_INVALID, "b2g_part_pr_begin_weighted: the graph has no edge values");
-  return part_pr_begin(g, alpha, nullptr, outweight_global);
+  return pr_begin_guarded(g, alpha, nullptr, outweight_global);
 }
 
 int b2g_part_pr_prepare(b2g_graph_t* g, float alpha, float* c_local, double* dsum_local) {
   if (!g || !g->partitioned || !c_local || !dsum_local)
     return fail(B2G_ERR_INVALID, "b2g_part_pr_prepare: bad arguments");
   return guarded([&] {
-    auto& S = g->ppr;
-    cudaStream_t st = g->ws.stream;
-    if (S.rows_per_rank > S.n_local)  // zero the padding slot(s) of the gathered layout
-      B2G_CHECK(cudaMemsetAsync(c_local + S.n_local, 0, sizeof(float) * (S.rows_per_rank - S.n_local), st));
-    part_pr_prepare_kernel<256><<<kPrPartials, 256, 0, st>>>(S.n_local, alpha, S.p.ptr, S.sc.iw.ptr,
-                                                             S.sc.plast.ptr, c_local,
-                                                             S.sc.partials.ptr, S.sc.err.ptr + 1,
-                                                             dsum_local);
-    g->ws.launches += 1;
-    B2G_CHECK(cudaGetLastError());
+    part_pr_prepare(g->ws, g->ppr, alpha, c_local, dsum_local);
     return 0;
   });
 }
@@ -1471,25 +1423,7 @@ int b2g_part_pr_pull(b2g_graph_t* g, float alpha, const float* c_all, const doub
   if (!g || !g->partitioned || !c_all || !dsum_global || !err_local)
     return fail(B2G_ERR_INVALID, "b2g_part_pr_pull: bad arguments");
   return guarded([&] {
-    auto& S = g->ppr;
-    cudaStream_t st = g->ws.stream;
-    const int sms = device_info_t::get().sm_count;
-    const int ntiles = S.t.n_edges > 0 ? (S.t.n_edges + kPrTile - 1) / kPrTile : 1;
-    part_pr_base_kernel<<<1, 1, 0, st>>>(dsum_global, alpha, S.n_global, S.sc.base.ptr);
-    ctrl_t* ctrl = g->ws.next_ctrl();
-    if (S.t.values)
-      pr_pull_tile_kernel<256, true><<<sms * 8, 256, 0, st>>>(
-          S.t, ntiles, S.sc.first_owned.ptr, c_all, S.sc.plast.ptr, S.sc.base.ptr, S.p.ptr,
-          S.sc.head.ptr, S.sc.tail.ptr, S.sc.tail_row.ptr, S.sc.err.ptr, ctrl);
-    else
-      pr_pull_tile_kernel<256, false><<<sms * 8, 256, 0, st>>>(
-          S.t, ntiles, S.sc.first_owned.ptr, c_all, S.sc.plast.ptr, S.sc.base.ptr, S.p.ptr,
-          S.sc.head.ptr, S.sc.tail.ptr, S.sc.tail_row.ptr, S.sc.err.ptr, ctrl);
-    pr_fixup_kernel<<<sms, 256, 0, st>>>(S.t, ntiles, S.sc.tail_row.ptr, S.sc.head.ptr, S.sc.tail.ptr,
-                                         S.sc.base.ptr, S.sc.plast.ptr, S.p.ptr, S.sc.err.ptr);
-    part_pr_err_kernel<<<1, 1, 0, st>>>(S.sc.err.ptr, err_local);
-    g->ws.launches += 4;
-    B2G_CHECK(cudaGetLastError());
+    part_pr_pull(g->ws, g->ppr, alpha, c_all, dsum_global, err_local);
     return 0;
   });
 }
@@ -1798,26 +1732,8 @@ int b2g_part_bfs_nccl(b2g_graph_t* g, int source, long long total_edges, const b
   });
 }
 
-// ---- SSSP and PageRank with the NCCL exchange driven from C++ (same per-iteration kernels as the b2g_part_sssp_* /
-// b2g_part_pr_* calls above; what moves here is the loop: no Python, no torch collective, one pinned record polled
-// per iteration) ------------------------------------------------------------------------------------------------
-namespace {
-/// all-reduce of N.stats (4 x int64) + publication to the pinned record + the iteration's one host wait
-void nccl_reduce_and_publish(b2g_graph_t* g, cudaStream_t st) {
-  const nccl_api_t& nccl = nccl_api_t::get();
-  auto& N = g->nccl;
-  if (g->pt.nparts > 1)
-    nccl.check(nccl.AllReduce(N.stats.ptr, N.stats.ptr, 4, ncclInt64, ncclSum, N.comm, st), "ncclAllReduce(stats)");
-  nccl_feedback_kernel<<<1, 1, 0, st>>>(N.stats.ptr, N.h_fb, ++N.seq);
-  g->ws.launches += 1;
-  wait_for_sequence(&N.h_fb->seq, N.seq, st);
-}
-__global__ void pr_err_to_stats_kernel(const float* err, long long* stats) {
-  stats[0] = __float_as_int(*err);  // non-negative floats order like their bit patterns
-  stats[1] = stats[2] = stats[3] = 0;
-}
-}  // namespace
-
+// ---- SSSP and PageRank with the NCCL exchange driven from C++: the loops of part_loops.cuh over nccl_exchange_t
+// (no Python, no torch collective, one pinned record polled per iteration) -----------------------------------------
 int b2g_part_sssp_nccl(b2g_graph_t* g, int source, int send_capacity, const b2g_options_t* opt,
                        b2g_stats_t* stats) {
   if (!g || !g->partitioned || !g->nccl.comm || source < 0 || source >= g->pt.n_global || send_capacity < 0)
@@ -1825,97 +1741,23 @@ int b2g_part_sssp_nccl(b2g_graph_t* g, int source, int send_capacity, const b2g_
   if (!g->view.values)
     return fail(B2G_ERR_INVALID, "b2g_part_sssp_nccl: the graph has no edge values");
   return guarded([&] {
-    const nccl_api_t& nccl = nccl_api_t::get();
     b2g_options_t o = resolved(opt);
     cudaStream_t st = g->ws.stream;
-    auto& S = g->psssp;
     auto& N = g->nccl;
-    const partition_t pt = g->pt;
-    const int np = pt.nparts;
-    const int rows = pt.rows_of(0) + 64;
-    int cap_s = send_capacity > 0 ? send_capacity : std::min(rows, 1 << 20);
+    nccl_exchange_t x{&N, g->pt.part, g->pt.nparts};
     const int launches0 = g->ws.launches;
+    part_sssp_report_t rep;
     B2G_CHECK(cudaEventRecord(g->ev0, st));
-    int it = 0;
-    unsigned long long relaxed = 0, verts = 0;
-    for (;;) {  // a message row that overflows restarts the run with rows four times as long
-      S.ensure(pt, std::max(cap_s, rows));
-      const size_t row_full = 2 * static_cast<size_t>(cap_s) + 1;
-      N.msg_out.ensure(static_cast<size_t>(np) * row_full + 64);
-      N.msg_in.ensure(static_cast<size_t>(np) * row_full + 64);
-      g->part_deg.ensure(2);
-      part_sssp_reset_kernel<<<device_info_t::get().sm_count * 8, 256, 0, st>>>(
-          pt, source, S.dist.ptr, S.stamp.ptr, S.best_sent.ptr, S.q[0].ptr, S.counts.ptr);
-      B2G_CHECK(cudaMemsetAsync(S.overflow.ptr, 0, sizeof(int), st));
-      B2G_CHECK(cudaMemsetAsync(g->part_deg.ptr, 0, 16, st));
-      nccl_seed_stats_kernel<<<1, 1, 0, st>>>(pt, source, g->view.row_offsets, N.stats.ptr);
-      g->ws.launches += 2;
-      S.cur = 0;
-      nccl_reduce_and_publish(g, st);  // every rank learns the source's degree: the bound of iteration 0's messages
-      long long n_f = N.h_fb->v[0], m_f = N.h_fb->v[1];
-      if (n_f != 1)
-        throw std::runtime_error("b2g_part_sssp_nccl: the source is owned by no rank");
-      bool overflowed = false;
-      it = 0;
-      relaxed = verts = 0;
-      while (n_f > 0) {
-        const int nxt = S.cur ^ 1;
-        // no rank forwards more pairs to a peer than the frontier has out-edges (known on every rank: the sizes
-        // of the grouped Send / Recv agree without a count round trip)
-        const int cap = static_cast<int>(std::min<long long>(cap_s, std::max<long long>(m_f, 256)));
-        const size_t row = 2 * static_cast<size_t>(cap) + 1;
-        B2G_CHECK(cudaMemsetAsync(S.counts.ptr + nxt, 0, sizeof(int), st));
-        B2G_CHECK(cudaMemsetAsync(S.send_count.ptr, 0, 64 * sizeof(int), st));
-        part_relax_op op{pt,          S.dist.ptr,     S.stamp.ptr,      S.best_sent.ptr, it,
-                         S.send_ids.ptr, S.send_vals.ptr, S.send_count.ptr, S.send_cap,      S.overflow.ptr};
-        ctrl_t* c = nullptr;
-        launch_advance<advance_output_t::vertices, true, true>(g->ws, g->view, S.q[S.cur].ptr, S.counts.ptr + S.cur,
-                                                              pt.n_local, S.q[nxt].ptr, S.counts.ptr + nxt,
-                                                              pt.n_local, op, to_launch(o), &c);
-        if (np > 1) {
-          part_pack_pairs_kernel<<<dim3(32, np), 256, 0, st>>>(S.send_ids.ptr, S.send_vals.ptr, S.send_count.ptr,
-                                                               S.send_cap, np, cap, N.msg_out.ptr);
-          nccl.check(nccl.GroupStart(), "ncclGroupStart");
-          for (int p = 0; p < np; ++p) {
-            if (p == pt.part)
-              continue;
-            nccl.check(nccl.Send(N.msg_out.ptr + p * row, row, ncclInt32, p, N.comm, st), "ncclSend");
-            nccl.check(nccl.Recv(N.msg_in.ptr + p * row, row, ncclInt32, p, N.comm, st), "ncclRecv");
-          }
-          nccl.check(nccl.GroupEnd(), "ncclGroupEnd");
-          part_relax_packed_kernel<<<dim3(64, np), 256, 0, st>>>(pt, N.msg_in.ptr, cap, S.dist.ptr, S.stamp.ptr, it,
-                                                                 g->view.row_offsets, S.q[nxt].ptr,
-                                                                 S.counts.ptr + nxt, g->part_deg.ptr, S.overflow.ptr);
-          g->ws.launches += 2;
-        }
-        S.cur = nxt;
-        part_stats_kernel<<<1, 1, 0, st>>>(S.counts.ptr + S.cur, c, g->part_deg.ptr, S.overflow.ptr, N.stats.ptr);
-        g->ws.launches += 1;
-        nccl_reduce_and_publish(g, st);
-        if (N.h_fb->v[3]) {
-          overflowed = true;
-          break;
-        }
-        verts += static_cast<unsigned long long>(n_f);
-        relaxed += static_cast<unsigned long long>(N.h_fb->v[2]);
-        n_f = N.h_fb->v[0];
-        m_f = N.h_fb->v[1];
-        ++it;
-      }
-      if (!overflowed)
-        break;
-      if (cap_s > (1 << 28))
-        throw std::runtime_error("b2g_part_sssp_nccl: message rows overflow at the largest capacity");
-      cap_s *= 4;
-    }
+    part_sssp_run(g->ws, g->view, g->pt, g->psssp, g->part_deg, N.msg_out, N.msg_in, N.stats, x, source,
+                  send_capacity, to_launch(o), &rep);
     B2G_CHECK(cudaEventRecord(g->ev1, st));
     B2G_CHECK(cudaStreamSynchronize(st));
     if (stats) {
       memset(stats, 0, sizeof *stats);
       fill_stats_common(g, stats, launches0);
-      stats->iterations = it;
-      stats->edges_touched = relaxed;
-      stats->vertices_touched = verts;
+      stats->iterations = rep.iterations;
+      stats->edges_touched = rep.edges_relaxed;
+      stats->vertices_touched = rep.verts_total;
     }
     return 0;
   });
@@ -1924,99 +1766,34 @@ int b2g_part_sssp_nccl(b2g_graph_t* g, int source, int send_capacity, const b2g_
 int b2g_part_pr_nccl(b2g_graph_t* g, float alpha, float tol, int max_iter, b2g_stats_t* stats) {
   if (!g || !g->partitioned || !g->nccl.comm)
     return fail(B2G_ERR_INVALID, "b2g_part_pr_nccl: call b2g_part_nccl_init first");
-  const nccl_api_t* api = nullptr;
-  int rc = guarded([&] {
-    api = &nccl_api_t::get();
-    return 0;
-  });
-  if (rc)
-    return rc;
-  const nccl_api_t& nccl = *api;
-  auto& S = g->ppr;
-  auto& N = g->nccl;
-  const int np = g->pt.nparts;
-  const size_t V = static_cast<size_t>(g->pt.n_global);
-  const size_t R = static_cast<size_t>(g->pt.rows_of(0));
-  cudaStream_t st = g->ws.stream;
-  const int launches0 = g->ws.launches;
-  // ---- row sums of the whole graph (out-degrees, or sums of the weights), then the per-graph setup ------------
-  rc = guarded([&] {
-    B2G_CHECK(cudaEventRecord(g->ev0, st));
-    S.c_local.ensure(R + 16);
-    S.c_all.ensure(static_cast<size_t>(np) * R + 16);
-    if (g->view.values)
-      S.outweight.ensure(V + 16);
-    else
-      S.outdeg.ensure(V + 16);
-    B2G_CHECK(cudaMemsetAsync(S.c_local.ptr, 0, sizeof(float) * R, st));
-    return 0;
-  });
-  if (rc)
-    return rc;
-  if (g->view.values) {
-    if ((rc = b2g_part_pr_outweights(g, S.outweight.ptr)))
-      return rc;
-  } else if ((rc = b2g_part_pr_outdegrees(g, S.outdeg.ptr))) {
-    return rc;
-  }
-  rc = guarded([&] {
-    if (np > 1) {
-      if (g->view.values)
-        nccl.check(nccl.AllReduce(S.outweight.ptr, S.outweight.ptr, V, ncclFloat64, ncclSum, N.comm, st),
-                   "ncclAllReduce(row sums)");
-      else
-        nccl.check(nccl.AllReduce(S.outdeg.ptr, S.outdeg.ptr, V, ncclInt32, ncclSum, N.comm, st),
-                   "ncclAllReduce(out-degrees)");
-    }
-    return 0;
-  });
-  if (rc)
-    return rc;
-  rc = g->view.values ? b2g_part_pr_begin_weighted(g, alpha, S.outweight.ptr) : b2g_part_pr_begin(g, alpha, S.outdeg.ptr);
-  if (rc)
-    return rc;
-  // ---- the iteration loop (pr.hxx:107-195: converged = max |p - plast| < tol, checked once iteration >= 1) ------
-  int it = 0;
-  for (;;) {
-    if (it > 0) {
-      float err = 0.0f;
-      rc = guarded([&] {
-        pr_err_to_stats_kernel<<<1, 1, 0, st>>>(S.err.ptr, N.stats.ptr);
-        if (np > 1)  // the error is a max: bit patterns of non-negative floats, reduced as integers
-          nccl.check(nccl.AllReduce(N.stats.ptr, N.stats.ptr, 1, ncclInt64, ncclMax, N.comm, st), "ncclAllReduce(err)");
-        nccl_feedback_kernel<<<1, 1, 0, st>>>(N.stats.ptr, N.h_fb, ++N.seq);
-        g->ws.launches += 2;
-        wait_for_sequence(&N.h_fb->seq, N.seq, st);
-        const int bits = static_cast<int>(N.h_fb->v[0]);
-        memcpy(&err, &bits, sizeof err);
-        return 0;
-      });
-      if (rc)
-        return rc;
-      if (err < tol)
-        break;
-    }
-    if (max_iter > 0 && it >= max_iter)
-      break;
-    if ((rc = b2g_part_pr_prepare(g, alpha, S.c_local.ptr, S.dsum.ptr)))
-      return rc;
-    const float* c_all = S.c_local.ptr;
-    rc = guarded([&] {
-      if (np > 1) {
-        nccl.check(nccl.AllGather(S.c_local.ptr, S.c_all.ptr, R, ncclFloat32, N.comm, st), "ncclAllGather(c)");
-        nccl.check(nccl.AllReduce(S.dsum.ptr, S.dsum.ptr, 1, ncclFloat64, ncclSum, N.comm, st),
-                   "ncclAllReduce(dangling)");
-        c_all = S.c_all.ptr;
-      }
-      return 0;
-    });
-    if (rc)
-      return rc;
-    if ((rc = b2g_part_pr_pull(g, alpha, c_all, S.dsum.ptr, S.err.ptr)))
-      return rc;
-    ++it;
-  }
   return guarded([&] {
+    auto& S = g->ppr;
+    auto& N = g->nccl;
+    nccl_exchange_t x{&N, g->pt.part, g->pt.nparts};
+    const size_t V = static_cast<size_t>(g->pt.n_global);
+    const int sms = device_info_t::get().sm_count;
+    cudaStream_t st = g->ws.stream;
+    const int launches0 = g->ws.launches;
+    B2G_CHECK(cudaEventRecord(g->ev0, st));
+    // row sums of the whole graph (out-degrees, or fp64 sums of the weights), reduced over the ranks once
+    if (g->view.values) {
+      S.outweight.ensure(V + 16);
+      B2G_CHECK(cudaMemsetAsync(S.outweight.ptr, 0, sizeof(double) * V, st));
+      if (g->n_edges)
+        part_pr_outweight_kernel<<<sms * 8, 256, 0, st>>>(g->view.column_indices, g->view.values, g->n_edges,
+                                                          S.outweight.ptr);
+      x.all_reduce_sum(S.outweight.ptr, V, st);
+      part_pr_begin(g->ws, g->view, g->pt, S, alpha, nullptr, S.outweight.ptr);
+    } else {
+      S.outdeg.ensure(V + 16);
+      B2G_CHECK(cudaMemsetAsync(S.outdeg.ptr, 0, sizeof(int) * V, st));
+      if (g->n_edges)
+        part_pr_outdeg_kernel<<<sms * 8, 256, 0, st>>>(g->view.column_indices, g->n_edges, S.outdeg.ptr);
+      x.all_reduce_sum(S.outdeg.ptr, V, st);
+      part_pr_begin(g->ws, g->view, g->pt, S, alpha, S.outdeg.ptr, nullptr);
+    }
+    g->ws.launches += 1;
+    const int it = part_pr_run(g->ws, S, N.stats, x, alpha, tol, max_iter);
     B2G_CHECK(cudaEventRecord(g->ev1, st));
     B2G_CHECK(cudaStreamSynchronize(st));
     if (stats) {

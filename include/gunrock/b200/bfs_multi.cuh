@@ -95,7 +95,8 @@ struct multi_bfs_cache_t {
 /// Cut `g` (resident on the current device) into rank `r`'s rows, written into `ro_buf` / `ci_buf` that live on
 /// the rank's device (allocated here after the row scan told the edge count).
 inline csr_view_t partition_rows_to(workspace_t& ws0, const csr_view_t& g, const partition_t& pt, int rank_device,
-                                    int home_device, dbuf_t<int>& ro_buf, dbuf_t<int>& ci_buf) {
+                                    int home_device, dbuf_t<int>& ro_buf, dbuf_t<int>& ci_buf,
+                                    dbuf_t<float>* vals_buf = nullptr) {
   const int n_local = pt.n_local, P = pt.nparts, part = pt.part;
   B2G_CHECK(cudaSetDevice(rank_device));
   int* lro = ro_buf.ensure(static_cast<size_t>(n_local) + 1 + 16);
@@ -115,11 +116,12 @@ inline csr_view_t partition_rows_to(workspace_t& ws0, const csr_view_t& g, const
   B2G_CHECK(cudaStreamSynchronize(ws0.stream));
   B2G_CHECK(cudaSetDevice(rank_device));
   int* lci = ci_buf.ensure(static_cast<size_t>(n_edges) + 16 + 64);  // + 64 B: TMA slabs may over-read the tail
+  float* lvals = (vals_buf && g.values) ? vals_buf->ensure(static_cast<size_t>(n_edges) + 16 + 64) : nullptr;
   B2G_CHECK(cudaSetDevice(home_device));
   if (n_local > 0 && n_edges > 0) {
     const int sms = device_info_t::get().sm_count;
-    part_gather_rows_kernel<<<sms * 8, 256, 0, ws0.stream>>>(g.row_offsets, g.column_indices, nullptr, P, part,
-                                                             n_local, lro, lci, nullptr);
+    part_gather_rows_kernel<<<sms * 8, 256, 0, ws0.stream>>>(g.row_offsets, g.column_indices, lvals ? g.values : nullptr,
+                                                             P, part, n_local, lro, lci, lvals);
     ws0.launches += 1;
   }
   B2G_CHECK(cudaStreamSynchronize(ws0.stream));
@@ -128,7 +130,7 @@ inline csr_view_t partition_rows_to(workspace_t& ws0, const csr_view_t& g, const
   v.n_edges = n_edges;
   v.row_offsets = lro;
   v.column_indices = lci;
-  v.values = nullptr;
+  v.values = lvals;
   v.uid = next_graph_uid();
   return v;
 }

@@ -26,6 +26,7 @@
 #include <nccl.h>  // types and enums only; every entry point is resolved with dlsym
 
 #include <gunrock/b200/bfs_p2p.cuh>
+#include <gunrock/b200/part_loops.cuh>
 
 namespace gunrock {
 namespace b200 {
@@ -147,16 +148,6 @@ static __global__ void nccl_row_headers_kernel(const int* __restrict__ send_coun
   }
 }
 
-/// The source's degree on its owner, 0 elsewhere: the run's first all-reduce tells every rank the size of level 0.
-static __global__ void nccl_seed_stats_kernel(partition_t pt, int source, const int* __restrict__ ro, long long* stats) {
-  stats[0] = stats[1] = stats[2] = stats[3] = 0;
-  if (pt.owner(source) == pt.part) {
-    const int l = pt.local(source);
-    stats[0] = 1;
-    stats[1] = ro[l + 1] - ro[l];
-  }
-}
-
 static __global__ void nccl_feedback_kernel(const long long* __restrict__ stats, nccl_feedback_t* fb, int seq) {
   fb->v[0] = stats[0];
   fb->v[1] = stats[1];
@@ -165,6 +156,65 @@ static __global__ void nccl_feedback_kernel(const long long* __restrict__ stats,
   __threadfence_system();
   fb->seq = seq;
 }
+
+/// The exchange policy of part_loops.cuh over one rank's NCCL communicator (SSSP / PageRank loops).
+struct nccl_exchange_t {
+  nccl_state_t* N = nullptr;
+  int rank_ = 0, nparts_ = 1;
+  int rank() const { return rank_; }
+  int nparts() const { return nparts_; }
+  void publish_and_wait(workspace_t& ws, cudaStream_t st) {
+    nccl_feedback_kernel<<<1, 1, 0, st>>>(N->stats.ptr, N->h_fb, ++N->seq);
+    ws.launches += 1;
+    wait_for_sequence(&N->h_fb->seq, N->seq, st);
+  }
+  void all_to_all_rows(const int* out, int* in, size_t row_len, cudaStream_t st) {
+    const nccl_api_t& nccl = nccl_api_t::get();
+    nccl.check(nccl.GroupStart(), "ncclGroupStart");
+    for (int p = 0; p < nparts_; ++p) {
+      if (p == rank_)
+        continue;
+      nccl.check(nccl.Send(out + p * row_len, row_len, ncclInt32, p, N->comm, st), "ncclSend");
+      nccl.check(nccl.Recv(in + p * row_len, row_len, ncclInt32, p, N->comm, st), "ncclRecv");
+    }
+    nccl.check(nccl.GroupEnd(), "ncclGroupEnd");
+  }
+  /// `d_stats` must be N->stats.ptr (the record the feedback kernel publishes).
+  void reduce_stats(workspace_t& ws, long long* d_stats, long long h_out[4], cudaStream_t st) {
+    const nccl_api_t& nccl = nccl_api_t::get();
+    if (nparts_ > 1)
+      nccl.check(nccl.AllReduce(d_stats, d_stats, 4, ncclInt64, ncclSum, N->comm, st), "ncclAllReduce(stats)");
+    publish_and_wait(ws, st);
+    for (int k = 0; k < 4; ++k)
+      h_out[k] = N->h_fb->v[k];
+  }
+  void all_reduce_sum(double* v, size_t n, cudaStream_t st) {
+    if (nparts_ > 1)
+      nccl_api_t::get().check(nccl_api_t::get().AllReduce(v, v, n, ncclFloat64, ncclSum, N->comm, st),
+                              "ncclAllReduce(fp64 sum)");
+  }
+  void all_reduce_sum(int* v, size_t n, cudaStream_t st) {
+    if (nparts_ > 1)
+      nccl_api_t::get().check(nccl_api_t::get().AllReduce(v, v, n, ncclInt32, ncclSum, N->comm, st),
+                              "ncclAllReduce(int32 sum)");
+  }
+  void all_gather(const float* local, float* all, size_t n, cudaStream_t st) {
+    nccl_api_t::get().check(nccl_api_t::get().AllGather(local, all, n, ncclFloat32, N->comm, st), "ncclAllGather");
+  }
+  /// max of one non-negative float: its bit pattern reduced as an integer (`d_scratch` must be N->stats.ptr).
+  float reduce_max(workspace_t& ws, const float* d_v, long long* d_scratch, cudaStream_t st) {
+    part_float_bits_kernel<<<1, 1, 0, st>>>(d_v, d_scratch);
+    ws.launches += 1;
+    if (nparts_ > 1)
+      nccl_api_t::get().check(nccl_api_t::get().AllReduce(d_scratch, d_scratch, 1, ncclInt64, ncclMax, N->comm, st),
+                              "ncclAllReduce(max)");
+    publish_and_wait(ws, st);
+    const int bits = static_cast<int>(N->h_fb->v[0]);
+    float f;
+    std::memcpy(&f, &bits, sizeof f);
+    return f;
+  }
+};
 
 /**
  * @brief One rank's level loop with the NCCL exchange (file header).  COLLECTIVE over the communicator in `N`.
@@ -204,7 +254,7 @@ inline void part_bfs_nccl_run(workspace_t& ws, const csr_view_t& view, const csr
   part_seed_kernel<<<1, 1, 0, st>>>(pt, source, S.dist.ptr, S.visited.ptr);
   B2G_CHECK(cudaMemsetAsync(S.overflow.ptr, 0, sizeof(int), st));
   B2G_CHECK(cudaMemsetAsync(part_deg.ptr, 0, 16, st));
-  nccl_seed_stats_kernel<<<1, 1, 0, st>>>(pt, source, view.row_offsets, N.stats.ptr);
+  part_seed_stats_kernel<<<1, 1, 0, st>>>(pt, source, view.row_offsets, N.stats.ptr);
   ws.launches += 3;
   auto reduce_and_publish = [&]() {
     if (np > 1)

@@ -479,6 +479,86 @@ struct part_pr_state_t {
   ctrl_t* ctrl = nullptr;
 };
 
+// ---- the per-rank steps of one partitioned PageRank (enqueued on ws.stream; the collectives between them belong
+// to the caller: C ABI b2g_part_pr_* + torch.distributed, or part_pr_run in part_loops.cuh) -------------------------
+/// Per-graph setup (column remap + tile table, cached on the row-offsets pointer) and reset of p / plast / iweights
+/// from the GLOBAL out-degrees or, for a graph with values, the global fp64 row sums of the weights (exactly one
+/// of the two is non-null).  `view` = the rank's in-edge rows with global source ids.
+template <typename partition_type>  // b200::partition_t (bfs_partitioned.cuh); a template keeps this header light
+inline void part_pr_begin(workspace_t& ws, const csr_view_t& view, const partition_type& pt, part_pr_state_t& S,
+                          float alpha, const int* outdeg_global, const double* outweight_global) {
+  cudaStream_t st = ws.stream;
+  const int sms = device_info_t::get().sm_count;
+  S.nparts = pt.nparts;
+  S.part = pt.part;
+  S.n_global = pt.n_global;
+  S.n_local = pt.n_local;
+  S.rows_per_rank = pt.rows_of(0);
+  S.sc.ensure(S.n_local, view.n_edges);
+  S.p.ensure(static_cast<size_t>(S.n_local) + 16);
+  S.dsum.ensure(2);
+  S.err.ensure(2);
+  if (S.remapped.cap < static_cast<size_t>(view.n_edges) + 16 || S.t.row_offsets != view.row_offsets) {
+    S.remapped.ensure(static_cast<size_t>(view.n_edges) + 16);
+    if (view.n_edges)
+      part_pr_remap_kernel<<<sms * 8, 256, 0, st>>>(view.column_indices, view.n_edges, S.nparts, S.rows_per_rank,
+                                                    S.remapped.ptr);
+    S.t.n_vertices = S.n_local;
+    S.t.n_edges = view.n_edges;
+    S.t.row_offsets = view.row_offsets;
+    S.t.column_indices = S.remapped.ptr;
+    S.t.uid = next_graph_uid();
+    const int ntiles = view.n_edges > 0 ? (view.n_edges + kPrTile - 1) / kPrTile : 1;
+    pr_tile_table_kernel<<<sms * 2, 256, 0, st>>>(S.t.row_offsets, S.n_local, ntiles, S.sc.first_owned.ptr);
+    S.sc.tiled_for.set(S.t);
+    ws.launches += 2;
+  }
+  S.t.values = outweight_global ? view.values : nullptr;  // the remap keeps the edge order
+  if (outweight_global)
+    part_pr_reset_weighted_kernel<<<sms * 8, 256, 0, st>>>(S.n_local, S.nparts, S.part, S.n_global, alpha,
+                                                           outweight_global, S.p.ptr, S.sc.plast.ptr, S.sc.iw.ptr);
+  else
+    part_pr_reset_kernel<<<sms * 8, 256, 0, st>>>(S.n_local, S.nparts, S.part, S.n_global, alpha, outdeg_global,
+                                                  S.p.ptr, S.sc.plast.ptr, S.sc.iw.ptr);
+  B2G_CHECK(cudaMemsetAsync(S.sc.err.ptr, 0, 2 * sizeof(unsigned), st));
+  ws.launches += 1;
+  B2G_CHECK(cudaGetLastError());
+}
+
+/// plast = p, c_local = plast * iweights (rows_per_rank floats, zero padded), dsum_local = the dangling partial.
+inline void part_pr_prepare(workspace_t& ws, part_pr_state_t& S, float alpha, float* c_local, double* dsum_local) {
+  cudaStream_t st = ws.stream;
+  if (S.rows_per_rank > S.n_local)  // zero the padding slot(s) of the gathered layout
+    B2G_CHECK(cudaMemsetAsync(c_local + S.n_local, 0, sizeof(float) * (S.rows_per_rank - S.n_local), st));
+  part_pr_prepare_kernel<256><<<kPrPartials, 256, 0, st>>>(S.n_local, alpha, S.p.ptr, S.sc.iw.ptr, S.sc.plast.ptr,
+                                                           c_local, S.sc.partials.ptr, S.sc.err.ptr + 1, dsum_local);
+  ws.launches += 1;
+  B2G_CHECK(cudaGetLastError());
+}
+
+/// One pull over the owned rows from the gathered c and the global dangling sum; err_local = max |p - plast|.
+inline void part_pr_pull(workspace_t& ws, part_pr_state_t& S, float alpha, const float* c_all,
+                         const double* dsum_global, float* err_local) {
+  cudaStream_t st = ws.stream;
+  const int sms = device_info_t::get().sm_count;
+  const int ntiles = S.t.n_edges > 0 ? (S.t.n_edges + kPrTile - 1) / kPrTile : 1;
+  part_pr_base_kernel<<<1, 1, 0, st>>>(dsum_global, alpha, S.n_global, S.sc.base.ptr);
+  ctrl_t* ctrl = ws.next_ctrl();
+  if (S.t.values)
+    pr_pull_tile_kernel<256, true><<<sms * 8, 256, 0, st>>>(S.t, ntiles, S.sc.first_owned.ptr, c_all, S.sc.plast.ptr,
+                                                            S.sc.base.ptr, S.p.ptr, S.sc.head.ptr, S.sc.tail.ptr,
+                                                            S.sc.tail_row.ptr, S.sc.err.ptr, ctrl);
+  else
+    pr_pull_tile_kernel<256, false><<<sms * 8, 256, 0, st>>>(S.t, ntiles, S.sc.first_owned.ptr, c_all, S.sc.plast.ptr,
+                                                             S.sc.base.ptr, S.p.ptr, S.sc.head.ptr, S.sc.tail.ptr,
+                                                             S.sc.tail_row.ptr, S.sc.err.ptr, ctrl);
+  pr_fixup_kernel<<<sms, 256, 0, st>>>(S.t, ntiles, S.sc.tail_row.ptr, S.sc.head.ptr, S.sc.tail.ptr, S.sc.base.ptr,
+                                       S.sc.plast.ptr, S.p.ptr, S.sc.err.ptr);
+  part_pr_err_kernel<<<1, 1, 0, st>>>(S.sc.err.ptr, err_local);
+  ws.launches += 4;
+  B2G_CHECK(cudaGetLastError());
+}
+
 static __global__ void pr_err_feedback_kernel(unsigned* err_bits, float* h_err) {
   *h_err = __uint_as_float(*err_bits);
   *err_bits = 0;

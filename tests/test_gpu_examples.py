@@ -143,8 +143,10 @@ def test_per_graph_caches_across_graphs_and_contexts():
 def test_bfs_run_over_a_multi_device_context(ranks):
     """`gunrock::bfs::run(G, param, result, context)` with a gcuda::multi_context_t of several contexts runs the
     1-D partitioned traversal (frontier exchange by the kernels over peer memory) and returns the depths of the
-    host BFS and of the single-device run, bit for bit.  With fewer GPUs than ranks the ranks share devices
-    (eager module loading then: see examples/multi_context_selftest.cu)."""
+    host BFS and of the single-device run, bit for bit; `sssp::run` / `pr::run` with the same context run the
+    partitioned loops of b200/part_loops.cuh over peer loads + host barriers (distances bit-equal to, ranks within
+    1e-6 of, the single-device run).  With fewer GPUs than ranks the ranks share devices (eager module loading
+    then: see examples/multi_context_selftest.cu)."""
     import torch
     n = torch.cuda.device_count()
     devices = [str(r % max(n, 1)) for r in range(ranks)]
