@@ -19,7 +19,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgunrock_b200.so")
+# B2G_LIB_PATH: an A/B build of the same library (e.g. other launch bounds); never a fallback -- it must exist
+LIB_PATH = os.environ.get("B2G_LIB_PATH") or os.path.join(_HERE, "libgunrock_b200.so")
 
 HOST, DEVICE = 0, 1
 INT_MAX = 2**31 - 1

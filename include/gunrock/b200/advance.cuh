@@ -213,7 +213,11 @@ constexpr int warp_path_ints() {
  */
 template <int kThreads, advance_input_t kIn, advance_output_t kOut, bool kDegSum, bool kWeights,
           typename Op>
+#ifdef B2G_BINNED_CTAS  // A/B builds only (-DB2G_BINNED_CTAS=n): cap the registers for n resident CTAs per SM
+__global__ void __launch_bounds__(kThreads, B2G_BINNED_CTAS)
+#else
 __global__ void __launch_bounds__(kThreads)
+#endif
 advance_binned_kernel(advance_params_t p, Op op) {
   constexpr int kWarps = kThreads / 32;
   constexpr int kSpan = 256;            // ranks per warp span
@@ -411,7 +415,10 @@ __global__ void advance_hub_table_kernel(advance_params_t p) {
  * When the CSR arrays are not 16-byte aligned (p.tma_ok == 0) the slab is read with plain coalesced loads.
  */
 template <int kThreads, int kChunk, advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
-__global__ void __launch_bounds__(kThreads, kWeights ? 4 : 5)
+#ifndef B2G_HUB_CTAS_W
+#define B2G_HUB_CTAS_W 4  // resident CTAs per SM the weighted slab kernel is compiled for (A/B builds: -DB2G_HUB_CTAS_W=n)
+#endif
+__global__ void __launch_bounds__(kThreads, kWeights ? B2G_HUB_CTAS_W : 5)
 advance_hub_kernel(advance_params_t p, Op op) {
   constexpr int kWarps = kThreads / 32;
   constexpr int kHB = kChunk / kThreads;  // slab edges per thread: all of them in flight at once

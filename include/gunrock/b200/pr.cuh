@@ -18,6 +18,8 @@
  */
 #pragma once
 
+#include <cstdlib>
+
 #include <stdexcept>
 #include <vector>
 
@@ -174,8 +176,8 @@ pr_prepare_kernel(int V, float alpha, const float* __restrict__ p, const float* 
  * a partial (tail of this tile / head of the following ones) that pr_fixup_kernel folds in a
  * fixed order, so the result does not depend on scheduling.
  */
-template <int kThreads, bool kWeights>
-__global__ void __launch_bounds__(kThreads)
+template <int kThreads, bool kWeights, int kMinCtas = 6>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
 pr_pull_tile_kernel(csr_view_t t, int ntiles, const int* __restrict__ first_owned,
                     const float* __restrict__ c, const float* __restrict__ plast,
                     const float* __restrict__ base_ptr, float* __restrict__ p,
@@ -607,8 +609,16 @@ inline int pr_run(workspace_t& ws, pr_scratch_t& sc, const csr_view_t& g, const 
                                                         sc.base.ptr);
     ctrl_t* ctrl = ws.next_ctrl();
     const int grid = sms * 8;  // tickets are dynamic; residency is capped by the hardware
+    static const int full_occupancy = [] {  // A/B: B2G_PR_CTAS=8 caps the unweighted kernel at 32 registers
+      const char* e = std::getenv("B2G_PR_CTAS");
+      return e ? std::atoi(e) : 0;
+    }();
     if (t.values)
       pr_pull_tile_kernel<256, true><<<grid, 256, 0, st>>>(
+          t, ntiles, sc.first_owned.ptr, sc.c.ptr, sc.plast.ptr, sc.base.ptr, p, sc.head.ptr,
+          sc.tail.ptr, sc.tail_row.ptr, sc.err.ptr, ctrl);
+    else if (full_occupancy == 8)
+      pr_pull_tile_kernel<256, false, 8><<<grid, 256, 0, st>>>(
           t, ntiles, sc.first_owned.ptr, sc.c.ptr, sc.plast.ptr, sc.base.ptr, p, sc.head.ptr,
           sc.tail.ptr, sc.tail_row.ptr, sc.err.ptr, ctrl);
     else

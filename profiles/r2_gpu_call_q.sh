@@ -1,17 +1,13 @@
 #!/bin/bash
-# Round 2, GPU call Q (4 GPUs): the final code on distinct devices -- bfs / sssp / pr over a 4-device multi_context_t
-# (peer-memory BFS exchange, thread exchange for SSSP / PageRank, then B2G_EXCHANGE=nccl for BFS), the torchrun
-# worker at 4 ranks, and the N = 4 bench line.
+# Round 2, GPU call Q (2 GPUs): bfs / sssp / pr over a multi_context_t of two DISTINCT devices (peer-memory BFS
+# exchange; SSSP / PageRank over peer loads + host barriers), three ranks on two devices, and B2G_EXCHANGE=nccl.
 set -u
 OUT=gpurun_out/r2q
 mkdir -p "$OUT"
-( time examples/bin/multi_context_selftest 18 0 1 2 3 ) > "$OUT/multi_context_4dev.txt" 2>&1
-tail -12 "$OUT/multi_context_4dev.txt" | cut -c1-200
-( B2G_EXCHANGE=nccl examples/bin/multi_context_selftest 16 0 1 2 3 ) > "$OUT/multi_context_4dev_nccl.txt" 2>&1
-tail -2 "$OUT/multi_context_4dev_nccl.txt" | cut -c1-200
-timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "nccl_two_or_more" 2>&1 | tail -6 > "$OUT/pytest_multi.txt"
-tail -3 "$OUT/pytest_multi.txt"
-TR4="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29579"
-( time $TR4 bench.py --gpus 4 --steps 20 --warmup 5 --no-cpu-baseline ) > "$OUT/bench_n4.json" 2> "$OUT/bench_n4.err"
-tail -1 "$OUT/bench_n4.json" | cut -c1-600
+( time examples/bin/multi_context_selftest 18 0 1 ) > "$OUT/multi_context_2dev.txt" 2>&1
+grep -c "wrong depths: 0" "$OUT/multi_context_2dev.txt"; grep -E "sssp|pagerank|ALL OK|FAILED|real" "$OUT/multi_context_2dev.txt" | cut -c1-220
+( CUDA_MODULE_LOADING=EAGER B2G_P2P_TIMEOUT_MS=20000 examples/bin/multi_context_selftest 16 0 1 0 ) > "$OUT/multi_context_3ranks_2dev.txt" 2>&1
+tail -3 "$OUT/multi_context_3ranks_2dev.txt" | cut -c1-220
+( B2G_EXCHANGE=nccl examples/bin/multi_context_selftest 16 0 1 ) > "$OUT/multi_context_2dev_nccl.txt" 2>&1
+tail -2 "$OUT/multi_context_2dev_nccl.txt" | cut -c1-220
 ls -la "$OUT"
