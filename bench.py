@@ -301,10 +301,21 @@ def run_reference(args, wl, name):
     build_s = time.time() - t0
     run, kind, cores = cpu_run_factory(wl, ro, ci, w)
     src = bench_source(ro)
-    for _ in range(args.warmup):
+    # A step of this arm is one FULL run of the reference's CPU implementation (11-17 s for BFS on RMAT-26): the
+    # sample is bounded by running as many of the requested W + K runs as fit a wall-clock budget (at least one
+    # timed run); MTEPS is a rate, so fewer runs change its noise, not its meaning.
+    budget_s = float(os.environ.get("B2G_REFERENCE_BUDGET_S", "100"))
+    t_first = time.time()
+    res, t = run(src)
+    per_run_s = max(time.time() - t_first, 1e-3)
+    ms = []
+    n_warm = min(args.warmup, max(1, int(0.2 * budget_s / per_run_s))) if args.warmup > 0 else 0
+    if n_warm == 0:
+        ms.append(t)                      # no warm-up requested: the first run is a timed one
+    for _ in range(max(n_warm - 1, 0)):
         run(src)
-    ms, res = [], None
-    for _ in range(args.steps):
+    n_timed = min(args.steps, max(1, int((budget_s - n_warm * per_run_s) / per_run_s)))
+    while len(ms) < n_timed:
         res, t = run(src)
         ms.append(t)
     et = reached_degree_sum(wl, ro, res[0] if wl["alg"] == "pr" else res, res[1] if wl["alg"] == "pr" else None)
@@ -312,6 +323,7 @@ def run_reference(args, wl, name):
     value = et * len(ms) / total_ms / 1e3
     line = {"impl": "reference", "metric": f"MTEPS ({name})", "value": value, "unit": "MTEPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "steps_timed": len(ms), "warmup_run": n_warm,
             "ms_per_step": total_ms / max(len(ms), 1), "higher_is_better": True,
             "scaling": "strong" if wl.get("partitioned") else "weak",
             "vs_baseline": None, "dtype": "int32" if wl["alg"] == "bfs" else "f32", "data": "synthetic",
@@ -319,7 +331,8 @@ def run_reference(args, wl, name):
                        "source": src, "edges_touched_per_step": et,
                        "numerator": "sum of out-degrees of the reached vertices"},
             "cpu_baseline": {"value": value, "unit": "MTEPS", "cores": cores, "kind": kind,
-                             "sample": f"{len(ms)} full {wl['alg']} run(s) from the bench source, "
+                             "sample": f"{len(ms)} full {wl['alg']} run(s) (of {args.steps} requested; bounded by a "
+                                       f"{budget_s:.0f} s budget, B2G_REFERENCE_BUDGET_S) from the bench source, "
                                        f"validator's own timer; host cores available: {os.cpu_count()}; "
                                        f"the graph was built on the host with {oracle.num_threads()} threads "
                                        f"in {build_s:.1f} s (untimed)"},

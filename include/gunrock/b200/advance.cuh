@@ -213,10 +213,14 @@ constexpr int warp_path_ints() {
  */
 template <int kThreads, advance_input_t kIn, advance_output_t kOut, bool kDegSum, bool kWeights,
           typename Op>
-#ifdef B2G_BINNED_CTAS  // A/B builds only (-DB2G_BINNED_CTAS=n): cap the registers for n resident CTAs per SM
+// Resident CTAs per SM the kernel is compiled for.  Measured (profiles/r2_r_occupancy_ab.txt): the unweighted
+// functors (BFS claims) gain 7 % at 6 CTAs / 40 registers (BFS push RMAT-22 block_mapped 0.788 -> 0.733 ms, no
+// spills); the weighted ones (SSSP relax) LOSE at 40 or 32 registers (8.06 -> 9.57 / 8.18 ms: fewer loads in flight
+// per thread cost more than the extra warps hide) and keep their natural 48.
+#ifdef B2G_BINNED_CTAS  // A/B builds only (-DB2G_BINNED_CTAS=n)
 __global__ void __launch_bounds__(kThreads, B2G_BINNED_CTAS)
 #else
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kWeights ? 5 : 6)
 #endif
 advance_binned_kernel(advance_params_t p, Op op) {
   constexpr int kWarps = kThreads / 32;
