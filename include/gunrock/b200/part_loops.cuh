@@ -19,13 +19,13 @@
  */
 #pragma once
 
-#include <condition_variable>
 #include <cstring>
-#include <mutex>
 #include <stdexcept>
 
+#include <gunrock/b200/bfs_p2p.cuh>  // kMaxPeers
 #include <gunrock/b200/bfs_partitioned.cuh>
 #include <gunrock/b200/pr.cuh>
+#include <gunrock/b200/thread_hub.hxx>
 
 namespace gunrock {
 namespace b200 {
@@ -46,6 +46,8 @@ static __global__ void part_float_bits_kernel(const float* v, long long* stats) 
   stats[1] = stats[2] = stats[3] = 0;
 }
 
+static_assert(kHubMaxRanks == kMaxPeers, "thread_hub_t and the peer-memory windows agree on the rank limit");
+
 struct peer_table_t {
   const void* p[kMaxPeers];
 };
@@ -64,47 +66,6 @@ static __global__ void part_sum_peers_kernel(peer_table_t t, int nparts, size_t 
 // ---------------------------------------------------------------------------------------------------------------
 // Exchange between the threads of one process, one thread per rank.
 // ---------------------------------------------------------------------------------------------------------------
-/// Shared by the ranks of one run: a reusable barrier and the slots the ranks publish pointers / values in.
-struct thread_hub_t {
-  int nparts = 1;
-  std::mutex m;
-  std::condition_variable cv;
-  int waiting = 0;
-  unsigned long long generation = 0;
-  bool aborted = false;
-  const void* ptr[kMaxPeers] = {};
-  long long vals[2][kMaxPeers][4] = {};
-  float fvals[2][kMaxPeers] = {};
-
-  void reset(int n) {
-    std::lock_guard<std::mutex> lk(m);
-    nparts = n;
-    waiting = 0;
-    aborted = false;
-  }
-  /// Every rank arrives; throws in all of them when one has failed (`abort`), so no thread waits for ever.
-  void barrier() {
-    std::unique_lock<std::mutex> lk(m);
-    if (aborted)
-      throw std::runtime_error("a peer rank of this multi-device run failed");
-    const unsigned long long gen = generation;
-    if (++waiting == nparts) {
-      waiting = 0;
-      ++generation;
-      cv.notify_all();
-      return;
-    }
-    cv.wait(lk, [&] { return generation != gen || aborted; });
-    if (generation == gen)
-      throw std::runtime_error("a peer rank of this multi-device run failed");
-  }
-  void abort() {
-    std::lock_guard<std::mutex> lk(m);
-    aborted = true;
-    cv.notify_all();
-  }
-};
-
 /// One rank's end of the hub.  Needs the peers' device memory to be addressable from this rank's device (peer
 /// access enabled, or ranks sharing a device).
 struct thread_exchange_t {
