@@ -147,6 +147,73 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    # ---- NVML from a SEPARATE process (multi-GPU runs): an NVML query made inside a rank's own process stalls that
+    # rank's level loop for milliseconds; a child process polls the same two values and prints time-stamped lines,
+    # the parent keeps those that fall inside the timed region.
+    CHILD = ("import sys,time,pynvml\n"
+             "pynvml.nvmlInit()\n"
+             "h=pynvml.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))\n"
+             "g=getattr(pynvml,'nvmlDeviceGetCurrentClocksEventReasons',None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons\n"
+             "print('max',pynvml.nvmlDeviceGetMaxClockInfo(h,pynvml.NVML_CLOCK_SM),flush=True)\n"
+             "while True:\n"
+             "    print(time.time(),pynvml.nvmlDeviceGetClockInfo(h,pynvml.NVML_CLOCK_SM),int(g(h)),flush=True)\n"
+             "    time.sleep(float(sys.argv[2]))\n")
+
+    def start_child(self):
+        """Spawn the polling child now (its start-up takes ~0.2 s: call this before the warm-up steps)."""
+        idx = self.idx
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.idx])
+            except (ValueError, IndexError):
+                pass
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", self.CHILD, str(idx), str(self.period)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+            self.kind = "nvml-child"
+        except Exception:
+            self.proc = None
+
+    def stop_child(self, t_begin, t_end):
+        """Samples whose time stamps fall inside [t_begin, t_end] (host clock); ends the child."""
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sampler"]}
+        time.sleep(2.5 * self.period)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        mx, sm, reasons, total, inside, every = None, [], set(), 0, [], []
+        for ln in self.lines:
+            f = ln.split()
+            try:
+                if f[0] == "max":
+                    mx = float(f[1])
+                    continue
+                t, mhz, mask = float(f[0]), float(f[1]), int(f[2])
+            except (ValueError, IndexError):
+                continue
+            total += 1
+            every.append((mhz, mask))
+            if t_begin <= t <= t_end:
+                inside.append((mhz, mask))
+        note = "samples inside the timed region"
+        if not inside and every:    # a region shorter than the polling period: fall back to the whole run's samples
+            inside, note = every, "no sample fell inside the timed region: all samples of the run (warm-up included)"
+        for mhz, mask in inside:
+            sm.append(mhz)
+            for bit, nm in names.items():
+                if mask & bit:
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "samples_total": total, "reasons": sorted(reasons) if sm else ["no sampler"],
+                "source": "NVML polled every %g ms by a child process; %s" % (self.period * 1e3, note)}
+
     def stop(self):
         if self.kind == "nvml":
             self.stop_flag.set()
@@ -622,9 +689,11 @@ def run_partitioned(args, wl, name, rank, world, local):
         torch.cuda.synchronize()
         e0.record()
         inspected = 0
+        per_run.clear()
         for _ in range(k):
             dloc, st = step()
             inspected += st.edges_touched
+            per_run.append(float(st.elapsed_ms))      # the library's own events around this rank's level loop
             if copy_out is not None:
                 copy_out.copy_(dloc, non_blocking=False)
         e1.record()
@@ -634,28 +703,47 @@ def run_partitioned(args, wl, name, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), inspected, dloc, st
 
+    per_run = []
+
+    def run_spread():
+        r = sorted(per_run)
+        return {"best_ms": r[0], "median_ms": statistics.median(r), "worst_ms": r[-1],
+                "region": "rank 0, CUDA events around the level loop of each run"} if r else None
+
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local, period_s=0.005)   # ~4 samples inside a 20-step region of ~17 ms
+    if rank == 0 and not os.environ.get("B2G_BENCH_NO_SAMPLER"):
+        sampler.start_child()
     for _ in range(warm):
         primary()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # Clocks at N > 1.  An NVML query issued from a rank's OWN process stalls that rank's level loop for
+    # milliseconds (call U, 2 ranks: per-run median 0.76 ms, but the one run in ten that met a 10 ms in-process
+    # sample took 2.3 ms with the peer-memory exchange and 16.8 ms with NCCL; without any sampler best / median /
+    # worst were 0.744 / 0.747 / 0.755 ms) -- the single-GPU enactor shows no such effect.  So the sampling during
+    # the timed region is done by a CHILD process (started before the warm-up steps), and an identical region is
+    # timed once more with no sampler at all and reported beside it (`config.unsampled`).
+    t_begin = time.time()
     ms, inspected, dloc, st = timed(primary, args.steps)
+    t_end = time.time()
+    runs_primary = run_spread()
+    clocks = sampler.stop_child(t_begin, t_end) if rank == 0 else None
     # e2e: the rank's slice of the result is copied to pinned host memory inside the timed region
     h = torch.empty(G.n_local, dtype=torch.int32).pin_memory()
     ms2, _, dloc, _ = timed(primary, args.steps, copy_out=h)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_u, _, dloc, _ = timed(primary, args.steps)
+    unsampled = {"ms_per_step": ms_u / args.steps, "runs": run_spread(),
+                 "what": "the same %d-step region timed again with no clock sampler running" % args.steps}
     # the other exchange, same graph, same source, outside the headline's timed region
     other_rec = None
     try:
-        for _ in range(2):
+        for _ in range(3):
             other()
-        k2 = min(args.steps, 5)
+        k2 = min(args.steps, 10)
         ms_o, _, d_other, st_o = timed(other, k2)
         same = torch.tensor([int(torch.equal(dloc, d_other))], device="cuda")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         other_rec = {"exchange": "nccl" if args.exchange == "p2p" else "p2p", "ms_per_step": ms_o / k2,
-                     "depths_equal_primary": bool(same.item())}
+                     "steps": k2, "runs": run_spread(), "depths_equal_primary": bool(same.item())}
     except Exception as ex:
         other_rec = {"error": str(ex)[:300]}
 
@@ -704,7 +792,7 @@ def run_partitioned(args, wl, name, rank, world, local):
                 "config": {"workload": wl["desc"],
                            "exchange": "kernels over NVLink peer memory (CUDA IPC windows)" if args.exchange == "p2p"
                            else "NCCL from the C++ level loop: grouped ncclSend/ncclRecv, ncclAllGather, ncclAllReduce",
-                           "other_exchange": other_rec,
+                           "other_exchange": other_rec, "runs": runs_primary, "unsampled": unsampled,
                            "numerator": "sum of out-degrees of the reached vertices (identical at every N)",
                            "vertices": G.n_global, "edges": total_edges, "source": src,
                            "edges_touched_per_step": touched, "edges_inspected_per_step": inspected // args.steps,
