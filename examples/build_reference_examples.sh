@@ -10,7 +10,8 @@
 #  0. (no reference needed) examples/api_selftest.cu -> bin/api_selftest,
 #     examples/dense_frontier_selftest.cu (bitmap / boolmap frontier views) -> bin/dense_frontier_selftest,
 #     examples/cache_selftest.cu (per-graph caches of the fused enactors across graphs / contexts) -> bin/cache_selftest,
-#     examples/multi_context_selftest.cu (bfs::run over a multi-device gcuda::multi_context_t) -> bin/multi_context_selftest
+#     examples/multi_context_selftest.cu (bfs::run over a multi-device gcuda::multi_context_t) -> bin/multi_context_selftest,
+#     examples/reference_layout_selftest.cu (opt-in: advance output in the reference's edge-rank layout) -> bin/reference_layout_selftest
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 REF=${REF:-/root/reference}
@@ -22,6 +23,7 @@ nvcc $FLAGS -o "$OUT/api_selftest" "$ROOT/examples/api_selftest.cu" & pids+=($!)
 nvcc $FLAGS -o "$OUT/dense_frontier_selftest" "$ROOT/examples/dense_frontier_selftest.cu" & pids+=($!)
 nvcc $FLAGS -o "$OUT/cache_selftest" "$ROOT/examples/cache_selftest.cu" & pids+=($!)
 nvcc $FLAGS -o "$OUT/multi_context_selftest" "$ROOT/examples/multi_context_selftest.cu" & pids+=($!)
+nvcc $FLAGS -o "$OUT/reference_layout_selftest" "$ROOT/examples/reference_layout_selftest.cu" & pids+=($!)
 if [ ! -d "$REF" ]; then
   rc=0; for p in "${pids[@]}"; do wait $p || rc=1; done; exit $rc
 fi

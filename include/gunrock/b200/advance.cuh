@@ -671,9 +671,14 @@ __global__ void merge_path_partition_kernel(const int* __restrict__ scanned,
  * one warp-uniform search gives the row window, lanes finish with a <= 5-step local search.
  * Column loads are coalesced within rows; every tile costs the same number of edges whatever
  * the degree skew.
+ *
+ * kRanked = the REFERENCE's output layout instead of the compact one (opt-in, launch_advance_ranked): the
+ * output has one slot per edge rank -- out[rank] = the neighbour (or edge id) where the functor returned true,
+ * -1 where it did not, *out_count = scanned[n] -- which is what merge_path.hxx:218-279 writes and what
+ * callers that index the output by edge rank rely on.
  */
 template <int kThreads, int kTile, advance_input_t kIn, advance_output_t kOut, bool kDegSum,
-          bool kWeights, typename Op>
+          bool kWeights, bool kRanked, typename Op>
 __global__ void __launch_bounds__(kThreads)
 advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, Op op) {
   constexpr int kWarps = kThreads / 32;
@@ -815,16 +820,30 @@ advance_merge_path_kernel(advance_params_t p, const int* __restrict__ scanned, O
           keep[k] = valid[k] && op_commit(op, u[k], nb[k], e[k], w[k], tok[k]);
         if (kOut != advance_output_t::none) {
 #pragma unroll
-          for (int k = 0; k < kBatch; ++k)
-            em.push(keep[k], kOut == advance_output_t::edges ? e[k] : op_emit(op, nb[k]));
+          for (int k = 0; k < kBatch; ++k) {
+            const int item = kOut == advance_output_t::edges ? e[k] : op_emit(op, nb[k]);
+            if constexpr (kRanked) {
+              const int rank = r0 + 32 * k + lane;  // coalesced: consecutive lanes, consecutive slots
+              if (valid[k] && rank < p.out_capacity)
+                p.out[rank] = keep[k] ? item : -1;
+            } else {
+              em.push(keep[k], item);
+            }
+          }
         }
       }
     }
   }
-  if (kOut != advance_output_t::none)
+  if (kOut != advance_output_t::none && !kRanked)
     em.flush();
-  if (blockIdx.x == 0 && threadIdx.x == 0)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(&p.ctrl->edges, static_cast<unsigned long long>(total));
+    if (kRanked && kOut != advance_output_t::none) {
+      *p.out_count = min(total, p.out_capacity);
+      if (total > p.out_capacity)
+        p.ctrl->overflow = 1;
+    }
+  }
 }
 
 /**
@@ -1210,7 +1229,7 @@ inline bool aligned16(const void* p) {
 /// merge_path proper: partition into kTile-edge tiles, then the CTA kernel.
 /// Ranks are int32 (as in the reference, merge_path.hxx:325-327), so 2^31/kTile tiles bound every
 /// possible frontier, duplicates included.
-template <int kTile, advance_output_t kOut, bool kDegSum, bool kWeights, typename Op>
+template <int kTile, advance_output_t kOut, bool kDegSum, bool kWeights, bool kRanked = false, typename Op>
 inline void launch_merge_path_tiles(workspace_t& ws, advance_params_t& p, const int* scanned,
                                     bool graph_in, int grid, Op op) {
   constexpr int kThreads = 256;
@@ -1221,10 +1240,10 @@ inline void launch_merge_path_tiles(workspace_t& ws, advance_params_t& p, const 
   p.tile_rows = tile_rows;
   p.ctrl = ws.next_ctrl();
   if (graph_in)
-    advance_merge_path_kernel<kThreads, kTile, advance_input_t::graph, kOut, kDegSum, kWeights>
+    advance_merge_path_kernel<kThreads, kTile, advance_input_t::graph, kOut, kDegSum, kWeights, kRanked>
         <<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
   else
-    advance_merge_path_kernel<kThreads, kTile, advance_input_t::vertices, kOut, kDegSum, kWeights>
+    advance_merge_path_kernel<kThreads, kTile, advance_input_t::vertices, kOut, kDegSum, kWeights, kRanked>
         <<<grid, kThreads, 0, ws.stream>>>(p, scanned, op);
 }
 
@@ -1351,6 +1370,40 @@ inline void launch_advance(workspace_t& ws,
     }
   }
   ws.launches += (cfg.lb == lb_t::thread_mapped) ? 1 : 2;
+  if (ctrl_out)
+    *ctrl_out = p.ctrl;
+  B2G_CHECK(cudaGetLastError());
+}
+
+/**
+ * @brief One advance with the REFERENCE's output layout (opt-in; `standard_context_t::reference_advance_output`):
+ * slot r of the output belongs to edge rank r of the input frontier's expansion and holds the neighbour (edge id
+ * for an edge output) or -1, `*out_count` = the frontier's out-degree sum -- merge_path.hxx:218-279 /
+ * block_mapped.hxx:150-176 / thread_mapped.hxx:58-81 all produce a frontier of that shape (block_mapped with a
+ * CTA-order permutation of the rows).  Every load balancer takes the tile kernel here: the layout IS the
+ * merge-path rank space.  `out_capacity` must hold the degree sum (the caller sizes it, advance.hxx).
+ */
+template <advance_output_t kOut, bool kWeights, typename Op>
+inline void launch_advance_ranked(workspace_t& ws, const csr_view_t& g, const int* in, const int* in_count,
+                                  int in_upper_bound, int* out, int* out_count, int out_capacity, Op op,
+                                  const advance_launch_t& cfg, ctrl_t** ctrl_out = nullptr) {
+  static_assert(kOut != advance_output_t::none, "a ranked advance has an output frontier");
+  constexpr int kTile = 2048;
+  const int sms = device_info_t::get().sm_count;
+  advance_params_t p;
+  p.g = g;
+  p.in = in;
+  p.in_count = in_count;
+  p.out = out;
+  p.out_count = out_count;
+  p.out_capacity = out_capacity;
+  const bool graph_in = (in == nullptr);
+  const int* row_base = g.row_offsets;
+  const int* scanned = graph_in ? g.row_offsets
+                                : frontier_degree_scan(ws, g, in, in_count, in_upper_bound, &row_base);
+  p.row_base = row_base;
+  launch_merge_path_tiles<kTile, kOut, false, kWeights, true>(ws, p, scanned, graph_in, sms * cfg.ctas_per_sm, op);
+  ws.launches += 2;
   if (ctrl_out)
     *ctrl_out = p.ctrl;
   B2G_CHECK(cudaGetLastError());

@@ -52,6 +52,11 @@ class standard_context_t : public context_t {
   util::timer_t _timer;
   b200::workspace_t _workspace;
   bool _owns_stream = false;
+#ifdef GUNROCK_B200_REFERENCE_ADVANCE_OUTPUT
+  bool _reference_advance_output = true;
+#else
+  bool _reference_advance_output = false;
+#endif
   /// Scratch of the fused enactors (bfs / sssp / pr ...), one object per type, created on first use and
   /// destroyed WITH the context (device buffers, pinned blocks, events).  Nothing outside the context
   /// keeps a pointer-keyed table of contexts, so a freed-and-reallocated context can never alias
@@ -111,6 +116,13 @@ class standard_context_t : public context_t {
   auto execution_policy() { return thrust::cuda::par_nosync.on(_stream); }
   /// B200 operator scratch bound to this context's stream.
   b200::workspace_t& workspace() { return _workspace; }
+  /// Opt-in compatibility switch for `operators::advance::execute` (default off; on by default when the TU is
+  /// compiled with -DGUNROCK_B200_REFERENCE_ADVANCE_OUTPUT).  Off: the output frontier is compact.  On: it has
+  /// the reference's shape -- one slot per (input entry, out-edge) in edge-rank order, -1 where the functor
+  /// returned false, size = the input frontier's out-degree sum (merge_path.hxx:218-279) -- for code that
+  /// indexes an advance's output by edge rank or counts its invalid slots.
+  bool reference_advance_output() const { return _reference_advance_output; }
+  void reference_advance_output(bool on) { _reference_advance_output = on; }
   /// The context-owned scratch object of type T (default-constructed on first use).
   template <typename T>
   T& scratch() {

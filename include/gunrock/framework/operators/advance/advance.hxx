@@ -8,7 +8,9 @@
  * Operator contract unchanged (advance.hxx:35-49): `op(source, neighbor, edge, weight) -> bool`,
  * called once per (input entry, out-edge); `true` adds the neighbour (or the edge id for an edge
  * output) to the output frontier.  Behavioural differences, all documented in DESIGN.md:
- *   - the output frontier is compact (no invalid slots); a following filter sees only valid ids;
+ *   - the output frontier is compact (no invalid slots); a following filter sees only valid ids.  The
+ *     reference's layout (one slot per edge rank, -1 for rejected edges, merge_path.hxx:218-279) is an
+ *     opt-in: `context.get_context(0)->reference_advance_output(true)` or -DGUNROCK_B200_REFERENCE_ADVANCE_OUTPUT;
  *   - nothing synchronises with the host; the output size stays on the device until asked for;
  *   - `direction` is accepted and ignored exactly as in the reference -- pull and
  *     direction-optimised traversal are provided by the fused enactors (gunrock/b200/bfs.cuh);
@@ -104,7 +106,8 @@ void execute(graph_t& G,
     // kernels raise stays as the backstop (it reaches the frontier's own storage, mark_produced).
     std::size_t want = static_cast<std::size_t>(
         view.n_edges > view.n_vertices ? view.n_edges : view.n_vertices);
-    if (input_type != advance_io_type_t::graph && !input->is_known_unique()) {
+    const bool ranked = context0->reference_advance_output();
+    if (input_type != advance_io_type_t::graph && (ranked || !input->is_known_unique())) {
       const unsigned long long total = b200::frontier_degree_total(ws, view, in, in_count, in_bound);
       error::throw_if_exception(total > 0x7fffffffull, "advance: the output frontier would exceed 2^31 entries");
       if (static_cast<std::size_t>(total) > want)
@@ -118,9 +121,20 @@ void execute(graph_t& G,
     constexpr b200::advance_output_t kOut = output_type == advance_io_type_t::edges
                                                 ? b200::advance_output_t::edges
                                                 : b200::advance_output_t::vertices;
-    b200::launch_advance<kOut, false, true>(
-        ws, view, in, in_count, in_bound, reinterpret_cast<int*>(output->get()), output->count_ptr(),
-        static_cast<int>(output->get_capacity()), f, cfg, &ctrl);
+    if (ranked) {
+      // the reference's shape: slot = edge rank, -1 where `op` said false; every load balancer shares the
+      // rank-ordered tile kernel (the layout is the merge-path rank space)
+      const std::size_t slots = input_type == advance_io_type_t::graph
+                                    ? static_cast<std::size_t>(view.n_edges)
+                                    : static_cast<std::size_t>(cfg.edges_upper_bound);
+      b200::launch_advance_ranked<kOut, true>(
+          ws, view, in, in_count, in_bound, reinterpret_cast<int*>(output->get()), output->count_ptr(),
+          static_cast<int>(slots < output->get_capacity() ? slots : output->get_capacity()), f, cfg, &ctrl);
+    } else {
+      b200::launch_advance<kOut, false, true>(
+          ws, view, in, in_count, in_bound, reinterpret_cast<int*>(output->get()), output->count_ptr(),
+          static_cast<int>(output->get_capacity()), f, cfg, &ctrl);
+    }
     output->mark_produced(ws.stream, ctrl);
   }
 }

@@ -6,6 +6,7 @@
 //   * advance_warp_path_kernel: warp-private spans, 4 / 8 chunks in flight (the fused BFS / SSSP functors' default);
 //   * advance_binned_kernel + advance_hub_kernel ("block_mapped"; the hub kernel's cp.async.bulk + mbarrier staging is
 //     emulated as an immediate copy), advance_thread_mapped_kernel, advance_tail_kernel (several levels per launch);
+//   * the reference's output layout of advance_merge_path_kernel (one slot per edge rank, -1 for rejected edges);
 //   * both with the BFS claim functor (bitmap test-and-set) and the SSSP relax functor (needs the source id,
 //     reads weights), degree-sum accounting on.
 // Usage: emu_advance <seed>;  prints "EMU OK <checks>" and returns 0 when every check passes.
@@ -166,7 +167,7 @@ static run_out_t run_bfs(const graph_t& g, const frontier_case_t& f, const std::
   } else if (kind == kind_t::cta2048) {
     rows = partition<2048>(f);
     p.tile_rows = rows.data();
-    cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_merge_path_kernel<256, 2048, kV, kO, true, false>(p, f.scanned.data(), op); });
+    cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_merge_path_kernel<256, 2048, kV, kO, true, false, false>(p, f.scanned.data(), op); });
   } else {
     rows = partition<256>(f);
     p.tile_rows = rows.data();
@@ -245,7 +246,7 @@ static void run_and_check_limits(const graph_t& g, const frontier_case_t& f, con
     if (which == 0) {
       std::vector<int> rows = partition<2048>(f);
       p.tile_rows = rows.data();
-      cuemu::launch(2, 256, 0, 1, [&] { advance_merge_path_kernel<256, 2048, kV, kO, true, false>(p, f.scanned.data(), op); });
+      cuemu::launch(2, 256, 0, 1, [&] { advance_merge_path_kernel<256, 2048, kV, kO, true, false, false>(p, f.scanned.data(), op); });
     } else {
       p.hub_threshold = 64;
       p.hubs = hubs.data();
@@ -274,6 +275,68 @@ static void run_and_check_limits(const graph_t& g, const frontier_case_t& f, con
       CHECK(untouched);
     }
   }
+}
+
+/// The reference's output layout (advance_merge_path_kernel<..., kRanked = true>, launch_advance_ranked): slot r belongs
+/// to edge rank r of the frontier's expansion -- the neighbour / edge id where the functor said true, -1 elsewhere --
+/// and the count is the frontier's out-degree sum (merge_path.hxx:218-279).  A capacity below the sum raises overflow
+/// and writes nothing past it.
+struct keep_even_op {
+  int* calls;
+  __device__ bool operator()(int, int dst, int, float) const {
+    atomicAdd(calls, 1);
+    return (dst & 1) == 0;
+  }
+};
+static void run_and_check_ranked(const graph_t& g, const frontier_case_t& f, int grid_ctas) {
+  const int n = static_cast<int>(f.in.size());
+  const int total = f.scanned[n];
+  constexpr auto kV = advance_input_t::vertices;
+  std::vector<int> rows = partition<2048>(f);
+  for (int which = 0; which < 3; ++which) {  // 0: vertex output, 1: edge output, 2: capacity too small
+    const int cap = which == 2 ? total / 2 : total + 7;
+    std::vector<int> out(static_cast<size_t>(total) + 64, -7);
+    int out_count = -3, calls = 0;
+    ctrl_t ctrl;
+    std::memset(&ctrl, 0, sizeof ctrl);
+    advance_params_t p;
+    p.g = g.view();
+    p.in = f.in.data();
+    p.in_count = &n;
+    p.out = out.data();
+    p.out_count = &out_count;
+    p.out_capacity = cap;
+    p.ctrl = &ctrl;
+    p.row_base = f.row_base.data();
+    p.tile_rows = rows.data();
+    keep_even_op op{&calls};
+    if (which == 1)
+      cuemu::launch(grid_ctas, 256, 0, 1, [&] {
+        advance_merge_path_kernel<256, 2048, kV, advance_output_t::edges, false, false, true>(p, f.scanned.data(), op); });
+    else
+      cuemu::launch(grid_ctas, 256, 0, 1, [&] {
+        advance_merge_path_kernel<256, 2048, kV, advance_output_t::vertices, false, false, true>(p, f.scanned.data(), op); });
+    std::vector<int> expect;
+    for (int v : f.in) {
+      if (v < 0)
+        continue;
+      for (int e = g.ro[v]; e < g.ro[v + 1]; ++e)
+        expect.push_back((g.ci[e] & 1) == 0 ? (which == 1 ? e : g.ci[e]) : -1);
+    }
+    CHECK(static_cast<int>(expect.size()) == total);
+    CHECK(calls == total);                         // the functor runs once per edge whatever the capacity
+    CHECK(out_count == std::min(total, cap));
+    CHECK(ctrl.overflow == (which == 2 && total > cap ? 1 : 0));
+    CHECK(ctrl.edges == static_cast<unsigned long long>(total));
+    bool same = true, untouched = true;
+    for (int r = 0; r < std::min(total, cap); ++r)
+      same = same && out[r] == expect[r];
+    for (size_t r = std::min(total, cap); r < out.size(); ++r)
+      untouched = untouched && out[r] == -7;
+    CHECK(same);
+    CHECK(untouched);
+  }
+  std::printf("ranked layout: frontier %4d rows %7d slots ok\n", n, total);
 }
 
 /// One relaxation sweep with the SSSP functor (reads the source id and the weights).
@@ -327,7 +390,7 @@ static void run_and_check_sssp(const graph_t& g, const frontier_case_t& f, int m
   } else {
     rows = partition<2048>(f);
     p.tile_rows = rows.data();
-    cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_merge_path_kernel<256, 2048, kV, kO, true, true>(p, f.scanned.data(), op); });
+    cuemu::launch(grid_ctas, 256, 0, 1, [&] { advance_merge_path_kernel<256, 2048, kV, kO, true, true, false>(p, f.scanned.data(), op); });
   }
   // expected: dist = min over candidates of (dist0[src] + w) -- sources keep their start value unless relaxed too.
   // (a source may itself be lowered during the sweep; candidates then use either value: accept both bounds)
@@ -499,6 +562,7 @@ int main(int argc, char** argv) {
     }
     if (f.scanned.back() > 2000)
       run_and_check_limits(g, f, visited0);
+    run_and_check_ranked(g, f, 3);
     if (std::find(f.in.begin(), f.in.end(), -1) != f.in.end())
       continue;  // the SSSP sweep below labels its sources
     run_and_check_sssp(g, f, 0, 2);

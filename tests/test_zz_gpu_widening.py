@@ -242,3 +242,13 @@ def test_reference_mst_matches_its_cpu_run(tmp_path):
     g = float(re.search(r"GPU MST Weight: ([\d.]+)", out).group(1))
     c = float(re.search(r"CPU MST Weight: ([\d.]+)", out).group(1))
     assert g == c, out[-1500:]
+
+
+def test_zz_reference_output_layout_of_advance_selftest():
+    """Opt-in compatibility switch (`standard_context_t::reference_advance_output`): an advance's output frontier in
+    the reference's shape -- one slot per edge rank, -1 where the functor returned false, size = the input's
+    out-degree sum (reference merge_path.hxx:218-279) -- for all load balancers, vertex / edge outputs, an input with
+    an invalid slot and a duplicate, the whole graph as input, and a filter over the result.  (Kernel logic is also
+    covered on CPU by tests/test_cuemu_kernels.py.)"""
+    out = run([need("reference_layout_selftest")])
+    assert "ALL OK" in out, out[-2000:]
