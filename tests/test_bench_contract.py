@@ -85,3 +85,45 @@ print(json.dumps({{"impl": "reference_gpu", "algorithm": alg, "load_balance": lb
     assert abs(out["block_mapped"]["mteps"] - 4000 / 2.0 / 1e3) < 1e-12
     monkeypatch.setattr(bench, "ROOT", str(tmp_path / "nowhere"))
     assert "unavailable" in bench.reference_gpu_leg(FakeGraph(), {"alg": "bfs"}, 0, 1)
+
+
+def test_clock_sampler_child_process_protocol(monkeypatch):
+    """N > 1 runs sample clocks from a CHILD process (bench.ClockSampler.start_child / stop_child): time-stamped
+    lines, only those inside the timed region count, throttle bits become reason names, a region shorter than the
+    polling period falls back to all samples, and a child that cannot start NVML yields 'no sampler' -- never an
+    exception.  The child here is a stand-in that prints the same line format without NVML."""
+    import time
+    import bench
+
+    fake = ("import sys,time\n"
+            "print('max',1965,flush=True)\n"
+            "i=0\n"
+            "while True:\n"
+            "    print(time.time(),1965-15*(i%2),0x4 if i%5==0 else 0,flush=True)\n"
+            "    i+=1\n"
+            "    time.sleep(float(sys.argv[2]))\n")
+    monkeypatch.setattr(bench.ClockSampler, "CHILD", fake)
+    s = bench.ClockSampler(0, period_s=0.005)
+    s.start_child()
+    assert s.kind == "nvml-child"
+    time.sleep(0.3)                       # "warm-up": samples before the region must not count
+    t0 = time.time()
+    time.sleep(0.2)
+    t1 = time.time()
+    c = s.stop_child(t0, t1)
+    assert c["sm_max_mhz"] == 1965.0 and c["sm_mhz"] in (1950.0, 1957.5, 1965.0)
+    assert 5 <= c["samples"] < c["samples_total"] and c["reasons"] == ["sw_power_cap"]
+    assert "inside the timed region" in c["source"]
+    # a region no sample falls into: all samples of the run, and the note says so
+    s = bench.ClockSampler(0, period_s=0.005)
+    s.start_child()
+    time.sleep(0.2)
+    c = s.stop_child(0.0, 1.0)
+    assert c["samples"] == c["samples_total"] > 0 and "no sample fell inside" in c["source"]
+    # a child that dies at once (no NVML on this box: the real CHILD)
+    monkeypatch.undo()
+    s = bench.ClockSampler(0, period_s=0.005)
+    s.start_child()
+    c = s.stop_child(time.time(), time.time() + 1)
+    assert c["sm_mhz"] is None or isinstance(c["sm_mhz"], float)      # None here; a float on a GPU box
+    assert isinstance(c["reasons"], list)
