@@ -174,6 +174,13 @@ class ClockSampler:
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
             self.kind = "nvml-child"
+            # Wait until the child is SAMPLING (its first lines arrive) before any timed work starts: nvmlInit
+            # attaches every GPU of the box and holds the driver's locks for up to seconds -- call X (2 ranks) had
+            # the child still initialising during the 17 ms timed region: no sample at all and one traversal of
+            # 8.6 ms among 0.75 ms ones.  Bounded: a child that cannot load NVML exits and the wait ends.
+            deadline = time.time() + 20.0
+            while time.time() < deadline and len(self.lines) < 3 and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -713,15 +720,17 @@ def run_partitioned(args, wl, name, rank, world, local):
     warm = max(args.warmup, 3)
     sampler = ClockSampler(local, period_s=0.005)   # ~4 samples inside a 20-step region of ~17 ms
     if rank == 0 and not os.environ.get("B2G_BENCH_NO_SAMPLER"):
-        sampler.start_child()
+        sampler.start_child()      # returns once the child is sampling (its NVML start-up can take seconds)
+    dist.barrier()                 # the other ranks must not enter a traversal (bounded device-side spins) before that
     for _ in range(warm):
         primary()
     # Clocks at N > 1.  An NVML query issued from a rank's OWN process stalls that rank's level loop for
     # milliseconds (call U, 2 ranks: per-run median 0.76 ms, but the one run in ten that met a 10 ms in-process
     # sample took 2.3 ms with the peer-memory exchange and 16.8 ms with NCCL; without any sampler best / median /
     # worst were 0.744 / 0.747 / 0.755 ms) -- the single-GPU enactor shows no such effect.  So the sampling during
-    # the timed region is done by a CHILD process (started before the warm-up steps), and an identical region is
-    # timed once more with no sampler at all and reported beside it (`config.unsampled`).
+    # the timed region is done by a CHILD process (started, and waited for until it is sampling, before the warm-up
+    # steps: its nvmlInit stalls every rank's driver calls for the seconds it takes -- call X), and an identical
+    # region is timed once more with no sampler at all and reported beside it (`config.unsampled`).
     t_begin = time.time()
     ms, inspected, dloc, st = timed(primary, args.steps)
     t_end = time.time()
