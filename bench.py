@@ -718,7 +718,10 @@ def run_partitioned(args, wl, name, rank, world, local):
                 "region": "rank 0, CUDA events around the level loop of each run"} if r else None
 
     warm = max(args.warmup, 3)
-    sampler = ClockSampler(local, period_s=0.005)   # ~4 samples inside a 20-step region of ~17 ms
+    # 10 ms, the period of the N = 1 sampler: 1-2 samples inside a 20-step region of ~20 ms (call Y, 5 ms: 3 inside,
+    # the sampled region 1.13 ms / step against 1.01 un-sampled -- per-run medians 0.835 / 0.818); a region no sample
+    # falls into reports the samples of the whole run (warm-up and e2e regions: the same load) and says so
+    sampler = ClockSampler(local, period_s=0.010)
     if rank == 0 and not os.environ.get("B2G_BENCH_NO_SAMPLER"):
         sampler.start_child()      # returns once the child is sampling (its NVML start-up can take seconds)
     dist.barrier()                 # the other ranks must not enter a traversal (bounded device-side spins) before that
