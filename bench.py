@@ -720,7 +720,7 @@ def run_partitioned(args, wl, name, rank, world, local):
     warm = max(args.warmup, 3)
     # 10 ms, the period of the N = 1 sampler: 1-2 samples inside a 20-step region of ~20 ms (call Y, 5 ms: 3 inside,
     # the sampled region 1.13 ms / step against 1.01 un-sampled -- per-run medians 0.835 / 0.818); a region no sample
-    # falls into reports the samples of the whole run (warm-up and e2e regions: the same load) and says so
+    # falls into reports all samples the child took (they start before the warm-up steps: the same load) and says so
     sampler = ClockSampler(local, period_s=0.010)
     if rank == 0 and not os.environ.get("B2G_BENCH_NO_SAMPLER"):
         sampler.start_child()      # returns once the child is sampling (its NVML start-up can take seconds)
