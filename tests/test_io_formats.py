@@ -2,6 +2,7 @@
 include/gunrock/io/smtx.hxx:56-169) and `gunrock::array` (include/gunrock/container/array.hxx; reference
 include/gunrock/container/array.hxx:92-169).  Compiled as host code with nvcc (Thrust host vectors), nothing is
 launched."""
+import os
 import subprocess
 
 from conftest import ROOT
@@ -79,3 +80,100 @@ def test_smtx_reader_and_array(tmp_path):
     assert run("4 5\n")[0] == 3                                      # truncated file
     r = subprocess.run([str(exe), str(tmp_path / "missing.smtx")], capture_output=True, text=True)
     assert r.returncode == 4 and "Unable to open file" in r.stdout
+
+
+MTX_SRC = r"""
+#include <cstdio>
+#include <gunrock/io/matrix_market.hxx>
+using namespace gunrock;
+int main(int argc, char** argv) {
+  io::matrix_market_t<int, int, float> mm;
+  auto [props, coo] = mm.load(argv[1]);
+  std::printf("%d %d %d w%d s%d d%d\n", coo.number_of_rows, coo.number_of_columns, coo.number_of_nonzeros,
+              int(props.weighted), int(props.symmetric), int(props.directed));
+  FILE* f = fopen(argv[2], "wb");
+  const std::size_t n = coo.row_indices.size();
+  fwrite(coo.row_indices.data(), 4, n, f);
+  fwrite(coo.column_indices.data(), 4, n, f);
+  fwrite(coo.nonzero_values.data(), 4, n, f);
+  fclose(f);
+}
+"""
+
+
+def test_matrix_market_loader_parallel_fast_path_equals_the_entry_loop(tmp_path):
+    """include/gunrock/io/matrix_market.hxx parses a clean body with all host threads and leaves every irregular
+    body to the entry-at-a-time fscanf loop (the reference's reading order, matrix_market.hxx:153-250).  Whatever
+    the thread count, the outcome -- arrays bit for bit, properties, or the failure -- must be that loop's; clean
+    files are also compared with the unmodified reference loader (oracle/_ref) and the C restatement."""
+    import numpy as np
+    import oracle
+
+    src = tmp_path / "m.cu"
+    src.write_text(MTX_SRC)
+    exe = tmp_path / "m"
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "--extended-lambda", "--expt-relaxed-constexpr",
+                    "-gencode", "arch=compute_100a,code=sm_100a", f"-I{ROOT}/include", str(src), "-o", str(exe)],
+                   check=True, timeout=600)
+    rng = np.random.default_rng(7)
+    n = 5000
+    r, c = rng.integers(1, 301, n), rng.integers(1, 301, n)
+    w = rng.standard_normal(n) * 1e3
+    body_real = "\n".join(f"{a} {b} {float(x)!r}" for a, b, x in zip(r, c, w))
+    files = {
+        "real_general": "%%MatrixMarket matrix coordinate real general\n% a comment\n%\n300 300 5000\n" + body_real + "\n",
+        "no_final_newline": "%%MatrixMarket matrix coordinate real general\n300 300 5000\n" + body_real,
+        "pattern_symmetric": "%%MatrixMarket matrix coordinate pattern symmetric\n300 300 5000\n"
+                             + "\n".join(f"{max(a, b)} {min(a, b)}" for a, b in zip(r, c)) + "\n",
+        "integer_general": "%%MatrixMarket MATRIX Coordinate Integer General\n300 300 5000\n"
+                           + "\n".join(f"{a} {b} {int(x)}" for a, b, x in zip(r, c, w)) + "\n",
+        "blanks_tabs_crlf": "%%MatrixMarket matrix coordinate real general\n9 9 4\n\n  1\t2   3.5  \r\n\n3 4 -1e-3\r\n"
+                            "5 6 1E5\n   \n7 8 .25\n\n",
+        "odd_numbers": "%%MatrixMarket matrix coordinate real general\n9 9 4\n1 2 inf\n3 4 0x1p-3\n5 6 1e-50\n7 8 -0.0\n",
+        "empty_body": "%%MatrixMarket matrix coordinate pattern general\n5 5 0\n",
+        # ---- irregular bodies: the fast path must step aside --------------------------------------------------
+        "entry_split_over_lines": "%%MatrixMarket matrix coordinate real general\n9 9 3\n1 2\n3.5\n3 4 1\n5\n6 2\n",
+        "two_entries_per_line": "%%MatrixMarket matrix coordinate pattern general\n9 9 4\n1 2 3 4\n5 6 7 8\n",
+        "more_entries_than_announced": "%%MatrixMarket matrix coordinate pattern general\n9 9 2\n1 2\n3 4\n5 6\n7 8\n",
+        "plus_sign": "%%MatrixMarket matrix coordinate pattern general\n9 9 2\n+1 2\n3 4\n",
+        "short_file": "%%MatrixMarket matrix coordinate pattern general\n9 9 3\n1 2\n3 4\n",
+        "zero_index": "%%MatrixMarket matrix coordinate pattern general\n9 9 2\n1 2\n0 4\n",
+        "comment_in_body": "%%MatrixMarket matrix coordinate pattern general\n9 9 2\n1 2\n% no\n3 4\n",
+        "value_missing": "%%MatrixMarket matrix coordinate real general\n9 9 2\n1 2 1.5\n3 4\n",
+        "garbage_value": "%%MatrixMarket matrix coordinate real general\n9 9 2\n1 2 1.5x\n3 4 2\n",
+    }
+    clean = {"real_general", "no_final_newline", "pattern_symmetric", "integer_general", "blanks_tabs_crlf",
+             "odd_numbers", "empty_body"}
+    for name, text in files.items():
+        path = tmp_path / f"{name}.mtx"
+        path.write_text(text, newline="")
+        outcomes = {}
+        for threads in ("1", "2", "3", "7", None):
+            env = dict(os.environ)
+            env.pop("GUNROCK_B200_MTX_THREADS", None)
+            if threads:
+                env["GUNROCK_B200_MTX_THREADS"] = threads
+            out = tmp_path / f"{name}.{threads}.bin"
+            p = subprocess.run([str(exe), str(path), str(out)], capture_output=True, text=True, env=env, timeout=60)
+            outcomes[threads] = (p.returncode, p.stdout, out.read_bytes() if p.returncode == 0 else b"")
+        ref = outcomes["1"]      # the entry-at-a-time loop
+        for threads, got in outcomes.items():
+            assert got == ref, (name, threads, got[:2], ref[:2])
+        if name in clean:
+            assert ref[0] == 0, (name, ref[:2])
+            loaders = [oracle.load_mtx] + ([oracle.ref_load_mtx] if oracle.ref_available() else [])
+            for load in loaders:
+                g = load(str(path))
+                k = g["nnz"]
+                raw = np.frombuffer(ref[2], dtype=np.uint8)
+                assert len(raw) == 12 * k, (name, len(raw), k)
+                assert np.array_equal(raw[:4 * k].view(np.int32), g["I"]), name
+                assert np.array_equal(raw[4 * k:8 * k].view(np.int32), g["J"]), name
+                assert np.array_equal(raw[8 * k:].view(np.uint32), g["V"].view(np.uint32)), name   # bit for bit
+                assert ref[1].split()[:3] == [str(g["n_rows"]), str(g["n_cols"]), str(k)], name
+    # irregular bodies: whatever the loop decides is the answer (equality above); the failures the reference defines
+    # must still be failures
+    for name in ("short_file", "zero_index", "value_missing"):
+        p = subprocess.run([str(exe), str(tmp_path / f"{name}.mtx"), str(tmp_path / "x.bin")], capture_output=True,
+                           text=True, timeout=60)
+        assert p.returncode != 0, name
