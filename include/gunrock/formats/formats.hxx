@@ -8,13 +8,20 @@
  * index_t rows, index_t cols, offset_t nnz, offsets[rows+1], indices[nnz], values[nnz]).
  *
  * from_coo keeps the reference's result exactly (stable counting sort by row, duplicates and
- * self loops kept, csr.hxx:81-140) but does the histogram + scatter with std:: algorithms on the
- * host arrays once and uploads once.
+ * self loops kept, csr.hxx:81-140) but does the histogram + scatter on the host arrays once and
+ * uploads once.  Both it and csc_t::from_csr go through `detail::stable_bucket` with all host threads
+ * (after the text parse this is the longest step of an example program's ingest):
+ * the histogram is taken over entry chunks, the keys are cut into blocks of ~equal entry counts, and
+ * each thread scatters the entries of ITS key block walking the entries in order -- which keeps the
+ * sort stable and the result bit-identical to the serial loop.  `GUNROCK_B200_HOST_THREADS=1` forces that loop.
  */
 #pragma once
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <gunrock/container/vector.hxx>
@@ -25,6 +32,97 @@ namespace gunrock {
 namespace format {
 
 using namespace memory;
+
+namespace detail {
+
+inline unsigned host_threads(std::size_t items) {
+  unsigned t = std::thread::hardware_concurrency();
+  if (const char* env = std::getenv("GUNROCK_B200_HOST_THREADS"))
+    return static_cast<unsigned>(std::max(1, std::min(64, std::atoi(env))));
+  // every thread of the scatter pass reads all keys: beyond 16 the extra streams cost more than they save
+  t = std::max(1u, std::min(t, 16u));
+  return static_cast<unsigned>(std::min<std::size_t>(t, items / (std::size_t(1) << 19) + 1));
+}
+
+/**
+ * @brief Stable counting sort of `n` entries into `buckets` buckets: `offsets[b]` = first slot of bucket b
+ * (`offsets[buckets]` = n), and `place(k, slot)` is called once per entry k with its slot; entries of a bucket
+ * keep their order.  `key(k)` must be in [0, buckets) -- checked, an out-of-range key throws instead of
+ * corrupting memory (the reference indexes unchecked, csr.hxx:96-115).
+ */
+template <typename offset_t, typename key_fn, typename place_fn>
+void stable_bucket(std::size_t n, std::size_t buckets, offset_t* offsets, key_fn key, place_fn place) {
+  const unsigned threads = host_threads(n);
+  std::fill(offsets, offsets + buckets + 1, offset_t(0));
+  if (threads <= 1) {
+    for (std::size_t k = 0; k < n; ++k) {
+      const std::size_t b = static_cast<std::size_t>(key(k));
+      if (b >= buckets)  // (the message is only built on failure: this loop runs once per entry)
+        error::throw_if_exception(true, "sparse format conversion: index out of range");
+      ++offsets[b + 1];
+    }
+    for (std::size_t b = 0; b < buckets; ++b)
+      offsets[b + 1] += offsets[b];
+    std::vector<offset_t> cursor(offsets, offsets + buckets);
+    for (std::size_t k = 0; k < n; ++k)
+      place(k, cursor[static_cast<std::size_t>(key(k))]++);
+    return;
+  }
+  // 1. histogram over entry chunks (relaxed atomic increments: contended only on hub rows)
+  std::vector<char> bad(threads, 0);
+  {
+    std::vector<std::thread> team;
+    auto count = [&](unsigned t) {
+      const std::size_t lo = n / threads * t, hi = t + 1 == threads ? n : n / threads * (t + 1);
+      for (std::size_t k = lo; k < hi; ++k) {
+        const std::size_t b = static_cast<std::size_t>(key(k));
+        if (b >= buckets) {
+          bad[t] = 1;
+          return;
+        }
+        __atomic_fetch_add(&offsets[b + 1], offset_t(1), __ATOMIC_RELAXED);
+      }
+    };
+    for (unsigned t = 1; t < threads; ++t)
+      team.emplace_back(count, t);
+    count(0);
+    for (auto& th : team)
+      th.join();
+  }
+  error::throw_if_exception(std::count(bad.begin(), bad.end(), 1) != 0,
+                            "sparse format conversion: index out of range");
+  for (std::size_t b = 0; b < buckets; ++b)
+    offsets[b + 1] += offsets[b];
+  // 2. key blocks of ~n / threads entries each; a thread scatters the entries of its block, in entry order
+  std::vector<std::size_t> cut(threads + 1, buckets);
+  cut[0] = 0;
+  for (unsigned t = 1; t < threads; ++t) {
+    const offset_t want = static_cast<offset_t>(n / threads * t);
+    cut[t] = static_cast<std::size_t>(std::lower_bound(offsets, offsets + buckets, want) - offsets);
+    cut[t] = std::max(cut[t], cut[t - 1]);
+  }
+  {
+    std::vector<std::thread> team;
+    auto scatter = [&](unsigned t) {
+      const std::size_t lo = cut[t], hi = cut[t + 1];
+      if (lo >= hi)
+        return;
+      std::vector<offset_t> cursor(offsets + lo, offsets + hi);
+      for (std::size_t k = 0; k < n; ++k) {
+        const std::size_t b = static_cast<std::size_t>(key(k));
+        if (b >= lo && b < hi)
+          place(k, cursor[b - lo]++);
+      }
+    };
+    for (unsigned t = 1; t < threads; ++t)
+      team.emplace_back(scatter, t);
+    scatter(0);
+    for (auto& th : team)
+      th.join();
+  }
+}
+
+}  // namespace detail
 
 template <memory_space_t space, typename index_t, typename offset_t, typename value_t>
 struct coo_t {
@@ -101,19 +199,26 @@ struct csr_t {
     thrust::host_vector<offset_t> offs(rows + 1, 0);
     thrust::host_vector<index_t> cols(nnz);
     thrust::host_vector<value_t> vals(nnz);
-    for (std::size_t k = 0; k < nnz; ++k)
-      ++offs[static_cast<std::size_t>(coo.row_indices[k]) + 1];
-    for (std::size_t r = 0; r < rows; ++r)
-      offs[r + 1] += offs[r];
-    std::vector<offset_t> cursor(offs.begin(), offs.begin() + rows);
-    for (std::size_t k = 0; k < nnz; ++k) {
-      offset_t at = cursor[coo.row_indices[k]]++;
-      cols[at] = coo.column_indices[k];
-      vals[at] = coo.nonzero_values[k];
+    const index_t* ri = coo.row_indices.data();
+    const index_t* cj = coo.column_indices.data();
+    const value_t* vv = coo.nonzero_values.data();
+    index_t* out_c = cols.data();
+    value_t* out_v = vals.data();
+    detail::stable_bucket(
+        nnz, rows, offs.data(), [=](std::size_t k) { return ri[k]; },
+        [=](std::size_t k, offset_t at) {
+          out_c[at] = cj[k];
+          out_v[at] = vv[k];
+        });
+    if constexpr (space == memory_space_t::host) {  // host result: adopt the arrays instead of copying them
+      row_offsets.swap(offs);
+      column_indices.swap(cols);
+      nonzero_values.swap(vals);
+    } else {
+      row_offsets = offs;
+      column_indices = cols;
+      nonzero_values = vals;
     }
-    row_offsets = offs;
-    column_indices = cols;
-    nonzero_values = vals;
     return *this;
   }
 
@@ -190,20 +295,31 @@ struct csc_t {
     thrust::host_vector<offset_t> offs(cols + 1, 0);
     thrust::host_vector<index_t> rows(nnz);
     thrust::host_vector<value_t> vals(nnz);
-    for (std::size_t e = 0; e < nnz; ++e)
-      ++offs[static_cast<std::size_t>(ci[e]) + 1];
-    for (std::size_t c = 0; c < cols; ++c)
-      offs[c + 1] += offs[c];
-    std::vector<offset_t> cursor(offs.begin(), offs.begin() + cols);
+    // source row of every entry (what the serial double loop walks implicitly), then the same stable bucket
+    // sort by column: entries of a column stay in source-row order
+    std::vector<index_t> src(nnz);
     for (index_t u = 0; u < number_of_rows; ++u)
-      for (offset_t e = ro[u]; e < ro[u + 1]; ++e) {
-        offset_t at = cursor[ci[e]]++;
-        rows[at] = u;
-        vals[at] = vv[e];
-      }
-    column_offsets = offs;
-    row_indices = rows;
-    nonzero_values = vals;
+      std::fill(src.begin() + ro[u], src.begin() + ro[u + 1], u);
+    const index_t* col = ci.data();
+    const value_t* val = vv.data();
+    const index_t* from = src.data();
+    index_t* out_r = rows.data();
+    value_t* out_v = vals.data();
+    detail::stable_bucket(
+        nnz, cols, offs.data(), [=](std::size_t e) { return col[e]; },
+        [=](std::size_t e, offset_t at) {
+          out_r[at] = from[e];
+          out_v[at] = val[e];
+        });
+    if constexpr (space == memory_space_t::host) {
+      column_offsets.swap(offs);
+      row_indices.swap(rows);
+      nonzero_values.swap(vals);
+    } else {
+      column_offsets = offs;
+      row_indices = rows;
+      nonzero_values = vals;
+    }
     return *this;
   }
 };

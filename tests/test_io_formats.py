@@ -177,3 +177,84 @@ def test_matrix_market_loader_parallel_fast_path_equals_the_entry_loop(tmp_path)
         p = subprocess.run([str(exe), str(tmp_path / f"{name}.mtx"), str(tmp_path / "x.bin")], capture_output=True,
                            text=True, timeout=60)
         assert p.returncode != 0, name
+
+
+CSR_SRC = r"""
+#include <cstdio>
+#include <gunrock/io/matrix_market.hxx>
+using namespace gunrock;
+using namespace memory;
+template <typename vec_t>
+static void dump(FILE* f, const vec_t& v) { fwrite(v.data(), sizeof(v[0]), v.size(), f); }
+int main(int argc, char** argv) {
+  io::matrix_market_t<int, int, float> mm;
+  auto [props, coo] = mm.load(argv[1]);
+  if (argc > 3) coo.row_indices[coo.row_indices.size() / 2] = coo.number_of_rows;   // an index out of range
+  format::csr_t<memory_space_t::host, int, int, float> csr;
+  csr.from_coo(coo);
+  format::csc_t<memory_space_t::host, int, int, float> csc;
+  csc.from_csr(csr);
+  FILE* f = fopen(argv[2], "wb");
+  dump(f, csr.row_offsets); dump(f, csr.column_indices); dump(f, csr.nonzero_values);
+  dump(f, csc.column_offsets); dump(f, csc.row_indices); dump(f, csc.nonzero_values);
+  fclose(f);
+  std::printf("%d %d %d\n", csr.number_of_rows, csr.number_of_columns, csr.number_of_nonzeros);
+}
+"""
+
+
+def test_from_coo_and_from_csr_with_host_threads_equal_the_serial_loops(tmp_path):
+    """format::csr_t::from_coo / csc_t::from_csr (include/gunrock/formats/formats.hxx; reference formats/csr.hxx:81-140,
+    csc.hxx:62-102) run their stable counting sort with all host threads.  Any thread count must give the serial
+    loop's arrays bit for bit -- a skewed graph with hub rows, duplicates, self loops and empty rows -- and those
+    must be the reference's own from_coo (oracle/_ref) and the C restatement's from_coo / transpose."""
+    import numpy as np
+    import oracle
+
+    src = tmp_path / "c.cu"
+    src.write_text(CSR_SRC)
+    exe = tmp_path / "c"
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "--extended-lambda", "--expt-relaxed-constexpr",
+                    "-gencode", "arch=compute_100a,code=sm_100a", f"-I{ROOT}/include", str(src), "-o", str(exe)],
+                   check=True, timeout=600)
+    rng = np.random.default_rng(11)
+    n_rows, n_cols, nnz = 3000, 2500, 200_000
+    r = np.minimum((n_rows * rng.random(nnz) ** 4).astype(np.int64), n_rows - 1)      # hubs at the low ids
+    r[r % 11 == 5] = 7                                                                   # empty rows + one fat row
+    c = np.minimum((n_cols * rng.random(nnz) ** 2).astype(np.int64), n_cols - 1)
+    c[::97] = np.minimum(r[::97], n_cols - 1)                                            # self loops
+    r[1::2000], c[1::2000] = r[0::2000][:len(r[1::2000])], c[0::2000][:len(c[1::2000])]  # exact duplicates
+    w = (rng.integers(1, 1 << 20, nnz) / 64.0).astype(np.float32)
+    mtx = tmp_path / "skew.mtx"
+    with open(mtx, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate real general\n{n_rows} {n_cols} {nnz}\n")
+        f.write("\n".join(f"{a + 1} {b + 1} {float(x)!r}" for a, b, x in zip(r, c, w)) + "\n")
+
+    def run(threads, *extra):
+        env = dict(os.environ)
+        env.pop("GUNROCK_B200_HOST_THREADS", None)
+        if threads:
+            env["GUNROCK_B200_HOST_THREADS"] = threads
+        out = tmp_path / f"csr.{threads}.bin"
+        p = subprocess.run([str(exe), str(mtx), str(out), *extra], capture_output=True, text=True, env=env, timeout=120)
+        return p.returncode, p.stdout, (out.read_bytes() if p.returncode == 0 else b"")
+
+    serial = run("1")
+    assert serial[0] == 0 and serial[1].split() == [str(n_rows), str(n_cols), str(nnz)]
+    for threads in ("2", "3", "5", "16", None):
+        assert run(threads) == serial, threads
+    raw = np.frombuffer(serial[2], dtype=np.uint8)
+    cut = np.cumsum([0, 4 * (n_rows + 1), 4 * nnz, 4 * nnz, 4 * (n_cols + 1), 4 * nnz, 4 * nnz])
+    ro, ci, vv, co, rj, tv = (raw[a:b] for a, b in zip(cut[:-1], cut[1:]))
+    checks = [oracle.csr_from_coo(n_rows, r, c, w)]
+    if oracle.ref_available():
+        checks.append(oracle.ref_csr_from_coo(n_rows, n_cols, r, c, w))
+    for e_ro, e_ci, e_v in checks:
+        assert np.array_equal(ro.view(np.int32), e_ro) and np.array_equal(ci.view(np.int32), e_ci)
+        assert np.array_equal(vv.view(np.uint32), e_v.view(np.uint32))
+    t_ro, t_ci, t_v = oracle.csr_transpose(n_rows, n_cols, ro.view(np.int32), ci.view(np.int32), vv.view(np.float32))
+    assert np.array_equal(co.view(np.int32), t_ro) and np.array_equal(rj.view(np.int32), t_ci)
+    assert np.array_equal(tv.view(np.uint32), t_v.view(np.uint32))
+    # an index outside [0, rows) is an error with any thread count (the reference would write out of bounds)
+    for threads in ("1", "4"):
+        assert run(threads, "corrupt")[0] != 0
