@@ -106,6 +106,8 @@ _SYMBOLS = [
     "b2g_graph_build_transpose", "b2g_graph_destroy", "b2g_graph_info", "b2g_graph_device_ptrs",
     "b2g_graph_download", "b2g_graph_max_degree_vertex", "b2g_bfs", "b2g_sssp", "b2g_pr",
     "b2g_advance_bfs", "b2g_filter", "b2g_uniquify",
+    # host-side ingest (no device involved)
+    "b2g_mtx_load", "b2g_host_free", "b2g_csr_from_coo_host",
     # multi-GPU per-rank steps (bound in gunrock_b200/multi_gpu.py)
     "b2g_graph_create_rmat_part", "b2g_graph_create_csr_part", "b2g_part_info", "b2g_part_bfs_begin",
     "b2g_part_bfs_topdown", "b2g_part_bfs_send_buffer", "b2g_part_bfs_claim",
@@ -155,6 +157,10 @@ def lib() -> C.CDLL:
                                       C.POINTER(u64)]
         L.b2g_filter.argtypes = [vp, ip, vp, vp, ip, vp, vp, vp]
         L.b2g_uniquify.argtypes = [vp, vp, vp, ip, vp, vp, ip]
+        L.b2g_mtx_load.argtypes = [C.c_char_p] + [C.POINTER(ip)] * 3 + [C.POINTER(vp)] * 3 + [C.POINTER(ip)] * 3
+        L.b2g_host_free.argtypes = [vp]
+        L.b2g_host_free.restype = None
+        L.b2g_csr_from_coo_host.argtypes = [ip, ip, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -356,3 +362,51 @@ def uniquify(G: graph_t, frontier, frontier_count, out, out_count, best_effort: 
     _check(lib().b2g_uniquify(G._h, frontier.data_ptr(), frontier_count.data_ptr(),
                               int(frontier.numel()), out.data_ptr(), out_count.data_ptr(),
                               int(best_effort)), "b2g_uniquify")
+
+
+# ---- host-side ingest (no device involved) -----------------------------------------------------------------
+def load_mtx(path: str) -> dict:
+    """io::matrix_market_t::load (include/gunrock/io/matrix_market.hxx:99-254) through the C ABI (`b2g_mtx_load`):
+    a clean body is parsed by all host threads, results identical to the reference's loader.  Returns
+    ``dict(n_rows, n_cols, nnz, I, J, V, directed, weighted, symmetric)`` with numpy arrays; a bad file raises
+    GunrockB200Error carrying the reference's message."""
+    L = lib()
+    n_rows, n_cols, nnz = C.c_int(), C.c_int(), C.c_int()
+    I, J, V = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    d, w, sy = C.c_int(), C.c_int(), C.c_int()
+    _check(L.b2g_mtx_load(os.fsencode(path), C.byref(n_rows), C.byref(n_cols), C.byref(nnz), C.byref(I), C.byref(J),
+                          C.byref(V), C.byref(d), C.byref(w), C.byref(sy)), "b2g_mtx_load")
+    n = nnz.value
+    try:
+        def take(p, ctype, dtype):
+            if n == 0:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(n,)).astype(dtype, copy=True)
+        out = dict(n_rows=n_rows.value, n_cols=n_cols.value, nnz=n, I=take(I, C.c_int, np.int32),
+                   J=take(J, C.c_int, np.int32), V=take(V, C.c_float, np.float32),
+                   directed=bool(d.value), weighted=bool(w.value), symmetric=bool(sy.value))
+    finally:
+        for p in (I, J, V):
+            L.b2g_host_free(p)
+    return out
+
+
+def csr_from_coo_host(n_rows: int, I, J, V=None):
+    """format::csr_t<host>::from_coo (include/gunrock/formats/csr.hxx:81-140) through the C ABI
+    (`b2g_csr_from_coo_host`): stable counting sort by row with all host threads.  Returns
+    ``(row_offsets, column_indices, values)``; values is None when V is None."""
+    I = np.ascontiguousarray(I, np.int32)
+    J = np.ascontiguousarray(J, np.int32)
+    nnz = int(I.size)
+    if J.size != nnz or (V is not None and np.size(V) != nnz):
+        raise ValueError("I, J (and V) must have the same length")
+    Vc = None if V is None else np.ascontiguousarray(V, np.float32)
+    ro = np.empty(int(n_rows) + 1, np.int32)
+    ci = np.empty(nnz, np.int32)
+    vals = None if V is None else np.empty(nnz, np.float32)
+    _check(lib().b2g_csr_from_coo_host(int(n_rows), nnz, I.ctypes.data if nnz else None, J.ctypes.data if nnz else None,
+                                       None if Vc is None or not nnz else Vc.ctypes.data, ro.ctypes.data,
+                                       ci.ctypes.data if nnz else None,
+                                       None if vals is None or not nnz else vals.ctypes.data),
+           "b2g_csr_from_coo_host")
+    return ro, ci, vals

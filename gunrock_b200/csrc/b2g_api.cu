@@ -31,6 +31,8 @@
 #include <gunrock/b200/pr.cuh>
 #include <gunrock/b200/sssp.cuh>
 #include <gunrock/b200/transpose.cuh>
+#include <gunrock/formats/formats.hxx>       // host-side ingest only: format::detail::stable_bucket
+#include <gunrock/io/detail/mtx_reader.hxx>  // host-side ingest only: io::detail::mtx_read
 
 using namespace gunrock::b200;
 
@@ -1824,6 +1826,70 @@ int b2g_part_bfs_distances(b2g_graph_t* g, int* distances, int loc) {
                               loc == B2G_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
                               g->ws.stream));
     B2G_CHECK(cudaStreamSynchronize(g->ws.stream));
+    return 0;
+  });
+}
+
+// ---- host-side ingest: file formats either side of the path (no device involved) --------------------------
+int b2g_mtx_load(const char* path, int* n_rows, int* n_cols, int* nnz, int** I, int** J, float** V,
+                 int* directed, int* weighted, int* symmetric) {
+  if (!path || !n_rows || !n_cols || !nnz || !I || !J || !V)
+    return fail(B2G_ERR_INVALID, "b2g_mtx_load: null argument");
+  return guarded([&] {
+    namespace mio = gunrock::io::detail;
+    mio::mtx_header_t header;
+    std::vector<int> rows, cols;
+    std::vector<float> vals;
+    const mio::mtx_status_t st =
+        mio::mtx_read<int, float>(path, static_cast<size_t>(INT_MAX), header, rows, cols, vals);
+    if (st != mio::mtx_status_t::ok)
+      return fail(B2G_ERR_INVALID, std::string(mio::mtx_message(st)) + ": " + path);
+    const size_t n = rows.size();
+    int* out_i = static_cast<int*>(malloc(sizeof(int) * (n ? n : 1)));
+    int* out_j = static_cast<int*>(malloc(sizeof(int) * (n ? n : 1)));
+    float* out_v = static_cast<float*>(malloc(sizeof(float) * (n ? n : 1)));
+    if (!out_i || !out_j || !out_v) {
+      free(out_i);
+      free(out_j);
+      free(out_v);
+      return fail(B2G_ERR_INTERNAL, "b2g_mtx_load: out of host memory");
+    }
+    std::copy(rows.begin(), rows.end(), out_i);
+    std::copy(cols.begin(), cols.end(), out_j);
+    std::copy(vals.begin(), vals.end(), out_v);
+    *n_rows = static_cast<int>(header.rows);
+    *n_cols = static_cast<int>(header.columns);
+    *nnz = static_cast<int>(n);
+    *I = out_i;
+    *J = out_j;
+    *V = out_v;
+    if (directed)
+      *directed = header.symmetric ? 0 : 1;
+    if (weighted)
+      *weighted = header.pattern ? 0 : 1;
+    if (symmetric)
+      *symmetric = header.symmetric ? 1 : 0;
+    return 0;
+  });
+}
+
+void b2g_host_free(void* p) {
+  free(p);
+}
+
+int b2g_csr_from_coo_host(int n_rows, int nnz, const int* I, const int* J, const float* V, int* row_offsets,
+                          int* column_indices, float* values) {
+  if (n_rows < 0 || nnz < 0 || !row_offsets || (nnz > 0 && (!I || !J || !column_indices)) ||
+      (nnz > 0 && V && !values))
+    return fail(B2G_ERR_INVALID, "b2g_csr_from_coo_host: bad arguments");
+  return guarded([&] {
+    gunrock::format::detail::stable_bucket(
+        static_cast<size_t>(nnz), static_cast<size_t>(n_rows), row_offsets, [=](size_t k) { return I[k]; },
+        [=](size_t k, int at) {
+          column_indices[at] = J[k];
+          if (V)
+            values[at] = V[k];
+        });
     return 0;
   });
 }

@@ -87,16 +87,12 @@ class csr_t(_format_base):                # formats/csr.hxx (bindings.cu:109-116
     def from_coo(self, coo: coo_t) -> "csr_t":
         """csr_t::from_coo (formats/csr.hxx:81-140): stable counting sort by row -- a row keeps its
         entries in COO order; duplicates and self loops are kept."""
+        from . import csr_from_coo_host
         n = int(coo.number_of_rows)
-        rows = np.asarray(coo.row_indices, np.int64)
-        if rows.size and (rows.min() < 0 or rows.max() >= n):
-            raise GunrockB200Error("coo_t row index out of range")
-        order = np.argsort(rows, kind="stable")
+        ro, ci, vals = csr_from_coo_host(n, coo.row_indices, coo.column_indices, coo.nonzero_values)
         self.number_of_rows, self.number_of_columns = n, int(coo.number_of_columns)
-        self.number_of_nonzeros = int(rows.size)
-        self.row_offsets = np.concatenate(([0], np.cumsum(np.bincount(rows, minlength=n)))).astype(np.int32)
-        self.column_indices = np.ascontiguousarray(np.asarray(coo.column_indices, np.int32)[order])
-        self.nonzero_values = np.ascontiguousarray(np.asarray(coo.nonzero_values, np.float32)[order])
+        self.number_of_nonzeros = int(ci.size)
+        self.row_offsets, self.column_indices, self.nonzero_values = ro, ci, vals
         return self
 
     def read_binary(self, filename: str) -> "csr_t":
@@ -135,51 +131,14 @@ class matrix_market_t:
     off-diagonal entries are followed IN PLACE by their mirror (diagonal entries kept once)."""
 
     def load(self, filename: str) -> Tuple[graph_properties_t, coo_t]:
-        with open(filename, "r") as f:
-            banner = f.readline().split()
-            if len(banner) != 5 or banner[0] != "%%MatrixMarket":
-                raise GunrockB200Error(f"{filename}: could not process the Matrix Market banner")
-            _, mtx, crd, data_type, storage = (x.lower() for x in banner)
-            if mtx != "matrix" or crd != "coordinate":
-                raise GunrockB200Error(f"{filename}: file is not a sparse matrix")
-            if data_type not in ("pattern", "real", "integer"):
-                raise GunrockB200Error(f"{filename}: unsupported data type {data_type!r}")
-            pattern, symmetric = data_type == "pattern", storage == "symmetric"
-            line = f.readline()
-            while line and (line.startswith("%") or not line.strip()):
-                line = f.readline()
-            try:
-                n_rows, n_cols, nnz = (int(x) for x in line.split()[:3])
-            except ValueError as e:
-                raise GunrockB200Error(f"{filename}: bad size line {line!r}") from e
-            if max(n_rows, n_cols, nnz) >= 2**31 - 1:
-                raise GunrockB200Error(f"{filename}: vertex_t / edge_t overflow")
-            body = np.loadtxt(f, dtype=np.float64, ndmin=2, max_rows=nnz) if nnz else np.zeros((0, 3))
-        if body.shape[0] != nnz or body.shape[1] < (2 if pattern else 3):
-            raise GunrockB200Error(f"{filename}: expected {nnz} entries")
-        r = body[:, 0].astype(np.int64) - 1
-        c = body[:, 1].astype(np.int64) - 1
-        if nnz and (r.min() < 0 or c.min() < 0):
-            raise GunrockB200Error(f"{filename}: indices are 1-based")
-        w = np.ones(nnz, np.float32) if pattern else body[:, 2].astype(np.float32)
-        if symmetric:
-            # entry k is followed by its mirror unless it sits on the diagonal
-            off = r != c
-            reps = 1 + off.astype(np.int64)
-            first = np.cumsum(reps) - reps                     # slot of each original entry
-            total = int(reps.sum())
-            I = np.empty(total, np.int64)
-            J = np.empty(total, np.int64)
-            V = np.empty(total, np.float32)
-            I[first], J[first], V[first] = r, c, w
-            m = first[off] + 1
-            I[m], J[m], V[m] = c[off], r[off], w[off]
-        else:
-            I, J, V = r, c, w
+        # the native reader of include/gunrock/io/detail/mtx_reader.hxx through the C ABI: every host thread on a
+        # clean body, the reference's entry-at-a-time order otherwise -- the arrays the reference's loader returns
+        from . import load_mtx
+        m = load_mtx(filename)
         props = graph_properties_t()
-        props.directed, props.weighted, props.symmetric = (not symmetric), (not pattern), symmetric
-        coo = coo_t(n_rows, n_cols, len(I))
-        coo.row_indices, coo.column_indices, coo.nonzero_values = I.astype(np.int32), J.astype(np.int32), V
+        props.directed, props.weighted, props.symmetric = m["directed"], m["weighted"], m["symmetric"]
+        coo = coo_t(m["n_rows"], m["n_cols"], m["nnz"])
+        coo.row_indices, coo.column_indices, coo.nonzero_values = m["I"], m["J"], m["V"]
         return props, coo
 
 

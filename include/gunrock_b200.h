@@ -129,6 +129,22 @@ int b2g_graph_download(const b2g_graph_t* g, int* row_offsets, int* column_indic
 /* Vertex of maximum out-degree (lowest id on ties) -- the bench source rule. */
 int b2g_graph_max_degree_vertex(const b2g_graph_t* g, int* vertex, int* degree);
 
+/* ---- host-side ingest (no device needed): the file formats either side of the path ------------
+ * io::matrix_market_t::load (include/gunrock/io/matrix_market.hxx:99-254): coordinate files, pattern /
+ * real / integer, general / symmetric; 1-based -> 0-based, pattern => weight 1.0, a symmetric file's
+ * off-diagonal entries are followed in place by their mirror.  A clean body is parsed by all host
+ * threads, results identical to the reference's loader.  *I, *J, *V are allocated by the library
+ * (*nnz entries each, mirrors included) and released with b2g_host_free.  Bad files return
+ * B2G_ERR_INVALID with the reference's message in b2g_last_error() instead of exiting the process. */
+int b2g_mtx_load(const char* path, int* n_rows, int* n_cols, int* nnz, int** I, int** J, float** V,
+                 int* directed, int* weighted, int* symmetric);
+void b2g_host_free(void* p);
+/* format::csr_t<host>::from_coo (include/gunrock/formats/csr.hxx:81-140) on host arrays: stable counting
+ * sort by row with all host threads, duplicates and self loops kept.  Outputs are caller-allocated:
+ * row_offsets[n_rows+1], column_indices[nnz], values[nnz] (V == NULL => values may be NULL). */
+int b2g_csr_from_coo_host(int n_rows, int nnz, const int* I, const int* J, const float* V,
+                          int* row_offsets, int* column_indices, float* values);
+
 /* ---- algorithms (fused enactors) ----------------------------------------------------------- */
 
 /* gunrock::bfs::run (include/gunrock/algorithms/bfs.hxx:162-182): distances[V] int32, INT_MAX if

@@ -258,3 +258,65 @@ def test_from_coo_and_from_csr_with_host_threads_equal_the_serial_loops(tmp_path
     # an index outside [0, rows) is an error with any thread count (the reference would write out of bounds)
     for threads in ("1", "4"):
         assert run(threads, "corrupt")[0] != 0
+
+
+def test_c_abi_host_ingest_and_the_python_module_on_top_of_it(tmp_path):
+    """`b2g_mtx_load` / `b2g_csr_from_coo_host` (include/gunrock_b200.h; host-only, no device needed) and
+    `gunrock.matrix_market_t().load` / `csr_t().from_coo` that sit on them: same arrays as the C restatement and the
+    unmodified reference loader / from_coo, bad files raise instead of exiting the interpreter."""
+    import numpy as np
+    import pytest
+    import oracle
+    import gunrock_b200 as gb
+    from gunrock_b200 import pygunrock as gunrock
+
+    rng = np.random.default_rng(3)
+    n, nnz = 400, 9000
+    r, c = rng.integers(1, n + 1, nnz), rng.integers(1, n + 1, nnz)
+    w = rng.standard_normal(nnz)
+    files = {
+        "sym.mtx": "%%MatrixMarket matrix coordinate real symmetric\n% comment\n"
+                   f"{n} {n} {nnz}\n" + "\n".join(f"{max(a, b)} {min(a, b)} {float(x)!r}" for a, b, x in zip(r, c, w)) + "\n",
+        "pat.mtx": f"%%MatrixMarket matrix coordinate pattern general\n{n} {n} {nnz}\n"
+                   + "\n".join(f"{a} {b}" for a, b in zip(r, c)) + "\n",
+        "split.mtx": "%%MatrixMarket matrix coordinate real general\n9 9 2\n1 2\n3.5 3\n4 1e2\n",   # irregular body
+    }
+    for name, text in files.items():
+        path = tmp_path / name
+        path.write_text(text)
+        got = gb.load_mtx(str(path))
+        for load in [oracle.load_mtx] + ([oracle.ref_load_mtx] if oracle.ref_available() else []):
+            exp = load(str(path))
+            assert (got["n_rows"], got["n_cols"], got["nnz"]) == (exp["n_rows"], exp["n_cols"], exp["nnz"]), name
+            assert (got["directed"], got["weighted"], got["symmetric"]) == \
+                (exp["directed"], exp["weighted"], exp["symmetric"]), name
+            assert np.array_equal(got["I"], exp["I"]) and np.array_equal(got["J"], exp["J"]), name
+            assert np.array_equal(got["V"].view(np.uint32), exp["V"].view(np.uint32)), name
+        # the Python module: loader + from_coo
+        props, coo = gunrock.matrix_market_t().load(str(path))
+        assert (props.directed, props.weighted, props.symmetric) == (got["directed"], got["weighted"], got["symmetric"])
+        csr = gunrock.csr_t().from_coo(coo)
+        e_ro, e_ci, e_v = oracle.csr_from_coo(coo.number_of_rows, coo.row_indices, coo.column_indices,
+                                              coo.nonzero_values)
+        assert np.array_equal(csr.row_offsets, e_ro) and np.array_equal(csr.column_indices, e_ci), name
+        assert np.array_equal(csr.nonzero_values.view(np.uint32), e_v.view(np.uint32)), name
+        assert csr.number_of_nonzeros == got["nnz"] and csr.row_offsets.dtype == np.int32
+    # from_coo without values, an empty COO, an out-of-range row
+    ro, ci, vals = gb.csr_from_coo_host(5, [4, 0, 4, 2], [1, 2, 0, 2])
+    assert ro.tolist() == [0, 1, 1, 2, 2, 4] and ci.tolist() == [2, 2, 1, 0] and vals is None
+    ro, ci, vals = gb.csr_from_coo_host(3, [], [], np.zeros(0, np.float32))
+    assert ro.tolist() == [0, 0, 0, 0] and ci.size == 0 and vals.size == 0
+    with pytest.raises(gb.GunrockB200Error, match="out of range"):
+        gb.csr_from_coo_host(3, [0, 3], [0, 0])
+    # bad files: an error with the reference's message, not exit(1)
+    for text, message in (("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n", "not a sparse matrix"),
+                          ("hello\n", "banner"),
+                          ("%%MatrixMarket matrix coordinate complex general\n2 2 1\n1 1 1 0\n", "format type"),
+                          ("%%MatrixMarket matrix coordinate pattern general\n2 2 2\n1 1\n", "Could not read edge"),
+                          ("%%MatrixMarket matrix coordinate pattern general\n2 2 1\n0 1\n", "zero-indexed")):
+        bad = tmp_path / "bad.mtx"
+        bad.write_text(text)
+        with pytest.raises(gb.GunrockB200Error, match=message):
+            gb.load_mtx(str(bad))
+    with pytest.raises(gb.GunrockB200Error, match="could not be opened"):
+        gb.load_mtx(str(tmp_path / "missing.mtx"))
