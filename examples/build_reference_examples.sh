@@ -45,6 +45,10 @@ for alg in bc color geo hits kcore ppr spmv mst tc spgemm; do
   echo "#include \"$REF/include/gunrock/algorithms/$alg.hxx\"" > "$SHIM/$alg.hxx"
   nvcc $FLAGS -I"$OUT/shim" -I"$REF/examples/algorithms/$alg" -o "$OUT/ext_$alg" "$REF/examples/algorithms/$alg/$alg.cu" & pids+=($!)
 done
+#  5. the reference's tools, unchanged: tools/csr_binary.cu (.mtx -> binary .csr through our loader, from_coo and
+#     write_binary) -> bin/tool_csr_binary, tools/cmd.cu (the cxxopts surface of include/cxxopts.hpp) -> bin/tool_cmd
+nvcc $FLAGS -o "$OUT/tool_csr_binary" "$REF/examples/tools/csr_binary.cu" & pids+=($!)
+nvcc $FLAGS -o "$OUT/tool_cmd" "$REF/examples/tools/cmd.cu" & pids+=($!)
 rc=0
 for p in "${pids[@]}"; do wait $p || rc=1; done
 ls -la "$OUT"

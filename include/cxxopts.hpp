@@ -15,6 +15,7 @@
 
 #include <cstdlib>
 #include <initializer_list>
+#include <iostream>  // callers print `options.help()` with std::cout and include nothing else (examples/tools/cmd.cu)
 #include <map>
 #include <memory>
 #include <sstream>

@@ -50,3 +50,24 @@ def test_cxxopts_subset(tmp_path):
     rc, out = run()
     assert rc == 0 and "Usage:" in out            # no --market: help, like the examples
     assert run("--nope")[0] == 3 and run("-m")[0] == 3
+
+
+def test_reference_cmd_tool_compiles_unchanged_and_runs():
+    """The reference's examples/tools/cmd.cu (its command-line parser test: <cxxopts.hpp> + util/filepath.hxx and
+    nothing else) built UNCHANGED by examples/build_reference_examples.sh -> examples/bin/tool_cmd.  Host only."""
+    import os
+    import pytest
+    exe = os.path.join(ROOT, "examples", "bin", "tool_cmd")
+    if not os.path.exists(exe):
+        pytest.skip("examples/bin/tool_cmd not built (needs /root/reference at build time)")
+
+    def run(*a):
+        r = subprocess.run([exe, *a], capture_output=True, text=True, timeout=30)
+        return r.returncode, r.stdout
+
+    assert run("-m", "graph.mtx") == (0, "")                 # a .mtx name: accepted silently
+    assert run("--csr", "graph.csr", "-d", "1") == (0, "")
+    rc, out = run("-m", "graph.txt")                          # not a market file: help
+    assert rc == 0 and "Gunrock commandline parser test" in out and "--market arg" in out and "--csr arg" in out
+    rc, out = run()
+    assert rc == 0 and "Usage:" in out
