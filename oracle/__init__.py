@@ -247,6 +247,22 @@ def ref_load_mtx(path: str) -> dict:
     return _load_mtx_with(ref(), "ref_load_mtx", "ref_free", path)
 
 
+def ref_load_smtx(path: str, first_line_csv: bool = False) -> dict:
+    """The UNMODIFIED reference `.smtx` reader (io/smtx.hxx:56-169); the random values it attaches are dropped."""
+    L = ref()
+    n_rows, n_cols, nnz = C.c_int(), C.c_int(), C.c_int()
+    ro, ci = C.POINTER(C.c_int)(), C.POINTER(C.c_int)()
+    rc = L.ref_load_smtx(path.encode(), int(first_line_csv), C.byref(n_rows), C.byref(n_cols), C.byref(nnz),
+                         C.byref(ro), C.byref(ci))
+    if rc != 0:
+        raise RuntimeError(f"ref_load_smtx({path}) failed")
+    r = np.ctypeslib.as_array(ro, shape=(n_rows.value + 1,)).copy()
+    c = np.ctypeslib.as_array(ci, shape=(max(nnz.value, 1),))[:nnz.value].copy()
+    for p in (ro, ci):
+        L.ref_free(C.cast(p, C.c_void_p))
+    return dict(n_rows=n_rows.value, n_cols=n_cols.value, nnz=nnz.value, row_offsets=r, column_indices=c)
+
+
 def ref_csr_from_coo(n_rows, n_cols, I, J, V):
     I = np.ascontiguousarray(I, np.int32)
     J = np.ascontiguousarray(J, np.int32)

@@ -7,6 +7,7 @@
 // What it exposes (host only, no GPU needed):
 //   ref_load_mtx        -> gunrock::io::matrix_market_t::load      (include/gunrock/io/matrix_market.hxx:104-254)
 //   ref_csr_from_coo    -> gunrock::format::csr_t<host>::from_coo  (include/gunrock/formats/csr.hxx:81-140)
+//   ref_load_smtx       -> gunrock::io::smtx_t::load               (include/gunrock/io/smtx.hxx:56-169)
 //   ref_bfs_cpu         -> bfs_cpu::run                            (examples/algorithms/bfs/bfs_cpu.hxx:20-68)
 //   ref_sssp_cpu        -> sssp_cpu::run                           (examples/algorithms/sssp/sssp_cpu.hxx:22-72)
 //
@@ -18,6 +19,7 @@
 #include <string>
 
 #include <gunrock/algorithms/algorithms.hxx>
+#include <gunrock/io/smtx.hxx>
 
 #include "bfs_cpu.hxx"
 #include "sssp_cpu.hxx"
@@ -66,6 +68,24 @@ int ref_load_mtx(const char* filename,
 
 void ref_free(void* p) {
   free(p);
+}
+
+// .smtx through the reference's own reader.  Arrays are malloc'ed (free with ref_free); the values the reference
+// attaches are random draws (smtx.hxx:139-140) and are not returned.
+int ref_load_smtx(const char* filename, int first_line_csv, int* n_rows, int* n_cols, int* nnz, int** row_offsets,
+                  int** column_indices) {
+  io::smtx_t<vertex_t, edge_t, weight_t> smtx;
+  try {
+    auto csr = smtx.load(std::string(filename), first_line_csv != 0);
+    *n_rows = csr.number_of_rows;
+    *n_cols = csr.number_of_columns;
+    *nnz = csr.number_of_nonzeros;
+    *row_offsets = dup_out(csr.row_offsets.data(), csr.row_offsets.size());
+    *column_indices = dup_out(csr.column_indices.data(), csr.column_indices.size());
+  } catch (const std::exception&) {
+    return 1;
+  }
+  return 0;
 }
 
 // COO (host) -> CSR (host) through the reference's own from_coo.

@@ -3,7 +3,7 @@
 Run in the authoring container (needs /root/reference and `make -C oracle ref`):
     python tests/golden/make_golden.py
 Every expected array below is produced by the reference's own code compiled from where it lies:
-    io::matrix_market_t::load, format::csr_t::from_coo, bfs_cpu::run, sssp_cpu::run
+    io::matrix_market_t::load, io::smtx_t::load, format::csr_t::from_coo, bfs_cpu::run, sssp_cpu::run
 (oracle/ref_driver.cu).  The RMAT inputs are defined by the oracle's counter-based generator; only
 its parameters and a sha256 of the resulting CSR are stored, the expected distances come from
 the reference validators run on that CSR.
@@ -100,6 +100,17 @@ def main():
         arrays[f"sssp_abs_bits_{s}"] = np.ascontiguousarray(g.sssp(s)[0], np.float32).view(np.uint32)
     np.savez_compressed(os.path.join(HERE, "bips98_606.npz"), **arrays)
     print("wrote bips98_606.npz", os.path.getsize(os.path.join(HERE, "bips98_606.npz")), "bytes; sources", srcs)
+
+    # 6. the reference's `.smtx` dataset through its own reader (io/smtx.hxx:56-169); its unit test asserts the
+    #    sizes 96 x 96 with 4608 entries (unittests/io/smtx.cuh:28-30).  Only the structure is stored: the values
+    #    the reference attaches are random draws.
+    path = os.path.join(REF, "datasets/layers.0.blocks.0.attn.proj_swin_tiny_unstructured_50.smtx")
+    g = oracle.ref_load_smtx(path)
+    assert (g["n_rows"], g["n_cols"], g["nnz"]) == (96, 96, 4608)
+    np.savez_compressed(os.path.join(HERE, "swin_tiny_attn_proj_smtx.npz"),
+                        shape=np.array([g["n_rows"], g["n_cols"], g["nnz"]], np.int32),
+                        row_offsets=g["row_offsets"], column_indices=g["column_indices"])
+    print("wrote swin_tiny_attn_proj_smtx.npz")
 
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, separators=(",", ":"))

@@ -51,6 +51,55 @@ int main(int argc, char** argv) {
 """
 
 
+SMTX_DUMP_SRC = r"""
+#include <cstdio>
+#include <gunrock/io/smtx.hxx>
+using namespace gunrock;
+int main(int argc, char** argv) {
+  io::smtx_t<int, int, float> loader;
+  auto csr = loader.load(argv[1]);
+  std::printf("%d %d %d\n", csr.number_of_rows, csr.number_of_columns, csr.number_of_nonzeros);
+  FILE* f = fopen(argv[2], "wb");
+  fwrite(csr.row_offsets.data(), 4, csr.row_offsets.size(), f);
+  fwrite(csr.column_indices.data(), 4, csr.column_indices.size(), f);
+  fclose(f);
+}
+"""
+
+
+def test_smtx_reader_against_the_reference_dataset_golden(tmp_path):
+    """Golden vector: the reference's one `.smtx` dataset read by the reference's own `io::smtx_t::load`
+    (tests/golden/make_golden.py -> swin_tiny_attn_proj_smtx.npz); its unit test asserts 96 x 96 with 4608 entries
+    (/root/reference/unittests/io/smtx.cuh:28-30).  Our reader must give the same structure on the same file --
+    re-serialised from the golden arrays, and the original where the reference tree is present."""
+    import numpy as np
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "swin_tiny_attn_proj_smtx.npz"))
+    rows, cols, nnz = (int(x) for x in g["shape"])
+    assert (rows, cols, nnz) == (96, 96, 4608)
+    src = tmp_path / "s.cu"
+    src.write_text(SMTX_DUMP_SRC)
+    exe = tmp_path / "s"
+    subprocess.run(["nvcc", "-std=c++17", "--extended-lambda", "--expt-relaxed-constexpr",
+                    "-gencode", "arch=compute_100a,code=sm_100a", f"-I{ROOT}/include", str(src), "-o", str(exe)],
+                   check=True, timeout=600)
+    again = tmp_path / "again.smtx"
+    again.write_text("% Sparse matrix file format .smtx\n% re-serialised from tests/golden\n"
+                     f"{rows}, {cols}, {nnz}\n".replace(", ", " ")
+                     + " ".join(str(int(x)) for x in g["row_offsets"]) + "\n"
+                     + " ".join(str(int(x)) for x in g["column_indices"]) + "\n")
+    files = [str(again)]
+    original = "/root/reference/datasets/layers.0.blocks.0.attn.proj_swin_tiny_unstructured_50.smtx"
+    if os.path.exists(original):
+        files.append(original)
+    for path in files:
+        out = tmp_path / "dump.bin"
+        r = subprocess.run([str(exe), path, str(out)], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and r.stdout.split() == ["96", "96", "4608"], (path, r.stdout, r.stderr)
+        raw = np.fromfile(out, dtype=np.int32)
+        assert np.array_equal(raw[:rows + 1], g["row_offsets"]) and np.array_equal(raw[rows + 1:], g["column_indices"])
+
+
 def test_smtx_reader_and_array(tmp_path):
     src = tmp_path / "t.cu"
     src.write_text(SRC)
