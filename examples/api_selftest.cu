@@ -333,9 +333,15 @@ int main() {
   // ---- launch_box_t --------------------------------------------------------------------------------
   {
     using namespace gcuda;
-    typedef launch_box_t<launch_params_t<sm_90, dim3_t<128>, dim3_t<4>, 0>,
+    typedef launch_box_t<launch_params_t<sm_90 | sm_89, dim3_t<128>, dim3_t<4>, 1, 0>,
                          launch_params_dynamic_grid_t<fallback, dim3_t<256>, 3>> box_t;
     static_assert(box_t::block_dimensions_t::size() == 256, "fallback entry selected for SM_TARGET 100");
+    // an entry naming the target (among others) wins over the fallback, wherever it stands
+    typedef launch_box_t<launch_params_t<fallback, dim3_t<64>, dim3_t<2>>,
+                         launch_params_t<sm_90 | sm_100, dim3_t<128>, dim3_t<4>, 2, 16>> named_t;
+    static_assert(named_t::block_dimensions_t::size() == 128 && named_t::items_per_thread == 2 &&
+                      named_t::shared_memory_bytes == 16 && named_t::grid_dimensions_t::x == 4,
+                  "sm_90 | sm_100 serves SM_TARGET 100");
     box_t box;
     thrust::device_vector<int> v(1000, 0);
     int* p = v.data().get();

@@ -49,6 +49,10 @@ done
 #     write_binary) -> bin/tool_csr_binary, tools/cmd.cu (the cxxopts surface of include/cxxopts.hpp) -> bin/tool_cmd
 nvcc $FLAGS -o "$OUT/tool_csr_binary" "$REF/examples/tools/csr_binary.cu" & pids+=($!)
 nvcc $FLAGS -o "$OUT/tool_cmd" "$REF/examples/tools/cmd.cu" & pids+=($!)
+#  6. the reference's OWN unit tests (unittests/unittests.hxx and the 15 headers it includes), unchanged, against
+#     our include tree; tests/gtest_shim/gtest/gtest.h stands in for googletest (not in the image); tc.hxx is the
+#     reference's, through the shim directory of section 4 -> bin/ref_unittests (--gtest_filter, --gtest_list_tests)
+nvcc $FLAGS -I"$OUT/shim" -I"$REF/unittests" -I"$ROOT/tests/gtest_shim" -o "$OUT/ref_unittests" "$ROOT/examples/ref_unittests_main.cu" & pids+=($!)
 rc=0
 for p in "${pids[@]}"; do wait $p || rc=1; done
 ls -la "$OUT"

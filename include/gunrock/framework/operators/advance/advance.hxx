@@ -19,6 +19,8 @@
  */
 #pragma once
 
+#include <type_traits>
+
 #include <gunrock/b200/advance.cuh>
 #include <gunrock/cuda/context.hxx>
 #include <gunrock/error.hxx>
@@ -31,7 +33,9 @@ namespace advance {
 namespace detail {
 
 /// Adapts the user's `op(vertex_t const&, vertex_t const&, edge_t const&, weight_t const&)`.
-template <typename graph_t, typename operator_t>
+template <typename graph_t,
+          typename operator_t,
+          bool float_weights = std::is_same<typename graph_t::weight_type, float>::value>
 struct op_adapter_t {
   operator_t op;
   __device__ __forceinline__ bool operator()(int src, int dst, int edge, float w) const {
@@ -41,6 +45,34 @@ struct op_adapter_t {
     return op(s, d, e, wt);
   }
 };
+/// weight_t other than float (int, double ...): the kernels walk the structure only (graph_t::structure_view) and
+/// the edge's weight is read here, in its own type, by edge id.
+template <typename graph_t, typename operator_t>
+struct op_adapter_t<graph_t, operator_t, false> {
+  operator_t op;
+  const typename graph_t::weight_type* typed_values;
+  __device__ __forceinline__ bool operator()(int src, int dst, int edge, float) const {
+    typename graph_t::vertex_type s = src, d = dst;
+    typename graph_t::edge_type e = edge;
+    typename graph_t::weight_type wt =
+        typed_values ? typed_values[edge] : static_cast<typename graph_t::weight_type>(1);
+    return op(s, d, e, wt);
+  }
+};
+template <typename graph_t, typename operator_t>
+op_adapter_t<graph_t, operator_t> make_op_adapter(graph_t& G, operator_t op) {
+  if constexpr (std::is_same<typename graph_t::weight_type, float>::value)
+    return op_adapter_t<graph_t, operator_t>{op};
+  else
+    return op_adapter_t<graph_t, operator_t>{op, G.get_nonzero_values()};
+}
+template <typename graph_t>
+b200::csr_view_t kernel_view(graph_t& G) {
+  if constexpr (std::is_same<typename graph_t::weight_type, float>::value)
+    return G.csr_view();
+  else
+    return G.structure_view();
+}
 
 inline b200::lb_t to_lb(load_balance_t lb) {
   switch (lb) {
@@ -80,8 +112,8 @@ void execute(graph_t& G,
                 "edge input frontiers are not supported by the B200 advance");
   auto context0 = context.get_context(0);
   b200::workspace_t& ws = context0->workspace();
-  auto view = G.csr_view();
-  detail::op_adapter_t<graph_t, operator_t> f{op};
+  auto view = detail::kernel_view(G);
+  auto f = detail::make_op_adapter(G, op);
   b200::advance_launch_t cfg;
   cfg.lb = detail::to_lb(lb);
 

@@ -9,6 +9,7 @@
 #include <gunrock/b200/ptx.cuh>
 #include <gunrock/cuda/context.hxx>
 #include <gunrock/error.hxx>
+#include <gunrock/framework/frontier/frontier.hxx>  // parallel_for over a frontier; callers include only this header
 #include <gunrock/framework/operators/configs.hxx>
 
 namespace gunrock {

@@ -16,6 +16,7 @@
 #pragma once
 
 #include <cassert>
+#include <cmath>
 #include <type_traits>
 
 #include <gunrock/b200/runtime.cuh>
@@ -53,6 +54,10 @@ template <typename T>
 struct is_csc_view : std::false_type {};
 template <memory_space_t space, typename vertex_t, typename edge_t, typename weight_t>
 struct is_csc_view<graph_csc_t<space, vertex_t, edge_t, weight_t>> : std::true_type {};
+template <typename T>
+struct is_coo_view : std::false_type {};
+template <memory_space_t space, typename vertex_t, typename edge_t, typename weight_t>
+struct is_coo_view<graph_coo_t<space, vertex_t, edge_t, weight_t>> : std::true_type {};
 }  // namespace detail
 
 template <memory_space_t space, typename vertex_t, typename edge_t, typename weight_t>
@@ -67,6 +72,10 @@ class graph_t {
   using vertex_pair_type = vertex_pair_t<vertex_t>;
   using csr_view_type = graph_csr_t<space, vertex_t, edge_t, weight_t>;
   using csc_view_type = graph_csc_t<space, vertex_t, edge_t, weight_t>;
+  // the reference's names for the view tags (graph/graph.hxx:74-81)
+  using graph_csr_view_t = csr_view_type;
+  using graph_csc_view_t = csc_view_type;
+  using graph_coo_view_t = graph_coo_t<space, vertex_t, edge_t, weight_t>;
 
   __host__ __device__ graph_t() {}
   __host__ __device__ graph_t(std::nullptr_t) {}
@@ -91,10 +100,22 @@ class graph_t {
   bool is_directed() { return properties.directed; }
   bool is_symmetric() { return properties.symmetric; }
   bool is_weighted() { return properties.weighted; }
-  /// Which views are attached (graph/graph.hxx:284-296 `contains_representation`).
+  /// Which views are attached (graph/graph.hxx:169-173 `contains_representation`): the CSR always, the CSC when
+  /// the graph was built with one (a run-time property here, a compile-time one in the reference), never a COO.
   template <typename view_t>
   __host__ __device__ __forceinline__ constexpr bool contains_representation() const {
-    return true;
+    if constexpr (detail::is_csc_view<view_t>::value)
+      return t_offsets != nullptr;
+    else if constexpr (detail::is_coo_view<view_t>::value)
+      return false;
+    else
+      return true;
+  }
+  /// Where the graph's arrays live (graph/graph.hxx:180-183).
+  __host__ __device__ __forceinline__ constexpr memory_space_t memory_space() const { return space; }
+  /// Number of attached views (graph/graph.hxx:158-161).
+  __host__ __device__ __forceinline__ std::size_t number_of_graph_representations() const {
+    return t_offsets != nullptr ? 2 : 1;
   }
 
   // --- accessors (graph/csr.hxx:61-178; CSC flavour graph/csc.hxx:42-100) -----------------
@@ -219,6 +240,22 @@ class graph_t {
     v.uid = uid;
     return v;
   }
+  /// The CSR structure without its values, for graphs whose weight_t is not float (the reference's unit tests build
+  /// `graph_t<device, int, int, int>`): the generic advance hands such a graph's typed weights to the user's
+  /// operator itself (operators/advance/advance.hxx), the kernels see an unweighted graph.
+  b200::csr_view_t structure_view() const {
+    static_assert(std::is_integral<vertex_t>::value && sizeof(vertex_t) == 4 &&
+                      std::is_integral<edge_t>::value && sizeof(edge_t) == 4,
+                  "the sm_100a kernels are built for 32-bit vertex_t / edge_t");
+    b200::csr_view_t v;
+    v.n_vertices = static_cast<int>(n_rows);
+    v.n_edges = static_cast<int>(n_nonzeros);
+    v.row_offsets = reinterpret_cast<const int*>(offsets);
+    v.column_indices = reinterpret_cast<const int*>(indices);
+    v.values = nullptr;
+    v.uid = uid;
+    return v;
+  }
   b200::csr_view_t csc_view() const {
     check_kernel_types();
     b200::csr_view_t v;
@@ -295,10 +332,65 @@ auto build(graph_properties_t properties,
   return build<space>(properties, csr, csc);
 }
 
+/// Mean out-degree (graph/graph.hxx:348-355 sums the degrees vertex by vertex; the sum IS the edge count).
 template <typename graph_type>
-double get_average_degree(graph_type const& G) {
+__host__ __device__ double get_average_degree(graph_type const& G) {
   return static_cast<double>(G.get_number_of_edges()) /
          static_cast<double>(G.get_number_of_vertices());
+}
+
+/// Population standard deviation of the out-degrees (graph/graph.hxx:368-378); callable where the graph's
+/// arrays are (host code for a host graph, device code for a device graph), as in the reference.
+template <typename graph_type>
+__host__ __device__ double get_degree_standard_deviation(graph_type const& G) {
+  const double mean = get_average_degree(G);
+  double accum = 0.0;
+  for (typename graph_type::vertex_type v = 0; v < G.get_number_of_vertices(); ++v) {
+    const double d = static_cast<double>(G.get_number_of_neighbors(v)) - mean;
+    accum += d * d;
+  }
+  return sqrt(accum / static_cast<double>(G.get_number_of_vertices()));
+}
+
+namespace detail {
+template <typename graph_type, typename histogram_t>
+__global__ void degree_histogram_kernel(graph_type G, histogram_t* histogram, int bins) {
+  // per-CTA counts in shared memory first: a power-law graph puts most vertices into three or four bins
+  __shared__ unsigned local[72];
+  for (int b = threadIdx.x; b < bins; b += blockDim.x)
+    local[b] = 0;
+  __syncthreads();
+  const long long n = G.get_number_of_vertices();
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const unsigned long long degree =
+        static_cast<unsigned long long>(G.get_number_of_neighbors(static_cast<typename graph_type::vertex_type>(v)));
+    const int bin = degree == 0 ? 0 : 64 - __clzll(degree);  // smallest b with degree < 2^b
+    atomicAdd(&local[bin < bins ? bin : bins - 1], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < bins; b += blockDim.x)
+    if (local[b])
+      atomicAdd(histogram + b, static_cast<histogram_t>(local[b]));
+}
+}  // namespace detail
+
+/**
+ * @brief Log-scale degree histogram of a DEVICE graph (graph/graph.hxx:393-440): `histogram` (device memory,
+ * 8 * sizeof(vertex_t) + 1 counters) is zeroed, then bin b counts the vertices whose degree d satisfies
+ * 2^(b-1) <= d < 2^b (bin 0: degree 0).  One grid-stride kernel with per-CTA shared-memory counts; asynchronous on
+ * `stream` like the reference's Thrust calls.
+ */
+template <typename graph_type, typename histogram_t>
+void build_degree_histogram(graph_type const& G, histogram_t* histogram, cudaStream_t stream = 0) {
+  constexpr int bins = static_cast<int>(sizeof(typename graph_type::vertex_type) * 8 + 1);
+  static_assert(bins <= 72, "histogram bins exceed the kernel's shared-memory table");
+  cudaMemsetAsync(histogram, 0, sizeof(histogram_t) * bins, stream);
+  const long long n = G.get_number_of_vertices();
+  if (n <= 0)
+    return;
+  const int blocks = static_cast<int>(n / 256 + 1 < 1184 ? n / 256 + 1 : 1184);
+  detail::degree_histogram_kernel<<<blocks, 256, 0, stream>>>(G, histogram, bins);
 }
 
 }  // namespace graph

@@ -71,3 +71,26 @@ def test_reference_cmd_tool_compiles_unchanged_and_runs():
     assert rc == 0 and "Gunrock commandline parser test" in out and "--market arg" in out and "--csr arg" in out
     rc, out = run()
     assert rc == 0 and "Usage:" in out
+
+
+def test_reference_unit_tests_compile_unchanged_and_the_host_only_ones_pass():
+    """examples/bin/ref_unittests = the reference's own unit tests (/root/reference/unittests/unittests.hxx: formats,
+    graph, memory, problem, parallel_for, advance merge_path, type limits, launch box, context, device properties,
+    array, .smtx, triangle counting) compiled UNCHANGED against include/ with tests/gtest_shim standing in for
+    googletest.  All 19 are in the binary; the ones that need no device run here."""
+    import os
+    import pytest
+    exe = os.path.join(ROOT, "examples", "bin", "ref_unittests")
+    if not os.path.exists(exe):
+        pytest.skip("examples/bin/ref_unittests not built (needs /root/reference at build time)")
+    listed = subprocess.run([exe, "--gtest_list_tests"], capture_output=True, text=True, timeout=30).stdout.split()
+    assert len(listed) == 19 and {"graph.graph", "operators.prallel_for", "algorithm.tc", "io.smtx",
+                                  "containers.array", "cuda.launch_box_occupancy"} <= set(listed)
+    host_only = ["cuda.device_properties", "cuda.launch_box_fallback", "cuda.launch_box_define",
+                 "operators_advance.merge_path_coordinate_struct", "operators_advance.merge_path_enum_exists"]
+    r = subprocess.run([exe, "--gtest_filter=" + ":".join(host_only)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "5 tests ran, 0 failed" in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]
+    for name in host_only:
+        assert f"[       OK ] {name}" in r.stdout
+    # the fallback entry is what SM_TARGET = 100 selects in the reference's box (it lists sm_35 ... sm_86 only)
+    assert "block_dimensions:    16, 1, 1" in r.stdout and "grid_dimensions:     2, 1, 1" in r.stdout
